@@ -1,0 +1,150 @@
+/* beam_b200.h -- C ABI of the B200-native (sm_100a) acceleration-structure build + closest-hit trace path.
+ *
+ * This is the drop-in boundary for the hot path of d1kkop/RaytracerCuda ("Beam").  In the reference the seam is the set
+ * of extern "C" launchers defined in Raytracer/BuildTree.cu / Hash.cu / RTClear.cu and re-declared by hand at the top of
+ * each host .cpp (SceneTree.cpp:11-35, SceneHash.cpp:10-24, Camera.cpp:16-19).  Part 1 below exports those symbols with
+ * the same names, argument order and x86-64 SysV calling convention (glm::vec3 by value == struct of 3 floats by value;
+ * `const glm::vec3&` / `const glm::mat3&` == pointer), so the reference's own SceneTree.cpp / Camera.cpp link against
+ * libbeam_b200.so unchanged.  Part 2 is the explicit, handle-based form the same kernels are reached through when the
+ * caller wants hit records, ray batches, build statistics or streams -- things the reference ABI cannot express.
+ *
+ * All pointers named d_* (and every pointer in Part 1) are DEVICE pointers.  No function falls back to the CPU: if no
+ * CUDA device is usable the calls fail with BM_ERROR_CUDA (Part 2) or abort with a message (Part 1, which like the
+ * reference returns void, CudaComon.cuh:59-68).
+ */
+#ifndef BEAM_B200_H
+#define BEAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float x, y, z; } bmVec3;          /* layout == glm::vec3 */
+typedef struct { float m[9]; } bmMat3;             /* layout == glm::mat3, column-major: m[3*col + row] */
+
+/* Beam.h:8-16 error codes (returned as uint32 by the host-class mirror), plus codes for Part 2 */
+enum {
+    BM_OK = 0,                      /* ERROR_ALL_FINE */
+    BM_ERROR_NO_VERTICES = 1,
+    BM_ERROR_INVALID_PARAMETER = 2,
+    BM_ERROR_GPU_ALLOC_FAIL = 3,
+    BM_ERROR_INVALID_FORMAT = 4,
+    BM_ERROR_RT_CAM_MISMATCH = 5,
+    BM_ERROR_UNLOCK_FIRST = 6,
+    BM_ERROR_LOCK_FIRST = 7,
+    BM_ERROR_NO_RENDER_TARGET = 8,
+    BM_ERROR_CUDA = 100,            /* a CUDA runtime call or kernel launch failed; see bmLastErrorString() */
+    BM_ERROR_UNSUPPORTED_WORLD = 101, /* world box / leaf size does not give a uniform leaf depth <= 32 */
+    BM_ERROR_NOT_BUILT = 102,
+    BM_ERROR_CAPACITY = 103
+};
+
+/* SharedTypes.h:10-18 StaticMeshData (136 bytes, device pointers). Same layout: bmMarch reads normals (slot 1) through it. */
+#define BM_VERTEX_DATA_COUNT 10
+typedef struct {
+    float*    m_vertexData[BM_VERTEX_DATA_COUNT];
+    uint32_t  m_vertexDataSizes[BM_VERTEX_DATA_COUNT];
+    uint32_t* m_indices;
+    uint32_t  m_numVertices;
+    uint32_t  m_numIndices;
+} bmStaticMeshData;
+
+/* Trace2.cu:45-48 bmRay {o, d}: 24 bytes.  Explicit ray batches use this record. */
+typedef struct { float o[3]; float d[3]; } bmRay;
+
+/* Hit record written by bmTraceRays / bmTraceCamera: 16 bytes.
+ * Replaces bmRayFaceHitResult {bmFace*, dist, u, v} (SharedTypes.h:31-35): the face pointer becomes a global triangle id
+ * (mesh base + face index, see bmTreeMeshBases); miss = { FLT_MAX, 0, 0, 0xFFFFFFFF }. */
+typedef struct { float t, u, v; uint32_t tri; } bmHit;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Part 1 -- the reference's own entry points (same symbols).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* BuildTree.cu:120-148. `rootNode` identifies the tree (one bmGetNodeSize() buffer per SceneTree, SceneTree.cpp:52).
+ * The store / pool pointers are accepted and ignored: node, leaf and triangle storage is owned by the library because
+ * the layout changed (sorted leaf ranges + 64-byte nodes instead of pointer-linked pools). Clears the staged mesh list. */
+void bmResetScene(void* rootNode, void* faceStore, void* faceGroupStore, void* nodeStore,
+                  void* faces, void* facePtrs, void* nodes, uint32_t maxFaces, uint32_t maxFacePtrs, uint32_t maxNodes);
+
+/* BuildTree.cu:259-287. Stages mesh `meshIdx` (device positions vec3[], device indices u32[numIndices]) for the tree
+ * identified by treeRootNode, with world box [bMin,bMax].  The sort-based builder needs every mesh before it can emit
+ * the hierarchy, so the build itself runs in bmBuildTree, or lazily inside the first bmMarch after an insert. */
+void bmInsertMeshInTree(const bmVec3* vertices, const uint32_t* indices, uint32_t numIndices, uint32_t meshIdx,
+                        bmVec3 bMin, bmVec3 bMax, void* treeRootNode, void* faceStore, void* faceGroupStore,
+                        void* nodeStore, void* material);
+
+/* BuildTree.cu:502-520. One primary ray per pixel: dir = orient * initialRays[i] from eye; buffer[i] = shaded pixel
+ * ((u32)|n.z*255| << 16 on a hit, 255<<8 on a miss, BuildTree.cu:486-496).  `pitch` is ignored as in the reference. */
+void bmMarch(const void* root, const bmVec3* bMin, const bmVec3* bMax, const bmVec3* initialRays,
+             uint32_t* buffer, uint32_t pitch, uint32_t width, uint32_t height,
+             const bmVec3* eye, const bmMat3* orient, const bmStaticMeshData* meshData);
+
+/* BuildTree.cu:546-555. Kept so SceneTree.cpp:48-59 can size its (now unused) pools. Values equal the reference's. */
+uint32_t bmGetFaceSize(void);
+uint32_t bmGetFacePtrSize(void);
+uint32_t bmGetMaterialSize(void);
+uint32_t bmGetNodeSize(void);
+uint32_t bmGetFaceStoreSize(void);
+uint32_t bmGetNodeStoreSize(void);
+uint32_t bmGetFaceGroupStoreSize(void);
+
+/* RTClear.cu:19-31 */
+void bmClear(uint32_t* buffer, uint32_t pitch, uint32_t width, uint32_t height, uint32_t clearValue);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Part 2 -- explicit handle-based entry points (same kernels).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct bmTree bmTree;
+
+/* trace modes */
+enum {
+    BM_TRACE_REFERENCE = 0,  /* the reference's semantics (BuildTree.cu:394-484): front-to-back by split plane, stop at the
+                                first leaf cell that produced a hit, strict-minimum d of any sign inside that leaf, at most
+                                256 faces per leaf.  This is the parity mode. */
+    BM_TRACE_CLOSEST = 1     /* exhaustive closest hit with t >= 0 (ordered traversal with t-range culling) */
+};
+
+const char* bmLastErrorString(void);
+
+/* World box, leaf size and depth cap default to SceneTree.cpp:43-45 and BuildTree.cuh:14-18 when null / 0. */
+int  bmTreeCreate(bmTree** out, const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth);
+void bmTreeDestroy(bmTree* tree);
+int  bmTreeSetStream(bmTree* tree, void* cudaStream);          /* cudaStream_t; default 0 */
+int  bmTreeReset(bmTree* tree);                                /* forget staged meshes (bmResetScene) */
+int  bmTreeAddMesh(bmTree* tree, const float* d_positions, const uint32_t* d_indices, uint32_t numIndices, uint32_t meshIdx);
+/* keys -> sort -> leaves -> radix tree -> refit -> 64-byte nodes. Asynchronous on the tree's stream except for two
+ * 8-byte read-backs (pair and leaf counts) that size the later stages. */
+int  bmTreeBuild(bmTree* tree);
+int  bmBuildTree(void* treeRootNode);                          /* same, for a tree made through Part 1 */
+bmTree* bmTreeFromRoot(const void* treeRootNode);              /* Part 1 handle -> Part 2 handle (NULL if unknown) */
+
+/* stats[0..7] = triangles, (leaf,triangle) pairs, leaves, internal nodes, leaf depth (code bits), largest leaf,
+ *               leaves over 256 faces, meshes */
+int  bmTreeStats(const bmTree* tree, uint64_t* stats8);
+/* Canonical outputs for parity checks (device -> caller-provided DEVICE buffers, sized from bmTreeStats):
+ *   pairs : code[P], tri[P] sorted by (code, global triangle id)        -- "keys" and "sorted primitive order"
+ *   nodes : prefixLen[N], prefix[N] of the N = leaves-1 internal nodes   -- "topology"
+ *   child boxes: 12 floats per internal node (lo0,hi0,lo1,hi1)           -- "node bounds" */
+int  bmTreeCopyPairs(const bmTree* tree, uint32_t* d_code, uint32_t* d_tri);
+int  bmTreeCopyTopology(const bmTree* tree, uint32_t* d_prefixLen, uint32_t* d_prefix, uint32_t* d_child0, uint32_t* d_child1);
+int  bmTreeCopyChildBoxes(const bmTree* tree, float* d_boxes12);
+int  bmTreeMeshBases(const bmTree* tree, uint32_t* h_bases, uint32_t capacity);   /* host array: first global id of each mesh */
+
+/* Explicit ray batch -> hit records. d_counters (nullable) receives {node visits, triangle tests} as two uint64. */
+int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters);
+/* Camera rays (dir = orient * initialRays[i] from eye), hit records and/or shaded pixels (either may be null). */
+int  bmTraceCamera(bmTree* tree, const float* d_initialRays3, uint64_t numRays, const float* eye3, const float* orient9,
+                   int mode, bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters);
+
+/* Spatial-hash key functions of Hash.cu:17-64 evaluated on the device (bit-exact targets):
+ * out[i] = bmHash3(make_uint3(bmMap(x), bmMap(y), bmMap(z))) and the three bmMap cell coordinates. */
+int  bmHashKeys(const float* d_points3, uint64_t n, uint32_t* d_hash, int32_t* d_cells3, void* cudaStream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEAM_B200_H */

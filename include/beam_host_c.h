@@ -1,0 +1,38 @@
+/* beam_host_c.h -- flat C view of the host classes in beam_host.hpp (Beam::IScene / IMesh / ICamera / IRenderTarget,
+ * i.e. the reference's public interface Raytracer/Beam.h:32-72), for callers without a C++ compiler (ctypes, cgo, JNI ...).
+ * Handles are opaque; every data pointer here is a HOST pointer -- uploads and read-backs happen inside the calls, exactly
+ * where the reference does them (Mesh.cpp:30-54, Camera.cpp:43-72).  Return values are the Beam.h u32 error codes. */
+#ifndef BEAM_HOST_C_H
+#define BEAM_HOST_C_H
+#include "beam_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+void*    beamSceneCreate(void);                                   /* IScene::create(); NULL when no CUDA device is usable */
+void     beamSceneDestroy(void* scene);
+void     beamSceneAddMesh(void* scene, void* mesh);               /* IScene::addMesh */
+void     beamSceneRemoveMesh(void* scene, void* mesh);            /* IScene::removeMesh */
+void     beamSceneUpdateGPUScene(void* scene);                    /* IScene::updateGPUScene: builds the tree */
+void*    beamSceneTree(void* scene);                              /* the scene's bmTree* (NULL before the first build) */
+void*    beamMeshCreate(void);                                    /* IMesh::create() */
+void     beamMeshDestroy(void* mesh);
+uint32_t beamMeshSetVertexData(void* mesh, const float* hostData, uint32_t numVertices, uint32_t numComponents, uint32_t slotId, int asyncCopy);
+uint32_t beamMeshSetIndices(void* mesh, const uint32_t* hostIndices, uint32_t numIndices, int asyncCopy);
+void*    beamCameraCreate(void);                                  /* ICamera::create() */
+void     beamCameraDestroy(void* camera);
+uint32_t beamCameraSetInitialRays(void* camera, uint32_t width, uint32_t height, float left, float right, float top, float bottom, float zoom);
+uint32_t beamCameraCopyInitialRays(void* camera, float* host3);   /* the direction table, width*height*3 floats */
+uint32_t beamCameraClear(void* camera, uint32_t value);
+uint32_t beamCameraTraceScene(void* camera, const float* eye3, const float* orient3x3, void* scene);
+uint32_t beamCameraTraceSceneHits(void* camera, const float* eye3, const float* orient3x3, void* scene, bmHit* hostHits);
+void*    beamRenderTargetCreateHeadless(uint32_t width, uint32_t height, uint32_t pitch);
+void     beamRenderTargetDestroy(void* rt);
+uint32_t beamRenderTargetLock(void* rt);
+uint32_t beamRenderTargetUnlock(void* rt);
+void*    beamRenderTargetBuffer(void* rt);                        /* device pointer while locked */
+uint32_t beamRenderTargetReadPixels(void* rt, uint32_t* hostPixels);
+int      beamDeviceSynchronize(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,112 @@
+"""ctypes binding of include/beam_b200.h.  There is no fallback: a missing or unloadable library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbeam_b200.so")
+
+BM_OK = 0
+BM_TRACE_REFERENCE = 0
+BM_TRACE_CLOSEST = 1
+ERROR_NAMES = {0: "ERROR_ALL_FINE", 1: "ERROR_NO_VERTICES", 2: "ERROR_INVALID_PARAMETER", 3: "ERROR_GPU_ALLOC_FAIL", 4: "ERROR_INVALID_FORMAT",
+               5: "ERROR_RT_CAM_MISMATCH", 6: "ERROR_UNLOCK_FIRST", 7: "ERROR_LOCK_FIRST", 8: "ERROR_NO_RENDER_TARGET",
+               100: "BM_ERROR_CUDA", 101: "BM_ERROR_UNSUPPORTED_WORLD", 102: "BM_ERROR_NOT_BUILT", 103: "BM_ERROR_CAPACITY"}
+
+# every symbol include/beam_b200.h declares (tests/test_abi.py checks the library exports each one)
+ABI_SYMBOLS = [
+    "bmResetScene", "bmInsertMeshInTree", "bmMarch", "bmGetFaceSize", "bmGetFacePtrSize", "bmGetMaterialSize", "bmGetNodeSize",
+    "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
+    "bmLastErrorString", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases",
+    "bmTraceRays", "bmTraceCamera", "bmHashKeys",
+    # include/beam_host_c.h
+    "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
+    "beamMeshCreate", "beamMeshDestroy", "beamMeshSetVertexData", "beamMeshSetIndices",
+    "beamCameraCreate", "beamCameraDestroy", "beamCameraSetInitialRays", "beamCameraCopyInitialRays", "beamCameraClear",
+    "beamCameraTraceScene", "beamCameraTraceSceneHits",
+    "beamRenderTargetCreateHeadless", "beamRenderTargetDestroy", "beamRenderTargetLock", "beamRenderTargetUnlock", "beamRenderTargetBuffer",
+    "beamRenderTargetReadPixels", "beamDeviceSynchronize",
+]
+
+
+class BeamError(RuntimeError):
+    pass
+
+
+class bmVec3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class bmMat3(C.Structure):
+    _fields_ = [("m", C.c_float * 9)]
+
+
+class bmStaticMeshData(C.Structure):
+    _fields_ = [("m_vertexData", C.c_void_p * 10), ("m_vertexDataSizes", C.c_uint32 * 10), ("m_indices", C.c_void_p),
+                ("m_numVertices", C.c_uint32), ("m_numIndices", C.c_uint32)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BeamError(f"{LIB_PATH} is missing: build it with `python -m raytracercuda_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.bmLastErrorString.restype = C.c_char_p
+    L.bmTreeCreate.argtypes = [C.POINTER(vp), vp, vp, C.c_float, u32]
+    L.bmTreeDestroy.argtypes = [vp]; L.bmTreeDestroy.restype = None
+    L.bmTreeSetStream.argtypes = [vp, vp]
+    L.bmTreeReset.argtypes = [vp]
+    L.bmTreeAddMesh.argtypes = [vp, vp, vp, u32, u32]
+    L.bmTreeBuild.argtypes = [vp]
+    L.bmBuildTree.argtypes = [vp]
+    L.bmTreeFromRoot.argtypes = [vp]; L.bmTreeFromRoot.restype = vp
+    L.bmTreeStats.argtypes = [vp, C.POINTER(u64)]
+    L.bmTreeCopyPairs.argtypes = [vp, vp, vp]
+    L.bmTreeCopyTopology.argtypes = [vp, vp, vp, vp, vp]
+    L.bmTreeCopyChildBoxes.argtypes = [vp, vp]
+    L.bmTreeMeshBases.argtypes = [vp, C.POINTER(u32), u32]
+    L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]
+    L.bmTraceCamera.argtypes = [vp, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
+    L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]
+    L.bmResetScene.argtypes = [vp] * 7 + [u32] * 3; L.bmResetScene.restype = None
+    L.bmInsertMeshInTree.argtypes = [vp, vp, u32, u32, bmVec3, bmVec3, vp, vp, vp, vp, vp]; L.bmInsertMeshInTree.restype = None
+    L.bmMarch.argtypes = [vp, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, u32, u32, u32, C.POINTER(bmVec3), C.POINTER(bmMat3), vp]
+    L.bmMarch.restype = None
+    L.bmClear.argtypes = [vp, u32, u32, u32, u32]; L.bmClear.restype = None
+    for n in ("bmGetFaceSize", "bmGetFacePtrSize", "bmGetMaterialSize", "bmGetNodeSize", "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize"):
+        getattr(L, n).restype = u32
+    f = C.c_float
+    for n in ("beamSceneCreate", "beamMeshCreate", "beamCameraCreate", "beamSceneTree", "beamRenderTargetBuffer"):
+        getattr(L, n).restype = vp
+    L.beamSceneTree.argtypes = [vp]; L.beamRenderTargetBuffer.argtypes = [vp]
+    for n in ("beamSceneDestroy", "beamMeshDestroy", "beamCameraDestroy", "beamRenderTargetDestroy", "beamSceneUpdateGPUScene"):
+        getattr(L, n).argtypes = [vp]; getattr(L, n).restype = None
+    L.beamSceneAddMesh.argtypes = [vp, vp]; L.beamSceneAddMesh.restype = None
+    L.beamSceneRemoveMesh.argtypes = [vp, vp]; L.beamSceneRemoveMesh.restype = None
+    L.beamMeshSetVertexData.argtypes = [vp, vp, u32, u32, u32, i32]; L.beamMeshSetVertexData.restype = u32
+    L.beamMeshSetIndices.argtypes = [vp, vp, u32, i32]; L.beamMeshSetIndices.restype = u32
+    L.beamCameraSetInitialRays.argtypes = [vp, u32, u32, f, f, f, f, f]; L.beamCameraSetInitialRays.restype = u32
+    L.beamCameraCopyInitialRays.argtypes = [vp, vp]; L.beamCameraCopyInitialRays.restype = u32
+    L.beamCameraClear.argtypes = [vp, u32]; L.beamCameraClear.restype = u32
+    L.beamCameraTraceScene.argtypes = [vp, vp, vp, vp]; L.beamCameraTraceScene.restype = u32
+    L.beamCameraTraceSceneHits.argtypes = [vp, vp, vp, vp, vp]; L.beamCameraTraceSceneHits.restype = u32
+    L.beamRenderTargetCreateHeadless.argtypes = [u32, u32, u32]; L.beamRenderTargetCreateHeadless.restype = vp
+    L.beamRenderTargetLock.argtypes = [vp]; L.beamRenderTargetLock.restype = u32
+    L.beamRenderTargetUnlock.argtypes = [vp]; L.beamRenderTargetUnlock.restype = u32
+    L.beamRenderTargetReadPixels.argtypes = [vp, vp]; L.beamRenderTargetReadPixels.restype = u32
+    _lib = L
+    return L
+
+
+def check(code: int, what: str = "") -> None:
+    if code != BM_OK:
+        msg = load().bmLastErrorString().decode(errors="replace")
+        raise BeamError(f"{what or 'beam_b200'} failed: {ERROR_NAMES.get(code, code)} {msg}")

@@ -1,0 +1,76 @@
+// bm_device.cuh -- device-side views, launch helpers and the internal interfaces between the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include "bm_math.cuh"
+#include "../../include/beam_b200.h"
+
+namespace bm
+{
+// ---- error plumbing -------------------------------------------------------------------------------------------------
+void set_error(const std::string& s);
+const char* last_error();
+#define BM_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ::bm::set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); return BM_ERROR_CUDA; } } while (0)
+#define BM_TRY(expr) do { int r_ = (expr); if (r_ != BM_OK) return r_; } while (0)
+
+inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+int sm_count();
+
+// ---- HBM layout of a finished tree (all index-based, no absolute pointers inside the arrays) --------------------------
+//
+//  nodes  : N = L-1 internal nodes of the binary radix tree over the L distinct leaf codes, 64 bytes each, 64-byte aligned:
+//             float4 q0 = (lo0.x lo0.y lo0.z hi0.x)     child 0 = lower half ("left"), tight box = union of whole triangles
+//             float4 q1 = (hi0.y hi0.z lo1.x lo1.y)
+//             float4 q2 = (lo1.z hi1.x hi1.y hi1.z)
+//             uint4  q3 = (child0, child1, prefix, prefixLen)   child bit 31 = leaf; prefix = top prefixLen bits of the codes
+//           The node IS the reference kd node at depth prefixLen with two children; its cell box follows from
+//           (prefix, prefixLen) through the grid tables, its split axis is prefixLen % 3.
+//  leaves : uint4 (code, first pair, pair count, 0), sorted by code.
+//  ltris  : one 48-byte record per (leaf, triangle) pair in sorted order, so a leaf's triangles are one contiguous run:
+//             float4 (v0.xyz, global triangle id) (e1.xyz = v1-v0, mesh index) (e2.xyz = v2-v0, face index in mesh)
+struct TreeView
+{
+    Grid grid;
+    const float4* nodes;
+    const uint4* leaves;
+    const float4* ltris;
+    u32 numLeaves;
+    u32 rootRef;          // bit 31 = leaf
+    u32 maxLeafFaces;     // MAX_FACES_PER_BOX (BuildTree.cuh:17): reference mode tests at most this many faces per leaf
+};
+static const u32 LEAF_BIT = 0x80000000u;
+
+// ---- scan.cu --------------------------------------------------------------------------------------------------------
+size_t scan_temp_bytes(size_t n);
+// out[i] = sum(in[0..i-1]); *d_total (device, nullable) = sum of all. in == out allowed. temp: scan_temp_bytes(n) bytes.
+int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s);
+
+// ---- sort.cu --------------------------------------------------------------------------------------------------------
+size_t sort_temp_bytes(size_t n);
+// Stable LSD radix sort of (key, value) pairs on the low `bits` bits of the key. Input in buffer A; A and B ping-pong;
+// *resultInB tells which pair of buffers holds the sorted result (B after an odd number of 8-bit passes).
+int radix_sort_pairs(u32* d_keysA, u32* d_valsA, u32* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB);
+
+// ---- keygen.cu ------------------------------------------------------------------------------------------------------
+int gather_mesh(const float* d_pos, const u32* d_idx, u32 numTris, u32 meshIdx, u32 base, float4* d_soup, cudaStream_t s);
+int count_pairs(const Grid& g, const float4* d_soup, u32 numTris, u32* d_counts, cudaStream_t s);
+int emit_pairs(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, u32* d_keys, u32* d_vals, cudaStream_t s);
+
+// ---- hierarchy.cu ---------------------------------------------------------------------------------------------------
+int mark_heads(const u32* d_keys, size_t n, u32* d_flags, cudaStream_t s);
+int write_leaves(const u32* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, uint4* d_leaves, cudaStream_t s);
+int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_ltris, cudaStream_t s);
+int leaf_bounds(const uint4* d_leaves, u32 numLeaves, const float4* d_ltris, float* d_leafBox6, float pad, u32* d_stats, cudaStream_t s);
+int emit_hierarchy(const uint4* d_leaves, u32 numLeaves, int D, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s);
+int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit, float4* d_nodes, cudaStream_t s);
+
+// ---- trace.cu -------------------------------------------------------------------------------------------------------
+struct CameraIn { const float* initialRays; float eye[3]; float orient[9]; };
+int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* d_hits, u64* d_counters, cudaStream_t s);
+int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
+                 u64* d_counters, cudaStream_t s);
+int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
+int hash_keys(const float* d_points3, u64 n, u32* d_hash, i32* d_cells3, cudaStream_t s);
+} // namespace bm

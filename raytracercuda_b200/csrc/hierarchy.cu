@@ -1,0 +1,202 @@
+// hierarchy.cu -- from sorted (code, triangle) pairs to the traversable tree:
+//   leaf segmentation (distinct codes)  ->  Karras-style binary radix tree over the distinct codes, one thread per internal
+//   node  ->  bottom-up refit of tight boxes with one atomic counter per node  ->  64-byte nodes.
+//
+// Topology equivalence with the reference: the reference kd node at depth d with TWO children is
+// exactly the radix-tree node whose keys share a d-bit prefix and then differ; single-child chain nodes of the reference
+// have no counterpart because they take no decision.  emit_hierarchy stores (prefix, prefixLen) so that the node's cell
+// box, split axis (prefixLen % 3) and split plane are the reference's.
+#include "bm_device.cuh"
+
+namespace bm
+{
+namespace
+{
+__global__ void mark_heads_kernel(const u32* __restrict__ keys, size_t n, u32* __restrict__ flags)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void write_leaves_kernel(const u32* __restrict__ keys, const u32* __restrict__ flags, const u32* __restrict__ leafIdx, size_t n,
+                                    u32 numLeaves, uint4* __restrict__ leaves)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!flags[i]) return;
+    // run length: scan forward to the next head (leaves are short: <= a few hundred pairs)
+    size_t j = i + 1;
+    while (j < n && !flags[j]) ++j;
+    leaves[leafIdx[i]] = make_uint4(keys[i], (u32)i, (u32)(j - i), 0u);
+}
+
+__global__ void pack_leaf_tris_kernel(const float4* __restrict__ soup, const u32* __restrict__ vals, size_t n, float4* __restrict__ ltris)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* p = soup + 3 * (size_t)vals[i];
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    float4* o = ltris + 3 * i;
+    // e1 = v1 - v0, e2 = v2 - v0: the first two operations of bmTriIntersect (CudaComon.cuh:122-123)
+    o[0] = a;
+    o[1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, b.w);
+    o[2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, c.w);
+}
+
+// tight box of a leaf = union of its WHOLE triangles (not clipped to the cell: reference mode must still find a hit that lies
+// outside the cell, BuildTree.cu:413-431).  stats[0] = max leaf size, stats[1] = leaves above 256 faces.
+__global__ void leaf_bounds_kernel(const uint4* __restrict__ leaves, u32 numLeaves, const float4* __restrict__ ltris, float* __restrict__ box6,
+                                   float pad, u32* stats)
+{
+    u32 l = blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 lf = l < numLeaves ? leaves[l] : make_uint4(0, 0, 0, 0);
+    // leaf-size statistics: one atomic per warp, and only while the running maximum still grows
+    u32 wmax = __reduce_max_sync(0xFFFFFFFFu, lf.z);
+    u32 wover = __popc(__ballot_sync(0xFFFFFFFFu, lf.z > 256u));
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (wmax > __ldcg(&stats[0])) atomicMax(&stats[0], wmax);
+        if (wover) atomicAdd(&stats[1], wover);
+    }
+    if (l >= numLeaves) return;
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (u32 i = 0; i < lf.z; i++)
+    {
+        const float4* p = ltris + 3 * (size_t)(lf.y + i);
+        float4 a = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+        // v1 = v0 + e1 may differ from the stored vertex by one rounding, and a hit the triangle test accepts numerically may
+        // lie a few ulps of the ray length outside the exact box: `pad` (world extent * 2^-20, << cell size) absorbs both
+        float v[3][3] = { { a.x, a.y, a.z }, { a.x + e1.x, a.y + e1.y, a.z + e1.z }, { a.x + e2.x, a.y + e2.y, a.z + e2.z } };
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+            {
+                float x = v[k][q];
+                lo[q] = fminf(lo[q], x - pad); hi[q] = fmaxf(hi[q], x + pad);
+            }
+    }
+    float* o = box6 + 6 * (size_t)l;
+    o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = hi[0]; o[4] = hi[1]; o[5] = hi[2];
+}
+
+__device__ __forceinline__ int delta(const uint4* __restrict__ leaves, int i, int j, int n)
+{
+    if (j < 0 || j >= n) return -1;
+    return __clz(__ldg(&leaves[i].x) ^ __ldg(&leaves[j].x));       // codes are distinct, so never 32
+}
+
+// Karras 2012, one thread per internal node i in [0, L-1)
+__global__ void karras_kernel(const uint4* __restrict__ leaves, u32 numLeaves, int D, float4* __restrict__ nodes,
+                              u32* __restrict__ parentOfNode, u32* __restrict__ parentOfLeaf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = (int)numLeaves;
+    if (i >= n - 1) return;
+    int d = (delta(leaves, i, i + 1, n) - delta(leaves, i, i - 1, n)) >= 0 ? 1 : -1;
+    int dmin = delta(leaves, i, i - d, n);
+    int lmax = 2;
+    while (delta(leaves, i, i + lmax * d, n) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(leaves, i, i + (l + t) * d, n) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(leaves, i, j, n);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1)
+    {
+        if (delta(leaves, i, i + (s + t) * d, n) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    u32 c0 = (gamma == first) ? ((u32)gamma | LEAF_BIT) : (u32)gamma;
+    u32 c1 = (gamma + 1 == last) ? ((u32)(gamma + 1) | LEAF_BIT) : (u32)(gamma + 1);
+    if (c0 & LEAF_BIT) parentOfLeaf[gamma] = (u32)i; else parentOfNode[gamma] = (u32)i;
+    if (c1 & LEAF_BIT) parentOfLeaf[gamma + 1] = (u32)i; else parentOfNode[gamma + 1] = (u32)i;
+    if (i == 0) parentOfNode[0] = 0xFFFFFFFFu;
+    int plen = dnode - (32 - D);                     // common prefix length inside the D-bit code
+    u32 prefix = plen > 0 ? (leaves[i].x >> (D - plen)) : 0u;
+    nodes[4 * (size_t)i + 3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
+}
+
+__device__ __forceinline__ void load_box(const float* p, float b[6])
+{
+#pragma unroll
+    for (int k = 0; k < 6; k++) b[k] = __ldcg(p + k);   // written by another thread of this launch: bypass L1
+}
+
+// bottom-up: thread per leaf climbs; the second thread to reach a node has both child boxes available
+__global__ void refit_kernel(u32 numLeaves, const float* __restrict__ leafBox, float* nodeBox, const u32* __restrict__ parentOfNode,
+                             const u32* __restrict__ parentOfLeaf, u32* visit, float4* nodes)
+{
+    u32 l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= numLeaves) return;
+    u32 cur = parentOfLeaf[l];
+    while (cur != 0xFFFFFFFFu)
+    {
+        __threadfence();
+        if (atomicAdd(&visit[cur], 1u) == 0u) return;
+        __threadfence();
+        float4 q3 = __ldcg(&nodes[4 * (size_t)cur + 3]);
+        u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
+        float b0[6], b1[6];
+        load_box((c0 & LEAF_BIT) ? leafBox + 6 * (size_t)(c0 & ~LEAF_BIT) : nodeBox + 6 * (size_t)c0, b0);
+        load_box((c1 & LEAF_BIT) ? leafBox + 6 * (size_t)(c1 & ~LEAF_BIT) : nodeBox + 6 * (size_t)c1, b1);
+        nodes[4 * (size_t)cur + 0] = make_float4(b0[0], b0[1], b0[2], b0[3]);
+        nodes[4 * (size_t)cur + 1] = make_float4(b0[4], b0[5], b1[0], b1[1]);
+        nodes[4 * (size_t)cur + 2] = make_float4(b1[2], b1[3], b1[4], b1[5]);
+        float* o = nodeBox + 6 * (size_t)cur;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { __stcg(o + k, fminf(b0[k], b1[k])); __stcg(o + 3 + k, fmaxf(b0[3 + k], b1[3 + k])); }
+        cur = parentOfNode[cur];
+    }
+}
+} // namespace
+
+int mark_heads(const u32* d_keys, size_t n, u32* d_flags, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    mark_heads_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, n, d_flags);
+    BM_CUDA(cudaGetLastError());
+    return BM_OK;
+}
+int write_leaves(const u32* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, uint4* d_leaves, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    write_leaves_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, d_flags, d_leafIdx, n, numLeaves, d_leaves);
+    BM_CUDA(cudaGetLastError());
+    return BM_OK;
+}
+int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_ltris, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    pack_leaf_tris_kernel<<<div_up(n, 256), 256, 0, s>>>(d_soup, d_vals, n, d_ltris);
+    BM_CUDA(cudaGetLastError());
+    return BM_OK;
+}
+int leaf_bounds(const uint4* d_leaves, u32 numLeaves, const float4* d_ltris, float* d_leafBox6, float pad, u32* d_stats, cudaStream_t s)
+{
+    if (!numLeaves) return BM_OK;
+    leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_ltris, d_leafBox6, pad, d_stats);
+    BM_CUDA(cudaGetLastError());
+    return BM_OK;
+}
+int emit_hierarchy(const uint4* d_leaves, u32 numLeaves, int D, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s)
+{
+    if (numLeaves < 2) return BM_OK;
+    karras_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(d_leaves, numLeaves, D, d_nodes, d_parentOfNode, d_parentOfLeaf);
+    BM_CUDA(cudaGetLastError());
+    return BM_OK;
+}
+int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit,
+          float4* d_nodes, cudaStream_t s)
+{
+    if (numLeaves < 2) return BM_OK;
+    BM_CUDA(cudaMemsetAsync(d_visit, 0, (size_t)(numLeaves - 1) * 4, s));
+    refit_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(numLeaves, d_leafBox6, d_nodeBox6, d_parentOfNode, d_parentOfLeaf, d_visit, d_nodes);
+    BM_CUDA(cudaGetLastError());
+    return BM_OK;
+}
+} // namespace bm

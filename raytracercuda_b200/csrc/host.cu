@@ -1,0 +1,270 @@
+// host.cu -- host classes behind include/beam_host.hpp.  They own device memory and call the extern "C" launchers of
+// include/beam_b200.h Part 1 exactly where the reference's host classes call theirs:
+//   SceneTree::updateGPUScene -> bmResetScene, bmInsertMeshInTree per mesh (SceneTree.cpp:70-107) [+ bmBuildTree]
+//   SceneTree::march          -> bmMarch (SceneTree.cpp:109-127)
+//   Camera::clear             -> bmClear (Camera.cpp:74-83)
+// plus a flat C view of the classes (beam*) so tests and bench.py can drive them through ctypes with HOST buffers.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "bm_device.cuh"
+#include "../../include/beam_host.hpp"
+
+namespace Beam
+{
+// RAII device allocation (DeviceBuffer.h/.cpp with size_t sizes)
+class DeviceBuffer
+{
+public:
+    explicit DeviceBuffer(size_t size) : m_size(size) { if (cudaMalloc(&m_dev, size ? size : 1) != cudaSuccess) { cudaGetLastError(); m_dev = nullptr; } }
+    ~DeviceBuffer() { if (m_dev) cudaFree(m_dev); }
+    bool ok() const { return m_dev != nullptr; }
+    void copyFrom(const void* host, bool wait)
+    {
+        if (wait) cudaMemcpy(m_dev, host, m_size, cudaMemcpyHostToDevice);
+        else cudaMemcpyAsync(m_dev, host, m_size, cudaMemcpyHostToDevice);
+    }
+    void copyTo(void* host, bool wait) const
+    {
+        if (wait) cudaMemcpy(host, m_dev, m_size, cudaMemcpyDeviceToHost);
+        else cudaMemcpyAsync(host, m_dev, m_size, cudaMemcpyDeviceToHost);
+    }
+    template <typename T> T* ptr() const { return reinterpret_cast<T*>(m_dev); }
+    size_t size() const { return m_size; }
+private:
+    void* m_dev = nullptr; size_t m_size;
+};
+
+class RenderTarget : public IRenderTarget
+{
+public:
+    RenderTarget(u32 w, u32 h, u32 pitch) : m_pitch(pitch), m_width(w), m_height(h), m_store((size_t)pitch * h) {}
+    ~RenderTarget() { if (m_locked) unlock(); }
+    void* buffer() const override { return m_locked ? m_store.ptr<void>() : nullptr; }
+    u32 pitch() const override { return m_pitch; }
+    u32 width() const override { return m_width; }
+    u32 height() const override { return m_height; }
+    u32 lock() override { if (m_locked) return ERROR_UNLOCK_FIRST; m_locked = true; s_current = this; return ERROR_ALL_FINE; }
+    u32 unlock() override { if (!m_locked) return ERROR_LOCK_FIRST; m_locked = false; if (s_current == this) s_current = nullptr; return ERROR_ALL_FINE; }
+    u32 readPixels(u32* host) const override
+    {
+        if (!host) return ERROR_INVALID_PARAMETER;
+        // the trace kernels write row-major without pitch, like bmMarchKernel (BuildTree.cu:489-495 indexes buffer[i])
+        if (cudaMemcpy(host, m_store.ptr<void>(), (size_t)m_width * m_height * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return BM_ERROR_CUDA;
+        return ERROR_ALL_FINE;
+    }
+    bool ok() const { return m_store.ok(); }
+    static IRenderTarget* get() { return s_current; }
+private:
+    u32 m_pitch, m_width, m_height; bool m_locked = false; DeviceBuffer m_store;
+    static IRenderTarget* s_current;
+};
+IRenderTarget* RenderTarget::s_current = nullptr;
+
+sptr<IRenderTarget> IRenderTarget::createHeadless(u32 width, u32 height, u32 pitch)
+{
+    if (width == 0 || height == 0 || pitch < width * 4) return nullptr;        // argument rule of RenderTarget.cpp:19
+    auto rt = std::make_shared<RenderTarget>(width, height, pitch);
+    if (!rt->ok()) return nullptr;
+    return rt;
+}
+
+class Scene;
+class Mesh : public IMesh
+{
+public:
+    Mesh() { for (u32& s : m_sizes) s = 0; }
+    // argument rules of Mesh.cpp:30-54
+    u32 setVertexData(const float* data, u32 numVertices, u32 numComponents, u32 slotId, bool asyncCopy) override
+    {
+        if (!data || numVertices == 0 || slotId >= VERTEX_DATA_COUNT || numComponents > 4 || (m_numVertices != 0 && m_numVertices != numVertices) ||
+            (slotId == VERTEX_DATA_POSITION && numComponents != 3))
+            return ERROR_INVALID_PARAMETER;
+        auto buf = std::make_shared<DeviceBuffer>(sizeof(float) * (size_t)numComponents * numVertices);
+        if (!buf->ok()) return ERROR_GPU_ALLOC_FAIL;
+        buf->copyFrom(data, !asyncCopy);
+        m_data[slotId] = buf; m_sizes[slotId] = numComponents; m_numVertices = numVertices;
+        return ERROR_ALL_FINE;
+    }
+    u32 setIndices(const u32* indices, u32 numIndices, bool asyncCopy) override
+    {
+        if (!indices || (numIndices % 3) != 0 || numIndices == 0) return ERROR_INVALID_PARAMETER;
+        auto buf = std::make_shared<DeviceBuffer>((size_t)numIndices * sizeof(u32));
+        if (!buf->ok()) return ERROR_GPU_ALLOC_FAIL;
+        buf->copyFrom(indices, !asyncCopy);
+        m_indices = buf; m_numIndices = numIndices;
+        return ERROR_ALL_FINE;
+    }
+    wptr<IScene> scene() const override { return m_scene; }
+    wptr<IScene> m_scene;
+    u32 m_numVertices = 0, m_numIndices = 0;
+    sptr<DeviceBuffer> m_indices, m_data[VERTEX_DATA_COUNT];
+    u32 m_sizes[VERTEX_DATA_COUNT];
+};
+sptr<IMesh> IMesh::create() { return std::make_shared<Mesh>(); }
+
+// Scene + SceneTree (Scene.cpp, SceneTree.cpp).  TREE is the only scene type with behaviour in the reference.
+class Scene : public IScene
+{
+public:
+    Scene()
+    {
+        m_min = { -30.f, -30.f, -30.f }; m_max = { 30.f, 30.f, 30.f };               // SceneTree.cpp:43-45
+        m_root = std::make_shared<DeviceBuffer>(bmGetNodeSize());                       // identifies the tree to the bm* launchers
+    }
+    void addMesh(const sptr<IMesh>& mesh) override { m_meshes.push_back(std::static_pointer_cast<Mesh>(mesh)); m_dirtyTable = true; }
+    void removeMesh(const IMesh& mesh) override
+    {
+        for (auto it = m_meshes.begin(); it != m_meshes.end(); ++it) if (it->get() == &mesh) { m_meshes.erase(it); m_dirtyTable = true; break; }
+    }
+    // Scene::updateMeshPtrs, Scene.cpp:58-79
+    void updateMeshPtrs()
+    {
+        if (!m_dirtyTable) return;
+        std::vector<bmStaticMeshData> tab(m_meshes.size());
+        for (size_t i = 0; i < m_meshes.size(); i++)
+        {
+            auto& m = m_meshes[i];
+            memset(&tab[i], 0, sizeof(tab[i]));
+            tab[i].m_indices = m->m_indices ? m->m_indices->ptr<u32>() : nullptr;
+            for (u32 s = 0; s < VERTEX_DATA_COUNT; s++) { tab[i].m_vertexData[s] = m->m_data[s] ? m->m_data[s]->ptr<float>() : nullptr; tab[i].m_vertexDataSizes[s] = m->m_sizes[s]; }
+            tab[i].m_numIndices = m->m_numIndices; tab[i].m_numVertices = m->m_numVertices;
+        }
+        m_table = std::make_shared<DeviceBuffer>(std::max<size_t>(1, tab.size()) * sizeof(bmStaticMeshData));
+        if (!tab.empty()) m_table->copyFrom(tab.data(), true);
+        m_dirtyTable = false;
+    }
+    void updateGPUScene() override
+    {
+        updateMeshPtrs();
+        bmResetScene(m_root->ptr<void>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0);
+        for (u32 i = 0; i < m_meshes.size(); i++)
+        {
+            auto& m = m_meshes[i];
+            if (!m->m_data[VERTEX_DATA_POSITION] || !m->m_indices) continue;
+            bmInsertMeshInTree(m->m_data[VERTEX_DATA_POSITION]->ptr<const bmVec3>(), m->m_indices->ptr<u32>(), m->m_numIndices, i, m_min, m_max,
+                               m_root->ptr<void>(), nullptr, nullptr, nullptr, nullptr);
+        }
+        bmBuildTree(m_root->ptr<void>());
+    }
+    // Scene::march + SceneTree::march, Scene.cpp:81-97, SceneTree.cpp:109-127
+    u32 march(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh)
+    {
+        IRenderTarget* rt = RenderTarget::get();
+        if (!rt) return ERROR_NO_RENDER_TARGET;
+        if (rt->width() != raysWide || rt->height() != raysHigh) return ERROR_RT_CAM_MISMATCH;
+        bmVec3 eye = { eye3[0], eye3[1], eye3[2] }; bmMat3 orient; memcpy(orient.m, orient9, 36);
+        bmMarch(m_root->ptr<void>(), &m_min, &m_max, rays->ptr<const bmVec3>(), rt->buffer<u32>(), rt->pitch(), rt->width(), rt->height(), &eye, &orient,
+                m_table ? m_table->ptr<const bmStaticMeshData>() : nullptr);
+        return ERROR_ALL_FINE;
+    }
+    u32 marchHits(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh, bmHit* hostHits)
+    {
+        bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
+        size_t n = (size_t)raysWide * raysHigh;
+        IRenderTarget* rt = RenderTarget::get();
+        if (rt && (rt->width() != raysWide || rt->height() != raysHigh)) return ERROR_RT_CAM_MISMATCH;
+        if (!t) { for (size_t i = 0; i < n; i++) hostHits[i] = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu }; return ERROR_ALL_FINE; }
+        DeviceBuffer hits(n * sizeof(bmHit));
+        if (!hits.ok()) return ERROR_GPU_ALLOC_FAIL;
+        int r = bmTraceCamera(t, rays->ptr<const float>(), n, eye3, orient9, BM_TRACE_REFERENCE, hits.ptr<bmHit>(), rt ? rt->buffer<u32>() : nullptr,
+                              m_table ? m_table->ptr<const bmStaticMeshData>() : nullptr, nullptr);
+        if (r != BM_OK) return (u32)r;
+        hits.copyTo(hostHits, true);
+        return ERROR_ALL_FINE;
+    }
+    void* rootKey() const { return m_root->ptr<void>(); }
+private:
+    bmVec3 m_min, m_max;
+    std::vector<sptr<Mesh>> m_meshes;
+    sptr<DeviceBuffer> m_root, m_table;
+    bool m_dirtyTable = true;
+};
+sptr<IScene> IScene::create() { return std::make_shared<Scene>(); }
+
+class Camera : public ICamera
+{
+public:
+    // Camera::setInitialRays, Camera.cpp:43-72: per-pixel unit directions built on the host with accumulating rx / ry
+    u32 setInitialRays(u32 width, u32 height, float left, float right, float top, float bottom, float zoom) override
+    {
+        if (width == 0 || height == 0) return ERROR_INVALID_PARAMETER;
+        m_width = width; m_height = height;
+        std::vector<float> tab((size_t)width * height * 3);
+        float dx = (right - left) / width;
+        float dy = (bottom - top) / height;
+        float ry = top + dy * .5f;
+        float z2 = zoom * zoom;
+        for (u32 y = 0; y < height; y++, ry += dy)
+        {
+            float rx = left + dx * .5f;
+            for (u32 x = 0; x < width; x++, rx += dx)
+            {
+                float d = 1.f / sqrtf(z2 + rx * rx + ry * ry);
+                if (std::isnan(d) || d <= 0.f) return ERROR_INVALID_PARAMETER;
+                size_t a = ((size_t)y * width + x) * 3;
+                tab[a] = rx * d; tab[a + 1] = ry * d; tab[a + 2] = zoom * d;
+            }
+        }
+        m_rays = std::make_shared<DeviceBuffer>(tab.size() * sizeof(float));
+        if (!m_rays->ok()) return ERROR_GPU_ALLOC_FAIL;
+        m_rays->copyFrom(tab.data(), true);
+        return ERROR_ALL_FINE;
+    }
+    u32 clear(u32 value) override
+    {
+        IRenderTarget* rt = RenderTarget::get();
+        if (!rt) return ERROR_NO_RENDER_TARGET;
+        bmClear(rt->buffer<u32>(), rt->pitch(), rt->width(), rt->height(), value);
+        return ERROR_ALL_FINE;
+    }
+    u32 traceScene(const float* eye3, const float* orient3x3, sptr<IScene>& scene) override
+    {
+        if (!eye3 || !orient3x3 || !scene || m_width == 0 || m_height == 0 || !m_rays) return ERROR_INVALID_PARAMETER;   // Camera.cpp:88-92
+        return static_cast<Scene*>(scene.get())->march(eye3, orient3x3, m_rays, m_width, m_height);
+    }
+    u32 traceSceneHits(const float* eye3, const float* orient3x3, sptr<IScene>& scene, bmHit* hostHits) override
+    {
+        if (!eye3 || !orient3x3 || !scene || m_width == 0 || m_height == 0 || !m_rays || !hostHits) return ERROR_INVALID_PARAMETER;
+        return static_cast<Scene*>(scene.get())->marchHits(eye3, orient3x3, m_rays, m_width, m_height, hostHits);
+    }
+    u32 copyInitialRays(float* host) const { if (!m_rays) return ERROR_INVALID_PARAMETER; m_rays->copyTo(host, true); return ERROR_ALL_FINE; }
+private:
+    u32 m_width = 0, m_height = 0;
+    sptr<DeviceBuffer> m_rays;
+};
+sptr<ICamera> ICamera::create() { return std::make_shared<Camera>(); }
+} // namespace Beam
+
+// ---- flat C view for ctypes (handles are heap-allocated shared_ptr copies) -------------------------------------------------
+using namespace Beam;
+extern "C"
+{
+void* beamSceneCreate() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); bm::set_error("no usable CUDA device: this library has no CPU path"); return nullptr; } return new sptr<IScene>(IScene::create()); }
+void  beamSceneDestroy(void* s) { delete (sptr<IScene>*)s; }
+void* beamMeshCreate() { return new sptr<IMesh>(IMesh::create()); }
+void  beamMeshDestroy(void* m) { delete (sptr<IMesh>*)m; }
+uint32_t beamMeshSetVertexData(void* m, const float* hostData, uint32_t numVertices, uint32_t numComponents, uint32_t slotId, int asyncCopy)
+{ return (*(sptr<IMesh>*)m)->setVertexData(hostData, numVertices, numComponents, slotId, asyncCopy != 0); }
+uint32_t beamMeshSetIndices(void* m, const uint32_t* hostIndices, uint32_t numIndices, int asyncCopy)
+{ return (*(sptr<IMesh>*)m)->setIndices(hostIndices, numIndices, asyncCopy != 0); }
+void  beamSceneAddMesh(void* s, void* m) { (*(sptr<IScene>*)s)->addMesh(*(sptr<IMesh>*)m); }
+void  beamSceneRemoveMesh(void* s, void* m) { (*(sptr<IScene>*)s)->removeMesh(**(sptr<IMesh>*)m); }
+void  beamSceneUpdateGPUScene(void* s) { (*(sptr<IScene>*)s)->updateGPUScene(); }
+void* beamSceneTree(void* s) { return bmTreeFromRoot(static_cast<Scene*>(((sptr<IScene>*)s)->get())->rootKey()); }
+void* beamCameraCreate() { return new sptr<ICamera>(ICamera::create()); }
+void  beamCameraDestroy(void* c) { delete (sptr<ICamera>*)c; }
+uint32_t beamCameraSetInitialRays(void* c, uint32_t w, uint32_t h, float l, float r, float t, float b, float zoom) { return (*(sptr<ICamera>*)c)->setInitialRays(w, h, l, r, t, b, zoom); }
+uint32_t beamCameraCopyInitialRays(void* c, float* host) { return static_cast<Camera*>(((sptr<ICamera>*)c)->get())->copyInitialRays(host); }
+uint32_t beamCameraClear(void* c, uint32_t value) { return (*(sptr<ICamera>*)c)->clear(value); }
+uint32_t beamCameraTraceScene(void* c, const float* eye3, const float* orient9, void* s) { return (*(sptr<ICamera>*)c)->traceScene(eye3, orient9, *(sptr<IScene>*)s); }
+uint32_t beamCameraTraceSceneHits(void* c, const float* eye3, const float* orient9, void* s, bmHit* hostHits) { return (*(sptr<ICamera>*)c)->traceSceneHits(eye3, orient9, *(sptr<IScene>*)s, hostHits); }
+void* beamRenderTargetCreateHeadless(uint32_t w, uint32_t h, uint32_t pitch) { auto rt = IRenderTarget::createHeadless(w, h, pitch); return rt ? new sptr<IRenderTarget>(rt) : nullptr; }
+void  beamRenderTargetDestroy(void* r) { delete (sptr<IRenderTarget>*)r; }
+uint32_t beamRenderTargetLock(void* r) { return (*(sptr<IRenderTarget>*)r)->lock(); }
+uint32_t beamRenderTargetUnlock(void* r) { return (*(sptr<IRenderTarget>*)r)->unlock(); }
+void* beamRenderTargetBuffer(void* r) { return (*(sptr<IRenderTarget>*)r)->buffer(); }
+uint32_t beamRenderTargetReadPixels(void* r, uint32_t* hostPixels) { return (*(sptr<IRenderTarget>*)r)->readPixels(hostPixels); }
+int   beamDeviceSynchronize() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : BM_ERROR_CUDA; }
+}

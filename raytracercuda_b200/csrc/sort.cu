@@ -1,0 +1,169 @@
+// sort.cu -- stable LSD radix sort of (leaf code, triangle id) pairs, 8 bits per pass, staged through shared memory with
+// warp-level match/ballot ranking (north_star: "a device radix sort staged through shared memory, with warp-level scans
+// and ballots").
+//
+// Per pass:  tile histogram (1 read of the keys)  ->  exclusive scan of the digit-major [256][tiles] table  ->  scatter
+// (1 read of keys+values, 1 write).  A tile is 4096 consecutive pairs handled by 8 warps; warp w owns the contiguous
+// sub-range [512w, 512w+512) as 16 rows of 32 lanes, so (warp, row, lane) order == input order and ranking inside a digit
+// is stable.  In the scatter kernel the tile is first permuted into digit order in shared memory, then written out so that
+// consecutive threads write consecutive addresses of each digit run.
+// HBM traffic per pass: 4 B (histogram) + 8 B + 8 B per pair; 4 passes for the 31-bit codes of the default world.
+#include "bm_device.cuh"
+
+namespace bm
+{
+namespace
+{
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 4096
+constexpr int RS_BINS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u32* __restrict__ keys, size_t n, int shift, u32 numTiles, u32* __restrict__ counts)
+{
+    __shared__ u32 hist[RS_BINS];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    size_t base = (size_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++)
+    {
+        size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
+        u32 d = idx < n ? ((keys[idx] >> shift) & 0xFFu) : (u32)RS_BINS;
+        // aggregate equal digits inside the warp before touching shared memory
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        if (d < RS_BINS && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[d], (u32)__popc(peers));
+    }
+    __syncthreads();
+    counts[(size_t)threadIdx.x * numTiles + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
+                                                                   u32* __restrict__ keysOut, u32* __restrict__ valsOut,
+                                                                   size_t n, int shift, u32 numTiles, const u32* __restrict__ scanned)
+{
+    __shared__ u32 warpHist[RS_WARPS][RS_BINS + 1];     // +1: bin 256 swallows the out-of-range tail
+    __shared__ u32 digitStart[RS_BINS + 1];
+    __shared__ u32 globalBase[RS_BINS];
+    __shared__ u32 sKeys[RS_TILE];
+    __shared__ u32 sVals[RS_TILE];
+
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * (RS_BINS + 1); i += RS_THREADS) (&warpHist[0][0])[i] = 0;
+    __syncthreads();
+
+    const size_t tileBase = (size_t)blockIdx.x * RS_TILE;
+    const size_t warpBase = tileBase + (size_t)w * (RS_ITEMS * 32);
+    u32 key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++)
+    {
+        size_t idx = warpBase + (size_t)r * 32 + lane;
+        bool ok = idx < n;
+        key[r] = ok ? keysIn[idx] : 0xFFFFFFFFu;
+        val[r] = ok ? valsIn[idx] : 0u;
+    }
+    // stable rank of every item among the items of the same digit in this warp
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++)
+    {
+        size_t idx = warpBase + (size_t)r * 32 + lane;
+        u32 d = idx < n ? ((key[r] >> shift) & 0xFFu) : (u32)RS_BINS;
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        unsigned leader = __ffs(peers) - 1;
+        u32 before = 0;
+        if (lane == leader) { before = warpHist[w][d]; warpHist[w][d] = before + __popc(peers); }
+        before = __shfl_sync(0xFFFFFFFFu, before, leader);
+        rank[r] = before + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over the warps, tile total, global base of this tile's run
+    {
+        u32 d = threadIdx.x;      // RS_THREADS == RS_BINS
+        u32 run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) { u32 c = warpHist[ww][d]; warpHist[ww][d] = run; run += c; }
+        digitStart[d] = run;      // tile count of digit d, scanned below
+        globalBase[d] = scanned[(size_t)d * numTiles + blockIdx.x];
+    }
+    __syncthreads();
+    if (w == 0)
+    {
+        // exclusive scan of the 256 digit counts by one warp (8 per lane)
+        u32 c[8], s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { c[i] = digitStart[lane * 8 + i]; s += c[i]; }
+        u32 inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (unsigned)o) inc += t; }
+        u32 ex = inc - s;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { digitStart[lane * 8 + i] = ex; ex += c[i]; }
+        if (lane == 31) digitStart[RS_BINS] = ex;
+    }
+    __syncthreads();
+    // permute the tile into digit order in shared memory
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++)
+    {
+        size_t idx = warpBase + (size_t)r * 32 + lane;
+        if (idx < n)
+        {
+            u32 d = (key[r] >> shift) & 0xFFu;
+            u32 pos = digitStart[d] + warpHist[w][d] + rank[r];
+            sKeys[pos] = key[r];
+            sVals[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    const u32 valid = digitStart[RS_BINS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++)
+    {
+        u32 pos = i * RS_THREADS + threadIdx.x;
+        if (pos < valid)
+        {
+            u32 k = sKeys[pos];
+            u32 d = (k >> shift) & 0xFFu;
+            size_t g = (size_t)globalBase[d] + (pos - digitStart[d]);
+            keysOut[g] = k;
+            valsOut[g] = sVals[pos];
+        }
+    }
+}
+} // namespace
+
+size_t sort_temp_bytes(size_t n)
+{
+    size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    size_t counts = ((tiles * RS_BINS * 4 + 255) / 256) * 256;
+    return counts + scan_temp_bytes(tiles * RS_BINS);
+}
+
+int radix_sort_pairs(u32* d_keysA, u32* d_valsA, u32* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB)
+{
+    int passes = (bits + 7) / 8;
+    if (passes < 1) passes = 1;
+    *resultInB = passes & 1;
+    if (n == 0) return BM_OK;
+    size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    u32* counts = (u32*)d_temp;
+    void* scanTemp = (char*)d_temp + ((tiles * RS_BINS * 4 + 255) / 256) * 256;
+    u32 *ka = d_keysA, *va = d_valsA, *kb = d_keysB, *vb = d_valsB;
+    for (int p = 0; p < passes; p++)
+    {
+        int shift = 8 * p;
+        radix_hist_kernel<<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, n, shift, (u32)tiles, counts);
+        BM_CUDA(cudaGetLastError());
+        BM_TRY(exclusive_scan_u32(counts, counts, tiles * RS_BINS, nullptr, scanTemp, s));
+        radix_scatter_kernel<<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, (u32)tiles, counts);
+        BM_CUDA(cudaGetLastError());
+        u32* t;
+        t = ka; ka = kb; kb = t;
+        t = va; va = vb; vb = t;
+    }
+    return BM_OK;
+}
+} // namespace bm

@@ -1,0 +1,371 @@
+// tree.cu -- host side of the C ABI (include/beam_b200.h): the tree object, the build pipeline and the reference-symbol
+// wrappers.  Everything here only allocates, launches and reads back two counters; all arithmetic runs in the kernels.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "bm_device.cuh"
+#include "bm_grid_host.h"
+
+namespace bm
+{
+static thread_local std::string g_error;
+void set_error(const std::string& s) { g_error = s; }
+const char* last_error() { return g_error.c_str(); }
+
+int sm_count()
+{
+    static int n = 0;
+    if (!n)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// grow-only device buffer: rebuilding a scene of the same size performs no allocation
+struct DevBuf
+{
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return BM_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return BM_ERROR_GPU_ALLOC_FAIL; }
+        cap = want;
+        return BM_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct StagedMesh { const float* pos; const u32* idx; u32 numTris; u32 meshIdx; };
+} // namespace bm
+
+using namespace bm;
+
+struct bmTree
+{
+    HostGrid hgrid;
+    Grid dgrid;                      // device table pointers
+    DevBuf tables;
+    cudaStream_t stream = 0;
+    std::vector<StagedMesh> staged;
+    std::vector<u32> meshBase;       // indexed by position in `staged` order
+    bool built = false;
+    // build products
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars;
+    u32* sortedKeys = nullptr; u32* sortedVals = nullptr;
+    u64 T = 0, P = 0, L = 0;
+    u32 maxLeaf = 0, overLeaves = 0;
+    u32 hostScalars[8];
+
+    TreeView view() const
+    {
+        TreeView v;
+        v.grid = dgrid; v.nodes = nodes.as<float4>(); v.leaves = leaves.as<uint4>(); v.ltris = ltris.as<float4>();
+        v.numLeaves = (u32)L; v.rootRef = (L == 1) ? (0u | LEAF_BIT) : 0u; v.maxLeafFaces = 256;
+        return v;
+    }
+    ~bmTree()
+    {
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars };
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+static int tree_build(bmTree* t)
+{
+    cudaStream_t s = t->stream;
+    // 1. soup
+    u64 T = 0;
+    t->meshBase.clear();
+    for (auto& m : t->staged) { t->meshBase.push_back((u32)T); T += m.numTris; }
+    if (T >= 0xFFFFFFFFull) { set_error("more than 2^32-2 triangles"); return BM_ERROR_CAPACITY; }
+    t->T = T; t->P = 0; t->L = 0; t->maxLeaf = 0; t->overLeaves = 0;
+    BM_TRY(t->scalars.reserve(64));
+    BM_CUDA(cudaMemsetAsync(t->scalars.p, 0, 64, s));
+    if (T == 0) { t->built = true; return BM_OK; }
+    BM_TRY(t->soup.reserve(T * 48));
+    for (size_t k = 0; k < t->staged.size(); k++)
+    {
+        auto& m = t->staged[k];
+        BM_TRY(gather_mesh(m.pos, m.idx, m.numTris, m.meshIdx, t->meshBase[k], t->soup.as<float4>(), s));
+    }
+    // 2. pair counts per triangle -> offsets
+    BM_TRY(t->counts.reserve(T * 4));
+    BM_TRY(t->temp.reserve(scan_temp_bytes(T)));
+    BM_TRY(count_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), s));
+    u32* d_scal = t->scalars.as<u32>();
+    BM_TRY(exclusive_scan_u32(t->counts.as<u32>(), t->counts.as<u32>(), T, d_scal + 0, t->temp.p, s));
+    BM_CUDA(cudaMemcpyAsync(&t->hostScalars[0], d_scal + 0, 4, cudaMemcpyDeviceToHost, s));
+    BM_CUDA(cudaStreamSynchronize(s));
+    u64 P = t->hostScalars[0];
+    t->P = P;
+    if (P == 0) { t->built = true; return BM_OK; }      // every triangle outside the world box
+    // 3. emit + sort
+    BM_TRY(t->keysA.reserve(P * 4)); BM_TRY(t->valsA.reserve(P * 4)); BM_TRY(t->keysB.reserve(P * 4)); BM_TRY(t->valsB.reserve(P * 4));
+    BM_TRY(t->temp.reserve(sort_temp_bytes(P) > scan_temp_bytes(P) ? sort_temp_bytes(P) : scan_temp_bytes(P)));
+    BM_TRY(emit_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->keysA.as<u32>(), t->valsA.as<u32>(), s));
+    int inB = 0;
+    BM_TRY(radix_sort_pairs(t->keysA.as<u32>(), t->valsA.as<u32>(), t->keysB.as<u32>(), t->valsB.as<u32>(), P, t->hgrid.D, t->temp.p, s, &inB));
+    t->sortedKeys = inB ? t->keysB.as<u32>() : t->keysA.as<u32>();
+    t->sortedVals = inB ? t->valsB.as<u32>() : t->valsA.as<u32>();
+    u32* spareKeys = inB ? t->keysA.as<u32>() : t->keysB.as<u32>();   // reused as leaf index per pair
+    // 4. leaves
+    BM_TRY(t->flags.reserve(P * 4));
+    BM_TRY(mark_heads(t->sortedKeys, P, t->flags.as<u32>(), s));
+    BM_TRY(exclusive_scan_u32(t->flags.as<u32>(), spareKeys, P, d_scal + 1, t->temp.p, s));
+    BM_CUDA(cudaMemcpyAsync(&t->hostScalars[1], d_scal + 1, 4, cudaMemcpyDeviceToHost, s));
+    BM_TRY(t->ltris.reserve(P * 48));
+    BM_TRY(pack_leaf_tris(t->soup.as<float4>(), t->sortedVals, P, t->ltris.as<float4>(), s));      // overlaps the read-back
+    BM_CUDA(cudaStreamSynchronize(s));
+    u64 L = t->hostScalars[1];
+    t->L = L;
+    BM_TRY(t->leaves.reserve(L * 16));
+    BM_TRY(write_leaves(t->sortedKeys, t->flags.as<u32>(), spareKeys, P, (u32)L, t->leaves.as<uint4>(), s));
+    BM_TRY(t->leafBox.reserve(L * 24));
+    float ext = 0.f;
+    for (int a = 0; a < 3; a++) ext = fmaxf(ext, t->hgrid.wmax[a] - t->hgrid.wmin[a]);
+    float pad = ext * (1.f / 1048576.f);
+    BM_TRY(leaf_bounds(t->leaves.as<uint4>(), (u32)L, t->ltris.as<float4>(), t->leafBox.as<float>(), pad, d_scal + 2, s));
+    // 5. hierarchy + refit
+    if (L >= 2)
+    {
+        BM_TRY(t->nodes.reserve((L - 1) * 64)); BM_TRY(t->nodeBox.reserve((L - 1) * 24));
+        BM_TRY(t->parentN.reserve((L - 1) * 4)); BM_TRY(t->parentL.reserve(L * 4)); BM_TRY(t->visit.reserve((L - 1) * 4));
+        BM_TRY(emit_hierarchy(t->leaves.as<uint4>(), (u32)L, t->hgrid.D, t->nodes.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), s));
+        BM_TRY(refit((u32)L, t->leafBox.as<float>(), t->nodeBox.as<float>(), t->parentN.as<u32>(), t->parentL.as<u32>(), t->visit.as<u32>(), t->nodes.as<float4>(), s));
+    }
+    t->built = true;
+    return BM_OK;
+}
+
+static int tree_finish_stats(bmTree* t)
+{
+    if (t->P == 0) return BM_OK;
+    BM_CUDA(cudaMemcpyAsync(&t->hostScalars[2], t->scalars.as<u32>() + 2, 8, cudaMemcpyDeviceToHost, t->stream));
+    BM_CUDA(cudaStreamSynchronize(t->stream));
+    t->maxLeaf = t->hostScalars[2]; t->overLeaves = t->hostScalars[3];
+    return BM_OK;
+}
+
+// ---- Part 2 -------------------------------------------------------------------------------------------------------------
+extern "C" const char* bmLastErrorString(void) { return bm::last_error(); }
+
+extern "C" int bmTreeCreate(bmTree** out, const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth)
+{
+    if (!out) return BM_ERROR_INVALID_PARAMETER;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    {
+        cudaGetLastError();
+        set_error("no usable CUDA device: this library has no CPU path");
+        return BM_ERROR_CUDA;
+    }
+    const float dmin[3] = { -30.f, -30.f, -30.f }, dmax[3] = { 30.f, 30.f, 30.f };      // SceneTree.cpp:43-45
+    bmTree* t = new bmTree();
+    if (!build_host_grid(t->hgrid, worldMin3 ? worldMin3 : dmin, worldMax3 ? worldMax3 : dmax, minLeafSize > 0 ? minLeafSize : .03f, maxDepth ? maxDepth : 38))
+    {
+        delete t;
+        set_error("world box / leaf size does not give a uniform leaf depth of at most 32 (and at most 11 bits per axis)");
+        return BM_ERROR_UNSUPPORTED_WORLD;
+    }
+    size_t n0 = t->hgrid.tab[0].size(), n1 = t->hgrid.tab[1].size(), n2 = t->hgrid.tab[2].size();
+    int r = t->tables.reserve((n0 + n1 + n2) * 4);
+    if (r != BM_OK) { delete t; return r; }
+    float* d = t->tables.as<float>();
+    cudaError_t e = cudaMemcpy(d, t->hgrid.tab[0].data(), n0 * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n0, t->hgrid.tab[1].data(), n1 * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n0 + n1, t->hgrid.tab[2].data(), n2 * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error(std::string("table upload: ") + cudaGetErrorString(e)); delete t; return BM_ERROR_CUDA; }
+    t->dgrid.tab[0] = d; t->dgrid.tab[1] = d + n0; t->dgrid.tab[2] = d + n0 + n1;
+    for (int a = 0; a < 3; a++) t->dgrid.k[a] = t->hgrid.k[a];
+    t->dgrid.D = t->hgrid.D;
+    *out = t;
+    return BM_OK;
+}
+
+extern "C" void bmTreeDestroy(bmTree* t) { delete t; }
+extern "C" int bmTreeSetStream(bmTree* t, void* stream) { if (!t) return BM_ERROR_INVALID_PARAMETER; t->stream = (cudaStream_t)stream; return BM_OK; }
+extern "C" int bmTreeReset(bmTree* t) { if (!t) return BM_ERROR_INVALID_PARAMETER; t->staged.clear(); t->built = false; return BM_OK; }
+
+extern "C" int bmTreeAddMesh(bmTree* t, const float* d_positions, const uint32_t* d_indices, uint32_t numIndices, uint32_t meshIdx)
+{
+    if (!t || !d_positions || !d_indices || (numIndices % 3) != 0) return BM_ERROR_INVALID_PARAMETER;
+    t->staged.push_back({ d_positions, d_indices, numIndices / 3, meshIdx });
+    t->built = false;
+    return BM_OK;
+}
+
+extern "C" int bmTreeBuild(bmTree* t)
+{
+    if (!t) return BM_ERROR_INVALID_PARAMETER;
+    return tree_build(t);
+}
+
+extern "C" int bmTreeStats(const bmTree* tc, uint64_t* s)
+{
+    bmTree* t = const_cast<bmTree*>(tc);
+    if (!t || !s) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    BM_TRY(tree_finish_stats(t));
+    s[0] = t->T; s[1] = t->P; s[2] = t->L; s[3] = t->L ? t->L - 1 : 0; s[4] = (u64)t->hgrid.D; s[5] = t->maxLeaf; s[6] = t->overLeaves; s[7] = t->staged.size();
+    return BM_OK;
+}
+
+extern "C" int bmTreeCopyPairs(const bmTree* t, uint32_t* d_code, uint32_t* d_tri)
+{
+    if (!t) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    if (!t->P) return BM_OK;
+    if (d_code) BM_CUDA(cudaMemcpyAsync(d_code, t->sortedKeys, t->P * 4, cudaMemcpyDeviceToDevice, t->stream));
+    if (d_tri) BM_CUDA(cudaMemcpyAsync(d_tri, t->sortedVals, t->P * 4, cudaMemcpyDeviceToDevice, t->stream));
+    return BM_OK;
+}
+
+extern "C" int bmTreeCopyTopology(const bmTree* t, uint32_t* d_prefixLen, uint32_t* d_prefix, uint32_t* d_child0, uint32_t* d_child1)
+{
+    if (!t) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    if (t->L < 2) return BM_OK;
+    size_t N = t->L - 1;
+    const char* q3 = (const char*)t->nodes.p + 48;
+    if (d_child0)    BM_CUDA(cudaMemcpy2DAsync(d_child0, 4, q3 + 0, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    if (d_child1)    BM_CUDA(cudaMemcpy2DAsync(d_child1, 4, q3 + 4, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    if (d_prefix)    BM_CUDA(cudaMemcpy2DAsync(d_prefix, 4, q3 + 8, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    if (d_prefixLen) BM_CUDA(cudaMemcpy2DAsync(d_prefixLen, 4, q3 + 12, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    return BM_OK;
+}
+
+extern "C" int bmTreeCopyChildBoxes(const bmTree* t, float* d_boxes12)
+{
+    if (!t) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    if (t->L < 2) return BM_OK;
+    BM_CUDA(cudaMemcpy2DAsync(d_boxes12, 48, t->nodes.p, 64, 48, t->L - 1, cudaMemcpyDeviceToDevice, t->stream));
+    return BM_OK;
+}
+
+extern "C" int bmTreeMeshBases(const bmTree* t, uint32_t* h_bases, uint32_t capacity)
+{
+    if (!t || !h_bases) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    for (size_t i = 0; i < t->meshBase.size() && i < capacity; i++) h_bases[i] = t->meshBase[i];
+    return BM_OK;
+}
+
+extern "C" int bmTraceRays(bmTree* t, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters)
+{
+    if (!t || (!d_rays && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) BM_TRY(tree_build(t));
+    return trace_rays(t->view(), d_rays, numRays, mode, d_hits, d_counters, t->stream);
+}
+
+extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, const float* eye3, const float* orient9, int mode,
+                             bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters)
+{
+    if (!t || !eye3 || !orient9 || (!d_initialRays3 && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
+    if (d_pixels && !d_meshData) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) BM_TRY(tree_build(t));
+    CameraIn cam; cam.initialRays = d_initialRays3;
+    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
+    return trace_camera(t->view(), cam, numRays, mode, d_hits, d_pixels, d_meshData, d_counters, t->stream);
+}
+
+extern "C" int bmHashKeys(const float* d_points3, uint64_t n, uint32_t* d_hash, int32_t* d_cells3, void* stream)
+{
+    if (!d_points3 && n) return BM_ERROR_INVALID_PARAMETER;
+    return hash_keys(d_points3, n, d_hash, d_cells3, (cudaStream_t)stream);
+}
+
+// ---- Part 1: the reference's symbols -------------------------------------------------------------------------------------
+namespace
+{
+std::mutex g_regMutex;
+std::map<const void*, bmTree*> g_registry;      // rootNode device pointer -> tree
+
+[[noreturn]] void die(const char* what)
+{
+    // same policy as CUDA_CALL (CudaComon.cuh:59-68): print and exit; the reference's launchers return void
+    fprintf(stderr, "beam_b200: %s: %s\n", what, bm::last_error());
+    exit(1);
+}
+
+bmTree* find_tree(const void* root)
+{
+    std::lock_guard<std::mutex> lk(g_regMutex);
+    auto it = g_registry.find(root);
+    return it == g_registry.end() ? nullptr : it->second;
+}
+}
+
+extern "C" bmTree* bmTreeFromRoot(const void* root) { return find_tree(root); }
+
+extern "C" void bmResetScene(void* rootNode, void*, void*, void*, void*, void*, void*, uint32_t, uint32_t, uint32_t)
+{
+    bmTree* t = find_tree(rootNode);
+    if (t) bmTreeReset(t);
+    // a tree is created by the first bmInsertMeshInTree, which carries the world box
+}
+
+extern "C" void bmInsertMeshInTree(const bmVec3* vertices, const uint32_t* indices, uint32_t numIndices, uint32_t meshIdx,
+                                   bmVec3 bMin, bmVec3 bMax, void* treeRootNode, void*, void*, void*, void*)
+{
+    bmTree* t = find_tree(treeRootNode);
+    float mn[3] = { bMin.x, bMin.y, bMin.z }, mx[3] = { bMax.x, bMax.y, bMax.z };
+    if (t && (memcmp(t->hgrid.wmin, mn, 12) != 0 || memcmp(t->hgrid.wmax, mx, 12) != 0))
+    {
+        std::lock_guard<std::mutex> lk(g_regMutex);
+        g_registry.erase(treeRootNode); delete t; t = nullptr;
+    }
+    if (!t)
+    {
+        if (bmTreeCreate(&t, mn, mx, 0.f, 0) != BM_OK) die("bmInsertMeshInTree");
+        std::lock_guard<std::mutex> lk(g_regMutex);
+        g_registry[treeRootNode] = t;
+    }
+    if (bmTreeAddMesh(t, (const float*)vertices, indices, numIndices, meshIdx) != BM_OK) { bm::set_error("invalid mesh arguments"); die("bmInsertMeshInTree"); }
+}
+
+extern "C" int bmBuildTree(void* treeRootNode)
+{
+    bmTree* t = find_tree(treeRootNode);
+    if (!t) return BM_OK;      // nothing inserted: empty scene
+    return bmTreeBuild(t);
+}
+
+extern "C" void bmMarch(const void* root, const bmVec3*, const bmVec3*, const bmVec3* initialRays, uint32_t* buffer, uint32_t,
+                        uint32_t width, uint32_t height, const bmVec3* eye, const bmMat3* orient, const bmStaticMeshData* meshData)
+{
+    bmTree* t = find_tree(root);
+    u64 n = (u64)width * height;
+    if (!t)
+    {
+        // no mesh was ever inserted: every pixel misses (BuildTree.cu:493-496)
+        if (bm::clear_u32(buffer, n, 255u << 8, 0) != BM_OK) die("bmMarch");
+        return;
+    }
+    if (bmTraceCamera(t, (const float*)initialRays, n, &eye->x, orient->m, BM_TRACE_REFERENCE, nullptr, buffer, meshData, nullptr) != BM_OK) die("bmMarch");
+}
+
+extern "C" void bmClear(uint32_t* buffer, uint32_t pitch, uint32_t, uint32_t height, uint32_t clearValue)
+{
+    // RTClear.cu:21: maxAddr = pitch/4*height - 1, addresses clamped to it -> exactly pitch/4*height words are written
+    if (bm::clear_u32(buffer, (size_t)(pitch / 4) * height, clearValue, 0) != BM_OK) die("bmClear");
+}
+
+// sizes of the reference's structs (BuildTree.cu:546-555 on LP64)
+extern "C" uint32_t bmGetFaceSize(void) { return 32; }
+extern "C" uint32_t bmGetFacePtrSize(void) { return 8; }
+extern "C" uint32_t bmGetMaterialSize(void) { return 4; }
+extern "C" uint32_t bmGetNodeSize(void) { return 32; }
+extern "C" uint32_t bmGetFaceStoreSize(void) { return 16; }
+extern "C" uint32_t bmGetNodeStoreSize(void) { return 16; }
+extern "C" uint32_t bmGetFaceGroupStoreSize(void) { return 16; }

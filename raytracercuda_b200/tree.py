@@ -1,0 +1,155 @@
+"""Python view of the handle-based C ABI (include/beam_b200.h, Part 2).  torch provides device memory and streams only;
+every computation happens in libbeam_b200.so's CUDA kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BM_TRACE_CLOSEST, BM_TRACE_REFERENCE, check  # noqa: F401
+
+MISS = 0xFFFFFFFF
+
+
+def _dev_tensor(a, dtype, device):
+    if isinstance(a, torch.Tensor):
+        t = a.to(device=device, dtype=dtype).contiguous()
+    else:
+        arr = np.ascontiguousarray(a)
+        if arr.dtype == np.uint32:
+            arr = arr.view(np.int32)
+        t = torch.from_numpy(arr).to(device=device, dtype=dtype).contiguous()
+    return t
+
+
+def _u32(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint32)
+
+
+class Tree:
+    """bmTree*: staged meshes -> build -> trace.  Mirrors SceneTree's use of bmResetScene / bmInsertMeshInTree / bmMarch
+    (SceneTree.cpp:70-127) on the explicit entry points."""
+
+    def __init__(self, device="cuda:0", world_min=None, world_max=None, min_leaf=0.0, max_depth=0):
+        self.L = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.BeamError("beam_b200 needs a CUDA device: there is no CPU path")
+        torch.cuda.set_device(self.device)
+        torch.cuda.init()
+        torch.zeros(1, device=self.device)          # make sure the primary context exists before the library's first call
+        h = C.c_void_p()
+        wmin = None if world_min is None else np.ascontiguousarray(world_min, np.float32)
+        wmax = None if world_max is None else np.ascontiguousarray(world_max, np.float32)
+        check(self.L.bmTreeCreate(C.byref(h), None if wmin is None else wmin.ctypes.data, None if wmax is None else wmax.ctypes.data,
+                                  float(min_leaf), int(max_depth)), "bmTreeCreate")
+        self.h = h
+        self._meshes = []        # keeps device tensors alive: the library stages pointers, like the reference
+        self.use_stream(torch.cuda.current_stream(self.device))
+
+    def use_stream(self, stream: torch.cuda.Stream):
+        self.stream = stream
+        check(self.L.bmTreeSetStream(self.h, C.c_void_p(stream.cuda_stream)), "bmTreeSetStream")
+
+    def reset(self):
+        check(self.L.bmTreeReset(self.h), "bmTreeReset")
+        self._meshes = []
+
+    def add_mesh(self, positions, indices, mesh_idx=None):
+        P = _dev_tensor(positions, torch.float32, self.device).reshape(-1, 3)
+        I = _dev_tensor(indices, torch.int32, self.device).reshape(-1)
+        if mesh_idx is None:
+            mesh_idx = len(self._meshes)
+        check(self.L.bmTreeAddMesh(self.h, P.data_ptr(), I.data_ptr(), I.numel(), int(mesh_idx)), "bmTreeAddMesh")
+        self._meshes.append((P, I))
+        return mesh_idx
+
+    def build(self):
+        check(self.L.bmTreeBuild(self.h), "bmTreeBuild")
+
+    def stats(self) -> dict:
+        s = (C.c_uint64 * 8)()
+        check(self.L.bmTreeStats(self.h, s), "bmTreeStats")
+        k = ["triangles", "pairs", "leaves", "nodes", "depth", "max_leaf_faces", "overflow_leaves", "meshes"]
+        return {n: int(v) for n, v in zip(k, s)}
+
+    def mesh_bases(self) -> np.ndarray:
+        n = len(self._meshes)
+        b = (C.c_uint32 * max(n, 1))()
+        check(self.L.bmTreeMeshBases(self.h, b, n), "bmTreeMeshBases")
+        return np.array(b[:n], dtype=np.uint32)
+
+    def pairs(self):
+        P = self.stats()["pairs"]
+        code = torch.empty(P, dtype=torch.int32, device=self.device); tri = torch.empty(P, dtype=torch.int32, device=self.device)
+        check(self.L.bmTreeCopyPairs(self.h, code.data_ptr(), tri.data_ptr()), "bmTreeCopyPairs")
+        self.stream.synchronize()
+        return _u32(code), _u32(tri)
+
+    def topology(self):
+        N = self.stats()["nodes"]
+        t = [torch.empty(N, dtype=torch.int32, device=self.device) for _ in range(4)]
+        check(self.L.bmTreeCopyTopology(self.h, *[x.data_ptr() for x in t]), "bmTreeCopyTopology")
+        self.stream.synchronize()
+        plen, prefix, c0, c1 = [_u32(x) for x in t]
+        return plen, prefix, c0, c1
+
+    def child_boxes(self) -> np.ndarray:
+        N = self.stats()["nodes"]
+        b = torch.empty((N, 12), dtype=torch.float32, device=self.device)
+        check(self.L.bmTreeCopyChildBoxes(self.h, b.data_ptr()), "bmTreeCopyChildBoxes")
+        self.stream.synchronize()
+        return b.cpu().numpy()
+
+    def trace_rays(self, rays, mode=BM_TRACE_REFERENCE, counters=False, hits_out=None):
+        """rays: (n,6) float32 (origin, direction) = bmRay records. Returns the (n,4) hit tensor [t,u,v,tri-bits] on the device."""
+        R = _dev_tensor(rays, torch.float32, self.device).reshape(-1, 6)
+        n = R.shape[0]
+        hits = hits_out if hits_out is not None else torch.empty((n, 4), dtype=torch.float32, device=self.device)
+        cnt = torch.zeros(2, dtype=torch.int64, device=self.device) if counters else None
+        check(self.L.bmTraceRays(self.h, R.data_ptr(), n, int(mode), hits.data_ptr(), None if cnt is None else cnt.data_ptr()), "bmTraceRays")
+        return (hits, cnt) if counters else hits
+
+    def trace_camera(self, initial_rays, eye, orient, mode=BM_TRACE_REFERENCE, want_hits=True, pixels=None, mesh_table=None, counters=False):
+        R = _dev_tensor(initial_rays, torch.float32, self.device).reshape(-1, 3)
+        n = R.shape[0]
+        e = (C.c_float * 3)(*[float(x) for x in eye])
+        o = (C.c_float * 9)(*[float(x) for x in np.asarray(orient, np.float32).reshape(-1)])
+        hits = torch.empty((n, 4), dtype=torch.float32, device=self.device) if want_hits else None
+        cnt = torch.zeros(2, dtype=torch.int64, device=self.device) if counters else None
+        check(self.L.bmTraceCamera(self.h, R.data_ptr(), n, e, o, int(mode), None if hits is None else hits.data_ptr(),
+                                   None if pixels is None else pixels.data_ptr(), None if mesh_table is None else mesh_table.data_ptr(),
+                                   None if cnt is None else cnt.data_ptr()), "bmTraceCamera")
+        return hits, cnt
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.bmTreeDestroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def hits_to_numpy(hits: torch.Tensor):
+    """(n,4) device tensor -> dict of numpy arrays t,u,v (float32) and tri (uint32, MISS on a miss)."""
+    h = hits.cpu().numpy()
+    return {"t": h[:, 0].copy(), "u": h[:, 1].copy(), "v": h[:, 2].copy(), "tri": h[:, 3].copy().view(np.uint32)}
+
+
+def make_mesh_table(meshes, device) -> torch.Tensor:
+    """Device array of StaticMeshData (SharedTypes.h:10-18, 136 bytes each) from [(positions, indices, normals|None)] device tensors."""
+    n = len(meshes)
+    arr = (_lib.bmStaticMeshData * n)()
+    for i, (P, I, N) in enumerate(meshes):
+        arr[i].m_vertexData[0] = P.data_ptr(); arr[i].m_vertexDataSizes[0] = 3
+        if N is not None:
+            arr[i].m_vertexData[1] = N.data_ptr(); arr[i].m_vertexDataSizes[1] = 3
+        arr[i].m_indices = I.data_ptr(); arr[i].m_numVertices = P.shape[0]; arr[i].m_numIndices = I.numel()
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device)

@@ -1,0 +1,54 @@
+// Test-only: compiles the product's host+device inline arithmetic (csrc/bm_math.cuh, bm_sat.cuh) for the CPU so that the
+// no-GPU test tier can check the very same source against the oracle.  Never shipped, never used by the product.
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../../raytracercuda_b200/csrc/bm_sat.cuh"
+#include "../../raytracercuda_b200/csrc/bm_grid_host.h"
+using namespace bm;
+
+struct Collect { std::vector<uint64_t>* out; uint32_t tri; void operator()(u32 code) const { out->push_back(((uint64_t)code << 32) | tri); } };
+
+extern "C"
+{
+// pairs for an indexed mesh with the default world; returns count, fills sorted (code, tri) when out pointers non-null
+uint64_t hc_pairs(const float* pos, const uint32_t* idx, uint32_t numTris, const float* wmin, const float* wmax, float minLeaf, uint32_t maxDepth,
+                  uint32_t* code, uint32_t* tri, uint64_t cap, int* D)
+{
+    HostGrid hg;
+    if (!build_host_grid(hg, wmin, wmax, minLeaf, maxDepth)) return ~0ull;
+    Grid g; for (int a = 0; a < 3; a++) { g.tab[a] = hg.tab[a].data(); g.k[a] = hg.k[a]; } g.D = hg.D;
+    if (D) *D = hg.D;
+    std::vector<uint64_t> out;
+    for (uint32_t t = 0; t < numTris; t++)
+    {
+        const float* a = pos + 3 * idx[3 * t]; const float* b = pos + 3 * idx[3 * t + 1]; const float* c = pos + 3 * idx[3 * t + 2];
+        Collect col = { &out, t };
+        descend_triangle(g, mk3(a[0], a[1], a[2]), mk3(b[0], b[1], b[2]), mk3(c[0], c[1], c[2]), col);
+    }
+    std::sort(out.begin(), out.end());
+    if (code && tri) for (size_t i = 0; i < out.size() && i < cap; i++) { code[i] = (uint32_t)(out[i] >> 32); tri[i] = (uint32_t)out[i]; }
+    return out.size();
+}
+int hc_grid(const float* wmin, const float* wmax, float minLeaf, uint32_t maxDepth, int* k3, int* D, float* tabx, float* taby, float* tabz)
+{
+    HostGrid hg;
+    if (!build_host_grid(hg, wmin, wmax, minLeaf, maxDepth)) return 0;
+    for (int a = 0; a < 3; a++) k3[a] = hg.k[a]; *D = hg.D;
+    if (tabx) memcpy(tabx, hg.tab[0].data(), hg.tab[0].size() * 4);
+    if (taby) memcpy(taby, hg.tab[1].data(), hg.tab[1].size() * 4);
+    if (tabz) memcpy(tabz, hg.tab[2].data(), hg.tab[2].size() * 4);
+    return 1;
+}
+uint32_t hc_encode(int depth, uint32_t ix, uint32_t iy, uint32_t iz) { return encode_path(depth, ix, iy, iz); }
+void hc_decode(int depth, uint32_t p, uint32_t* xyz) { decode_path(depth, p, xyz[0], xyz[1], xyz[2]); }
+float hc_box_ray(const float* mn, const float* mx, const float* o, const float* id) { return box_ray(mk3(mn[0],mn[1],mn[2]), mk3(mx[0],mx[1],mx[2]), mk3(o[0],o[1],o[2]), mk3(id[0],id[1],id[2])); }
+float hc_tri_intersect(const float* o, const float* d, const float* v0, const float* v1, const float* v2, float* u, float* v)
+{
+    V3 a = mk3(v0[0],v0[1],v0[2]), b = mk3(v1[0],v1[1],v1[2]), c = mk3(v2[0],v2[1],v2[2]);
+    return tri_intersect(mk3(o[0],o[1],o[2]), mk3(d[0],d[1],d[2]), a, b - a, c - a, *u, *v);
+}
+uint32_t hc_hash3(uint32_t x, uint32_t y, uint32_t z) { return hash3(x, y, z); }
+uint32_t hc_hash(uint32_t x) { return hash32(x); }
+int32_t hc_map(float f) { return map_cell(f); }
+}

@@ -1,0 +1,136 @@
+"""GPU tier: the host-class mirror of the reference's public interface (Beam.h:32-72) end to end with HOST buffers, and
+the reference's own extern "C" symbols (bmResetScene / bmInsertMeshInTree / bmMarch / bmClear)."""
+import ctypes as C
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(meshes, names):
+    from raytracercuda_b200.host import IMesh, IScene, VERTEX_DATA_NORMAL, VERTEX_DATA_POSITION
+    scene = IScene.create()
+    for n in names:
+        P, I, N = meshes[n]
+        m = IMesh.create()
+        assert m.setIndices(I, I.size) == 0
+        assert m.setVertexData(P, P.shape[0], 3, VERTEX_DATA_POSITION) == 0
+        assert m.setVertexData(N, N.shape[0], 3, VERTEX_DATA_NORMAL) == 0
+        scene.addMesh(m)
+    return scene
+
+
+@pytest.mark.parametrize("name", ["f16", "suzanne", "bunny"])
+def test_viewer_sequence_matches_reference_pixels(name, meshes, golden, beam_lib, cuda_device):
+    """Program::initialize / renderFrame (TestProgram/Program.cpp:140-194, 287-355) replayed headless"""
+    from raytracercuda_b200.host import ICamera, IRenderTarget
+    scene = _scene(meshes, [name])
+    scene.updateGPUScene()
+    cam = ICamera.create()
+    assert cam.setInitialRays(200, 200, -1, 1, -1, 1, 1) == 0
+    assert zlib.crc32(cam.initialRays().tobytes()) == golden["initial_rays_200x200_crc32"]
+    rt = IRenderTarget.createHeadless(200, 200)
+    assert rt.lock() == 0
+    assert cam.clear(0x12345678) == 0
+    assert (rt.readPixels() == 0x12345678).all()
+    assert cam.traceScene([0, 0, -2.1], np.eye(3, dtype=np.float32), scene) == 0
+    px = rt.readPixels()
+    want = np.load(os.path.join(GOLDEN, "pixels_%s_200x200.npz" % name))["pixels"]
+    assert np.array_equal(px, want)
+    err, hits = cam.traceSceneHits([0, 0, -2.1], np.eye(3, dtype=np.float32), scene)
+    assert err == 0 and int((hits["tri"] != 0xFFFFFFFF).sum()) == golden["meshes"][name]["trace"]["200x200"]["hits"]
+    assert rt.unlock() == 0
+
+
+def test_error_codes(meshes, beam_lib, cuda_device):
+    from raytracercuda_b200 import host as H
+    m = H.IMesh.create()
+    P, I, N = meshes["f16"]
+    assert m.setVertexData(None, 10, 3, 0) == H.ERROR_INVALID_PARAMETER
+    assert m.setVertexData(P, 0, 3, 0) == H.ERROR_INVALID_PARAMETER
+    assert m.setVertexData(P, P.shape[0], 4, H.VERTEX_DATA_POSITION) == H.ERROR_INVALID_PARAMETER      # positions need 3 components
+    assert m.setVertexData(P, P.shape[0], 5, H.VERTEX_DATA_EXTRA1) == H.ERROR_INVALID_PARAMETER
+    assert m.setVertexData(P, P.shape[0], 3, H.VERTEX_DATA_COUNT) == H.ERROR_INVALID_PARAMETER
+    assert m.setVertexData(P, P.shape[0], 3, H.VERTEX_DATA_POSITION) == 0
+    assert m.setVertexData(N[:-1], P.shape[0] - 1, 3, H.VERTEX_DATA_NORMAL) == H.ERROR_INVALID_PARAMETER  # all slots share one vertex count
+    assert m.setIndices(I, I.size - 1) == H.ERROR_INVALID_PARAMETER
+    assert m.setIndices(None, 3) == H.ERROR_INVALID_PARAMETER
+    assert m.setIndices(I, I.size) == 0
+    cam = H.ICamera.create()
+    assert cam.setInitialRays(0, 10) == H.ERROR_INVALID_PARAMETER
+    scene = H.IScene.create(); scene.addMesh(m); scene.updateGPUScene()
+    assert cam.traceScene([0, 0, -2.1], np.eye(3), scene) == H.ERROR_INVALID_PARAMETER                  # no rays yet
+    assert cam.setInitialRays(64, 48, -1, 1, -1, 1, 1) == 0
+    assert cam.clear(0) == H.ERROR_NO_RENDER_TARGET
+    assert cam.traceScene([0, 0, -2.1], np.eye(3), scene) == H.ERROR_NO_RENDER_TARGET
+    assert cam.traceScene(None, np.eye(3), scene) == H.ERROR_INVALID_PARAMETER
+    assert H.IRenderTarget.createHeadless(0, 10) is None and H.IRenderTarget.createHeadless(64, 48, 64) is None
+    rt = H.IRenderTarget.createHeadless(32, 32)
+    assert rt.unlock() == H.ERROR_LOCK_FIRST
+    assert rt.lock() == 0 and rt.lock() == H.ERROR_UNLOCK_FIRST
+    assert cam.traceScene([0, 0, -2.1], np.eye(3), scene) == H.ERROR_RT_CAM_MISMATCH
+    assert rt.unlock() == 0
+    rt2 = H.IRenderTarget.createHeadless(64, 48)
+    assert rt2.lock() == 0 and cam.traceScene([0, 0, -2.1], np.eye(3), scene) == 0
+    assert (rt2.readPixels() != 255 << 8).sum() > 0
+    # removeMesh + rebuild -> empty scene -> all miss
+    scene.removeMesh(m); scene.updateGPUScene()
+    assert cam.traceScene([0, 0, -2.1], np.eye(3), scene) == 0
+    assert (rt2.readPixels() == 255 << 8).all()
+    assert rt2.unlock() == 0
+
+
+def test_reference_symbols_direct(meshes, golden, beam_lib, cuda_device):
+    """SceneTree.cpp's own call sequence on the reference's symbols, with torch-owned device memory and lazy build in bmMarch"""
+    import torch
+    from raytracercuda_b200 import _lib
+    from raytracercuda_b200.tree import make_mesh_table
+    L = beam_lib
+    P, I, N = meshes["suzanne"]
+    dev = cuda_device
+    Pd = torch.from_numpy(P).to(dev); Id = torch.from_numpy(I.view(np.int32)).to(dev).reshape(-1); Nd = torch.from_numpy(N).to(dev)
+    root = torch.zeros(L.bmGetNodeSize(), dtype=torch.uint8, device=dev)
+    assert [L.bmGetFaceSize(), L.bmGetFacePtrSize(), L.bmGetMaterialSize(), L.bmGetNodeSize(), L.bmGetFaceStoreSize(), L.bmGetNodeStoreSize(),
+            L.bmGetFaceGroupStoreSize()] == [golden["struct_sizes"][k] for k in ("bmFace", "bmFacePtr", "bmMaterial", "bmTreeNode", "bmFaceStore", "bmNodeStore", "bmFaceGroupStore")]
+    assert C.sizeof(_lib.bmStaticMeshData) == golden["struct_sizes"]["StaticMeshData"] == 136
+    L.bmResetScene(root.data_ptr(), None, None, None, None, None, None, 1 << 24, 1 << 24, 1 << 24)
+    lo, hi = _lib.bmVec3(-30, -30, -30), _lib.bmVec3(30, 30, 30)
+    L.bmInsertMeshInTree(Pd.data_ptr(), Id.data_ptr(), Id.numel(), 0, lo, hi, root.data_ptr(), None, None, None, None)
+    from raytracercuda_b200.host import ICamera
+    cam = ICamera.create(); cam.setInitialRays(200, 200, -1, 1, -1, 1, 1)
+    rays = torch.from_numpy(cam.initialRays()).to(dev)
+    table = make_mesh_table([(Pd, Id, Nd)], dev)
+    buf = torch.zeros(200 * 200, dtype=torch.int32, device=dev)
+    eye = _lib.bmVec3(0, 0, -2.1); orient = _lib.bmMat3((C.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1))
+    L.bmMarch(root.data_ptr(), C.byref(lo), C.byref(hi), rays.data_ptr(), buf.data_ptr(), 800, 200, 200, C.byref(eye), C.byref(orient), table.data_ptr())
+    torch.cuda.synchronize()
+    want = np.load(os.path.join(GOLDEN, "pixels_suzanne_200x200.npz"))["pixels"].reshape(-1)
+    assert np.array_equal(buf.cpu().numpy().view(np.uint32), want)
+    L.bmClear(buf.data_ptr(), 800, 200, 200, 7)
+    torch.cuda.synchronize()
+    assert (buf.cpu().numpy() == 7).all()
+    # an unknown root (nothing inserted) renders the miss colour
+    root2 = torch.zeros(32, dtype=torch.uint8, device=dev)
+    L.bmMarch(root2.data_ptr(), C.byref(lo), C.byref(hi), rays.data_ptr(), buf.data_ptr(), 800, 200, 200, C.byref(eye), C.byref(orient), table.data_ptr())
+    torch.cuda.synchronize()
+    assert (buf.cpu().numpy().view(np.uint32) == 255 << 8).all()
+
+
+def test_hash_keys_on_device(golden, beam_lib, cuda_device):
+    import torch
+    z = np.load(os.path.join(GOLDEN, "hashkeys.npz"))
+    pts = torch.from_numpy(z["pts"]).to(cuda_device)
+    h = torch.empty(pts.shape[0], dtype=torch.int32, device=cuda_device); c = torch.empty((pts.shape[0], 3), dtype=torch.int32, device=cuda_device)
+    assert beam_lib.bmHashKeys(pts.data_ptr(), pts.shape[0], h.data_ptr(), c.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(h.cpu().numpy().view(np.uint32), z["hash"]) and np.array_equal(c.cpu().numpy(), z["cells"])
+    xs = np.array([[x, 0.0, 0.0] for x, _ in golden["hash"]["bmMap"]], np.float32)
+    pts = torch.from_numpy(xs).to(cuda_device); c = torch.empty((xs.shape[0], 3), dtype=torch.int32, device=cuda_device)
+    assert beam_lib.bmHashKeys(pts.data_ptr(), xs.shape[0], None, c.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert list(c.cpu().numpy()[:, 0]) == [w for _, w in golden["hash"]["bmMap"]]

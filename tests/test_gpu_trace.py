@@ -1,0 +1,162 @@
+"""GPU tier: closest-hit traversal through the C ABI against the oracle on identical ray buffers.
+Bar: reference-mode triangle id equal on >= 99.99 % of rays (ties in t excluded), t within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, random_soup
+from oracle.bindings import OracleScene
+
+pytestmark = pytest.mark.gpu
+NT = os.cpu_count() or 1
+EYE = [0.0, 0.0, -2.1]
+ID3 = np.eye(3, dtype=np.float32)
+
+
+def _compare(h, r, bases, min_agree=0.9999, what=""):
+    """h: GPU hits dict; r: oracle dict.  Returns the agreement fraction."""
+    otri = np.where(r["tri"] == 0xFFFFFFFF, np.uint32(0xFFFFFFFF), bases[np.minimum(r["mesh"], len(bases) - 1)] + r["tri"]).astype(np.uint32)
+    considered = r["tie"] == 0
+    same = (h["tri"] == otri)
+    agree = same[considered].mean()
+    assert agree >= min_agree, f"{what}: triangle id agreement {agree:.6f}"
+    both = same & (otri != 0xFFFFFFFF)
+    rel = np.abs(h["t"][both] - r["t"][both]) / np.maximum(np.abs(r["t"][both]), 1e-20)
+    assert rel.size == 0 or rel.max() <= 1e-5, f"{what}: t differs by {rel.max():.3g} relative"
+    miss = same & (otri == 0xFFFFFFFF)
+    assert (h["t"][miss] == np.finfo(np.float32).max).all()
+    return agree, (rel.max() if rel.size else 0.0)
+
+
+@pytest.mark.parametrize("name,W,H", [("f16", 500, 500), ("suzanne", 320, 180), ("bunny", 640, 360)])
+def test_camera_reference_mode(name, W, H, meshes, golden, oracle_lib, beam_lib, cuda_device):
+    import torch
+    from raytracercuda_b200.tree import Tree, hits_to_numpy, make_mesh_table
+    P, I, N = meshes[name]
+    t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+    s = OracleScene(oracle_lib); s.add_mesh(P, I, N); s.build()
+    rays = oracle_lib.initial_rays(W, H)
+    r = s.trace_camera(rays, EYE, ID3, 0, NT)
+    Pd, Id = t._meshes[0]
+    Nd = torch.from_numpy(N).to(cuda_device)
+    table = make_mesh_table([(Pd, Id, Nd)], cuda_device)
+    px = torch.empty(W * H, dtype=torch.int32, device=cuda_device)
+    hits, cnt = t.trace_camera(rays, EYE, ID3, pixels=px, mesh_table=table, counters=True)
+    h = hits_to_numpy(hits)
+    agree, rel = _compare(h, r, t.mesh_bases(), what=name)
+    assert agree == 1.0 and rel == 0.0, "bundled meshes are expected to match the oracle bit for bit"
+    assert np.array_equal(h["u"][h["tri"] != 0xFFFFFFFF], r["u"][r["tri"] != 0xFFFFFFFF])
+    gp = px.cpu().numpy().view(np.uint32)
+    assert np.array_equal(gp, r["pixels"]), "shaded pixels differ"
+    res = "%dx%d" % (W, H)
+    if res in golden["meshes"][name]["trace"]:
+        assert int((gp != 255 << 8).sum()) == golden["meshes"][name]["trace"][res]["hits"]
+    c = cnt.cpu().numpy()
+    assert 0 < c[0] / (W * H) < r["node_visits"] / (W * H)        # fewer node visits than the reference's chain walk
+    t.close(); s.close()
+
+
+@pytest.mark.parametrize("name", ["f16", "suzanne", "bunny"])
+def test_reference_pixels_golden(name, meshes, beam_lib, cuda_device):
+    """against the unmodified reference's own pixels (tests/golden/pixels_*.npz)"""
+    import torch
+    from raytracercuda_b200.tree import Tree, make_mesh_table
+    P, I, N = meshes[name]
+    want = np.load(os.path.join(GOLDEN, "pixels_%s_200x200.npz" % name))["pixels"].reshape(-1)
+    t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+    Pd, Id = t._meshes[0]
+    table = make_mesh_table([(Pd, Id, torch.from_numpy(N).to(cuda_device))], cuda_device)
+    from raytracercuda_b200.host import ICamera
+    cam = ICamera.create(); assert cam.setInitialRays(200, 200, -1, 1, -1, 1, 1) == 0
+    px = torch.empty(200 * 200, dtype=torch.int32, device=cuda_device)
+    t.trace_camera(cam.initialRays(), EYE, ID3, want_hits=False, pixels=px, mesh_table=table)
+    assert np.array_equal(px.cpu().numpy().view(np.uint32), want)
+    t.close()
+
+
+def _ray_batch(rng, n, ext):
+    o = rng.uniform(-ext, ext, (n, 3)); d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    R = np.concatenate([o, d], 1).astype(np.float32)
+    R[::97, 3] = 0.0          # axis-parallel components: inf / NaN slab paths
+    R[::193, 4] = 0.0
+    return R
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_incoherent_rays_on_meshes(mode, meshes, oracle_lib, beam_lib, cuda_device):
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    rng = np.random.default_rng(11)
+    for name in ("suzanne", "bunny"):
+        P, I, N = meshes[name]
+        t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+        s = OracleScene(oracle_lib); s.add_mesh(P, I, N); s.build()
+        R = _ray_batch(rng, 60000, 2.5)          # origins inside and outside the model, incl. inside populated cells
+        r = s.trace_rays(R[:, :3], R[:, 3:], mode, NT)
+        h = hits_to_numpy(t.trace_rays(R, mode))
+        agree, rel = _compare(h, r, t.mesh_bases(), what=f"{name} mode {mode}")
+        if mode == 0:
+            assert (r["t"][r["tri"] != 0xFFFFFFFF] < 0).any(), "the batch should exercise the reference's negative-t hits"
+        t.close(); s.close()
+
+
+def test_incoherent_rays_on_soup(oracle_lib, beam_lib, cuda_device):
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    rng = np.random.default_rng(12)
+    P, I = random_soup(rng, 30000, 2.0, 0.15)
+    t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+    s = OracleScene(oracle_lib); s.add_mesh(P, I); s.build()
+    R = _ray_batch(rng, 50000, 2.2)
+    for mode in (0, 1):
+        r = s.trace_rays(R[:, :3], R[:, 3:], mode, NT)
+        h = hits_to_numpy(t.trace_rays(R, mode))
+        _compare(h, r, t.mesh_bases(), what=f"soup mode {mode}")
+        assert (r["tri"] != 0xFFFFFFFF).mean() > 0.3
+    t.close(); s.close()
+
+
+def test_reference_vs_exhaustive_closest(meshes, oracle_lib, beam_lib, cuda_device):
+    """report-style check: on the bundled meshes the reference's first-leaf answer is the true closest hit for >= 99.99 %"""
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    for name in ("suzanne", "bunny"):
+        P, I, N = meshes[name]
+        t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+        rays = oracle_lib.initial_rays(400, 400)
+        h0 = hits_to_numpy(t.trace_camera(rays, EYE, ID3, mode=0)[0]); h1 = hits_to_numpy(t.trace_camera(rays, EYE, ID3, mode=1)[0])
+        assert (h0["tri"] == h1["tri"]).mean() >= 0.9999
+        t.close()
+
+
+def test_edge_cases(oracle_lib, beam_lib, cuda_device):
+    import torch
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    rays = oracle_lib.initial_rays(16, 16)
+    # empty scene
+    t = Tree(cuda_device); t.build()
+    h = hits_to_numpy(t.trace_camera(rays, EYE, ID3)[0])
+    assert (h["tri"] == 0xFFFFFFFF).all() and (h["t"] == np.finfo(np.float32).max).all()
+    assert t.trace_rays(np.zeros((0, 6), np.float32)).shape[0] == 0
+    t.close()
+    # single leaf (root is a leaf) and the viewer's commented two-triangle scene (Program.cpp:153-185)
+    P = np.array([[-1, -1, 1.56], [0, 1, 1.56], [1, -1, 1.56], [2, 1, 1.56]], np.float32)
+    for I in (np.array([[0, 1, 2]], np.uint32), np.array([[0, 1, 2], [1, 2, 3]], np.uint32)):
+        t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+        s = OracleScene(oracle_lib); s.add_mesh(P, I); s.build()
+        r = s.trace_camera(oracle_lib.initial_rays(64, 64), EYE, ID3, 0)
+        h = hits_to_numpy(t.trace_camera(oracle_lib.initial_rays(64, 64), EYE, ID3)[0])
+        _compare(h, r, t.mesh_bases(), min_agree=1.0)
+        assert (h["tri"] != 0xFFFFFFFF).sum() > 100
+        t.close(); s.close()
+    # leaf cap: only the first 256 faces of a leaf are tested in reference mode
+    tri1 = np.array([[0.001, 0.001, 0.5], [0.02, 0.001, 0.5], [0.001, 0.02, 0.5]], np.float32)
+    Pc = np.tile(tri1, (300, 1)); Pc[3 * 299:, 2] = 0.49      # the 300th copy is nearer to the eye but beyond the cap
+    Ic = np.arange(900, dtype=np.uint32).reshape(-1, 3)
+    t = Tree(cuda_device); t.add_mesh(Pc, Ic); t.build()
+    s = OracleScene(oracle_lib); s.add_mesh(Pc, Ic); s.build()
+    R = np.array([[0.005, 0.005, -1, 0, 0, 1]], np.float32)
+    r = s.trace_rays(R[:, :3], R[:, 3:], 0)
+    h = hits_to_numpy(t.trace_rays(R, 0))
+    assert h["tri"][0] == r["tri"][0] == 0 and h["t"][0] == r["t"][0]
+    h1 = hits_to_numpy(t.trace_rays(R, 1))
+    assert h1["tri"][0] == 299
+    t.close(); s.close()

@@ -1,0 +1,111 @@
+"""CPU tier: the product's host+device inline arithmetic (csrc/bm_math.cuh, bm_sat.cuh, bm_grid_host.h) compiled for the
+CPU (tests/hostcheck) and checked against the oracle -- the same source the kernels execute."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, random_soup
+from oracle.bindings import OracleScene
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(ROOT, "tests", "hostcheck", "_hostcheck.so")
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
+    H = C.CDLL(so)
+    H.hc_pairs.argtypes = [f32p, u32p, C.c_uint32, f32p, f32p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    H.hc_pairs.restype = C.c_uint64
+    H.hc_grid.argtypes = [f32p, f32p, C.c_float, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
+    H.hc_encode.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]; H.hc_encode.restype = C.c_uint32
+    H.hc_decode.argtypes = [C.c_int, C.c_uint32, u32p]
+    H.hc_box_ray.argtypes = [f32p] * 4; H.hc_box_ray.restype = C.c_float
+    H.hc_tri_intersect.argtypes = [f32p] * 5 + [C.POINTER(C.c_float)] * 2; H.hc_tri_intersect.restype = C.c_float
+    H.hc_hash.argtypes = [C.c_uint32]; H.hc_hash.restype = C.c_uint32
+    H.hc_map.argtypes = [C.c_float]; H.hc_map.restype = C.c_int32
+    return H
+
+
+def _pairs(H, P, I, wmin=(-30, -30, -30), wmax=(30, 30, 30)):
+    I = np.ascontiguousarray(I, np.uint32).reshape(-1)
+    a = np.array(wmin, np.float32); b = np.array(wmax, np.float32); D = C.c_int(0)
+    n = H.hc_pairs(P, I, I.size // 3, a, b, 0.03, 38, None, None, 0, C.byref(D))
+    assert n != 2**64 - 1
+    code = np.zeros(n, np.uint32); tri = np.zeros(n, np.uint32)
+    H.hc_pairs(P, I, I.size // 3, a, b, 0.03, 38, code.ctypes.data, tri.ctypes.data, n, C.byref(D))
+    return code, tri, D.value
+
+
+@pytest.mark.parametrize("name", ["f16", "suzanne"])
+def test_descent_equals_oracle_on_meshes(name, hc, meshes, oracle_lib):
+    P, I, N = meshes[name]
+    s = OracleScene(oracle_lib); s.add_mesh(P, I); s.build()
+    oc, om, ot = s.pairs()
+    code, tri, D = _pairs(hc, P, I)
+    assert D == 31 and np.array_equal(code, oc) and np.array_equal(tri, ot)
+
+
+def test_descent_equals_oracle_on_soups(hc, oracle_lib):
+    rng = np.random.default_rng(1)
+    for n, ext, edge in ((8000, 29.0, 0.05), (200, 31.0, 1.5)):
+        P, I = random_soup(rng, n, ext, edge)
+        s = OracleScene(oracle_lib); s.add_mesh(P, I); s.build()
+        oc, om, ot = s.pairs()
+        code, tri, D = _pairs(hc, P, I)
+        assert np.array_equal(code, oc) and np.array_equal(tri, ot)
+
+
+def test_grid_default_world(hc):
+    k = (C.c_int * 3)(); D = C.c_int()
+    tx = np.zeros(2049, np.float32); ty = np.zeros(1025, np.float32); tz = np.zeros(1025, np.float32)
+    a = np.full(3, -30, np.float32); b = np.full(3, 30, np.float32)
+    assert hc.hc_grid(a, b, 0.03, 38, k, C.byref(D), tx.ctypes.data, ty.ctypes.data, tz.ctypes.data) == 1
+    assert list(k) == [11, 10, 10] and D.value == 31               # every leaf at depth 31, 2048x1024x1024 cells
+    assert np.array_equal(tx, (-30 + np.arange(2049) * (60.0 / 2048)).astype(np.float32))      # boundaries are exact floats
+    assert np.array_equal(ty, (-30 + np.arange(1025) * (60.0 / 1024)).astype(np.float32))
+    assert hc.hc_grid(np.full(3, -1000, np.float32), np.full(3, 1000, np.float32), 0.03, 38, k, C.byref(D), None, None, None) == 0
+
+
+def test_path_code_roundtrip(hc):
+    rng = np.random.default_rng(2)
+    out = np.zeros(3, np.uint32)
+    for depth in range(1, 33):
+        nb = [(depth + 2 - a) // 3 for a in range(3)]
+        for _ in range(50):
+            xyz = [int(rng.integers(0, 1 << nb[a])) if nb[a] else 0 for a in range(3)]
+            p = hc.hc_encode(depth, *xyz)
+            assert p < (1 << depth) if depth < 32 else True
+            hc.hc_decode(depth, p, out)
+            assert list(out) == xyz
+            # bit d of the path (MSB first) is bit of axis d%3, most significant first
+            bits = []
+            cnt = [0, 0, 0]
+            for d in range(depth):
+                a = d % 3
+                bits.append((xyz[a] >> (nb[a] - 1 - cnt[a])) & 1); cnt[a] += 1
+            assert p == int("".join(map(str, bits)), 2)
+
+
+def test_primitives_equal_golden(hc):
+    z = np.load(os.path.join(GOLDEN, "primitives.npz"))
+    u, v = C.c_float(), C.c_float()
+    for i in range(z["cen"].shape[0]):
+        t = hc.hc_tri_intersect(z["org"][i].copy(), z["dir"][i].copy(), z["tri"][i, 0].copy(), z["tri"][i, 1].copy(), z["tri"][i, 2].copy(), C.byref(u), C.byref(v))
+        assert np.float32(t).view(np.uint32) == z["t"][i].view(np.uint32)
+        with np.errstate(divide="ignore"):
+            iv = (np.float32(1) / z["dir"][i]).astype(np.float32)
+        b = hc.hc_box_ray((z["cen"][i] - z["half"][i]).astype(np.float32), (z["cen"][i] + z["half"][i]).astype(np.float32), z["org"][i].copy(), iv)
+        assert np.float32(b).view(np.uint32) == z["box"][i].view(np.uint32)
+
+
+def test_hash_keys(hc, golden):
+    for k, want in golden["hash"]["bmHash"]:
+        assert hc.hc_hash(k) == want
+    for x, want in golden["hash"]["bmMap"]:
+        assert hc.hc_map(x) == want
