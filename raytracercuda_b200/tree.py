@@ -152,4 +152,6 @@ def make_mesh_table(meshes, device) -> torch.Tensor:
             arr[i].m_vertexData[1] = N.data_ptr(); arr[i].m_vertexDataSizes[1] = 3
         arr[i].m_indices = I.data_ptr(); arr[i].m_numVertices = P.shape[0]; arr[i].m_numIndices = I.numel()
     raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
-    return torch.from_numpy(raw).to(device)
+    table = torch.from_numpy(raw).to(device)
+    table._beam_keepalive = list(meshes)      # the table holds raw device pointers: keep their owners alive with it
+    return table

@@ -30,15 +30,19 @@ def _oracle(oracle_lib, parts, **kw):
 
 def _check_tree_against_oracle(t, s, parts):
     st, so = t.stats(), s.stats()
-    assert st["pairs"] == so["pairs"] and st["leaves"] == so["leaves"]
+    assert st["leaves"] == so["leaves"]
     assert st["max_leaf_faces"] == so["max_leaf_faces"] and st["overflow_leaves"] == so["overflow_leaves"]
     code, tri = t.pairs()
     oc, om, ot = s.pairs()
     bases = t.mesh_bases()
-    # oracle lists (code, mesh, tri) capped at 256 per leaf; the GPU list is uncapped -> compare leaf by leaf when capped
-    if so["overflow_leaves"] == 0:
-        assert np.array_equal(code, oc), "leaf path codes differ"
-        assert np.array_equal(tri, bases[om] + ot), "sorted primitive order differs"
+    # the reference keeps at most 256 faces per leaf (BuildTree.cuh:17, BuildTree.cu:53-60) and so does the oracle's list;
+    # the GPU list keeps every pair (the cap is applied by the reference-mode trace) -> cap it the same way to compare
+    heads = np.flatnonzero(np.concatenate([[True], code[1:] != code[:-1]])) if code.size else np.zeros(0, np.int64)
+    rank = np.arange(code.size) - np.repeat(heads, np.diff(np.concatenate([heads, [code.size]])))
+    keep = rank < 256
+    assert (~keep).sum() == 0 or so["overflow_leaves"] > 0
+    assert np.array_equal(code[keep], oc), "leaf path codes differ"
+    assert np.array_equal(tri[keep], bases[om] + ot), "sorted primitive order differs"
     # sortedness by (code, global triangle id): the property the stable sort must deliver
     key = (code.astype(np.uint64) << np.uint64(32)) | tri.astype(np.uint64)
     assert (key[1:] > key[:-1]).all()
