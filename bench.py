@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the hot path (BASELINE.json metric: Mrays/s closest-hit (primary + diffuse) and BVH
+build Mtris/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
+
+One STEP = one frame of the workload through the C ABI: primary rays of this rank's camera (bmTraceCamera, reference
+semantics), one diffuse bounce generation (bmCameraRays + bmBounceRays) and its trace (bmTraceRays); at N > 1 the ranks render
+interleaved rows of an N-times taller image with a replicated tree (weak scaling) and all-gather the framebuffer (NCCL).
+`value` = rays traced by all ranks / device time of the step with every input resident in HBM; `e2e` = the same step fed
+from pinned HOST buffers (camera table H2D each step, framebuffer + bounce hits D2H each step).  The BVH build (soup resident
+-> tree traceable) is timed in the same run and reported under "build".  L2 is flushed between timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "Mrays/s closest-hit (primary + diffuse)"
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+NODE_BYTES, TRI_BYTES = 64, 48
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index; self.proc = None; self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False); self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            out["reasons"] = ["nvidia-smi unavailable"]; return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (the product has no CPU path)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from raytracercuda_b200 import build
+    if local == 0:
+        build.build_library()
+    if world > 1:
+        dist.barrier()
+    from raytracercuda_b200 import _lib, host, workloads
+    from raytracercuda_b200.tree import Tree, make_mesh_table
+    L = _lib.load()
+    wl = workloads.get(args.workload)
+    W, H = wl.width, wl.height
+    n = W * H
+    eye = wl.eye; orient = np.eye(3, dtype=np.float32)
+    frustum = workloads.interleaved_rows_frustum(wl.frustum, H, rank, world)
+
+    # --- scene + camera resident on the device -------------------------------------------------------------------------
+    cam = host.ICamera.create()
+    assert cam.setInitialRays(W, H, *frustum) == 0
+    rays_pinned = torch.from_numpy(cam.initialRays()).pin_memory()
+    rays_dev = rays_pinned.to(dev)
+    Pd = torch.from_numpy(wl.positions).to(dev); Id = torch.from_numpy(wl.indices.view(np.int32)).to(dev).reshape(-1); Nd = torch.from_numpy(wl.normals).to(dev)
+    table = make_mesh_table([(Pd, Id, Nd)], dev)
+    tree = Tree(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def build_once():
+        tree.reset(); tree.add_mesh(Pd, Id); tree.build()
+
+    build_once()
+    st = tree.stats()
+    hits1 = torch.empty((n, 4), dtype=torch.float32, device=dev); pixels = torch.empty(n, dtype=torch.int32, device=dev)
+    rays1 = torch.empty((n, 6), dtype=torch.float32, device=dev); rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    src2 = torch.empty(n, dtype=torch.int32, device=dev); cnt2 = torch.zeros(1, dtype=torch.int32, device=dev)
+    hits2 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world, n), dtype=torch.int32, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    pix_host = torch.empty(n, dtype=torch.int32).pin_memory(); hits2_host = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def frame(rays_in, marks=None):
+        """one step on the device; returns rays traced by this rank"""
+        if marks is not None: marks[0].record()
+        _lib.check(L.bmTraceCamera(tree.h, rays_in.data_ptr(), n, _f3(eye), _f9(orient), 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+        if marks is not None: marks[1].record()
+        total = n
+        if wl.bounces:
+            tree.camera_rays(rays_in, eye, orient, width=W, out=rays1)
+            tree.bounce_rays(rays1, hits1, sample=0, bounce=1, seed=args.seed, out=rays2, src=src2, count=cnt2)
+            cnt_host.copy_(cnt2, non_blocking=True)
+            stream.synchronize()
+            nb = int(cnt_host[0])
+            if marks is not None: marks[2].record()
+            _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), None), "bmTraceRays")
+            total += nb
+        if marks is not None: marks[3].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), pixels)
+        return total
+
+    import ctypes as C
+    _f3 = lambda a: (C.c_float * 3)(*[float(x) for x in a])
+    _f9 = lambda a: (C.c_float * 9)(*[float(x) for x in np.asarray(a, np.float32).reshape(-1)])
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # --- warm-up -------------------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        rays_step = frame(rays_dev)
+    # per-ray traversal counters of the same traversal (instrumented launch, outside the timed region)
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
+    torch.cuda.synchronize(dev)
+    V1, K1 = [int(x) for x in cnt.cpu()]
+    nb = int(cnt_host[0]) if wl.bounces else 0
+    V2 = K2 = 0
+    if nb:
+        cnt.zero_()
+        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+        torch.cuda.synchronize(dev)
+        V2, K2 = [int(x) for x in cnt.cpu()]
+
+    # --- timed: K steps, device resident, L2 flushed between steps --------------------------------------------------------
+    sampler = ClockSampler(local)
+    launches0 = L.bmLaunchCount()
+    sync_all()
+    sampler.start()
+    step_ms, prim_ms, bounce_ms = [], [], []
+    total_rays = 0
+    for _ in range(args.steps):
+        flush.zero_()
+        marks = [ev() for _ in range(4)]; e0, e1 = ev(), ev()
+        sync_all()
+        e0.record()
+        total_rays += frame(rays_dev, marks)
+        e1.record()
+        sync_all()
+        step_ms.append(e0.elapsed_time(e1)); prim_ms.append(marks[0].elapsed_time(marks[1]))
+        bounce_ms.append(marks[2].elapsed_time(marks[3]) if wl.bounces else 0.0)
+    clocks = sampler.stop()
+    launches = L.bmLaunchCount() - launches0
+    # max over ranks of the summed step time; rays summed over ranks
+    t_sum = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev); r_sum = torch.tensor([float(total_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_sum, op=dist.ReduceOp.MAX); dist.all_reduce(r_sum, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t_sum.item()) / args.steps
+    value = float(r_sum.item()) / args.steps / (ms_per_step * 1e-3) / 1e6
+
+    # --- timed: e2e through host buffers ---------------------------------------------------------------------------------
+    def frame_e2e():
+        r = rays_dev.copy_(rays_pinned, non_blocking=True)
+        total = frame(r)
+        pix_host.copy_(pixels, non_blocking=True)
+        if wl.bounces:
+            hits2_host[: int(cnt_host[0])].copy_(hits2[: int(cnt_host[0])], non_blocking=True)
+        stream.synchronize()
+        return total
+    for _ in range(2):
+        frame_e2e()
+    e2e_ms, e2e_rays = [], 0
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = ev(), ev()
+        sync_all()
+        e0.record(); e2e_rays += frame_e2e(); e1.record()
+        sync_all()
+        e2e_ms.append(e0.elapsed_time(e1))
+    t2 = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev); r2 = torch.tensor([float(e2e_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
+    e2e_value = float(r2.item()) / (float(t2.item()) * 1e-3) / 1e6
+    h2d = n * 12 + 48
+    d2h = n * 4 + (nb * 16 if wl.bounces else 0) + (4 if wl.bounces else 0)
+
+    # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
+    build_ms = []
+    for i in range(2 + args.steps):
+        flush.zero_()
+        e0, e1 = ev(), ev()
+        torch.cuda.synchronize(dev)
+        e0.record(); build_once(); e1.record()
+        torch.cuda.synchronize(dev)
+        if i >= 2:
+            build_ms.append(e0.elapsed_time(e1))
+    bms = statistics.mean(build_ms)
+    peak, peak_src = measured_peaks()
+    build_bytes = 48 * st["triangles"] + 8 * st["pairs"] + NODE_BYTES * st["nodes"]
+    build = {"metric": "BVH build Mtris/s", "value": st["triangles"] / (bms * 1e-3) / 1e6, "unit": "Mtris/s", "ms": bms,
+             "triangles": st["triangles"], "pairs": st["pairs"], "leaves": st["leaves"], "nodes": st["nodes"],
+             "roofline": {"bound": "hbm", "achieved": build_bytes / (bms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": build_bytes / (bms * 1e-3) / 1e9 / peak, "traffic": None,
+                          "algorithmic_bytes": build_bytes, "note": "48 B/tri + 8 B/pair + 64 B/node over the whole build (SURVEY 8d); " + peak_src},
+             "replication": "every rank builds its own replica" if world > 1 else "single GPU"}
+
+    # --- roofline of the dominant kernel: the primary-ray trace launch ---------------------------------------------------
+    pms = statistics.mean(prim_ms)
+    prim_bytes = n * (12 + 16 + 4) + NODE_BYTES * V1 + TRI_BYTES * K1
+    roofline = {"bound": "hbm", "kernel": "trace_kernel<camera> (bmTraceCamera, reference semantics)", "achieved": prim_bytes / (pms * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": prim_bytes / (pms * 1e-3) / 1e9 / peak, "traffic": None,
+                "ms_per_launch": pms, "mrays_per_s": n / (pms * 1e-3) / 1e6,
+                "bytes_per_ray": prim_bytes / n, "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n,
+                "note": "algorithmic bytes = 12 B ray + 16 B hit + 4 B pixel + 64 B x node visits + 48 B x triangle tests (counters of the same traversal); "
+                        + peak_src + "; the tree (~%.0f MB) is L2-resident on B200, so this kernel is latency/issue-bound, not HBM-bound (SURVEY 8d)" %
+                        ((st["nodes"] * 64 + st["pairs"] * 48 + st["leaves"] * 16) / 1e6)}
+    if wl.bounces and nb:
+        bms2 = statistics.mean(bounce_ms)
+        roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb / (bms2 * 1e-3) / 1e6, "rays": nb,
+                                     "node_visits_per_ray": V2 / nb, "tri_tests_per_ray": K2 / nb,
+                                     "achieved": (nb * (24 + 16) + NODE_BYTES * V2 + TRI_BYTES * K2) / (bms2 * 1e-3) / 1e9}
+
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "rays_per_step_per_gpu": rays_step, "primary_rays_per_gpu": n, "bounce_rays_per_gpu": nb,
+                       "trace_mode": "reference semantics (BM_TRACE_REFERENCE)", "l2": "flushed between timed steps (256 MiB write)",
+                       "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer" if world > 1 else "single GPU",
+                       "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl, rays_pinned.numpy(), rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def _oracle_scene(wl):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_build/liboracle.so"], stdout=subprocess.DEVNULL)
+    from oracle.bindings import OracleLib, OracleScene
+    O = OracleLib()
+    s = OracleScene(O); s.add_mesh(wl.positions, wl.indices, wl.normals)
+    return O, s
+
+
+def cpu_baseline(wl, initial_rays, bounce_rays, bounce_src, budget_rays=400_000):
+    """The CPU restatement of the reference path (oracle/oracle.cpp, kind "port") on the host cores, on a bounded sample of
+    the same workload: the whole BVH build, then a strided sample of the primary rays plus the bounce rays they spawned."""
+    cores = os.cpu_count() or 1
+    O, s = _oracle_scene(wl)
+    tb = s.build()
+    n = initial_rays.shape[0]
+    stride = max(1, n // budget_rays)
+    sel = np.arange(0, n, stride)
+    r = s.trace_camera(initial_rays[sel], wl.eye, np.eye(3, dtype=np.float32), 0, cores)
+    rays, secs = sel.size, r["seconds"]
+    if bounce_rays is not None and bounce_rays.shape[0]:
+        keep = (bounce_src % stride) == 0
+        B = np.ascontiguousarray(bounce_rays[keep])
+        if B.shape[0]:
+            r2 = s.trace_rays(B[:, :3], B[:, 3:], 0, cores)
+            rays += B.shape[0]; secs += r2["seconds"]
+    s.close()
+    return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+            "sample": "every %d-th primary ray (%d) + the bounce rays they spawned, %d rays total, %d threads over rays; tree built on 1 thread" % (stride, sel.size, rays, cores),
+            "build": {"value": wl.num_tris / tb / 1e6, "unit": "Mtris/s", "cores": 1, "seconds": tb}}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (its serial host-emulation algorithm as restated in
+    oracle/oracle.cpp, validated bit-for-bit against the unmodified reference build oracle/_ref) on all host threads.
+    Each step = a bounded sample of the workload's frame (strided primaries + a diffuse bounce for every hit)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from raytracercuda_b200 import workloads
+    wl = workloads.get(args.workload)
+    cores = os.cpu_count() or 1
+    O, s = _oracle_scene(wl)
+    tb = s.build()
+    n = wl.width * wl.height
+    stride = max(1, n // args.reference_rays)
+    rays = O.initial_rays(wl.width, wl.height, wl.frustum)[::stride]
+    rng = np.random.default_rng(args.seed)
+    eye = np.asarray(wl.eye, np.float32)
+
+    def step():
+        r = s.trace_camera(rays, wl.eye, np.eye(3, dtype=np.float32), 0, cores)
+        total, secs = rays.shape[0], r["seconds"]
+        if wl.bounces:
+            hit = r["tri"] != 0xFFFFFFFF
+            if hit.any():
+                # host-side bounce rays with the same construction (hit + 1e-4 n, cosine-weighted about the geometric normal)
+                d = rays[hit]; t = r["t"][hit]
+                tri = wl.indices[r["tri"][hit]]
+                p0, p1, p2 = wl.positions[tri[:, 0]], wl.positions[tri[:, 1]], wl.positions[tri[:, 2]]
+                nrm = np.cross(p1 - p0, p2 - p0); nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+                nrm = np.where((nrm * d).sum(1, keepdims=True) > 0, -nrm, nrm)
+                hp = eye + t[:, None] * d
+                u1, u2 = rng.random(t.size), rng.random(t.size)
+                rr, phi = np.sqrt(u1), 2 * np.pi * u2
+                a = np.where(np.abs(nrm[:, :1]) > 0.9, np.array([[0, 1, 0]]), np.array([[1, 0, 0]]))
+                t1 = np.cross(nrm, a); t1 /= np.linalg.norm(t1, axis=1, keepdims=True); t2 = np.cross(nrm, t1)
+                nd = t1 * (rr * np.cos(phi))[:, None] + t2 * (rr * np.sin(phi))[:, None] + nrm * np.sqrt(np.maximum(0, 1 - u1))[:, None]
+                r2 = s.trace_rays((hp + 1e-4 * nrm).astype(np.float32), nd.astype(np.float32), 0, cores)
+                total += t.size; secs += r2["seconds"]
+        return total, secs
+
+    for _ in range(args.warmup):
+        step()
+    tot, sec = 0, 0.0
+    for _ in range(args.steps):
+        a, b = step(); tot += a; sec += b
+    value = tot / sec / 1e6
+    sample = "every %d-th primary ray (%d) + one diffuse bounce per hit, per step; %d threads over rays" % (stride, rays.shape[0], cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "rays_per_step": tot // args.steps, "trace_mode": "reference semantics"},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu": cpu_model(), "sample": sample,
+                             "build": {"value": wl.num_tris / tb / 1e6, "unit": "Mtris/s", "cores": 1, "seconds": tb}},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    s.close()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-rays", type=int, default=200_000, help="primary rays per step of the --impl reference sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

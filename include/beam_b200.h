@@ -109,6 +109,7 @@ enum {
 };
 
 const char* bmLastErrorString(void);
+uint64_t bmLaunchCount(void);          /* kernels launched by this library so far in this process */
 
 /* World box, leaf size and depth cap default to SceneTree.cpp:43-45 and BuildTree.cuh:14-18 when null / 0. */
 int  bmTreeCreate(bmTree** out, const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth);
@@ -139,6 +140,18 @@ int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, 
 /* Camera rays (dir = orient * initialRays[i] from eye), hit records and/or shaded pixels (either may be null). */
 int  bmTraceCamera(bmTree* tree, const float* d_initialRays3, uint64_t numRays, const float* eye3, const float* orient9,
                    int mode, bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters);
+
+/* Ray-batch producers for the multi-sample / bounce workloads (defined by this repo; the reference has no secondary rays,
+ * SURVEY.md section 8d).  bmCameraRays writes the camera's rays as bmRay records; sample == 0xFFFFFFFF means the exact
+ * pixel-centre table entry (identical to what bmMarch traces), otherwise the direction is jittered inside the pixel
+ * (jitterX/Y = pixel size in units of zoom) by a counter-based hash of (ray, sample, seed).
+ * bmBounceRays writes one cosine-weighted diffuse bounce ray per hit (origin = hit + 1e-4 n, geometric normal n facing the
+ * incoming ray), compacted in ray order; d_srcIndex (nullable) receives the index of the primary ray of each bounce ray and
+ * *d_count (device uint32) the number of bounce rays.  d_out / d_srcIndex need room for numRays entries. */
+int  bmCameraRays(const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                  float jitterX, float jitterY, uint32_t sample, uint32_t seed, bmRay* d_out, void* cudaStream);
+int  bmBounceRays(bmTree* tree, const bmRay* d_rays, const bmHit* d_hits, uint64_t numRays, uint32_t sample, uint32_t bounce,
+                  uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count);
 
 /* Spatial-hash key functions of Hash.cu:17-64 evaluated on the device (bit-exact targets):
  * out[i] = bmHash3(make_uint3(bmMap(x), bmMap(y), bmMap(z))) and the three bmMap cell coordinates. */

@@ -18,9 +18,9 @@ ERROR_NAMES = {0: "ERROR_ALL_FINE", 1: "ERROR_NO_VERTICES", 2: "ERROR_INVALID_PA
 ABI_SYMBOLS = [
     "bmResetScene", "bmInsertMeshInTree", "bmMarch", "bmGetFaceSize", "bmGetFacePtrSize", "bmGetMaterialSize", "bmGetNodeSize",
     "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
-    "bmLastErrorString", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
+    "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
     "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases",
-    "bmTraceRays", "bmTraceCamera", "bmHashKeys",
+    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
     "beamMeshCreate", "beamMeshDestroy", "beamMeshSetVertexData", "beamMeshSetIndices",
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
     L = C.CDLL(LIB_PATH)
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.bmLastErrorString.restype = C.c_char_p
+    L.bmLaunchCount.restype = u64
     L.bmTreeCreate.argtypes = [C.POINTER(vp), vp, vp, C.c_float, u32]
     L.bmTreeDestroy.argtypes = [vp]; L.bmTreeDestroy.restype = None
     L.bmTreeSetStream.argtypes = [vp, vp]
@@ -76,6 +77,8 @@ def load() -> C.CDLL:
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]
     L.bmTraceCamera.argtypes = [vp, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
     L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]
+    L.bmCameraRays.argtypes = [vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, u32, u32, vp, vp]
+    L.bmBounceRays.argtypes = [vp, vp, vp, u64, u32, u32, u32, vp, vp, vp]
     L.bmResetScene.argtypes = [vp] * 7 + [u32] * 3; L.bmResetScene.restype = None
     L.bmInsertMeshInTree.argtypes = [vp, vp, u32, u32, bmVec3, bmVec3, vp, vp, vp, vp, vp]; L.bmInsertMeshInTree.restype = None
     L.bmMarch.argtypes = [vp, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, u32, u32, u32, C.POINTER(bmVec3), C.POINTER(bmMat3), vp]

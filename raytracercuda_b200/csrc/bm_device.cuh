@@ -13,6 +13,9 @@ namespace bm
 void set_error(const std::string& s);
 const char* last_error();
 #define BM_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ::bm::set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); return BM_ERROR_CUDA; } } while (0)
+// after every kernel launch: count it (bmLaunchCount, the bench's gpu_launches evidence) and surface launch errors
+extern unsigned long long g_launches;
+#define BM_LAUNCHED() do { ++::bm::g_launches; BM_CUDA(cudaGetLastError()); } while (0)
 #define BM_TRY(expr) do { int r_ = (expr); if (r_ != BM_OK) return r_; } while (0)
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -72,5 +75,10 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* 
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
                  u64* d_counters, cudaStream_t s);
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
+
+// ---- rays.cu --------------------------------------------------------------------------------------------------------
+int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* d_out, cudaStream_t s);
+int bounce_rays(const bmRay* d_rays, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed, u32* d_flagsAndOffsets,
+                void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s);
 int hash_keys(const float* d_points3, u64 n, u32* d_hash, i32* d_cells3, cudaStream_t s);
 } // namespace bm

@@ -159,35 +159,35 @@ int mark_heads(const u32* d_keys, size_t n, u32* d_flags, cudaStream_t s)
 {
     if (!n) return BM_OK;
     mark_heads_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, n, d_flags);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 int write_leaves(const u32* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, uint4* d_leaves, cudaStream_t s)
 {
     if (!n) return BM_OK;
     write_leaves_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, d_flags, d_leafIdx, n, numLeaves, d_leaves);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_ltris, cudaStream_t s)
 {
     if (!n) return BM_OK;
     pack_leaf_tris_kernel<<<div_up(n, 256), 256, 0, s>>>(d_soup, d_vals, n, d_ltris);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 int leaf_bounds(const uint4* d_leaves, u32 numLeaves, const float4* d_ltris, float* d_leafBox6, float pad, u32* d_stats, cudaStream_t s)
 {
     if (!numLeaves) return BM_OK;
     leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_ltris, d_leafBox6, pad, d_stats);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 int emit_hierarchy(const uint4* d_leaves, u32 numLeaves, int D, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s)
 {
     if (numLeaves < 2) return BM_OK;
     karras_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(d_leaves, numLeaves, D, d_nodes, d_parentOfNode, d_parentOfLeaf);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit,
@@ -196,7 +196,7 @@ int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* 
     if (numLeaves < 2) return BM_OK;
     BM_CUDA(cudaMemsetAsync(d_visit, 0, (size_t)(numLeaves - 1) * 4, s));
     refit_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(numLeaves, d_leafBox6, d_nodeBox6, d_parentOfNode, d_parentOfLeaf, d_visit, d_nodes);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 } // namespace bm

@@ -61,21 +61,21 @@ int gather_mesh(const float* d_pos, const u32* d_idx, u32 numTris, u32 meshIdx, 
 {
     if (!numTris) return BM_OK;
     gather_kernel<<<div_up(numTris, 256), 256, 0, s>>>(d_pos, d_idx, numTris, meshIdx, base, d_soup);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 int count_pairs(const Grid& g, const float4* d_soup, u32 numTris, u32* d_counts, cudaStream_t s)
 {
     if (!numTris) return BM_OK;
     count_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, d_counts);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 int emit_pairs(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, u32* d_keys, u32* d_vals, cudaStream_t s)
 {
     if (!numTris) return BM_OK;
     emit_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, d_offsets, d_keys, d_vals);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 } // namespace bm

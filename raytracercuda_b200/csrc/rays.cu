@@ -1,0 +1,110 @@
+// rays.cu -- ray-batch producers for the workloads the reference only names (SURVEY.md section 8d "Secondary / spp rays"):
+//   * camera_rays: materialise bmRay{o,d} records from the camera's direction table (optionally jittered inside the pixel
+//     for sample s of a multi-sample frame);
+//   * bounce_rays: one diffuse bounce ray per primary hit: origin = hit + 1e-4*n, direction cosine-weighted about the
+//     geometric normal n (flipped towards the incoming ray's origin), RNG = counter-based hash of (ray index, sample,
+//     bounce, seed).  Hits are compacted in ray order (flag -> exclusive scan -> scatter), so the output order is
+//     deterministic; srcIndex maps each bounce ray back to its primary ray.
+// Parity for these rays is judged on identical ray buffers (the oracle traces the buffer the GPU produced), so the
+// sin/cos/sqrt used here need not be bit-compatible with any host implementation.
+#include "bm_device.cuh"
+
+namespace bm
+{
+namespace
+{
+__device__ __forceinline__ u32 pcg_hash(u32 v)
+{
+    u32 state = v * 747796405u + 2891336453u;
+    u32 word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ float u01(u32 h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
+
+__global__ void camera_rays_kernel(CameraIn cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* __restrict__ out)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = cam.initialRays + 3 * i;
+    float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
+    if (sample != 0xFFFFFFFFu)
+    {
+        // jitter inside the pixel: the table stores unit vectors (rx,ry,zoom)*d; perturb in the image plane and renormalise
+        u32 h = pcg_hash((u32)i ^ pcg_hash(sample * 0x9E3779B9u + seed));
+        float jx = (u01(h) - .5f) * jitterX, jy = (u01(pcg_hash(h)) - .5f) * jitterY;
+        float s = 1.f / z;                       // z = zoom*d > 0
+        float px = x * s + jx, py = y * s + jy;  // in units of zoom
+        float inv = rsqrtf(1.f + px * px + py * py);
+        x = px * inv; y = py * inv; z = inv;
+    }
+    const float* m = cam.orient;
+    bmRay o;
+    o.o[0] = cam.eye[0]; o.o[1] = cam.eye[1]; o.o[2] = cam.eye[2];
+    o.d[0] = m[0] * x + m[3] * y + m[6] * z; o.d[1] = m[1] * x + m[4] * y + m[7] * z; o.d[2] = m[2] * x + m[5] * y + m[8] * z;
+    out[i] = o;
+}
+
+__global__ void hit_flags_kernel(const bmHit* __restrict__ hits, u64 n, u32* __restrict__ flags)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = hits[i].tri != 0xFFFFFFFFu ? 1u : 0u;
+}
+
+__global__ void bounce_kernel(const bmRay* __restrict__ rays, const bmHit* __restrict__ hits, const u32* __restrict__ offsets, u64 n,
+                              const float4* __restrict__ soup, u32 sample, u32 bounce, u32 seed, bmRay* __restrict__ out, u32* __restrict__ srcIndex)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 hf = reinterpret_cast<const float4*>(hits)[i];
+    u32 tri = __float_as_uint(hf.w);
+    if (tri == 0xFFFFFFFFu) return;
+    bmRay r = rays[i];
+    const float4* p = soup + 3 * (size_t)tri;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    V3 e1 = mk3(b.x - a.x, b.y - a.y, b.z - a.z), e2 = mk3(c.x - a.x, c.y - a.y, c.z - a.z);
+    V3 nrm = cross3(e1, e2);
+    float len2 = dot3(nrm, nrm);
+    nrm = len2 > 0.f ? nrm * rsqrtf(len2) : mk3(0.f, 0.f, 1.f);
+    V3 d = mk3(r.d[0], r.d[1], r.d[2]);
+    if (dot3(nrm, d) > 0.f) nrm = nrm * -1.f;                 // face the side the ray came from
+    float t = hf.x;
+    V3 hp = mk3(r.o[0] + t * d.x, r.o[1] + t * d.y, r.o[2] + t * d.z);
+    u32 h = pcg_hash((u32)i ^ pcg_hash(seed ^ pcg_hash(sample * 0x9E3779B9u + bounce * 0x85EBCA6Bu)));
+    float u1 = u01(h), u2 = u01(pcg_hash(h ^ 0xB5297A4Du));
+    float rr = sqrtf(u1), phi = 6.28318530718f * u2;
+    float lx = rr * cosf(phi), ly = rr * sinf(phi), lz = sqrtf(fmaxf(0.f, 1.f - u1));
+    // branchless orthonormal basis (Duff et al. 2017)
+    float sgn = copysignf(1.f, nrm.z);
+    float aa = -1.f / (sgn + nrm.z), bb = nrm.x * nrm.y * aa;
+    V3 t1 = mk3(1.f + sgn * nrm.x * nrm.x * aa, sgn * bb, -sgn * nrm.x), t2 = mk3(bb, sgn + nrm.y * nrm.y * aa, -nrm.y);
+    V3 nd = mk3(t1.x * lx + t2.x * ly + nrm.x * lz, t1.y * lx + t2.y * ly + nrm.y * lz, t1.z * lx + t2.z * ly + nrm.z * lz);
+    bmRay o;
+    o.o[0] = hp.x + 1e-4f * nrm.x; o.o[1] = hp.y + 1e-4f * nrm.y; o.o[2] = hp.z + 1e-4f * nrm.z;
+    o.d[0] = nd.x; o.d[1] = nd.y; o.d[2] = nd.z;
+    u32 k = offsets[i];
+    out[k] = o;
+    if (srcIndex) srcIndex[k] = (u32)i;
+}
+} // namespace
+
+int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* d_out, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    camera_rays_kernel<<<div_up(n, 256), 256, 0, s>>>(cam, n, width, jitterX, jitterY, sample, seed, d_out);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+
+int bounce_rays(const bmRay* d_rays, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed, u32* d_flagsAndOffsets,
+                void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s)
+{
+    if (!n) { BM_CUDA(cudaMemsetAsync(d_count, 0, 4, s)); return BM_OK; }
+    hit_flags_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits, n, d_flagsAndOffsets);
+    BM_LAUNCHED();
+    BM_TRY(exclusive_scan_u32(d_flagsAndOffsets, d_flagsAndOffsets, n, d_count, d_scanTemp, s));
+    bounce_kernel<<<div_up(n, 256), 256, 0, s>>>(d_rays, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+} // namespace bm

@@ -92,17 +92,17 @@ int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void
     if (tiles == 1)
     {
         tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, n, nullptr, d_total);
-        BM_CUDA(cudaGetLastError());
+        BM_LAUNCHED();
         return BM_OK;
     }
     u32* sums = (u32*)d_temp;
     void* next = (char*)d_temp + ((tiles * 4 + 255) / 256) * 256;
     tile_sums_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, n, sums);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     BM_TRY(exclusive_scan_u32(sums, sums, tiles, d_total, next, s));
     // when d_total is requested the recursion wrote it (sum of tile sums == grand total)
     tile_scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, n, sums, nullptr);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 } // namespace bm

@@ -156,10 +156,10 @@ int radix_sort_pairs(u32* d_keysA, u32* d_valsA, u32* d_keysB, u32* d_valsB, siz
     {
         int shift = 8 * p;
         radix_hist_kernel<<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, n, shift, (u32)tiles, counts);
-        BM_CUDA(cudaGetLastError());
+        BM_LAUNCHED();
         BM_TRY(exclusive_scan_u32(counts, counts, tiles * RS_BINS, nullptr, scanTemp, s));
         radix_scatter_kernel<<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, (u32)tiles, counts);
-        BM_CUDA(cudaGetLastError());
+        BM_LAUNCHED();
         u32* t;
         t = ka; ka = kb; kb = t;
         t = va; va = vb; vb = t;

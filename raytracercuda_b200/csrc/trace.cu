@@ -231,7 +231,7 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* 
     if (!n) return BM_OK;
     CameraIn cam = {};
     trace_kernel<false><<<trace_grid(n), TR_THREADS, 0, s>>>(tv, d_rays, cam, n, mode, d_hits, nullptr, nullptr, d_counters);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 
@@ -240,7 +240,7 @@ int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, int mode, bmHit
 {
     if (!n) return BM_OK;
     trace_kernel<true><<<trace_grid(n), TR_THREADS, 0, s>>>(tv, nullptr, cam, n, mode, d_hits, d_pixels, d_meshData, d_counters);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 
@@ -250,7 +250,7 @@ int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s)
     unsigned blocks = div_up(n, 256);
     unsigned cap = (unsigned)sm_count() * 8;
     clear_kernel<<<blocks < cap ? blocks : cap, 256, 0, s>>>(d_buf, n, value);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 
@@ -258,7 +258,7 @@ int hash_keys(const float* d_points3, u64 n, u32* d_hash, i32* d_cells3, cudaStr
 {
     if (!n) return BM_OK;
     hash_kernel<<<div_up(n, 256), 256, 0, s>>>(d_points3, n, d_hash, d_cells3);
-    BM_CUDA(cudaGetLastError());
+    BM_LAUNCHED();
     return BM_OK;
 }
 } // namespace bm

@@ -11,6 +11,7 @@
 
 namespace bm
 {
+unsigned long long g_launches = 0;
 static thread_local std::string g_error;
 void set_error(const std::string& s) { g_error = s; }
 const char* last_error() { return g_error.c_str(); }
@@ -59,7 +60,7 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp;
     u32* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
     u32 maxLeaf = 0, overLeaves = 0;
@@ -74,7 +75,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -157,6 +158,7 @@ static int tree_finish_stats(bmTree* t)
 
 // ---- Part 2 -------------------------------------------------------------------------------------------------------------
 extern "C" const char* bmLastErrorString(void) { return bm::last_error(); }
+extern "C" uint64_t bmLaunchCount(void) { return bm::g_launches; }
 
 extern "C" int bmTreeCreate(bmTree** out, const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth)
 {
@@ -277,6 +279,26 @@ extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t nu
     CameraIn cam; cam.initialRays = d_initialRays3;
     memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
     return trace_camera(t->view(), cam, numRays, mode, d_hits, d_pixels, d_meshData, d_counters, t->stream);
+}
+
+extern "C" int bmCameraRays(const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                            float jitterX, float jitterY, uint32_t sample, uint32_t seed, bmRay* d_out, void* stream)
+{
+    if ((!d_initialRays3 || !d_out) && numRays) return BM_ERROR_INVALID_PARAMETER;
+    if (!eye3 || !orient9) return BM_ERROR_INVALID_PARAMETER;
+    CameraIn cam; cam.initialRays = d_initialRays3;
+    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
+    return camera_rays(cam, numRays, width, jitterX, jitterY, sample, seed, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int bmBounceRays(bmTree* t, const bmRay* d_rays, const bmHit* d_hits, uint64_t numRays, uint32_t sample, uint32_t bounce, uint32_t seed,
+                            bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count)
+{
+    if (!t || !d_count || ((!d_rays || !d_hits || !d_out) && numRays) || numRays >= 0xFFFFFFFFull) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    BM_TRY(t->rayFlags.reserve(numRays * 4 + 4));
+    BM_TRY(t->rayTemp.reserve(scan_temp_bytes(numRays)));
+    return bounce_rays(d_rays, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
 }
 
 extern "C" int bmHashKeys(const float* d_points3, uint64_t n, uint32_t* d_hash, int32_t* d_cells3, void* stream)

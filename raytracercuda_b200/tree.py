@@ -103,10 +103,10 @@ class Tree:
         self.stream.synchronize()
         return b.cpu().numpy()
 
-    def trace_rays(self, rays, mode=BM_TRACE_REFERENCE, counters=False, hits_out=None):
+    def trace_rays(self, rays, mode=BM_TRACE_REFERENCE, counters=False, hits_out=None, num=None):
         """rays: (n,6) float32 (origin, direction) = bmRay records. Returns the (n,4) hit tensor [t,u,v,tri-bits] on the device."""
         R = _dev_tensor(rays, torch.float32, self.device).reshape(-1, 6)
-        n = R.shape[0]
+        n = R.shape[0] if num is None else int(num)
         hits = hits_out if hits_out is not None else torch.empty((n, 4), dtype=torch.float32, device=self.device)
         cnt = torch.zeros(2, dtype=torch.int64, device=self.device) if counters else None
         check(self.L.bmTraceRays(self.h, R.data_ptr(), n, int(mode), hits.data_ptr(), None if cnt is None else cnt.data_ptr()), "bmTraceRays")
@@ -123,6 +123,26 @@ class Tree:
                                    None if pixels is None else pixels.data_ptr(), None if mesh_table is None else mesh_table.data_ptr(),
                                    None if cnt is None else cnt.data_ptr()), "bmTraceCamera")
         return hits, cnt
+
+    def camera_rays(self, initial_rays_dev: torch.Tensor, eye, orient, width=0, jitter=(0.0, 0.0), sample=0xFFFFFFFF, seed=0, out=None):
+        """bmCameraRays: (n,6) bmRay records for the camera table (device tensor (n,3))"""
+        n = initial_rays_dev.shape[0]
+        out = out if out is not None else torch.empty((n, 6), dtype=torch.float32, device=self.device)
+        e = (C.c_float * 3)(*[float(x) for x in eye])
+        o = (C.c_float * 9)(*[float(x) for x in np.asarray(orient, np.float32).reshape(-1)])
+        check(self.L.bmCameraRays(initial_rays_dev.data_ptr(), n, int(width), e, o, float(jitter[0]), float(jitter[1]), int(sample), int(seed),
+                                  out.data_ptr(), C.c_void_p(self.stream.cuda_stream)), "bmCameraRays")
+        return out
+
+    def bounce_rays(self, rays: torch.Tensor, hits: torch.Tensor, sample=0, bounce=1, seed=0, out=None, src=None, count=None):
+        """bmBounceRays: compacted diffuse bounce rays for the hits; returns (rays_out, src_index, count tensor (device int32[1]))"""
+        n = rays.shape[0]
+        out = out if out is not None else torch.empty((n, 6), dtype=torch.float32, device=self.device)
+        src = src if src is not None else torch.empty(n, dtype=torch.int32, device=self.device)
+        count = count if count is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(self.L.bmBounceRays(self.h, rays.data_ptr(), hits.data_ptr(), n, int(sample), int(bounce), int(seed), out.data_ptr(), src.data_ptr(),
+                                  count.data_ptr()), "bmBounceRays")
+        return out, src, count
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:

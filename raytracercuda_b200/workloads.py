@@ -1,0 +1,63 @@
+"""Bench / test workloads = BASELINE.json `configs`, with the stand-ins SURVEY.md section 8(d) defines for the assets the
+reference tree no longer ships (armadillo.obj, tyra.obj are missing large blobs)."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_MESHES = os.path.join(ROOT, "tests", "golden", "meshes.npz")
+
+
+@dataclass
+class Workload:
+    name: str                  # goes into the bench line's config.workload
+    description: str
+    positions: np.ndarray      # (V,3) float32
+    indices: np.ndarray        # (F,3) uint32
+    normals: np.ndarray        # (V,3) float32
+    width: int
+    height: int
+    bounces: int               # diffuse bounce generations traced after the primary rays
+    eye: tuple = synth.EYE
+    frustum: tuple = synth.FRUSTUM
+
+    @property
+    def num_tris(self):
+        return int(self.indices.shape[0])
+
+
+def _bundled(name):
+    z = np.load(GOLDEN_MESHES)
+    return z[name + "_pos"], z[name + "_idx"], z[name + "_nrm"]
+
+
+def get(name: str) -> Workload:
+    if name == "c1":
+        P, I, N = _bundled("bunny")
+        return Workload("c1: Content/bunny.obj (69,630 tris) BVH build + 1 spp primary closest-hit at 1280x720", "configs[0]", P, I, N, 1280, 720, 0)
+    if name == "c2":
+        P, I, N = synth.displaced_icosphere(7, seed=1)
+        return Workload("c2: armadillo STAND-IN (displaced icosphere, 327,680 tris, seed 1; Content/armadillo.obj is a missing blob) BVH build + "
+                        "primary and 1-bounce diffuse rays at 1920x1080", "configs[1]", P, I, N, 1920, 1080, 1)
+    if name == "c2small":        # same scene class at a size the CPU test tier can afford
+        P, I, N = synth.displaced_icosphere(4, seed=1)
+        return Workload("c2small: displaced icosphere 5,120 tris, 320x180 primary + 1 bounce", "test", P, I, N, 320, 180, 1)
+    if name == "c4":
+        P, I, N = synth.displaced_icosphere(9, seed=2)
+        return Workload("c4: tyra STAND-IN (displaced icosphere, 5,242,880 tris, seed 2) 3840x2160", "configs[3]", P, I, N, 3840, 2160, 0)
+    raise ValueError(name)
+
+
+def interleaved_rows_frustum(frustum, height, rank, world):
+    """Frustum (left,right,top,bottom,zoom) whose `height` rows are rows rank, rank+world, ... of the image that has
+    height*world rows over the full frustum: ICamera::setInitialRays(W, height, *this) then yields exactly those rows
+    (Camera.cpp:50-57: ry = top + dy/2 + k*dy with dy = (bottom-top)/height)."""
+    left, right, top, bottom, zoom = frustum
+    dy_full = (bottom - top) / (height * world)
+    top_r = top + (rank + 0.5 - 0.5 * world) * dy_full
+    return (left, right, top_r, top_r + height * world * dy_full, zoom)
