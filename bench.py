@@ -151,7 +151,7 @@ def run_b200(args):
     def frame(rays_in, marks=None):
         """one step on the device; returns rays traced by this rank"""
         if marks is not None: marks[0].record()
-        _lib.check(L.bmTraceCamera(tree.h, rays_in.data_ptr(), n, _f3(eye), _f9(orient), 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+        _lib.check(L.bmTraceCamera(tree.h, rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
         if marks is not None: marks[1].record()
         total = n
         if wl.bounces:
@@ -183,7 +183,7 @@ def run_b200(args):
         rays_step = frame(rays_dev)
     # per-ray traversal counters of the same traversal (instrumented launch, outside the timed region)
     cnt = torch.zeros(2, dtype=torch.int64, device=dev)
-    _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
+    _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
     torch.cuda.synchronize(dev)
     V1, K1 = [int(x) for x in cnt.cpu()]
     nb = int(cnt_host[0]) if wl.bounces else 0

@@ -137,8 +137,10 @@ int  bmTreeMeshBases(const bmTree* tree, uint32_t* h_bases, uint32_t capacity); 
 
 /* Explicit ray batch -> hit records. d_counters (nullable) receives {node visits, triangle tests} as two uint64. */
 int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters);
-/* Camera rays (dir = orient * initialRays[i] from eye), hit records and/or shaded pixels (either may be null). */
-int  bmTraceCamera(bmTree* tree, const float* d_initialRays3, uint64_t numRays, const float* eye3, const float* orient9,
+/* Camera rays (dir = orient * initialRays[i] from eye), hit records and/or shaded pixels (either may be null).
+ * width = row length of the image the table describes (numRays % width == 0): warps then start on 8x4 pixel tiles; 0 = trace in
+ * linear order.  Results are always written at index i of the table, whatever the order of traversal. */
+int  bmTraceCamera(bmTree* tree, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
                    int mode, bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters);
 
 /* Ray-batch producers for the multi-sample / bounce workloads (defined by this repo; the reference has no secondary rays,

@@ -75,7 +75,7 @@ def load() -> C.CDLL:
     L.bmTreeCopyChildBoxes.argtypes = [vp, vp]
     L.bmTreeMeshBases.argtypes = [vp, C.POINTER(u32), u32]
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]
-    L.bmTraceCamera.argtypes = [vp, vp, u64, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
+    L.bmTraceCamera.argtypes = [vp, vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
     L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]
     L.bmCameraRays.argtypes = [vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, u32, u32, vp, vp]
     L.bmBounceRays.argtypes = [vp, vp, vp, u64, u32, u32, u32, vp, vp, vp]

@@ -71,9 +71,10 @@ int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* 
 
 // ---- trace.cu -------------------------------------------------------------------------------------------------------
 struct CameraIn { const float* initialRays; float eye[3]; float orient[9]; };
-int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* d_hits, u64* d_counters, cudaStream_t s);
-int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
-                 u64* d_counters, cudaStream_t s);
+// d_workCounter: one u32 of device scratch per launch in flight (the persistent warps' work queue head)
+int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s);
+int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
+                 u64* d_counters, u32* d_workCounter, cudaStream_t s);
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
 
 // ---- rays.cu --------------------------------------------------------------------------------------------------------

@@ -168,7 +168,7 @@ public:
         if (!t) { for (size_t i = 0; i < n; i++) hostHits[i] = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu }; return ERROR_ALL_FINE; }
         DeviceBuffer hits(n * sizeof(bmHit));
         if (!hits.ok()) return ERROR_GPU_ALLOC_FAIL;
-        int r = bmTraceCamera(t, rays->ptr<const float>(), n, eye3, orient9, BM_TRACE_REFERENCE, hits.ptr<bmHit>(), rt ? rt->buffer<u32>() : nullptr,
+        int r = bmTraceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, BM_TRACE_REFERENCE, hits.ptr<bmHit>(), rt ? rt->buffer<u32>() : nullptr,
                               m_table ? m_table->ptr<const bmStaticMeshData>() : nullptr, nullptr);
         if (r != BM_OK) return (u32)r;
         hits.copyTo(hostHits, true);

@@ -16,77 +16,39 @@ namespace bm
 namespace
 {
 constexpr int TR_THREADS = 128;
-constexpr int TR_STACK = 40;     // radix tree depth <= D <= 32
+constexpr int TR_STACK = 36;     // radix tree depth <= D <= 32
+constexpr u32 REF_EMPTY = 0x7FFFFFFFu;   // "nothing left to visit" (never a valid internal index: N < 2^31 - 1)
 
 struct HitRec { float t, u, v; u32 tri, mesh, face; };
 
 __device__ __forceinline__ V3 f4xyz(float4 a) { return mk3(a.x, a.y, a.z); }
 
-__device__ __forceinline__ void leaf_faces(const TreeView& tv, u32 first, u32 cnt, V3 o, V3 d, bool forwardOnly, HitRec& best, u32& nt)
+// ---- one step of each traversal flavour, shared by every kernel variant -------------------------------------------------
+// Internal node in REFERENCE mode: cell test with the reference's slab arithmetic, child order by the split plane
+// (BuildTree.cu:398-481), children whose tight box the ray's line misses are not pushed.
+__device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d, V3 inv, u32* stack, int& top)
 {
-    const float4* p = tv.ltris + 3 * (size_t)first;
-    for (u32 i = 0; i < cnt; i++, p += 3)
-    {
-        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-        float u, v;
-        float dd = tri_intersect(o, d, f4xyz(a), f4xyz(b), f4xyz(c), u, v);
-        nt++;
-        if (forwardOnly && !(dd >= 0.f)) continue;
-        if (dd < best.t)
-        {
-            best.t = dd; best.u = u; best.v = v;
-            best.tri = __float_as_uint(a.w); best.mesh = __float_as_uint(b.w); best.face = __float_as_uint(c.w);
-        }
-    }
-}
-
-__device__ HitRec traverse_reference(const TreeView& tv, V3 o, V3 d, u32& nv, u32& nt)
-{
-    HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
-    if (tv.numLeaves == 0) return best;
-    const V3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
     const Grid& g = tv.grid;
-    u32 stack[TR_STACK];
-    int top = 0;
-    stack[0] = tv.rootRef;
-    while (top >= 0)
-    {
-        u32 ref = stack[top--];
-        nv++;
-        if (ref & LEAF_BIT)
-        {
-            uint4 lf = __ldg(tv.leaves + (ref & ~LEAF_BIT));
-            u32 ix, iy, iz; decode_path(g.D, lf.x, ix, iy, iz);
-            V3 mn, mx; cell_box(g, g.D, ix, iy, iz, mn, mx);
-            if (box_ray(mn, mx, o, inv) == FLT_MAX) continue;                     // BuildTree.cu:405-406
-            leaf_faces(tv, lf.y, min(lf.z, tv.maxLeafFaces), o, d, false, best, nt);
-            if (best.t != FLT_MAX) break;                                          // :427-431
-        }
-        else
-        {
-            const float4* np = tv.nodes + 4 * (size_t)ref;
-            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-            u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), prefix = __float_as_uint(q3.z);
-            int plen = (int)__float_as_uint(q3.w);
-            u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
-            V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
-            float boxDist = box_ray(mn, mx, o, inv);
-            if (boxDist == FLT_MAX) continue;
-            int axis = plen % 3;
-            u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
-            int sh = g.k[axis] - axis_bits(plen, axis);                            // >= 1: the node splits on this axis
-            float s = __ldg(g.tab[axis] + (((ia << 1) | 1u) << (sh - 1)));         // == .5f*(max+min) of the cell, :443
-            float p = get(o, axis) + boxDist * get(d, axis);                       // :444
-            bool leftFirst = p < s;
-            bool h0 = line_hits_box(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), o, inv);
-            bool h1 = line_hits_box(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), o, inv);
-            u32 nearRef = leftFirst ? c0 : c1, farRef = leftFirst ? c1 : c0;
-            bool nearHit = leftFirst ? h0 : h1, farHit = leftFirst ? h1 : h0;
-            if (farHit) stack[++top] = farRef;
-            if (nearHit) stack[++top] = nearRef;
-        }
-    }
-    return best;
+    const float4* np = tv.nodes + 4 * (size_t)ref;
+    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), prefix = __float_as_uint(q3.z);
+    int plen = (int)__float_as_uint(q3.w);
+    u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
+    V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
+    float boxDist = box_ray(mn, mx, o, inv);
+    if (boxDist == FLT_MAX) return;
+    int axis = plen % 3;
+    u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+    int sh = g.k[axis] - axis_bits(plen, axis);                            // >= 1: the node splits on this axis
+    float s = BM_LDG(g.tab[axis] + (((ia << 1) | 1u) << (sh - 1)));        // == .5f*(max+min) of the cell, :443
+    float p = get(o, axis) + boxDist * get(d, axis);                       // :444
+    bool leftFirst = p < s;
+    bool h0 = line_hits_box(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), o, inv);
+    bool h1 = line_hits_box(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), o, inv);
+    u32 nearRef = leftFirst ? c0 : c1, farRef = leftFirst ? c1 : c0;
+    bool nearHit = leftFirst ? h0 : h1, farHit = leftFirst ? h1 : h0;
+    if (farHit) stack[++top] = farRef;
+    if (nearHit) stack[++top] = nearRef;
 }
 
 // tight-box slab for the exhaustive mode: forward interval [0, tmax]
@@ -99,43 +61,33 @@ __device__ __forceinline__ bool box_interval(V3 bMin, V3 bMax, V3 o, V3 inv, flo
     return tn <= tf;
 }
 
-__device__ HitRec traverse_closest(const TreeView& tv, V3 o, V3 d, u32& nv, u32& nt)
+// Internal node in CLOSEST mode: both tight boxes against [0, best.t], near child on top of the stack.  A popped subtree
+// whose box lies beyond the hit found meanwhile is rejected again when its own node is visited (its children fail).
+__device__ __forceinline__ void closest_node(const TreeView& tv, u32 ref, V3 o, V3 inv, float tbest, u32* stack, int& top)
 {
-    HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
-    if (tv.numLeaves == 0) return best;
-    const V3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-    u32 stack[TR_STACK]; float stackT[TR_STACK];
-    int top = 0;
-    stack[0] = tv.rootRef; stackT[0] = 0.f;
-    while (top >= 0)
+    const float4* np = tv.nodes + 4 * (size_t)ref;
+    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
+    float t0, t1;
+    bool h0 = box_interval(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), o, inv, tbest, t0);
+    bool h1 = box_interval(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), o, inv, tbest, t1);
+    bool firstIs0 = t0 <= t1;
+    u32 nearRef = firstIs0 ? c0 : c1, farRef = firstIs0 ? c1 : c0;
+    bool nearHit = firstIs0 ? h0 : h1, farHit = firstIs0 ? h1 : h0;
+    if (farHit) stack[++top] = farRef;
+    if (nearHit) stack[++top] = nearRef;
+}
+
+__device__ __forceinline__ void test_face(float4 a, float4 b, float4 c, V3 o, V3 d, bool forwardOnly, HitRec& best)
+{
+    float u, v;
+    float dd = tri_intersect(o, d, f4xyz(a), f4xyz(b), f4xyz(c), u, v);
+    if (forwardOnly && !(dd >= 0.f)) return;
+    if (dd < best.t)                                                       // strict: the first face in list order wins a tie
     {
-        u32 ref = stack[top]; float tn = stackT[top]; --top;
-        if (tn > best.t) continue;
-        nv++;
-        if (ref & LEAF_BIT)
-        {
-            uint4 lf = __ldg(tv.leaves + (ref & ~LEAF_BIT));
-            leaf_faces(tv, lf.y, lf.z, o, d, true, best, nt);
-        }
-        else
-        {
-            const float4* np = tv.nodes + 4 * (size_t)ref;
-            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-            u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
-            float t0, t1;
-            bool h0 = box_interval(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), o, inv, best.t, t0);
-            bool h1 = box_interval(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), o, inv, best.t, t1);
-            if (h0 && h1)
-            {
-                bool firstIs0 = t0 <= t1;
-                ++top; stack[top] = firstIs0 ? c1 : c0; stackT[top] = firstIs0 ? t1 : t0;
-                ++top; stack[top] = firstIs0 ? c0 : c1; stackT[top] = firstIs0 ? t0 : t1;
-            }
-            else if (h0) { ++top; stack[top] = c0; stackT[top] = t0; }
-            else if (h1) { ++top; stack[top] = c1; stackT[top] = t1; }
-        }
+        best.t = dd; best.u = u; best.v = v;
+        best.tri = __float_as_uint(a.w); best.mesh = __float_as_uint(b.w); best.face = __float_as_uint(c.w);
     }
-    return best;
 }
 
 // bmFaceInterpolate<vec3>(face, u, v, meshData, 1) + normalize + pack (CudaComon.cuh:253-266, BuildTree.cu:486-496).
@@ -168,39 +120,142 @@ __device__ u32 shade(const HitRec& h, const bmStaticMeshData* __restrict__ meshD
     return (u32)fabsf(n.z * 255) << 16;
 }
 
-template <bool CAMERA>
-__global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, int mode,
-                                                           bmHit* __restrict__ hits, u32* __restrict__ pixels,
-                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters)
+// Slot -> ray index.  With a width, slots enumerate 8x4 pixel tiles (one tile per warp-sized fetch) so that the lanes of a
+// warp start on neighbouring pixels in both directions; slots that fall outside the image map to "no ray".
+__device__ __forceinline__ bool slot_to_ray(u32 slot, u64 n, u32 width, u32 height, u64& ray)
 {
+    if (width == 0) { ray = slot; return slot < n; }
+    u32 tilesX = (width + 7) >> 3;
+    u32 tile = slot >> 5, in = slot & 31;
+    u32 px = (tile % tilesX) * 8 + (in & 7), py = (tile / tilesX) * 4 + (in >> 3);
+    ray = (u64)py * width + px;
+    return px < width && py < height;
+}
+
+// Persistent warps (one resident grid; every warp pulls work from a global counter), while-while traversal:
+//   refill idle lanes -> all lanes with a pending internal node walk nodes until none has one -> all lanes with a pending
+//   leaf test its triangles together -> lanes whose ray is finished write their result and become idle.
+// Keeping the two phases warp-synchronous is what lifts SIMT efficiency: in the first version (profiles/r1_a) only 11 of
+// 32 lanes were active on average because leaf loops and node walks of different lanes serialised each other.
+template <int MODE, bool CAMERA, bool COUNT>
+__global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
+                                                           u32 totalSlots, bmHit* __restrict__ hits, u32* __restrict__ pixels,
+                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31;
+    u32 stack[TR_STACK];
+    int top = -1;
+    u32 cur = REF_EMPTY;
+    bool active = false, exhausted = false;
+    u64 rayIdx = 0;
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1);
+    HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
     u32 nv = 0, nt = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+
+    for (;;)
     {
-        V3 o, d;
-        if (CAMERA)
+        // ---- refill -----------------------------------------------------------------------------------------------------
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted)
         {
-            const float* r = cam.initialRays + 3 * i;
-            float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
-            const float* m = cam.orient;                                      // glm mat3 * vec3 (type_mat3x3.inl:424-430)
-            d = mk3(m[0] * x + m[3] * y + m[6] * z, m[1] * x + m[4] * y + m[7] * z, m[2] * x + m[5] * y + m[8] * z);
-            o = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(workCounter, (u32)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= totalSlots) exhausted = true;
+            if (!active)
+            {
+                u32 slot = base + __popc(idle & ((1u << lane) - 1u));
+                if (slot < totalSlots && slot_to_ray(slot, n, width, height, rayIdx))
+                {
+                    if (CAMERA)
+                    {
+                        const float* r = cam.initialRays + 3 * rayIdx;
+                        float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
+                        const float* m = cam.orient;                              // glm mat3 * vec3 (type_mat3x3.inl:424-430)
+                        d = mk3(m[0] * x + m[3] * y + m[6] * z, m[1] * x + m[4] * y + m[7] * z, m[2] * x + m[5] * y + m[8] * z);
+                        o = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
+                    }
+                    else
+                    {
+                        const float* r = reinterpret_cast<const float*>(rays + rayIdx);
+                        o = mk3(__ldg(r), __ldg(r + 1), __ldg(r + 2));
+                        d = mk3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
+                    }
+                    inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+                    best.t = FLT_MAX; best.u = 0.f; best.v = 0.f; best.tri = best.mesh = best.face = 0xFFFFFFFFu;
+                    top = -1;
+                    cur = tv.numLeaves ? tv.rootRef : REF_EMPTY;
+                    active = true;
+                }
+            }
         }
-        else
+        if (!__any_sync(FULL, active)) break;
+
+        // ---- phase 1: internal nodes, until no lane has one pending ----------------------------------------------------------
+        for (;;)
         {
-            const float* r = reinterpret_cast<const float*>(rays + i);
-            o = mk3(__ldg(r), __ldg(r + 1), __ldg(r + 2));
-            d = mk3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
+            bool inner = active && cur != REF_EMPTY && !(cur & LEAF_BIT);
+            if (!__any_sync(FULL, inner)) break;
+            if (inner)
+            {
+                if (COUNT) nv++;
+                if (MODE == BM_TRACE_REFERENCE) ref_node(tv, cur, o, d, inv, stack, top);
+                else closest_node(tv, cur, o, inv, best.t, stack, top);
+                cur = top >= 0 ? stack[top--] : REF_EMPTY;
+            }
         }
-        HitRec h = (mode == BM_TRACE_REFERENCE) ? traverse_reference(tv, o, d, nv, nt) : traverse_closest(tv, o, d, nv, nt);
-        if (hits) { bmHit out; out.t = h.t; out.u = h.u; out.v = h.v; out.tri = h.tri; reinterpret_cast<float4*>(hits)[i] = *reinterpret_cast<float4*>(&out); }
-        if (pixels) pixels[i] = shade(h, meshData);
+
+        // ---- phase 2: one pending leaf per lane, triangles tested in lock step ------------------------------------------------
+        bool finished = false;
+        {
+            bool isLeaf = active && cur != REF_EMPTY;          // after phase 1 a pending ref is a leaf
+            u32 first = 0, cnt = 0;
+            if (isLeaf)
+            {
+                if (COUNT) nv++;
+                uint4 lf = __ldg(tv.leaves + (cur & ~LEAF_BIT));
+                first = lf.y;
+                if (MODE == BM_TRACE_REFERENCE)
+                {
+                    u32 ix, iy, iz; decode_path(tv.grid.D, lf.x, ix, iy, iz);
+                    V3 mn, mx; cell_box(tv.grid, tv.grid.D, ix, iy, iz, mn, mx);
+                    if (box_ray(mn, mx, o, inv) != FLT_MAX) cnt = min(lf.z, tv.maxLeafFaces);      // BuildTree.cu:405-411
+                }
+                else cnt = lf.z;
+            }
+            u32 maxCnt = __reduce_max_sync(FULL, cnt);
+            const float4* p = tv.ltris + 3 * (size_t)first;
+            for (u32 i = 0; i < maxCnt; i++, p += 3)
+            {
+                if (i < cnt)
+                {
+                    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+                    if (COUNT) nt++;
+                    test_face(a, b, c, o, d, MODE != BM_TRACE_REFERENCE, best);
+                }
+            }
+            if (isLeaf)
+            {
+                if (MODE == BM_TRACE_REFERENCE && best.t != FLT_MAX) finished = true;              // :427-431
+                else cur = top >= 0 ? stack[top--] : REF_EMPTY;
+            }
+        }
+
+        // ---- retire ------------------------------------------------------------------------------------------------------------
+        if (active && (finished || cur == REF_EMPTY))
+        {
+            if (hits) { reinterpret_cast<float4*>(hits)[rayIdx] = make_float4(best.t, best.u, best.v, __uint_as_float(best.tri)); }
+            if (pixels) pixels[rayIdx] = shade(best, meshData);
+            active = false;
+        }
     }
-    if (counters)
+    if (COUNT)
     {
         u64 a = nv, b = nt;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xFFFFFFFFu, a, o); b += __shfl_down_sync(0xFFFFFFFFu, b, o); }
-        if ((threadIdx.x & 31) == 0) { atomicAdd((unsigned long long*)&counters[0], (unsigned long long)a); atomicAdd((unsigned long long*)&counters[1], (unsigned long long)b); }
+        for (int k = 16; k > 0; k >>= 1) { a += __shfl_down_sync(FULL, a, k); b += __shfl_down_sync(FULL, b, k); }
+        if (lane == 0) { atomicAdd((unsigned long long*)&counters[0], (unsigned long long)a); atomicAdd((unsigned long long*)&counters[1], (unsigned long long)b); }
     }
 }
 
@@ -218,30 +273,53 @@ __global__ void hash_kernel(const float* __restrict__ pts, u64 n, u32* __restric
     if (hash) hash[i] = hash3((u32)cx, (u32)cy, (u32)cz);
 }
 
-unsigned trace_grid(u64 n)
+template <int MODE, bool CAMERA, bool COUNT>
+int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, u32 width, bmHit* d_hits, u32* d_pixels,
+                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
-    u64 blocks = (n + TR_THREADS - 1) / TR_THREADS;
-    u64 cap = (u64)sm_count() * 16;
-    return (unsigned)(blocks < cap ? (blocks ? blocks : 1) : cap);
+    static int blocksPerSM = 0;
+    if (!blocksPerSM)
+    {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
+    }
+    u32 height = width ? (u32)((n + width - 1) / width) : 0;
+    u64 slots = width ? (u64)((width + 7) / 8) * ((height + 3) / 4) * 32 : n;
+    if (slots >= 0xFFFFFFF0ull) { set_error("more than 2^32 rays in one launch"); return BM_ERROR_CAPACITY; }
+    u64 warps = (slots + 31) / 32;
+    u64 blocks = (warps + TR_THREADS / 32 - 1) / (TR_THREADS / 32);
+    u64 cap = (u64)sm_count() * blocksPerSM;
+    if (blocks > cap) blocks = cap;
+    BM_CUDA(cudaMemsetAsync(d_workCounter, 0, 4, s));
+    trace_kernel<MODE, CAMERA, COUNT><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_hits, d_pixels, d_meshData,
+                                                                            d_counters, d_workCounter);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+
+template <bool CAMERA>
+int dispatch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels,
+                   const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, cudaStream_t s)
+{
+    if (mode == BM_TRACE_REFERENCE)
+        return d_counters ? launch_trace<BM_TRACE_REFERENCE, CAMERA, true>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
+                          : launch_trace<BM_TRACE_REFERENCE, CAMERA, false>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
+    return d_counters ? launch_trace<BM_TRACE_CLOSEST, CAMERA, true>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
+                      : launch_trace<BM_TRACE_CLOSEST, CAMERA, false>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
 }
 } // namespace
 
-int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* d_hits, u64* d_counters, cudaStream_t s)
+int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
     if (!n) return BM_OK;
     CameraIn cam = {};
-    trace_kernel<false><<<trace_grid(n), TR_THREADS, 0, s>>>(tv, d_rays, cam, n, mode, d_hits, nullptr, nullptr, d_counters);
-    BM_LAUNCHED();
-    return BM_OK;
+    return dispatch_trace<false>(tv, d_rays, cam, n, 0, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, s);
 }
 
-int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
-                 u64* d_counters, cudaStream_t s)
+int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
+                 u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    trace_kernel<true><<<trace_grid(n), TR_THREADS, 0, s>>>(tv, nullptr, cam, n, mode, d_hits, d_pixels, d_meshData, d_counters);
-    BM_LAUNCHED();
-    return BM_OK;
+    return dispatch_trace<true>(tv, nullptr, cam, n, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
 }
 
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s)

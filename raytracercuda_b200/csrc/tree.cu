@@ -267,10 +267,11 @@ extern "C" int bmTraceRays(bmTree* t, const bmRay* d_rays, uint64_t numRays, int
 {
     if (!t || (!d_rays && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) BM_TRY(tree_build(t));
-    return trace_rays(t->view(), d_rays, numRays, mode, d_hits, d_counters, t->stream);
+    BM_TRY(t->scalars.reserve(64));
+    return trace_rays(t->view(), d_rays, numRays, mode, d_hits, d_counters, t->scalars.as<u32>() + 8, t->stream);
 }
 
-extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, const float* eye3, const float* orient9, int mode,
+extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9, int mode,
                              bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters)
 {
     if (!t || !eye3 || !orient9 || (!d_initialRays3 && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
@@ -278,7 +279,9 @@ extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t nu
     if (!t->built) BM_TRY(tree_build(t));
     CameraIn cam; cam.initialRays = d_initialRays3;
     memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
-    return trace_camera(t->view(), cam, numRays, mode, d_hits, d_pixels, d_meshData, d_counters, t->stream);
+    if (width && numRays % width) return BM_ERROR_INVALID_PARAMETER;
+    BM_TRY(t->scalars.reserve(64));
+    return trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, t->stream);
 }
 
 extern "C" int bmCameraRays(const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
@@ -374,7 +377,7 @@ extern "C" void bmMarch(const void* root, const bmVec3*, const bmVec3*, const bm
         if (bm::clear_u32(buffer, n, 255u << 8, 0) != BM_OK) die("bmMarch");
         return;
     }
-    if (bmTraceCamera(t, (const float*)initialRays, n, &eye->x, orient->m, BM_TRACE_REFERENCE, nullptr, buffer, meshData, nullptr) != BM_OK) die("bmMarch");
+    if (bmTraceCamera(t, (const float*)initialRays, n, width, &eye->x, orient->m, BM_TRACE_REFERENCE, nullptr, buffer, meshData, nullptr) != BM_OK) die("bmMarch");
 }
 
 extern "C" void bmClear(uint32_t* buffer, uint32_t pitch, uint32_t, uint32_t height, uint32_t clearValue)

@@ -112,14 +112,14 @@ class Tree:
         check(self.L.bmTraceRays(self.h, R.data_ptr(), n, int(mode), hits.data_ptr(), None if cnt is None else cnt.data_ptr()), "bmTraceRays")
         return (hits, cnt) if counters else hits
 
-    def trace_camera(self, initial_rays, eye, orient, mode=BM_TRACE_REFERENCE, want_hits=True, pixels=None, mesh_table=None, counters=False):
+    def trace_camera(self, initial_rays, eye, orient, mode=BM_TRACE_REFERENCE, want_hits=True, pixels=None, mesh_table=None, counters=False, width=0):
         R = _dev_tensor(initial_rays, torch.float32, self.device).reshape(-1, 3)
         n = R.shape[0]
         e = (C.c_float * 3)(*[float(x) for x in eye])
         o = (C.c_float * 9)(*[float(x) for x in np.asarray(orient, np.float32).reshape(-1)])
         hits = torch.empty((n, 4), dtype=torch.float32, device=self.device) if want_hits else None
         cnt = torch.zeros(2, dtype=torch.int64, device=self.device) if counters else None
-        check(self.L.bmTraceCamera(self.h, R.data_ptr(), n, e, o, int(mode), None if hits is None else hits.data_ptr(),
+        check(self.L.bmTraceCamera(self.h, R.data_ptr(), n, int(width), e, o, int(mode), None if hits is None else hits.data_ptr(),
                                    None if pixels is None else pixels.data_ptr(), None if mesh_table is None else mesh_table.data_ptr(),
                                    None if cnt is None else cnt.data_ptr()), "bmTraceCamera")
         return hits, cnt

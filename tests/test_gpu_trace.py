@@ -42,7 +42,7 @@ def test_camera_reference_mode(name, W, H, meshes, golden, oracle_lib, beam_lib,
     Nd = torch.from_numpy(N).to(cuda_device)
     table = make_mesh_table([(Pd, Id, Nd)], cuda_device)
     px = torch.empty(W * H, dtype=torch.int32, device=cuda_device)
-    hits, cnt = t.trace_camera(rays, EYE, ID3, pixels=px, mesh_table=table, counters=True)
+    hits, cnt = t.trace_camera(rays, EYE, ID3, pixels=px, mesh_table=table, counters=True, width=W)      # 8x4 tile order
     h = hits_to_numpy(hits)
     agree, rel = _compare(h, r, t.mesh_bases(), what=name)
     assert agree == 1.0 and rel == 0.0, "bundled meshes are expected to match the oracle bit for bit"
