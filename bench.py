@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 METRIC = "Mrays/s closest-hit (primary + diffuse)"
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
-NODE_BYTES, TRI_BYTES = 64, 48
+NODE_BYTES, TRI_BYTES, CLUSTER_BYTES, LEAF_BYTES = 96, 48, 32, 48     # bytes a visit reads: node = 6 float4 of its 128-byte record
 
 
 def measured_peaks():
@@ -182,17 +182,17 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         rays_step = frame(rays_dev)
     # per-ray traversal counters of the same traversal (instrumented launch, outside the timed region)
-    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(3, dtype=torch.int64, device=dev)
     _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
     torch.cuda.synchronize(dev)
-    V1, K1 = [int(x) for x in cnt.cpu()]
+    V1, K1, C1 = [int(x) for x in cnt.cpu()]
     nb = int(cnt_host[0]) if wl.bounces else 0
-    V2 = K2 = 0
+    V2 = K2 = C2 = 0
     if nb:
         cnt.zero_()
         _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
         torch.cuda.synchronize(dev)
-        V2, K2 = [int(x) for x in cnt.cpu()]
+        V2, K2, C2 = [int(x) for x in cnt.cpu()]
 
     # --- timed: K steps, device resident, L2 flushed between steps --------------------------------------------------------
     sampler = ClockSampler(local)
@@ -258,29 +258,29 @@ def run_b200(args):
             build_ms.append(e0.elapsed_time(e1))
     bms = statistics.mean(build_ms)
     peak, peak_src = measured_peaks()
-    build_bytes = 48 * st["triangles"] + 8 * st["pairs"] + NODE_BYTES * st["nodes"]
+    build_bytes = 48 * st["triangles"] + 12 * st["pairs"] + 128 * st["nodes"] + 48 * st["pairs"] + 48 * st["leaves"] + 8 * st["pairs"]
     build = {"metric": "BVH build Mtris/s", "value": st["triangles"] / (bms * 1e-3) / 1e6, "unit": "Mtris/s", "ms": bms,
              "triangles": st["triangles"], "pairs": st["pairs"], "leaves": st["leaves"], "nodes": st["nodes"],
              "roofline": {"bound": "hbm", "achieved": build_bytes / (bms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": build_bytes / (bms * 1e-3) / 1e9 / peak, "traffic": None,
-                          "algorithmic_bytes": build_bytes, "note": "48 B/tri + 8 B/pair + 64 B/node over the whole build (SURVEY 8d); " + peak_src},
+                          "algorithmic_bytes": build_bytes, "note": "compulsory bytes of the whole build: 48 B/tri soup read + 12 B/pair (8 B key + 4 B id) written + outputs (128 B/node, 48 B/leaf, 48 B/pair triangle record, 32 B per 4 pairs cluster box); sort passes excluded (SURVEY 8d); " + peak_src},
              "replication": "every rank builds its own replica" if world > 1 else "single GPU"}
 
     # --- roofline of the dominant kernel: the primary-ray trace launch ---------------------------------------------------
     pms = statistics.mean(prim_ms)
-    prim_bytes = n * (12 + 16 + 4) + NODE_BYTES * V1 + TRI_BYTES * K1
+    prim_bytes = n * (12 + 16 + 4) + NODE_BYTES * V1 + TRI_BYTES * K1 + CLUSTER_BYTES * C1
     roofline = {"bound": "hbm", "kernel": "trace_kernel<camera> (bmTraceCamera, reference semantics)", "achieved": prim_bytes / (pms * 1e-3) / 1e9,
                 "peak": peak, "unit": "GB/s", "frac": prim_bytes / (pms * 1e-3) / 1e9 / peak, "traffic": None,
                 "ms_per_launch": pms, "mrays_per_s": n / (pms * 1e-3) / 1e6,
-                "bytes_per_ray": prim_bytes / n, "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n,
-                "note": "algorithmic bytes = 12 B ray + 16 B hit + 4 B pixel + 64 B x node visits + 48 B x triangle tests (counters of the same traversal); "
+                "bytes_per_ray": prim_bytes / n, "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n, "cluster_boxes_per_ray": C1 / n,
+                "note": "algorithmic bytes = 12 B ray + 16 B hit + 4 B pixel + 96 B x node/leaf visits + 32 B x cluster boxes + 48 B x triangle tests (counters of the same traversal); "
                         + peak_src + "; the tree (~%.0f MB) is L2-resident on B200, so this kernel is latency/issue-bound, not HBM-bound (SURVEY 8d)" %
-                        ((st["nodes"] * 64 + st["pairs"] * 48 + st["leaves"] * 16) / 1e6)}
+                        ((st["nodes"] * 128 + st["pairs"] * 56 + st["leaves"] * 48) / 1e6)}
     if wl.bounces and nb:
         bms2 = statistics.mean(bounce_ms)
         roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb / (bms2 * 1e-3) / 1e6, "rays": nb,
-                                     "node_visits_per_ray": V2 / nb, "tri_tests_per_ray": K2 / nb,
-                                     "achieved": (nb * (24 + 16) + NODE_BYTES * V2 + TRI_BYTES * K2) / (bms2 * 1e-3) / 1e9}
+                                     "node_visits_per_ray": V2 / nb, "tri_tests_per_ray": K2 / nb, "cluster_boxes_per_ray": C2 / nb,
+                                     "achieved": (nb * (24 + 16) + NODE_BYTES * V2 + TRI_BYTES * K2 + CLUSTER_BYTES * C2) / (bms2 * 1e-3) / 1e9}
 
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -135,7 +135,8 @@ int  bmTreeCopyTopology(const bmTree* tree, uint32_t* d_prefixLen, uint32_t* d_p
 int  bmTreeCopyChildBoxes(const bmTree* tree, float* d_boxes12);
 int  bmTreeMeshBases(const bmTree* tree, uint32_t* h_bases, uint32_t capacity);   /* host array: first global id of each mesh */
 
-/* Explicit ray batch -> hit records. d_counters (nullable) receives {node visits, triangle tests} as two uint64. */
+/* Explicit ray batch -> hit records. d_counters (nullable) accumulates {node + leaf visits, triangle tests, cluster boxes tested}
+ * into three uint64 (the traversal work behind the bytes-per-ray roofline model). */
 int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters);
 /* Camera rays (dir = orient * initialRays[i] from eye), hit records and/or shaded pixels (either may be null).
  * width = row length of the image the table describes (numRays % width == 0): warps then start on 8x4 pixel tiles; 0 = trace in

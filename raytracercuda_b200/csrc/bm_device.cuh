@@ -23,27 +23,36 @@ int sm_count();
 
 // ---- HBM layout of a finished tree (all index-based, no absolute pointers inside the arrays) --------------------------
 //
-//  nodes  : N = L-1 internal nodes of the binary radix tree over the L distinct leaf codes, 64 bytes each, 64-byte aligned:
-//             float4 q0 = (lo0.x lo0.y lo0.z hi0.x)     child 0 = lower half ("left"), tight box = union of whole triangles
-//             float4 q1 = (hi0.y hi0.z lo1.x lo1.y)
-//             float4 q2 = (lo1.z hi1.x hi1.y hi1.z)
-//             uint4  q3 = (child0, child1, prefix, prefixLen)   child bit 31 = leaf; prefix = top prefixLen bits of the codes
-//           The node IS the reference kd node at depth prefixLen with two children; its cell box follows from
-//           (prefix, prefixLen) through the grid tables, its split axis is prefixLen % 3.
-//  leaves : uint4 (code, first pair, pair count, 0), sorted by code.
-//  ltris  : one 48-byte record per (leaf, triangle) pair in sorted order, so a leaf's triangles are one contiguous run:
-//             float4 (v0.xyz, global triangle id) (e1.xyz = v1-v0, mesh index) (e2.xyz = v2-v0, face index in mesh)
+//  nodes    : N = L-1 internal nodes of the binary radix tree over the L distinct leaf codes, 128 bytes each (two 64-byte
+//             lines, 128-byte aligned):
+//               float4 q0 = (lo0.x lo0.y lo0.z hi0.x)     child 0 = lower half ("left"); tight box = union of whole triangles
+//               float4 q1 = (hi0.y hi0.z lo1.x lo1.y)
+//               float4 q2 = (lo1.z hi1.x hi1.y hi1.z)
+//               uint4  q3 = (child0, child1, prefix, prefixLen)   child bit 31 = leaf; prefix = top prefixLen bits of the codes
+//               float4 q4 = (cellMin.xyz, split plane s)           the reference kd node at depth prefixLen IS this node: its
+//               float4 q5 = (cellMax.xyz, split axis)              implicit box, axis prefixLen % 3 and plane .5f*(min+max)
+//               q6, q7    = unused
+//  leaves   : 48 bytes each, sorted by code: uint4 (code, first pair, pair count, first cluster), float4 (cellMin.xyz, cellMax.x),
+//             float4 (cellMax.y, cellMax.z, -, -).
+//  ltris    : one 48-byte record per (leaf, triangle) pair; the pairs of a leaf are contiguous and ordered by the in-cell
+//             Morton sub-key:  float4 (v0.xyz, global triangle id) (e1.xyz = v1-v0, mesh index | EXCLUDED bit) (e2.xyz = v2-v0,
+//             face index in mesh).  EXCLUDED marks pairs beyond the reference's 256-faces-per-leaf cap (BuildTree.cuh:17).
+//  clusters : 32 bytes per group of CLUSTER consecutive pairs of one leaf: float4 (lo.xyz, hi.x) (hi.y, hi.z, -, -) = padded
+//             union of the group's whole triangles.  A leaf tests a group's triangles only if the ray's line meets its box.
+constexpr int SUB_BITS = 15;
+constexpr int CLUSTER = 4;
+constexpr int NODE_F4 = 8, LEAF_F4 = 3, CLUSTER_F4 = 2;
+static const u32 LEAF_BIT = 0x80000000u;
+static const u32 EXCLUDED_BIT = 0x80000000u;
 struct TreeView
 {
-    Grid grid;
     const float4* nodes;
-    const uint4* leaves;
+    const float4* leaves;
     const float4* ltris;
+    const float4* clusters;
     u32 numLeaves;
     u32 rootRef;          // bit 31 = leaf
-    u32 maxLeafFaces;     // MAX_FACES_PER_BOX (BuildTree.cuh:17): reference mode tests at most this many faces per leaf
 };
-static const u32 LEAF_BIT = 0x80000000u;
 
 // ---- scan.cu --------------------------------------------------------------------------------------------------------
 size_t scan_temp_bytes(size_t n);
@@ -55,19 +64,25 @@ size_t sort_temp_bytes(size_t n);
 // Stable LSD radix sort of (key, value) pairs on the low `bits` bits of the key. Input in buffer A; A and B ping-pong;
 // *resultInB tells which pair of buffers holds the sorted result (B after an odd number of 8-bit passes).
 int radix_sort_pairs(u32* d_keysA, u32* d_valsA, u32* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB);
+int radix_sort_pairs64(u64* d_keysA, u32* d_valsA, u64* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB);
 
 // ---- keygen.cu ------------------------------------------------------------------------------------------------------
 int gather_mesh(const float* d_pos, const u32* d_idx, u32 numTris, u32 meshIdx, u32 base, float4* d_soup, cudaStream_t s);
 int count_pairs(const Grid& g, const float4* d_soup, u32 numTris, u32* d_counts, cudaStream_t s);
-int emit_pairs(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, u32* d_keys, u32* d_vals, cudaStream_t s);
+int emit_pairs(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, u64* d_keys, u32* d_vals, cudaStream_t s);
 
 // ---- hierarchy.cu ---------------------------------------------------------------------------------------------------
-int mark_heads(const u32* d_keys, size_t n, u32* d_flags, cudaStream_t s);
-int write_leaves(const u32* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, uint4* d_leaves, cudaStream_t s);
+int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s);
+int write_leaves(const Grid& g, const u64* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, float4* d_leaves, u32* d_clusterCounts,
+                 cudaStream_t s);
 int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_ltris, cudaStream_t s);
-int leaf_bounds(const uint4* d_leaves, u32 numLeaves, const float4* d_ltris, float* d_leafBox6, float pad, u32* d_stats, cudaStream_t s);
-int emit_hierarchy(const uint4* d_leaves, u32 numLeaves, int D, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s);
+// cluster boxes + leaf boxes + leaf statistics + the 256-cap exclusion flags; d_clusterFirst = exclusive scan of the cluster counts
+int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_clusterFirst, float4* d_ltris, float4* d_clusters, float* d_leafBox6, float pad, u32* d_stats,
+                cudaStream_t s);
+int emit_hierarchy(const Grid& g, const float4* d_leaves, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s);
 int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit, float4* d_nodes, cudaStream_t s);
+int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, u64* d_out, cudaStream_t s);
+int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s);
 
 // ---- trace.cu -------------------------------------------------------------------------------------------------------
 struct CameraIn { const float* initialRays; float eye[3]; float orient[9]; };

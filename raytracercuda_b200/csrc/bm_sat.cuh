@@ -129,7 +129,7 @@ BM_HD void axis_range(const float* tab, int k, float vmin, float vmax, int& lo, 
 
 // Reference descent for ONE triangle (BuildTree.cu:191-255), restricted to cells inside the exact per-axis ranges:
 // depth-first over the implicit kd nodes; a child is entered iff the reference's own test on the child box passes;
-// reaching depth D emits the leaf path code.  `emit(code)` is called once per (leaf, triangle) pair.  Because every
+// reaching depth D emits the leaf path code.  `emit(code, ix, iy, iz)` is called once per (leaf, triangle) pair.  Because every
 // level evaluates the reference's test on the reference's box, the emitted set equals the reference's leaf set by
 // construction (no float-monotonicity assumption).  Returns the number of pairs.
 template <class Emit>
@@ -152,7 +152,7 @@ BM_HD u32 descend_triangle(const Grid& g, V3 a, V3 b, V3 c, Emit emit)
     {
         u64 e = stack[top--];
         u32 d = (u32)(e >> 33), ix = (u32)(e >> 22) & 0x7FFu, iy = (u32)(e >> 11) & 0x7FFu, iz = (u32)e & 0x7FFu;
-        if ((int)d == g.D) { emit(encode_path(g.D, ix, iy, iz)); ++count; continue; }
+        if ((int)d == g.D) { emit(encode_path(g.D, ix, iy, iz), ix, iy, iz); ++count; continue; }
         int ax = d % 3;
         u32 nd = d + 1;
 #pragma unroll

@@ -1,26 +1,26 @@
-// hierarchy.cu -- from sorted (code, triangle) pairs to the traversable tree:
+// hierarchy.cu -- from sorted (key, triangle) pairs to the traversable tree:
 //   leaf segmentation (distinct codes)  ->  Karras-style binary radix tree over the distinct codes, one thread per internal
-//   node  ->  bottom-up refit of tight boxes with one atomic counter per node  ->  64-byte nodes.
+//   node  ->  bottom-up refit of tight boxes with one atomic counter per node  ->  128-byte nodes.
 //
 // Topology equivalence with the reference: the reference kd node at depth d with TWO children is
 // exactly the radix-tree node whose keys share a d-bit prefix and then differ; single-child chain nodes of the reference
-// have no counterpart because they take no decision.  emit_hierarchy stores (prefix, prefixLen) so that the node's cell
-// box, split axis (prefixLen % 3) and split plane are the reference's.
+// have no counterpart because they take no decision.  emit_hierarchy stores (prefix, prefixLen) and, precomputed from the
+// grid tables, the node's cell box, split axis (prefixLen % 3) and split plane -- the reference's own values.
 #include "bm_device.cuh"
 
 namespace bm
 {
 namespace
 {
-__global__ void mark_heads_kernel(const u32* __restrict__ keys, size_t n, u32* __restrict__ flags)
+__global__ void mark_heads_kernel(const u64* __restrict__ keys, size_t n, u32* __restrict__ flags)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    flags[i] = (i == 0 || (keys[i] >> SUB_BITS) != (keys[i - 1] >> SUB_BITS)) ? 1u : 0u;
 }
 
-__global__ void write_leaves_kernel(const u32* __restrict__ keys, const u32* __restrict__ flags, const u32* __restrict__ leafIdx, size_t n,
-                                    u32 numLeaves, uint4* __restrict__ leaves)
+__global__ void write_leaves_kernel(Grid g, const u64* __restrict__ keys, const u32* __restrict__ flags, const u32* __restrict__ leafIdx, size_t n,
+                                    u32 numLeaves, float4* __restrict__ leaves, u32* __restrict__ clusterCounts)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -28,7 +28,14 @@ __global__ void write_leaves_kernel(const u32* __restrict__ keys, const u32* __r
     // run length: scan forward to the next head (leaves are short: <= a few hundred pairs)
     size_t j = i + 1;
     while (j < n && !flags[j]) ++j;
-    leaves[leafIdx[i]] = make_uint4(keys[i], (u32)i, (u32)(j - i), 0u);
+    u32 l = leafIdx[i], code = (u32)(keys[i] >> SUB_BITS), cnt = (u32)(j - i);
+    u32 ix, iy, iz; decode_path(g.D, code, ix, iy, iz);
+    V3 mn, mx; cell_box(g, g.D, ix, iy, iz, mn, mx);
+    float4* o = leaves + LEAF_F4 * (size_t)l;
+    o[0] = make_float4(__uint_as_float(code), __uint_as_float((u32)i), __uint_as_float(cnt), __uint_as_float(0u));
+    o[1] = make_float4(mn.x, mn.y, mn.z, mx.x);
+    o[2] = make_float4(mx.y, mx.z, 0.f, 0.f);
+    clusterCounts[l] = (cnt + CLUSTER - 1) / CLUSTER;
 }
 
 __global__ void pack_leaf_tris_kernel(const float4* __restrict__ soup, const u32* __restrict__ vals, size_t n, float4* __restrict__ ltris)
@@ -44,56 +51,80 @@ __global__ void pack_leaf_tris_kernel(const float4* __restrict__ soup, const u32
     o[2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, c.w);
 }
 
-// tight box of a leaf = union of its WHOLE triangles (not clipped to the cell: reference mode must still find a hit that lies
-// outside the cell, BuildTree.cu:413-431).  stats[0] = max leaf size, stats[1] = leaves above 256 faces.
-__global__ void leaf_bounds_kernel(const uint4* __restrict__ leaves, u32 numLeaves, const float4* __restrict__ ltris, float* __restrict__ box6,
-                                   float pad, u32* stats)
+// Per leaf: cluster boxes (groups of CLUSTER consecutive pairs), the leaf's tight box (their union), leaf-size statistics and the
+// reference's face cap.  Boxes enclose WHOLE triangles (not clipped to the cell: reference mode must still find a hit that lies
+// outside the cell, BuildTree.cu:413-431).  v1 = v0 + e1 may differ from the stored vertex by one rounding, and a hit the triangle
+// test accepts numerically may lie a few ulps of the ray length outside the exact box: `pad` (world extent * 2^-20, far below the
+// cell size) absorbs both.  stats[0] = max leaf size, stats[1] = leaves above 256 faces.
+__global__ void leaf_bounds_kernel(float4* __restrict__ leaves, u32 numLeaves, const u32* __restrict__ clusterFirst, float4* __restrict__ ltris,
+                                   float4* __restrict__ clusters, float* __restrict__ box6, float pad, u32* stats)
 {
     u32 l = blockIdx.x * blockDim.x + threadIdx.x;
-    uint4 lf = l < numLeaves ? leaves[l] : make_uint4(0, 0, 0, 0);
-    // leaf-size statistics: one atomic per warp, and only while the running maximum still grows
-    u32 wmax = __reduce_max_sync(0xFFFFFFFFu, lf.z);
-    u32 wover = __popc(__ballot_sync(0xFFFFFFFFu, lf.z > 256u));
+    float4 r0 = l < numLeaves ? leaves[LEAF_F4 * (size_t)l] : make_float4(0, 0, 0, 0);
+    u32 first = __float_as_uint(r0.y), cnt = l < numLeaves ? __float_as_uint(r0.z) : 0u;
+    u32 wmax = __reduce_max_sync(0xFFFFFFFFu, cnt);
+    u32 wover = __popc(__ballot_sync(0xFFFFFFFFu, cnt > 256u));
     if ((threadIdx.x & 31) == 0)
     {
         if (wmax > __ldcg(&stats[0])) atomicMax(&stats[0], wmax);
         if (wover) atomicAdd(&stats[1], wover);
     }
     if (l >= numLeaves) return;
+    u32 cf = clusterFirst[l];
+    leaves[LEAF_F4 * (size_t)l].w = __uint_as_float(cf);
     float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-    for (u32 i = 0; i < lf.z; i++)
+    for (u32 c0 = 0; c0 < cnt; c0 += CLUSTER)
     {
-        const float4* p = ltris + 3 * (size_t)(lf.y + i);
-        float4 a = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
-        // v1 = v0 + e1 may differ from the stored vertex by one rounding, and a hit the triangle test accepts numerically may
-        // lie a few ulps of the ray length outside the exact box: `pad` (world extent * 2^-20, << cell size) absorbs both
-        float v[3][3] = { { a.x, a.y, a.z }, { a.x + e1.x, a.y + e1.y, a.z + e1.z }, { a.x + e2.x, a.y + e2.y, a.z + e2.z } };
+        float clo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, chi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+        for (u32 i = c0; i < min(c0 + CLUSTER, cnt); i++)
+        {
+            const float4* p = ltris + 3 * (size_t)(first + i);
+            float4 a = p[0], e1 = p[1], e2 = p[2];
+            float v[3][3] = { { a.x, a.y, a.z }, { a.x + e1.x, a.y + e1.y, a.z + e1.z }, { a.x + e2.x, a.y + e2.y, a.z + e2.z } };
 #pragma unroll
-        for (int k = 0; k < 3; k++)
+            for (int k = 0; k < 3; k++)
 #pragma unroll
-            for (int q = 0; q < 3; q++)
-            {
-                float x = v[k][q];
-                lo[q] = fminf(lo[q], x - pad); hi[q] = fmaxf(hi[q], x + pad);
-            }
+                for (int q = 0; q < 3; q++) { clo[q] = fminf(clo[q], v[k][q] - pad); chi[q] = fmaxf(chi[q], v[k][q] + pad); }
+        }
+        float4* o = clusters + CLUSTER_F4 * (size_t)(cf + c0 / CLUSTER);
+        o[0] = make_float4(clo[0], clo[1], clo[2], chi[0]);
+        o[1] = make_float4(chi[1], chi[2], 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], clo[q]); hi[q] = fmaxf(hi[q], chi[q]); }
     }
     float* o = box6 + 6 * (size_t)l;
     o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = hi[0]; o[4] = hi[1]; o[5] = hi[2];
+    // face cap: the reference keeps the first 256 faces inserted into a leaf = the 256 smallest (mesh, triangle) ids; mark the rest
+    if (cnt > 256u)
+    {
+        for (u32 i = 0; i < cnt; i++)
+        {
+            u32 ti = __float_as_uint(ltris[3 * (size_t)(first + i)].w), rank = 0;
+            for (u32 j = 0; j < cnt; j++) rank += __float_as_uint(ltris[3 * (size_t)(first + j)].w) < ti ? 1u : 0u;
+            if (rank >= 256u)
+            {
+                float4* p = ltris + 3 * (size_t)(first + i) + 1;
+                p->w = __uint_as_float(__float_as_uint(p->w) | EXCLUDED_BIT);
+            }
+        }
+    }
 }
 
-__device__ __forceinline__ int delta(const uint4* __restrict__ leaves, int i, int j, int n)
+__device__ __forceinline__ u32 leaf_code(const float4* __restrict__ leaves, int i) { return __float_as_uint(__ldg(&leaves[LEAF_F4 * (size_t)i].x)); }
+__device__ __forceinline__ int delta(const float4* __restrict__ leaves, int i, int j, int n)
 {
     if (j < 0 || j >= n) return -1;
-    return __clz(__ldg(&leaves[i].x) ^ __ldg(&leaves[j].x));       // codes are distinct, so never 32
+    return __clz(leaf_code(leaves, i) ^ leaf_code(leaves, j));       // codes are distinct, so never 32
 }
 
 // Karras 2012, one thread per internal node i in [0, L-1)
-__global__ void karras_kernel(const uint4* __restrict__ leaves, u32 numLeaves, int D, float4* __restrict__ nodes,
+__global__ void karras_kernel(Grid g, const float4* __restrict__ leaves, u32 numLeaves, float4* __restrict__ nodes,
                               u32* __restrict__ parentOfNode, u32* __restrict__ parentOfLeaf)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n = (int)numLeaves;
     if (i >= n - 1) return;
+    const int D = g.D;
     int d = (delta(leaves, i, i + 1, n) - delta(leaves, i, i - 1, n)) >= 0 ? 1 : -1;
     int dmin = delta(leaves, i, i - d, n);
     int lmax = 2;
@@ -117,8 +148,18 @@ __global__ void karras_kernel(const uint4* __restrict__ leaves, u32 numLeaves, i
     if (c1 & LEAF_BIT) parentOfLeaf[gamma + 1] = (u32)i; else parentOfNode[gamma + 1] = (u32)i;
     if (i == 0) parentOfNode[0] = 0xFFFFFFFFu;
     int plen = dnode - (32 - D);                     // common prefix length inside the D-bit code
-    u32 prefix = plen > 0 ? (leaves[i].x >> (D - plen)) : 0u;
-    nodes[4 * (size_t)i + 3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
+    u32 prefix = plen > 0 ? (leaf_code(leaves, i) >> (D - plen)) : 0u;
+    float4* o = nodes + NODE_F4 * (size_t)i;
+    o[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
+    // the reference node's implicit box and split plane (BuildTree.cu:436-443), straight from the grid tables
+    u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
+    V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
+    int axis = plen % 3;
+    u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+    int sh = g.k[axis] - axis_bits(plen, axis);      // >= 1: the node splits on this axis
+    float sp = BM_LDG(g.tab[axis] + (((ia << 1) | 1u) << (sh - 1)));
+    o[4] = make_float4(mn.x, mn.y, mn.z, sp);
+    o[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
 }
 
 __device__ __forceinline__ void load_box(const float* p, float b[6])
@@ -139,33 +180,48 @@ __global__ void refit_kernel(u32 numLeaves, const float* __restrict__ leafBox, f
         __threadfence();
         if (atomicAdd(&visit[cur], 1u) == 0u) return;
         __threadfence();
-        float4 q3 = __ldcg(&nodes[4 * (size_t)cur + 3]);
+        float4 q3 = __ldcg(&nodes[NODE_F4 * (size_t)cur + 3]);
         u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
         float b0[6], b1[6];
         load_box((c0 & LEAF_BIT) ? leafBox + 6 * (size_t)(c0 & ~LEAF_BIT) : nodeBox + 6 * (size_t)c0, b0);
         load_box((c1 & LEAF_BIT) ? leafBox + 6 * (size_t)(c1 & ~LEAF_BIT) : nodeBox + 6 * (size_t)c1, b1);
-        nodes[4 * (size_t)cur + 0] = make_float4(b0[0], b0[1], b0[2], b0[3]);
-        nodes[4 * (size_t)cur + 1] = make_float4(b0[4], b0[5], b1[0], b1[1]);
-        nodes[4 * (size_t)cur + 2] = make_float4(b1[2], b1[3], b1[4], b1[5]);
+        nodes[NODE_F4 * (size_t)cur + 0] = make_float4(b0[0], b0[1], b0[2], b0[3]);
+        nodes[NODE_F4 * (size_t)cur + 1] = make_float4(b0[4], b0[5], b1[0], b1[1]);
+        nodes[NODE_F4 * (size_t)cur + 2] = make_float4(b1[2], b1[3], b1[4], b1[5]);
         float* o = nodeBox + 6 * (size_t)cur;
 #pragma unroll
         for (int k = 0; k < 3; k++) { __stcg(o + k, fminf(b0[k], b1[k])); __stcg(o + 3 + k, fmaxf(b0[3 + k], b1[3 + k])); }
         cur = parentOfNode[cur];
     }
 }
+
+// (code << SUB_BITS | sub, tri)  ->  (code << 32 | tri): the key whose order is the canonical (code, triangle) order
+__global__ void canonical_keys_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, size_t n, u64* __restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ((keys[i] >> SUB_BITS) << 32) | vals[i];
+}
+__global__ void split_canonical_kernel(const u64* __restrict__ keys, size_t n, u32* __restrict__ code, u32* __restrict__ tri)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (code) code[i] = (u32)(keys[i] >> 32);
+    if (tri) tri[i] = (u32)keys[i];
+}
 } // namespace
 
-int mark_heads(const u32* d_keys, size_t n, u32* d_flags, cudaStream_t s)
+int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s)
 {
     if (!n) return BM_OK;
     mark_heads_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, n, d_flags);
     BM_LAUNCHED();
     return BM_OK;
 }
-int write_leaves(const u32* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, uint4* d_leaves, cudaStream_t s)
+int write_leaves(const Grid& g, const u64* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, float4* d_leaves, u32* d_clusterCounts,
+                 cudaStream_t s)
 {
     if (!n) return BM_OK;
-    write_leaves_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, d_flags, d_leafIdx, n, numLeaves, d_leaves);
+    write_leaves_kernel<<<div_up(n, 256), 256, 0, s>>>(g, d_keys, d_flags, d_leafIdx, n, numLeaves, d_leaves, d_clusterCounts);
     BM_LAUNCHED();
     return BM_OK;
 }
@@ -176,17 +232,18 @@ int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_
     BM_LAUNCHED();
     return BM_OK;
 }
-int leaf_bounds(const uint4* d_leaves, u32 numLeaves, const float4* d_ltris, float* d_leafBox6, float pad, u32* d_stats, cudaStream_t s)
+int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_clusterFirst, float4* d_ltris, float4* d_clusters, float* d_leafBox6, float pad, u32* d_stats,
+                cudaStream_t s)
 {
     if (!numLeaves) return BM_OK;
-    leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_ltris, d_leafBox6, pad, d_stats);
+    leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_clusterFirst, d_ltris, d_clusters, d_leafBox6, pad, d_stats);
     BM_LAUNCHED();
     return BM_OK;
 }
-int emit_hierarchy(const uint4* d_leaves, u32 numLeaves, int D, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s)
+int emit_hierarchy(const Grid& g, const float4* d_leaves, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s)
 {
     if (numLeaves < 2) return BM_OK;
-    karras_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(d_leaves, numLeaves, D, d_nodes, d_parentOfNode, d_parentOfLeaf);
+    karras_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(g, d_leaves, numLeaves, d_nodes, d_parentOfNode, d_parentOfLeaf);
     BM_LAUNCHED();
     return BM_OK;
 }
@@ -196,6 +253,20 @@ int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* 
     if (numLeaves < 2) return BM_OK;
     BM_CUDA(cudaMemsetAsync(d_visit, 0, (size_t)(numLeaves - 1) * 4, s));
     refit_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(numLeaves, d_leafBox6, d_nodeBox6, d_parentOfNode, d_parentOfLeaf, d_visit, d_nodes);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, u64* d_out, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    canonical_keys_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, d_vals, n, d_out);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    split_canonical_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, n, d_code, d_tri);
     BM_LAUNCHED();
     return BM_OK;
 }

@@ -16,12 +16,14 @@ namespace
 {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;      // 4096
 constexpr int RS_BINS = 256;
+// items per thread: 16 for 4-byte keys (tile 4096), 8 for 8-byte keys (tile 2048) -- keeps static shared memory under 48 KB
+template <class K> struct RsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 8; static constexpr int TILE = RS_THREADS * ITEMS; };
 
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u32* __restrict__ keys, size_t n, int shift, u32 numTiles, u32* __restrict__ counts)
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const K* __restrict__ keys, size_t n, int shift, u32 numTiles, u32* __restrict__ counts)
 {
+    constexpr int RS_ITEMS = RsCfg<K>::ITEMS, RS_TILE = RsCfg<K>::TILE;
     __shared__ u32 hist[RS_BINS];
     hist[threadIdx.x] = 0;
     __syncthreads();
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u32* __res
     for (int i = 0; i < RS_ITEMS; i++)
     {
         size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
-        u32 d = idx < n ? ((keys[idx] >> shift) & 0xFFu) : (u32)RS_BINS;
+        u32 d = idx < n ? ((u32)(keys[idx] >> shift) & 0xFFu) : (u32)RS_BINS;
         // aggregate equal digits inside the warp before touching shared memory
         unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
         if (d < RS_BINS && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[d], (u32)__popc(peers));
@@ -39,14 +41,16 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const u32* __res
     counts[(size_t)threadIdx.x * numTiles + blockIdx.x] = hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u32* __restrict__ keysIn, const u32* __restrict__ valsIn,
-                                                                   u32* __restrict__ keysOut, u32* __restrict__ valsOut,
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const K* __restrict__ keysIn, const u32* __restrict__ valsIn,
+                                                                   K* __restrict__ keysOut, u32* __restrict__ valsOut,
                                                                    size_t n, int shift, u32 numTiles, const u32* __restrict__ scanned)
 {
+    constexpr int RS_ITEMS = RsCfg<K>::ITEMS, RS_TILE = RsCfg<K>::TILE;
     __shared__ u32 warpHist[RS_WARPS][RS_BINS + 1];     // +1: bin 256 swallows the out-of-range tail
     __shared__ u32 digitStart[RS_BINS + 1];
     __shared__ u32 globalBase[RS_BINS];
-    __shared__ u32 sKeys[RS_TILE];
+    __shared__ K sKeys[RS_TILE];
     __shared__ u32 sVals[RS_TILE];
 
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -55,13 +59,13 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u32* __
 
     const size_t tileBase = (size_t)blockIdx.x * RS_TILE;
     const size_t warpBase = tileBase + (size_t)w * (RS_ITEMS * 32);
-    u32 key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+    K key[RS_ITEMS]; u32 val[RS_ITEMS], rank[RS_ITEMS];
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++)
     {
         size_t idx = warpBase + (size_t)r * 32 + lane;
         bool ok = idx < n;
-        key[r] = ok ? keysIn[idx] : 0xFFFFFFFFu;
+        key[r] = ok ? keysIn[idx] : (K)0;
         val[r] = ok ? valsIn[idx] : 0u;
     }
     // stable rank of every item among the items of the same digit in this warp
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u32* __
     for (int r = 0; r < RS_ITEMS; r++)
     {
         size_t idx = warpBase + (size_t)r * 32 + lane;
-        u32 d = idx < n ? ((key[r] >> shift) & 0xFFu) : (u32)RS_BINS;
+        u32 d = idx < n ? ((u32)(key[r] >> shift) & 0xFFu) : (u32)RS_BINS;
         unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
         unsigned leader = __ffs(peers) - 1;
         u32 before = 0;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u32* __
         size_t idx = warpBase + (size_t)r * 32 + lane;
         if (idx < n)
         {
-            u32 d = (key[r] >> shift) & 0xFFu;
+            u32 d = (u32)(key[r] >> shift) & 0xFFu;
             u32 pos = digitStart[d] + warpHist[w][d] + rank[r];
             sKeys[pos] = key[r];
             sVals[pos] = val[r];
@@ -125,8 +129,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u32* __
         u32 pos = i * RS_THREADS + threadIdx.x;
         if (pos < valid)
         {
-            u32 k = sKeys[pos];
-            u32 d = (k >> shift) & 0xFFu;
+            K k = sKeys[pos];
+            u32 d = (u32)(k >> shift) & 0xFFu;
             size_t g = (size_t)globalBase[d] + (pos - digitStart[d]);
             keysOut[g] = k;
             valsOut[g] = sVals[pos];
@@ -137,33 +141,44 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const u32* __
 
 size_t sort_temp_bytes(size_t n)
 {
+    const size_t RS_TILE = RsCfg<u64>::TILE;      // the smaller tile -> the larger table
     size_t tiles = (n + RS_TILE - 1) / RS_TILE;
     size_t counts = ((tiles * RS_BINS * 4 + 255) / 256) * 256;
     return counts + scan_temp_bytes(tiles * RS_BINS);
 }
 
-int radix_sort_pairs(u32* d_keysA, u32* d_valsA, u32* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB)
+template <class K>
+static int radix_sort_impl(K* d_keysA, u32* d_valsA, K* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB)
 {
     int passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
     *resultInB = passes & 1;
     if (n == 0) return BM_OK;
+    const size_t RS_TILE = RsCfg<K>::TILE;
     size_t tiles = (n + RS_TILE - 1) / RS_TILE;
     u32* counts = (u32*)d_temp;
     void* scanTemp = (char*)d_temp + ((tiles * RS_BINS * 4 + 255) / 256) * 256;
-    u32 *ka = d_keysA, *va = d_valsA, *kb = d_keysB, *vb = d_valsB;
+    K *ka = d_keysA, *kb = d_keysB; u32 *va = d_valsA, *vb = d_valsB;
     for (int p = 0; p < passes; p++)
     {
         int shift = 8 * p;
-        radix_hist_kernel<<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, n, shift, (u32)tiles, counts);
+        radix_hist_kernel<K><<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, n, shift, (u32)tiles, counts);
         BM_LAUNCHED();
         BM_TRY(exclusive_scan_u32(counts, counts, tiles * RS_BINS, nullptr, scanTemp, s));
-        radix_scatter_kernel<<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, (u32)tiles, counts);
+        radix_scatter_kernel<K><<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, shift, (u32)tiles, counts);
         BM_LAUNCHED();
-        u32* t;
-        t = ka; ka = kb; kb = t;
-        t = va; va = vb; vb = t;
+        K* t = ka; ka = kb; kb = t;
+        u32* tv = va; va = vb; vb = tv;
     }
     return BM_OK;
+}
+
+int radix_sort_pairs(u32* d_keysA, u32* d_valsA, u32* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB)
+{
+    return radix_sort_impl<u32>(d_keysA, d_valsA, d_keysB, d_valsB, n, bits, d_temp, s, resultInB);
+}
+int radix_sort_pairs64(u64* d_keysA, u32* d_valsA, u64* d_keysB, u32* d_valsB, size_t n, int bits, void* d_temp, cudaStream_t s, int* resultInB)
+{
+    return radix_sort_impl<u64>(d_keysA, d_valsA, d_keysB, d_valsB, n, bits, d_temp, s, resultInB);
 }
 } // namespace bm

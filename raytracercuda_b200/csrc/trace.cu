@@ -28,21 +28,15 @@ __device__ __forceinline__ V3 f4xyz(float4 a) { return mk3(a.x, a.y, a.z); }
 // (BuildTree.cu:398-481), children whose tight box the ray's line misses are not pushed.
 __device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d, V3 inv, u32* stack, int& top)
 {
-    const Grid& g = tv.grid;
-    const float4* np = tv.nodes + 4 * (size_t)ref;
-    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-    u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), prefix = __float_as_uint(q3.z);
-    int plen = (int)__float_as_uint(q3.w);
-    u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
-    V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
-    float boxDist = box_ray(mn, mx, o, inv);
+    const float4* np = tv.nodes + NODE_F4 * (size_t)ref;
+    float4 q4 = __ldg(np + 4), q5 = __ldg(np + 5);
+    float boxDist = box_ray(mk3(q4.x, q4.y, q4.z), mk3(q5.x, q5.y, q5.z), o, inv);     // the node's cell, :398
     if (boxDist == FLT_MAX) return;
-    int axis = plen % 3;
-    u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
-    int sh = g.k[axis] - axis_bits(plen, axis);                            // >= 1: the node splits on this axis
-    float s = BM_LDG(g.tab[axis] + (((ia << 1) | 1u) << (sh - 1)));        // == .5f*(max+min) of the cell, :443
-    float p = get(o, axis) + boxDist * get(d, axis);                       // :444
-    bool leftFirst = p < s;
+    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
+    int axis = (int)__float_as_uint(q5.w);
+    float p = get(o, axis) + boxDist * get(d, axis);                                   // :444
+    bool leftFirst = p < q4.w;                                                          // s = .5f*(max+min) of the cell, :443
     bool h0 = line_hits_box(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), o, inv);
     bool h1 = line_hits_box(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), o, inv);
     u32 nearRef = leftFirst ? c0 : c1, farRef = leftFirst ? c1 : c0;
@@ -65,7 +59,7 @@ __device__ __forceinline__ bool box_interval(V3 bMin, V3 bMax, V3 o, V3 inv, flo
 // whose box lies beyond the hit found meanwhile is rejected again when its own node is visited (its children fail).
 __device__ __forceinline__ void closest_node(const TreeView& tv, u32 ref, V3 o, V3 inv, float tbest, u32* stack, int& top)
 {
-    const float4* np = tv.nodes + 4 * (size_t)ref;
+    const float4* np = tv.nodes + NODE_F4 * (size_t)ref;
     float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
     u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
     float t0, t1;
@@ -78,15 +72,22 @@ __device__ __forceinline__ void closest_node(const TreeView& tv, u32 ref, V3 o, 
     if (nearHit) stack[++top] = nearRef;
 }
 
-__device__ __forceinline__ void test_face(float4 a, float4 b, float4 c, V3 o, V3 d, bool forwardOnly, HitRec& best)
+// One face against the ray.  The reference keeps the strict minimum while walking the leaf's list in insertion order, i.e. on
+// equal d the face inserted first = the smaller (mesh, triangle) id wins (BuildTree.cu:413-424); the pairs of a leaf are stored
+// in sub-key order here, so the tie is broken on the id explicitly.
+template <int MODE>
+__device__ __forceinline__ void test_face(float4 a, float4 b, float4 c, V3 o, V3 d, HitRec& best)
 {
+    u32 meshBits = __float_as_uint(b.w);
+    if (MODE == BM_TRACE_REFERENCE && (meshBits & EXCLUDED_BIT)) return;       // beyond the 256-face cap of its leaf
     float u, v;
     float dd = tri_intersect(o, d, f4xyz(a), f4xyz(b), f4xyz(c), u, v);
-    if (forwardOnly && !(dd >= 0.f)) return;
-    if (dd < best.t)                                                       // strict: the first face in list order wins a tie
+    if (MODE != BM_TRACE_REFERENCE && !(dd >= 0.f)) return;
+    u32 tri = __float_as_uint(a.w);
+    if (dd < best.t || (dd == best.t && dd != FLT_MAX && tri < best.tri))
     {
         best.t = dd; best.u = u; best.v = v;
-        best.tri = __float_as_uint(a.w); best.mesh = __float_as_uint(b.w); best.face = __float_as_uint(c.w);
+        best.tri = tri; best.mesh = meshBits & ~EXCLUDED_BIT; best.face = __float_as_uint(c.w);
     }
 }
 
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
     u64 rayIdx = 0;
     V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1);
     HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
-    u32 nv = 0, nt = 0;
+    u32 nv = 0, nt = 0, nc = 0;
 
     for (;;)
     {
@@ -206,33 +207,70 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
             }
         }
 
-        // ---- phase 2: one pending leaf per lane, triangles tested in lock step ------------------------------------------------
+        // ---- phase 2: one pending leaf per lane ---------------------------------------------------------------------------------
+        // stage A: every lane scans the cluster boxes of its leaf (groups of CLUSTER faces) and keeps a bit mask of the groups the
+        // ray's line meets; stage B: lanes pop one group at a time and test its faces in lock step.  Both loops are warp-uniform.
         bool finished = false;
         {
             bool isLeaf = active && cur != REF_EMPTY;          // after phase 1 a pending ref is a leaf
-            u32 first = 0, cnt = 0;
+            u32 first = 0, cnt = 0, cfirst = 0;
             if (isLeaf)
             {
                 if (COUNT) nv++;
-                uint4 lf = __ldg(tv.leaves + (cur & ~LEAF_BIT));
-                first = lf.y;
+                const float4* lp = tv.leaves + LEAF_F4 * (size_t)(cur & ~LEAF_BIT);
+                float4 r0 = __ldg(lp);
+                first = __float_as_uint(r0.y); cfirst = __float_as_uint(r0.w);
                 if (MODE == BM_TRACE_REFERENCE)
                 {
-                    u32 ix, iy, iz; decode_path(tv.grid.D, lf.x, ix, iy, iz);
-                    V3 mn, mx; cell_box(tv.grid, tv.grid.D, ix, iy, iz, mn, mx);
-                    if (box_ray(mn, mx, o, inv) != FLT_MAX) cnt = min(lf.z, tv.maxLeafFaces);      // BuildTree.cu:405-411
+                    float4 r1 = __ldg(lp + 1), r2 = __ldg(lp + 2);
+                    if (box_ray(mk3(r1.x, r1.y, r1.z), mk3(r1.w, r2.x, r2.y), o, inv) != FLT_MAX) cnt = __float_as_uint(r0.z);      // BuildTree.cu:405-406
                 }
-                else cnt = lf.z;
+                else cnt = __float_as_uint(r0.z);
             }
-            u32 maxCnt = __reduce_max_sync(FULL, cnt);
-            const float4* p = tv.ltris + 3 * (size_t)first;
-            for (u32 i = 0; i < maxCnt; i++, p += 3)
+            u32 ncl = (cnt + CLUSTER - 1) / CLUSTER;
+            bool big = ncl > 64u;                                          // > 256 faces in one leaf: no mask, test everything (rare)
+            unsigned long long mask = (cnt && cnt <= (u32)CLUSTER) ? 1ull : 0ull;   // a single group: its box is the leaf box the parent tested
+            u32 scan = (cnt > (u32)CLUSTER && !big) ? ncl : 0u;            // groups whose boxes this lane has to look at
+            u32 maxScan = __reduce_max_sync(FULL, scan);
             {
-                if (i < cnt)
+                const float4* cp = tv.clusters + CLUSTER_F4 * (size_t)cfirst;
+                for (u32 i = 0; i < maxScan; i++, cp += CLUSTER_F4)
                 {
-                    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-                    if (COUNT) nt++;
-                    test_face(a, b, c, o, d, MODE != BM_TRACE_REFERENCE, best);
+                    if (i < scan)
+                    {
+                        float4 b0 = __ldg(cp), b1 = __ldg(cp + 1);
+                        if (COUNT) nc++;
+                        if (line_hits_box(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), o, inv)) mask |= 1ull << i;
+                    }
+                }
+            }
+            while (__any_sync(FULL, mask != 0ull))
+            {
+                if (mask)
+                {
+                    u32 g = (u32)__ffsll((long long)mask) - 1u;
+                    mask &= mask - 1ull;
+                    u32 i0 = g * CLUSTER, i1 = min(i0 + CLUSTER, cnt);
+                    const float4* p = tv.ltris + 3 * (size_t)(first + i0);
+                    for (u32 i = i0; i < i1; i++, p += 3)
+                    {
+                        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+                        if (COUNT) nt++;
+                        test_face<MODE>(a, b, c, o, d, best);
+                    }
+                }
+            }
+            if (__any_sync(FULL, big))
+            {
+                if (big)
+                {
+                    const float4* p = tv.ltris + 3 * (size_t)first;
+                    for (u32 i = 0; i < cnt; i++, p += 3)
+                    {
+                        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+                        if (COUNT) nt++;
+                        test_face<MODE>(a, b, c, o, d, best);
+                    }
                 }
             }
             if (isLeaf)
@@ -252,10 +290,14 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
     }
     if (COUNT)
     {
-        u64 a = nv, b = nt;
+        u64 a = nv, b = nt, c = nc;
 #pragma unroll
-        for (int k = 16; k > 0; k >>= 1) { a += __shfl_down_sync(FULL, a, k); b += __shfl_down_sync(FULL, b, k); }
-        if (lane == 0) { atomicAdd((unsigned long long*)&counters[0], (unsigned long long)a); atomicAdd((unsigned long long*)&counters[1], (unsigned long long)b); }
+        for (int k = 16; k > 0; k >>= 1) { a += __shfl_down_sync(FULL, a, k); b += __shfl_down_sync(FULL, b, k); c += __shfl_down_sync(FULL, c, k); }
+        if (lane == 0)
+        {
+            atomicAdd((unsigned long long*)&counters[0], (unsigned long long)a); atomicAdd((unsigned long long*)&counters[1], (unsigned long long)b);
+            atomicAdd((unsigned long long*)&counters[2], (unsigned long long)c);
+        }
     }
 }
 

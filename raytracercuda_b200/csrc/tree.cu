@@ -60,8 +60,8 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp;
-    u32* sortedKeys = nullptr; u32* sortedVals = nullptr;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV;
+    u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
     u32 maxLeaf = 0, overLeaves = 0;
     u32 hostScalars[8];
@@ -69,13 +69,13 @@ struct bmTree
     TreeView view() const
     {
         TreeView v;
-        v.grid = dgrid; v.nodes = nodes.as<float4>(); v.leaves = leaves.as<uint4>(); v.ltris = ltris.as<float4>();
-        v.numLeaves = (u32)L; v.rootRef = (L == 1) ? (0u | LEAF_BIT) : 0u; v.maxLeafFaces = 256;
+        v.nodes = nodes.as<float4>(); v.leaves = leaves.as<float4>(); v.ltris = ltris.as<float4>(); v.clusters = clusters.as<float4>();
+        v.numLeaves = (u32)L; v.rootRef = (L == 1) ? (0u | LEAF_BIT) : 0u;
         return v;
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -109,38 +109,41 @@ static int tree_build(bmTree* t)
     u64 P = t->hostScalars[0];
     t->P = P;
     if (P == 0) { t->built = true; return BM_OK; }      // every triangle outside the world box
-    // 3. emit + sort
-    BM_TRY(t->keysA.reserve(P * 4)); BM_TRY(t->valsA.reserve(P * 4)); BM_TRY(t->keysB.reserve(P * 4)); BM_TRY(t->valsB.reserve(P * 4));
+    // 3. emit + sort: key = leaf code (D bits) | in-cell sub-key (SUB_BITS), payload = triangle id
+    BM_TRY(t->keysA.reserve(P * 8)); BM_TRY(t->valsA.reserve(P * 4)); BM_TRY(t->keysB.reserve(P * 8)); BM_TRY(t->valsB.reserve(P * 4));
     BM_TRY(t->temp.reserve(sort_temp_bytes(P) > scan_temp_bytes(P) ? sort_temp_bytes(P) : scan_temp_bytes(P)));
-    BM_TRY(emit_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->keysA.as<u32>(), t->valsA.as<u32>(), s));
+    BM_TRY(emit_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->keysA.as<u64>(), t->valsA.as<u32>(), s));
     int inB = 0;
-    BM_TRY(radix_sort_pairs(t->keysA.as<u32>(), t->valsA.as<u32>(), t->keysB.as<u32>(), t->valsB.as<u32>(), P, t->hgrid.D, t->temp.p, s, &inB));
-    t->sortedKeys = inB ? t->keysB.as<u32>() : t->keysA.as<u32>();
+    BM_TRY(radix_sort_pairs64(t->keysA.as<u64>(), t->valsA.as<u32>(), t->keysB.as<u64>(), t->valsB.as<u32>(), P, t->hgrid.D + SUB_BITS, t->temp.p, s, &inB));
+    t->sortedKeys = inB ? t->keysB.as<u64>() : t->keysA.as<u64>();
     t->sortedVals = inB ? t->valsB.as<u32>() : t->valsA.as<u32>();
-    u32* spareKeys = inB ? t->keysA.as<u32>() : t->keysB.as<u32>();   // reused as leaf index per pair
+    u32* leafIdx = inB ? t->valsA.as<u32>() : t->valsB.as<u32>();     // the spare payload buffer: leaf index per pair
     // 4. leaves
     BM_TRY(t->flags.reserve(P * 4));
     BM_TRY(mark_heads(t->sortedKeys, P, t->flags.as<u32>(), s));
-    BM_TRY(exclusive_scan_u32(t->flags.as<u32>(), spareKeys, P, d_scal + 1, t->temp.p, s));
+    BM_TRY(exclusive_scan_u32(t->flags.as<u32>(), leafIdx, P, d_scal + 1, t->temp.p, s));
     BM_CUDA(cudaMemcpyAsync(&t->hostScalars[1], d_scal + 1, 4, cudaMemcpyDeviceToHost, s));
     BM_TRY(t->ltris.reserve(P * 48));
     BM_TRY(pack_leaf_tris(t->soup.as<float4>(), t->sortedVals, P, t->ltris.as<float4>(), s));      // overlaps the read-back
     BM_CUDA(cudaStreamSynchronize(s));
     u64 L = t->hostScalars[1];
     t->L = L;
-    BM_TRY(t->leaves.reserve(L * 16));
-    BM_TRY(write_leaves(t->sortedKeys, t->flags.as<u32>(), spareKeys, P, (u32)L, t->leaves.as<uint4>(), s));
+    BM_TRY(t->leaves.reserve(L * 16 * LEAF_F4)); BM_TRY(t->clusterCounts.reserve(L * 4 + 4));
+    BM_TRY(write_leaves(t->dgrid, t->sortedKeys, t->flags.as<u32>(), leafIdx, P, (u32)L, t->leaves.as<float4>(), t->clusterCounts.as<u32>(), s));
+    BM_TRY(exclusive_scan_u32(t->clusterCounts.as<u32>(), t->clusterCounts.as<u32>(), L, nullptr, t->temp.p, s));
+    BM_TRY(t->clusters.reserve((P / CLUSTER + L + 1) * 16 * CLUSTER_F4));
     BM_TRY(t->leafBox.reserve(L * 24));
     float ext = 0.f;
     for (int a = 0; a < 3; a++) ext = fmaxf(ext, t->hgrid.wmax[a] - t->hgrid.wmin[a]);
     float pad = ext * (1.f / 1048576.f);
-    BM_TRY(leaf_bounds(t->leaves.as<uint4>(), (u32)L, t->ltris.as<float4>(), t->leafBox.as<float>(), pad, d_scal + 2, s));
+    BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(), t->leafBox.as<float>(), pad,
+                       d_scal + 2, s));
     // 5. hierarchy + refit
     if (L >= 2)
     {
-        BM_TRY(t->nodes.reserve((L - 1) * 64)); BM_TRY(t->nodeBox.reserve((L - 1) * 24));
+        BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4)); BM_TRY(t->nodeBox.reserve((L - 1) * 24));
         BM_TRY(t->parentN.reserve((L - 1) * 4)); BM_TRY(t->parentL.reserve(L * 4)); BM_TRY(t->visit.reserve((L - 1) * 4));
-        BM_TRY(emit_hierarchy(t->leaves.as<uint4>(), (u32)L, t->hgrid.D, t->nodes.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), s));
+        BM_TRY(emit_hierarchy(t->dgrid, t->leaves.as<float4>(), (u32)L, t->nodes.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), s));
         BM_TRY(refit((u32)L, t->leafBox.as<float>(), t->nodeBox.as<float>(), t->parentN.as<u32>(), t->parentL.as<u32>(), t->visit.as<u32>(), t->nodes.as<float4>(), s));
     }
     t->built = true;
@@ -222,13 +225,21 @@ extern "C" int bmTreeStats(const bmTree* tc, uint64_t* s)
     return BM_OK;
 }
 
-extern "C" int bmTreeCopyPairs(const bmTree* t, uint32_t* d_code, uint32_t* d_tri)
+extern "C" int bmTreeCopyPairs(const bmTree* tc, uint32_t* d_code, uint32_t* d_tri)
 {
+    bmTree* t = const_cast<bmTree*>(tc);
     if (!t) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) return BM_ERROR_NOT_BUILT;
     if (!t->P) return BM_OK;
-    if (d_code) BM_CUDA(cudaMemcpyAsync(d_code, t->sortedKeys, t->P * 4, cudaMemcpyDeviceToDevice, t->stream));
-    if (d_tri) BM_CUDA(cudaMemcpyAsync(d_tri, t->sortedVals, t->P * 4, cudaMemcpyDeviceToDevice, t->stream));
+    // The tree keeps the pairs of a leaf in sub-key order; the canonical list parity is defined on is ordered by
+    // (code, global triangle id).  It is produced here on request: rekey to code<<32|tri and sort (not part of the build).
+    size_t P = t->P;
+    BM_TRY(t->canonA.reserve(P * 8)); BM_TRY(t->canonB.reserve(P * 8)); BM_TRY(t->canonV.reserve(P * 8));
+    BM_TRY(t->temp.reserve(sort_temp_bytes(P)));
+    BM_TRY(canonical_keys(t->sortedKeys, t->sortedVals, P, t->canonA.as<u64>(), t->stream));
+    int inB = 0;
+    BM_TRY(radix_sort_pairs64(t->canonA.as<u64>(), t->canonV.as<u32>(), t->canonB.as<u64>(), t->canonV.as<u32>() + P, P, 32 + t->hgrid.D, t->temp.p, t->stream, &inB));
+    BM_TRY(split_canonical(inB ? t->canonB.as<u64>() : t->canonA.as<u64>(), P, d_code, d_tri, t->stream));
     return BM_OK;
 }
 
@@ -239,10 +250,11 @@ extern "C" int bmTreeCopyTopology(const bmTree* t, uint32_t* d_prefixLen, uint32
     if (t->L < 2) return BM_OK;
     size_t N = t->L - 1;
     const char* q3 = (const char*)t->nodes.p + 48;
-    if (d_child0)    BM_CUDA(cudaMemcpy2DAsync(d_child0, 4, q3 + 0, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
-    if (d_child1)    BM_CUDA(cudaMemcpy2DAsync(d_child1, 4, q3 + 4, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
-    if (d_prefix)    BM_CUDA(cudaMemcpy2DAsync(d_prefix, 4, q3 + 8, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
-    if (d_prefixLen) BM_CUDA(cudaMemcpy2DAsync(d_prefixLen, 4, q3 + 12, 64, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    const size_t stride = 16 * NODE_F4;
+    if (d_child0)    BM_CUDA(cudaMemcpy2DAsync(d_child0, 4, q3 + 0, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    if (d_child1)    BM_CUDA(cudaMemcpy2DAsync(d_child1, 4, q3 + 4, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    if (d_prefix)    BM_CUDA(cudaMemcpy2DAsync(d_prefix, 4, q3 + 8, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
+    if (d_prefixLen) BM_CUDA(cudaMemcpy2DAsync(d_prefixLen, 4, q3 + 12, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
     return BM_OK;
 }
 
@@ -251,7 +263,7 @@ extern "C" int bmTreeCopyChildBoxes(const bmTree* t, float* d_boxes12)
     if (!t) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) return BM_ERROR_NOT_BUILT;
     if (t->L < 2) return BM_OK;
-    BM_CUDA(cudaMemcpy2DAsync(d_boxes12, 48, t->nodes.p, 64, 48, t->L - 1, cudaMemcpyDeviceToDevice, t->stream));
+    BM_CUDA(cudaMemcpy2DAsync(d_boxes12, 48, t->nodes.p, 16 * NODE_F4, 48, t->L - 1, cudaMemcpyDeviceToDevice, t->stream));
     return BM_OK;
 }
 

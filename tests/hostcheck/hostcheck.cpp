@@ -7,7 +7,7 @@
 #include "../../raytracercuda_b200/csrc/bm_grid_host.h"
 using namespace bm;
 
-struct Collect { std::vector<uint64_t>* out; uint32_t tri; void operator()(u32 code) const { out->push_back(((uint64_t)code << 32) | tri); } };
+struct Collect { std::vector<uint64_t>* out; uint32_t tri; void operator()(u32 code, u32, u32, u32) const { out->push_back(((uint64_t)code << 32) | tri); } };
 
 extern "C"
 {
