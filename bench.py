@@ -155,18 +155,20 @@ def run_b200(args):
         if marks is not None: marks[1].record()
         total = n
         if wl.bounces:
-            tree.camera_rays(rays_in, eye, orient, width=W, out=rays1)
-            tree.bounce_rays(rays1, hits1, sample=0, bounce=1, seed=args.seed, out=rays2, src=src2, count=cnt2)
-            cnt_host.copy_(cnt2, non_blocking=True)
-            stream.synchronize()
-            nb = int(cnt_host[0])
+            _lib.check(L.bmBounceRaysCamera(tree.h, rays_in.data_ptr(), _f3(eye), _f9(orient), hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(),
+                                            src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
             if marks is not None: marks[2].record()
-            _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), None), "bmTraceRays")
-            total += nb
+            # the bounce count stays on the device: the trace kernel reads it there (no host round trip inside the step)
+            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, 0, hits2.data_ptr(), None), "bmTraceRaysIndirect")
+            cnt_host.copy_(cnt2, non_blocking=True)
         if marks is not None: marks[3].record()
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), pixels)
         return total
+
+    def bounce_count():
+        stream.synchronize()
+        return int(cnt_host[0]) if wl.bounces else 0
 
     import ctypes as C
     _f3 = lambda a: (C.c_float * 3)(*[float(x) for x in a])
@@ -180,7 +182,7 @@ def run_b200(args):
 
     # --- warm-up -------------------------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        rays_step = frame(rays_dev)
+        rays_step = frame(rays_dev) + bounce_count()
     # per-ray traversal counters of the same traversal (instrumented launch, outside the timed region)
     cnt = torch.zeros(3, dtype=torch.int64, device=dev)
     _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
@@ -209,6 +211,7 @@ def run_b200(args):
         total_rays += frame(rays_dev, marks)
         e1.record()
         sync_all()
+        total_rays += bounce_count()
         step_ms.append(e0.elapsed_time(e1)); prim_ms.append(marks[0].elapsed_time(marks[1]))
         bounce_ms.append(marks[2].elapsed_time(marks[3]) if wl.bounces else 0.0)
     clocks = sampler.stop()
@@ -225,10 +228,11 @@ def run_b200(args):
         r = rays_dev.copy_(rays_pinned, non_blocking=True)
         total = frame(r)
         pix_host.copy_(pixels, non_blocking=True)
-        if wl.bounces:
-            hits2_host[: int(cnt_host[0])].copy_(hits2[: int(cnt_host[0])], non_blocking=True)
+        nbk = bounce_count()                      # the host needs the count to size the read-back of the bounce hits
+        if nbk:
+            hits2_host[:nbk].copy_(hits2[:nbk], non_blocking=True)
         stream.synchronize()
-        return total
+        return total + nbk
     for _ in range(2):
         frame_e2e()
     e2e_ms, e2e_rays = [], 0

@@ -138,6 +138,9 @@ int  bmTreeMeshBases(const bmTree* tree, uint32_t* h_bases, uint32_t capacity); 
 /* Explicit ray batch -> hit records. d_counters (nullable) accumulates {node + leaf visits, triangle tests, cluster boxes tested}
  * into three uint64 (the traversal work behind the bytes-per-ray roofline model). */
 int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters);
+/* Same, with the ray count read from DEVICE memory when the kernel starts (*d_numRays <= maxRays): lets a producer such as
+ * bmBounceRays feed the trace without a host round trip. */
+int  bmTraceRaysIndirect(bmTree* tree, const bmRay* d_rays, const uint32_t* d_numRays, uint64_t maxRays, int mode, bmHit* d_hits, uint64_t* d_counters);
 /* Camera rays (dir = orient * initialRays[i] from eye), hit records and/or shaded pixels (either may be null).
  * width = row length of the image the table describes (numRays % width == 0): warps then start on 8x4 pixel tiles; 0 = trace in
  * linear order.  Results are always written at index i of the table, whatever the order of traversal. */
@@ -155,6 +158,9 @@ int  bmCameraRays(const float* d_initialRays3, uint64_t numRays, uint32_t width,
                   float jitterX, float jitterY, uint32_t sample, uint32_t seed, bmRay* d_out, void* cudaStream);
 int  bmBounceRays(bmTree* tree, const bmRay* d_rays, const bmHit* d_hits, uint64_t numRays, uint32_t sample, uint32_t bounce,
                   uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count);
+/* bmBounceRays for the hits of a bmTraceCamera / bmMarch launch: the primary rays are re-formed from the camera table */
+int  bmBounceRaysCamera(bmTree* tree, const float* d_initialRays3, const float* eye3, const float* orient9, const bmHit* d_hits,
+                        uint64_t numRays, uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count);
 
 /* Spatial-hash key functions of Hash.cu:17-64 evaluated on the device (bit-exact targets):
  * out[i] = bmHash3(make_uint3(bmMap(x), bmMap(y), bmMap(z))) and the three bmMap cell coordinates. */

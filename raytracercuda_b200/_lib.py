@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
     "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases",
-    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays",
+    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
     "beamMeshCreate", "beamMeshDestroy", "beamMeshSetVertexData", "beamMeshSetIndices",
@@ -79,6 +79,8 @@ def load() -> C.CDLL:
     L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]
     L.bmCameraRays.argtypes = [vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, u32, u32, vp, vp]
     L.bmBounceRays.argtypes = [vp, vp, vp, u64, u32, u32, u32, vp, vp, vp]
+    L.bmBounceRaysCamera.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, u64, u32, u32, u32, vp, vp, vp]
+    L.bmTraceRaysIndirect.argtypes = [vp, vp, vp, u64, i32, vp, vp]
     L.bmResetScene.argtypes = [vp] * 7 + [u32] * 3; L.bmResetScene.restype = None
     L.bmInsertMeshInTree.argtypes = [vp, vp, u32, u32, bmVec3, bmVec3, vp, vp, vp, vp, vp]; L.bmInsertMeshInTree.restype = None
     L.bmMarch.argtypes = [vp, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, u32, u32, u32, C.POINTER(bmVec3), C.POINTER(bmMat3), vp]

@@ -87,14 +87,15 @@ int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaSt
 // ---- trace.cu -------------------------------------------------------------------------------------------------------
 struct CameraIn { const float* initialRays; float eye[3]; float orient[9]; };
 // d_workCounter: one u32 of device scratch per launch in flight (the persistent warps' work queue head)
-int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s);
+// d_numRays (nullable): the ray count is read from device memory at kernel start (<= n, which then only sizes the grid)
+int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numRays, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s);
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
                  u64* d_counters, u32* d_workCounter, cudaStream_t s);
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
 
 // ---- rays.cu --------------------------------------------------------------------------------------------------------
 int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* d_out, cudaStream_t s);
-int bounce_rays(const bmRay* d_rays, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed, u32* d_flagsAndOffsets,
-                void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s);
+int bounce_rays(const bmRay* d_rays, const CameraIn* cam, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed,
+                u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s);
 int hash_keys(const float* d_points3, u64 n, u32* d_hash, i32* d_cells3, cudaStream_t s);
 } // namespace bm

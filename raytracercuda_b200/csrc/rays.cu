@@ -51,7 +51,8 @@ __global__ void hit_flags_kernel(const bmHit* __restrict__ hits, u64 n, u32* __r
     flags[i] = hits[i].tri != 0xFFFFFFFFu ? 1u : 0u;
 }
 
-__global__ void bounce_kernel(const bmRay* __restrict__ rays, const bmHit* __restrict__ hits, const u32* __restrict__ offsets, u64 n,
+template <bool CAMERA>
+__global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, const bmHit* __restrict__ hits, const u32* __restrict__ offsets, u64 n,
                               const float4* __restrict__ soup, u32 sample, u32 bounce, u32 seed, bmRay* __restrict__ out, u32* __restrict__ srcIndex)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +60,17 @@ __global__ void bounce_kernel(const bmRay* __restrict__ rays, const bmHit* __res
     float4 hf = reinterpret_cast<const float4*>(hits)[i];
     u32 tri = __float_as_uint(hf.w);
     if (tri == 0xFFFFFFFFu) return;
-    bmRay r = rays[i];
+    bmRay r;
+    if (CAMERA)
+    {
+        // the primary ray exactly as bmMarch / bmTraceCamera formed it (dir = orient * initialRays[i] from eye)
+        const float* q = cam.initialRays + 3 * i;
+        float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+        const float* m = cam.orient;
+        r.o[0] = cam.eye[0]; r.o[1] = cam.eye[1]; r.o[2] = cam.eye[2];
+        r.d[0] = m[0] * x + m[3] * y + m[6] * z; r.d[1] = m[1] * x + m[4] * y + m[7] * z; r.d[2] = m[2] * x + m[5] * y + m[8] * z;
+    }
+    else r = rays[i];
     const float4* p = soup + 3 * (size_t)tri;
     float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     V3 e1 = mk3(b.x - a.x, b.y - a.y, b.z - a.z), e2 = mk3(c.x - a.x, c.y - a.y, c.z - a.z);
@@ -96,14 +107,15 @@ int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitt
     return BM_OK;
 }
 
-int bounce_rays(const bmRay* d_rays, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed, u32* d_flagsAndOffsets,
-                void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s)
+int bounce_rays(const bmRay* d_rays, const CameraIn* cam, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed,
+                u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s)
 {
     if (!n) { BM_CUDA(cudaMemsetAsync(d_count, 0, 4, s)); return BM_OK; }
     hit_flags_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits, n, d_flagsAndOffsets);
     BM_LAUNCHED();
     BM_TRY(exclusive_scan_u32(d_flagsAndOffsets, d_flagsAndOffsets, n, d_count, d_scanTemp, s));
-    bounce_kernel<<<div_up(n, 256), 256, 0, s>>>(d_rays, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex);
+    if (cam) bounce_kernel<true><<<div_up(n, 256), 256, 0, s>>>(nullptr, *cam, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex);
+    else { CameraIn none = {}; bounce_kernel<false><<<div_up(n, 256), 256, 0, s>>>(d_rays, none, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex); }
     BM_LAUNCHED();
     return BM_OK;
 }

@@ -23,22 +23,36 @@ struct HitRec { float t, u, v; u32 tri, mesh, face; };
 
 __device__ __forceinline__ V3 f4xyz(float4 a) { return mk3(a.x, a.y, a.z); }
 
+// Conservative LINE/box cull on the padded tight boxes, one FMA per slab plane: t = b*inv - o*inv with o*inv hoisted per ray.
+// Its rounding differs from (b-o)*inv by at most |o|*2^-24 in space, far inside the boxes' pad (world extent * 2^-20), and a NaN
+// (0*inf, inf-inf on axis-parallel rays) drops out of fminf/fmaxf, i.e. that slab simply does not cull.  Never decides a result:
+// it only skips subtrees / face groups that cannot contain a hit.
+__device__ __forceinline__ bool line_hits_box_fma(V3 bMin, V3 bMax, V3 inv, V3 oi)
+{
+    float x0 = __fmaf_rn(bMin.x, inv.x, -oi.x), x1 = __fmaf_rn(bMax.x, inv.x, -oi.x);
+    float y0 = __fmaf_rn(bMin.y, inv.y, -oi.y), y1 = __fmaf_rn(bMax.y, inv.y, -oi.y);
+    float z0 = __fmaf_rn(bMin.z, inv.z, -oi.z), z1 = __fmaf_rn(bMax.z, inv.z, -oi.z);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return !(tf < tn);
+}
+
 // ---- one step of each traversal flavour, shared by every kernel variant -------------------------------------------------
 // Internal node in REFERENCE mode: cell test with the reference's slab arithmetic, child order by the split plane
 // (BuildTree.cu:398-481), children whose tight box the ray's line misses are not pushed.
-__device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d, V3 inv, u32* stack, int& top)
+__device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d, V3 inv, V3 oi, u32* stack, int& top)
 {
     const float4* np = tv.nodes + NODE_F4 * (size_t)ref;
-    float4 q4 = __ldg(np + 4), q5 = __ldg(np + 5);
+    // all six quads at once: the node is one 128-byte L1 line, and a second dependent round trip would double the latency
+    float4 q4 = __ldg(np + 4), q5 = __ldg(np + 5), q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
     float boxDist = box_ray(mk3(q4.x, q4.y, q4.z), mk3(q5.x, q5.y, q5.z), o, inv);     // the node's cell, :398
     if (boxDist == FLT_MAX) return;
-    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
     u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
     int axis = (int)__float_as_uint(q5.w);
     float p = get(o, axis) + boxDist * get(d, axis);                                   // :444
     bool leftFirst = p < q4.w;                                                          // s = .5f*(max+min) of the cell, :443
-    bool h0 = line_hits_box(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), o, inv);
-    bool h1 = line_hits_box(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), o, inv);
+    bool h0 = line_hits_box_fma(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), inv, oi);
+    bool h1 = line_hits_box_fma(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), inv, oi);
     u32 nearRef = leftFirst ? c0 : c1, farRef = leftFirst ? c1 : c0;
     bool nearHit = leftFirst ? h0 : h1, farHit = leftFirst ? h1 : h0;
     if (farHit) stack[++top] = farRef;
@@ -140,9 +154,10 @@ __device__ __forceinline__ bool slot_to_ray(u32 slot, u64 n, u32 width, u32 heig
 // 32 lanes were active on average because leaf loops and node walks of different lanes serialised each other.
 template <int MODE, bool CAMERA, bool COUNT>
 __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
-                                                           u32 totalSlots, bmHit* __restrict__ hits, u32* __restrict__ pixels,
+                                                           u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
                                                            const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter)
 {
+    if (numRaysDev) { n = __ldg(numRaysDev); totalSlots = (u32)n; }       // count produced on the device (bmBounceRays): no host round trip
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
     u32 stack[TR_STACK];
@@ -150,7 +165,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
     u32 cur = REF_EMPTY;
     bool active = false, exhausted = false;
     u64 rayIdx = 0;
-    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1);
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), oi = mk3(0, 0, 0);
     HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
     u32 nv = 0, nt = 0, nc = 0;
 
@@ -184,6 +199,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
                         d = mk3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
                     }
                     inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+                    oi = o * inv;
                     best.t = FLT_MAX; best.u = 0.f; best.v = 0.f; best.tri = best.mesh = best.face = 0xFFFFFFFFu;
                     top = -1;
                     cur = tv.numLeaves ? tv.rootRef : REF_EMPTY;
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
             if (inner)
             {
                 if (COUNT) nv++;
-                if (MODE == BM_TRACE_REFERENCE) ref_node(tv, cur, o, d, inv, stack, top);
+                if (MODE == BM_TRACE_REFERENCE) ref_node(tv, cur, o, d, inv, oi, stack, top);
                 else closest_node(tv, cur, o, inv, best.t, stack, top);
                 cur = top >= 0 ? stack[top--] : REF_EMPTY;
             }
@@ -218,11 +234,10 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
             {
                 if (COUNT) nv++;
                 const float4* lp = tv.leaves + LEAF_F4 * (size_t)(cur & ~LEAF_BIT);
-                float4 r0 = __ldg(lp);
+                float4 r0 = __ldg(lp), r1 = __ldg(lp + 1), r2 = __ldg(lp + 2);
                 first = __float_as_uint(r0.y); cfirst = __float_as_uint(r0.w);
                 if (MODE == BM_TRACE_REFERENCE)
                 {
-                    float4 r1 = __ldg(lp + 1), r2 = __ldg(lp + 2);
                     if (box_ray(mk3(r1.x, r1.y, r1.z), mk3(r1.w, r2.x, r2.y), o, inv) != FLT_MAX) cnt = __float_as_uint(r0.z);      // BuildTree.cu:405-406
                 }
                 else cnt = __float_as_uint(r0.z);
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
                     {
                         float4 b0 = __ldg(cp), b1 = __ldg(cp + 1);
                         if (COUNT) nc++;
-                        if (line_hits_box(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), o, inv)) mask |= 1ull << i;
+                        if (line_hits_box_fma(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), inv, oi)) mask |= 1ull << i;
                     }
                 }
             }
@@ -316,7 +331,7 @@ __global__ void hash_kernel(const float* __restrict__ pts, u64 n, u32* __restric
 }
 
 template <int MODE, bool CAMERA, bool COUNT>
-int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, u32 width, bmHit* d_hits, u32* d_pixels,
+int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
                  const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
     static int blocksPerSM = 0;
@@ -332,36 +347,36 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     u64 cap = (u64)sm_count() * blocksPerSM;
     if (blocks > cap) blocks = cap;
     BM_CUDA(cudaMemsetAsync(d_workCounter, 0, 4, s));
-    trace_kernel<MODE, CAMERA, COUNT><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_hits, d_pixels, d_meshData,
+    trace_kernel<MODE, CAMERA, COUNT><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
                                                                             d_counters, d_workCounter);
     BM_LAUNCHED();
     return BM_OK;
 }
 
 template <bool CAMERA>
-int dispatch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels,
+int dispatch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, int mode, bmHit* d_hits, u32* d_pixels,
                    const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
     if (mode == BM_TRACE_REFERENCE)
-        return d_counters ? launch_trace<BM_TRACE_REFERENCE, CAMERA, true>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
-                          : launch_trace<BM_TRACE_REFERENCE, CAMERA, false>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
-    return d_counters ? launch_trace<BM_TRACE_CLOSEST, CAMERA, true>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
-                      : launch_trace<BM_TRACE_CLOSEST, CAMERA, false>(tv, d_rays, cam, n, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
+        return d_counters ? launch_trace<BM_TRACE_REFERENCE, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
+                          : launch_trace<BM_TRACE_REFERENCE, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
+    return d_counters ? launch_trace<BM_TRACE_CLOSEST, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
+                      : launch_trace<BM_TRACE_CLOSEST, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
 }
 } // namespace
 
-int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s)
+int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numRays, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
     if (!n) return BM_OK;
     CameraIn cam = {};
-    return dispatch_trace<false>(tv, d_rays, cam, n, 0, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, s);
+    return dispatch_trace<false>(tv, d_rays, cam, n, d_numRays, 0, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, s);
 }
 
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
                  u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    return dispatch_trace<true>(tv, nullptr, cam, n, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
+    return dispatch_trace<true>(tv, nullptr, cam, n, nullptr, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
 }
 
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s)

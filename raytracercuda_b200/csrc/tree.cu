@@ -280,7 +280,15 @@ extern "C" int bmTraceRays(bmTree* t, const bmRay* d_rays, uint64_t numRays, int
     if (!t || (!d_rays && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) BM_TRY(tree_build(t));
     BM_TRY(t->scalars.reserve(64));
-    return trace_rays(t->view(), d_rays, numRays, mode, d_hits, d_counters, t->scalars.as<u32>() + 8, t->stream);
+    return trace_rays(t->view(), d_rays, numRays, nullptr, mode, d_hits, d_counters, t->scalars.as<u32>() + 8, t->stream);
+}
+
+extern "C" int bmTraceRaysIndirect(bmTree* t, const bmRay* d_rays, const uint32_t* d_numRays, uint64_t maxRays, int mode, bmHit* d_hits, uint64_t* d_counters)
+{
+    if (!t || !d_numRays || (!d_rays && maxRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) BM_TRY(tree_build(t));
+    BM_TRY(t->scalars.reserve(64));
+    return trace_rays(t->view(), d_rays, maxRays, d_numRays, mode, d_hits, d_counters, t->scalars.as<u32>() + 8, t->stream);
 }
 
 extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9, int mode,
@@ -313,7 +321,19 @@ extern "C" int bmBounceRays(bmTree* t, const bmRay* d_rays, const bmHit* d_hits,
     if (!t->built) return BM_ERROR_NOT_BUILT;
     BM_TRY(t->rayFlags.reserve(numRays * 4 + 4));
     BM_TRY(t->rayTemp.reserve(scan_temp_bytes(numRays)));
-    return bounce_rays(d_rays, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
+    return bounce_rays(d_rays, nullptr, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
+}
+
+extern "C" int bmBounceRaysCamera(bmTree* t, const float* d_initialRays3, const float* eye3, const float* orient9, const bmHit* d_hits, uint64_t numRays,
+                                  uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count)
+{
+    if (!t || !d_count || !eye3 || !orient9 || ((!d_initialRays3 || !d_hits || !d_out) && numRays) || numRays >= 0xFFFFFFFFull) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    BM_TRY(t->rayFlags.reserve(numRays * 4 + 4));
+    BM_TRY(t->rayTemp.reserve(scan_temp_bytes(numRays)));
+    CameraIn cam; cam.initialRays = d_initialRays3;
+    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
+    return bounce_rays(nullptr, &cam, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
 }
 
 extern "C" int bmHashKeys(const float* d_points3, uint64_t n, uint32_t* d_hash, int32_t* d_cells3, void* stream)

@@ -160,3 +160,49 @@ def test_edge_cases(oracle_lib, beam_lib, cuda_device):
     h1 = hits_to_numpy(t.trace_rays(R, 1))
     assert h1["tri"][0] == 299
     t.close(); s.close()
+
+
+def test_bounce_rays_workflow(oracle_lib, beam_lib, cuda_device):
+    """config-2 style frame on a small stand-in: primary -> diffuse bounce rays (GPU-generated) -> bounce trace with the count kept
+    on the device; the oracle traces the SAME bounce buffer (parity on identical ray buffers)."""
+    import ctypes as C
+    import torch
+    from raytracercuda_b200 import synth, workloads
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    wl = workloads.get("c2small")
+    W, H = wl.width, wl.height
+    n = W * H
+    t = Tree(cuda_device); t.add_mesh(wl.positions, wl.indices); t.build()
+    s = OracleScene(oracle_lib); s.add_mesh(wl.positions, wl.indices, wl.normals); s.build()
+    rays = oracle_lib.initial_rays(W, H)
+    rd = torch.from_numpy(rays).to(cuda_device)
+    hits1, _ = t.trace_camera(rd, synth.EYE, synth.IDENTITY, width=W)
+    f3 = (C.c_float * 3)(*synth.EYE); f9 = (C.c_float * 9)(*synth.IDENTITY.reshape(-1))
+    out = torch.zeros((n, 6), dtype=torch.float32, device=cuda_device); src = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    assert beam_lib.bmBounceRaysCamera(t.h, rd.data_ptr(), f3, f9, hits1.data_ptr(), n, 0, 1, 7, out.data_ptr(), src.data_ptr(), cnt.data_ptr()) == 0
+    nb = int(cnt.cpu()[0])
+    h1 = hits_to_numpy(hits1)
+    hit_idx = np.flatnonzero(h1["tri"] != 0xFFFFFFFF)
+    assert nb == hit_idx.size > 1000
+    assert np.array_equal(src.cpu().numpy()[:nb], hit_idx)                       # compacted in ray order
+    # same rays through the explicit-ray entry point (bmCameraRays + bmBounceRays)
+    cam_rays = t.camera_rays(rd, synth.EYE, synth.IDENTITY, width=W)
+    out2, src2, cnt2 = t.bounce_rays(cam_rays, hits1, sample=0, bounce=1, seed=7)
+    assert int(cnt2.cpu()[0]) == nb and torch.equal(out2[:nb], out[:nb])
+    B = out[:nb].cpu().numpy()
+    # geometry of the construction: origin sits 1e-4 off the hit point on the side the ray came from, direction is a unit vector
+    # in the hemisphere of that normal
+    o1 = np.asarray(synth.EYE, np.float32) + h1["t"][hit_idx, None] * rays[hit_idx]
+    off = B[:, :3] - o1
+    assert np.abs(np.linalg.norm(off, axis=1) - 1e-4).max() < 2e-6
+    assert np.abs(np.linalg.norm(B[:, 3:], axis=1) - 1).max() < 1e-5
+    assert ((off * B[:, 3:]).sum(1) > -1e-9).all() and ((off * rays[hit_idx]).sum(1) < 0).all()
+    # bounce trace with the device-side count vs the oracle on the same buffer
+    hits2 = torch.full((n, 4), -1.0, dtype=torch.float32, device=cuda_device)
+    assert beam_lib.bmTraceRaysIndirect(t.h, out.data_ptr(), cnt.data_ptr(), n, 0, hits2.data_ptr(), None) == 0
+    h2 = hits_to_numpy(hits2[:nb])
+    assert (hits2[nb:].cpu().numpy() == -1.0).all()                               # nothing beyond the device count is touched
+    r = s.trace_rays(B[:, :3], B[:, 3:], 0, NT)
+    _compare(h2, r, t.mesh_bases(), what="bounce rays")
+    t.close(); s.close()
