@@ -23,10 +23,12 @@ struct HitRec { float t, u, v; u32 tri, mesh, face; };
 
 __device__ __forceinline__ V3 f4xyz(float4 a) { return mk3(a.x, a.y, a.z); }
 
-// Conservative LINE/box cull on the padded tight boxes, one FMA per slab plane: t = b*inv - o*inv with o*inv hoisted per ray.
-// Its rounding differs from (b-o)*inv by at most |o|*2^-24 in space, far inside the boxes' pad (world extent * 2^-20), and a NaN
-// (0*inf, inf-inf on axis-parallel rays) drops out of fminf/fmaxf, i.e. that slab simply does not cull.  Never decides a result:
+// Conservative LINE/box cull on the padded tight boxes, one FMA per slab plane: t = b*ic - o*ic with o*ic hoisted per ray.
+// ic is 1/d clamped to +-1e30 (cull_inv), so an axis-parallel ray gives +-huge finite values with the right signs instead of the
+// inf - inf = NaN an unclamped reciprocal would produce (a NaN on one side of a slab would silently flip the test).  Rounding
+// differs from (b-o)/d by at most |o|*2^-24 in space, far inside the boxes' pad (world extent * 2^-20).  Never decides a result:
 // it only skips subtrees / face groups that cannot contain a hit.
+__device__ __forceinline__ float cull_inv(float inv) { return (inv == inv) ? fminf(fmaxf(inv, -1e30f), 1e30f) : 1e30f; }
 __device__ __forceinline__ bool line_hits_box_fma(V3 bMin, V3 bMax, V3 inv, V3 oi)
 {
     float x0 = __fmaf_rn(bMin.x, inv.x, -oi.x), x1 = __fmaf_rn(bMax.x, inv.x, -oi.x);
@@ -40,7 +42,7 @@ __device__ __forceinline__ bool line_hits_box_fma(V3 bMin, V3 bMax, V3 inv, V3 o
 // ---- one step of each traversal flavour, shared by every kernel variant -------------------------------------------------
 // Internal node in REFERENCE mode: cell test with the reference's slab arithmetic, child order by the split plane
 // (BuildTree.cu:398-481), children whose tight box the ray's line misses are not pushed.
-__device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d, V3 inv, V3 oi, u32* stack, int& top)
+__device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d, V3 inv, V3 ic, V3 oi, u32* stack, int& top)
 {
     const float4* np = tv.nodes + NODE_F4 * (size_t)ref;
     // all six quads at once: the node is one 128-byte L1 line, and a second dependent round trip would double the latency
@@ -51,8 +53,8 @@ __device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d
     int axis = (int)__float_as_uint(q5.w);
     float p = get(o, axis) + boxDist * get(d, axis);                                   // :444
     bool leftFirst = p < q4.w;                                                          // s = .5f*(max+min) of the cell, :443
-    bool h0 = line_hits_box_fma(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), inv, oi);
-    bool h1 = line_hits_box_fma(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), inv, oi);
+    bool h0 = line_hits_box_fma(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), ic, oi);
+    bool h1 = line_hits_box_fma(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), ic, oi);
     u32 nearRef = leftFirst ? c0 : c1, farRef = leftFirst ? c1 : c0;
     bool nearHit = leftFirst ? h0 : h1, farHit = leftFirst ? h1 : h0;
     if (farHit) stack[++top] = farRef;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
     u32 cur = REF_EMPTY;
     bool active = false, exhausted = false;
     u64 rayIdx = 0;
-    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), oi = mk3(0, 0, 0);
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), ic = mk3(0, 0, 1), oi = mk3(0, 0, 0);
     HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
     u32 nv = 0, nt = 0, nc = 0;
 
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
                         d = mk3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
                     }
                     inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-                    oi = o * inv;
+                    ic = mk3(cull_inv(inv.x), cull_inv(inv.y), cull_inv(inv.z));
+                    oi = o * ic;
                     best.t = FLT_MAX; best.u = 0.f; best.v = 0.f; best.tri = best.mesh = best.face = 0xFFFFFFFFu;
                     top = -1;
                     cur = tv.numLeaves ? tv.rootRef : REF_EMPTY;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
             if (inner)
             {
                 if (COUNT) nv++;
-                if (MODE == BM_TRACE_REFERENCE) ref_node(tv, cur, o, d, inv, oi, stack, top);
+                if (MODE == BM_TRACE_REFERENCE) ref_node(tv, cur, o, d, inv, ic, oi, stack, top);
                 else closest_node(tv, cur, o, inv, best.t, stack, top);
                 cur = top >= 0 ? stack[top--] : REF_EMPTY;
             }
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
                     {
                         float4 b0 = __ldg(cp), b1 = __ldg(cp + 1);
                         if (COUNT) nc++;
-                        if (line_hits_box_fma(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), inv, oi)) mask |= 1ull << i;
+                        if (line_hits_box_fma(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), ic, oi)) mask |= 1ull << i;
                     }
                 }
             }
