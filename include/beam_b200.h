@@ -3,9 +3,11 @@
  * This is the drop-in boundary for the hot path of d1kkop/RaytracerCuda ("Beam").  In the reference the seam is the set
  * of extern "C" launchers defined in Raytracer/BuildTree.cu / Hash.cu / RTClear.cu and re-declared by hand at the top of
  * each host .cpp (SceneTree.cpp:11-35, SceneHash.cpp:10-24, Camera.cpp:16-19).  Part 1 below exports those symbols with
- * the same names, argument order and x86-64 SysV calling convention (glm::vec3 by value == struct of 3 floats by value;
- * `const glm::vec3&` / `const glm::mat3&` == pointer), so the reference's own SceneTree.cpp / Camera.cpp link against
- * libbeam_b200.so unchanged.  Part 2 is the explicit, handle-based form the same kernels are reached through when the
+ * the same names, argument order and calling convention, so the reference's own SceneTree.cpp / Camera.cpp link against
+ * libbeam_b200.so unchanged (tests/test_gpu_reference_binaries.py does exactly that).  Note on the convention: glm 0.9.9.0's
+ * vec3 has a user-provided copy constructor, so `glm::vec3 bMin` BY VALUE is passed by invisible reference under the Itanium
+ * C++ ABI (and every struct > 8 bytes is under Win64): at the binary level by-value vec3, `const vec3&` and `const mat3&` are
+ * all pointers, which is how they are declared here.  Part 2 is the explicit, handle-based form the same kernels are reached through when the
  * caller wants hit records, ray batches, build statistics or streams -- things the reference ABI cannot express.
  *
  * All pointers named d_* (and every pointer in Part 1) are DEVICE pointers.  No function falls back to the CPU: if no
@@ -74,8 +76,8 @@ void bmResetScene(void* rootNode, void* faceStore, void* faceGroupStore, void* n
  * identified by treeRootNode, with world box [bMin,bMax].  The sort-based builder needs every mesh before it can emit
  * the hierarchy, so the build itself runs in bmBuildTree, or lazily inside the first bmMarch after an insert. */
 void bmInsertMeshInTree(const bmVec3* vertices, const uint32_t* indices, uint32_t numIndices, uint32_t meshIdx,
-                        bmVec3 bMin, bmVec3 bMax, void* treeRootNode, void* faceStore, void* faceGroupStore,
-                        void* nodeStore, void* material);
+                        const bmVec3* bMin /* glm::vec3 by value */, const bmVec3* bMax /* glm::vec3 by value */,
+                        void* treeRootNode, void* faceStore, void* faceGroupStore, void* nodeStore, void* material);
 
 /* BuildTree.cu:502-520. One primary ray per pixel: dir = orient * initialRays[i] from eye; buffer[i] = shaded pixel
  * ((u32)|n.z*255| << 16 on a hit, 255<<8 on a miss, BuildTree.cu:486-496).  `pitch` is ignored as in the reference. */

@@ -211,3 +211,62 @@ class OracleScene:
         if self.h:
             self.O.lib.orc_scene_destroy(self.h)
             self.h = None
+
+
+class RefGpuScene:
+    """The reference's UNMODIFIED host classes in CUDA-1 mode (oracle/ref_gpu_driver.cpp, oracle/build_ref_cuda.sh).
+    which = "refhost_b200": on top of this repo's libbeam_b200.so (drop-in proof);  "refcuda": on top of the reference's own
+    kernels rebuilt for sm_100a (second baseline).  Needs a GPU."""
+
+    def __init__(self, which: str):
+        path = os.path.join(HERE, "_ref", "libbeam_%s.so" % which)
+        self.lib = C.CDLL(path, mode=os.RTLD_NOW | os.RTLD_LOCAL | getattr(os, "RTLD_DEEPBIND", 0))
+        L = self.lib
+        vp = C.c_void_p
+        L.refgpu_scene_create.restype = vp
+        L.refgpu_scene_destroy.argtypes = [vp]
+        L.refgpu_scene_add_mesh.argtypes = [vp, _f32p, vp, C.c_uint32, _u32p, C.c_uint32]
+        L.refgpu_scene_build.argtypes = [vp]; L.refgpu_scene_build.restype = C.c_double
+        L.refgpu_camera.argtypes = [vp, C.c_uint32, C.c_uint32] + [C.c_float] * 5
+        L.refgpu_trace.argtypes = [vp, _f32p, _f32p, C.c_int, C.POINTER(C.c_int)]; L.refgpu_trace.restype = C.c_double
+        L.refgpu_read_pixels.argtypes = [vp, _u32p]
+        self.h = L.refgpu_scene_create()
+        self._keep = []
+        self.W = self.H = 0
+
+    @staticmethod
+    def available(which: str) -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", "libbeam_%s.so" % which))
+
+    def add_mesh(self, positions, indices, normals=None):
+        P = np.ascontiguousarray(positions, dtype=np.float32)
+        I = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        N = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32)
+        self._keep += [P, I, N]
+        err = self.lib.refgpu_scene_add_mesh(self.h, P, None if N is None else N.ctypes.data, P.shape[0], I, I.size)
+        assert err == 0, err
+
+    def build(self) -> float:
+        return self.lib.refgpu_scene_build(self.h)
+
+    def camera(self, W, H, frustum=(-1, 1, -1, 1, 1)):
+        err = self.lib.refgpu_camera(self.h, W, H, *[float(x) for x in frustum])
+        assert err == 0, err
+        self.W, self.H = W, H
+
+    def trace(self, eye, orient, repeat=1):
+        e = np.ascontiguousarray(eye, np.float32); o = np.ascontiguousarray(orient, np.float32).reshape(-1)
+        err = C.c_int(0)
+        sec = self.lib.refgpu_trace(self.h, e, o, int(repeat), C.byref(err))
+        assert err.value == 0, err.value
+        return sec
+
+    def pixels(self):
+        px = np.zeros(self.W * self.H, np.uint32)
+        assert self.lib.refgpu_read_pixels(self.h, px) == 0
+        return px.reshape(self.H, self.W)
+
+    def close(self):
+        if self.h:
+            self.lib.refgpu_scene_destroy(self.h)
+            self.h = None

@@ -12,6 +12,16 @@
 #include <cstring>
 using namespace Beam;
 
+// CUDA 0 (host-emulation oracle): the pixel buffer is host memory.  CUDA 1 (oracle/build_ref_cuda.sh: the reference's host
+// classes compiled as they ship, in front of either this repo's kernels or the reference's own): it is device memory.
+#if CUDA
+static void* rt_alloc(size_t n) { void* p = nullptr; CUDA_CALL(cudaMalloc(&p, n)); CUDA_CALL(cudaMemset(p, 0, n)); return p; }
+static void  rt_free(void* p) { cudaFree(p); }
+#else
+static void* rt_alloc(size_t n) { return calloc(n, 1); }
+static void  rt_free(void* p) { free(p); }
+#endif
+
 namespace Beam
 {
     sptr<IRenderTarget> IRenderTarget::registerGLTBO(u32 tbo, u32 width, u32 height, u32 pitch)
@@ -37,7 +47,7 @@ namespace Beam
     u32 RenderTarget::lock()
     {
         if ( m_buffer ) return ERROR_UNLOCK_FIRST;
-        m_buffer = calloc( (size_t)m_pitch * m_height, 1 );
+        m_buffer = rt_alloc( (size_t)m_pitch * m_height );
         m_RT = this;
         return ERROR_ALL_FINE;
     }
@@ -45,7 +55,7 @@ namespace Beam
     u32 RenderTarget::unlock()
     {
         if ( !m_buffer ) return ERROR_LOCK_FIRST;
-        free( m_buffer );
+        rt_free( m_buffer );
         m_buffer = nullptr;
         m_RT = nullptr;
         return ERROR_ALL_FINE;

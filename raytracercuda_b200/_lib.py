@@ -82,7 +82,7 @@ def load() -> C.CDLL:
     L.bmBounceRaysCamera.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, u64, u32, u32, u32, vp, vp, vp]
     L.bmTraceRaysIndirect.argtypes = [vp, vp, vp, u64, i32, vp, vp]
     L.bmResetScene.argtypes = [vp] * 7 + [u32] * 3; L.bmResetScene.restype = None
-    L.bmInsertMeshInTree.argtypes = [vp, vp, u32, u32, bmVec3, bmVec3, vp, vp, vp, vp, vp]; L.bmInsertMeshInTree.restype = None
+    L.bmInsertMeshInTree.argtypes = [vp, vp, u32, u32, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, vp, vp, vp]; L.bmInsertMeshInTree.restype = None
     L.bmMarch.argtypes = [vp, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, u32, u32, u32, C.POINTER(bmVec3), C.POINTER(bmMat3), vp]
     L.bmMarch.restype = None
     L.bmClear.argtypes = [vp, u32, u32, u32, u32]; L.bmClear.restype = None

@@ -143,7 +143,7 @@ public:
         {
             auto& m = m_meshes[i];
             if (!m->m_data[VERTEX_DATA_POSITION] || !m->m_indices) continue;
-            bmInsertMeshInTree(m->m_data[VERTEX_DATA_POSITION]->ptr<const bmVec3>(), m->m_indices->ptr<u32>(), m->m_numIndices, i, m_min, m_max,
+            bmInsertMeshInTree(m->m_data[VERTEX_DATA_POSITION]->ptr<const bmVec3>(), m->m_indices->ptr<u32>(), m->m_numIndices, i, &m_min, &m_max,
                                m_root->ptr<void>(), nullptr, nullptr, nullptr, nullptr);
         }
         bmBuildTree(m_root->ptr<void>());

@@ -373,10 +373,10 @@ extern "C" void bmResetScene(void* rootNode, void*, void*, void*, void*, void*, 
 }
 
 extern "C" void bmInsertMeshInTree(const bmVec3* vertices, const uint32_t* indices, uint32_t numIndices, uint32_t meshIdx,
-                                   bmVec3 bMin, bmVec3 bMax, void* treeRootNode, void*, void*, void*, void*)
+                                   const bmVec3* bMin, const bmVec3* bMax, void* treeRootNode, void*, void*, void*, void*)
 {
     bmTree* t = find_tree(treeRootNode);
-    float mn[3] = { bMin.x, bMin.y, bMin.z }, mx[3] = { bMax.x, bMax.y, bMax.z };
+    float mn[3] = { bMin->x, bMin->y, bMin->z }, mx[3] = { bMax->x, bMax->y, bMax->z };
     if (t && (memcmp(t->hgrid.wmin, mn, 12) != 0 || memcmp(t->hgrid.wmax, mx, 12) != 0))
     {
         std::lock_guard<std::mutex> lk(g_regMutex);

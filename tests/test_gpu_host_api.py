@@ -100,7 +100,7 @@ def test_reference_symbols_direct(meshes, golden, beam_lib, cuda_device):
     assert C.sizeof(_lib.bmStaticMeshData) == golden["struct_sizes"]["StaticMeshData"] == 136
     L.bmResetScene(root.data_ptr(), None, None, None, None, None, None, 1 << 24, 1 << 24, 1 << 24)
     lo, hi = _lib.bmVec3(-30, -30, -30), _lib.bmVec3(30, 30, 30)
-    L.bmInsertMeshInTree(Pd.data_ptr(), Id.data_ptr(), Id.numel(), 0, lo, hi, root.data_ptr(), None, None, None, None)
+    L.bmInsertMeshInTree(Pd.data_ptr(), Id.data_ptr(), Id.numel(), 0, C.byref(lo), C.byref(hi), root.data_ptr(), None, None, None, None)
     from raytracercuda_b200.host import ICamera
     cam = ICamera.create(); cam.setInitialRays(200, 200, -1, 1, -1, 1, 1)
     rays = torch.from_numpy(cam.initialRays()).to(dev)
