@@ -70,6 +70,10 @@ int radix_sort_pairs64(u64* d_keysA, u32* d_valsA, u64* d_keysB, u32* d_valsB, s
 int gather_mesh(const float* d_pos, const u32* d_idx, u32 numTris, u32 meshIdx, u32 base, float4* d_soup, cudaStream_t s);
 int count_pairs(const Grid& g, const float4* d_soup, u32 numTris, u32* d_counts, cudaStream_t s);
 int emit_pairs(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, u64* d_keys, u32* d_vals, cudaStream_t s);
+// flat path: classify = candidate ranges + per-candidate test into a bit mask (one SAT pass), emit = decode the masks
+int classify_pairs(const Grid& g, const float4* d_soup, u32 numTris, float margin, u32* d_counts, u64* d_masks, u64* d_infos, cudaStream_t s);
+int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, const u64* d_masks, const u64* d_infos, u64* d_keys, u32* d_vals,
+                    cudaStream_t s);
 
 // ---- hierarchy.cu ---------------------------------------------------------------------------------------------------
 int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s);

@@ -127,6 +127,38 @@ BM_HD void axis_range(const float* tab, int k, float vmin, float vmax, int& lo, 
     hi = i;
 }
 
+// ---- flat candidate test (the fast path of key generation) --------------------------------------------------------------
+// Is (triangle, leaf cell) a pair of the reference tree?  The reference reaches a leaf only if ITS test passes on every
+// ancestor box of the path (BuildTree.cu:216-226), and in float arithmetic the tests on large ancestor boxes are not implied
+// by the test on the leaf (their rounding error grows with the box).  pair_test therefore walks the path upwards from the leaf
+// and evaluates the reference's test on each box, but stops as soon as some vertex of the triangle lies inside the current box
+// with margin `m` on all three axes.  From there on every larger box contains that vertex with at least the same margin (going
+// to the parent moves one face outwards, none inwards), and a vertex inside a box with margin m >= ~8 * 2^-24 * (box size +
+// |v - c|) makes each of the 13 float tests pass with room to spare:
+//   * box axes: the vertex itself is inside;
+//   * edge-cross axes: for the projected vertex |p| <= fa*(hy-m) + fb*(hz-m) = rad - m*(fa+fb) with the SAME float fa, fb on both
+//     sides, so only the ~5 roundings of p and rad (each <= 2^-24 relative) are in play; the third vertex projects onto one of the
+//     two that the test uses up to 2^-23 * |edge|^2;
+//   * plane: the triangle's plane passes through that vertex, so the box's extreme corners lie >= m*|n|_1 on either side.
+// m = world extent * 2^-19 (1.1e-4 for the +-30 world, 2.6 x the requirement at the largest box).  Hence the result equals the
+// reference's descent by construction; tests/test_gpu_build.py also checks it bit for bit against the descent kernel.
+BM_HD bool pair_test(const Grid& g, const TriSat& t, u32 ix, u32 iy, u32 iz, float m)
+{
+    for (int d = g.D; d >= 1; --d)
+    {
+        int sx = g.k[0] - axis_bits(d, 0), sy = g.k[1] - axis_bits(d, 1), sz = g.k[2] - axis_bits(d, 2);
+        V3 mn, mx; cell_box(g, d, ix >> sx, iy >> sy, iz >> sz, mn, mx);
+        float bc[3] = { (mx.x + mn.x) * .5f, (mx.y + mn.y) * .5f, (mx.z + mn.z) * .5f };
+        float hs[3] = { (mx.x - mn.x) * .5f, (mx.y - mn.y) * .5f, (mx.z - mn.z) * .5f };
+        float hx = hs[0] - m, hy = hs[1] - m, hz = hs[2] - m;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (fabsf(t.v[k].x - bc[0]) <= hx && fabsf(t.v[k].y - bc[1]) <= hy && fabsf(t.v[k].z - bc[2]) <= hz) return true;
+        if (!sat_box(t, bc, hs)) return false;
+    }
+    return true;
+}
+
 // Reference descent for ONE triangle (BuildTree.cu:191-255), restricted to cells inside the exact per-axis ranges:
 // depth-first over the implicit kd nodes; a child is entered iff the reference's own test on the child box passes;
 // reaching depth D emits the leaf path code.  `emit(code, ix, iy, iz)` is called once per (leaf, triangle) pair.  Because every

@@ -35,21 +35,28 @@ struct NoEmit { BM_HD void operator()(u32, u32, u32, u32) const {} };
 // cell (centre of the triangle's box clipped to the cell, 5 bits per axis).  The code part decides everything parity is
 // defined on; the sub-key only orders the triangles of one leaf spatially so that consecutive groups of four get tight
 // cluster boxes (hierarchy.cu).  It is not part of any reference behaviour, so its arithmetic is free.
+// sub-key of a pair: 15-bit Morton code of the centre of (triangle box clipped to the cell) inside the cell
+__device__ __forceinline__ u32 sub_key(const Grid& g, u32 ix, u32 iy, u32 iz, V3 tmin, V3 tmax)
+{
+    V3 mn, mx; cell_box(g, g.D, ix, iy, iz, mn, mx);
+    float cx = .5f * (fmaxf(tmin.x, mn.x) + fminf(tmax.x, mx.x)), cy = .5f * (fmaxf(tmin.y, mn.y) + fminf(tmax.y, mx.y)),
+          cz = .5f * (fmaxf(tmin.z, mn.z) + fminf(tmax.z, mx.z));
+    int qx = (int)((cx - mn.x) / (mx.x - mn.x) * 32.f), qy = (int)((cy - mn.y) / (mx.y - mn.y) * 32.f), qz = (int)((cz - mn.z) / (mx.z - mn.z) * 32.f);
+    qx = min(max(qx, 0), 31); qy = min(max(qy, 0), 31); qz = min(max(qz, 0), 31);
+    return (spread3((u32)qx) << 2) | (spread3((u32)qy) << 1) | spread3((u32)qz);
+}
+
 struct WriteEmit
 {
     u64* keys; u32* vals; u32 pos; u32 tri; const Grid* g; V3 tmin, tmax;
     __device__ void operator()(u32 code, u32 ix, u32 iy, u32 iz)
     {
-        V3 mn, mx; cell_box(*g, g->D, ix, iy, iz, mn, mx);
-        float cx = .5f * (fmaxf(tmin.x, mn.x) + fminf(tmax.x, mx.x)), cy = .5f * (fmaxf(tmin.y, mn.y) + fminf(tmax.y, mx.y)),
-              cz = .5f * (fmaxf(tmin.z, mn.z) + fminf(tmax.z, mx.z));
-        int qx = (int)((cx - mn.x) / (mx.x - mn.x) * 32.f), qy = (int)((cy - mn.y) / (mx.y - mn.y) * 32.f), qz = (int)((cz - mn.z) / (mx.z - mn.z) * 32.f);
-        qx = min(max(qx, 0), 31); qy = min(max(qy, 0), 31); qz = min(max(qz, 0), 31);
-        u32 sub = (spread3((u32)qx) << 2) | (spread3((u32)qy) << 1) | spread3((u32)qz);
-        keys[pos] = ((u64)code << SUB_BITS) | sub; vals[pos] = tri; ++pos;
+        keys[pos] = ((u64)code << SUB_BITS) | sub_key(*g, ix, iy, iz, tmin, tmax); vals[pos] = tri; ++pos;
     }
 };
 
+// ---- descent path (reference algorithm per triangle; used for triangles with more than 64 candidate cells, and as the
+//      cross-check of the flat path when BM_KEYGEN=descent) ------------------------------------------------------------------
 __global__ void __launch_bounds__(KG_THREADS) count_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, u32* __restrict__ counts)
 {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,6 +78,73 @@ __global__ void __launch_bounds__(KG_THREADS) emit_kernel(Grid g, const float4* 
                     mk3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z))) };
     descend_triangle<WriteEmit&>(g, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), w);
 }
+
+// ---- flat path: one SAT pass -------------------------------------------------------------------------------------------------
+// classify: exact per-axis candidate ranges; up to 64 candidate cells -> pair_test each, remember the outcome as a bit mask so
+// that the emit pass needs no geometry test at all; more than 64 -> counted by the descent.
+// info = ix0 | iy0 << 11 | iz0 << 22 | nx << 33 | ny << 40 | large << 63
+__global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, float margin,
+                                                              u32* __restrict__ counts, u64* __restrict__ masks, u64* __restrict__ infos)
+{
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numTris) return;
+    const float4* p = soup + 3 * (size_t)t;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    V3 va = mk3(a.x, a.y, a.z), vb = mk3(b.x, b.y, b.z), vc = mk3(c.x, c.y, c.z);
+    int lo[3], hi[3];
+    axis_range(g.tab[0], g.k[0], fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
+    axis_range(g.tab[1], g.k[1], fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
+    axis_range(g.tab[2], g.k[2], fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
+    if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) { counts[t] = 0; masks[t] = 0; infos[t] = 0; return; }
+    u64 nx = (u64)(hi[0] - lo[0] + 1), ny = (u64)(hi[1] - lo[1] + 1), nz = (u64)(hi[2] - lo[2] + 1);
+    if (nx * ny * nz > 64ull)
+    {
+        counts[t] = descend_triangle(g, va, vb, vc, NoEmit());
+        masks[t] = 0; infos[t] = 1ull << 63;
+        return;
+    }
+    TriSat ts; trisat_init(ts, va, vb, vc);
+    u64 mask = 0; u32 bit = 0;
+    for (int iz = lo[2]; iz <= hi[2]; iz++)
+        for (int iy = lo[1]; iy <= hi[1]; iy++)
+            for (int ix = lo[0]; ix <= hi[0]; ix++, bit++)
+                if (pair_test(g, ts, (u32)ix, (u32)iy, (u32)iz, margin)) mask |= 1ull << bit;
+    counts[t] = (u32)__popcll(mask);
+    masks[t] = mask;
+    infos[t] = (u64)lo[0] | ((u64)lo[1] << 11) | ((u64)lo[2] << 22) | (nx << 33) | (ny << 40);
+}
+
+__global__ void __launch_bounds__(KG_THREADS) emit_flat_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, const u32* __restrict__ offsets,
+                                                               const u64* __restrict__ masks, const u64* __restrict__ infos,
+                                                               u64* __restrict__ keys, u32* __restrict__ vals)
+{
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numTris) return;
+    u64 info = infos[t], mask = masks[t];
+    if (!mask && !(info >> 63)) return;
+    const float4* p = soup + 3 * (size_t)t;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    V3 tmin = mk3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+    V3 tmax = mk3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+    u32 pos = offsets[t];
+    if (info >> 63)
+    {
+        WriteEmit w = { keys, vals, pos, t, &g, tmin, tmax };
+        descend_triangle<WriteEmit&>(g, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), w);
+        return;
+    }
+    u32 x0 = (u32)info & 0x7FFu, y0 = (u32)(info >> 11) & 0x7FFu, z0 = (u32)(info >> 22) & 0x7FFu, nx = (u32)(info >> 33) & 0x7Fu, ny = (u32)(info >> 40) & 0x7Fu;
+    // the descent emits a triangle's codes in no particular order and the sort is keyed on (code, sub-key), so any order works here
+    while (mask)
+    {
+        u32 bit = (u32)__ffsll((long long)mask) - 1u;
+        mask &= mask - 1ull;
+        u32 ix = x0 + bit % nx, iy = y0 + (bit / nx) % ny, iz = z0 + bit / (nx * ny);
+        keys[pos] = ((u64)encode_path(g.D, ix, iy, iz) << SUB_BITS) | sub_key(g, ix, iy, iz, tmin, tmax);
+        vals[pos] = t;
+        ++pos;
+    }
+}
 } // namespace
 
 int gather_mesh(const float* d_pos, const u32* d_idx, u32 numTris, u32 meshIdx, u32 base, float4* d_soup, cudaStream_t s)
@@ -84,6 +158,21 @@ int count_pairs(const Grid& g, const float4* d_soup, u32 numTris, u32* d_counts,
 {
     if (!numTris) return BM_OK;
     count_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, d_counts);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+int classify_pairs(const Grid& g, const float4* d_soup, u32 numTris, float margin, u32* d_counts, u64* d_masks, u64* d_infos, cudaStream_t s)
+{
+    if (!numTris) return BM_OK;
+    classify_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, margin, d_counts, d_masks, d_infos);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, const u64* d_masks, const u64* d_infos, u64* d_keys, u32* d_vals,
+                    cudaStream_t s)
+{
+    if (!numTris) return BM_OK;
+    emit_flat_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, d_offsets, d_masks, d_infos, d_keys, d_vals);
     BM_LAUNCHED();
     return BM_OK;
 }

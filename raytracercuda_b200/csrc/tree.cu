@@ -60,7 +60,7 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos;
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
     u32 maxLeaf = 0, overLeaves = 0;
@@ -75,7 +75,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -101,7 +101,16 @@ static int tree_build(bmTree* t)
     // 2. pair counts per triangle -> offsets
     BM_TRY(t->counts.reserve(T * 4));
     BM_TRY(t->temp.reserve(scan_temp_bytes(T)));
-    BM_TRY(count_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), s));
+    float ext = 0.f;
+    for (int a = 0; a < 3; a++) ext = fmaxf(ext, t->hgrid.wmax[a] - t->hgrid.wmin[a]);
+    const char* kg = getenv("BM_KEYGEN");
+    const bool flat = !(kg && strcmp(kg, "descent") == 0);          // BM_KEYGEN=descent: per-triangle reference descent only (cross-check)
+    if (flat)
+    {
+        BM_TRY(t->masks.reserve(T * 8)); BM_TRY(t->infos.reserve(T * 8));
+        BM_TRY(classify_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, ext * (1.f / 524288.f), t->counts.as<u32>(), t->masks.as<u64>(), t->infos.as<u64>(), s));
+    }
+    else BM_TRY(count_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), s));
     u32* d_scal = t->scalars.as<u32>();
     BM_TRY(exclusive_scan_u32(t->counts.as<u32>(), t->counts.as<u32>(), T, d_scal + 0, t->temp.p, s));
     BM_CUDA(cudaMemcpyAsync(&t->hostScalars[0], d_scal + 0, 4, cudaMemcpyDeviceToHost, s));
@@ -112,7 +121,8 @@ static int tree_build(bmTree* t)
     // 3. emit + sort: key = leaf code (D bits) | in-cell sub-key (SUB_BITS), payload = triangle id
     BM_TRY(t->keysA.reserve(P * 8)); BM_TRY(t->valsA.reserve(P * 4)); BM_TRY(t->keysB.reserve(P * 8)); BM_TRY(t->valsB.reserve(P * 4));
     BM_TRY(t->temp.reserve(sort_temp_bytes(P) > scan_temp_bytes(P) ? sort_temp_bytes(P) : scan_temp_bytes(P)));
-    BM_TRY(emit_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->keysA.as<u64>(), t->valsA.as<u32>(), s));
+    if (flat) BM_TRY(emit_pairs_flat(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->masks.as<u64>(), t->infos.as<u64>(), t->keysA.as<u64>(), t->valsA.as<u32>(), s));
+    else BM_TRY(emit_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->keysA.as<u64>(), t->valsA.as<u32>(), s));
     int inB = 0;
     BM_TRY(radix_sort_pairs64(t->keysA.as<u64>(), t->valsA.as<u32>(), t->keysB.as<u64>(), t->valsB.as<u32>(), P, t->hgrid.D + SUB_BITS, t->temp.p, s, &inB));
     t->sortedKeys = inB ? t->keysB.as<u64>() : t->keysA.as<u64>();
@@ -133,8 +143,6 @@ static int tree_build(bmTree* t)
     BM_TRY(exclusive_scan_u32(t->clusterCounts.as<u32>(), t->clusterCounts.as<u32>(), L, nullptr, t->temp.p, s));
     BM_TRY(t->clusters.reserve((P / CLUSTER + L + 1) * 16 * CLUSTER_F4));
     BM_TRY(t->leafBox.reserve(L * 24));
-    float ext = 0.f;
-    for (int a = 0; a < 3; a++) ext = fmaxf(ext, t->hgrid.wmax[a] - t->hgrid.wmin[a]);
     float pad = ext * (1.f / 1048576.f);
     BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(), t->leafBox.as<float>(), pad,
                        d_scal + 2, s));

@@ -30,6 +30,39 @@ uint64_t hc_pairs(const float* pos, const uint32_t* idx, uint32_t numTris, const
     if (code && tri) for (size_t i = 0; i < out.size() && i < cap; i++) { code[i] = (uint32_t)(out[i] >> 32); tri[i] = (uint32_t)out[i]; }
     return out.size();
 }
+// the flat path of key generation (classify_kernel's logic): exact per-axis ranges, pair_test per candidate cell when there are
+// at most 64 candidates, descent otherwise
+uint64_t hc_pairs_flat(const float* pos, const uint32_t* idx, uint32_t numTris, const float* wmin, const float* wmax, float minLeaf, uint32_t maxDepth,
+                       uint32_t* code, uint32_t* tri, uint64_t cap, uint64_t* numFlatCandidates)
+{
+    HostGrid hg;
+    if (!build_host_grid(hg, wmin, wmax, minLeaf, maxDepth)) return ~0ull;
+    Grid g; for (int a = 0; a < 3; a++) { g.tab[a] = hg.tab[a].data(); g.k[a] = hg.k[a]; } g.D = hg.D;
+    float ext = 0.f; for (int a = 0; a < 3; a++) ext = std::max(ext, wmax[a] - wmin[a]);
+    float margin = ext * (1.f / 524288.f);
+    std::vector<uint64_t> out;
+    uint64_t cand = 0;
+    for (uint32_t t = 0; t < numTris; t++)
+    {
+        const float* a = pos + 3 * idx[3 * t]; const float* b = pos + 3 * idx[3 * t + 1]; const float* c = pos + 3 * idx[3 * t + 2];
+        V3 va = mk3(a[0], a[1], a[2]), vb = mk3(b[0], b[1], b[2]), vc = mk3(c[0], c[1], c[2]);
+        int lo[3], hi[3];
+        axis_range(g.tab[0], g.k[0], fminf(a[0], fminf(b[0], c[0])), fmaxf(a[0], fmaxf(b[0], c[0])), lo[0], hi[0]);
+        axis_range(g.tab[1], g.k[1], fminf(a[1], fminf(b[1], c[1])), fmaxf(a[1], fmaxf(b[1], c[1])), lo[1], hi[1]);
+        axis_range(g.tab[2], g.k[2], fminf(a[2], fminf(b[2], c[2])), fmaxf(a[2], fmaxf(b[2], c[2])), lo[2], hi[2]);
+        if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) continue;
+        uint64_t n = (uint64_t)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+        if (n > 64) { Collect col = { &out, t }; descend_triangle(g, va, vb, vc, col); continue; }
+        cand += n;
+        TriSat ts; trisat_init(ts, va, vb, vc);
+        for (int iz = lo[2]; iz <= hi[2]; iz++) for (int iy = lo[1]; iy <= hi[1]; iy++) for (int ix = lo[0]; ix <= hi[0]; ix++)
+            if (pair_test(g, ts, (u32)ix, (u32)iy, (u32)iz, margin)) out.push_back(((uint64_t)encode_path(g.D, ix, iy, iz) << 32) | t);
+    }
+    std::sort(out.begin(), out.end());
+    if (code && tri) for (size_t i = 0; i < out.size() && i < cap; i++) { code[i] = (uint32_t)(out[i] >> 32); tri[i] = (uint32_t)out[i]; }
+    if (numFlatCandidates) *numFlatCandidates = cand;
+    return out.size();
+}
 int hc_grid(const float* wmin, const float* wmax, float minLeaf, uint32_t maxDepth, int* k3, int* D, float* tabx, float* taby, float* tabz)
 {
     HostGrid hg;

@@ -218,3 +218,28 @@ def test_large_soup_properties(beam_lib, cuda_device):
     refs = np.concatenate([c0, c1])
     assert np.array_equal(np.sort(refs[refs >= 0x80000000] & 0x7FFFFFFF), np.arange(st["leaves"]))
     t.close()
+
+
+def test_flat_keygen_equals_descent_keygen(beam_lib, cuda_device, monkeypatch):
+    """The fast key generator (per-candidate test with the margin-guarded ancestor walk) against the per-triangle reference descent,
+    on the GPU, at a size the CPU oracle cannot reach: 3M triangles of mixed sizes, many hugging the big split planes."""
+    from raytracercuda_b200.tree import Tree
+    rng = np.random.default_rng(33)
+    n = 3_000_000
+    c = rng.uniform(-29.5, 29.5, (n, 1, 3)).astype(np.float32)
+    snap = rng.integers(0, 4, n) == 0
+    planes = np.array([0.0, 15.0, -15.0, 7.5, -7.5, 3.75, -3.75, 1.875], np.float32)
+    ax = rng.integers(0, 3, n)
+    c[snap, 0, ax[snap]] = planes[rng.integers(0, planes.size, snap.sum())] + rng.choice(np.array([0, 1e-7, -1e-7, 1e-5, -1e-4, 1e-3], np.float32), snap.sum())
+    size = rng.choice(np.array([0.003, 0.01, 0.03, 0.1], np.float32), (n, 1, 1))
+    P = (c + rng.uniform(-1, 1, (n, 3, 3)).astype(np.float32) * size).reshape(-1, 3)
+    I = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+    out = {}
+    for mode in ("flat", "descent"):
+        monkeypatch.setenv("BM_KEYGEN", mode)
+        t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+        out[mode] = (t.stats(), *t.pairs())
+        t.close()
+    assert out["flat"][0] == out["descent"][0]
+    assert np.array_equal(out["flat"][1], out["descent"][1]) and np.array_equal(out["flat"][2], out["descent"][2])
+    assert out["flat"][0]["pairs"] > 2 * n

@@ -22,6 +22,8 @@ def hc():
     H = C.CDLL(so)
     H.hc_pairs.argtypes = [f32p, u32p, C.c_uint32, f32p, f32p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
     H.hc_pairs.restype = C.c_uint64
+    H.hc_pairs_flat.argtypes = [f32p, u32p, C.c_uint32, f32p, f32p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    H.hc_pairs_flat.restype = C.c_uint64
     H.hc_grid.argtypes = [f32p, f32p, C.c_float, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
     H.hc_encode.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]; H.hc_encode.restype = C.c_uint32
     H.hc_decode.argtypes = [C.c_int, C.c_uint32, u32p]
@@ -40,6 +42,60 @@ def _pairs(H, P, I, wmin=(-30, -30, -30), wmax=(30, 30, 30)):
     code = np.zeros(n, np.uint32); tri = np.zeros(n, np.uint32)
     H.hc_pairs(P, I, I.size // 3, a, b, 0.03, 38, code.ctypes.data, tri.ctypes.data, n, C.byref(D))
     return code, tri, D.value
+
+
+def _pairs_flat(H, P, I, wmin=(-30, -30, -30), wmax=(30, 30, 30)):
+    I = np.ascontiguousarray(I, np.uint32).reshape(-1)
+    a = np.array(wmin, np.float32); b = np.array(wmax, np.float32); cand = C.c_uint64(0)
+    n = H.hc_pairs_flat(P, I, I.size // 3, a, b, 0.03, 38, None, None, 0, C.byref(cand))
+    code = np.zeros(n, np.uint32); tri = np.zeros(n, np.uint32)
+    H.hc_pairs_flat(P, I, I.size // 3, a, b, 0.03, 38, code.ctypes.data, tri.ctypes.data, n, C.byref(cand))
+    return code, tri, cand.value
+
+
+@pytest.mark.parametrize("name", ["f16", "suzanne", "bunny"])
+def test_flat_keygen_equals_oracle_on_meshes(name, hc, meshes, oracle_lib):
+    P, I, N = meshes[name]
+    s = OracleScene(oracle_lib); s.add_mesh(P, I); s.build()
+    oc, om, ot = s.pairs()
+    code, tri, cand = _pairs_flat(hc, P, I)
+    assert cand > I.shape[0]
+    assert np.array_equal(code, oc) and np.array_equal(tri, ot)
+
+
+def test_flat_keygen_equals_oracle_near_split_planes(hc, oracle_lib):
+    """triangles hugging the large ancestors' split planes (x=0, y=0, z=0, +-15, +-7.5 ...), where the float SAT of the big boxes
+    is least trustworthy, plus thin slivers and axis-aligned triangles"""
+    rng = np.random.default_rng(21)
+    planes = np.array([0.0, 15.0, -15.0, 7.5, -7.5, 3.75, 22.5, -0.029296875, 0.05859375], np.float32)
+    parts = []
+    for k in range(6000):
+        c = rng.uniform(-29, 29, 3)
+        ax = rng.integers(0, 3)
+        c[ax] = planes[rng.integers(0, planes.size)] + rng.choice([0.0, 1e-7, -1e-7, 1e-5, -1e-5, 1e-3, -1e-3, 4e-3])
+        e = rng.uniform(-0.02, 0.02, (3, 3))
+        kind = k % 4
+        if kind == 1: e[:, ax] *= 1e-3                 # nearly parallel to the plane
+        if kind == 2: e[:, ax] = 0.0                   # exactly in a plane parallel to it
+        if kind == 3: e[:, (ax + 1) % 3] = 0.0         # edge vectors with zero components: degenerate cross axes
+        parts.append((c + e).astype(np.float32))
+    P = np.concatenate(parts, 0); I = np.arange(P.shape[0], dtype=np.uint32).reshape(-1, 3)
+    s = OracleScene(oracle_lib); s.add_mesh(P, I); s.build()
+    oc, om, ot = s.pairs()
+    code, tri, cand = _pairs_flat(hc, P, I)
+    assert np.array_equal(code, oc) and np.array_equal(tri, ot)
+    dcode, dtri, D = _pairs(hc, P, I)
+    assert np.array_equal(dcode, oc) and np.array_equal(dtri, ot)
+
+
+def test_flat_keygen_equals_oracle_on_soups(hc, oracle_lib):
+    rng = np.random.default_rng(22)
+    for n, ext, edge in ((8000, 29.0, 0.05), (3000, 2.0, 0.004), (1500, 10.0, 0.08), (200, 31.0, 1.5)):
+        P, I = random_soup(rng, n, ext, edge)
+        s = OracleScene(oracle_lib); s.add_mesh(P, I); s.build()
+        oc, om, ot = s.pairs()
+        code, tri, cand = _pairs_flat(hc, P, I)
+        assert np.array_equal(code, oc) and np.array_equal(tri, ot), (n, ext, edge)
 
 
 @pytest.mark.parametrize("name", ["f16", "suzanne"])
