@@ -130,14 +130,24 @@ def run_b200(args):
     rays_dev = rays_pinned.to(dev)
     Pd = torch.from_numpy(wl.positions).to(dev); Id = torch.from_numpy(wl.indices.view(np.int32)).to(dev).reshape(-1); Nd = torch.from_numpy(wl.normals).to(dev)
     table = make_mesh_table([(Pd, Id, Nd)], dev)
-    tree = Tree(dev)
     stream = torch.cuda.current_stream(dev)
+    # the tree is built once (rank 0) and replicated to the peers over NCCL (index-based arrays, bmTreeExport / bmTreeImport)
+    built = Tree(dev) if rank == 0 else None
 
     def build_once():
-        tree.reset(); tree.add_mesh(Pd, Id); tree.build()
+        built.reset(); built.add_mesh(Pd, Id); built.build()
 
-    build_once()
-    st = tree.stats()
+    if rank == 0:
+        build_once()
+    from raytracercuda_b200.dist import replicate_tree
+    tree = replicate_tree(built, dev, 0)
+    stats_t = torch.zeros(8, dtype=torch.int64, device=dev)
+    if rank == 0:
+        s0 = built.stats()
+        stats_t.copy_(torch.tensor([s0[k] for k in ("triangles", "pairs", "leaves", "nodes", "depth", "max_leaf_faces", "overflow_leaves", "meshes")]))
+    if world > 1:
+        dist.broadcast(stats_t, 0)
+    st = dict(zip(("triangles", "pairs", "leaves", "nodes", "depth", "max_leaf_faces", "overflow_leaves", "meshes"), [int(x) for x in stats_t.cpu()]))
     hits1 = torch.empty((n, 4), dtype=torch.float32, device=dev); pixels = torch.empty(n, dtype=torch.int32, device=dev)
     rays1 = torch.empty((n, 6), dtype=torch.float32, device=dev); rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev)
     src2 = torch.empty(n, dtype=torch.int32, device=dev); cnt2 = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -252,15 +262,35 @@ def run_b200(args):
 
     # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
     build_ms = []
-    for i in range(2 + args.steps):
-        flush.zero_()
-        e0, e1 = ev(), ev()
-        torch.cuda.synchronize(dev)
-        e0.record(); build_once(); e1.record()
-        torch.cuda.synchronize(dev)
-        if i >= 2:
-            build_ms.append(e0.elapsed_time(e1))
-    bms = statistics.mean(build_ms)
+    if rank == 0:
+        for i in range(2 + args.steps):
+            flush.zero_()
+            e0, e1 = ev(), ev()
+            torch.cuda.synchronize(dev)
+            e0.record(); build_once(); e1.record()
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                build_ms.append(e0.elapsed_time(e1))
+    rep_ms = 0.0
+    if world > 1:
+        # replication cost: export + NCCL broadcast of the arrays + import, max over ranks
+        sync_all()
+        reps = []
+        for i in range(3):
+            e0, e1 = ev(), ev()
+            sync_all()
+            e0.record(); _t = replicate_tree(built, dev, 0); e1.record()
+            sync_all()
+            reps.append(e0.elapsed_time(e1))
+            if rank != 0:
+                _t.close()
+        rt = torch.tensor([min(reps)], dtype=torch.float64, device=dev)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        rep_ms = float(rt.item())
+    bt = torch.tensor([statistics.mean(build_ms) if build_ms else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.broadcast(bt, 0)
+    bms = float(bt.item())
     peak, peak_src = measured_peaks()
     build_bytes = 48 * st["triangles"] + 12 * st["pairs"] + 128 * st["nodes"] + 48 * st["pairs"] + 48 * st["leaves"] + 8 * st["pairs"]
     build = {"metric": "BVH build Mtris/s", "value": st["triangles"] / (bms * 1e-3) / 1e6, "unit": "Mtris/s", "ms": bms,
@@ -268,7 +298,8 @@ def run_b200(args):
              "roofline": {"bound": "hbm", "achieved": build_bytes / (bms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": build_bytes / (bms * 1e-3) / 1e9 / peak, "traffic": None,
                           "algorithmic_bytes": build_bytes, "note": "compulsory bytes of the whole build: 48 B/tri soup read + 12 B/pair (8 B key + 4 B id) written + outputs (128 B/node, 48 B/leaf, 48 B/pair triangle record, 32 B per 4 pairs cluster box); sort passes excluded (SURVEY 8d); " + peak_src},
-             "replication": "every rank builds its own replica" if world > 1 else "single GPU"}
+             "replication": ("built on rank 0, arrays replicated to %d peers by NCCL broadcast in %.3f ms (not included in ms)" % (world - 1, rep_ms)) if world > 1 else "single GPU",
+             "replicate_ms": rep_ms}
 
     # --- roofline of the dominant kernel: the primary-ray trace launch ---------------------------------------------------
     pms = statistics.mean(prim_ms)

@@ -137,6 +137,16 @@ int  bmTreeCopyTopology(const bmTree* tree, uint32_t* d_prefixLen, uint32_t* d_p
 int  bmTreeCopyChildBoxes(const bmTree* tree, float* d_boxes12);
 int  bmTreeMeshBases(const bmTree* tree, uint32_t* h_bases, uint32_t capacity);   /* host array: first global id of each mesh */
 
+/* Replication (multi-GPU: build once, copy to peers).  The traversal arrays hold indices only, so they can be copied byte for
+ * byte.  sizes8 = bytes of {nodes, leaves, triangle records, cluster boxes, soup} then {leaves, pairs, triangles} counts.
+ * bmTreeExport copies the arrays into caller-owned device buffers (on the tree's stream); after those bytes have been moved to
+ * another GPU (ncclBroadcast, P2P ...) bmTreeImport wraps them as a read-only tree there: no copy, the caller keeps the buffers
+ * alive; such a tree can be traced (and feed bmBounceRays) but not rebuilt or inspected with bmTreeCopy*. */
+int  bmTreeArraySizes(const bmTree* tree, uint64_t* sizes8);
+int  bmTreeExport(const bmTree* tree, void* d_nodes, void* d_leaves, void* d_ltris, void* d_clusters, void* d_soup);
+int  bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
+                  uint64_t numLeaves, uint64_t numPairs, uint64_t numTris);
+
 /* Explicit ray batch -> hit records. d_counters (nullable) accumulates {node + leaf visits, triangle tests, cluster boxes tested}
  * into three uint64 (the traversal work behind the bytes-per-ray roofline model). */
 int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters);

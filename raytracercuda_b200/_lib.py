@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "bmResetScene", "bmInsertMeshInTree", "bmMarch", "bmGetFaceSize", "bmGetFacePtrSize", "bmGetMaterialSize", "bmGetNodeSize",
     "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
-    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport",
     "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
@@ -74,6 +74,9 @@ def load() -> C.CDLL:
     L.bmTreeCopyTopology.argtypes = [vp, vp, vp, vp, vp]
     L.bmTreeCopyChildBoxes.argtypes = [vp, vp]
     L.bmTreeMeshBases.argtypes = [vp, C.POINTER(u32), u32]
+    L.bmTreeArraySizes.argtypes = [vp, C.POINTER(u64)]
+    L.bmTreeExport.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.bmTreeImport.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, u64, u64, u64]
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]
     L.bmTraceCamera.argtypes = [vp, vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
     L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]

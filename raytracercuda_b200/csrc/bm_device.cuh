@@ -78,13 +78,13 @@ int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32*
 // ---- hierarchy.cu ---------------------------------------------------------------------------------------------------
 int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s);
 int write_leaves(const Grid& g, const u64* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, float4* d_leaves, u32* d_clusterCounts,
-                 cudaStream_t s);
+                 u32* d_codes, cudaStream_t s);
 int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_ltris, cudaStream_t s);
 // cluster boxes + leaf boxes + leaf statistics + the 256-cap exclusion flags; d_clusterFirst = exclusive scan of the cluster counts
-int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_clusterFirst, float4* d_ltris, float4* d_clusters, float* d_leafBox6, float pad, u32* d_stats,
-                cudaStream_t s);
-int emit_hierarchy(const Grid& g, const float4* d_leaves, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s);
-int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit, float4* d_nodes, cudaStream_t s);
+int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* d_leafIdx, size_t numPairs, const u32* d_clusterFirst, float4* d_ltris,
+                float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, cudaStream_t s);
+int emit_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s);
+int refit(u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit, float4* d_nodes, cudaStream_t s);
 int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, u64* d_out, cudaStream_t s);
 int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s);
 

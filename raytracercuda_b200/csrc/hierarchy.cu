@@ -20,7 +20,7 @@ __global__ void mark_heads_kernel(const u64* __restrict__ keys, size_t n, u32* _
 }
 
 __global__ void write_leaves_kernel(Grid g, const u64* __restrict__ keys, const u32* __restrict__ flags, const u32* __restrict__ leafIdx, size_t n,
-                                    u32 numLeaves, float4* __restrict__ leaves, u32* __restrict__ clusterCounts)
+                                    u32 numLeaves, float4* __restrict__ leaves, u32* __restrict__ clusterCounts, u32* __restrict__ codes)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -36,6 +36,7 @@ __global__ void write_leaves_kernel(Grid g, const u64* __restrict__ keys, const 
     o[1] = make_float4(mn.x, mn.y, mn.z, mx.x);
     o[2] = make_float4(mx.y, mx.z, 0.f, 0.f);
     clusterCounts[l] = (cnt + CLUSTER - 1) / CLUSTER;
+    codes[l] = code;                                   // dense copy for the hierarchy's binary searches
 }
 
 __global__ void pack_leaf_tris_kernel(const float4* __restrict__ soup, const u32* __restrict__ vals, size_t n, float4* __restrict__ ltris)
@@ -51,13 +52,42 @@ __global__ void pack_leaf_tris_kernel(const float4* __restrict__ soup, const u32
     o[2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, c.w);
 }
 
-// Per leaf: cluster boxes (groups of CLUSTER consecutive pairs), the leaf's tight box (their union), leaf-size statistics and the
-// reference's face cap.  Boxes enclose WHOLE triangles (not clipped to the cell: reference mode must still find a hit that lies
-// outside the cell, BuildTree.cu:413-431).  v1 = v0 + e1 may differ from the stored vertex by one rounding, and a hit the triangle
-// test accepts numerically may lie a few ulps of the ray length outside the exact box: `pad` (world extent * 2^-20, far below the
-// cell size) absorbs both.  stats[0] = max leaf size, stats[1] = leaves above 256 faces.
+// Cluster boxes: one thread per pair; the thread of the first pair of each group of CLUSTER consecutive pairs of a leaf builds the
+// group's box.  Boxes enclose WHOLE triangles (not clipped to the cell: reference mode must still find a hit that lies outside the
+// cell, BuildTree.cu:413-431).  v1 = v0 + e1 may differ from the stored vertex by one rounding, and a hit the triangle test accepts
+// numerically may lie a few ulps of the ray length outside the exact box: `pad` (world extent * 2^-20, far below the cell size)
+// absorbs both.
+__global__ void cluster_bounds_kernel(const float4* __restrict__ leaves, const u32* __restrict__ flags, const u32* __restrict__ leafIdx,
+                                      const u32* __restrict__ clusterFirst, size_t n, const float4* __restrict__ ltris, float4* __restrict__ clusters, float pad)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 l = leafIdx[i] + flags[i] - 1u;        // leafIdx = exclusive scan of the head flags: heads before i, so a non-head pair sees its leaf + 1
+    float4 r0 = __ldg(&leaves[LEAF_F4 * (size_t)l]);
+    u32 first = __float_as_uint(r0.y), cnt = __float_as_uint(r0.z);
+    u32 local = (u32)(i - first);
+    if (local % CLUSTER) return;
+    float clo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, chi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    u32 end = min(local + CLUSTER, cnt);
+    for (u32 k = local; k < end; k++)
+    {
+        const float4* p = ltris + 3 * (size_t)(first + k);
+        float4 a = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+        float v[3][3] = { { a.x, a.y, a.z }, { a.x + e1.x, a.y + e1.y, a.z + e1.z }, { a.x + e2.x, a.y + e2.y, a.z + e2.z } };
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) { clo[c] = fminf(clo[c], v[q][c] - pad); chi[c] = fmaxf(chi[c], v[q][c] + pad); }
+    }
+    float4* o = clusters + CLUSTER_F4 * (size_t)(clusterFirst[l] + local / CLUSTER);
+    o[0] = make_float4(clo[0], clo[1], clo[2], chi[0]);
+    o[1] = make_float4(chi[1], chi[2], 0.f, 0.f);
+}
+
+// Per leaf: tight box = union of its cluster boxes, first-cluster index into the record, leaf-size statistics (stats[0] = max leaf
+// size, stats[1] = leaves above 256 faces) and the reference's face cap.
 __global__ void leaf_bounds_kernel(float4* __restrict__ leaves, u32 numLeaves, const u32* __restrict__ clusterFirst, float4* __restrict__ ltris,
-                                   float4* __restrict__ clusters, float* __restrict__ box6, float pad, u32* stats)
+                                   const float4* __restrict__ clusters, float4* __restrict__ box2, u32* stats)
 {
     u32 l = blockIdx.x * blockDim.x + threadIdx.x;
     float4 r0 = l < numLeaves ? leaves[LEAF_F4 * (size_t)l] : make_float4(0, 0, 0, 0);
@@ -73,27 +103,16 @@ __global__ void leaf_bounds_kernel(float4* __restrict__ leaves, u32 numLeaves, c
     u32 cf = clusterFirst[l];
     leaves[LEAF_F4 * (size_t)l].w = __uint_as_float(cf);
     float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-    for (u32 c0 = 0; c0 < cnt; c0 += CLUSTER)
+    u32 ncl = (cnt + CLUSTER - 1) / CLUSTER;
+    for (u32 c = 0; c < ncl; c++)
     {
-        float clo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, chi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-        for (u32 i = c0; i < min(c0 + CLUSTER, cnt); i++)
-        {
-            const float4* p = ltris + 3 * (size_t)(first + i);
-            float4 a = p[0], e1 = p[1], e2 = p[2];
-            float v[3][3] = { { a.x, a.y, a.z }, { a.x + e1.x, a.y + e1.y, a.z + e1.z }, { a.x + e2.x, a.y + e2.y, a.z + e2.z } };
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-#pragma unroll
-                for (int q = 0; q < 3; q++) { clo[q] = fminf(clo[q], v[k][q] - pad); chi[q] = fmaxf(chi[q], v[k][q] + pad); }
-        }
-        float4* o = clusters + CLUSTER_F4 * (size_t)(cf + c0 / CLUSTER);
-        o[0] = make_float4(clo[0], clo[1], clo[2], chi[0]);
-        o[1] = make_float4(chi[1], chi[2], 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < 3; q++) { lo[q] = fminf(lo[q], clo[q]); hi[q] = fmaxf(hi[q], chi[q]); }
+        const float4* p = clusters + CLUSTER_F4 * (size_t)(cf + c);
+        float4 b0 = p[0], b1 = p[1];
+        lo[0] = fminf(lo[0], b0.x); lo[1] = fminf(lo[1], b0.y); lo[2] = fminf(lo[2], b0.z);
+        hi[0] = fmaxf(hi[0], b0.w); hi[1] = fmaxf(hi[1], b1.x); hi[2] = fmaxf(hi[2], b1.y);
     }
-    float* o = box6 + 6 * (size_t)l;
-    o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = hi[0]; o[4] = hi[1]; o[5] = hi[2];
+    box2[2 * (size_t)l] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+    box2[2 * (size_t)l + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
     // face cap: the reference keeps the first 256 faces inserted into a leaf = the 256 smallest (mesh, triangle) ids; mark the rest
     if (cnt > 256u)
     {
@@ -110,15 +129,15 @@ __global__ void leaf_bounds_kernel(float4* __restrict__ leaves, u32 numLeaves, c
     }
 }
 
-__device__ __forceinline__ u32 leaf_code(const float4* __restrict__ leaves, int i) { return __float_as_uint(__ldg(&leaves[LEAF_F4 * (size_t)i].x)); }
-__device__ __forceinline__ int delta(const float4* __restrict__ leaves, int i, int j, int n)
+__device__ __forceinline__ u32 leaf_code(const u32* __restrict__ codes, int i) { return __ldg(codes + i); }
+__device__ __forceinline__ int delta(const u32* __restrict__ codes, int i, int j, int n)
 {
     if (j < 0 || j >= n) return -1;
-    return __clz(leaf_code(leaves, i) ^ leaf_code(leaves, j));       // codes are distinct, so never 32
+    return __clz(leaf_code(codes, i) ^ leaf_code(codes, j));       // codes are distinct, so never 32
 }
 
 // Karras 2012, one thread per internal node i in [0, L-1)
-__global__ void karras_kernel(Grid g, const float4* __restrict__ leaves, u32 numLeaves, float4* __restrict__ nodes,
+__global__ void karras_kernel(Grid g, const u32* __restrict__ leaves, u32 numLeaves, float4* __restrict__ nodes,
                               u32* __restrict__ parentOfNode, u32* __restrict__ parentOfLeaf)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,14 +181,12 @@ __global__ void karras_kernel(Grid g, const float4* __restrict__ leaves, u32 num
     o[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
 }
 
-__device__ __forceinline__ void load_box(const float* p, float b[6])
-{
-#pragma unroll
-    for (int k = 0; k < 6; k++) b[k] = __ldcg(p + k);   // written by another thread of this launch: bypass L1
-}
+// boxes travel as two float4: (lo.xyz, hi.x) (hi.y, hi.z, -, -)
+struct Box2 { float4 a, b; };
+__device__ __forceinline__ Box2 load_box(const float4* p) { Box2 r; r.a = __ldcg(p); r.b = __ldcg(p + 1); return r; }   // written by another thread of this launch: bypass L1
 
 // bottom-up: thread per leaf climbs; the second thread to reach a node has both child boxes available
-__global__ void refit_kernel(u32 numLeaves, const float* __restrict__ leafBox, float* nodeBox, const u32* __restrict__ parentOfNode,
+__global__ void refit_kernel(u32 numLeaves, const float4* __restrict__ leafBox, float4* nodeBox, const u32* __restrict__ parentOfNode,
                              const u32* __restrict__ parentOfLeaf, u32* visit, float4* nodes)
 {
     u32 l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,15 +199,15 @@ __global__ void refit_kernel(u32 numLeaves, const float* __restrict__ leafBox, f
         __threadfence();
         float4 q3 = __ldcg(&nodes[NODE_F4 * (size_t)cur + 3]);
         u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
-        float b0[6], b1[6];
-        load_box((c0 & LEAF_BIT) ? leafBox + 6 * (size_t)(c0 & ~LEAF_BIT) : nodeBox + 6 * (size_t)c0, b0);
-        load_box((c1 & LEAF_BIT) ? leafBox + 6 * (size_t)(c1 & ~LEAF_BIT) : nodeBox + 6 * (size_t)c1, b1);
-        nodes[NODE_F4 * (size_t)cur + 0] = make_float4(b0[0], b0[1], b0[2], b0[3]);
-        nodes[NODE_F4 * (size_t)cur + 1] = make_float4(b0[4], b0[5], b1[0], b1[1]);
-        nodes[NODE_F4 * (size_t)cur + 2] = make_float4(b1[2], b1[3], b1[4], b1[5]);
-        float* o = nodeBox + 6 * (size_t)cur;
-#pragma unroll
-        for (int k = 0; k < 3; k++) { __stcg(o + k, fminf(b0[k], b1[k])); __stcg(o + 3 + k, fmaxf(b0[3 + k], b1[3 + k])); }
+        Box2 b0 = load_box((c0 & LEAF_BIT) ? leafBox + 2 * (size_t)(c0 & ~LEAF_BIT) : nodeBox + 2 * (size_t)c0);
+        Box2 b1 = load_box((c1 & LEAF_BIT) ? leafBox + 2 * (size_t)(c1 & ~LEAF_BIT) : nodeBox + 2 * (size_t)c1);
+        float4* np = nodes + NODE_F4 * (size_t)cur;
+        np[0] = b0.a;                                                   // lo0.xyz hi0.x
+        np[1] = make_float4(b0.b.x, b0.b.y, b1.a.x, b1.a.y);            // hi0.yz lo1.xy
+        np[2] = make_float4(b1.a.z, b1.a.w, b1.b.x, b1.b.y);            // lo1.z hi1.xyz
+        float4* o = nodeBox + 2 * (size_t)cur;
+        __stcg(o, make_float4(fminf(b0.a.x, b1.a.x), fminf(b0.a.y, b1.a.y), fminf(b0.a.z, b1.a.z), fmaxf(b0.a.w, b1.a.w)));
+        __stcg(o + 1, make_float4(fmaxf(b0.b.x, b1.b.x), fmaxf(b0.b.y, b1.b.y), 0.f, 0.f));
         cur = parentOfNode[cur];
     }
 }
@@ -218,10 +235,10 @@ int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s)
     return BM_OK;
 }
 int write_leaves(const Grid& g, const u64* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, float4* d_leaves, u32* d_clusterCounts,
-                 cudaStream_t s)
+                 u32* d_codes, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    write_leaves_kernel<<<div_up(n, 256), 256, 0, s>>>(g, d_keys, d_flags, d_leafIdx, n, numLeaves, d_leaves, d_clusterCounts);
+    write_leaves_kernel<<<div_up(n, 256), 256, 0, s>>>(g, d_keys, d_flags, d_leafIdx, n, numLeaves, d_leaves, d_clusterCounts, d_codes);
     BM_LAUNCHED();
     return BM_OK;
 }
@@ -232,27 +249,29 @@ int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_
     BM_LAUNCHED();
     return BM_OK;
 }
-int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_clusterFirst, float4* d_ltris, float4* d_clusters, float* d_leafBox6, float pad, u32* d_stats,
-                cudaStream_t s)
+int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* d_leafIdx, size_t numPairs, const u32* d_clusterFirst, float4* d_ltris,
+                float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, cudaStream_t s)
 {
     if (!numLeaves) return BM_OK;
-    leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_clusterFirst, d_ltris, d_clusters, d_leafBox6, pad, d_stats);
+    cluster_bounds_kernel<<<div_up(numPairs, 256), 256, 0, s>>>(d_leaves, d_flags, d_leafIdx, d_clusterFirst, numPairs, d_ltris, d_clusters, pad);
+    BM_LAUNCHED();
+    leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_clusterFirst, d_ltris, d_clusters, d_leafBox2, d_stats);
     BM_LAUNCHED();
     return BM_OK;
 }
-int emit_hierarchy(const Grid& g, const float4* d_leaves, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s)
+int emit_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s)
 {
     if (numLeaves < 2) return BM_OK;
-    karras_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(g, d_leaves, numLeaves, d_nodes, d_parentOfNode, d_parentOfLeaf);
+    karras_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_nodes, d_parentOfNode, d_parentOfLeaf);
     BM_LAUNCHED();
     return BM_OK;
 }
-int refit(u32 numLeaves, const float* d_leafBox6, float* d_nodeBox6, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit,
+int refit(u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit,
           float4* d_nodes, cudaStream_t s)
 {
     if (numLeaves < 2) return BM_OK;
     BM_CUDA(cudaMemsetAsync(d_visit, 0, (size_t)(numLeaves - 1) * 4, s));
-    refit_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(numLeaves, d_leafBox6, d_nodeBox6, d_parentOfNode, d_parentOfLeaf, d_visit, d_nodes);
+    refit_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(numLeaves, d_leafBox2, d_nodeBox2, d_parentOfNode, d_parentOfLeaf, d_visit, d_nodes);
     BM_LAUNCHED();
     return BM_OK;
 }

@@ -76,6 +76,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(const u32* in, 
     for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
     if (totalOut && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *totalOut = (tileOffsets ? tileOffsets[blockIdx.x] : 0) + total;
 }
+// small arrays (digit tables of small sorts, cluster counts ...): one block walks the array tile by tile carrying the running
+// total -- one launch instead of three
+__global__ void __launch_bounds__(SCAN_THREADS) small_scan_kernel(const u32* in, u32* out, size_t n, u32* __restrict__ totalOut)
+{
+    __shared__ u32 total;
+    u32 carry = 0;
+    for (size_t tileBase = 0; tileBase < n; tileBase += SCAN_TILE)
+    {
+        size_t base = tileBase + (size_t)threadIdx.x * SCAN_ITEMS;
+        u32 v[SCAN_ITEMS], s = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+        u32 ex = block_exclusive_scan(s, &total) + carry;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+        carry += total;
+        __syncthreads();
+    }
+    if (totalOut && threadIdx.x == 0) *totalOut = carry;
+}
+constexpr size_t SMALL_SCAN_MAX = 16 * (size_t)SCAN_TILE;    // 65,536 elements
 } // namespace
 
 size_t scan_temp_bytes(size_t n)
@@ -89,9 +110,9 @@ int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void
 {
     if (n == 0) { if (d_total) BM_CUDA(cudaMemsetAsync(d_total, 0, 4, s)); return BM_OK; }
     size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    if (tiles == 1)
+    if (n <= SMALL_SCAN_MAX)
     {
-        tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, n, nullptr, d_total);
+        small_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_total);
         BM_LAUNCHED();
         return BM_OK;
     }

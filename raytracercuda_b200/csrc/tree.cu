@@ -30,10 +30,12 @@ int sm_count()
 // grow-only device buffer: rebuilding a scene of the same size performs no allocation
 struct DevBuf
 {
-    void* p = nullptr; size_t cap = 0;
+    void* p = nullptr; size_t cap = 0; bool owned = true;
+    void adopt(const void* ext, size_t bytes) { release(); p = const_cast<void*>(ext); cap = bytes; owned = false; }   // caller keeps it alive
     int reserve(size_t bytes)
     {
         if (bytes <= cap) return BM_OK;
+        if (!owned) { set_error("imported (read-only) tree: rebuild not possible"); return BM_ERROR_INVALID_PARAMETER; }
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -41,7 +43,7 @@ struct DevBuf
         cap = want;
         return BM_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; cap = 0; owned = true; }
     template <class T> T* as() const { return (T*)p; }
 };
 
@@ -58,9 +60,9 @@ struct bmTree
     cudaStream_t stream = 0;
     std::vector<StagedMesh> staged;
     std::vector<u32> meshBase;       // indexed by position in `staged` order
-    bool built = false;
+    bool built = false, imported = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes;
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
     u32 maxLeaf = 0, overLeaves = 0;
@@ -75,7 +77,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -138,21 +140,21 @@ static int tree_build(bmTree* t)
     BM_CUDA(cudaStreamSynchronize(s));
     u64 L = t->hostScalars[1];
     t->L = L;
-    BM_TRY(t->leaves.reserve(L * 16 * LEAF_F4)); BM_TRY(t->clusterCounts.reserve(L * 4 + 4));
-    BM_TRY(write_leaves(t->dgrid, t->sortedKeys, t->flags.as<u32>(), leafIdx, P, (u32)L, t->leaves.as<float4>(), t->clusterCounts.as<u32>(), s));
+    BM_TRY(t->leaves.reserve(L * 16 * LEAF_F4)); BM_TRY(t->clusterCounts.reserve(L * 4 + 4)); BM_TRY(t->codes.reserve(L * 4 + 4));
+    BM_TRY(write_leaves(t->dgrid, t->sortedKeys, t->flags.as<u32>(), leafIdx, P, (u32)L, t->leaves.as<float4>(), t->clusterCounts.as<u32>(), t->codes.as<u32>(), s));
     BM_TRY(exclusive_scan_u32(t->clusterCounts.as<u32>(), t->clusterCounts.as<u32>(), L, nullptr, t->temp.p, s));
     BM_TRY(t->clusters.reserve((P / CLUSTER + L + 1) * 16 * CLUSTER_F4));
-    BM_TRY(t->leafBox.reserve(L * 24));
+    BM_TRY(t->leafBox.reserve(L * 32));
     float pad = ext * (1.f / 1048576.f);
-    BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(), t->leafBox.as<float>(), pad,
-                       d_scal + 2, s));
+    BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->flags.as<u32>(), leafIdx, P, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(),
+                       t->leafBox.as<float4>(), pad, d_scal + 2, s));
     // 5. hierarchy + refit
     if (L >= 2)
     {
-        BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4)); BM_TRY(t->nodeBox.reserve((L - 1) * 24));
+        BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4)); BM_TRY(t->nodeBox.reserve((L - 1) * 32));
         BM_TRY(t->parentN.reserve((L - 1) * 4)); BM_TRY(t->parentL.reserve(L * 4)); BM_TRY(t->visit.reserve((L - 1) * 4));
-        BM_TRY(emit_hierarchy(t->dgrid, t->leaves.as<float4>(), (u32)L, t->nodes.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), s));
-        BM_TRY(refit((u32)L, t->leafBox.as<float>(), t->nodeBox.as<float>(), t->parentN.as<u32>(), t->parentL.as<u32>(), t->visit.as<u32>(), t->nodes.as<float4>(), s));
+        BM_TRY(emit_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->nodes.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), s));
+        BM_TRY(refit((u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), t->visit.as<u32>(), t->nodes.as<float4>(), s));
     }
     t->built = true;
     return BM_OK;
@@ -220,6 +222,7 @@ extern "C" int bmTreeAddMesh(bmTree* t, const float* d_positions, const uint32_t
 extern "C" int bmTreeBuild(bmTree* t)
 {
     if (!t) return BM_ERROR_INVALID_PARAMETER;
+    if (t->imported) { set_error("imported (read-only) tree: rebuild not possible"); return BM_ERROR_INVALID_PARAMETER; }
     return tree_build(t);
 }
 
@@ -228,7 +231,7 @@ extern "C" int bmTreeStats(const bmTree* tc, uint64_t* s)
     bmTree* t = const_cast<bmTree*>(tc);
     if (!t || !s) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) return BM_ERROR_NOT_BUILT;
-    BM_TRY(tree_finish_stats(t));
+    if (!t->imported) BM_TRY(tree_finish_stats(t));
     s[0] = t->T; s[1] = t->P; s[2] = t->L; s[3] = t->L ? t->L - 1 : 0; s[4] = (u64)t->hgrid.D; s[5] = t->maxLeaf; s[6] = t->overLeaves; s[7] = t->staged.size();
     return BM_OK;
 }
@@ -237,7 +240,7 @@ extern "C" int bmTreeCopyPairs(const bmTree* tc, uint32_t* d_code, uint32_t* d_t
 {
     bmTree* t = const_cast<bmTree*>(tc);
     if (!t) return BM_ERROR_INVALID_PARAMETER;
-    if (!t->built) return BM_ERROR_NOT_BUILT;
+    if (!t->built || t->imported) return BM_ERROR_NOT_BUILT;
     if (!t->P) return BM_OK;
     // The tree keeps the pairs of a leaf in sub-key order; the canonical list parity is defined on is ordered by
     // (code, global triangle id).  It is produced here on request: rekey to code<<32|tri and sort (not part of the build).
@@ -280,6 +283,50 @@ extern "C" int bmTreeMeshBases(const bmTree* t, uint32_t* h_bases, uint32_t capa
     if (!t || !h_bases) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) return BM_ERROR_NOT_BUILT;
     for (size_t i = 0; i < t->meshBase.size() && i < capacity; i++) h_bases[i] = t->meshBase[i];
+    return BM_OK;
+}
+
+// ---- replication: the traversal arrays are index-based, so a tree can be copied to / adopted from caller-owned device memory ----
+extern "C" int bmTreeArraySizes(const bmTree* t, uint64_t* sizes8)
+{
+    if (!t || !sizes8) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    size_t nC = t->P ? t->P / CLUSTER + t->L + 1 : 0;
+    sizes8[0] = t->L >= 2 ? (t->L - 1) * 16ull * NODE_F4 : 0;     // nodes
+    sizes8[1] = t->L * 16ull * LEAF_F4;                             // leaves
+    sizes8[2] = t->P * 48ull;                                       // triangle records
+    sizes8[3] = nC * 16ull * CLUSTER_F4;                            // cluster boxes
+    sizes8[4] = t->T * 48ull;                                       // soup (only bmBounceRays reads it)
+    sizes8[5] = t->L; sizes8[6] = t->P; sizes8[7] = t->T;
+    return BM_OK;
+}
+
+extern "C" int bmTreeExport(const bmTree* t, void* d_nodes, void* d_leaves, void* d_ltris, void* d_clusters, void* d_soup)
+{
+    uint64_t sz[8];
+    BM_TRY(bmTreeArraySizes(t, sz));
+    const void* src[5] = { t->nodes.p, t->leaves.p, t->ltris.p, t->clusters.p, t->soup.p };
+    void* dst[5] = { d_nodes, d_leaves, d_ltris, d_clusters, d_soup };
+    for (int i = 0; i < 5; i++)
+        if (dst[i] && sz[i]) BM_CUDA(cudaMemcpyAsync(dst[i], src[i], sz[i], cudaMemcpyDeviceToDevice, t->stream));
+    return BM_OK;
+}
+
+extern "C" int bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
+                            uint64_t numLeaves, uint64_t numPairs, uint64_t numTris)
+{
+    if (!out) return BM_ERROR_INVALID_PARAMETER;
+    bmTree* t = nullptr;
+    BM_TRY(bmTreeCreate(&t, nullptr, nullptr, 0.f, 0));
+    t->L = numLeaves; t->P = numPairs; t->T = numTris;
+    size_t nC = numPairs ? numPairs / CLUSTER + numLeaves + 1 : 0;
+    t->nodes.adopt(d_nodes, numLeaves >= 2 ? (numLeaves - 1) * 16ull * NODE_F4 : 0);
+    t->leaves.adopt(d_leaves, numLeaves * 16ull * LEAF_F4);
+    t->ltris.adopt(d_ltris, numPairs * 48ull);
+    t->clusters.adopt(d_clusters, nC * 16ull * CLUSTER_F4);
+    t->soup.adopt(d_soup, numTris * 48ull);
+    t->built = true; t->imported = true;
+    *out = t;
     return BM_OK;
 }
 

@@ -206,3 +206,34 @@ def test_bounce_rays_workflow(oracle_lib, beam_lib, cuda_device):
     r = s.trace_rays(B[:, :3], B[:, 3:], 0, NT)
     _compare(h2, r, t.mesh_bases(), what="bounce rays")
     t.close(); s.close()
+
+
+def test_export_import_replica_traces_identically(meshes, beam_lib, cuda_device):
+    """multi-GPU replication path on one GPU: export the traversal arrays, adopt them as a read-only tree, trace both"""
+    import ctypes as C
+    import torch
+    from raytracercuda_b200 import _lib
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    P, I, N = meshes["bunny"]
+    t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+    sz = (C.c_uint64 * 8)()
+    assert beam_lib.bmTreeArraySizes(t.h, sz) == 0
+    st = t.stats()
+    assert (sz[5], sz[6], sz[7]) == (st["leaves"], st["pairs"], st["triangles"])
+    bufs = [torch.empty(max(int(b), 16), dtype=torch.uint8, device=cuda_device) for b in sz[:5]]
+    assert beam_lib.bmTreeExport(t.h, *[b.data_ptr() for b in bufs]) == 0
+    torch.cuda.synchronize()
+    h = C.c_void_p()
+    assert beam_lib.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7]) == 0
+    rng = np.random.default_rng(5)
+    R = torch.from_numpy(_ray_batch(rng, 40000, 2.5)).to(cuda_device)
+    a = hits_to_numpy(t.trace_rays(R, 0))
+    hits = torch.empty((R.shape[0], 4), dtype=torch.float32, device=cuda_device)
+    assert beam_lib.bmTraceRays(h, R.data_ptr(), R.shape[0], 0, hits.data_ptr(), None) == 0
+    b = hits_to_numpy(hits)
+    assert np.array_equal(a["tri"], b["tri"]) and np.array_equal(a["t"], b["t"])
+    assert beam_lib.bmTreeBuild(h) != 0                      # read-only
+    st8 = (C.c_uint64 * 8)()
+    assert beam_lib.bmTreeStats(h, st8) == 0 and st8[2] == st["leaves"]
+    beam_lib.bmTreeDestroy(h)
+    t.close()
