@@ -107,6 +107,10 @@ def run_b200(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (the product has no CPU path)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # libraries (NCCL's version banner) must not write to stdout: the driver reads ONE JSON line there
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from raytracercuda_b200 import build
@@ -234,15 +238,50 @@ def run_b200(args):
     value = float(r_sum.item()) / args.steps / (ms_per_step * 1e-3) / 1e6
 
     # --- timed: e2e through host buffers ---------------------------------------------------------------------------------
+    # Every step: the camera table comes from pinned host memory, the framebuffer and the bounce hit records go back to pinned host
+    # memory.  The frame is cut into row bands; band k+1 is uploaded and band k-1 downloaded (copy streams) while band k is traced
+    # (compute stream), so the copies hide behind the kernels instead of adding to them.
+    BANDS = args.e2e_bands if H % args.e2e_bands == 0 else 1
+    nbnd = n // BANDS
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    cntb = torch.zeros(BANDS, dtype=torch.int32, device=dev); cntb_host = torch.zeros(BANDS, dtype=torch.int32).pin_memory()
+    e2e_rays_dev = torch.empty_like(rays_dev)
+
     def frame_e2e():
-        r = rays_dev.copy_(rays_pinned, non_blocking=True)
-        total = frame(r)
-        pix_host.copy_(pixels, non_blocking=True)
-        nbk = bounce_count()                      # the host needs the count to size the read-back of the bounce hits
-        if nbk:
-            hits2_host[:nbk].copy_(hits2[:nbk], non_blocking=True)
-        stream.synchronize()
-        return total + nbk
+        evh = [torch.cuda.Event() for _ in range(BANDS)]; evc = [torch.cuda.Event() for _ in range(BANDS)]; evd = [torch.cuda.Event() for _ in range(BANDS)]
+        s_h2d.wait_stream(stream); s_d2h.wait_stream(stream)
+        for k in range(BANDS):
+            lo, hi = k * nbnd, (k + 1) * nbnd
+            with torch.cuda.stream(s_h2d):
+                e2e_rays_dev[lo:hi].copy_(rays_pinned[lo:hi], non_blocking=True)
+                evh[k].record(s_h2d)
+            stream.wait_event(evh[k])
+            rp = e2e_rays_dev.data_ptr() + lo * 12
+            _lib.check(L.bmTraceCamera(tree.h, rp, nbnd, W, _f3(eye), _f9(orient), 0, hits1.data_ptr() + lo * 16, pixels.data_ptr() + lo * 4, table.data_ptr(), None), "bmTraceCamera")
+            if wl.bounces:
+                _lib.check(L.bmBounceRaysCamera(tree.h, rp, _f3(eye), _f9(orient), hits1.data_ptr() + lo * 16, nbnd, 0, 1, args.seed, rays2.data_ptr() + lo * 24,
+                                                src2.data_ptr() + lo * 4, cntb.data_ptr() + k * 4), "bmBounceRaysCamera")
+                _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr() + lo * 24, cntb.data_ptr() + k * 4, nbnd, 0, hits2.data_ptr() + lo * 16, None), "bmTraceRaysIndirect")
+            evc[k].record(stream)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(evc[k])
+                pix_host[lo:hi].copy_(pixels[lo:hi], non_blocking=True)
+                if wl.bounces:
+                    cntb_host[k:k + 1].copy_(cntb[k:k + 1], non_blocking=True)
+                evd[k].record(s_d2h)
+        total = n
+        for k in range(BANDS):
+            if wl.bounces:
+                evd[k].synchronize()
+                c = int(cntb_host[k]); lo = k * nbnd
+                total += c
+                if c:
+                    with torch.cuda.stream(s_d2h):
+                        hits2_host[lo:lo + c].copy_(hits2[lo:lo + c], non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), pixels)
+        s_d2h.synchronize(); stream.synchronize()
+        return total
     for _ in range(2):
         frame_e2e()
     e2e_ms, e2e_rays = [], 0
@@ -258,7 +297,7 @@ def run_b200(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
     e2e_value = float(r2.item()) / (float(t2.item()) * 1e-3) / 1e6
     h2d = n * 12 + 48
-    d2h = n * 4 + (nb * 16 if wl.bounces else 0) + (4 if wl.bounces else 0)
+    d2h = n * 4 + (nb * 16 if wl.bounces else 0) + (4 * BANDS if wl.bounces else 0)
 
     # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
     build_ms = []
@@ -323,14 +362,18 @@ def run_b200(args):
                        "trace_mode": "reference semantics (BM_TRACE_REFERENCE)", "l2": "flushed between timed steps (256 MiB write)",
                        "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer" if world > 1 else "single GPU",
                        "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
+                    "pipeline": "%d row bands; H2D of the camera table, trace and D2H of framebuffer + bounce hits overlap on 3 streams" % BANDS},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, rays_pinned.numpy(), rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
 
@@ -433,6 +476,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-bands", type=int, default=4)
     ap.add_argument("--reference-rays", type=int, default=200_000, help="primary rays per step of the --impl reference sample")
     args = ap.parse_args()
     if args.impl == "reference":
