@@ -198,17 +198,17 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         rays_step = frame(rays_dev) + bounce_count()
     # per-ray traversal counters of the same traversal (instrumented launch, outside the timed region)
-    cnt = torch.zeros(3, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
     _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
     torch.cuda.synchronize(dev)
-    V1, K1, C1 = [int(x) for x in cnt.cpu()]
+    V1, K1, C1, LONG1 = [int(x) for x in cnt.cpu()]
     nb = int(cnt_host[0]) if wl.bounces else 0
     V2 = K2 = C2 = 0
     if nb:
         cnt.zero_()
         _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
         torch.cuda.synchronize(dev)
-        V2, K2, C2 = [int(x) for x in cnt.cpu()]
+        V2, K2, C2, LONG2 = [int(x) for x in cnt.cpu()]
 
     # --- timed: K steps, device resident, L2 flushed between steps --------------------------------------------------------
     sampler = ClockSampler(local)
@@ -247,40 +247,62 @@ def run_b200(args):
     cntb = torch.zeros(BANDS, dtype=torch.int32, device=dev); cntb_host = torch.zeros(BANDS, dtype=torch.int32).pin_memory()
     e2e_rays_dev = torch.empty_like(rays_dev)
 
-    def frame_e2e():
-        evh = [torch.cuda.Event() for _ in range(BANDS)]; evc = [torch.cuda.Event() for _ in range(BANDS)]; evd = [torch.cuda.Event() for _ in range(BANDS)]
-        s_h2d.wait_stream(stream); s_d2h.wait_stream(stream)
+    def enqueue_bands(comp):
+        """all bands of one frame: H2D on s_h2d, kernels on `comp`, D2H of pixels + bounce counts on s_d2h (fork/join around comp)"""
+        s_h2d.wait_stream(comp); s_d2h.wait_stream(comp)
         for k in range(BANDS):
             lo, hi = k * nbnd, (k + 1) * nbnd
+            evh, evc = torch.cuda.Event(), torch.cuda.Event()
             with torch.cuda.stream(s_h2d):
                 e2e_rays_dev[lo:hi].copy_(rays_pinned[lo:hi], non_blocking=True)
-                evh[k].record(s_h2d)
-            stream.wait_event(evh[k])
+                evh.record(s_h2d)
+            comp.wait_event(evh)
             rp = e2e_rays_dev.data_ptr() + lo * 12
             _lib.check(L.bmTraceCamera(tree.h, rp, nbnd, W, _f3(eye), _f9(orient), 0, hits1.data_ptr() + lo * 16, pixels.data_ptr() + lo * 4, table.data_ptr(), None), "bmTraceCamera")
             if wl.bounces:
                 _lib.check(L.bmBounceRaysCamera(tree.h, rp, _f3(eye), _f9(orient), hits1.data_ptr() + lo * 16, nbnd, 0, 1, args.seed, rays2.data_ptr() + lo * 24,
                                                 src2.data_ptr() + lo * 4, cntb.data_ptr() + k * 4), "bmBounceRaysCamera")
                 _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr() + lo * 24, cntb.data_ptr() + k * 4, nbnd, 0, hits2.data_ptr() + lo * 16, None), "bmTraceRaysIndirect")
-            evc[k].record(stream)
+            evc.record(comp)
             with torch.cuda.stream(s_d2h):
-                s_d2h.wait_event(evc[k])
+                s_d2h.wait_event(evc)
                 pix_host[lo:hi].copy_(pixels[lo:hi], non_blocking=True)
                 if wl.bounces:
                     cntb_host[k:k + 1].copy_(cntb[k:k + 1], non_blocking=True)
-                evd[k].record(s_d2h)
+        comp.wait_stream(s_h2d); comp.wait_stream(s_d2h)
+
+    # the per-frame launch sequence is fixed, so it is captured once into a CUDA graph and replayed (removes the host launch cost
+    # of 4 bands x ~10 launches); the bounce hit records are read back after the replay, sized by the counts the graph produced
+    graph = None
+    try:
+        enqueue_bands(stream); stream.synchronize()                 # warm-up outside capture (allocations, occupancy queries)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            cs = torch.cuda.current_stream(dev)
+            tree.use_stream(cs)
+            enqueue_bands(cs)
+        tree.use_stream(stream)
+    except Exception as ex:                                          # keep the run alive; say so in the line
+        sys.stderr.write("e2e: CUDA graph capture failed (%r), falling back to direct launches\n" % (ex,))
+        graph = None
+        tree.use_stream(stream)
+
+    def frame_e2e():
+        if graph is not None:
+            graph.replay()
+        else:
+            enqueue_bands(stream)
+        stream.synchronize()
         total = n
-        for k in range(BANDS):
-            if wl.bounces:
-                evd[k].synchronize()
+        if wl.bounces:
+            for k in range(BANDS):
                 c = int(cntb_host[k]); lo = k * nbnd
                 total += c
                 if c:
-                    with torch.cuda.stream(s_d2h):
-                        hits2_host[lo:lo + c].copy_(hits2[lo:lo + c], non_blocking=True)
+                    hits2_host[lo:lo + c].copy_(hits2[lo:lo + c], non_blocking=True)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), pixels)
-        s_d2h.synchronize(); stream.synchronize()
+        stream.synchronize()
         return total
     for _ in range(2):
         frame_e2e()
@@ -346,7 +368,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "trace_kernel<camera> (bmTraceCamera, reference semantics)", "achieved": prim_bytes / (pms * 1e-3) / 1e9,
                 "peak": peak, "unit": "GB/s", "frac": prim_bytes / (pms * 1e-3) / 1e9 / peak, "traffic": None,
                 "ms_per_launch": pms, "mrays_per_s": n / (pms * 1e-3) / 1e6,
-                "bytes_per_ray": prim_bytes / n, "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n, "cluster_boxes_per_ray": C1 / n,
+                "bytes_per_ray": prim_bytes / n, "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n, "cluster_boxes_per_ray": C1 / n, "longest_ray_steps": LONG1,
                 "note": "algorithmic bytes = 12 B ray + 16 B hit + 4 B pixel + 96 B x node/leaf visits + 32 B x cluster boxes + 48 B x triangle tests (counters of the same traversal); "
                         + peak_src + "; the tree (~%.0f MB) is L2-resident on B200, so this kernel is latency/issue-bound, not HBM-bound (SURVEY 8d)" %
                         ((st["nodes"] * 128 + st["pairs"] * 56 + st["leaves"] * 48) / 1e6)}
@@ -363,7 +385,8 @@ def run_b200(args):
                        "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer" if world > 1 else "single GPU",
                        "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
-                    "pipeline": "%d row bands; H2D of the camera table, trace and D2H of framebuffer + bounce hits overlap on 3 streams" % BANDS},
+                    "pipeline": "%d row bands; H2D of the camera table, trace and D2H of framebuffer overlap on 3 streams, %s; bounce hit records read back after, sized by the device-side counts"
+                                % (BANDS, "replayed as one CUDA graph" if graph is not None else "direct launches")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

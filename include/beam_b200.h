@@ -147,8 +147,9 @@ int  bmTreeExport(const bmTree* tree, void* d_nodes, void* d_leaves, void* d_ltr
 int  bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
                   uint64_t numLeaves, uint64_t numPairs, uint64_t numTris);
 
-/* Explicit ray batch -> hit records. d_counters (nullable) accumulates {node + leaf visits, triangle tests, cluster boxes tested}
- * into three uint64 (the traversal work behind the bytes-per-ray roofline model). */
+/* Explicit ray batch -> hit records. d_counters (nullable, FOUR uint64) accumulates {node + leaf visits, triangle tests, cluster
+ * boxes tested} (the traversal work behind the bytes-per-ray roofline model) and keeps in [3] the largest number of such steps any
+ * single ray needed (the launch's critical path). */
 int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters);
 /* Same, with the ray count read from DEVICE memory when the kernel starts (*d_numRays <= maxRays): lets a producer such as
  * bmBounceRays feed the trace without a host round trip. */

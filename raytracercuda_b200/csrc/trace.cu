@@ -17,6 +17,7 @@ namespace
 {
 constexpr int TR_THREADS = 128;
 constexpr int TR_STACK = 36;     // radix tree depth <= D <= 32
+constexpr int COOP_MAX_LANES = 8;   // at most this many pending leaves in a warp -> process them warp-cooperatively
 constexpr u32 REF_EMPTY = 0x7FFFFFFFu;   // "nothing left to visit" (never a valid internal index: N < 2^31 - 1)
 
 struct HitRec { float t, u, v; u32 tri, mesh, face; };
@@ -137,6 +138,93 @@ __device__ u32 shade(const HitRec& h, const bmStaticMeshData* __restrict__ meshD
     return (u32)fabsf(n.z * 255) << 16;
 }
 
+// monotone map float -> u32 (any sign, -0 folded onto +0) so that (d, triangle id) pairs can be min-reduced as one 64-bit key
+__device__ __forceinline__ u32 orderable(float f)
+{
+    u32 u = __float_as_uint(f == 0.f ? 0.f : f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Warp-cooperative leaf: all 32 lanes work on ONE ray's leaf -- 32 cluster boxes per step, then 32 faces per step (8 passing groups
+// of 4) -- and a 64-bit min-reduction picks the winner under the reference's rule (strict minimum d of any sign, smaller id on a
+// tie).  Used when only a few lanes of the warp have a leaf pending (the tail of a launch is a handful of long, grazing rays whose
+// work is ~90 % cluster boxes and faces): it turns hundreds of dependent steps of one lane into a few warp-wide ones.
+template <int MODE, bool COUNT>
+__device__ __forceinline__ void coop_leaf(const TreeView& tv, unsigned lane, int owner, V3 o, V3 d, V3 ic, V3 oi, u32 first, u32 cnt, u32 cfirst,
+                                          HitRec& best, u32& nt, u32& nc)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    // the owner's ray and leaf, broadcast
+    V3 ro = mk3(__shfl_sync(FULL, o.x, owner), __shfl_sync(FULL, o.y, owner), __shfl_sync(FULL, o.z, owner));
+    V3 rd = mk3(__shfl_sync(FULL, d.x, owner), __shfl_sync(FULL, d.y, owner), __shfl_sync(FULL, d.z, owner));
+    V3 ric = mk3(__shfl_sync(FULL, ic.x, owner), __shfl_sync(FULL, ic.y, owner), __shfl_sync(FULL, ic.z, owner));
+    V3 roi = mk3(__shfl_sync(FULL, oi.x, owner), __shfl_sync(FULL, oi.y, owner), __shfl_sync(FULL, oi.z, owner));
+    u32 lfirst = __shfl_sync(FULL, first, owner), lcnt = __shfl_sync(FULL, cnt, owner), lcf = __shfl_sync(FULL, cfirst, owner);
+    HitRec mine = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
+    u32 ngroups = (lcnt + CLUSTER - 1) / CLUSTER;
+    u32 tests = 0, boxes = 0;
+    for (u32 gbase = 0; gbase < ngroups; gbase += 32)
+    {
+        // 32 cluster boxes at once (a single group needs no box: the parent tested the leaf box)
+        u32 g = gbase + lane;
+        bool pass = false;
+        if (g < ngroups)
+        {
+            if (ngroups == 1) pass = true;
+            else
+            {
+                const float4* cp = tv.clusters + CLUSTER_F4 * (size_t)(lcf + g);
+                float4 b0 = __ldg(cp), b1 = __ldg(cp + 1);
+                boxes++;
+                pass = line_hits_box_fma(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), ric, roi);
+            }
+        }
+        unsigned bits = __ballot_sync(FULL, pass);
+        // faces of the passing groups, 8 groups (32 faces) per step
+        u32 npass = __popc(bits);
+        for (u32 k0 = 0; k0 < npass; k0 += 8)
+        {
+            u32 k = k0 + (lane >> 2);
+            if (k < npass)
+            {
+                u32 grp = gbase + __fns(bits, 0, (int)k + 1);
+                u32 i = grp * CLUSTER + (lane & 3);
+                if (i < lcnt)
+                {
+                    const float4* p = tv.ltris + 3 * (size_t)(lfirst + i);
+                    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+                    tests++;
+                    test_face<MODE>(a, b, c, ro, rd, mine);
+                }
+            }
+        }
+    }
+    // winner = min over lanes of (d, id)
+    u32 khi = orderable(mine.t), klo = mine.tri;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1)
+    {
+        u32 ohi = __shfl_xor_sync(FULL, khi, m), olo = __shfl_xor_sync(FULL, klo, m);
+        if (ohi < khi || (ohi == khi && olo < klo)) { khi = ohi; klo = olo; }
+    }
+    unsigned who = __ballot_sync(FULL, orderable(mine.t) == khi && mine.tri == klo);
+    int w = __ffs(who) - 1;
+    float wt = __shfl_sync(FULL, mine.t, w), wu = __shfl_sync(FULL, mine.u, w), wv = __shfl_sync(FULL, mine.v, w);
+    u32 wtri = __shfl_sync(FULL, mine.tri, w), wmesh = __shfl_sync(FULL, mine.mesh, w), wface = __shfl_sync(FULL, mine.face, w);
+    if (COUNT)
+    {
+        tests = __reduce_add_sync(FULL, tests); boxes = __reduce_add_sync(FULL, boxes);
+    }
+    if ((int)lane == owner)
+    {
+        if (COUNT) { nt += tests; nc += boxes; }
+        if (wt < best.t || (wt == best.t && wt != FLT_MAX && wtri < best.tri))
+        {
+            best.t = wt; best.u = wu; best.v = wv; best.tri = wtri; best.mesh = wmesh; best.face = wface;
+        }
+    }
+}
+
 // Slot -> ray index.  With a width, slots enumerate 8x4 pixel tiles (one tile per warp-sized fetch) so that the lanes of a
 // warp start on neighbouring pixels in both directions; slots that fall outside the image map to "no ray".
 __device__ __forceinline__ bool slot_to_ray(u32 slot, u64 n, u32 width, u32 height, u64& ray)
@@ -169,7 +257,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
     u64 rayIdx = 0;
     V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), ic = mk3(0, 0, 1), oi = mk3(0, 0, 0);
     HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
-    u32 nv = 0, nt = 0, nc = 0;
+    u32 nv = 0, nt = 0, nc = 0, rayStart = 0, longest = 0;      // COUNT only: totals, and the longest single ray (the kernel's critical path)
 
     for (;;)
     {
@@ -207,6 +295,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
                     top = -1;
                     cur = tv.numLeaves ? tv.rootRef : REF_EMPTY;
                     active = true;
+                    if (COUNT) rayStart = nv + nt + nc;
                 }
             }
         }
@@ -245,20 +334,48 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
                 }
                 else cnt = __float_as_uint(r0.z);
             }
+            // few lanes with a leaf to test: let the whole warp work on them one after the other
+            unsigned pend = __ballot_sync(FULL, cnt > 0u);
+            if (pend && __popc(pend) <= COOP_MAX_LANES)
+            {
+                while (pend)
+                {
+                    int owner = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    coop_leaf<MODE, COUNT>(tv, lane, owner, o, d, ic, oi, first, cnt, cfirst, best, nt, nc);
+                }
+                cnt = 0;                                  // done: skip the per-lane path below
+            }
             u32 ncl = (cnt + CLUSTER - 1) / CLUSTER;
             bool big = ncl > 64u;                                          // > 256 faces in one leaf: no mask, test everything (rare)
             unsigned long long mask = (cnt && cnt <= (u32)CLUSTER) ? 1ull : 0ull;   // a single group: its box is the leaf box the parent tested
             u32 scan = (cnt > (u32)CLUSTER && !big) ? ncl : 0u;            // groups whose boxes this lane has to look at
             u32 maxScan = __reduce_max_sync(FULL, scan);
             {
+                // four boxes per trip with all eight loads issued before the first test: the tests are independent, so the L2
+                // latency is paid once per trip instead of once per box (the longest rays graze many populated leaves)
                 const float4* cp = tv.clusters + CLUSTER_F4 * (size_t)cfirst;
-                for (u32 i = 0; i < maxScan; i++, cp += CLUSTER_F4)
+                for (u32 i = 0; i < maxScan; i += 4, cp += 4 * CLUSTER_F4)
                 {
                     if (i < scan)
                     {
-                        float4 b0 = __ldg(cp), b1 = __ldg(cp + 1);
-                        if (COUNT) nc++;
-                        if (line_hits_box_fma(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), ic, oi)) mask |= 1ull << i;
+                        float4 b[8];
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            bool ok = i + k < scan;
+                            b[2 * k] = ok ? __ldg(cp + 2 * k) : make_float4(0, 0, 0, 0);
+                            b[2 * k + 1] = ok ? __ldg(cp + 2 * k + 1) : make_float4(0, 0, 0, 0);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            if (i + k < scan)
+                            {
+                                if (COUNT) nc++;
+                                if (line_hits_box_fma(mk3(b[2 * k].x, b[2 * k].y, b[2 * k].z), mk3(b[2 * k].w, b[2 * k + 1].x, b[2 * k + 1].y), ic, oi)) mask |= 1ull << (i + k);
+                            }
+                        }
                     }
                 }
             }
@@ -270,11 +387,15 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
                     mask &= mask - 1ull;
                     u32 i0 = g * CLUSTER, i1 = min(i0 + CLUSTER, cnt);
                     const float4* p = tv.ltris + 3 * (size_t)(first + i0);
-                    for (u32 i = i0; i < i1; i++, p += 3)
+                    // two faces per trip, their six loads issued together (same reasoning as the box scan)
+                    for (u32 i = i0; i < i1; i += 2, p += 6)
                     {
-                        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-                        if (COUNT) nt++;
-                        test_face<MODE>(a, b, c, o, d, best);
+                        bool two = i + 1 < i1;
+                        float4 a0 = __ldg(p), b0 = __ldg(p + 1), c0 = __ldg(p + 2);
+                        float4 a1 = two ? __ldg(p + 3) : a0, b1 = two ? __ldg(p + 4) : b0, c1 = two ? __ldg(p + 5) : c0;
+                        if (COUNT) nt += two ? 2 : 1;
+                        test_face<MODE>(a0, b0, c0, o, d, best);
+                        if (two) test_face<MODE>(a1, b1, c1, o, d, best);
                     }
                 }
             }
@@ -304,6 +425,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
             if (hits) { reinterpret_cast<float4*>(hits)[rayIdx] = make_float4(best.t, best.u, best.v, __uint_as_float(best.tri)); }
             if (pixels) pixels[rayIdx] = shade(best, meshData);
             active = false;
+            if (COUNT) longest = max(longest, nv + nt + nc - rayStart);
         }
     }
     if (COUNT)
@@ -316,6 +438,8 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bm
             atomicAdd((unsigned long long*)&counters[0], (unsigned long long)a); atomicAdd((unsigned long long*)&counters[1], (unsigned long long)b);
             atomicAdd((unsigned long long*)&counters[2], (unsigned long long)c);
         }
+        longest = __reduce_max_sync(FULL, longest);
+        if (lane == 0) atomicMax((unsigned long long*)&counters[3], (unsigned long long)longest);
     }
 }
 

@@ -108,7 +108,7 @@ class Tree:
         R = _dev_tensor(rays, torch.float32, self.device).reshape(-1, 6)
         n = R.shape[0] if num is None else int(num)
         hits = hits_out if hits_out is not None else torch.empty((n, 4), dtype=torch.float32, device=self.device)
-        cnt = torch.zeros(3, dtype=torch.int64, device=self.device) if counters else None
+        cnt = torch.zeros(4, dtype=torch.int64, device=self.device) if counters else None
         check(self.L.bmTraceRays(self.h, R.data_ptr(), n, int(mode), hits.data_ptr(), None if cnt is None else cnt.data_ptr()), "bmTraceRays")
         return (hits, cnt) if counters else hits
 
@@ -118,7 +118,7 @@ class Tree:
         e = (C.c_float * 3)(*[float(x) for x in eye])
         o = (C.c_float * 9)(*[float(x) for x in np.asarray(orient, np.float32).reshape(-1)])
         hits = torch.empty((n, 4), dtype=torch.float32, device=self.device) if want_hits else None
-        cnt = torch.zeros(3, dtype=torch.int64, device=self.device) if counters else None
+        cnt = torch.zeros(4, dtype=torch.int64, device=self.device) if counters else None
         check(self.L.bmTraceCamera(self.h, R.data_ptr(), n, int(width), e, o, int(mode), None if hits is None else hits.data_ptr(),
                                    None if pixels is None else pixels.data_ptr(), None if mesh_table is None else mesh_table.data_ptr(),
                                    None if cnt is None else cnt.data_ptr()), "bmTraceCamera")

@@ -26,10 +26,10 @@ hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
 L = _lib.load()
 out = {"triangles": st["triangles"], "pairs": st["pairs"], "leaves": st["leaves"], "build_ms": min(bms), "build_mtris_per_s": st["triangles"] / min(bms) / 1e3, "rays": n}
 for mode, name in ((0, "reference"), (1, "closest")):
-    cnt = torch.zeros(3, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
     _lib.check(L.bmTraceRays(t.h, R.data_ptr(), n, mode, hits.data_ptr(), cnt.data_ptr()), "trace")
     torch.cuda.synchronize()
-    V, K, Cc = [int(x) for x in cnt.cpu()]
+    V, K, Cc, LG = [int(x) for x in cnt.cpu()]
     ms = []
     for i in range(3):
         e0, e1 = ev(), ev(); torch.cuda.synchronize(); e0.record()
