@@ -243,7 +243,7 @@ __device__ __forceinline__ bool slot_to_ray(u32 slot, u64 n, u32 width, u32 heig
 // Keeping the two phases warp-synchronous is what lifts SIMT efficiency: in the first version (profiles/r1_a) only 11 of
 // 32 lanes were active on average because leaf loops and node walks of different lanes serialised each other.
 template <int MODE, bool CAMERA, bool COUNT>
-__global__ void __launch_bounds__(TR_THREADS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
+__global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
                                                            const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter)
 {
