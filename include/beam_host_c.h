@@ -32,6 +32,21 @@ uint32_t beamRenderTargetUnlock(void* rt);
 void*    beamRenderTargetBuffer(void* rt);                        /* device pointer while locked */
 uint32_t beamRenderTargetReadPixels(void* rt, uint32_t* hostPixels);
 int      beamDeviceSynchronize(void);
+
+/* Wavefront OBJ import (replaces TestProgram/Model.cpp + Assimp; rules in raytracercuda_b200/csrc/objload.cpp).  Pure host code. */
+void*           beamObjLoad(const char* path, int splitByMaterial);   /* never NULL; check beamObjError */
+const char*     beamObjError(void* obj);                              /* NULL when the file parsed */
+void            beamObjFree(void* obj);
+uint32_t        beamObjNumVertices(void* obj);
+uint32_t        beamObjNumMeshes(void* obj);                          /* 1, or one per usemtl group */
+int             beamObjHasNormals(void* obj);
+const float*    beamObjPositions(void* obj);                          /* numVertices * 3 */
+const float*    beamObjNormals(void* obj);                            /* numVertices * 3 or NULL */
+uint32_t        beamObjMeshNumIndices(void* obj, uint32_t mesh);
+const uint32_t* beamObjMeshIndices(void* obj, uint32_t mesh);
+const char*     beamObjMeshName(void* obj, uint32_t mesh);
+int             beamSceneLoadObj(void* scene, const char* path, int splitByMaterial);   /* Model::load: meshes added, or -1 */
+int             beamWritePPM(const char* path, const uint32_t* hostPixels, uint32_t width, uint32_t height);
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,8 @@ ABI_SYMBOLS = [
     "beamCameraTraceScene", "beamCameraTraceSceneHits",
     "beamRenderTargetCreateHeadless", "beamRenderTargetDestroy", "beamRenderTargetLock", "beamRenderTargetUnlock", "beamRenderTargetBuffer",
     "beamRenderTargetReadPixels", "beamDeviceSynchronize",
+    "beamObjLoad", "beamObjError", "beamObjFree", "beamObjNumVertices", "beamObjNumMeshes", "beamObjHasNormals", "beamObjPositions", "beamObjNormals",
+    "beamObjMeshNumIndices", "beamObjMeshIndices", "beamObjMeshName", "beamSceneLoadObj", "beamWritePPM",
 ]
 
 
@@ -110,6 +112,19 @@ def load() -> C.CDLL:
     L.beamRenderTargetLock.argtypes = [vp]; L.beamRenderTargetLock.restype = u32
     L.beamRenderTargetUnlock.argtypes = [vp]; L.beamRenderTargetUnlock.restype = u32
     L.beamRenderTargetReadPixels.argtypes = [vp, vp]; L.beamRenderTargetReadPixels.restype = u32
+    L.beamObjLoad.argtypes = [C.c_char_p, i32]; L.beamObjLoad.restype = vp
+    L.beamObjError.argtypes = [vp]; L.beamObjError.restype = C.c_char_p
+    L.beamObjFree.argtypes = [vp]; L.beamObjFree.restype = None
+    for n in ("beamObjNumVertices", "beamObjNumMeshes"):
+        getattr(L, n).argtypes = [vp]; getattr(L, n).restype = u32
+    L.beamObjHasNormals.argtypes = [vp]
+    L.beamObjPositions.argtypes = [vp]; L.beamObjPositions.restype = C.POINTER(C.c_float)
+    L.beamObjNormals.argtypes = [vp]; L.beamObjNormals.restype = C.POINTER(C.c_float)
+    L.beamObjMeshNumIndices.argtypes = [vp, u32]; L.beamObjMeshNumIndices.restype = u32
+    L.beamObjMeshIndices.argtypes = [vp, u32]; L.beamObjMeshIndices.restype = C.POINTER(u32)
+    L.beamObjMeshName.argtypes = [vp, u32]; L.beamObjMeshName.restype = C.c_char_p
+    L.beamSceneLoadObj.argtypes = [vp, C.c_char_p, i32]
+    L.beamWritePPM.argtypes = [C.c_char_p, vp, u32, u32]
     _lib = L
     return L
 

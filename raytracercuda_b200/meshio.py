@@ -105,3 +105,26 @@ def compute_vertex_normals(positions: np.ndarray, indices: np.ndarray) -> np.nda
     l = np.linalg.norm(N, axis=1, keepdims=True)
     N = np.where(l > 0, N / np.maximum(l, 1e-300), np.array([0.0, 0.0, 1.0]))
     return N.astype(np.float32)
+
+
+def load_obj_native(path: str, split_by_material: bool = False) -> list[TriMesh]:
+    """the library's own C++ loader (csrc/objload.cpp, beamObjLoad) -- same rules as load_obj above"""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    h = L.beamObjLoad(path.encode(), int(split_by_material))
+    try:
+        err = L.beamObjError(h)
+        if err:
+            raise _lib.BeamError(err.decode())
+        V = L.beamObjNumVertices(h)
+        P = np.ctypeslib.as_array(L.beamObjPositions(h), shape=(V, 3)).copy()
+        N = np.ctypeslib.as_array(L.beamObjNormals(h), shape=(V, 3)).copy() if L.beamObjHasNormals(h) else None
+        out = []
+        for m in range(L.beamObjNumMeshes(h)):
+            n = L.beamObjMeshNumIndices(h, m)
+            I = np.ctypeslib.as_array(L.beamObjMeshIndices(h, m), shape=(n,)).copy().reshape(-1, 3)
+            out.append(TriMesh(P, I, N, L.beamObjMeshName(h, m).decode()))
+        return out
+    finally:
+        L.beamObjFree(h)
