@@ -175,6 +175,15 @@ int  bmBounceRays(bmTree* tree, const bmRay* d_rays, const bmHit* d_hits, uint64
 int  bmBounceRaysCamera(bmTree* tree, const float* d_initialRays3, const float* eye3, const float* orient9, const bmHit* d_hits,
                         uint64_t numRays, uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count);
 
+/* Progressive accumulation over samples (defined by this repo; the reference's SceneProgressive is an empty stub): one sample of a
+ * pixel = `ambient` if its primary ray hit + (1 - ambient) if the diffuse bounce ray of that hit escaped.  d_accum (float) and
+ * d_covered (uint32) are per pixel and must start zeroed; d_hits2 / d_src2 / d_count2 are bmBounceRays' outputs after tracing (pass
+ * d_hits2 = NULL for primary only).  bmProgressiveResolve writes grey = accum / samples into the pixel's three colour bytes, and the
+ * reference's miss colour (255 << 8) where no sample ever hit. */
+int  bmProgressiveAccumulate(const bmHit* d_hits1, uint64_t numRays, const bmHit* d_hits2, const uint32_t* d_src2, const uint32_t* d_count2,
+                             float ambient, float* d_accum, uint32_t* d_covered, void* cudaStream);
+int  bmProgressiveResolve(const float* d_accum, const uint32_t* d_covered, uint64_t numRays, uint32_t samples, uint32_t* d_pixels, void* cudaStream);
+
 /* Spatial-hash key functions of Hash.cu:17-64 evaluated on the device (bit-exact targets):
  * out[i] = bmHash3(make_uint3(bmMap(x), bmMap(y), bmMap(z))) and the three bmMap cell coordinates. */
 int  bmHashKeys(const float* d_points3, uint64_t n, uint32_t* d_hash, int32_t* d_cells3, void* cudaStream);

@@ -77,5 +77,8 @@ namespace Beam
         virtual u32 traceScene(const float* eye3, const float* orient3x3, sptr<IScene>& scene) = 0;
         // same trace, additionally (or instead: no render target needed when hostHits only) hit records copied to the host
         virtual u32 traceSceneHits(const float* eye3, const float* orient3x3, sptr<IScene>& scene, bmHit* hostHits) = 0;
+        // what the reference's SceneProgressive (an empty stub, SceneProgressive.cpp:27-77) set out to do: `samples` jittered primary
+        // rays per pixel, one diffuse bounce ray per hit, accumulated and resolved into the locked render target
+        virtual u32 traceSceneProgressive(const float* eye3, const float* orient3x3, sptr<IScene>& scene, u32 samples, u32 seed, u64* raysTraced = nullptr) = 0;
     };
 }

@@ -25,6 +25,8 @@ uint32_t beamCameraCopyInitialRays(void* camera, float* host3);   /* the directi
 uint32_t beamCameraClear(void* camera, uint32_t value);
 uint32_t beamCameraTraceScene(void* camera, const float* eye3, const float* orient3x3, void* scene);
 uint32_t beamCameraTraceSceneHits(void* camera, const float* eye3, const float* orient3x3, void* scene, bmHit* hostHits);
+uint32_t beamCameraTraceSceneProgressive(void* camera, const float* eye3, const float* orient3x3, void* scene, uint32_t samples, uint32_t seed,
+                                         uint64_t* raysTraced /* nullable */);
 void*    beamRenderTargetCreateHeadless(uint32_t width, uint32_t height, uint32_t pitch);
 void     beamRenderTargetDestroy(void* rt);
 uint32_t beamRenderTargetLock(void* rt);

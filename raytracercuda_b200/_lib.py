@@ -20,12 +20,12 @@ ABI_SYMBOLS = [
     "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
     "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport",
-    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect",
+    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
     "beamMeshCreate", "beamMeshDestroy", "beamMeshSetVertexData", "beamMeshSetIndices",
     "beamCameraCreate", "beamCameraDestroy", "beamCameraSetInitialRays", "beamCameraCopyInitialRays", "beamCameraClear",
-    "beamCameraTraceScene", "beamCameraTraceSceneHits",
+    "beamCameraTraceScene", "beamCameraTraceSceneHits", "beamCameraTraceSceneProgressive",
     "beamRenderTargetCreateHeadless", "beamRenderTargetDestroy", "beamRenderTargetLock", "beamRenderTargetUnlock", "beamRenderTargetBuffer",
     "beamRenderTargetReadPixels", "beamDeviceSynchronize",
     "beamObjLoad", "beamObjError", "beamObjFree", "beamObjNumVertices", "beamObjNumMeshes", "beamObjHasNormals", "beamObjPositions", "beamObjNormals",
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     L.bmBounceRays.argtypes = [vp, vp, vp, u64, u32, u32, u32, vp, vp, vp]
     L.bmBounceRaysCamera.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, u64, u32, u32, u32, vp, vp, vp]
     L.bmTraceRaysIndirect.argtypes = [vp, vp, vp, u64, i32, vp, vp]
+    L.bmProgressiveAccumulate.argtypes = [vp, u64, vp, vp, vp, C.c_float, vp, vp, vp]
+    L.bmProgressiveResolve.argtypes = [vp, vp, u64, u32, vp, vp]
     L.bmResetScene.argtypes = [vp] * 7 + [u32] * 3; L.bmResetScene.restype = None
     L.bmInsertMeshInTree.argtypes = [vp, vp, u32, u32, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, vp, vp, vp]; L.bmInsertMeshInTree.restype = None
     L.bmMarch.argtypes = [vp, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, u32, u32, u32, C.POINTER(bmVec3), C.POINTER(bmMat3), vp]
@@ -108,6 +110,7 @@ def load() -> C.CDLL:
     L.beamCameraClear.argtypes = [vp, u32]; L.beamCameraClear.restype = u32
     L.beamCameraTraceScene.argtypes = [vp, vp, vp, vp]; L.beamCameraTraceScene.restype = u32
     L.beamCameraTraceSceneHits.argtypes = [vp, vp, vp, vp, vp]; L.beamCameraTraceSceneHits.restype = u32
+    L.beamCameraTraceSceneProgressive.argtypes = [vp, vp, vp, vp, u32, u32, C.POINTER(u64)]; L.beamCameraTraceSceneProgressive.restype = u32
     L.beamRenderTargetCreateHeadless.argtypes = [u32, u32, u32]; L.beamRenderTargetCreateHeadless.restype = vp
     L.beamRenderTargetLock.argtypes = [vp]; L.beamRenderTargetLock.restype = u32
     L.beamRenderTargetUnlock.argtypes = [vp]; L.beamRenderTargetUnlock.restype = u32

@@ -174,6 +174,37 @@ public:
         hits.copyTo(hostHits, true);
         return ERROR_ALL_FINE;
     }
+    // progressive frame (see ICamera::traceSceneProgressive): every sample = jittered camera rays -> trace -> bounce rays -> trace -> accumulate
+    u32 marchProgressive(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh, float jx, float jy, u32 samples,
+                         u32 seed, u64* raysTraced)
+    {
+        IRenderTarget* rt = RenderTarget::get();
+        if (!rt) return ERROR_NO_RENDER_TARGET;
+        if (rt->width() != raysWide || rt->height() != raysHigh) return ERROR_RT_CAM_MISMATCH;
+        if (samples == 0) return ERROR_INVALID_PARAMETER;
+        size_t n = (size_t)raysWide * raysHigh;
+        bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
+        if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); if (raysTraced) *raysTraced = 0; return ERROR_ALL_FINE; }
+        DeviceBuffer r1(n * sizeof(bmRay)), h1(n * sizeof(bmHit)), r2(n * sizeof(bmRay)), h2(n * sizeof(bmHit)), src(n * 4), cnt(4), acc(n * 4), cov(n * 4);
+        if (!r1.ok() || !h1.ok() || !r2.ok() || !h2.ok() || !src.ok() || !cnt.ok() || !acc.ok() || !cov.ok()) return ERROR_GPU_ALLOC_FAIL;
+        cudaMemset(acc.ptr<void>(), 0, n * 4); cudaMemset(cov.ptr<void>(), 0, n * 4);
+        u64 total = 0;
+        for (u32 s = 0; s < samples; s++)
+        {
+            int r = bmCameraRays(rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, s, seed, r1.ptr<bmRay>(), nullptr);
+            if (!r) r = bmTraceRays(t, r1.ptr<bmRay>(), n, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr);
+            if (!r) r = bmBounceRays(t, r1.ptr<bmRay>(), h1.ptr<bmHit>(), n, s, 1, seed, r2.ptr<bmRay>(), src.ptr<u32>(), cnt.ptr<u32>());
+            if (!r) r = bmTraceRaysIndirect(t, r2.ptr<bmRay>(), cnt.ptr<u32>(), n, BM_TRACE_REFERENCE, h2.ptr<bmHit>(), nullptr);
+            if (!r) r = bmProgressiveAccumulate(h1.ptr<bmHit>(), n, h2.ptr<bmHit>(), src.ptr<u32>(), cnt.ptr<u32>(), 0.25f, acc.ptr<float>(), cov.ptr<u32>(), nullptr);
+            if (r) return (u32)r;
+            if (raysTraced) { u32 c = 0; cnt.copyTo(&c, true); total += n + c; }
+        }
+        int r = bmProgressiveResolve(acc.ptr<float>(), cov.ptr<u32>(), n, samples, rt->buffer<u32>(), nullptr);
+        if (r) return (u32)r;
+        cudaDeviceSynchronize();                   // the scratch buffers above die with this scope
+        if (raysTraced) *raysTraced = total;
+        return ERROR_ALL_FINE;
+    }
     void* rootKey() const { return m_root->ptr<void>(); }
 private:
     bmVec3 m_min, m_max;
@@ -191,6 +222,7 @@ public:
     {
         if (width == 0 || height == 0) return ERROR_INVALID_PARAMETER;
         m_width = width; m_height = height;
+        m_pixelW = fabsf((right - left) / width) / zoom; m_pixelH = fabsf((bottom - top) / height) / zoom;     // pixel size in units of zoom (jitter range)
         std::vector<float> tab((size_t)width * height * 3);
         float dx = (right - left) / width;
         float dy = (bottom - top) / height;
@@ -229,9 +261,15 @@ public:
         if (!eye3 || !orient3x3 || !scene || m_width == 0 || m_height == 0 || !m_rays || !hostHits) return ERROR_INVALID_PARAMETER;
         return static_cast<Scene*>(scene.get())->marchHits(eye3, orient3x3, m_rays, m_width, m_height, hostHits);
     }
+    u32 traceSceneProgressive(const float* eye3, const float* orient3x3, sptr<IScene>& scene, u32 samples, u32 seed, u64* raysTraced) override
+    {
+        if (!eye3 || !orient3x3 || !scene || m_width == 0 || m_height == 0 || !m_rays) return ERROR_INVALID_PARAMETER;
+        return static_cast<Scene*>(scene.get())->marchProgressive(eye3, orient3x3, m_rays, m_width, m_height, m_pixelW, m_pixelH, samples, seed, raysTraced);
+    }
     u32 copyInitialRays(float* host) const { if (!m_rays) return ERROR_INVALID_PARAMETER; m_rays->copyTo(host, true); return ERROR_ALL_FINE; }
 private:
     u32 m_width = 0, m_height = 0;
+    float m_pixelW = 0.f, m_pixelH = 0.f;
     sptr<DeviceBuffer> m_rays;
 };
 sptr<ICamera> ICamera::create() { return std::make_shared<Camera>(); }
@@ -260,6 +298,8 @@ uint32_t beamCameraCopyInitialRays(void* c, float* host) { return static_cast<Ca
 uint32_t beamCameraClear(void* c, uint32_t value) { return (*(sptr<ICamera>*)c)->clear(value); }
 uint32_t beamCameraTraceScene(void* c, const float* eye3, const float* orient9, void* s) { return (*(sptr<ICamera>*)c)->traceScene(eye3, orient9, *(sptr<IScene>*)s); }
 uint32_t beamCameraTraceSceneHits(void* c, const float* eye3, const float* orient9, void* s, bmHit* hostHits) { return (*(sptr<ICamera>*)c)->traceSceneHits(eye3, orient9, *(sptr<IScene>*)s, hostHits); }
+uint32_t beamCameraTraceSceneProgressive(void* c, const float* eye3, const float* orient9, void* s, uint32_t samples, uint32_t seed, uint64_t* raysTraced)
+{ return (*(sptr<ICamera>*)c)->traceSceneProgressive(eye3, orient9, *(sptr<IScene>*)s, samples, seed, raysTraced); }
 void* beamRenderTargetCreateHeadless(uint32_t w, uint32_t h, uint32_t pitch) { auto rt = IRenderTarget::createHeadless(w, h, pitch); return rt ? new sptr<IRenderTarget>(rt) : nullptr; }
 void  beamRenderTargetDestroy(void* r) { delete (sptr<IRenderTarget>*)r; }
 uint32_t beamRenderTargetLock(void* r) { return (*(sptr<IRenderTarget>*)r)->lock(); }

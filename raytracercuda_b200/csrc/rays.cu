@@ -97,7 +97,55 @@ __global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, cons
     out[k] = o;
     if (srcIndex) srcIndex[k] = (u32)i;
 }
+// ---- progressive accumulation (the estimator this repo defines for the multi-sample configs; the reference's SceneProgressive is an
+// empty stub, SceneProgressive.cpp:27-77).  One sample of a pixel = ambient if the primary ray hit, plus (1 - ambient) if the diffuse
+// bounce ray of that hit escaped (cosine-weighted ambient occlusion); pixels whose primary rays never hit keep the reference's miss
+// colour.  accum is one float per pixel, summed over samples; resolve divides by the sample count and packs grey into the red, green
+// and blue bytes. ----------------------------------------------------------------------------------------------------------------
+__global__ void accumulate_primary_kernel(const bmHit* __restrict__ hits, u64 n, float ambient, float* __restrict__ accum, u32* __restrict__ covered)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (hits[i].tri != 0xFFFFFFFFu) { accum[i] += ambient; covered[i] = 1u; }
+}
+__global__ void accumulate_bounce_kernel(const bmHit* __restrict__ hits2, const u32* __restrict__ src, const u32* __restrict__ count, float weight,
+                                         float* __restrict__ accum)
+{
+    u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *count) return;
+    if (hits2[k].tri == 0xFFFFFFFFu) accum[src[k]] += weight;       // src is injective (one bounce ray per primary hit): no atomics needed
+}
+__global__ void resolve_kernel(const float* __restrict__ accum, const u32* __restrict__ covered, u64 n, float invSamples, u32* __restrict__ pixels)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!covered[i]) { pixels[i] = 255u << 8; return; }
+    float v = fminf(fmaxf(accum[i] * invSamples, 0.f), 1.f);
+    u32 g = (u32)(v * 255.f);
+    pixels[i] = (g << 16) | (g << 8) | g;
+}
 } // namespace
+
+int progressive_accumulate(const bmHit* d_hits1, u64 n, const bmHit* d_hits2, const u32* d_src2, const u32* d_count2, float ambient, float* d_accum,
+                           u32* d_covered, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    accumulate_primary_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits1, n, ambient, d_accum, d_covered);
+    BM_LAUNCHED();
+    if (d_hits2)
+    {
+        accumulate_bounce_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits2, d_src2, d_count2, 1.f - ambient, d_accum);
+        BM_LAUNCHED();
+    }
+    return BM_OK;
+}
+int progressive_resolve(const float* d_accum, const u32* d_covered, u64 n, u32 samples, u32* d_pixels, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    resolve_kernel<<<div_up(n, 256), 256, 0, s>>>(d_accum, d_covered, n, 1.f / (float)(samples ? samples : 1), d_pixels);
+    BM_LAUNCHED();
+    return BM_OK;
+}
 
 int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* d_out, cudaStream_t s)
 {

@@ -391,6 +391,20 @@ extern "C" int bmBounceRaysCamera(bmTree* t, const float* d_initialRays3, const 
     return bounce_rays(nullptr, &cam, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
 }
 
+extern "C" int bmProgressiveAccumulate(const bmHit* d_hits1, uint64_t numRays, const bmHit* d_hits2, const uint32_t* d_src2, const uint32_t* d_count2,
+                                       float ambient, float* d_accum, uint32_t* d_covered, void* stream)
+{
+    if ((!d_hits1 || !d_accum || !d_covered) && numRays) return BM_ERROR_INVALID_PARAMETER;
+    if (d_hits2 && (!d_src2 || !d_count2)) return BM_ERROR_INVALID_PARAMETER;
+    return progressive_accumulate(d_hits1, numRays, d_hits2, d_src2, d_count2, ambient, d_accum, d_covered, (cudaStream_t)stream);
+}
+
+extern "C" int bmProgressiveResolve(const float* d_accum, const uint32_t* d_covered, uint64_t numRays, uint32_t samples, uint32_t* d_pixels, void* stream)
+{
+    if ((!d_accum || !d_covered || !d_pixels) && numRays) return BM_ERROR_INVALID_PARAMETER;
+    return progressive_resolve(d_accum, d_covered, numRays, samples, d_pixels, (cudaStream_t)stream);
+}
+
 extern "C" int bmHashKeys(const float* d_points3, uint64_t n, uint32_t* d_hash, int32_t* d_cells3, void* stream)
 {
     if (!d_points3 && n) return BM_ERROR_INVALID_PARAMETER;

@@ -134,6 +134,13 @@ class ICamera:
         err = self.L.beamCameraTraceSceneHits(self.h, e.ctypes.data, o.ctypes.data, scene.h, hits.ctypes.data)
         return err, hits
 
+    def traceSceneProgressive(self, eye3, orient3x3, scene: IScene, samples: int, seed: int = 0):
+        import ctypes as C
+        e = self._f(eye3, 3); o = self._f(orient3x3, 9)
+        rays = C.c_uint64(0)
+        err = self.L.beamCameraTraceSceneProgressive(self.h, e.ctypes.data, o.ctypes.data, scene.h, int(samples), int(seed), C.byref(rays))
+        return err, int(rays.value)
+
     def __del__(self):
         if getattr(self, "h", None):
             self.L.beamCameraDestroy(self.h); self.h = None

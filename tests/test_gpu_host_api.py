@@ -134,3 +134,75 @@ def test_hash_keys_on_device(golden, beam_lib, cuda_device):
     assert beam_lib.bmHashKeys(pts.data_ptr(), xs.shape[0], None, c.data_ptr(), None) == 0
     torch.cuda.synchronize()
     assert list(c.cpu().numpy()[:, 0]) == [w for _, w in golden["hash"]["bmMap"]]
+
+
+def test_progressive_frame(oracle_lib, beam_lib, cuda_device):
+    """ICamera::traceSceneProgressive (what SceneProgressive.cpp set out to be): N jittered samples per pixel, one diffuse bounce per
+    hit, accumulated and resolved.  Checked three ways: every traced batch against the oracle on the SAME ray buffer, the accumulation
+    against numpy, and the host-class frame against the same steps issued through the C ABI."""
+    import ctypes as C
+    import torch
+    from oracle.bindings import OracleScene
+    from raytracercuda_b200 import host as H, synth, workloads
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    wl = workloads.get("c2small")
+    W, Hh = 160, 96
+    n = W * Hh
+    SPP, SEED = 3, 11
+    # host-class path
+    scene = H.IScene.create(); m = H.IMesh.create()
+    assert m.setIndices(wl.indices, wl.indices.size) == 0 and m.setVertexData(wl.positions, wl.positions.shape[0], 3, 0) == 0
+    assert m.setVertexData(wl.normals, wl.normals.shape[0], 3, 1) == 0
+    scene.addMesh(m); scene.updateGPUScene()
+    cam = H.ICamera.create(); assert cam.setInitialRays(W, Hh, -1, 1, -1, 1, 1) == 0
+    rt = H.IRenderTarget.createHeadless(W, Hh); assert rt.lock() == 0
+    assert cam.traceSceneProgressive(synth.EYE, synth.IDENTITY, scene, 0)[0] == H.ERROR_INVALID_PARAMETER
+    err, rays_traced = cam.traceSceneProgressive(synth.EYE, synth.IDENTITY, scene, SPP, SEED)
+    assert err == 0
+    frame = rt.readPixels().reshape(-1)
+    # the same steps through the C ABI, with the oracle looking at every batch
+    t = Tree(cuda_device); t.add_mesh(wl.positions, wl.indices); t.build()
+    s = OracleScene(oracle_lib); s.add_mesh(wl.positions, wl.indices, wl.normals); s.build()
+    table = torch.from_numpy(cam.initialRays()).to(cuda_device)
+    acc = torch.zeros(n, dtype=torch.float32, device=cuda_device); cov = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    acc_np = np.zeros(n, np.float32); cov_np = np.zeros(n, bool)
+    jx, jy = 2.0 / W, 2.0 / Hh
+    total = 0
+    prev = None
+    for sidx in range(SPP):
+        r1 = t.camera_rays(table, synth.EYE, synth.IDENTITY, width=W, jitter=(jx, jy), sample=sidx, seed=SEED)
+        R1 = r1.cpu().numpy()
+        if prev is not None:
+            assert np.abs(R1[:, 3:] - prev[:, 3:]).max() > 1e-5                      # samples differ ...
+        prev = R1
+        centre = cam.initialRays()
+        ang = np.arccos(np.clip((R1[:, 3:] * centre).sum(1), -1, 1))
+        assert ang.max() < 1.5 * np.hypot(jx, jy) and np.abs(np.linalg.norm(R1[:, 3:], axis=1) - 1).max() < 1e-5     # ... but stay inside their pixel
+        h1 = t.trace_rays(r1, 0)
+        a = hits_to_numpy(h1); o1 = s.trace_rays(R1[:, :3], R1[:, 3:], 0, 4)
+        ok = o1["tie"] == 0
+        assert (a["tri"][ok] == o1["tri"][ok]).mean() >= 0.9999
+        r2, src, cnt = t.bounce_rays(r1, h1, sample=sidx, bounce=1, seed=SEED)
+        nb = int(cnt.cpu()[0])
+        h2 = torch.empty((n, 4), dtype=torch.float32, device=cuda_device)
+        assert beam_lib.bmTraceRaysIndirect(t.h, r2.data_ptr(), cnt.data_ptr(), n, 0, h2.data_ptr(), None) == 0
+        b = hits_to_numpy(h2[:nb]); R2 = r2[:nb].cpu().numpy(); o2 = s.trace_rays(R2[:, :3], R2[:, 3:], 0, 4)
+        ok2 = o2["tie"] == 0
+        assert (b["tri"][ok2] == o2["tri"][ok2]).mean() >= 0.9999
+        assert beam_lib.bmProgressiveAccumulate(h1.data_ptr(), n, h2.data_ptr(), src.data_ptr(), cnt.data_ptr(), 0.25, acc.data_ptr(), cov.data_ptr(), None) == 0
+        hit = a["tri"] != 0xFFFFFFFF
+        acc_np[hit] += np.float32(0.25); cov_np |= hit
+        esc = src.cpu().numpy()[:nb][b["tri"] == 0xFFFFFFFF]
+        acc_np[esc] += np.float32(0.75)
+        total += n + nb
+    px = torch.empty(n, dtype=torch.int32, device=cuda_device)
+    assert beam_lib.bmProgressiveResolve(acc.data_ptr(), cov.data_ptr(), n, SPP, px.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    got = px.cpu().numpy().view(np.uint32)
+    g = (np.clip(acc_np * np.float32(1.0 / SPP), 0, 1) * np.float32(255)).astype(np.uint32)
+    want = np.where(cov_np, (g << 16) | (g << 8) | g, np.uint32(255 << 8)).astype(np.uint32)
+    assert np.array_equal(got, want)
+    assert np.array_equal(frame, got) and rays_traced == total
+    assert cov_np.sum() > 1000 and 0 < (acc_np[cov_np] > 0.3 * SPP).mean() < 1
+    assert rt.unlock() == 0
+    t.close(); s.close()
