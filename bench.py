@@ -162,8 +162,35 @@ def run_b200(args):
     cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    SPP = wl.samples
+    jit = (abs(wl.frustum[1] - wl.frustum[0]) / W / wl.frustum[4], abs(frustum[3] - frustum[2]) / H / wl.frustum[4])
+    acc = torch.zeros(n, dtype=torch.float32, device=dev) if SPP > 1 else None
+    cov = torch.zeros(n, dtype=torch.int32, device=dev) if SPP > 1 else None
+    cnt_sum = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def frame_spp(rays_in):
+        """multi-sample frame (configs 3 and 4): per sample jittered camera rays -> trace -> bounce rays -> trace -> accumulate; resolve"""
+        acc.zero_(); cov.zero_(); cnt_sum.zero_()
+        sp = C.c_void_p(stream.cuda_stream)
+        for sidx in range(SPP):
+            _lib.check(L.bmCameraRays(rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), jit[0], jit[1], sidx, args.seed, rays1.data_ptr(), sp), "bmCameraRays")
+            _lib.check(L.bmTraceRays(tree.h, rays1.data_ptr(), n, 0, hits1.data_ptr(), None), "bmTraceRays")
+            _lib.check(L.bmBounceRays(tree.h, rays1.data_ptr(), hits1.data_ptr(), n, sidx, 1, args.seed, rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRays")
+            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, 0, hits2.data_ptr(), None), "bmTraceRaysIndirect")
+            _lib.check(L.bmProgressiveAccumulate(hits1.data_ptr(), n, hits2.data_ptr(), src2.data_ptr(), cnt2.data_ptr(), 0.25, acc.data_ptr(), cov.data_ptr(), sp), "accumulate")
+            cnt_sum.add_(cnt2)
+        _lib.check(L.bmProgressiveResolve(acc.data_ptr(), cov.data_ptr(), n, SPP, pixels.data_ptr(), sp), "resolve")
+        cnt_host.copy_(cnt_sum.to(torch.int32), non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), pixels)
+        return n * SPP
+
     def frame(rays_in, marks=None):
-        """one step on the device; returns rays traced by this rank"""
+        """one step on the device; returns rays traced by this rank (bounce rays are added by bounce_count())"""
+        if SPP > 1:
+            if marks is not None:
+                for m_ in marks: m_.record()
+            return frame_spp(rays_in)
         if marks is not None: marks[0].record()
         _lib.check(L.bmTraceCamera(tree.h, rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
         if marks is not None: marks[1].record()
@@ -241,7 +268,7 @@ def run_b200(args):
     # Every step: the camera table comes from pinned host memory, the framebuffer and the bounce hit records go back to pinned host
     # memory.  The frame is cut into row bands; band k+1 is uploaded and band k-1 downloaded (copy streams) while band k is traced
     # (compute stream), so the copies hide behind the kernels instead of adding to them.
-    BANDS = args.e2e_bands if H % args.e2e_bands == 0 else 1
+    BANDS = args.e2e_bands if (H % args.e2e_bands == 0 and SPP == 1) else 1
     nbnd = n // BANDS
     s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     cntb = torch.zeros(BANDS, dtype=torch.int32, device=dev); cntb_host = torch.zeros(BANDS, dtype=torch.int32).pin_memory()
@@ -275,6 +302,8 @@ def run_b200(args):
     # of 4 bands x ~10 launches); the bounce hit records are read back after the replay, sized by the counts the graph produced
     graph = None
     try:
+        if SPP > 1:
+            raise RuntimeError("multi-sample frame: direct launches")
         enqueue_bands(stream); stream.synchronize()                 # warm-up outside capture (allocations, occupancy queries)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -288,6 +317,12 @@ def run_b200(args):
         tree.use_stream(stream)
 
     def frame_e2e():
+        if SPP > 1:
+            e2e_rays_dev.copy_(rays_pinned, non_blocking=True)
+            total = frame_spp(e2e_rays_dev)
+            pix_host.copy_(pixels, non_blocking=True)
+            stream.synchronize()
+            return total + int(cnt_host[0])
         if graph is not None:
             graph.replay()
         else:
@@ -319,7 +354,7 @@ def run_b200(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
     e2e_value = float(r2.item()) / (float(t2.item()) * 1e-3) / 1e6
     h2d = n * 12 + 48
-    d2h = n * 4 + (nb * 16 if wl.bounces else 0) + (4 * BANDS if wl.bounces else 0)
+    d2h = n * 4 + ((nb * 16 if wl.bounces else 0) + (4 * BANDS if wl.bounces else 0) if SPP == 1 else 4)
 
     # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
     build_ms = []
@@ -364,6 +399,14 @@ def run_b200(args):
 
     # --- roofline of the dominant kernel: the primary-ray trace launch ---------------------------------------------------
     pms = statistics.mean(prim_ms)
+    if SPP > 1:
+        # multi-sample frames interleave many launches: time the dominant kernel (one camera launch of the frame's rays) on its own
+        tt = []
+        for _ in range(5):
+            flush.zero_(); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
+            _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, None), "bmTraceCamera")
+            e1.record(); torch.cuda.synchronize(dev); tt.append(e0.elapsed_time(e1))
+        pms = statistics.mean(tt)
     prim_bytes = n * (12 + 16 + 4) + NODE_BYTES * V1 + TRI_BYTES * K1 + CLUSTER_BYTES * C1
     roofline = {"bound": "hbm", "kernel": "trace_kernel<camera> (bmTraceCamera, reference semantics)", "achieved": prim_bytes / (pms * 1e-3) / 1e9,
                 "peak": peak, "unit": "GB/s", "frac": prim_bytes / (pms * 1e-3) / 1e9 / peak, "traffic": None,
@@ -372,7 +415,7 @@ def run_b200(args):
                 "note": "algorithmic bytes = 12 B ray + 16 B hit + 4 B pixel + 96 B x node/leaf visits + 32 B x cluster boxes + 48 B x triangle tests (counters of the same traversal); "
                         + peak_src + "; the tree (~%.0f MB) is L2-resident on B200, so this kernel is latency/issue-bound, not HBM-bound (SURVEY 8d)" %
                         ((st["nodes"] * 128 + st["pairs"] * 56 + st["leaves"] * 48) / 1e6)}
-    if wl.bounces and nb:
+    if wl.bounces and nb and SPP == 1:
         bms2 = statistics.mean(bounce_ms)
         roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb / (bms2 * 1e-3) / 1e6, "rays": nb,
                                      "node_visits_per_ray": V2 / nb, "tri_tests_per_ray": K2 / nb, "cluster_boxes_per_ray": C2 / nb,
@@ -380,7 +423,7 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "rays_per_step_per_gpu": rays_step, "primary_rays_per_gpu": n, "bounce_rays_per_gpu": nb,
+            "config": {"workload": wl.name, "rays_per_step_per_gpu": rays_step, "primary_rays_per_gpu": n * SPP, "bounce_rays_per_gpu": nb, "samples_per_pixel": SPP,
                        "trace_mode": "reference semantics (BM_TRACE_REFERENCE)", "l2": "flushed between timed steps (256 MiB write)",
                        "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer" if world > 1 else "single GPU",
                        "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
@@ -499,7 +542,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-bands", type=int, default=4)
+    ap.add_argument("--e2e-bands", type=int, default=1, help="row bands of the pipelined e2e frame (1 measured fastest: a trace launch has a ~0.25 ms critical path regardless of size)")
     ap.add_argument("--reference-rays", type=int, default=200_000, help="primary rays per step of the --impl reference sample")
     args = ap.parse_args()
     if args.impl == "reference":

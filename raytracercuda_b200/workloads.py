@@ -25,6 +25,7 @@ class Workload:
     bounces: int               # diffuse bounce generations traced after the primary rays
     eye: tuple = synth.EYE
     frustum: tuple = synth.FRUSTUM
+    samples: int = 1           # jittered samples per pixel (1 = the exact pixel-centre table, as the reference traces it)
 
     @property
     def num_tris(self):
@@ -47,9 +48,14 @@ def get(name: str) -> Workload:
     if name == "c2small":        # same scene class at a size the CPU test tier can afford
         P, I, N = synth.displaced_icosphere(4, seed=1)
         return Workload("c2small: displaced icosphere 5,120 tris, 320x180 primary + 1 bounce", "test", P, I, N, 320, 180, 1)
+    if name == "c3":
+        P, I, N = _bundled("f16")
+        return Workload("c3: Content/f16.obj (4,056 tris; the reference never reads the F16 textures) 64 spp jittered primary + 1 diffuse bounce at 1920x1080",
+                        "configs[2]", P, I, N, 1920, 1080, 1, samples=64)
     if name == "c4":
         P, I, N = synth.displaced_icosphere(9, seed=2)
-        return Workload("c4: tyra STAND-IN (displaced icosphere, 5,242,880 tris, seed 2) 3840x2160", "configs[3]", P, I, N, 3840, 2160, 0)
+        return Workload("c4: tyra STAND-IN (displaced icosphere, 5,242,880 tris, seed 2; Content/tyra.obj is a missing blob) 3840x2160 16 spp jittered primary + 1 diffuse bounce",
+                        "configs[3]", P, I, N, 3840, 2160, 1, samples=16)
     raise ValueError(name)
 
 
