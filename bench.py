@@ -231,9 +231,10 @@ def run_b200(args):
     V1, K1, C1, LONG1 = [int(x) for x in cnt.cpu()]
     nb = int(cnt_host[0]) if wl.bounces else 0
     V2 = K2 = C2 = 0
-    if nb:
+    nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST sample only
+    if nb_last and SPP == 1:
         cnt.zero_()
-        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, 0, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
         torch.cuda.synchronize(dev)
         V2, K2, C2, LONG2 = [int(x) for x in cnt.cpu()]
 

@@ -71,9 +71,10 @@ int gather_mesh(const float* d_pos, const u32* d_idx, u32 numTris, u32 meshIdx, 
 int count_pairs(const Grid& g, const float4* d_soup, u32 numTris, u32* d_counts, cudaStream_t s);
 int emit_pairs(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, u64* d_keys, u32* d_vals, cudaStream_t s);
 // flat path: classify = candidate ranges + per-candidate test into a bit mask (one SAT pass), emit = decode the masks
-int classify_pairs(const Grid& g, const float4* d_soup, u32 numTris, float margin, u32* d_counts, u64* d_masks, u64* d_infos, cudaStream_t s);
-int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, const u64* d_masks, const u64* d_infos, u64* d_keys, u32* d_vals,
-                    cudaStream_t s);
+int classify_pairs(const Grid& g, const float4* d_soup, u32 numTris, float margin, u32* d_counts, u64* d_masks, u64* d_infos, u32* d_largeList,
+                   u32* d_largeCount, cudaStream_t s);
+int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, const u64* d_masks, const u64* d_infos, const u32* d_largeList,
+                    const u32* d_largeCount, u64* d_keys, u32* d_vals, cudaStream_t s);
 
 // ---- hierarchy.cu ---------------------------------------------------------------------------------------------------
 int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s);
@@ -82,7 +83,7 @@ int write_leaves(const Grid& g, const u64* d_keys, const u32* d_flags, const u32
 int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_ltris, cudaStream_t s);
 // cluster boxes + leaf boxes + leaf statistics + the 256-cap exclusion flags; d_clusterFirst = exclusive scan of the cluster counts
 int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* d_leafIdx, size_t numPairs, const u32* d_clusterFirst, float4* d_ltris,
-                float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, cudaStream_t s);
+                float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, u32* d_overList, cudaStream_t s);
 int emit_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s);
 int refit(u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit, float4* d_nodes, cudaStream_t s);
 int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, u64* d_out, cudaStream_t s);

@@ -87,7 +87,7 @@ __global__ void cluster_bounds_kernel(const float4* __restrict__ leaves, const u
 // Per leaf: tight box = union of its cluster boxes, first-cluster index into the record, leaf-size statistics (stats[0] = max leaf
 // size, stats[1] = leaves above 256 faces) and the reference's face cap.
 __global__ void leaf_bounds_kernel(float4* __restrict__ leaves, u32 numLeaves, const u32* __restrict__ clusterFirst, float4* __restrict__ ltris,
-                                   const float4* __restrict__ clusters, float4* __restrict__ box2, u32* stats)
+                                   const float4* __restrict__ clusters, float4* __restrict__ box2, u32* stats, u32* __restrict__ overList)
 {
     u32 l = blockIdx.x * blockDim.x + threadIdx.x;
     float4 r0 = l < numLeaves ? leaves[LEAF_F4 * (size_t)l] : make_float4(0, 0, 0, 0);
@@ -113,13 +113,33 @@ __global__ void leaf_bounds_kernel(float4* __restrict__ leaves, u32 numLeaves, c
     }
     box2[2 * (size_t)l] = make_float4(lo[0], lo[1], lo[2], hi[0]);
     box2[2 * (size_t)l + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
-    // face cap: the reference keeps the first 256 faces inserted into a leaf = the 256 smallest (mesh, triangle) ids; mark the rest
-    if (cnt > 256u)
+    // face cap: leaves above 256 faces are queued for cap_flags_kernel
+    if (cnt > 256u) overList[atomicAdd(&stats[2], 1u)] = l;
+}
+
+// The reference keeps the first 256 faces inserted into a leaf (BuildTree.cu:53-60) = the 256 smallest (mesh, triangle) ids in its
+// serial mode; faces beyond that are never tested.  One block per queued leaf: rank of every face id among the leaf's ids, faces of rank
+// >= 256 get the EXCLUDED bit.  (O(n^2 / 256) per thread; such leaves only exist for meshes far denser than the reference can hold.)
+constexpr int CAP_THREADS = 256;
+constexpr u32 CAP_SMEM_IDS = 8192;
+__global__ void __launch_bounds__(CAP_THREADS) cap_flags_kernel(const float4* __restrict__ leaves, const u32* __restrict__ overList, const u32* stats,
+                                                                float4* __restrict__ ltris)
+{
+    __shared__ u32 ids[CAP_SMEM_IDS];
+    const u32 nOver = stats[2];
+    for (u32 item = blockIdx.x; item < nOver; item += gridDim.x)
     {
-        for (u32 i = 0; i < cnt; i++)
+        float4 r0 = leaves[LEAF_F4 * (size_t)overList[item]];
+        u32 first = __float_as_uint(r0.y), cnt = __float_as_uint(r0.z);
+        u32 inSmem = min(cnt, CAP_SMEM_IDS);
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < inSmem; i += CAP_THREADS) ids[i] = __float_as_uint(ltris[3 * (size_t)(first + i)].w);
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < cnt; i += CAP_THREADS)
         {
-            u32 ti = __float_as_uint(ltris[3 * (size_t)(first + i)].w), rank = 0;
-            for (u32 j = 0; j < cnt; j++) rank += __float_as_uint(ltris[3 * (size_t)(first + j)].w) < ti ? 1u : 0u;
+            u32 ti = i < inSmem ? ids[i] : __float_as_uint(ltris[3 * (size_t)(first + i)].w), rank = 0;
+            for (u32 j = 0; j < inSmem && rank < 256u; j++) rank += ids[j] < ti ? 1u : 0u;
+            for (u32 j = inSmem; j < cnt && rank < 256u; j++) rank += __float_as_uint(ltris[3 * (size_t)(first + j)].w) < ti ? 1u : 0u;
             if (rank >= 256u)
             {
                 float4* p = ltris + 3 * (size_t)(first + i) + 1;
@@ -250,12 +270,14 @@ int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_
     return BM_OK;
 }
 int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* d_leafIdx, size_t numPairs, const u32* d_clusterFirst, float4* d_ltris,
-                float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, cudaStream_t s)
+                float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, u32* d_overList, cudaStream_t s)
 {
     if (!numLeaves) return BM_OK;
     cluster_bounds_kernel<<<div_up(numPairs, 256), 256, 0, s>>>(d_leaves, d_flags, d_leafIdx, d_clusterFirst, numPairs, d_ltris, d_clusters, pad);
     BM_LAUNCHED();
-    leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_clusterFirst, d_ltris, d_clusters, d_leafBox2, d_stats);
+    leaf_bounds_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(d_leaves, numLeaves, d_clusterFirst, d_ltris, d_clusters, d_leafBox2, d_stats, d_overList);
+    BM_LAUNCHED();
+    cap_flags_kernel<<<(unsigned)sm_count() * 4, CAP_THREADS, 0, s>>>(d_leaves, d_overList, d_stats, d_ltris);     // exits at once when nothing is queued
     BM_LAUNCHED();
     return BM_OK;
 }

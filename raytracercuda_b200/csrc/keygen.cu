@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(KG_THREADS) emit_kernel(Grid g, const float4* 
 // that the emit pass needs no geometry test at all; more than 64 -> counted by the descent.
 // info = ix0 | iy0 << 11 | iz0 << 22 | nx << 33 | ny << 40 | large << 63
 __global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, float margin,
-                                                              u32* __restrict__ counts, u64* __restrict__ masks, u64* __restrict__ infos)
+                                                              u32* __restrict__ counts, u64* __restrict__ masks, u64* __restrict__ infos,
+                                                              u32* __restrict__ largeList, u32* largeCount)
 {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numTris) return;
@@ -99,8 +100,9 @@ __global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const floa
     u64 nx = (u64)(hi[0] - lo[0] + 1), ny = (u64)(hi[1] - lo[1] + 1), nz = (u64)(hi[2] - lo[2] + 1);
     if (nx * ny * nz > 64ull)
     {
-        counts[t] = descend_triangle(g, va, vb, vc, NoEmit());
-        masks[t] = 0; infos[t] = 1ull << 63;
+        // large triangle: handed to the warp-cooperative descent (large_kernel), which fills counts[t]
+        counts[t] = 0; masks[t] = 0; infos[t] = 1ull << 63;
+        largeList[atomicAdd(largeCount, 1u)] = t;
         return;
     }
     TriSat ts; trisat_init(ts, va, vb, vc);
@@ -121,18 +123,13 @@ __global__ void __launch_bounds__(KG_THREADS) emit_flat_kernel(Grid g, const flo
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numTris) return;
     u64 info = infos[t], mask = masks[t];
-    if (!mask && !(info >> 63)) return;
+    if (!mask) return;
     const float4* p = soup + 3 * (size_t)t;
     float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     V3 tmin = mk3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
     V3 tmax = mk3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
     u32 pos = offsets[t];
-    if (info >> 63)
-    {
-        WriteEmit w = { keys, vals, pos, t, &g, tmin, tmax };
-        descend_triangle<WriteEmit&>(g, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), w);
-        return;
-    }
+    if (info >> 63) return;                    // large triangle: emitted by large_kernel<true>
     u32 x0 = (u32)info & 0x7FFu, y0 = (u32)(info >> 11) & 0x7FFu, z0 = (u32)(info >> 22) & 0x7FFu, nx = (u32)(info >> 33) & 0x7Fu, ny = (u32)(info >> 40) & 0x7Fu;
     // the descent emits a triangle's codes in no particular order and the sort is keyed on (code, sub-key), so any order works here
     while (mask)
@@ -143,6 +140,94 @@ __global__ void __launch_bounds__(KG_THREADS) emit_flat_kernel(Grid g, const flo
         keys[pos] = ((u64)encode_path(g.D, ix, iy, iz) << SUB_BITS) | sub_key(g, ix, iy, iz, tmin, tmax);
         vals[pos] = t;
         ++pos;
+    }
+}
+// ---- large triangles: warp-cooperative reference descent -----------------------------------------------------------------------------
+// A triangle with more than 64 candidate cells (wings of f16, ground planes ...) would keep one thread busy for thousands of cells.
+// Here a warp takes one such triangle: the frontier of kd nodes lives in a per-warp shared-memory stack, every iteration pops up to 32
+// nodes, each lane evaluates the reference's test on the two children of its node (same expressions as descend_triangle: exact by
+// construction), surviving children are pushed with a ballot-prefix, children at leaf depth are counted (pass 1) or written (pass 2).
+constexpr int WD_WARPS = 4;
+constexpr int WD_CAP = 1280;      // entries per warp; the LIFO frontier stays below 32 * (D + 1) + 64
+
+template <bool EMIT>
+__global__ void __launch_bounds__(WD_WARPS * 32) large_kernel(Grid g, const float4* __restrict__ soup, const u32* __restrict__ largeList,
+                                                              const u32* __restrict__ largeCount, u32* __restrict__ counts, const u32* __restrict__ offsets,
+                                                              u64* __restrict__ keys, u32* __restrict__ vals)
+{
+    __shared__ u64 stk[WD_WARPS][WD_CAP];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 nLarge = *largeCount;
+    const u32 totalWarps = gridDim.x * WD_WARPS;
+    u64* st = stk[w];
+    for (u32 item = blockIdx.x * WD_WARPS + w; item < nLarge; item += totalWarps)
+    {
+        u32 t = largeList[item];
+        const float4* p = soup + 3 * (size_t)t;
+        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        V3 va = mk3(a.x, a.y, a.z), vb = mk3(b.x, b.y, b.z), vc = mk3(c.x, c.y, c.z);
+        V3 tmin = mk3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+        V3 tmax = mk3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+        int lo[3], hi[3];
+        axis_range(g.tab[0], g.k[0], tmin.x, tmax.x, lo[0], hi[0]);
+        axis_range(g.tab[1], g.k[1], tmin.y, tmax.y, lo[1], hi[1]);
+        axis_range(g.tab[2], g.k[2], tmin.z, tmax.z, lo[2], hi[2]);
+        TriSat ts; trisat_init(ts, va, vb, vc);
+        __syncwarp();
+        if (lane == 0) st[0] = 0;                 // root: depth 0, cell (0,0,0)
+        __syncwarp();
+        int top = 1;
+        u32 total = 0, outPos = EMIT ? offsets[t] : 0u;
+        while (top > 0)
+        {
+            int k = min(32, min(top, WD_CAP - top));
+            u64 e = (int)lane < k ? st[top - 1 - lane] : 0ull;
+            top -= k;
+            __syncwarp();
+            bool have = (int)lane < k;
+            u32 d = (u32)(e >> 33), ix = (u32)(e >> 22) & 0x7FFu, iy = (u32)(e >> 11) & 0x7FFu, iz = (u32)e & 0x7FFu;
+            int ax = d % 3;
+            u32 nd = d + 1;
+#pragma unroll
+            for (int side = 0; side < 2; side++)
+            {
+                u32 cx = ix, cy = iy, cz = iz;
+                if (ax == 0) cx = (ix << 1) | side; else if (ax == 1) cy = (iy << 1) | side; else cz = (iz << 1) | side;
+                bool pass = have;
+                if (pass)
+                {
+                    int shx = g.k[0] - axis_bits(nd, 0), shy = g.k[1] - axis_bits(nd, 1), shz = g.k[2] - axis_bits(nd, 2);
+                    if ((int)(((cx + 1) << shx) - 1) < lo[0] || (int)(cx << shx) > hi[0]) pass = false;
+                    else if ((int)(((cy + 1) << shy) - 1) < lo[1] || (int)(cy << shy) > hi[1]) pass = false;
+                    else if ((int)(((cz + 1) << shz) - 1) < lo[2] || (int)(cz << shz) > hi[2]) pass = false;
+                }
+                if (pass)
+                {
+                    V3 mn, mx; cell_box(g, nd, cx, cy, cz, mn, mx);
+                    float bc[3] = { (mx.x + mn.x) * .5f, (mx.y + mn.y) * .5f, (mx.z + mn.z) * .5f };      // BuildTree.cu:221-225
+                    float hs[3] = { (mx.x - mn.x) * .5f, (mx.y - mn.y) * .5f, (mx.z - mn.z) * .5f };
+                    pass = sat_box(ts, bc, hs) != 0;
+                }
+                bool leaf = (int)nd == g.D;              // warp-uniform only per lane's node depth: handle both kinds with two ballots
+                unsigned leafBits = __ballot_sync(FULL, pass && leaf);
+                unsigned pushBits = __ballot_sync(FULL, pass && !leaf);
+                if (pass && leaf)
+                {
+                    if (EMIT)
+                    {
+                        u32 pos = outPos + __popc(leafBits & ((1u << lane) - 1u));
+                        keys[pos] = ((u64)encode_path(g.D, cx, cy, cz) << SUB_BITS) | sub_key(g, cx, cy, cz, tmin, tmax);
+                        vals[pos] = t;
+                    }
+                }
+                outPos += __popc(leafBits); total += __popc(leafBits);
+                if (pass && !leaf) st[top + __popc(pushBits & ((1u << lane) - 1u))] = ((u64)nd << 33) | ((u64)cx << 22) | ((u64)cy << 11) | (u64)cz;
+                top += __popc(pushBits);
+            }
+            __syncwarp();
+        }
+        if (!EMIT && lane == 0) counts[t] = total;
     }
 }
 } // namespace
@@ -161,18 +246,25 @@ int count_pairs(const Grid& g, const float4* d_soup, u32 numTris, u32* d_counts,
     BM_LAUNCHED();
     return BM_OK;
 }
-int classify_pairs(const Grid& g, const float4* d_soup, u32 numTris, float margin, u32* d_counts, u64* d_masks, u64* d_infos, cudaStream_t s)
+int classify_pairs(const Grid& g, const float4* d_soup, u32 numTris, float margin, u32* d_counts, u64* d_masks, u64* d_infos, u32* d_largeList,
+                   u32* d_largeCount, cudaStream_t s)
 {
     if (!numTris) return BM_OK;
-    classify_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, margin, d_counts, d_masks, d_infos);
+    BM_CUDA(cudaMemsetAsync(d_largeCount, 0, 4, s));
+    classify_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, margin, d_counts, d_masks, d_infos, d_largeList, d_largeCount);
+    BM_LAUNCHED();
+    // large triangles (their number stays on the device: the grid is fixed, warps loop over the list)
+    large_kernel<false><<<(unsigned)sm_count() * 2, WD_WARPS * 32, 0, s>>>(g, d_soup, d_largeList, d_largeCount, d_counts, nullptr, nullptr, nullptr);
     BM_LAUNCHED();
     return BM_OK;
 }
-int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, const u64* d_masks, const u64* d_infos, u64* d_keys, u32* d_vals,
-                    cudaStream_t s)
+int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32* d_offsets, const u64* d_masks, const u64* d_infos, const u32* d_largeList,
+                    const u32* d_largeCount, u64* d_keys, u32* d_vals, cudaStream_t s)
 {
     if (!numTris) return BM_OK;
     emit_flat_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, d_offsets, d_masks, d_infos, d_keys, d_vals);
+    BM_LAUNCHED();
+    large_kernel<true><<<(unsigned)sm_count() * 2, WD_WARPS * 32, 0, s>>>(g, d_soup, d_largeList, d_largeCount, nullptr, d_offsets, d_keys, d_vals);
     BM_LAUNCHED();
     return BM_OK;
 }

@@ -347,68 +347,60 @@ __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const
                 cnt = 0;                                  // done: skip the per-lane path below
             }
             u32 ncl = (cnt + CLUSTER - 1) / CLUSTER;
-            bool big = ncl > 64u;                                          // > 256 faces in one leaf: no mask, test everything (rare)
-            unsigned long long mask = (cnt && cnt <= (u32)CLUSTER) ? 1ull : 0ull;   // a single group: its box is the leaf box the parent tested
-            u32 scan = (cnt > (u32)CLUSTER && !big) ? ncl : 0u;            // groups whose boxes this lane has to look at
-            u32 maxScan = __reduce_max_sync(FULL, scan);
+            u32 maxNcl = __reduce_max_sync(FULL, ncl);
+            // 64 groups per round (one bit each); leaves above 256 faces simply take several rounds
+            for (u32 cb = 0; cb < maxNcl; cb += 64)
             {
-                // four boxes per trip with all eight loads issued before the first test: the tests are independent, so the L2
-                // latency is paid once per trip instead of once per box (the longest rays graze many populated leaves)
-                const float4* cp = tv.clusters + CLUSTER_F4 * (size_t)cfirst;
-                for (u32 i = 0; i < maxScan; i += 4, cp += 4 * CLUSTER_F4)
+                u32 here = ncl > cb ? min(ncl - cb, 64u) : 0u;                        // groups of this lane in this round
+                unsigned long long mask = (here == 1u && ncl == 1u) ? 1ull : 0ull;    // a single group: its box is the leaf box the parent tested
+                u32 scan = (ncl > 1u) ? here : 0u;                                    // groups whose boxes this lane has to look at
+                u32 maxScan = __reduce_max_sync(FULL, scan);
                 {
-                    if (i < scan)
+                    // four boxes per trip with all eight loads issued before the first test: the tests are independent, so the L2
+                    // latency is paid once per trip instead of once per box (the longest rays graze many populated leaves)
+                    const float4* cp = tv.clusters + CLUSTER_F4 * (size_t)(cfirst + cb);
+                    for (u32 i = 0; i < maxScan; i += 4, cp += 4 * CLUSTER_F4)
                     {
-                        float4 b[8];
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
+                        if (i < scan)
                         {
-                            bool ok = i + k < scan;
-                            b[2 * k] = ok ? __ldg(cp + 2 * k) : make_float4(0, 0, 0, 0);
-                            b[2 * k + 1] = ok ? __ldg(cp + 2 * k + 1) : make_float4(0, 0, 0, 0);
-                        }
+                            float4 b[8];
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                        {
-                            if (i + k < scan)
+                            for (int k = 0; k < 4; k++)
                             {
-                                if (COUNT) nc++;
-                                if (line_hits_box_fma(mk3(b[2 * k].x, b[2 * k].y, b[2 * k].z), mk3(b[2 * k].w, b[2 * k + 1].x, b[2 * k + 1].y), ic, oi)) mask |= 1ull << (i + k);
+                                bool ok = i + k < scan;
+                                b[2 * k] = ok ? __ldg(cp + 2 * k) : make_float4(0, 0, 0, 0);
+                                b[2 * k + 1] = ok ? __ldg(cp + 2 * k + 1) : make_float4(0, 0, 0, 0);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                            {
+                                if (i + k < scan)
+                                {
+                                    if (COUNT) nc++;
+                                    if (line_hits_box_fma(mk3(b[2 * k].x, b[2 * k].y, b[2 * k].z), mk3(b[2 * k].w, b[2 * k + 1].x, b[2 * k + 1].y), ic, oi)) mask |= 1ull << (i + k);
+                                }
                             }
                         }
                     }
                 }
-            }
-            while (__any_sync(FULL, mask != 0ull))
-            {
-                if (mask)
+                while (__any_sync(FULL, mask != 0ull))
                 {
-                    u32 g = (u32)__ffsll((long long)mask) - 1u;
-                    mask &= mask - 1ull;
-                    u32 i0 = g * CLUSTER, i1 = min(i0 + CLUSTER, cnt);
-                    const float4* p = tv.ltris + 3 * (size_t)(first + i0);
-                    // two faces per trip, their six loads issued together (same reasoning as the box scan)
-                    for (u32 i = i0; i < i1; i += 2, p += 6)
+                    if (mask)
                     {
-                        bool two = i + 1 < i1;
-                        float4 a0 = __ldg(p), b0 = __ldg(p + 1), c0 = __ldg(p + 2);
-                        float4 a1 = two ? __ldg(p + 3) : a0, b1 = two ? __ldg(p + 4) : b0, c1 = two ? __ldg(p + 5) : c0;
-                        if (COUNT) nt += two ? 2 : 1;
-                        test_face<MODE>(a0, b0, c0, o, d, best);
-                        if (two) test_face<MODE>(a1, b1, c1, o, d, best);
-                    }
-                }
-            }
-            if (__any_sync(FULL, big))
-            {
-                if (big)
-                {
-                    const float4* p = tv.ltris + 3 * (size_t)first;
-                    for (u32 i = 0; i < cnt; i++, p += 3)
-                    {
-                        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-                        if (COUNT) nt++;
-                        test_face<MODE>(a, b, c, o, d, best);
+                        u32 g = cb + (u32)__ffsll((long long)mask) - 1u;
+                        mask &= mask - 1ull;
+                        u32 i0 = g * CLUSTER, i1 = min(i0 + CLUSTER, cnt);
+                        const float4* p = tv.ltris + 3 * (size_t)(first + i0);
+                        // two faces per trip, their six loads issued together (same reasoning as the box scan)
+                        for (u32 i = i0; i < i1; i += 2, p += 6)
+                        {
+                            bool two = i + 1 < i1;
+                            float4 a0 = __ldg(p), b0 = __ldg(p + 1), c0 = __ldg(p + 2);
+                            float4 a1 = two ? __ldg(p + 3) : a0, b1 = two ? __ldg(p + 4) : b0, c1 = two ? __ldg(p + 5) : c0;
+                            if (COUNT) nt += two ? 2 : 1;
+                            test_face<MODE>(a0, b0, c0, o, d, best);
+                            if (two) test_face<MODE>(a1, b1, c1, o, d, best);
+                        }
                     }
                 }
             }

@@ -62,7 +62,7 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false, imported = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList;
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
     u32 maxLeaf = 0, overLeaves = 0;
@@ -77,7 +77,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -109,8 +109,9 @@ static int tree_build(bmTree* t)
     const bool flat = !(kg && strcmp(kg, "descent") == 0);          // BM_KEYGEN=descent: per-triangle reference descent only (cross-check)
     if (flat)
     {
-        BM_TRY(t->masks.reserve(T * 8)); BM_TRY(t->infos.reserve(T * 8));
-        BM_TRY(classify_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, ext * (1.f / 524288.f), t->counts.as<u32>(), t->masks.as<u64>(), t->infos.as<u64>(), s));
+        BM_TRY(t->masks.reserve(T * 8)); BM_TRY(t->infos.reserve(T * 8)); BM_TRY(t->largeList.reserve(T * 4 + 4));
+        BM_TRY(classify_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, ext * (1.f / 524288.f), t->counts.as<u32>(), t->masks.as<u64>(), t->infos.as<u64>(),
+                              t->largeList.as<u32>(), t->scalars.as<u32>() + 10, s));
     }
     else BM_TRY(count_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), s));
     u32* d_scal = t->scalars.as<u32>();
@@ -123,7 +124,8 @@ static int tree_build(bmTree* t)
     // 3. emit + sort: key = leaf code (D bits) | in-cell sub-key (SUB_BITS), payload = triangle id
     BM_TRY(t->keysA.reserve(P * 8)); BM_TRY(t->valsA.reserve(P * 4)); BM_TRY(t->keysB.reserve(P * 8)); BM_TRY(t->valsB.reserve(P * 4));
     BM_TRY(t->temp.reserve(sort_temp_bytes(P) > scan_temp_bytes(P) ? sort_temp_bytes(P) : scan_temp_bytes(P)));
-    if (flat) BM_TRY(emit_pairs_flat(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->masks.as<u64>(), t->infos.as<u64>(), t->keysA.as<u64>(), t->valsA.as<u32>(), s));
+    if (flat) BM_TRY(emit_pairs_flat(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->masks.as<u64>(), t->infos.as<u64>(), t->largeList.as<u32>(),
+                                      t->scalars.as<u32>() + 10, t->keysA.as<u64>(), t->valsA.as<u32>(), s));
     else BM_TRY(emit_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->keysA.as<u64>(), t->valsA.as<u32>(), s));
     int inB = 0;
     BM_TRY(radix_sort_pairs64(t->keysA.as<u64>(), t->valsA.as<u32>(), t->keysB.as<u64>(), t->valsB.as<u32>(), P, t->hgrid.D + SUB_BITS, t->temp.p, s, &inB));
@@ -144,10 +146,10 @@ static int tree_build(bmTree* t)
     BM_TRY(write_leaves(t->dgrid, t->sortedKeys, t->flags.as<u32>(), leafIdx, P, (u32)L, t->leaves.as<float4>(), t->clusterCounts.as<u32>(), t->codes.as<u32>(), s));
     BM_TRY(exclusive_scan_u32(t->clusterCounts.as<u32>(), t->clusterCounts.as<u32>(), L, nullptr, t->temp.p, s));
     BM_TRY(t->clusters.reserve((P / CLUSTER + L + 1) * 16 * CLUSTER_F4));
-    BM_TRY(t->leafBox.reserve(L * 32));
+    BM_TRY(t->leafBox.reserve(L * 32)); BM_TRY(t->parentL.reserve(L * 4 + 4));
     float pad = ext * (1.f / 1048576.f);
     BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->flags.as<u32>(), leafIdx, P, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(),
-                       t->leafBox.as<float4>(), pad, d_scal + 2, s));
+                       t->leafBox.as<float4>(), pad, d_scal + 2, t->parentL.as<u32>(), s));     // parentL doubles as the overflow-leaf queue until emit_hierarchy fills it
     // 5. hierarchy + refit
     if (L >= 2)
     {

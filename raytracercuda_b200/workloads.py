@@ -52,6 +52,9 @@ def get(name: str) -> Workload:
         P, I, N = _bundled("f16")
         return Workload("c3: Content/f16.obj (4,056 tris; the reference never reads the F16 textures) 64 spp jittered primary + 1 diffuse bounce at 1920x1080",
                         "configs[2]", P, I, N, 1920, 1080, 1, samples=64)
+    if name == "c3small":
+        P, I, N = _bundled("f16")
+        return Workload("c3small: f16, 4 spp + 1 bounce at 320x180", "test", P, I, N, 320, 180, 1, samples=4)
     if name == "c4":
         P, I, N = synth.displaced_icosphere(9, seed=2)
         return Workload("c4: tyra STAND-IN (displaced icosphere, 5,242,880 tris, seed 2; Content/tyra.obj is a missing blob) 3840x2160 16 spp jittered primary + 1 diffuse bounce",
