@@ -12,7 +12,16 @@ struct HostGrid
     float minLeaf; uint32_t maxDepth;
     int k[3]; int D;
     std::vector<float> tab[3];
+    int uniform; float w[3];
 };
+
+// fills the device-facing Grid from a HostGrid (table pointers supplied by the caller)
+inline void fill_grid(Grid& g, const HostGrid& h, const float* t0, const float* t1, const float* t2)
+{
+    g.tab[0] = t0; g.tab[1] = t1; g.tab[2] = t2;
+    for (int a = 0; a < 3; a++) { g.k[a] = h.k[a]; g.wmin[a] = h.wmin[a]; g.w[a] = h.w[a]; }
+    g.D = h.D; g.uniform = h.uniform;
+}
 
 // Replays the reference's subdivision rule on the world box (BuildTree.cu:196-216): at depth d the node is a leaf when
 // min(edge) < minLeaf or d == maxDepth-1, else it is halved on axis d%3 at s = .5f*(min+max).  All nodes of one depth must
@@ -51,6 +60,19 @@ inline bool build_host_grid(HostGrid& g, const float wmin[3], const float wmax[3
         nt.back() = g.tab[a].back();
         g.tab[a].swap(nt);
         g.k[a]++;
+    }
+    // closed form available?  every boundary must equal wmin + i*w exactly (two separately rounded operations, as the kernels compute it)
+    g.uniform = 1;
+    for (int a = 0; a < 3; a++)
+    {
+        size_t n = g.tab[a].size() - 1;
+        g.w[a] = g.tab[a][1] - g.tab[a][0];
+        for (size_t i = 0; i <= n; i++)
+        {
+            volatile float prod = (float)i * g.w[a];
+            volatile float v = prod + g.wmin[a];
+            if (v != g.tab[a][i]) { g.uniform = 0; break; }
+        }
     }
     return g.D >= 1 && g.D <= 32 && g.k[0] <= 11 && g.k[1] <= 11 && g.k[2] <= 11;
 }

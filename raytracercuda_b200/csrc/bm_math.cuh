@@ -99,6 +99,10 @@ struct Grid
     const float* tab[3];
     int k[3];       // bits per axis at leaf depth
     int D;          // leaf depth = k[0]+k[1]+k[2] <= 32
+    // When every table entry equals wmin + i*w bit for bit (true for the reference's +-30 world: all boundaries are exact floats),
+    // `uniform` is set and boundaries are computed instead of loaded (checked entry by entry on the host, bm_grid_host.h).
+    int uniform;
+    float wmin[3], w[3];
 };
 
 BM_HD int axis_bits(int depth, int axis) { return (depth + 2 - axis) / 3; }   // splits on `axis` among depths 0..depth-1
@@ -147,12 +151,15 @@ BM_HD void decode_path(int depth, u32 p, u32& ix, u32& iy, u32& iz)
 #define BM_LDG(p) (*(p))
 #endif
 
+// boundary i (leaf resolution) of axis a
+BM_HD float grid_at(const Grid& g, int a, u32 i) { return g.uniform ? (float)i * g.w[a] + g.wmin[a] : BM_LDG(g.tab[a] + i); }
+
 // Box of the depth-`depth` cell (ix,iy,iz)
 BM_HD void cell_box(const Grid& g, int depth, u32 ix, u32 iy, u32 iz, V3& mn, V3& mx)
 {
     int sx = g.k[0] - axis_bits(depth, 0), sy = g.k[1] - axis_bits(depth, 1), sz = g.k[2] - axis_bits(depth, 2);
-    mn.x = BM_LDG(g.tab[0] + (ix << sx)); mx.x = BM_LDG(g.tab[0] + ((ix + 1) << sx));
-    mn.y = BM_LDG(g.tab[1] + (iy << sy)); mx.y = BM_LDG(g.tab[1] + ((iy + 1) << sy));
-    mn.z = BM_LDG(g.tab[2] + (iz << sz)); mx.z = BM_LDG(g.tab[2] + ((iz + 1) << sz));
+    mn.x = grid_at(g, 0, ix << sx); mx.x = grid_at(g, 0, (ix + 1) << sx);
+    mn.y = grid_at(g, 1, iy << sy); mx.y = grid_at(g, 1, (iy + 1) << sy);
+    mn.z = grid_at(g, 2, iz << sz); mx.z = grid_at(g, 2, (iz + 1) << sz);
 }
 } // namespace bm

@@ -72,10 +72,10 @@ BM_HD int sat_box(const TriSat& t, const float bc[3], const float hs[3])
 // triangle spanning [vmin,vmax] on that axis.  fl(v - c) is monotone in v and in c, so the passing cells form one
 // interval; it is found from a float estimate and corrected with the exact test expressions.  Cells outside it can
 // never be in the reference's leaf set for this triangle, which makes it a safe pruning bound for the descent.
-BM_HD void axis_range(const float* tab, int k, float vmin, float vmax, int& lo, int& hi)
+BM_HD void axis_range(const Grid& g, int ax, float vmin, float vmax, int& lo, int& hi)
 {
-    const int n = 1 << k;
-    float w0 = BM_LDG(tab), w1 = BM_LDG(tab + n);
+    const int n = 1 << g.k[ax];
+    float w0 = grid_at(g, ax, 0), w1 = grid_at(g, ax, n);
     float inv = (float)n / (w1 - w0);
     // lower end: smallest i with !(fl(vmin - c_i) > h_i)
     float f = (vmin - w0) * inv;
@@ -84,7 +84,7 @@ BM_HD void axis_range(const float* tab, int k, float vmin, float vmax, int& lo, 
     {
         if (i > 0)
         {
-            float a = BM_LDG(tab + i - 1), b = BM_LDG(tab + i);
+            float a = grid_at(g, ax, i - 1), b = grid_at(g, ax, i);
             float c = (b + a) * .5f, h = (b - a) * .5f;
             if (!(vmin - c > h)) { --i; continue; }
         }
@@ -94,7 +94,7 @@ BM_HD void axis_range(const float* tab, int k, float vmin, float vmax, int& lo, 
     {
         if (i < n)
         {
-            float a = BM_LDG(tab + i), b = BM_LDG(tab + i + 1);
+            float a = grid_at(g, ax, i), b = grid_at(g, ax, i + 1);
             float c = (b + a) * .5f, h = (b - a) * .5f;
             if (vmin - c > h) { ++i; continue; }
         }
@@ -108,7 +108,7 @@ BM_HD void axis_range(const float* tab, int k, float vmin, float vmax, int& lo, 
     {
         if (i < n - 1)
         {
-            float a = BM_LDG(tab + i + 1), b = BM_LDG(tab + i + 2);
+            float a = grid_at(g, ax, i + 1), b = grid_at(g, ax, i + 2);
             float c = (b + a) * .5f, h = (b - a) * .5f;
             if (!(vmax - c < -h)) { ++i; continue; }
         }
@@ -118,7 +118,7 @@ BM_HD void axis_range(const float* tab, int k, float vmin, float vmax, int& lo, 
     {
         if (i >= 0)
         {
-            float a = BM_LDG(tab + i), b = BM_LDG(tab + i + 1);
+            float a = grid_at(g, ax, i), b = grid_at(g, ax, i + 1);
             float c = (b + a) * .5f, h = (b - a) * .5f;
             if (vmax - c < -h) { --i; continue; }
         }
@@ -169,9 +169,9 @@ BM_HD u32 descend_triangle(const Grid& g, V3 a, V3 b, V3 c, Emit emit)
 {
     TriSat t; trisat_init(t, a, b, c);
     int lo[3], hi[3];
-    axis_range(g.tab[0], g.k[0], fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
-    axis_range(g.tab[1], g.k[1], fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
-    axis_range(g.tab[2], g.k[2], fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
+    axis_range(g, 0, fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
+    axis_range(g, 1, fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
+    axis_range(g, 2, fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
     if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) return 0;
 
     // explicit stack of packed (depth:6 | ix:11 | iy:11 | iz:11); a pop replaces one node by at most two deeper ones,

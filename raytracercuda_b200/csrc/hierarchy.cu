@@ -196,7 +196,7 @@ __global__ void karras_kernel(Grid g, const u32* __restrict__ leaves, u32 numLea
     int axis = plen % 3;
     u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
     int sh = g.k[axis] - axis_bits(plen, axis);      // >= 1: the node splits on this axis
-    float sp = BM_LDG(g.tab[axis] + (((ia << 1) | 1u) << (sh - 1)));
+    float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
     o[4] = make_float4(mn.x, mn.y, mn.z, sp);
     o[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
 }

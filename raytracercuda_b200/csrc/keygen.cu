@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const floa
     float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     V3 va = mk3(a.x, a.y, a.z), vb = mk3(b.x, b.y, b.z), vc = mk3(c.x, c.y, c.z);
     int lo[3], hi[3];
-    axis_range(g.tab[0], g.k[0], fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
-    axis_range(g.tab[1], g.k[1], fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
-    axis_range(g.tab[2], g.k[2], fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
+    axis_range(g, 0, fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
+    axis_range(g, 1, fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
+    axis_range(g, 2, fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
     if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) { counts[t] = 0; masks[t] = 0; infos[t] = 0; return; }
     u64 nx = (u64)(hi[0] - lo[0] + 1), ny = (u64)(hi[1] - lo[1] + 1), nz = (u64)(hi[2] - lo[2] + 1);
     if (nx * ny * nz > 64ull)
@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(WD_WARPS * 32) large_kernel(Grid g, const floa
         V3 tmin = mk3(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
         V3 tmax = mk3(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
         int lo[3], hi[3];
-        axis_range(g.tab[0], g.k[0], tmin.x, tmax.x, lo[0], hi[0]);
-        axis_range(g.tab[1], g.k[1], tmin.y, tmax.y, lo[1], hi[1]);
-        axis_range(g.tab[2], g.k[2], tmin.z, tmax.z, lo[2], hi[2]);
+        axis_range(g, 0, tmin.x, tmax.x, lo[0], hi[0]);
+        axis_range(g, 1, tmin.y, tmax.y, lo[1], hi[1]);
+        axis_range(g, 2, tmin.z, tmax.z, lo[2], hi[2]);
         TriSat ts; trisat_init(ts, va, vb, vc);
         __syncwarp();
         if (lane == 0) st[0] = 0;                 // root: depth 0, cell (0,0,0)

@@ -202,9 +202,7 @@ extern "C" int bmTreeCreate(bmTree** out, const float* worldMin3, const float* w
     if (e == cudaSuccess) e = cudaMemcpy(d + n0, t->hgrid.tab[1].data(), n1 * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + n0 + n1, t->hgrid.tab[2].data(), n2 * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error(std::string("table upload: ") + cudaGetErrorString(e)); delete t; return BM_ERROR_CUDA; }
-    t->dgrid.tab[0] = d; t->dgrid.tab[1] = d + n0; t->dgrid.tab[2] = d + n0 + n1;
-    for (int a = 0; a < 3; a++) t->dgrid.k[a] = t->hgrid.k[a];
-    t->dgrid.D = t->hgrid.D;
+    fill_grid(t->dgrid, t->hgrid, d, d + n0, d + n0 + n1);
     *out = t;
     return BM_OK;
 }

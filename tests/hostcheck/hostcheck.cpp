@@ -1,6 +1,7 @@
 // Test-only: compiles the product's host+device inline arithmetic (csrc/bm_math.cuh, bm_sat.cuh) for the CPU so that the
 // no-GPU test tier can check the very same source against the oracle.  Never shipped, never used by the product.
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include "../../raytracercuda_b200/csrc/bm_sat.cuh"
@@ -17,7 +18,8 @@ uint64_t hc_pairs(const float* pos, const uint32_t* idx, uint32_t numTris, const
 {
     HostGrid hg;
     if (!build_host_grid(hg, wmin, wmax, minLeaf, maxDepth)) return ~0ull;
-    Grid g; for (int a = 0; a < 3; a++) { g.tab[a] = hg.tab[a].data(); g.k[a] = hg.k[a]; } g.D = hg.D;
+    Grid g; fill_grid(g, hg, hg.tab[0].data(), hg.tab[1].data(), hg.tab[2].data());
+    if (getenv("HC_NO_UNIFORM")) g.uniform = 0;
     if (D) *D = hg.D;
     std::vector<uint64_t> out;
     for (uint32_t t = 0; t < numTris; t++)
@@ -37,7 +39,8 @@ uint64_t hc_pairs_flat(const float* pos, const uint32_t* idx, uint32_t numTris, 
 {
     HostGrid hg;
     if (!build_host_grid(hg, wmin, wmax, minLeaf, maxDepth)) return ~0ull;
-    Grid g; for (int a = 0; a < 3; a++) { g.tab[a] = hg.tab[a].data(); g.k[a] = hg.k[a]; } g.D = hg.D;
+    Grid g; fill_grid(g, hg, hg.tab[0].data(), hg.tab[1].data(), hg.tab[2].data());
+    if (getenv("HC_NO_UNIFORM")) g.uniform = 0;
     float ext = 0.f; for (int a = 0; a < 3; a++) ext = std::max(ext, wmax[a] - wmin[a]);
     float margin = ext * (1.f / 524288.f);
     std::vector<uint64_t> out;
@@ -47,9 +50,9 @@ uint64_t hc_pairs_flat(const float* pos, const uint32_t* idx, uint32_t numTris, 
         const float* a = pos + 3 * idx[3 * t]; const float* b = pos + 3 * idx[3 * t + 1]; const float* c = pos + 3 * idx[3 * t + 2];
         V3 va = mk3(a[0], a[1], a[2]), vb = mk3(b[0], b[1], b[2]), vc = mk3(c[0], c[1], c[2]);
         int lo[3], hi[3];
-        axis_range(g.tab[0], g.k[0], fminf(a[0], fminf(b[0], c[0])), fmaxf(a[0], fmaxf(b[0], c[0])), lo[0], hi[0]);
-        axis_range(g.tab[1], g.k[1], fminf(a[1], fminf(b[1], c[1])), fmaxf(a[1], fmaxf(b[1], c[1])), lo[1], hi[1]);
-        axis_range(g.tab[2], g.k[2], fminf(a[2], fminf(b[2], c[2])), fmaxf(a[2], fmaxf(b[2], c[2])), lo[2], hi[2]);
+        axis_range(g, 0, fminf(a[0], fminf(b[0], c[0])), fmaxf(a[0], fmaxf(b[0], c[0])), lo[0], hi[0]);
+        axis_range(g, 1, fminf(a[1], fminf(b[1], c[1])), fmaxf(a[1], fmaxf(b[1], c[1])), lo[1], hi[1]);
+        axis_range(g, 2, fminf(a[2], fminf(b[2], c[2])), fmaxf(a[2], fmaxf(b[2], c[2])), lo[2], hi[2]);
         if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) continue;
         uint64_t n = (uint64_t)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
         if (n > 64) { Collect col = { &out, t }; descend_triangle(g, va, vb, vc, col); continue; }
