@@ -1,0 +1,7 @@
+for k in 4 8 12 16 24 33; do
+  echo "== BM_LEAF_BREAK=$k"
+  BM_LEAF_BREAK=$k python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; print('c2', round(d['value'],1), round(d['ms_per_step'],3), round(r['ms_per_launch'],3), round(r['bounce_launch']['ms_per_launch'],3))"
+  BM_LEAF_BREAK=$k python scratch/sweep_c5.py 10 8 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('soup ref', round(d['reference']['mrays_per_s'],1), 'closest', round(d['closest']['mrays_per_s'],1))"
+done
