@@ -416,6 +416,12 @@ def run_b200(args):
                 "note": "algorithmic bytes = 12 B ray + 16 B hit + 4 B pixel + 96 B x node/leaf visits + 32 B x cluster boxes + 48 B x triangle tests (counters of the same traversal); "
                         + peak_src + "; the tree (~%.0f MB) is L2-resident on B200, so this kernel is latency/issue-bound, not HBM-bound (SURVEY 8d)" %
                         ((st["nodes"] * 128 + st["pairs"] * 56 + st["leaves"] * 48) / 1e6)}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tr:
+            roofline["traffic"] = tr["dram_bytes_per_launch"]; roofline["traffic_source"] = tr["source"]
+    except Exception:
+        pass
     if wl.bounces and nb and SPP == 1:
         bms2 = statistics.mean(bounce_ms)
         roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb / (bms2 * 1e-3) / 1e6, "rays": nb,
