@@ -80,40 +80,135 @@ __global__ void __launch_bounds__(KG_THREADS) emit_kernel(Grid g, const float4* 
 }
 
 // ---- flat path: one SAT pass -------------------------------------------------------------------------------------------------
-// classify: exact per-axis candidate ranges; up to 64 candidate cells -> pair_test each, remember the outcome as a bit mask so
-// that the emit pass needs no geometry test at all; more than 64 -> counted by the descent.
+// classify: exact per-axis candidate ranges; up to 64 candidate cells -> decide each with pair_test's walk, remember the outcome as a
+// bit mask so that the emit pass needs no geometry test at all; more than 64 -> queued for the warp-cooperative descent.
 // info = ix0 | iy0 << 11 | iz0 << 22 | nx << 33 | ny << 40 | large << 63
+//
+// SIMT shape.  pair_test is a walk "margin check at level d, else SAT at level d, then d-1": most candidates end at the first margin
+// check, a few need one or more SATs (~250 instructions each).  Done lane by lane the SATs of a warp execute one or two lanes at a
+// time (first version: 4.5 of 32 lanes active, profiles/r1_final).  Here each lane only does the cheap margin checks; whenever a SAT
+// is needed the (owner lane, candidate, level) item goes into a per-warp shared-memory ring, and the warp then drains the ring 32
+// items at a time -- every lane runs one SAT, possibly for another lane's triangle (vertices are staged in shared memory), and
+// continues that item's walk.  Same tests on the same boxes as pair_test, only scheduled differently.
+constexpr int CL_WARPS = KG_THREADS / 32;
+constexpr int CL_RING = 2048;                  // >= 32 lanes x 64 candidates: every candidate has at most one item alive
+
+__device__ __forceinline__ void level_box(const Grid& g, int d, u32 ix, u32 iy, u32 iz, float bc[3], float hs[3])
+{
+    int sx = g.k[0] - axis_bits(d, 0), sy = g.k[1] - axis_bits(d, 1), sz = g.k[2] - axis_bits(d, 2);
+    V3 mn, mx; cell_box(g, d, ix >> sx, iy >> sy, iz >> sz, mn, mx);
+    bc[0] = (mx.x + mn.x) * .5f; bc[1] = (mx.y + mn.y) * .5f; bc[2] = (mx.z + mn.z) * .5f;       // BuildTree.cu:221-225
+    hs[0] = (mx.x - mn.x) * .5f; hs[1] = (mx.y - mn.y) * .5f; hs[2] = (mx.z - mn.z) * .5f;
+}
+__device__ __forceinline__ bool vertex_inside(const TriSat& t, const float bc[3], const float hs[3], float m)
+{
+    float hx = hs[0] - m, hy = hs[1] - m, hz = hs[2] - m;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (fabsf(t.v[k].x - bc[0]) <= hx && fabsf(t.v[k].y - bc[1]) <= hy && fabsf(t.v[k].z - bc[2]) <= hz) return true;
+    return false;
+}
+
 __global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, float margin,
                                                               u32* __restrict__ counts, u64* __restrict__ masks, u64* __restrict__ infos,
                                                               u32* __restrict__ largeList, u32* largeCount)
 {
+    __shared__ u32 ring[CL_WARPS][CL_RING];
+    __shared__ float sv[CL_WARPS][32][9];
+    __shared__ u32 sorg[CL_WARPS][32][4];               // x0, y0, z0, nx | ny << 8
+    __shared__ unsigned long long smask[CL_WARPS][32];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= numTris) return;
-    const float4* p = soup + 3 * (size_t)t;
-    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    V3 va = mk3(a.x, a.y, a.z), vb = mk3(b.x, b.y, b.z), vc = mk3(c.x, c.y, c.z);
-    int lo[3], hi[3];
-    axis_range(g, 0, fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
-    axis_range(g, 1, fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
-    axis_range(g, 2, fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
-    if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) { counts[t] = 0; masks[t] = 0; infos[t] = 0; return; }
-    u64 nx = (u64)(hi[0] - lo[0] + 1), ny = (u64)(hi[1] - lo[1] + 1), nz = (u64)(hi[2] - lo[2] + 1);
-    if (nx * ny * nz > 64ull)
+    bool valid = t < numTris;
+    float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+    if (valid) { const float4* p = soup + 3 * (size_t)t; a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); }
+    TriSat ts; trisat_init(ts, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z));
+    int lo[3] = { 0, 0, 0 }, hi[3] = { -1, -1, -1 };
+    if (valid)
+    {
+        axis_range(g, 0, fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
+        axis_range(g, 1, fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
+        axis_range(g, 2, fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
+    }
+    bool empty = !valid || lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2];
+    u32 nx = empty ? 0u : (u32)(hi[0] - lo[0] + 1), ny = empty ? 0u : (u32)(hi[1] - lo[1] + 1), nz = empty ? 0u : (u32)(hi[2] - lo[2] + 1);
+    bool large = !empty && (u64)nx * ny * nz > 64ull;
+    u32 ncand = (empty || large) ? 0u : nx * ny * nz;
+    // stage this lane's triangle and candidate box for the other lanes
+    sv[w][lane][0] = a.x; sv[w][lane][1] = a.y; sv[w][lane][2] = a.z; sv[w][lane][3] = b.x; sv[w][lane][4] = b.y; sv[w][lane][5] = b.z;
+    sv[w][lane][6] = c.x; sv[w][lane][7] = c.y; sv[w][lane][8] = c.z;
+    sorg[w][lane][0] = (u32)lo[0]; sorg[w][lane][1] = (u32)lo[1]; sorg[w][lane][2] = (u32)lo[2]; sorg[w][lane][3] = nx | (ny << 8);
+    smask[w][lane] = 0ull;
+    __syncwarp();
+
+    // phase A: margin check of every candidate at leaf level; the rest is queued for a SAT at that level
+    u32 head = 0, tail = 0;                            // warp-uniform ring cursors (monotone; index = cursor % CL_RING)
+    u32 maxCand = __reduce_max_sync(FULL, ncand);
+    for (u32 k = 0; k < maxCand; k++)
+    {
+        bool need = false;
+        if (k < ncand)
+        {
+            u32 ix = (u32)lo[0] + k % nx, iy = (u32)lo[1] + (k / nx) % ny, iz = (u32)lo[2] + k / (nx * ny);
+            float bc[3], hs[3]; level_box(g, g.D, ix, iy, iz, bc, hs);
+            if (vertex_inside(ts, bc, hs, margin)) smask[w][lane] |= 1ull << k;
+            else need = true;
+        }
+        unsigned bits = __ballot_sync(FULL, need);
+        if (need) ring[w][(tail + __popc(bits & ((1u << lane) - 1u))) % CL_RING] = lane | (k << 5) | ((u32)g.D << 11);
+        tail += __popc(bits);
+    }
+    __syncwarp();
+
+    // phase B: drain the ring, 32 SATs per step
+    while (head < tail)
+    {
+        u32 n = min(32u, tail - head);
+        bool have = lane < n;
+        u32 item = have ? ring[w][(head + lane) % CL_RING] : 0u;
+        head += n;
+        __syncwarp();
+        bool again = false; u32 nextItem = 0;
+        if (have)
+        {
+            u32 owner = item & 31u, k = (item >> 5) & 63u; int d = (int)(item >> 11);
+            TriSat ot;
+            trisat_init(ot, mk3(sv[w][owner][0], sv[w][owner][1], sv[w][owner][2]), mk3(sv[w][owner][3], sv[w][owner][4], sv[w][owner][5]),
+                        mk3(sv[w][owner][6], sv[w][owner][7], sv[w][owner][8]));
+            u32 onx = sorg[w][owner][3] & 255u, ony = sorg[w][owner][3] >> 8;
+            u32 ix = sorg[w][owner][0] + k % onx, iy = sorg[w][owner][1] + (k / onx) % ony, iz = sorg[w][owner][2] + k / (onx * ony);
+            float bc[3], hs[3]; level_box(g, d, ix, iy, iz, bc, hs);
+            if (sat_box(ot, bc, hs))
+            {
+                // the walk goes on one level up: margin check there, else another SAT
+                bool accept = d == 1;
+                if (!accept)
+                {
+                    level_box(g, d - 1, ix, iy, iz, bc, hs);
+                    if (vertex_inside(ot, bc, hs, margin)) accept = true;
+                    else { again = true; nextItem = owner | (k << 5) | ((u32)(d - 1) << 11); }
+                }
+                if (accept) atomicOr(&smask[w][owner], 1ull << k);
+            }
+        }
+        unsigned bits = __ballot_sync(FULL, again);
+        if (again) ring[w][(tail + __popc(bits & ((1u << lane) - 1u))) % CL_RING] = nextItem;
+        tail += __popc(bits);
+        __syncwarp();
+    }
+    if (!valid) return;
+    if (large)
     {
         // large triangle: handed to the warp-cooperative descent (large_kernel), which fills counts[t]
         counts[t] = 0; masks[t] = 0; infos[t] = 1ull << 63;
         largeList[atomicAdd(largeCount, 1u)] = t;
         return;
     }
-    TriSat ts; trisat_init(ts, va, vb, vc);
-    u64 mask = 0; u32 bit = 0;
-    for (int iz = lo[2]; iz <= hi[2]; iz++)
-        for (int iy = lo[1]; iy <= hi[1]; iy++)
-            for (int ix = lo[0]; ix <= hi[0]; ix++, bit++)
-                if (pair_test(g, ts, (u32)ix, (u32)iy, (u32)iz, margin)) mask |= 1ull << bit;
+    u64 mask = smask[w][lane];
     counts[t] = (u32)__popcll(mask);
     masks[t] = mask;
-    infos[t] = (u64)lo[0] | ((u64)lo[1] << 11) | ((u64)lo[2] << 22) | (nx << 33) | (ny << 40);
+    infos[t] = empty ? 0ull : ((u64)lo[0] | ((u64)lo[1] << 11) | ((u64)lo[2] << 22) | ((u64)nx << 33) | ((u64)ny << 40));
 }
 
 __global__ void __launch_bounds__(KG_THREADS) emit_flat_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, const u32* __restrict__ offsets,
