@@ -460,6 +460,120 @@ def run_b200(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
+def run_c5(args):
+    """BASELINE config 5: counter-based triangle soup (default 100 M triangles) built once, then incoherent ray batches (origin uniform
+    in the world, direction uniform on the sphere) traced in reference mode.  One step = one batch of --c5-mrays million rays per rank;
+    ranks trace different batches against a replicated tree (weak scaling).  This is the HBM-bound case: the tree is far larger than L2."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    sys.stdout.flush(); saved_stdout = os.dup(1); os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from raytracercuda_b200 import build
+    if local == 0:
+        build.build_library()
+    if world > 1:
+        dist.barrier()
+    from raytracercuda_b200 import _lib, synth
+    from raytracercuda_b200.dist import replicate_tree
+    from raytracercuda_b200.tree import Tree
+    L = _lib.load()
+    T = int(args.c5_mtris * 1e6); n = int(args.c5_mrays * 1e6)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    built, build_ms, st = None, [], None
+    if rank == 0:
+        Pd, Id = synth.soup_torch(T, dev)
+        built = Tree(dev)
+        for i in range(3):
+            built.reset(); built.add_mesh(Pd, Id)
+            e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record(); built.build(); e1.record(); torch.cuda.synchronize(dev)
+            build_ms.append(e0.elapsed_time(e1))
+        st = built.stats()
+    e0, e1 = ev(), ev(); torch.cuda.synchronize(dev)
+    if world > 1: dist.barrier()
+    e0.record(); tree = replicate_tree(built, dev, 0); e1.record(); torch.cuda.synchronize(dev)
+    rep_ms = e0.elapsed_time(e1) if world > 1 else 0.0
+    stt = torch.zeros(4, dtype=torch.int64, device=dev)
+    if rank == 0:
+        stt.copy_(torch.tensor([st["triangles"], st["pairs"], st["leaves"], st["nodes"]]))
+    if world > 1:
+        dist.broadcast(stt, 0)
+    Tn, Pn, Ln, Nn = [int(x) for x in stt.cpu()]
+    rays = synth.incoherent_rays_torch(n, dev, start=rank * n)
+    hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    rays_pinned = rays.cpu().pin_memory(); hits_host = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize(dev)
+
+    def step(src):
+        _lib.check(L.bmTraceRays(tree.h, src.data_ptr(), n, 0, hits.data_ptr(), None), "bmTraceRays")
+    for _ in range(max(args.warmup, 3)):
+        step(rays)
+    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+    _lib.check(L.bmTraceRays(tree.h, rays.data_ptr(), n, 0, hits.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+    torch.cuda.synchronize(dev)
+    V, K, Cc, LONG = [int(x) for x in cnt.cpu()]
+    hit_rate = float((hits[:, 3].view(torch.int32) != -1).float().mean())
+    sampler = ClockSampler(local); launches0 = L.bmLaunchCount()
+    sync_all(); sampler.start()
+    ms = []
+    for _ in range(args.steps):
+        a, b = ev(), ev(); sync_all(); a.record(); step(rays); b.record(); sync_all(); ms.append(a.elapsed_time(b))
+    clocks = sampler.stop(); launches = L.bmLaunchCount() - launches0
+    tsum = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tsum, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tsum.item()) / args.steps
+    value = n * world / (ms_per_step * 1e-3) / 1e6
+    e2e_dev = torch.empty_like(rays); ems = []
+    for i in range(2 + args.steps):
+        a, b = ev(), ev(); sync_all(); a.record()
+        e2e_dev.copy_(rays_pinned, non_blocking=True); step(e2e_dev); hits_host.copy_(hits, non_blocking=True)
+        b.record(); sync_all()
+        if i >= 2: ems.append(a.elapsed_time(b))
+    t2 = torch.tensor([sum(ems)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = n * world / (float(t2.item()) / args.steps * 1e-3) / 1e6
+    peak, peak_src = measured_peaks()
+    by = n * (24 + 16) + NODE_BYTES * V + CLUSTER_BYTES * Cc + TRI_BYTES * K
+    kms = statistics.mean(ms)
+    bt = torch.tensor([min(build_ms) if build_ms else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.broadcast(bt, 0)
+    bms = float(bt.item())
+    build_bytes = 48 * Tn + 12 * Pn + 128 * Nn + 48 * Pn + 48 * Ln + 8 * Pn
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c5: synthetic %.0f M-triangle soup (splitmix64 seed 12345), incoherent rays (seed 54321), %.0f M rays per step per GPU, reference semantics" % (args.c5_mtris, args.c5_mrays),
+                       "rays_per_step_per_gpu": n, "l2": "tree (%.1f GB) and ray batch (%.1f GB) far exceed L2" % ((Nn * 128 + Pn * 56 + Ln * 48) / 1e9, n * 40 / 1e9),
+                       "sharding": "ray batches per rank, tree built on rank 0 and replicated by NCCL broadcast" if world > 1 else "single GPU", "hit_rate": hit_rate},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 16, "ms_per_step": float(t2.item()) / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "trace_kernel<rays> (bmTraceRays, reference semantics)", "achieved": by / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": by / (kms * 1e-3) / 1e9 / peak, "traffic": None, "ms_per_launch": kms, "bytes_per_ray": by / n, "node_visits_per_ray": V / n,
+                         "tri_tests_per_ray": K / n, "cluster_boxes_per_ray": Cc / n, "longest_ray_steps": LONG,
+                         "note": "24 B ray + 16 B hit + 96 B x node/leaf visits + 32 B x cluster boxes + 48 B x triangle tests; " + peak_src},
+            "build": {"metric": "BVH build Mtris/s", "value": Tn / (bms * 1e-3) / 1e6 if bms else None, "unit": "Mtris/s", "ms": bms, "triangles": Tn, "pairs": Pn, "leaves": Ln, "nodes": Nn,
+                      "roofline": {"bound": "hbm", "achieved": build_bytes / (bms * 1e-3) / 1e9 if bms else None, "peak": peak, "unit": "GB/s",
+                                   "frac": build_bytes / (bms * 1e-3) / 1e9 / peak if bms else None, "traffic": None, "algorithmic_bytes": build_bytes},
+                      "replicate_ms": rep_ms}}
+    sys.stdout.flush(); os.dup2(saved_stdout, 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        os.dup2(2, 1); dist.barrier(); dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
 def _oracle_scene(wl):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_build/liboracle.so"], stdout=subprocess.DEVNULL)
     from oracle.bindings import OracleLib, OracleScene
@@ -557,11 +671,15 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c5-mtris", type=float, default=100.0, help="workload c5: millions of soup triangles")
+    ap.add_argument("--c5-mrays", type=float, default=16.0, help="workload c5: millions of incoherent rays per step per GPU")
     ap.add_argument("--e2e-bands", type=int, default=1, help="row bands of the pipelined e2e frame (1 measured fastest: a trace launch has a ~0.25 ms critical path regardless of size)")
     ap.add_argument("--reference-rays", type=int, default=200_000, help="primary rays per step of the --impl reference sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_b200(args)
 

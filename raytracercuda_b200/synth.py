@@ -110,3 +110,53 @@ def orient_from_pan_pitch(pan: float, pitch: float) -> np.ndarray:
     Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]); Rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
     M = (Ry @ Rx).astype(np.float32)
     return np.ascontiguousarray(M.T).reshape(-1)      # row-major of the transpose == column-major of M
+
+
+# ---- the same generators on a torch device (config 5 at full size: 100 M triangles are generated where they are used) ----------------
+def _t_lsr(x, s):
+    import torch
+    return (x >> s) & ((1 << (64 - s)) - 1)                       # logical shift right on int64
+
+
+def _t_splitmix64(x):
+    import torch
+    x = x + torch.tensor(0x9E3779B97F4A7C15 - (1 << 64), dtype=torch.int64, device=x.device)
+    z = x
+    z = (z ^ _t_lsr(z, 30)) * torch.tensor(0xBF58476D1CE4E5B9 - (1 << 64), dtype=torch.int64, device=x.device)
+    z = (z ^ _t_lsr(z, 27)) * torch.tensor(0x94D049BB133111EB - (1 << 64), dtype=torch.int64, device=x.device)
+    return z ^ _t_lsr(z, 31)
+
+
+def _t_uniform(seed, k, lane):
+    import torch
+    x = _t_splitmix64(torch.tensor(seed, dtype=torch.int64, device=k.device) ^ _t_splitmix64(k * 16 + lane))
+    return _t_lsr(x, 11).to(torch.float64) * (1.0 / 9007199254740992.0)
+
+
+def soup_torch(num_tris: int, device, seed: int = 12345, extent: float = 28.0, edge: float = 0.02, start: int = 0, chunk: int = 1 << 22):
+    """soup() evaluated with torch on `device`, bit-identical to the numpy version; returns (positions (3n,3) float32, indices (3n,) int32)"""
+    import torch
+    P = torch.empty((num_tris, 3, 3), dtype=torch.float32, device=device)
+    for a0 in range(0, num_tris, chunk):
+        a1 = min(num_tris, a0 + chunk)
+        k = torch.arange(start + a0, start + a1, dtype=torch.int64, device=device)
+        c = [(_t_uniform(seed, k, a) * 2 - 1) * extent for a in range(3)]
+        for v in range(3):
+            for a in range(3):
+                P[a0:a1, v, a] = (c[a] + (_t_uniform(seed, k, 3 + 3 * v + a) * 2 - 1) * edge).to(torch.float32)
+    I = torch.arange(3 * num_tris, dtype=torch.int32, device=device)
+    return P.reshape(-1, 3), I
+
+
+def incoherent_rays_torch(num: int, device, seed: int = 54321, extent: float = 28.0, start: int = 0, out=None):
+    """incoherent_rays() evaluated with torch on `device` (same counter-based construction; float64 trig, float32 result)"""
+    import torch
+    k = torch.arange(start, start + num, dtype=torch.int64, device=device)
+    R = out if out is not None else torch.empty((num, 6), dtype=torch.float32, device=device)
+    for a in range(3):
+        R[:, a] = ((_t_uniform(seed, k, a) * 2 - 1) * extent).to(torch.float32)
+    z = _t_uniform(seed, k, 3) * 2 - 1
+    phi = _t_uniform(seed, k, 4) * (2 * np.pi)
+    r = torch.sqrt(torch.clamp(1 - z * z, min=0))
+    R[:, 3] = (r * torch.cos(phi)).to(torch.float32); R[:, 4] = (r * torch.sin(phi)).to(torch.float32); R[:, 5] = z.to(torch.float32)
+    return R
