@@ -144,8 +144,9 @@ int  bmTreeMeshBases(const bmTree* tree, uint32_t* h_bases, uint32_t capacity); 
  * alive; such a tree can be traced (and feed bmBounceRays) but not rebuilt or inspected with bmTreeCopy*. */
 int  bmTreeArraySizes(const bmTree* tree, uint64_t* sizes8);
 int  bmTreeExport(const bmTree* tree, void* d_nodes, void* d_leaves, void* d_ltris, void* d_clusters, void* d_soup);
+int  bmTreeRoot(const bmTree* tree, uint32_t* root);           /* reference of the root: node index, or 0x80000000 | 0 when the only leaf is the root */
 int  bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
-                  uint64_t numLeaves, uint64_t numPairs, uint64_t numTris);
+                  uint64_t numLeaves, uint64_t numPairs, uint64_t numTris, uint32_t root);
 
 /* Explicit ray batch -> hit records. d_counters (nullable, FOUR uint64) accumulates {node + leaf visits, triangle tests, cluster
  * boxes tested} (the traversal work behind the bytes-per-ray roofline model) and keeps in [3] the largest number of such steps any

@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "bmResetScene", "bmInsertMeshInTree", "bmMarch", "bmGetFaceSize", "bmGetFacePtrSize", "bmGetMaterialSize", "bmGetNodeSize",
     "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
-    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot",
     "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
@@ -78,7 +78,8 @@ def load() -> C.CDLL:
     L.bmTreeMeshBases.argtypes = [vp, C.POINTER(u32), u32]
     L.bmTreeArraySizes.argtypes = [vp, C.POINTER(u64)]
     L.bmTreeExport.argtypes = [vp, vp, vp, vp, vp, vp]
-    L.bmTreeImport.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, u64, u64, u64]
+    L.bmTreeImport.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, u64, u64, u64, u32]
+    L.bmTreeRoot.argtypes = [vp, C.POINTER(u32)]
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]
     L.bmTraceCamera.argtypes = [vp, vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
     L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]

@@ -51,7 +51,7 @@ struct TreeView
     const float4* ltris;
     const float4* clusters;
     u32 numLeaves;
-    u32 rootRef;          // bit 31 = leaf
+    const u32* root;      // device: index of the root node (numLeaves >= 2; a single leaf is its own root)
 };
 
 // ---- scan.cu --------------------------------------------------------------------------------------------------------
@@ -84,8 +84,9 @@ int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_
 // cluster boxes + leaf boxes + leaf statistics + the 256-cap exclusion flags; d_clusterFirst = exclusive scan of the cluster counts
 int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* d_leafIdx, size_t numPairs, const u32* d_clusterFirst, float4* d_ltris,
                 float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, u32* d_overList, cudaStream_t s);
-int emit_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s);
-int refit(u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit, float4* d_nodes, cudaStream_t s);
+// radix tree + tight boxes + reference-node data in one bottom-up pass; *d_root receives the root's node index
+int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
+                    float4* d_nodes, u32* d_root, cudaStream_t s);
 int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, u64* d_out, cudaStream_t s);
 int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s);
 

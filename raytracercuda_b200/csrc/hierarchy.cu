@@ -149,86 +149,67 @@ __global__ void __launch_bounds__(CAP_THREADS) cap_flags_kernel(const float4* __
     }
 }
 
-__device__ __forceinline__ u32 leaf_code(const u32* __restrict__ codes, int i) { return __ldg(codes + i); }
-__device__ __forceinline__ int delta(const u32* __restrict__ codes, int i, int j, int n)
+// ---- hierarchy emission + refit in one bottom-up pass ---------------------------------------------------------------------------
+// Apetrei 2014 ("Fast and simple agglomerative LBVH construction"): the binary radix tree over the sorted distinct codes, built from
+// the leaves upwards.  A thread owning the key range [l, r] (initially one leaf) joins the neighbour range across the boundary with
+// the smaller delta: delta(i) = code[i] ^ code[i+1]; if delta(r) < delta(l-1) its parent is internal node r (it is the LEFT child and
+// the parent's split lies between r and r+1), else node l-1 (RIGHT child).  One atomic exchange per node on the "other bound" tells
+// the second arrival (which then owns the merged range and both child boxes) from the first (which stops).  This is the same tree
+// Karras' top-down searches produce (node = split position), without the 2 log L random reads per node, and the tight boxes are
+// united on the way up, so no separate refit pass is needed.  Each node also receives the reference node it stands for: common
+// prefix (prefixLen bits of the codes of its range), cell box and split plane from the grid (BuildTree.cu:436-443).
+__device__ __forceinline__ u32 range_delta(const u32* __restrict__ codes, int i, int n)      // boundary between leaf i and i+1
 {
-    if (j < 0 || j >= n) return -1;
-    return __clz(leaf_code(codes, i) ^ leaf_code(codes, j));       // codes are distinct, so never 32
+    return (i < 0 || i >= n - 1) ? 0xFFFFFFFFu : (__ldg(codes + i) ^ __ldg(codes + i + 1));
 }
 
-// Karras 2012, one thread per internal node i in [0, L-1)
-__global__ void karras_kernel(Grid g, const u32* __restrict__ leaves, u32 numLeaves, float4* __restrict__ nodes,
-                              u32* __restrict__ parentOfNode, u32* __restrict__ parentOfLeaf)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = (int)numLeaves;
-    if (i >= n - 1) return;
-    const int D = g.D;
-    int d = (delta(leaves, i, i + 1, n) - delta(leaves, i, i - 1, n)) >= 0 ? 1 : -1;
-    int dmin = delta(leaves, i, i - d, n);
-    int lmax = 2;
-    while (delta(leaves, i, i + lmax * d, n) > dmin) lmax <<= 1;
-    int l = 0;
-    for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (delta(leaves, i, i + (l + t) * d, n) > dmin) l += t;
-    int j = i + l * d;
-    int dnode = delta(leaves, i, j, n);
-    int s = 0;
-    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1)
-    {
-        if (delta(leaves, i, i + (s + t) * d, n) > dnode) s += t;
-        if (t == 1) break;
-    }
-    int gamma = i + s * d + min(d, 0);
-    int first = min(i, j), last = max(i, j);
-    u32 c0 = (gamma == first) ? ((u32)gamma | LEAF_BIT) : (u32)gamma;
-    u32 c1 = (gamma + 1 == last) ? ((u32)(gamma + 1) | LEAF_BIT) : (u32)(gamma + 1);
-    if (c0 & LEAF_BIT) parentOfLeaf[gamma] = (u32)i; else parentOfNode[gamma] = (u32)i;
-    if (c1 & LEAF_BIT) parentOfLeaf[gamma + 1] = (u32)i; else parentOfNode[gamma + 1] = (u32)i;
-    if (i == 0) parentOfNode[0] = 0xFFFFFFFFu;
-    int plen = dnode - (32 - D);                     // common prefix length inside the D-bit code
-    u32 prefix = plen > 0 ? (leaf_code(leaves, i) >> (D - plen)) : 0u;
-    float4* o = nodes + NODE_F4 * (size_t)i;
-    o[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
-    // the reference node's implicit box and split plane (BuildTree.cu:436-443), straight from the grid tables
-    u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
-    V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
-    int axis = plen % 3;
-    u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
-    int sh = g.k[axis] - axis_bits(plen, axis);      // >= 1: the node splits on this axis
-    float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
-    o[4] = make_float4(mn.x, mn.y, mn.z, sp);
-    o[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
-}
-
-// boxes travel as two float4: (lo.xyz, hi.x) (hi.y, hi.z, -, -)
-struct Box2 { float4 a, b; };
+struct Box2 { float4 a, b; };                 // (lo.xyz, hi.x) (hi.y, hi.z, -, -)
 __device__ __forceinline__ Box2 load_box(const float4* p) { Box2 r; r.a = __ldcg(p); r.b = __ldcg(p + 1); return r; }   // written by another thread of this launch: bypass L1
 
-// bottom-up: thread per leaf climbs; the second thread to reach a node has both child boxes available
-__global__ void refit_kernel(u32 numLeaves, const float4* __restrict__ leafBox, float4* nodeBox, const u32* __restrict__ parentOfNode,
-                             const u32* __restrict__ parentOfLeaf, u32* visit, float4* nodes)
+__global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 numLeaves, const float4* __restrict__ leafBox, float4* nodeBox,
+                                   int* otherBound, u32* childRefs, float4* nodes, u32* rootOut)
 {
-    u32 l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= numLeaves) return;
-    u32 cur = parentOfLeaf[l];
-    while (cur != 0xFFFFFFFFu)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)numLeaves;
+    if (i >= n) return;
+    const int D = g.D;
+    int l = i, r = i;
+    u32 cur = (u32)i | LEAF_BIT;
+    for (;;)
     {
+        bool leftChild = (l == 0) || (r != n - 1 && range_delta(codes, r, n) < range_delta(codes, l - 1, n));
+        int parent = leftChild ? r : l - 1;
+        childRefs[2 * (size_t)parent + (leftChild ? 0 : 1)] = cur;
         __threadfence();
-        if (atomicAdd(&visit[cur], 1u) == 0u) return;
+        int other = atomicExch(&otherBound[parent], leftChild ? l : r);
+        if (other == -1) return;                      // first arrival: the sibling will finish this node
         __threadfence();
-        float4 q3 = __ldcg(&nodes[NODE_F4 * (size_t)cur + 3]);
-        u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
+        if (leftChild) r = other; else l = other;
+        // second arrival: both children are known and their boxes written
+        u32 c0 = __ldcg(&childRefs[2 * (size_t)parent]), c1 = __ldcg(&childRefs[2 * (size_t)parent + 1]);
         Box2 b0 = load_box((c0 & LEAF_BIT) ? leafBox + 2 * (size_t)(c0 & ~LEAF_BIT) : nodeBox + 2 * (size_t)c0);
         Box2 b1 = load_box((c1 & LEAF_BIT) ? leafBox + 2 * (size_t)(c1 & ~LEAF_BIT) : nodeBox + 2 * (size_t)c1);
-        float4* np = nodes + NODE_F4 * (size_t)cur;
+        u32 cl = __ldg(codes + l), cr = __ldg(codes + r);
+        int plen = __clz(cl ^ cr) - (32 - D);         // common prefix length inside the D-bit code (l < r: codes differ)
+        u32 prefix = plen > 0 ? (cl >> (D - plen)) : 0u;
+        u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
+        V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
+        int axis = plen % 3;
+        u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+        int sh = g.k[axis] - axis_bits(plen, axis);   // >= 1: the node splits on this axis
+        float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
+        float4* np = nodes + NODE_F4 * (size_t)parent;
         np[0] = b0.a;                                                   // lo0.xyz hi0.x
         np[1] = make_float4(b0.b.x, b0.b.y, b1.a.x, b1.a.y);            // hi0.yz lo1.xy
         np[2] = make_float4(b1.a.z, b1.a.w, b1.b.x, b1.b.y);            // lo1.z hi1.xyz
-        float4* o = nodeBox + 2 * (size_t)cur;
+        np[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
+        np[4] = make_float4(mn.x, mn.y, mn.z, sp);
+        np[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
+        if (l == 0 && r == n - 1) { *rootOut = (u32)parent; return; }
+        float4* o = nodeBox + 2 * (size_t)parent;
         __stcg(o, make_float4(fminf(b0.a.x, b1.a.x), fminf(b0.a.y, b1.a.y), fminf(b0.a.z, b1.a.z), fmaxf(b0.a.w, b1.a.w)));
         __stcg(o + 1, make_float4(fmaxf(b0.b.x, b1.b.x), fmaxf(b0.b.y, b1.b.y), 0.f, 0.f));
-        cur = parentOfNode[cur];
+        cur = (u32)parent;
     }
 }
 
@@ -281,19 +262,12 @@ int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* 
     BM_LAUNCHED();
     return BM_OK;
 }
-int emit_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, float4* d_nodes, u32* d_parentOfNode, u32* d_parentOfLeaf, cudaStream_t s)
+int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
+                    float4* d_nodes, u32* d_root, cudaStream_t s)
 {
     if (numLeaves < 2) return BM_OK;
-    karras_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_nodes, d_parentOfNode, d_parentOfLeaf);
-    BM_LAUNCHED();
-    return BM_OK;
-}
-int refit(u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, const u32* d_parentOfNode, const u32* d_parentOfLeaf, u32* d_visit,
-          float4* d_nodes, cudaStream_t s)
-{
-    if (numLeaves < 2) return BM_OK;
-    BM_CUDA(cudaMemsetAsync(d_visit, 0, (size_t)(numLeaves - 1) * 4, s));
-    refit_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(numLeaves, d_leafBox2, d_nodeBox2, d_parentOfNode, d_parentOfLeaf, d_visit, d_nodes);
+    BM_CUDA(cudaMemsetAsync(d_otherBound, 0xFF, (size_t)(numLeaves - 1) * 4, s));
+    agglomerate_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_otherBound, d_childRefs, d_nodes, d_root);
     BM_LAUNCHED();
     return BM_OK;
 }

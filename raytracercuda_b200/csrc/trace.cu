@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
                                                            const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int refillMin)
 {
+    const u32 rootRef = tv.numLeaves >= 2 ? __ldg(tv.root) : (tv.numLeaves == 1 ? (0u | LEAF_BIT) : REF_EMPTY);
     if (numRaysDev) { n = __ldg(numRaysDev); totalSlots = (u32)n; }       // count produced on the device (bmBounceRays): no host round trip
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const
                     oi = o * ic;
                     best.t = FLT_MAX; best.u = 0.f; best.v = 0.f; best.tri = best.mesh = best.face = 0xFFFFFFFFu;
                     top = -1;
-                    cur = tv.numLeaves ? tv.rootRef : REF_EMPTY;
+                    cur = rootRef;
                     active = true;
                     if (COUNT) rayStart = nv + nt + nc;
                 }

@@ -62,7 +62,7 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false, imported = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev;
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
     u32 maxLeaf = 0, overLeaves = 0;
@@ -72,12 +72,12 @@ struct bmTree
     {
         TreeView v;
         v.nodes = nodes.as<float4>(); v.leaves = leaves.as<float4>(); v.ltris = ltris.as<float4>(); v.clusters = clusters.as<float4>();
-        v.numLeaves = (u32)L; v.rootRef = (L == 1) ? (0u | LEAF_BIT) : 0u;
+        v.numLeaves = (u32)L; v.root = rootDev.as<u32>();
         return v;
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -91,8 +91,9 @@ static int tree_build(bmTree* t)
     for (auto& m : t->staged) { t->meshBase.push_back((u32)T); T += m.numTris; }
     if (T >= 0xFFFFFFFFull) { set_error("more than 2^32-2 triangles"); return BM_ERROR_CAPACITY; }
     t->T = T; t->P = 0; t->L = 0; t->maxLeaf = 0; t->overLeaves = 0;
-    BM_TRY(t->scalars.reserve(64));
+    BM_TRY(t->scalars.reserve(64)); BM_TRY(t->rootDev.reserve(16));
     BM_CUDA(cudaMemsetAsync(t->scalars.p, 0, 64, s));
+    BM_CUDA(cudaMemsetAsync(t->rootDev.p, 0, 16, s));
     if (T == 0) { t->built = true; return BM_OK; }
     BM_TRY(t->soup.reserve(T * 48));
     for (size_t k = 0; k < t->staged.size(); k++)
@@ -154,9 +155,9 @@ static int tree_build(bmTree* t)
     if (L >= 2)
     {
         BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4)); BM_TRY(t->nodeBox.reserve((L - 1) * 32));
-        BM_TRY(t->parentN.reserve((L - 1) * 4)); BM_TRY(t->parentL.reserve(L * 4)); BM_TRY(t->visit.reserve((L - 1) * 4));
-        BM_TRY(emit_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->nodes.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), s));
-        BM_TRY(refit((u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->parentN.as<u32>(), t->parentL.as<u32>(), t->visit.as<u32>(), t->nodes.as<float4>(), s));
+        BM_TRY(t->parentN.reserve((L - 1) * 8)); BM_TRY(t->visit.reserve((L - 1) * 4));
+        BM_TRY(build_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->visit.as<int>(), t->parentN.as<u32>(),
+                               t->nodes.as<float4>(), t->rootDev.as<u32>(), s));
     }
     t->built = true;
     return BM_OK;
@@ -301,6 +302,20 @@ extern "C" int bmTreeArraySizes(const bmTree* t, uint64_t* sizes8)
     return BM_OK;
 }
 
+extern "C" int bmTreeRoot(const bmTree* t, uint32_t* root)
+{
+    if (!t || !root) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    *root = 0;
+    if (t->L >= 2)
+    {
+        BM_CUDA(cudaMemcpyAsync(root, t->rootDev.p, 4, cudaMemcpyDeviceToHost, t->stream));
+        BM_CUDA(cudaStreamSynchronize(t->stream));
+    }
+    else if (t->L == 1) *root = LEAF_BIT;
+    return BM_OK;
+}
+
 extern "C" int bmTreeExport(const bmTree* t, void* d_nodes, void* d_leaves, void* d_ltris, void* d_clusters, void* d_soup)
 {
     uint64_t sz[8];
@@ -313,11 +328,13 @@ extern "C" int bmTreeExport(const bmTree* t, void* d_nodes, void* d_leaves, void
 }
 
 extern "C" int bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
-                            uint64_t numLeaves, uint64_t numPairs, uint64_t numTris)
+                            uint64_t numLeaves, uint64_t numPairs, uint64_t numTris, uint32_t root)
 {
     if (!out) return BM_ERROR_INVALID_PARAMETER;
     bmTree* t = nullptr;
     BM_TRY(bmTreeCreate(&t, nullptr, nullptr, 0.f, 0));
+    { int r = t->rootDev.reserve(16); if (r != BM_OK) { delete t; return r; } }
+    if (cudaMemcpy(t->rootDev.p, &root, 4, cudaMemcpyHostToDevice) != cudaSuccess) { delete t; set_error("root upload failed"); return BM_ERROR_CUDA; }
     t->L = numLeaves; t->P = numPairs; t->T = numTris;
     size_t nC = numPairs ? numPairs / CLUSTER + numLeaves + 1 : 0;
     t->nodes.adopt(d_nodes, numLeaves >= 2 ? (numLeaves - 1) * 16ull * NODE_F4 : 0);

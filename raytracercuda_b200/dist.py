@@ -41,11 +41,11 @@ def replicate_tree(tree: Tree | None, device, src: int = 0) -> Tree:
         return tree
     L = _lib.load()
     rank = dist.get_rank()
-    sizes = torch.zeros(8, dtype=torch.int64, device=device)
+    sizes = torch.zeros(9, dtype=torch.int64, device=device)
     if rank == src:
         s = (C.c_uint64 * 8)()
         _lib.check(L.bmTreeArraySizes(tree.h, s), "bmTreeArraySizes")
-        sizes.copy_(torch.tensor([int(x) for x in s], dtype=torch.int64))
+        sizes.copy_(torch.tensor([int(x) for x in s] + [tree.root()], dtype=torch.int64))
     dist.broadcast(sizes, src)
     sz = [int(x) for x in sizes.cpu()]
     bufs = [torch.empty(max(b, 16), dtype=torch.uint8, device=device) for b in sz[:5]]
@@ -59,7 +59,7 @@ def replicate_tree(tree: Tree | None, device, src: int = 0) -> Tree:
     out = Tree.__new__(Tree)
     out.L = L; out.device = torch.device(device); out._meshes = []
     h = C.c_void_p()
-    _lib.check(L.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7]), "bmTreeImport")
+    _lib.check(L.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7], sz[8]), "bmTreeImport")
     out.h = h
     out._imported_buffers = bufs          # keep the adopted memory alive with the handle
     out.use_stream(torch.cuda.current_stream(out.device))

@@ -75,6 +75,11 @@ class Tree:
         k = ["triangles", "pairs", "leaves", "nodes", "depth", "max_leaf_faces", "overflow_leaves", "meshes"]
         return {n: int(v) for n, v in zip(k, s)}
 
+    def root(self) -> int:
+        r = C.c_uint32(0)
+        check(self.L.bmTreeRoot(self.h, C.byref(r)), "bmTreeRoot")
+        return int(r.value)
+
     def mesh_bases(self) -> np.ndarray:
         n = len(self._meshes)
         b = (C.c_uint32 * max(n, 1))()

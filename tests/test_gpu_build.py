@@ -51,12 +51,16 @@ def _check_tree_against_oracle(t, s, parts):
     od, op = s.branches()
     mine = np.stack([plen, prefix], 1); mine = mine[np.lexsort((mine[:, 1], mine[:, 0]))]
     assert np.array_equal(mine, np.stack([od, op], 1)), "radix-tree topology differs from the reference's two-child nodes"
-    # structural checks: every internal node and every leaf is referenced exactly once
+    # structural checks: every leaf and every internal node except the root is referenced exactly once; left child = smaller codes
     L, N = st["leaves"], st["nodes"]
     if N:
         refs = np.concatenate([c0, c1])
         leaf_refs = np.sort(refs[refs >= 0x80000000] & 0x7FFFFFFF); node_refs = np.sort(refs[refs < 0x80000000])
-        assert np.array_equal(leaf_refs, np.arange(L)) and np.array_equal(node_refs, np.arange(1, N))
+        root = t.root()
+        assert np.array_equal(leaf_refs, np.arange(L)) and np.array_equal(node_refs, np.delete(np.arange(N), root))
+        assert plen[root] == plen.min()
+    else:
+        assert t.root() == (0x80000000 if L == 1 else 0)
     return code, tri, plen, prefix, c0, c1
 
 

@@ -224,7 +224,7 @@ def test_export_import_replica_traces_identically(meshes, beam_lib, cuda_device)
     assert beam_lib.bmTreeExport(t.h, *[b.data_ptr() for b in bufs]) == 0
     torch.cuda.synchronize()
     h = C.c_void_p()
-    assert beam_lib.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7]) == 0
+    assert beam_lib.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7], t.root()) == 0
     rng = np.random.default_rng(5)
     R = torch.from_numpy(_ray_batch(rng, 40000, 2.5)).to(cuda_device)
     a = hits_to_numpy(t.trace_rays(R, 0))
