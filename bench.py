@@ -274,96 +274,113 @@ def run_b200(args):
     value = float(r_sum.item()) / args.steps / (ms_per_step * 1e-3) / 1e6
 
     # --- timed: e2e through host buffers ---------------------------------------------------------------------------------
-    # Every step: the camera table comes from pinned host memory, the framebuffer and the bounce hit records go back to pinned host
-    # memory.  The frame is cut into row bands; band k+1 is uploaded and band k-1 downloaded (copy streams) while band k is traced
-    # (compute stream), so the copies hide behind the kernels instead of adding to them.
-    BANDS = args.e2e_bands if (H % args.e2e_bands == 0 and SPP == 1) else 1
-    nbnd = n // BANDS
+    # Every step: the camera table comes from pinned host memory (H2D), the framebuffer, the bounce count and the bounce hit records go
+    # back to pinned host memory (D2H).  Frames are pipelined the way a renderer streams them: DEPTH buffer sets, three streams -- the
+    # upload of frame i+1 and the download of frame i-1 run while frame i is traced.  The K steps are timed as one bracket (fill and
+    # drain included); the latency of one un-pipelined frame is reported beside it.  The L2 flush runs inside the compute stream.
+    DEPTH = 3
     s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    cntb = torch.zeros(BANDS, dtype=torch.int32, device=dev); cntb_host = torch.zeros(BANDS, dtype=torch.int32).pin_memory()
-    e2e_rays_dev = torch.empty_like(rays_dev)
+    slots = []
+    for _ in range(DEPTH if SPP == 1 else 0):
+        slots.append({"rays": torch.empty_like(rays_dev), "hits1": torch.empty_like(hits1), "pixels": torch.empty_like(pixels), "rays2": torch.empty_like(rays2),
+                      "src2": torch.empty_like(src2), "cnt": torch.zeros(1, dtype=torch.int32, device=dev), "hits2": torch.empty_like(hits2),
+                      "pix_host": torch.empty(n, dtype=torch.int32).pin_memory(), "hits2_host": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
+                      "cnt_host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev_comp": None, "ev_d2h": None, "ev_cnt": None})
 
-    def enqueue_bands(comp):
-        """all bands of one frame: H2D on s_h2d, kernels on `comp`, D2H of pixels + bounce counts on s_d2h (fork/join around comp)"""
-        s_h2d.wait_stream(comp); s_d2h.wait_stream(comp)
-        for k in range(BANDS):
-            lo, hi = k * nbnd, (k + 1) * nbnd
-            evh, evc = torch.cuda.Event(), torch.cuda.Event()
-            with torch.cuda.stream(s_h2d):
-                e2e_rays_dev[lo:hi].copy_(rays_pinned[lo:hi], non_blocking=True)
-                evh.record(s_h2d)
-            comp.wait_event(evh)
-            rp = e2e_rays_dev.data_ptr() + lo * 12
-            _lib.check(L.bmTraceCamera(tree.h, rp, nbnd, W, _f3(eye), _f9(orient), 0, hits1.data_ptr() + lo * 16, pixels.data_ptr() + lo * 4, table.data_ptr(), None), "bmTraceCamera")
+    def e2e_compute(i):
+        """upload + kernels of frame i (asynchronous)"""
+        S = slots[i % DEPTH]
+        with torch.cuda.stream(s_h2d):
+            if S["ev_comp"] is not None:
+                s_h2d.wait_event(S["ev_comp"])              # the previous frame in this slot has consumed its ray table
+            S["rays"].copy_(rays_pinned, non_blocking=True)
+            evh = torch.cuda.Event(); evh.record(s_h2d)
+        with torch.cuda.stream(stream):
+            stream.wait_event(evh)
+            if S["ev_d2h"] is not None:
+                stream.wait_event(S["ev_d2h"])              # ... and its results have left the device
+            flush.zero_()
+            _lib.check(L.bmTraceCamera(tree.h, S["rays"].data_ptr(), n, W, _f3(eye), _f9(orient), 0, S["hits1"].data_ptr(), S["pixels"].data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+            work = None
+            if world > 1:
+                work = dist.all_gather_into_tensor(gathered.view(-1), S["pixels"], async_op=True)
             if wl.bounces:
-                _lib.check(L.bmBounceRaysCamera(tree.h, rp, _f3(eye), _f9(orient), hits1.data_ptr() + lo * 16, nbnd, 0, 1, args.seed, rays2.data_ptr() + lo * 24,
-                                                src2.data_ptr() + lo * 4, cntb.data_ptr() + k * 4), "bmBounceRaysCamera")
-                _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr() + lo * 24, cntb.data_ptr() + k * 4, nbnd, 0, hits2.data_ptr() + lo * 16, None), "bmTraceRaysIndirect")
-            evc.record(comp)
-            with torch.cuda.stream(s_d2h):
-                s_d2h.wait_event(evc)
-                pix_host[lo:hi].copy_(pixels[lo:hi], non_blocking=True)
-                if wl.bounces:
-                    cntb_host[k:k + 1].copy_(cntb[k:k + 1], non_blocking=True)
-        comp.wait_stream(s_h2d); comp.wait_stream(s_d2h)
+                _lib.check(L.bmBounceRaysCamera(tree.h, S["rays"].data_ptr(), _f3(eye), _f9(orient), S["hits1"].data_ptr(), n, 0, 1, args.seed, S["rays2"].data_ptr(),
+                                                S["src2"].data_ptr(), S["cnt"].data_ptr()), "bmBounceRaysCamera")
+                _lib.check(L.bmTraceRaysIndirect(tree.h, S["rays2"].data_ptr(), S["cnt"].data_ptr(), n, 0, S["hits2"].data_ptr(), None), "bmTraceRaysIndirect")
+            if work is not None:
+                work.wait()
+            S["ev_comp"] = torch.cuda.Event(); S["ev_comp"].record(stream)
 
-    # the per-frame launch sequence is fixed, so it is captured once into a CUDA graph and replayed (removes the host launch cost
-    # of 4 bands x ~10 launches); the bounce hit records are read back after the replay, sized by the counts the graph produced
-    graph = None
-    try:
-        if SPP > 1:
-            raise RuntimeError("multi-sample frame: direct launches")
-        enqueue_bands(stream); stream.synchronize()                 # warm-up outside capture (allocations, occupancy queries)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            cs = torch.cuda.current_stream(dev)
-            tree.use_stream(cs)
-            enqueue_bands(cs)
-        tree.use_stream(stream)
-    except Exception as ex:                                          # keep the run alive; say so in the line
-        sys.stderr.write("e2e: CUDA graph capture failed (%r), falling back to direct launches\n" % (ex,))
-        graph = None
-        tree.use_stream(stream)
+    def e2e_download(i):
+        """framebuffer + bounce count of frame i to the host (asynchronous)"""
+        S = slots[i % DEPTH]
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(S["ev_comp"])
+            S["pix_host"].copy_(S["pixels"], non_blocking=True)
+            S["cnt_host"].copy_(S["cnt"], non_blocking=True)
+            S["ev_cnt"] = torch.cuda.Event(); S["ev_cnt"].record(s_d2h)
 
-    def frame_e2e():
-        if SPP > 1:
-            e2e_rays_dev.copy_(rays_pinned, non_blocking=True)
-            total = frame_spp(e2e_rays_dev)
-            pix_host.copy_(pixels, non_blocking=True)
-            stream.synchronize()
-            return total + int(cnt_host[0])
-        if graph is not None:
-            graph.replay()
-        else:
-            enqueue_bands(stream)
-        stream.synchronize()
-        total = n
-        if wl.bounces:
-            for k in range(BANDS):
-                c = int(cntb_host[k]); lo = k * nbnd
-                total += c
-                if c:
-                    hits2_host[lo:lo + c].copy_(hits2[lo:lo + c], non_blocking=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), pixels)
-        stream.synchronize()
+    def e2e_finish(i):
+        """host side of frame i: wait for its bounce count, fetch exactly that many hit records; returns the rays of the frame"""
+        S = slots[i % DEPTH]
+        S["ev_cnt"].synchronize()
+        c = int(S["cnt_host"][0]) if wl.bounces else 0
+        with torch.cuda.stream(s_d2h):
+            if c:
+                S["hits2_host"][:c].copy_(S["hits2"][:c], non_blocking=True)
+            S["ev_d2h"] = torch.cuda.Event(); S["ev_d2h"].record(s_d2h)
+        return n + c
+
+    def e2e_run(K):
+        total = 0
+        for i in range(K):
+            e2e_compute(i)
+            if i:
+                total += e2e_finish(i - 1)
+            e2e_download(i)
+        total += e2e_finish(K - 1)
+        stream.wait_event(slots[(K - 1) % DEPTH]["ev_d2h"])
         return total
-    for _ in range(2):
-        frame_e2e()
-    e2e_ms, e2e_rays = [], 0
-    for _ in range(args.steps):
-        flush.zero_()
+
+    def frame_e2e_spp():
+        e2e_rays_dev.copy_(rays_pinned, non_blocking=True)
+        total = frame_spp(e2e_rays_dev)
+        pix_host.copy_(pixels, non_blocking=True)
+        stream.synchronize()
+        return total + int(cnt_host[0])
+
+    e2e_rays = 0
+    if SPP == 1:
+        e2e_run(DEPTH + 1)                                   # warm-up (allocations, all slots touched)
+        lat = []
+        for _ in range(3):                                   # latency of one frame on its own
+            e0, e1 = ev(), ev(); sync_all(); e0.record(); e2e_run(1); e1.record(); sync_all(); lat.append(e0.elapsed_time(e1))
         e0, e1 = ev(), ev()
         sync_all()
-        e0.record(); e2e_rays += frame_e2e(); e1.record()
+        e0.record(); e2e_rays = e2e_run(args.steps); e1.record()
         sync_all()
-        e2e_ms.append(e0.elapsed_time(e1))
-    t2 = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev); r2 = torch.tensor([float(e2e_rays)], dtype=torch.float64, device=dev)
+        e2e_total_ms = e0.elapsed_time(e1)
+        e2e_latency_ms = statistics.mean(lat)
+    else:
+        e2e_rays_dev = torch.empty_like(rays_dev)
+        for _ in range(2):
+            frame_e2e_spp()
+        e2e_total_ms = 0.0
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = ev(), ev()
+            sync_all()
+            e0.record(); e2e_rays += frame_e2e_spp(); e1.record()
+            sync_all()
+            e2e_total_ms += e0.elapsed_time(e1)
+        e2e_latency_ms = e2e_total_ms / args.steps
+    t2 = torch.tensor([e2e_total_ms], dtype=torch.float64, device=dev); r2 = torch.tensor([float(e2e_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
     e2e_value = float(r2.item()) / (float(t2.item()) * 1e-3) / 1e6
-    h2d = n * 12 + 48
-    d2h = n * 4 + ((nb * 16 if wl.bounces else 0) + (4 * BANDS if wl.bounces else 0) if SPP == 1 else 4)
+    h2d = n * 12
+    d2h = n * 4 + 4 + (nb * 16 if (wl.bounces and SPP == 1) else 0)
 
     # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
     build_ms = []
@@ -443,8 +460,10 @@ def run_b200(args):
                        "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer overlapped with the bounce trace" if world > 1 else "single GPU",
                        "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
-                    "pipeline": "%d row bands; H2D of the camera table, trace and D2H of framebuffer overlap on 3 streams, %s; bounce hit records read back after, sized by the device-side counts"
-                                % (BANDS, "replayed as one CUDA graph" if graph is not None else "direct launches")},
+                    "single_frame_latency_ms": e2e_latency_ms,
+                    "pipeline": ("%d frames in flight on 3 streams (H2D of the camera table | L2 flush + trace + bounce + trace | D2H of framebuffer, bounce count and "
+                                 "bounce hit records sized by the device-side count); the K steps are one timed bracket, fill and drain included" % DEPTH) if SPP == 1
+                                else "one frame at a time: H2D of the camera table, the multi-sample frame, D2H of the framebuffer"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -673,7 +692,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5-mtris", type=float, default=100.0, help="workload c5: millions of soup triangles")
     ap.add_argument("--c5-mrays", type=float, default=16.0, help="workload c5: millions of incoherent rays per step per GPU")
-    ap.add_argument("--e2e-bands", type=int, default=1, help="row bands of the pipelined e2e frame (1 measured fastest: a trace launch has a ~0.25 ms critical path regardless of size)")
     ap.add_argument("--reference-rays", type=int, default=200_000, help="primary rays per step of the --impl reference sample")
     args = ap.parse_args()
     if args.impl == "reference":

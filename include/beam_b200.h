@@ -68,7 +68,7 @@ typedef struct { float t, u, v; uint32_t tri; } bmHit;
 
 /* BuildTree.cu:120-148. `rootNode` identifies the tree (one bmGetNodeSize() buffer per SceneTree, SceneTree.cpp:52).
  * The store / pool pointers are accepted and ignored: node, leaf and triangle storage is owned by the library because
- * the layout changed (sorted leaf ranges + 64-byte nodes instead of pointer-linked pools). Clears the staged mesh list. */
+ * the layout changed (sorted leaf ranges + 128-byte nodes instead of pointer-linked pools). Clears the staged mesh list. */
 void bmResetScene(void* rootNode, void* faceStore, void* faceGroupStore, void* nodeStore,
                   void* faces, void* facePtrs, void* nodes, uint32_t maxFaces, uint32_t maxFacePtrs, uint32_t maxNodes);
 
@@ -97,6 +97,32 @@ uint32_t bmGetFaceGroupStoreSize(void);
 /* RTClear.cu:19-31 */
 void bmClear(uint32_t* buffer, uint32_t pitch, uint32_t width, uint32_t height, uint32_t clearValue);
 
+/* Hash.cu exports re-declared by SceneHash.cpp:10-24 (TREE_TYPE == HASH, Types.h:10-13; the shipping value is TREE).
+ * `cells` identifies the scene.  The reference's hash-grid insertion and march are broken (only the
+ * first x-row of a triangle's cell range is inserted, 89 % agreement with the closest hit), so these entry points serve the
+ * scene from the same kd-tree as Part 1 over the default world box: bmMarchSpace writes the pixels bmMarch writes.
+ * The hash KEY functions are reproduced bit-exactly by bmHashKeys (Part 2). */
+void bmResetSpace(void* cells);
+void bmInsertMeshInSpace(const bmVec3* vertices, const uint32_t* indices, uint32_t numIndices, void* material, uint32_t meshIdx, void* cells);
+void bmMarchSpace(const bmVec3* initialRays, uint32_t* buffer, uint32_t pitch, uint32_t width, uint32_t height,
+                  const bmVec3* eye, const bmMat3* orient, const bmStaticMeshData* meshData, void* cells);
+uint32_t bmGetCellSize(void);          /* Hash.cu:69-89 sizeof(bmCell) = 8,208 */
+uint32_t bmGetMaxHashElements(void);   /* Hash.cu HASH_SIZE = 65,536 */
+
+/* Trace2.cu:188-228 exports re-declared by SceneProgressive.cpp:13-22 (TREE_TYPE == PROGRESSIVE).  bmMarchProgressive has an
+ * empty body in the reference and no caller; it is exported as the same no-op (`cb` is the reference's bmHitCallback function
+ * pointer).  The size getters return the reference's struct sizes.  The working progressive path is bmCameraRays /
+ * bmTraceRays / bmBounceRays / bmProgressiveAccumulate / bmProgressiveResolve below. */
+void bmMarchProgressive(void* rays, uint32_t numRays, void* rayBoxQueue, void* leafQueue, void* rayFaceQueue, void* bvhNodes,
+                        void* faceClusters, void* hitResultClusters, void* meshDataPtrs, void* cb);
+uint32_t bmGetStoreSize(void);
+uint32_t bmGetFaceClusterSize(void);
+uint32_t bmGetBvhNodeSize(void);
+uint32_t bmGetRaySize(void);
+uint32_t bmGetRayBoxSize(void);
+uint32_t bmGetRayFaceSize(void);
+uint32_t bmRayFaceHitClusterSize(void);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Part 2 -- explicit handle-based entry points (same kernels).
  * ------------------------------------------------------------------------------------------------------------------ */
@@ -119,7 +145,7 @@ void bmTreeDestroy(bmTree* tree);
 int  bmTreeSetStream(bmTree* tree, void* cudaStream);          /* cudaStream_t; default 0 */
 int  bmTreeReset(bmTree* tree);                                /* forget staged meshes (bmResetScene) */
 int  bmTreeAddMesh(bmTree* tree, const float* d_positions, const uint32_t* d_indices, uint32_t numIndices, uint32_t meshIdx);
-/* keys -> sort -> leaves -> radix tree -> refit -> 64-byte nodes. Asynchronous on the tree's stream except for two
+/* keys -> sort -> leaves -> one bottom-up pass (radix tree + tight boxes) -> 128-byte nodes. Asynchronous on the tree's stream except for two
  * 8-byte read-backs (pair and leaf counts) that size the later stages. */
 int  bmTreeBuild(bmTree* tree);
 int  bmBuildTree(void* treeRootNode);                          /* same, for a tree made through Part 1 */

@@ -40,4 +40,23 @@ HOSTOBJS=("$TMP/DeviceBuffer.o" "$TMP/Mesh.o" "$TMP/Scene.o" "$TMP/SceneTree.o" 
 nvcc -shared -ccbin g++ -o "$OUT/libbeam_refhost_b200.so" "${HOSTOBJS[@]}" -L"$(dirname "$LIBB200")" -lbeam_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../raytracercuda_b200'
 # (2) reference host over the reference's own kernels
 nvcc -shared -ccbin g++ -o "$OUT/libbeam_refcuda.so" "${HOSTOBJS[@]}" "$TMP/BuildTree.o" "$TMP/RTClear.o"
-echo "built $OUT/libbeam_refhost_b200.so $OUT/libbeam_refcuda.so"
+# (3) the reference host compiled with TREE_TYPE HASH / PROGRESSIVE (Types.h:13 patched in a scratch copy only): SceneHash.cpp and
+#     SceneProgressive.cpp then bind bmResetSpace / bmInsertMeshInSpace / bmMarchSpace / bmGetCellSize / bmGetMaxHashElements and the
+#     Trace2.cu size getters, all of which libbeam_b200.so exports as well.
+for variant in HASH PROGRESSIVE; do
+  V="$TMP/$variant"; mkdir -p "$V"
+  for f in "$TMP"/*; do b="$(basename "$f")"; [ -d "$f" ] && continue; case "$b" in *.o|Types.h) continue;; esac; ln -s "$(readlink -f "$f")" "$V/$b"; done
+  sed "s/^#define TREE_TYPE .*/#define TREE_TYPE          $variant/" "$REF/Raytracer/Types.h" > "$V/Types.h"
+  grep -q "^#define TREE_TYPE          $variant" "$V/Types.h"
+  NVV=(nvcc -x cu -gencode arch=compute_100a,code=sm_100a -std=c++17 -O2 -w -Xcompiler -fPIC -ccbin g++ -D__int32=int -D__int64=long -DNDEBUG
+       -DGLM_FORCE_UNRESTRICTED_GENTYPE -I"$V" -I"$REF/3rdParty/glm-0.9.9.0/glm" -include cstdio)   # SceneProgressive.cpp uses printf without <cstdio> (MSVC pulls it in)
+  for src in DeviceBuffer.cpp Mesh.cpp Scene.cpp SceneTree.cpp SceneHash.cpp SceneProgressive.cpp Camera.cpp Util.cpp; do
+    "${NVV[@]}" -c "$V/$src" -o "$V/${src%.*}.o" &
+  done
+  "${NVV[@]}" -c "$HERE/ref_headless_rt.cpp" -o "$V/ref_headless_rt.o" &
+  "${NVV[@]}" -c "$HERE/ref_gpu_driver.cpp" -o "$V/ref_gpu_driver.o" &
+  wait
+  lower="$(echo "$variant" | tr A-Z a-z)"
+  nvcc -shared -ccbin g++ -o "$OUT/libbeam_refhost_${lower}_b200.so" "$V"/*.o -L"$(dirname "$LIBB200")" -lbeam_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../raytracercuda_b200'
+done
+echo "built $OUT/libbeam_refhost_b200.so $OUT/libbeam_refhost_hash_b200.so $OUT/libbeam_refhost_progressive_b200.so $OUT/libbeam_refcuda.so"

@@ -18,6 +18,8 @@ ERROR_NAMES = {0: "ERROR_ALL_FINE", 1: "ERROR_NO_VERTICES", 2: "ERROR_INVALID_PA
 ABI_SYMBOLS = [
     "bmResetScene", "bmInsertMeshInTree", "bmMarch", "bmGetFaceSize", "bmGetFacePtrSize", "bmGetMaterialSize", "bmGetNodeSize",
     "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
+    "bmResetSpace", "bmInsertMeshInSpace", "bmMarchSpace", "bmGetCellSize", "bmGetMaxHashElements",
+    "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
     "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot",
     "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve",
@@ -94,6 +96,13 @@ def load() -> C.CDLL:
     L.bmMarch.argtypes = [vp, C.POINTER(bmVec3), C.POINTER(bmVec3), vp, vp, u32, u32, u32, C.POINTER(bmVec3), C.POINTER(bmMat3), vp]
     L.bmMarch.restype = None
     L.bmClear.argtypes = [vp, u32, u32, u32, u32]; L.bmClear.restype = None
+    L.bmResetSpace.argtypes = [vp]; L.bmResetSpace.restype = None
+    L.bmInsertMeshInSpace.argtypes = [vp, vp, u32, vp, u32, vp]; L.bmInsertMeshInSpace.restype = None
+    L.bmMarchSpace.argtypes = [vp, vp, u32, u32, u32, C.POINTER(bmVec3), C.POINTER(bmMat3), vp, vp]; L.bmMarchSpace.restype = None
+    L.bmMarchProgressive.argtypes = [vp, u32] + [vp] * 8; L.bmMarchProgressive.restype = None
+    for n in ("bmGetCellSize", "bmGetMaxHashElements", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize",
+              "bmGetRayFaceSize", "bmRayFaceHitClusterSize"):
+        getattr(L, n).restype = u32
     for n in ("bmGetFaceSize", "bmGetFacePtrSize", "bmGetMaterialSize", "bmGetNodeSize", "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize"):
         getattr(L, n).restype = u32
     f = C.c_float

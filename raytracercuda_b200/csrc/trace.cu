@@ -1,4 +1,4 @@
-// trace.cu -- ray / triangle closest-hit traversal of the 64-byte-node radix tree (replaces bmMarchKernel, BuildTree.cu:367-499),
+// trace.cu -- ray / triangle closest-hit traversal of the 128-byte-node radix tree (replaces bmMarchKernel, BuildTree.cu:367-499),
 // the pixel shade of BuildTree.cu:486-496, bmClear (RTClear.cu) and the spatial-hash key kernel (Hash.cu:17-64).
 //
 // BM_TRACE_REFERENCE reproduces the reference's traversal decisions on the contracted tree:

@@ -38,6 +38,11 @@ def test_reference_struct_sizes(beam_lib):
     from raytracercuda_b200 import _lib
     assert C.sizeof(_lib.bmStaticMeshData) == 136 and C.sizeof(_lib.bmVec3) == 12 and C.sizeof(_lib.bmMat3) == 36
     assert (beam_lib.bmGetFaceSize(), beam_lib.bmGetNodeSize(), beam_lib.bmGetFacePtrSize(), beam_lib.bmGetMaterialSize()) == (32, 32, 8, 4)
+    # SURVEY.md section 8c struct sizes (LP64) behind the HASH and PROGRESSIVE seams
+    L = beam_lib
+    assert (L.bmGetCellSize(), L.bmGetMaxHashElements()) == (8208, 65536)
+    assert (L.bmGetStoreSize(), L.bmGetFaceClusterSize(), L.bmGetBvhNodeSize(), L.bmGetRaySize(), L.bmGetRayBoxSize(), L.bmGetRayFaceSize(),
+            L.bmRayFaceHitClusterSize()) == (16, 512, 32, 24, 16, 16, 392)
 
 
 def test_no_cpu_fallback(beam_lib):

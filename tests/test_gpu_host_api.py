@@ -114,6 +114,14 @@ def test_reference_symbols_direct(meshes, golden, beam_lib, cuda_device):
     L.bmClear(buf.data_ptr(), 800, 200, 200, 7)
     torch.cuda.synchronize()
     assert (buf.cpu().numpy() == 7).all()
+    # SceneHash.cpp's call sequence (TREE_TYPE == HASH): the scene is keyed by `cells` and renders the same pixels
+    cells = torch.zeros(64, dtype=torch.uint8, device=dev)
+    L.bmResetSpace(cells.data_ptr())
+    L.bmInsertMeshInSpace(Pd.data_ptr(), Id.data_ptr(), Id.numel(), None, 0, cells.data_ptr())
+    L.bmMarchSpace(rays.data_ptr(), buf.data_ptr(), 800, 200, 200, C.byref(eye), C.byref(orient), table.data_ptr(), cells.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy().view(np.uint32), want)
+    L.bmMarchProgressive(None, 0, None, None, None, None, None, None, None, None)      # empty in the reference too (Trace2.cu:188-215)
     # an unknown root (nothing inserted) renders the miss colour
     root2 = torch.zeros(32, dtype=torch.uint8, device=dev)
     L.bmMarch(root2.data_ptr(), C.byref(lo), C.byref(hi), rays.data_ptr(), buf.data_ptr(), 800, 200, 200, C.byref(eye), C.byref(orient), table.data_ptr())

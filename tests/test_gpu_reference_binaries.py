@@ -34,6 +34,36 @@ def test_unmodified_reference_host_over_b200_kernels(name, meshes, beam_lib, cud
     s.close()
 
 
+@pytest.mark.skipif(not RefGpuScene.available("refhost_hash_b200"), reason="oracle/_ref/libbeam_refhost_hash_b200.so not built")
+def test_reference_host_hash_scene_over_b200_kernels(meshes, beam_lib, cuda_device):
+    """The reference host compiled with TREE_TYPE HASH (Types.h:13): SceneHash.cpp binds bmResetSpace / bmInsertMeshInSpace /
+    bmMarchSpace / bmGetCellSize / bmGetMaxHashElements.  The library serves that seam from the kd-tree, so the image is the
+    SceneTree image (the reference's own hash march is broken)."""
+    P, I, N = meshes["suzanne"]
+    s = RefGpuScene("refhost_hash_b200")
+    s.add_mesh(P, I, N)
+    s.build()
+    s.camera(200, 200)
+    s.trace(EYE, ID3)
+    want = np.load(os.path.join(GOLDEN, "pixels_suzanne_200x200.npz"))["pixels"]
+    assert np.array_equal(s.pixels(), want)
+    s.close()
+
+
+@pytest.mark.skipif(not RefGpuScene.available("refhost_progressive_b200"), reason="oracle/_ref/libbeam_refhost_progressive_b200.so not built")
+def test_reference_host_progressive_scene_links(meshes, beam_lib, cuda_device):
+    """TREE_TYPE PROGRESSIVE: SceneProgressive.cpp is an empty stub that only calls the Trace2.cu size getters; it must link and run
+    against the library and, like the reference, draw nothing (the frame keeps the cleared value)."""
+    P, I, N = meshes["f16"]
+    s = RefGpuScene("refhost_progressive_b200")
+    s.add_mesh(P, I, N)
+    s.build()
+    s.camera(64, 64)
+    s.trace(EYE, ID3)
+    assert (s.pixels() == 0).all()
+    s.close()
+
+
 @pytest.mark.skipif(not RefGpuScene.available("refcuda"), reason="oracle/_ref/libbeam_refcuda.so not built")
 @pytest.mark.parametrize("name", ["f16", "suzanne", "bunny"])
 def test_reference_cuda_kernels_on_b200(name, cuda_device):
