@@ -99,6 +99,29 @@ def cpu_model():
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
+def bind_near_gpu(index):
+    """Pin this process to the CPU cores of the GPU's NUMA node (NVML's ideal affinity) BEFORE any pinned host buffer is allocated:
+    first-touch then places the staging buffers on the socket the GPU hangs off, so the H2D / D2H copies of N ranks do not cross the
+    inter-socket link.  Best effort; returns a short description for the bench line."""
+    if os.environ.get("BENCH_NO_AFFINITY"):
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus near gpu %d" % (len(cpus), phys)
+    except Exception as ex:
+        return "unavailable (%s)" % type(ex).__name__
+    return "unavailable"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -107,6 +130,7 @@ def run_b200(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (the product has no CPU path)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = bind_near_gpu(local)
     # libraries (NCCL's version banner) must not write to stdout: the driver reads ONE JSON line there
     sys.stdout.flush()
     saved_stdout = os.dup(1)
@@ -186,38 +210,58 @@ def run_b200(args):
             dist.all_gather_into_tensor(gathered.view(-1), pixels)
         return n * SPP
 
-    def frame(rays_in, marks=None):
-        """one step on the device; returns rays traced by this rank (bounce rays are added by bounce_count())"""
+    # The frame is issued as NB row bands on NB streams (each through its own view of the tree): the traversal kernels are persistent
+    # grids with a long tail (a few grazing rays), and the tail of one band is filled by the other bands' work.  NB = 1 is one launch.
+    NB = args.bands if (SPP == 1 and H % args.bands == 0) else 1
+    nbnd = n // NB
+    band_streams = [torch.cuda.Stream(dev) for _ in range(NB)] if NB > 1 else [stream]
+    band_trees = [tree.view(band_streams[k]) for k in range(NB)] if NB > 1 else [tree]
+    cntb = torch.zeros(NB, dtype=torch.int32, device=dev); cntb_host = torch.zeros(NB, dtype=torch.int32).pin_memory()
+
+    def frame(rays_in, marks=None, out=None):
+        """one step on the device; returns the primary rays traced by this rank (bounce rays are added by bounce_count())"""
         if SPP > 1:
             if marks is not None:
                 for m_ in marks: m_.record()
             return frame_spp(rays_in)
+        o_hits1, o_pixels, o_rays2, o_src2, o_hits2, o_cnt, o_cnt_host = out if out is not None else (hits1, pixels, rays2, src2, hits2, cntb, cntb_host)
         if marks is not None: marks[0].record()
-        _lib.check(L.bmTraceCamera(tree.h, rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
-        if marks is not None: marks[1].record()
-        total = n
+        ev0 = torch.cuda.Event(); ev0.record(stream)
+        prim_done = []
+        for k in range(NB):
+            lo = k * nbnd; bs = band_streams[k]; bt = band_trees[k]
+            if NB > 1: bs.wait_event(ev0)
+            _lib.check(L.bmTraceCamera(bt.h, rays_in.data_ptr() + lo * 12, nbnd, W, _f3(eye), _f9(orient), 0, o_hits1.data_ptr() + lo * 16, o_pixels.data_ptr() + lo * 4,
+                                       table.data_ptr(), None), "bmTraceCamera")
+            if marks is not None and NB == 1: marks[1].record()
+            if world > 1:
+                e_ = torch.cuda.Event(); e_.record(bs); prim_done.append(e_)
+            if wl.bounces:
+                _lib.check(L.bmBounceRaysCamera(bt.h, rays_in.data_ptr() + lo * 12, _f3(eye), _f9(orient), o_hits1.data_ptr() + lo * 16, nbnd, 0, 1, args.seed,
+                                                o_rays2.data_ptr() + lo * 24, o_src2.data_ptr() + lo * 4, o_cnt.data_ptr() + k * 4), "bmBounceRaysCamera")
+                if marks is not None and NB == 1: marks[2].record()
+                # the bounce count stays on the device: the trace kernel reads it there (no host round trip inside the step)
+                _lib.check(L.bmTraceRaysIndirect(bt.h, o_rays2.data_ptr() + lo * 24, o_cnt.data_ptr() + k * 4, nbnd, 0, o_hits2.data_ptr() + lo * 16, None), "bmTraceRaysIndirect")
+            if NB > 1:
+                e_ = torch.cuda.Event(); e_.record(bs); stream.wait_event(e_)
         work = None
         if world > 1:
-            # the framebuffer is final once the primary launch is done: gather it on a side stream while the bounce rays are traced
-            evp = torch.cuda.Event(); evp.record(stream)
+            # the framebuffer is final once the primary launches are done: gather it on a side stream while the bounce rays are traced
             with torch.cuda.stream(comm):
-                comm.wait_event(evp)
-                work = dist.all_gather_into_tensor(gathered.view(-1), pixels, async_op=True)
+                for e_ in prim_done: comm.wait_event(e_)
+                work = dist.all_gather_into_tensor(gathered.view(-1), o_pixels, async_op=True)
         if wl.bounces:
-            _lib.check(L.bmBounceRaysCamera(tree.h, rays_in.data_ptr(), _f3(eye), _f9(orient), hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(),
-                                            src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
-            if marks is not None: marks[2].record()
-            # the bounce count stays on the device: the trace kernel reads it there (no host round trip inside the step)
-            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, 0, hits2.data_ptr(), None), "bmTraceRaysIndirect")
-            cnt_host.copy_(cnt2, non_blocking=True)
+            o_cnt_host.copy_(o_cnt, non_blocking=True)
         if marks is not None: marks[3].record()
         if work is not None:
             work.wait()                    # the step ends when the gathered frame is complete
-        return total
+        return n
 
     def bounce_count():
         stream.synchronize()
-        return int(cnt_host[0]) if wl.bounces else 0
+        if SPP > 1:
+            return int(cnt_host[0]) if wl.bounces else 0
+        return int(cntb_host.sum()) if wl.bounces else 0
 
     import ctypes as C
     _f3 = lambda a: (C.c_float * 3)(*[float(x) for x in a])
@@ -237,7 +281,17 @@ def run_b200(args):
     _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
     torch.cuda.synchronize(dev)
     V1, K1, C1, LONG1 = [int(x) for x in cnt.cpu()]
-    nb = int(cnt_host[0]) if wl.bounces else 0
+    def whole_frame_bounce_list():
+        """the frame's bounce rays as ONE compacted list in rays2 / src2 (the banded step leaves one list per band)"""
+        _lib.check(L.bmBounceRaysCamera(tree.h, rays_dev.data_ptr(), _f3(eye), _f9(orient), hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(),
+                                        src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
+        torch.cuda.synchronize(dev)
+        return int(cnt2.cpu()[0])
+    if SPP == 1:
+        nb = whole_frame_bounce_list() if wl.bounces else 0
+        assert nb == (int(cntb_host.sum()) if wl.bounces else 0), "band lists and the whole-frame list disagree"
+    else:
+        nb = int(cnt_host[0]) if wl.bounces else 0
     V2 = K2 = C2 = 0
     nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST sample only
     if nb_last and SPP == 1:
@@ -262,8 +316,8 @@ def run_b200(args):
         e1.record()
         sync_all()
         total_rays += bounce_count()
-        step_ms.append(e0.elapsed_time(e1)); prim_ms.append(marks[0].elapsed_time(marks[1]))
-        bounce_ms.append(marks[2].elapsed_time(marks[3]) if wl.bounces else 0.0)
+        step_ms.append(e0.elapsed_time(e1)); prim_ms.append(marks[0].elapsed_time(marks[1]) if (NB == 1 or SPP > 1) else 0.0)
+        bounce_ms.append(marks[2].elapsed_time(marks[3]) if (wl.bounces and (NB == 1 or SPP > 1)) else 0.0)
     clocks = sampler.stop()
     launches = L.bmLaunchCount() - launches0
     # max over ranks of the summed step time; rays summed over ranks
@@ -283,9 +337,10 @@ def run_b200(args):
     slots = []
     for _ in range(DEPTH if SPP == 1 else 0):
         slots.append({"rays": torch.empty_like(rays_dev), "hits1": torch.empty_like(hits1), "pixels": torch.empty_like(pixels), "rays2": torch.empty_like(rays2),
-                      "src2": torch.empty_like(src2), "cnt": torch.zeros(1, dtype=torch.int32, device=dev), "hits2": torch.empty_like(hits2),
+                      "src2": torch.empty_like(src2), "cnt": torch.zeros(NB, dtype=torch.int32, device=dev), "hits2": torch.empty_like(hits2),
                       "pix_host": torch.empty(n, dtype=torch.int32).pin_memory(), "hits2_host": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
-                      "cnt_host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev_comp": None, "ev_d2h": None, "ev_cnt": None})
+                      "cnt_host": torch.zeros(NB, dtype=torch.int32).pin_memory(), "cnt_scratch": torch.zeros(NB, dtype=torch.int32).pin_memory(),
+                      "ev_comp": None, "ev_d2h": None, "ev_cnt": None})
 
     def e2e_compute(i):
         """upload + kernels of frame i (asynchronous)"""
@@ -300,16 +355,7 @@ def run_b200(args):
             if S["ev_d2h"] is not None:
                 stream.wait_event(S["ev_d2h"])              # ... and its results have left the device
             flush.zero_()
-            _lib.check(L.bmTraceCamera(tree.h, S["rays"].data_ptr(), n, W, _f3(eye), _f9(orient), 0, S["hits1"].data_ptr(), S["pixels"].data_ptr(), table.data_ptr(), None), "bmTraceCamera")
-            work = None
-            if world > 1:
-                work = dist.all_gather_into_tensor(gathered.view(-1), S["pixels"], async_op=True)
-            if wl.bounces:
-                _lib.check(L.bmBounceRaysCamera(tree.h, S["rays"].data_ptr(), _f3(eye), _f9(orient), S["hits1"].data_ptr(), n, 0, 1, args.seed, S["rays2"].data_ptr(),
-                                                S["src2"].data_ptr(), S["cnt"].data_ptr()), "bmBounceRaysCamera")
-                _lib.check(L.bmTraceRaysIndirect(tree.h, S["rays2"].data_ptr(), S["cnt"].data_ptr(), n, 0, S["hits2"].data_ptr(), None), "bmTraceRaysIndirect")
-            if work is not None:
-                work.wait()
+            frame(S["rays"], None, out=(S["hits1"], S["pixels"], S["rays2"], S["src2"], S["hits2"], S["cnt"], S["cnt_scratch"]))
             S["ev_comp"] = torch.cuda.Event(); S["ev_comp"].record(stream)
 
     def e2e_download(i):
@@ -325,12 +371,15 @@ def run_b200(args):
         """host side of frame i: wait for its bounce count, fetch exactly that many hit records; returns the rays of the frame"""
         S = slots[i % DEPTH]
         S["ev_cnt"].synchronize()
-        c = int(S["cnt_host"][0]) if wl.bounces else 0
+        total = n
         with torch.cuda.stream(s_d2h):
-            if c:
-                S["hits2_host"][:c].copy_(S["hits2"][:c], non_blocking=True)
+            for k in range(NB if wl.bounces else 0):
+                c = int(S["cnt_host"][k]); lo = k * nbnd
+                total += c
+                if c:
+                    S["hits2_host"][lo:lo + c].copy_(S["hits2"][lo:lo + c], non_blocking=True)
             S["ev_d2h"] = torch.cuda.Event(); S["ev_d2h"].record(s_d2h)
-        return n + c
+        return total
 
     def e2e_run(K):
         total = 0
@@ -380,7 +429,7 @@ def run_b200(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
     e2e_value = float(r2.item()) / (float(t2.item()) * 1e-3) / 1e6
     h2d = n * 12
-    d2h = n * 4 + 4 + (nb * 16 if (wl.bounces and SPP == 1) else 0)
+    d2h = n * 4 + 4 * NB + (nb * 16 if (wl.bounces and SPP == 1) else 0)
 
     # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
     build_ms = []
@@ -425,8 +474,8 @@ def run_b200(args):
 
     # --- roofline of the dominant kernel: the primary-ray trace launch ---------------------------------------------------
     pms = statistics.mean(prim_ms)
-    if SPP > 1:
-        # multi-sample frames interleave many launches: time the dominant kernel (one camera launch of the frame's rays) on its own
+    if SPP > 1 or NB > 1:
+        # multi-sample / banded frames interleave launches: time the dominant kernel (one camera launch of the frame's rays) on its own
         tt = []
         for _ in range(5):
             flush.zero_(); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
@@ -448,6 +497,12 @@ def run_b200(args):
     except Exception:
         pass
     if wl.bounces and nb and SPP == 1:
+        if NB > 1:
+            bounce_ms = []
+            for _ in range(5):
+                flush.zero_(); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
+                _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), None), "bmTraceRays")
+                e1.record(); torch.cuda.synchronize(dev); bounce_ms.append(e0.elapsed_time(e1))
         bms2 = statistics.mean(bounce_ms)
         roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb / (bms2 * 1e-3) / 1e6, "rays": nb,
                                      "node_visits_per_ray": V2 / nb, "tri_tests_per_ray": K2 / nb, "cluster_boxes_per_ray": C2 / nb,
@@ -456,7 +511,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "rays_per_step_per_gpu": rays_step, "primary_rays_per_gpu": n * SPP, "bounce_rays_per_gpu": nb, "samples_per_pixel": SPP,
-                       "trace_mode": "reference semantics (BM_TRACE_REFERENCE)", "l2": "flushed between timed steps (256 MiB write)",
+                       "trace_mode": "reference semantics (BM_TRACE_REFERENCE)", "l2": "flushed between timed steps (256 MiB write)", "bands": NB, "cpu_affinity": numa,
                        "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer overlapped with the bounce trace" if world > 1 else "single GPU",
                        "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
@@ -467,6 +522,8 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if SPP == 1 and wl.bounces:
+            whole_frame_bounce_list()
         line["cpu_baseline"] = cpu_baseline(wl, rays_pinned.numpy(), rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
@@ -689,6 +746,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--bands", type=int, default=1, help="row bands of a frame issued concurrently on as many streams (tail filling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5-mtris", type=float, default=100.0, help="workload c5: millions of soup triangles")
     ap.add_argument("--c5-mrays", type=float, default=16.0, help="workload c5: millions of incoherent rays per step per GPU")

@@ -173,6 +173,10 @@ int  bmTreeExport(const bmTree* tree, void* d_nodes, void* d_leaves, void* d_ltr
 int  bmTreeRoot(const bmTree* tree, uint32_t* root);           /* reference of the root: node index, or 0x80000000 | 0 when the only leaf is the root */
 int  bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
                   uint64_t numLeaves, uint64_t numPairs, uint64_t numTris, uint32_t root);
+/* A second, read-only handle on the arrays of a built tree (no copy) with its own stream (bmTreeSetStream), work counter and bounce
+ * scratch: launches issued through different views of one tree may run concurrently, e.g. the two halves of a frame on two streams so
+ * that the tail of one half's traversal is filled by the other half's work.  Valid until `tree` is rebuilt or destroyed. */
+int  bmTreeView(const bmTree* tree, bmTree** out);
 
 /* Explicit ray batch -> hit records. d_counters (nullable, FOUR uint64) accumulates {node + leaf visits, triangle tests, cluster
  * boxes tested} (the traversal work behind the bytes-per-ray roofline model) and keeps in [3] the largest number of such steps any

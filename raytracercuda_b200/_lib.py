@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbeam_b200.so")
+LIB_PATH = os.environ.get("BEAM_B200_LIB") or os.path.join(HERE, "libbeam_b200.so")      # override: A/B runs of kernel variants
 
 BM_OK = 0
 BM_TRACE_REFERENCE = 0
@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "bmResetSpace", "bmInsertMeshInSpace", "bmMarchSpace", "bmGetCellSize", "bmGetMaxHashElements",
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
-    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView",
     "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     L.bmTreeExport.argtypes = [vp, vp, vp, vp, vp, vp]
     L.bmTreeImport.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, u64, u64, u64, u32]
     L.bmTreeRoot.argtypes = [vp, C.POINTER(u32)]
+    L.bmTreeView.argtypes = [vp, C.POINTER(vp)]
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]
     L.bmTraceCamera.argtypes = [vp, vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
     L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]

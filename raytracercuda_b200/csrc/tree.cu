@@ -347,6 +347,25 @@ extern "C" int bmTreeImport(bmTree** out, const void* d_nodes, const void* d_lea
     return BM_OK;
 }
 
+// A second handle on the arrays of a built tree with its own stream, work counter and bounce scratch: launches issued through
+// different views of one tree may run concurrently (the traversal only reads the arrays).
+extern "C" int bmTreeView(const bmTree* src, bmTree** out)
+{
+    if (!src || !out) return BM_ERROR_INVALID_PARAMETER;
+    if (!src->built) return BM_ERROR_NOT_BUILT;
+    uint64_t sz[8];
+    BM_TRY(bmTreeArraySizes(src, sz));
+    bmTree* t = nullptr;
+    BM_TRY(bmTreeCreate(&t, src->hgrid.wmin, src->hgrid.wmax, 0.f, 0));
+    t->L = src->L; t->P = src->P; t->T = src->T; t->meshBase = src->meshBase; t->maxLeaf = src->maxLeaf; t->overLeaves = src->overLeaves;
+    t->nodes.adopt(src->nodes.p, sz[0]); t->leaves.adopt(src->leaves.p, sz[1]); t->ltris.adopt(src->ltris.p, sz[2]);
+    t->clusters.adopt(src->clusters.p, sz[3]); t->soup.adopt(src->soup.p, sz[4]); t->rootDev.adopt(src->rootDev.p, 16);
+    t->stream = src->stream;
+    t->built = true; t->imported = true;
+    *out = t;
+    return BM_OK;
+}
+
 extern "C" int bmTraceRays(bmTree* t, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters)
 {
     if (!t || (!d_rays && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;

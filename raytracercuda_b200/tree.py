@@ -149,6 +149,17 @@ class Tree:
                                   count.data_ptr()), "bmBounceRays")
         return out, src, count
 
+    def view(self, stream: torch.cuda.Stream = None) -> "Tree":
+        """bmTreeView: a second handle on this built tree (no copy) with its own stream and scratch, for concurrent launches"""
+        out = Tree.__new__(Tree)
+        out.L = self.L; out.device = self.device; out._meshes = []
+        h = C.c_void_p()
+        check(self.L.bmTreeView(self.h, C.byref(h)), "bmTreeView")
+        out.h = h
+        out._source = self                   # the arrays belong to the source tree
+        out.use_stream(stream if stream is not None else torch.cuda.current_stream(self.device))
+        return out
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
             self.L.bmTreeDestroy(self.h)
