@@ -54,6 +54,11 @@ typedef struct {
     uint32_t  m_numIndices;
 } bmStaticMeshData;
 
+/* SharedTypes.h:20-23 bmMaterial {int texture}: one per mesh; texture = index into the texture table, < 0 = none. */
+typedef struct { int texture; } bmMaterial;
+/* A texture of the table bmShadeHits reads: width*height device texels 0x00RRGGBB, row 0 = top of the image. */
+typedef struct { const uint32_t* texels; uint32_t width, height; } bmTexture;
+
 /* Trace2.cu:45-48 bmRay {o, d}: 24 bytes.  Explicit ray batches use this record. */
 typedef struct { float o[3]; float d[3]; } bmRay;
 
@@ -214,6 +219,15 @@ int  bmBounceRaysCamera(bmTree* tree, const float* d_initialRays3, const float* 
 int  bmProgressiveAccumulate(const bmHit* d_hits1, uint64_t numRays, const bmHit* d_hits2, const uint32_t* d_src2, const uint32_t* d_count2,
                              float ambient, float* d_accum, uint32_t* d_covered, void* cudaStream);
 int  bmProgressiveResolve(const float* d_accum, const uint32_t* d_covered, uint64_t numRays, uint32_t samples, uint32_t* d_pixels, void* cudaStream);
+
+/* Deferred shading of hit records (what the reference's bmHitCallback / bmMaterial / VERTEX_DATA_UV1 declare but never implement,
+ * SharedTypes.h:20-37, Beam.h:21): miss -> 255<<8; hit on a mesh without texture or UV slot -> the reference's pixel
+ * (u32)|n.z*255| << 16 (BuildTree.cu:486-496, bit for bit what bmTraceCamera writes); hit on a textured mesh (d_materials[mesh].texture
+ * in [0, numTextures), UV in vertex-data slot 2 with >= 2 components) -> nearest texel at the interpolated uv (repeat wrap, v up),
+ * every channel scaled by |n.z|, packed 0x00RRGGBB.  d_materials may be null (no mesh textured).  Needs the tree for the
+ * triangle id -> (mesh, face) mapping; runs on the tree's stream. */
+int  bmShadeHits(bmTree* tree, const bmHit* d_hits, uint64_t numRays, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials,
+                 const bmTexture* d_textures, uint32_t numTextures, uint32_t* d_pixels);
 
 /* Spatial-hash key functions of Hash.cu:17-64 evaluated on the device (bit-exact targets):
  * out[i] = bmHash3(make_uint3(bmMap(x), bmMap(y), bmMap(z))) and the three bmMap cell coordinates. */

@@ -6,6 +6,7 @@
 //     (RenderTarget.cpp:53-83);
 //   * IRenderTarget::readPixels copies the framebuffer to the host (the viewer's GL present path is out of scope);
 //   * buffer sizes are size_t (the reference's u32 DeviceBuffer caps at 4 GiB, DeviceBuffer.h:9);
+//   * IMesh::setTexture + ICamera::traceSceneTextured: the UV / material path named by Beam.h:21 and SharedTypes.h:20-23;
 //   * ICamera::traceSceneHits also returns hit records (t, u, v, triangle) -- the reference only ever wrote pixels.
 #pragma once
 #include <cstddef>
@@ -54,6 +55,9 @@ namespace Beam
         static sptr<IMesh> create();
         virtual u32 setVertexData(const float* vertices, u32 numVertices, u32 numComponents, u32 slotId, bool asyncCopy = false) = 0;
         virtual u32 setIndices(const u32* indices, u32 numIndices, bool asyncCopy = false) = 0;
+        // the mesh's material texture (bmMaterial{int texture}, SharedTypes.h:20-23, has no setter in the reference): width*height
+        // host texels 0x00RRGGBB, row 0 = top of the image; sampled through the UVs in slot VERTEX_DATA_UV1 by traceSceneTextured
+        virtual u32 setTexture(const u32* texels, u32 width, u32 height) = 0;
         virtual wptr<IScene> scene() const = 0;
     };
 
@@ -77,6 +81,9 @@ namespace Beam
         virtual u32 traceScene(const float* eye3, const float* orient3x3, sptr<IScene>& scene) = 0;
         // same trace, additionally (or instead: no render target needed when hostHits only) hit records copied to the host
         virtual u32 traceSceneHits(const float* eye3, const float* orient3x3, sptr<IScene>& scene, bmHit* hostHits) = 0;
+        // traceScene with the material path the reference declares but never implements: textured meshes show their texture
+        // scaled by |n.z|, untextured ones the reference's pixel (bmShadeHits in beam_b200.h states the rule)
+        virtual u32 traceSceneTextured(const float* eye3, const float* orient3x3, sptr<IScene>& scene) = 0;
         // what the reference's SceneProgressive (an empty stub, SceneProgressive.cpp:27-77) set out to do: `samples` jittered primary
         // rays per pixel, one diffuse bounce ray per hit, accumulated and resolved into the locked render target
         virtual u32 traceSceneProgressive(const float* eye3, const float* orient3x3, sptr<IScene>& scene, u32 samples, u32 seed, u64* raysTraced = nullptr) = 0;

@@ -18,6 +18,7 @@ void*    beamMeshCreate(void);                                    /* IMesh::crea
 void     beamMeshDestroy(void* mesh);
 uint32_t beamMeshSetVertexData(void* mesh, const float* hostData, uint32_t numVertices, uint32_t numComponents, uint32_t slotId, int asyncCopy);
 uint32_t beamMeshSetIndices(void* mesh, const uint32_t* hostIndices, uint32_t numIndices, int asyncCopy);
+uint32_t beamMeshSetTexture(void* mesh, const uint32_t* hostTexels, uint32_t width, uint32_t height);   /* IMesh::setTexture: 0x00RRGGBB, row 0 = top */
 void*    beamCameraCreate(void);                                  /* ICamera::create() */
 void     beamCameraDestroy(void* camera);
 uint32_t beamCameraSetInitialRays(void* camera, uint32_t width, uint32_t height, float left, float right, float top, float bottom, float zoom);
@@ -25,6 +26,7 @@ uint32_t beamCameraCopyInitialRays(void* camera, float* host3);   /* the directi
 uint32_t beamCameraClear(void* camera, uint32_t value);
 uint32_t beamCameraTraceScene(void* camera, const float* eye3, const float* orient3x3, void* scene);
 uint32_t beamCameraTraceSceneHits(void* camera, const float* eye3, const float* orient3x3, void* scene, bmHit* hostHits);
+uint32_t beamCameraTraceSceneTextured(void* camera, const float* eye3, const float* orient3x3, void* scene);   /* ICamera::traceSceneTextured */
 uint32_t beamCameraTraceSceneProgressive(void* camera, const float* eye3, const float* orient3x3, void* scene, uint32_t samples, uint32_t seed,
                                          uint64_t* raysTraced /* nullable */);
 void*    beamRenderTargetCreateHeadless(uint32_t width, uint32_t height, uint32_t pitch);
@@ -47,7 +49,15 @@ const float*    beamObjNormals(void* obj);                            /* numVert
 uint32_t        beamObjMeshNumIndices(void* obj, uint32_t mesh);
 const uint32_t* beamObjMeshIndices(void* obj, uint32_t mesh);
 const char*     beamObjMeshName(void* obj, uint32_t mesh);
-int             beamSceneLoadObj(void* scene, const char* path, int splitByMaterial);   /* Model::load: meshes added, or -1 */
+int             beamObjHasUVs(void* obj);
+const float*    beamObjUVs(void* obj);                                /* numVertices * 2 or NULL (`vt`, first use per position wins) */
+const char*     beamObjMeshTexture(void* obj, uint32_t mesh);         /* map_Kd path of the mesh's material (relative to the OBJ resolved), or NULL */
+/* Uncompressed 24/32-bit BMP -> malloc'ed width*height texels 0x00RRGGBB, row 0 = top (free with beamImageFree); NULL on failure */
+uint32_t*       beamBmpLoad(const char* path, uint32_t* width, uint32_t* height);
+void            beamImageFree(uint32_t* texels);
+/* Model::load: every mesh of the file added to `scene` (positions, normals, UVs when present; with splitByMaterial also the
+ * materials' map_Kd BMP textures when they load); returns the number of meshes added, or -1 */
+int             beamSceneLoadObj(void* scene, const char* path, int splitByMaterial);
 int             beamWritePPM(const char* path, const uint32_t* hostPixels, uint32_t width, uint32_t height);
 #ifdef __cplusplus
 }

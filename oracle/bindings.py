@@ -207,6 +207,26 @@ class OracleScene:
         o["seconds"] = sec; o["node_visits"] = int(cnt[0]); o["tri_tests"] = int(cnt[1])
         return o
 
+    def set_mesh_uv(self, mesh, uv):
+        a = np.ascontiguousarray(uv, np.float32)
+        self.O.lib.orc_scene_set_mesh_uv.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        assert self.O.lib.orc_scene_set_mesh_uv(self.h, int(mesh), a.ctypes.data, int(a.shape[1])) == 0
+
+    def set_mesh_texture(self, mesh, texels):
+        a = np.ascontiguousarray(texels, np.uint32)
+        self.O.lib.orc_scene_set_mesh_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+        assert self.O.lib.orc_scene_set_mesh_texture(self.h, int(mesh), a.ctypes.data, int(a.shape[1]), int(a.shape[0])) == 0
+
+    def shade_hits(self, u, v, mesh, tri):
+        """pixels of hit records under the product's material rule (bmShadeHits); tri = face index within its mesh, 0xFFFFFFFF = miss"""
+        u = np.ascontiguousarray(u, np.float32); v = np.ascontiguousarray(v, np.float32)
+        mesh = np.ascontiguousarray(mesh, np.uint32); tri = np.ascontiguousarray(tri, np.uint32)
+        out = np.zeros(u.shape[0], np.uint32)
+        self.O.lib.orc_shade_hits.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 5
+        self.O.lib.orc_shade_hits.restype = None
+        self.O.lib.orc_shade_hits(self.h, u.shape[0], u.ctypes.data, v.ctypes.data, mesh.ctypes.data, tri.ctypes.data, out.ctypes.data)
+        return out
+
     def close(self):
         if self.h:
             self.O.lib.orc_scene_destroy(self.h)

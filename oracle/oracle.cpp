@@ -169,7 +169,12 @@ i32 map_cell(float f) { return (i32)floorf(f * (1.f / 0.03f)); }
 // ---------------------------------------------------------------------------------------------------------------------
 // Scene
 // ---------------------------------------------------------------------------------------------------------------------
-struct Mesh { std::vector<V3> pos; std::vector<V3> nrm; std::vector<u32> idx; };
+struct Mesh
+{
+    std::vector<V3> pos; std::vector<V3> nrm; std::vector<u32> idx;
+    std::vector<float> uv; u32 uvComps = 0;                       // vertex-data slot 2 (Beam.h:21 VERTEX_DATA_UV1)
+    std::vector<u32> texels; u32 texW = 0, texH = 0;              // the mesh's material texture, 0x00RRGGBB, row 0 = top
+};
 struct FaceRec { u32 i0, i1, i2, mesh, tri; };                    // bmFace (SharedTypes.h:25-29) + the triangle index
 struct Node { i32 left, right; i32 leaf; u32 faceInsertIdx; };    // bmTreeNode (BuildTree.cuh:26-36); leaf = index into leafFaces
 struct StackNode { V3 mn, mx; i32 node; u32 depth, axis; };       // bmStackNode (BuildTree.cuh:39-48)
@@ -284,6 +289,32 @@ u32 shade(const Scene& S, const Hit& h)
     else n = cross3(M.pos[i1] - M.pos[i0], M.pos[i2] - M.pos[i0]);      // extension: the reference has no such path
     n = n * (1.f / sqrtf(dot3(n, n)));                                    // glm::normalize = v * inversesqrt(dot(v,v))
     return (u32)fabsf(n.z * 255) << 16;
+}
+
+// Material path.  The reference declares it (SharedTypes.h:20-23 bmMaterial{int texture}, Beam.h:21 VERTEX_DATA_UV1, Content/f16.mtl
+// map_Kd) but never implements it, so there is nothing of the reference to restate: this is the CPU statement of the rule the product
+// defines for bmShadeHits (include/beam_b200.h), kept in the reference's arithmetic style (bmFaceInterpolate weights, no FMA).
+u32 shade_textured(const Scene& S, const Hit& h)
+{
+    if (h.tri == 0xFFFFFFFFu) return 255u << 8;
+    const Mesh& M = S.meshes[h.mesh];
+    if (M.texels.empty() || M.uv.empty() || M.uvComps < 2) return shade(S, h);
+    u32 i0 = M.idx[3 * h.tri], i1 = M.idx[3 * h.tri + 1], i2 = M.idx[3 * h.tri + 2];
+    V3 n;
+    float w = 1 - (h.u + h.v);
+    if (!M.nrm.empty()) n = M.nrm[i0] * w + M.nrm[i1] * h.u + M.nrm[i2] * h.v;
+    else n = cross3(M.pos[i1] - M.pos[i0], M.pos[i2] - M.pos[i0]);
+    n = n * (1.f / sqrtf(dot3(n, n)));
+    u32 c = M.uvComps;
+    float tu = M.uv[c * (size_t)i0] * w + M.uv[c * (size_t)i1] * h.u + M.uv[c * (size_t)i2] * h.v;
+    float tv = M.uv[c * (size_t)i0 + 1] * w + M.uv[c * (size_t)i1 + 1] * h.u + M.uv[c * (size_t)i2 + 1] * h.v;
+    tu = tu - floorf(tu); tv = 1.f - (tv - floorf(tv));
+    u32 x = (u32)(tu * (float)M.texW), y = (u32)(tv * (float)M.texH);
+    x = x < M.texW ? x : M.texW - 1; y = y < M.texH ? y : M.texH - 1;
+    u32 texel = M.texels[(size_t)y * M.texW + x];
+    float s = fabsf(n.z);
+    u32 r = (u32)((float)((texel >> 16) & 255u) * s), g = (u32)((float)((texel >> 8) & 255u) * s), b = (u32)((float)(texel & 255u) * s);
+    return (r << 16) | (g << 8) | b;
 }
 
 // BuildTree.cu:367-499 bmMarchKernel for one ray.  mode 0 = reference semantics (stop at the first leaf that produced a hit);
@@ -432,6 +463,35 @@ int orc_scene_add_mesh(void* h, const float* pos, const float* nrm, u32 numVerts
     M.idx.assign(idx, idx + numIdx);
     S->meshes.push_back(std::move(M));
     return 0;
+}
+
+int orc_scene_set_mesh_uv(void* h, u32 mesh, const float* uv, u32 comps)
+{
+    Scene* S = (Scene*)h;
+    if (mesh >= S->meshes.size() || !uv || comps < 1 || comps > 4) return 2;
+    Mesh& M = S->meshes[mesh];
+    M.uv.assign(uv, uv + (size_t)comps * M.pos.size()); M.uvComps = comps;
+    return 0;
+}
+
+int orc_scene_set_mesh_texture(void* h, u32 mesh, const u32* texels, u32 width, u32 height)
+{
+    Scene* S = (Scene*)h;
+    if (mesh >= S->meshes.size() || !texels || !width || !height) return 2;
+    Mesh& M = S->meshes[mesh];
+    M.texels.assign(texels, texels + (size_t)width * height); M.texW = width; M.texH = height;
+    return 0;
+}
+
+// pixels of hit records (u, v, mesh, triangle-in-mesh; tri = 0xFFFFFFFF on a miss) under the material rule above
+void orc_shade_hits(void* h, u64 n, const float* u, const float* v, const u32* mesh, const u32* tri, u32* pixels)
+{
+    Scene* S = (Scene*)h;
+    for (u64 i = 0; i < n; i++)
+    {
+        Hit hit = { 0.f, u[i], v[i], mesh[i], tri[i], 0 };
+        pixels[i] = shade_textured(*S, hit);
+    }
 }
 
 // SceneTree::updateGPUScene (SceneTree.cpp:70-91): reset, then insert every mesh in order. Returns seconds.

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
     "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView",
-    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve",
+    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
     "beamMeshCreate", "beamMeshDestroy", "beamMeshSetVertexData", "beamMeshSetIndices",
@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "beamRenderTargetReadPixels", "beamDeviceSynchronize",
     "beamObjLoad", "beamObjError", "beamObjFree", "beamObjNumVertices", "beamObjNumMeshes", "beamObjHasNormals", "beamObjPositions", "beamObjNormals",
     "beamObjMeshNumIndices", "beamObjMeshIndices", "beamObjMeshName", "beamSceneLoadObj", "beamWritePPM",
+    "beamMeshSetTexture", "beamCameraTraceSceneTextured", "beamObjHasUVs", "beamObjUVs", "beamObjMeshTexture", "beamBmpLoad", "beamImageFree",
 ]
 
 
@@ -45,6 +46,14 @@ class bmVec3(C.Structure):
 
 class bmMat3(C.Structure):
     _fields_ = [("m", C.c_float * 9)]
+
+
+class bmMaterial(C.Structure):
+    _fields_ = [("texture", C.c_int)]
+
+
+class bmTexture(C.Structure):
+    _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
 
 
 class bmStaticMeshData(C.Structure):
@@ -139,6 +148,14 @@ def load() -> C.CDLL:
     L.beamObjMeshName.argtypes = [vp, u32]; L.beamObjMeshName.restype = C.c_char_p
     L.beamSceneLoadObj.argtypes = [vp, C.c_char_p, i32]
     L.beamWritePPM.argtypes = [C.c_char_p, vp, u32, u32]
+    L.beamMeshSetTexture.argtypes = [vp, vp, u32, u32]; L.beamMeshSetTexture.restype = u32
+    L.beamCameraTraceSceneTextured.argtypes = [vp, vp, vp, vp]; L.beamCameraTraceSceneTextured.restype = u32
+    L.beamObjHasUVs.argtypes = [vp]
+    L.beamObjUVs.argtypes = [vp]; L.beamObjUVs.restype = C.POINTER(C.c_float)
+    L.beamObjMeshTexture.argtypes = [vp, u32]; L.beamObjMeshTexture.restype = C.c_char_p
+    L.beamBmpLoad.argtypes = [C.c_char_p, C.POINTER(u32), C.POINTER(u32)]; L.beamBmpLoad.restype = C.POINTER(u32)
+    L.beamImageFree.argtypes = [C.POINTER(u32)]; L.beamImageFree.restype = None
+    L.bmShadeHits.argtypes = [vp, vp, u64, vp, vp, vp, u32, vp]
     _lib = L
     return L
 

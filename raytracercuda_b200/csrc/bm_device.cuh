@@ -98,6 +98,8 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numR
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
                  u64* d_counters, u32* d_workCounter, cudaStream_t s);
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
+int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials, const bmTexture* d_textures,
+               u32 numTextures, u32* d_pixels, cudaStream_t s);
 
 // ---- rays.cu --------------------------------------------------------------------------------------------------------
 int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* d_out, cudaStream_t s);

@@ -96,8 +96,20 @@ public:
         m_indices = buf; m_numIndices = numIndices;
         return ERROR_ALL_FINE;
     }
+    // the material of the mesh (SharedTypes.h:20-23 bmMaterial{int texture}): width*height host texels 0x00RRGGBB, row 0 = top
+    u32 setTexture(const u32* texels, u32 width, u32 height) override
+    {
+        if (!texels || width == 0 || height == 0) return ERROR_INVALID_PARAMETER;
+        auto buf = std::make_shared<DeviceBuffer>((size_t)width * height * sizeof(u32));
+        if (!buf->ok()) return ERROR_GPU_ALLOC_FAIL;
+        buf->copyFrom(texels, true);
+        m_texture = buf; m_texW = width; m_texH = height;
+        return ERROR_ALL_FINE;
+    }
     wptr<IScene> scene() const override { return m_scene; }
     wptr<IScene> m_scene;
+    sptr<DeviceBuffer> m_texture;
+    u32 m_texW = 0, m_texH = 0;
     u32 m_numVertices = 0, m_numIndices = 0;
     sptr<DeviceBuffer> m_indices, m_data[VERTEX_DATA_COUNT];
     u32 m_sizes[VERTEX_DATA_COUNT];
@@ -133,6 +145,20 @@ public:
         }
         m_table = std::make_shared<DeviceBuffer>(std::max<size_t>(1, tab.size()) * sizeof(bmStaticMeshData));
         if (!tab.empty()) m_table->copyFrom(tab.data(), true);
+        // materials: one bmMaterial per mesh, one texture-table entry per textured mesh
+        std::vector<bmMaterial> mats(m_meshes.size());
+        std::vector<bmTexture> texs;
+        for (size_t i = 0; i < m_meshes.size(); i++)
+        {
+            auto& m = m_meshes[i];
+            mats[i].texture = -1;
+            if (m->m_texture) { mats[i].texture = (int)texs.size(); texs.push_back({ m->m_texture->ptr<const u32>(), m->m_texW, m->m_texH }); }
+        }
+        m_materials = std::make_shared<DeviceBuffer>(std::max<size_t>(1, mats.size()) * sizeof(bmMaterial));
+        if (!mats.empty()) m_materials->copyFrom(mats.data(), true);
+        m_textures = std::make_shared<DeviceBuffer>(std::max<size_t>(1, texs.size()) * sizeof(bmTexture));
+        if (!texs.empty()) m_textures->copyFrom(texs.data(), true);
+        m_numTextures = (u32)texs.size();
         m_dirtyTable = false;
     }
     void updateGPUScene() override
@@ -174,6 +200,25 @@ public:
         hits.copyTo(hostHits, true);
         return ERROR_ALL_FINE;
     }
+    // hits -> deferred shading with the meshes' materials (ICamera::traceSceneTextured)
+    u32 marchTextured(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh)
+    {
+        IRenderTarget* rt = RenderTarget::get();
+        if (!rt) return ERROR_NO_RENDER_TARGET;
+        if (rt->width() != raysWide || rt->height() != raysHigh) return ERROR_RT_CAM_MISMATCH;
+        updateMeshPtrs();                        // a texture set after updateGPUScene still counts
+        size_t n = (size_t)raysWide * raysHigh;
+        bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
+        if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); return ERROR_ALL_FINE; }
+        DeviceBuffer hits(n * sizeof(bmHit));
+        if (!hits.ok()) return ERROR_GPU_ALLOC_FAIL;
+        int r = bmTraceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, BM_TRACE_REFERENCE, hits.ptr<bmHit>(), nullptr, nullptr, nullptr);
+        if (!r) r = bmShadeHits(t, hits.ptr<bmHit>(), n, m_table->ptr<const bmStaticMeshData>(), m_materials->ptr<const bmMaterial>(),
+                                m_textures->ptr<const bmTexture>(), m_numTextures, rt->buffer<u32>());
+        if (r != BM_OK) return (u32)r;
+        cudaDeviceSynchronize();                 // `hits` dies with this scope
+        return ERROR_ALL_FINE;
+    }
     // progressive frame (see ICamera::traceSceneProgressive): every sample = jittered camera rays -> trace -> bounce rays -> trace -> accumulate
     u32 marchProgressive(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh, float jx, float jy, u32 samples,
                          u32 seed, u64* raysTraced)
@@ -209,7 +254,8 @@ public:
 private:
     bmVec3 m_min, m_max;
     std::vector<sptr<Mesh>> m_meshes;
-    sptr<DeviceBuffer> m_root, m_table;
+    sptr<DeviceBuffer> m_root, m_table, m_materials, m_textures;
+    u32 m_numTextures = 0;
     bool m_dirtyTable = true;
 };
 sptr<IScene> IScene::create() { return std::make_shared<Scene>(); }
@@ -266,6 +312,11 @@ public:
         if (!eye3 || !orient3x3 || !scene || m_width == 0 || m_height == 0 || !m_rays) return ERROR_INVALID_PARAMETER;
         return static_cast<Scene*>(scene.get())->marchProgressive(eye3, orient3x3, m_rays, m_width, m_height, m_pixelW, m_pixelH, samples, seed, raysTraced);
     }
+    u32 traceSceneTextured(const float* eye3, const float* orient3x3, sptr<IScene>& scene) override
+    {
+        if (!eye3 || !orient3x3 || !scene || m_width == 0 || m_height == 0 || !m_rays) return ERROR_INVALID_PARAMETER;
+        return static_cast<Scene*>(scene.get())->marchTextured(eye3, orient3x3, m_rays, m_width, m_height);
+    }
     u32 copyInitialRays(float* host) const { if (!m_rays) return ERROR_INVALID_PARAMETER; m_rays->copyTo(host, true); return ERROR_ALL_FINE; }
 private:
     u32 m_width = 0, m_height = 0;
@@ -287,6 +338,8 @@ uint32_t beamMeshSetVertexData(void* m, const float* hostData, uint32_t numVerti
 { return (*(sptr<IMesh>*)m)->setVertexData(hostData, numVertices, numComponents, slotId, asyncCopy != 0); }
 uint32_t beamMeshSetIndices(void* m, const uint32_t* hostIndices, uint32_t numIndices, int asyncCopy)
 { return (*(sptr<IMesh>*)m)->setIndices(hostIndices, numIndices, asyncCopy != 0); }
+uint32_t beamMeshSetTexture(void* m, const uint32_t* hostTexels, uint32_t width, uint32_t height) { return (*(sptr<IMesh>*)m)->setTexture(hostTexels, width, height); }
+uint32_t beamCameraTraceSceneTextured(void* c, const float* eye3, const float* orient9, void* s) { return (*(sptr<ICamera>*)c)->traceSceneTextured(eye3, orient9, *(sptr<IScene>*)s); }
 void  beamSceneAddMesh(void* s, void* m) { (*(sptr<IScene>*)s)->addMesh(*(sptr<IMesh>*)m); }
 void  beamSceneRemoveMesh(void* s, void* m) { (*(sptr<IScene>*)s)->removeMesh(**(sptr<IMesh>*)m); }
 void  beamSceneUpdateGPUScene(void* s) { (*(sptr<IScene>*)s)->updateGPUScene(); }

@@ -110,14 +110,13 @@ __device__ __forceinline__ void test_face(float4 a, float4 b, float4 c, V3 o, V3
     }
 }
 
-// bmFaceInterpolate<vec3>(face, u, v, meshData, 1) + normalize + pack (CudaComon.cuh:253-266, BuildTree.cu:486-496).
-// A mesh without normals (null slot 1; undefined behaviour in the reference) shades with the geometric normal.
-__device__ u32 shade(const HitRec& h, const bmStaticMeshData* __restrict__ meshData)
+// bmFaceInterpolate<vec3>(face, u, v, meshData, 1) + normalize (CudaComon.cuh:253-266, BuildTree.cu:486-492): the z component of
+// the shading normal.  A mesh without normals (null slot 1; undefined behaviour in the reference) uses the geometric normal.
+__device__ float shade_nz(u32 mesh, u32 face, float u, float v, const bmStaticMeshData* __restrict__ meshData, u32& i0, u32& i1, u32& i2)
 {
-    if (h.tri == 0xFFFFFFFFu) return 255u << 8;
-    const bmStaticMeshData* m = meshData + h.mesh;
-    const u32* idx = m->m_indices + 3 * (size_t)h.face;
-    u32 i0 = idx[0], i1 = idx[1], i2 = idx[2];
+    const bmStaticMeshData* m = meshData + mesh;
+    const u32* idx = m->m_indices + 3 * (size_t)face;
+    i0 = idx[0]; i1 = idx[1]; i2 = idx[2];
     const float* nrm = m->m_vertexData[1];
     V3 n;
     if (nrm)
@@ -125,8 +124,8 @@ __device__ u32 shade(const HitRec& h, const bmStaticMeshData* __restrict__ meshD
         V3 n0 = mk3(nrm[3 * i0], nrm[3 * i0 + 1], nrm[3 * i0 + 2]);
         V3 n1 = mk3(nrm[3 * i1], nrm[3 * i1 + 1], nrm[3 * i1 + 2]);
         V3 n2 = mk3(nrm[3 * i2], nrm[3 * i2 + 1], nrm[3 * i2 + 2]);
-        float w = 1 - (h.u + h.v);
-        n = n0 * w + n1 * h.u + n2 * h.v;
+        float w = 1 - (u + v);
+        n = n0 * w + n1 * u + n2 * v;
     }
     else
     {
@@ -137,7 +136,50 @@ __device__ u32 shade(const HitRec& h, const bmStaticMeshData* __restrict__ meshD
         n = cross3(p1 - p0, p2 - p0);
     }
     n = n * (1.f / sqrtf(dot3(n, n)));          // glm::normalize = v * inversesqrt(dot(v, v)), inversesqrt = 1/sqrt
-    return (u32)fabsf(n.z * 255) << 16;
+    return n.z;
+}
+
+// the reference's pixel (BuildTree.cu:486-496)
+__device__ u32 shade(const HitRec& h, const bmStaticMeshData* __restrict__ meshData)
+{
+    if (h.tri == 0xFFFFFFFFu) return 255u << 8;
+    u32 i0, i1, i2;
+    return (u32)fabsf(shade_nz(h.mesh, h.face, h.u, h.v, meshData, i0, i1, i2) * 255) << 16;
+}
+
+// Deferred shading of hit records with the material path the reference declares but never implements (SharedTypes.h:20-23
+// bmMaterial{int texture}, Beam.h:21 VERTEX_DATA_UV1, Content/f16.mtl map_Kd): the behaviour is defined here.
+//   miss                                  -> 255 << 8                                    (the reference's miss colour)
+//   hit, mesh without texture or UV slot  -> (u32)|n.z * 255| << 16                      (the reference's pixel, bit for bit)
+//   hit, textured mesh                    -> uv = bmFaceInterpolate(slot 2); texel = nearest, repeat wrap, v up (row 0 = top of the
+//                                            image); channel c -> (u32)(c * |n.z|), packed 0x00RRGGBB like the reference's red
+__global__ void shade_hits_kernel(const bmHit* __restrict__ hits, u64 n, const float4* __restrict__ soup, const bmStaticMeshData* __restrict__ meshData,
+                                  const bmMaterial* __restrict__ materials, const bmTexture* __restrict__ textures, u32 numTextures, u32* __restrict__ pixels)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 h = reinterpret_cast<const float4*>(hits)[i];
+    u32 tri = __float_as_uint(h.w);
+    if (tri == 0xFFFFFFFFu) { pixels[i] = 255u << 8; return; }
+    u32 mesh = __float_as_uint(soup[3 * (size_t)tri + 1].w), face = __float_as_uint(soup[3 * (size_t)tri + 2].w);
+    u32 i0, i1, i2;
+    float nz = shade_nz(mesh, face, h.y, h.z, meshData, i0, i1, i2);
+    int tex = materials ? materials[mesh].texture : -1;
+    const bmStaticMeshData* m = meshData + mesh;
+    const float* uv = m->m_vertexData[2];
+    u32 comps = m->m_vertexDataSizes[2];
+    if (tex < 0 || (u32)tex >= numTextures || !uv || comps < 2) { pixels[i] = (u32)fabsf(nz * 255) << 16; return; }
+    bmTexture t = textures[tex];
+    float w = 1 - (h.y + h.z);
+    float tu = uv[comps * (size_t)i0] * w + uv[comps * (size_t)i1] * h.y + uv[comps * (size_t)i2] * h.z;
+    float tv = uv[comps * (size_t)i0 + 1] * w + uv[comps * (size_t)i1 + 1] * h.y + uv[comps * (size_t)i2 + 1] * h.z;
+    tu = tu - floorf(tu); tv = 1.f - (tv - floorf(tv));
+    u32 x = (u32)(tu * (float)t.width), y = (u32)(tv * (float)t.height);
+    x = x < t.width ? x : t.width - 1; y = y < t.height ? y : t.height - 1;
+    u32 texel = t.texels[(size_t)y * t.width + x];
+    float s = fabsf(nz);
+    u32 r = (u32)((float)((texel >> 16) & 255u) * s), g = (u32)((float)((texel >> 8) & 255u) * s), b = (u32)((float)(texel & 255u) * s);
+    pixels[i] = (r << 16) | (g << 8) | b;
 }
 
 // monotone map float -> u32 (any sign, -0 folded onto +0) so that (d, triangle id) pairs can be min-reduced as one 64-bit key
@@ -525,6 +567,15 @@ int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int 
 {
     if (!n) return BM_OK;
     return dispatch_trace<true>(tv, nullptr, cam, n, nullptr, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
+}
+
+int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials, const bmTexture* d_textures,
+               u32 numTextures, u32* d_pixels, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    shade_hits_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits, n, d_soup, d_meshData, d_materials, d_textures, numTextures, d_pixels);
+    BM_LAUNCHED();
+    return BM_OK;
 }
 
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s)

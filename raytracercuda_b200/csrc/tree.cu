@@ -441,6 +441,14 @@ extern "C" int bmProgressiveResolve(const float* d_accum, const uint32_t* d_cove
     return progressive_resolve(d_accum, d_covered, numRays, samples, d_pixels, (cudaStream_t)stream);
 }
 
+extern "C" int bmShadeHits(bmTree* t, const bmHit* d_hits, uint64_t numRays, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials,
+                           const bmTexture* d_textures, uint32_t numTextures, uint32_t* d_pixels)
+{
+    if (!t || ((!d_hits || !d_pixels || !d_meshData) && numRays) || (numTextures && !d_textures)) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    return shade_hits(d_hits, numRays, t->soup.as<float4>(), d_meshData, d_materials, d_textures, numTextures, d_pixels, t->stream);
+}
+
 extern "C" int bmHashKeys(const float* d_points3, uint64_t n, uint32_t* d_hash, int32_t* d_cells3, void* stream)
 {
     if (!d_points3 && n) return BM_ERROR_INVALID_PARAMETER;

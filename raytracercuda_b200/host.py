@@ -32,6 +32,11 @@ class IMesh:
         a = None if indices is None else np.ascontiguousarray(indices, np.uint32)
         return self.L.beamMeshSetIndices(self.h, None if a is None else a.ctypes.data, int(numIndices), int(asyncCopy))
 
+    def setTexture(self, texels, width, height) -> int:
+        """IMesh::setTexture: (height, width) uint32 texels 0x00RRGGBB, row 0 = top"""
+        a = None if texels is None else np.ascontiguousarray(texels, np.uint32)
+        return self.L.beamMeshSetTexture(self.h, None if a is None else a.ctypes.data, int(width), int(height))
+
     def __del__(self):
         if getattr(self, "h", None):
             self.L.beamMeshDestroy(self.h); self.h = None
@@ -127,6 +132,10 @@ class ICamera:
     def traceScene(self, eye3, orient3x3, scene: IScene) -> int:
         e = self._f(eye3, 3); o = self._f(orient3x3, 9)
         return self.L.beamCameraTraceScene(self.h, None if e is None else e.ctypes.data, None if o is None else o.ctypes.data, None if scene is None else scene.h)
+
+    def traceSceneTextured(self, eye3, orient3x3, scene: IScene) -> int:
+        e = self._f(eye3, 3); o = self._f(orient3x3, 9)
+        return self.L.beamCameraTraceSceneTextured(self.h, None if e is None else e.ctypes.data, None if o is None else o.ctypes.data, None if scene is None else scene.h)
 
     def traceSceneHits(self, eye3, orient3x3, scene: IScene):
         e = self._f(eye3, 3); o = self._f(orient3x3, 9)

@@ -26,6 +26,8 @@ class TriMesh:
     indices: np.ndarray            # (F,3) uint32
     normals: np.ndarray | None     # (V,3) float32 or None
     name: str = ""
+    uvs: np.ndarray | None = None  # (V,2) float32 or None (native loader only)
+    texture: str | None = None     # map_Kd path of the mesh's material (native loader only)
 
     @property
     def num_tris(self) -> int:
@@ -107,6 +109,21 @@ def compute_vertex_normals(positions: np.ndarray, indices: np.ndarray) -> np.nda
     return N.astype(np.float32)
 
 
+def load_bmp_native(path: str) -> np.ndarray:
+    """beamBmpLoad: (height, width) uint32 texels 0x00RRGGBB, row 0 = top"""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    p = L.beamBmpLoad(path.encode(), C.byref(w), C.byref(h))
+    if not p:
+        raise _lib.BeamError("cannot load BMP " + path)
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value)).copy()
+    finally:
+        L.beamImageFree(p)
+
+
 def load_obj_native(path: str, split_by_material: bool = False) -> list[TriMesh]:
     """the library's own C++ loader (csrc/objload.cpp, beamObjLoad) -- same rules as load_obj above"""
     import ctypes as C
@@ -120,11 +137,13 @@ def load_obj_native(path: str, split_by_material: bool = False) -> list[TriMesh]
         V = L.beamObjNumVertices(h)
         P = np.ctypeslib.as_array(L.beamObjPositions(h), shape=(V, 3)).copy()
         N = np.ctypeslib.as_array(L.beamObjNormals(h), shape=(V, 3)).copy() if L.beamObjHasNormals(h) else None
+        UV = np.ctypeslib.as_array(L.beamObjUVs(h), shape=(V, 2)).copy() if L.beamObjHasUVs(h) else None
         out = []
         for m in range(L.beamObjNumMeshes(h)):
             n = L.beamObjMeshNumIndices(h, m)
             I = np.ctypeslib.as_array(L.beamObjMeshIndices(h, m), shape=(n,)).copy().reshape(-1, 3)
-            out.append(TriMesh(P, I, N, L.beamObjMeshName(h, m).decode()))
+            tex = L.beamObjMeshTexture(h, m)
+            out.append(TriMesh(P, I, N, L.beamObjMeshName(h, m).decode(), UV, tex.decode() if tex else None))
         return out
     finally:
         L.beamObjFree(h)

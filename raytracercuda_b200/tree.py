@@ -179,10 +179,13 @@ def hits_to_numpy(hits: torch.Tensor):
 
 
 def make_mesh_table(meshes, device) -> torch.Tensor:
-    """Device array of StaticMeshData (SharedTypes.h:10-18, 136 bytes each) from [(positions, indices, normals|None)] device tensors."""
+    """Device array of StaticMeshData (SharedTypes.h:10-18, 136 bytes each) from [(positions, indices, normals|None[, uvs|None])] device tensors."""
     n = len(meshes)
     arr = (_lib.bmStaticMeshData * n)()
-    for i, (P, I, N) in enumerate(meshes):
+    for i, m in enumerate(meshes):
+        P, I, N = m[0], m[1], m[2]
+        if len(m) > 3 and m[3] is not None:
+            arr[i].m_vertexData[2] = m[3].data_ptr(); arr[i].m_vertexDataSizes[2] = m[3].shape[1]      # VERTEX_DATA_UV1
         arr[i].m_vertexData[0] = P.data_ptr(); arr[i].m_vertexDataSizes[0] = 3
         if N is not None:
             arr[i].m_vertexData[1] = N.data_ptr(); arr[i].m_vertexDataSizes[1] = 3
