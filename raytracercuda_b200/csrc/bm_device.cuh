@@ -39,7 +39,10 @@ int sm_count();
 //             face index in mesh).  EXCLUDED marks pairs beyond the reference's 256-faces-per-leaf cap (BuildTree.cuh:17).
 //  clusters : 32 bytes per group of CLUSTER consecutive pairs of one leaf: float4 (lo.xyz, hi.x) (hi.y, hi.z, -, -) = padded
 //             union of the group's whole triangles.  A leaf tests a group's triangles only if the ray's line meets its box.
-constexpr int SUB_BITS = 15;
+#ifndef BM_SUB_BITS
+#define BM_SUB_BITS 9
+#endif
+constexpr int SUB_BITS = BM_SUB_BITS;      // multiple of 3
 constexpr int CLUSTER = 4;
 constexpr int NODE_F4 = 8, LEAF_F4 = 3, CLUSTER_F4 = 2;
 static const u32 LEAF_BIT = 0x80000000u;

@@ -35,14 +35,15 @@ struct NoEmit { BM_HD void operator()(u32, u32, u32, u32) const {} };
 // cell (centre of the triangle's box clipped to the cell, 5 bits per axis).  The code part decides everything parity is
 // defined on; the sub-key only orders the triangles of one leaf spatially so that consecutive groups of four get tight
 // cluster boxes (hierarchy.cu).  It is not part of any reference behaviour, so its arithmetic is free.
-// sub-key of a pair: 15-bit Morton code of the centre of (triangle box clipped to the cell) inside the cell
+// sub-key of a pair: SUB_BITS-bit Morton code of the centre of (triangle box clipped to the cell) inside the cell
 __device__ __forceinline__ u32 sub_key(const Grid& g, u32 ix, u32 iy, u32 iz, V3 tmin, V3 tmax)
 {
     V3 mn, mx; cell_box(g, g.D, ix, iy, iz, mn, mx);
     float cx = .5f * (fmaxf(tmin.x, mn.x) + fminf(tmax.x, mx.x)), cy = .5f * (fmaxf(tmin.y, mn.y) + fminf(tmax.y, mx.y)),
           cz = .5f * (fmaxf(tmin.z, mn.z) + fminf(tmax.z, mx.z));
-    int qx = (int)((cx - mn.x) / (mx.x - mn.x) * 32.f), qy = (int)((cy - mn.y) / (mx.y - mn.y) * 32.f), qz = (int)((cz - mn.z) / (mx.z - mn.z) * 32.f);
-    qx = min(max(qx, 0), 31); qy = min(max(qy, 0), 31); qz = min(max(qz, 0), 31);
+    constexpr int Q = 1 << (SUB_BITS / 3);
+    int qx = (int)((cx - mn.x) / (mx.x - mn.x) * (float)Q), qy = (int)((cy - mn.y) / (mx.y - mn.y) * (float)Q), qz = (int)((cz - mn.z) / (mx.z - mn.z) * (float)Q);
+    qx = min(max(qx, 0), Q - 1); qy = min(max(qy, 0), Q - 1); qz = min(max(qz, 0), Q - 1);
     return (spread3((u32)qx) << 2) | (spread3((u32)qy) << 1) | spread3((u32)qz);
 }
 
