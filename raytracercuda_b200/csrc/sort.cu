@@ -8,6 +8,8 @@
 // is stable.  In the scatter kernel the tile is first permuted into digit order in shared memory, then written out so that
 // consecutive threads write consecutive addresses of each digit run.
 // HBM traffic per pass: 4 B (histogram) + 8 B + 8 B per pair; 4 passes for the 31-bit codes of the default world.
+#include <cstdlib>
+#include <cstring>
 #include "bm_device.cuh"
 
 namespace bm
@@ -137,14 +139,163 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const K* __re
         }
     }
 }
+
+// ---- one-sweep variant (Adinets & Merrill 2022): per pass ONE kernel.  The digit counts of every pass come from one upfront
+// histogram of the input; a tile ranks its items, publishes its per-digit counts and obtains, per digit, the number of equal digits in
+// the tiles before it by decoupled look-back (thread d walks digit d's chain).  Tiles are numbered by an atomic ticket in the order
+// the blocks start, so a block only waits for blocks that already run; waits are bounded and trap.  status word: flag << 30 | count.
+constexpr int RS_MAX_PASSES = 8;
+constexpr u32 OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_VAL = (1u << 30) - 1u;
+
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) radix_all_hist_kernel(const K* __restrict__ keys, size_t n, int passes, u32* __restrict__ hist)
+{
+    __shared__ u32 h[RS_MAX_PASSES][RS_BINS];
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    for (size_t idx = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; idx < n; idx += (size_t)gridDim.x * RS_THREADS)
+    {
+        K k = keys[idx];
+        for (int p = 0; p < passes; p++) atomicAdd(&h[p][(u32)(k >> (8 * p)) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    for (int p = 0; p < passes; p++)
+    {
+        u32 c = h[p][threadIdx.x];
+        if (c) atomicAdd(&hist[p * RS_BINS + threadIdx.x], c);
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const K* __restrict__ keysIn, const u32* __restrict__ valsIn,
+                                                                    K* __restrict__ keysOut, u32* __restrict__ valsOut, size_t n, int shift,
+                                                                    const u32* __restrict__ passHist, u32* ticket, volatile u32* status)
+{
+    constexpr int RS_ITEMS = RsCfg<K>::ITEMS, RS_TILE = RsCfg<K>::TILE;
+    __shared__ u32 warpHist[RS_WARPS][RS_BINS + 1];     // +1: bin 256 swallows the out-of-range tail
+    __shared__ u32 digitStart[RS_BINS + 1];
+    __shared__ u32 globalBase[RS_BINS];
+    __shared__ u32 scanTmp[RS_WARPS];
+    __shared__ K sKeys[RS_TILE];
+    __shared__ u32 sVals[RS_TILE];
+    __shared__ u32 sTile;
+
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * (RS_BINS + 1); i += RS_THREADS) (&warpHist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tile = sTile;
+
+    const size_t tileBase = (size_t)tile * RS_TILE;
+    const size_t warpBase = tileBase + (size_t)w * (RS_ITEMS * 32);
+    K key[RS_ITEMS]; u32 val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++)
+    {
+        size_t idx = warpBase + (size_t)r * 32 + lane;
+        bool ok = idx < n;
+        key[r] = ok ? keysIn[idx] : (K)0;
+        val[r] = ok ? valsIn[idx] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++)
+    {
+        size_t idx = warpBase + (size_t)r * 32 + lane;
+        u32 d = idx < n ? ((u32)(key[r] >> shift) & 0xFFu) : (u32)RS_BINS;
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        unsigned leader = __ffs(peers) - 1;
+        u32 before = 0;
+        if (lane == leader) { before = warpHist[w][d]; warpHist[w][d] = before + __popc(peers); }
+        before = __shfl_sync(0xFFFFFFFFu, before, leader);
+        rank[r] = before + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const u32 d = threadIdx.x;      // RS_THREADS == RS_BINS: thread d owns digit d
+        u32 run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) { u32 c = warpHist[ww][d]; warpHist[ww][d] = run; run += c; }
+        digitStart[d] = run;            // tile count of digit d, scanned below
+        // publish, then look back along digit d's chain
+        volatile u32* st = status + d;
+        u32 prefix = 0;
+        if (tile == 0) st[0] = OS_INC | run;
+        else
+        {
+            st[(size_t)tile * RS_BINS] = OS_AGG | run;
+            for (long long t = (long long)tile - 1; t >= 0; --t)
+            {
+                u32 sv = st[(size_t)t * RS_BINS], spins = 0;
+                while ((sv >> 30) == 0u) { if (++spins > (1u << 24)) __trap(); sv = st[(size_t)t * RS_BINS]; }
+                prefix += sv & OS_VAL;
+                if ((sv >> 30) == 2u) break;
+            }
+            st[(size_t)tile * RS_BINS] = OS_INC | (prefix + run);
+        }
+        // global base of digit d = number of keys with a smaller digit (exclusive scan of the pass histogram) + equal digits before this tile
+        u32 hcount = passHist[d];
+        u32 inc = hcount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (unsigned)o) inc += x; }
+        if (lane == 31) scanTmp[w] = inc;
+        __syncthreads();
+        u32 woff = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) if ((unsigned)ww < w) woff += scanTmp[ww];
+        globalBase[d] = woff + inc - hcount + prefix;
+    }
+    __syncthreads();
+    if (w == 0)
+    {
+        u32 c[8], s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { c[i] = digitStart[lane * 8 + i]; s += c[i]; }
+        u32 inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= (unsigned)o) inc += t; }
+        u32 ex = inc - s;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { digitStart[lane * 8 + i] = ex; ex += c[i]; }
+        if (lane == 31) digitStart[RS_BINS] = ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++)
+    {
+        size_t idx = warpBase + (size_t)r * 32 + lane;
+        if (idx < n)
+        {
+            u32 d = (u32)(key[r] >> shift) & 0xFFu;
+            u32 pos = digitStart[d] + warpHist[w][d] + rank[r];
+            sKeys[pos] = key[r];
+            sVals[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    const u32 valid = digitStart[RS_BINS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++)
+    {
+        u32 pos = i * RS_THREADS + threadIdx.x;
+        if (pos < valid)
+        {
+            K k = sKeys[pos];
+            u32 d = (u32)(k >> shift) & 0xFFu;
+            size_t g = (size_t)globalBase[d] + (pos - digitStart[d]);
+            keysOut[g] = k;
+            valsOut[g] = sVals[pos];
+        }
+    }
+}
 } // namespace
 
 size_t sort_temp_bytes(size_t n)
 {
     const size_t RS_TILE = RsCfg<u64>::TILE;      // the smaller tile -> the larger table
     size_t tiles = (n + RS_TILE - 1) / RS_TILE;
-    size_t counts = ((tiles * RS_BINS * 4 + 255) / 256) * 256;
-    return counts + scan_temp_bytes(tiles * RS_BINS);
+    size_t counts = ((tiles * RS_BINS * 4 + 255) / 256) * 256;      // per-tile digit table (three-kernel path) or status words (one-sweep)
+    return counts + scan_temp_bytes(tiles * RS_BINS) + RS_MAX_PASSES * RS_BINS * 4 + 256;
 }
 
 template <class K>
@@ -159,6 +310,28 @@ static int radix_sort_impl(K* d_keysA, u32* d_valsA, K* d_keysB, u32* d_valsB, s
     u32* counts = (u32*)d_temp;
     void* scanTemp = (char*)d_temp + ((tiles * RS_BINS * 4 + 255) / 256) * 256;
     K *ka = d_keysA, *kb = d_keysB; u32 *va = d_valsA, *vb = d_valsB;
+    static const bool threeKernel = getenv("BM_SORT") && strcmp(getenv("BM_SORT"), "3k") == 0;
+    if (!threeKernel && n < (size_t)OS_VAL && passes <= RS_MAX_PASSES)
+    {
+        // layout: [status tiles*256 u32][scan temp (unused here)][hist passes*256 u32][ticket]
+        u32* hist = (u32*)((char*)scanTemp + scan_temp_bytes(tiles * RS_BINS));
+        u32* ticket = hist + RS_MAX_PASSES * RS_BINS;
+        BM_CUDA(cudaMemsetAsync(hist, 0, RS_MAX_PASSES * RS_BINS * 4 + 4, s));
+        unsigned hb = (unsigned)((n + RS_THREADS * 16 - 1) / (RS_THREADS * 16));
+        unsigned cap = (unsigned)sm_count() * 8;
+        radix_all_hist_kernel<K><<<hb < cap ? hb : cap, RS_THREADS, 0, s>>>(ka, n, passes, hist);
+        BM_LAUNCHED();
+        for (int p = 0; p < passes; p++)
+        {
+            BM_CUDA(cudaMemsetAsync(counts, 0, tiles * RS_BINS * 4, s));
+            if (p) BM_CUDA(cudaMemsetAsync(ticket, 0, 4, s));
+            radix_onesweep_kernel<K><<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, 8 * p, hist + p * RS_BINS, ticket, counts);
+            BM_LAUNCHED();
+            K* t = ka; ka = kb; kb = t;
+            u32* tv = va; va = vb; vb = tv;
+        }
+        return BM_OK;
+    }
     for (int p = 0; p < passes; p++)
     {
         int shift = 8 * p;

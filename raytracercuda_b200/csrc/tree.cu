@@ -82,9 +82,28 @@ struct bmTree
     }
 };
 
+// BM_BUILD_TIMING=1: CUDA events between the stages of a build, printed to stderr (development aid; adds one synchronise at the end)
+struct StageTimer
+{
+    bool on; cudaStream_t s; std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    StageTimer(cudaStream_t st) : on(getenv("BM_BUILD_TIMING") != nullptr), s(st) { mark("start"); }
+    void mark(const char* name) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back({ name, e }); }
+    ~StageTimer()
+    {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        std::string line = "beam_b200 build stages (us):";
+        for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); char b[96]; snprintf(b, sizeof b, " %s %.1f", ev[i].first, ms * 1e3f); line += b; }
+        float tot = 0; if (ev.size() > 1) cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
+        fprintf(stderr, "%s | total %.1f\n", line.c_str(), tot * 1e3f);
+        for (auto& e : ev) cudaEventDestroy(e.second);
+    }
+};
+
 static int tree_build(bmTree* t)
 {
     cudaStream_t s = t->stream;
+    StageTimer tm(s);
     // 1. soup
     u64 T = 0;
     t->meshBase.clear();
@@ -101,6 +120,7 @@ static int tree_build(bmTree* t)
         auto& m = t->staged[k];
         BM_TRY(gather_mesh(m.pos, m.idx, m.numTris, m.meshIdx, t->meshBase[k], t->soup.as<float4>(), s));
     }
+    tm.mark("gather");
     // 2. pair counts per triangle -> offsets
     BM_TRY(t->counts.reserve(T * 4));
     BM_TRY(t->temp.reserve(scan_temp_bytes(T)));
@@ -115,10 +135,12 @@ static int tree_build(bmTree* t)
                               t->largeList.as<u32>(), t->scalars.as<u32>() + 10, s));
     }
     else BM_TRY(count_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), s));
+    tm.mark("classify");
     u32* d_scal = t->scalars.as<u32>();
     BM_TRY(exclusive_scan_u32(t->counts.as<u32>(), t->counts.as<u32>(), T, d_scal + 0, t->temp.p, s));
     BM_CUDA(cudaMemcpyAsync(&t->hostScalars[0], d_scal + 0, 4, cudaMemcpyDeviceToHost, s));
     BM_CUDA(cudaStreamSynchronize(s));
+    tm.mark("scan+readback");
     u64 P = t->hostScalars[0];
     t->P = P;
     if (P == 0) { t->built = true; return BM_OK; }      // every triangle outside the world box
@@ -128,11 +150,13 @@ static int tree_build(bmTree* t)
     if (flat) BM_TRY(emit_pairs_flat(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->masks.as<u64>(), t->infos.as<u64>(), t->largeList.as<u32>(),
                                       t->scalars.as<u32>() + 10, t->keysA.as<u64>(), t->valsA.as<u32>(), s));
     else BM_TRY(emit_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), t->keysA.as<u64>(), t->valsA.as<u32>(), s));
+    tm.mark("emit");
     int inB = 0;
     BM_TRY(radix_sort_pairs64(t->keysA.as<u64>(), t->valsA.as<u32>(), t->keysB.as<u64>(), t->valsB.as<u32>(), P, t->hgrid.D + SUB_BITS, t->temp.p, s, &inB));
     t->sortedKeys = inB ? t->keysB.as<u64>() : t->keysA.as<u64>();
     t->sortedVals = inB ? t->valsB.as<u32>() : t->valsA.as<u32>();
     u32* leafIdx = inB ? t->valsA.as<u32>() : t->valsB.as<u32>();     // the spare payload buffer: leaf index per pair
+    tm.mark("sort");
     // 4. leaves
     BM_TRY(t->flags.reserve(P * 4));
     BM_TRY(mark_heads(t->sortedKeys, P, t->flags.as<u32>(), s));
@@ -143,6 +167,7 @@ static int tree_build(bmTree* t)
     BM_CUDA(cudaStreamSynchronize(s));
     u64 L = t->hostScalars[1];
     t->L = L;
+    tm.mark("heads+scan+pack+readback");
     BM_TRY(t->leaves.reserve(L * 16 * LEAF_F4)); BM_TRY(t->clusterCounts.reserve(L * 4 + 4)); BM_TRY(t->codes.reserve(L * 4 + 4));
     BM_TRY(write_leaves(t->dgrid, t->sortedKeys, t->flags.as<u32>(), leafIdx, P, (u32)L, t->leaves.as<float4>(), t->clusterCounts.as<u32>(), t->codes.as<u32>(), s));
     BM_TRY(exclusive_scan_u32(t->clusterCounts.as<u32>(), t->clusterCounts.as<u32>(), L, nullptr, t->temp.p, s));
@@ -151,6 +176,7 @@ static int tree_build(bmTree* t)
     float pad = ext * (1.f / 1048576.f);
     BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->flags.as<u32>(), leafIdx, P, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(),
                        t->leafBox.as<float4>(), pad, d_scal + 2, t->parentL.as<u32>(), s));     // parentL doubles as the overflow-leaf queue until emit_hierarchy fills it
+    tm.mark("leaves+clusters+bounds");
     // 5. hierarchy + refit
     if (L >= 2)
     {
@@ -159,6 +185,7 @@ static int tree_build(bmTree* t)
         BM_TRY(build_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->visit.as<int>(), t->parentN.as<u32>(),
                                t->nodes.as<float4>(), t->rootDev.as<u32>(), s));
     }
+    tm.mark("hierarchy");
     t->built = true;
     return BM_OK;
 }
