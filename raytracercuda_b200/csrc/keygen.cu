@@ -86,13 +86,31 @@ __global__ void __launch_bounds__(KG_THREADS) emit_kernel(Grid g, const float4* 
 // info = ix0 | iy0 << 11 | iz0 << 22 | nx << 33 | ny << 40 | large << 63
 //
 // SIMT shape.  pair_test is a walk "margin check at level d, else SAT at level d, then d-1": most candidates end at the first margin
-// check, a few need one or more SATs (~250 instructions each).  Done lane by lane the SATs of a warp execute one or two lanes at a
-// time (first version: 4.5 of 32 lanes active, profiles/r1_final).  Here each lane only does the cheap margin checks; whenever a SAT
-// is needed the (owner lane, candidate, level) item goes into a per-warp shared-memory ring, and the warp then drains the ring 32
-// items at a time -- every lane runs one SAT, possibly for another lane's triangle (vertices are staged in shared memory), and
-// continues that item's walk.  Same tests on the same boxes as pair_test, only scheduled differently.
-constexpr int CL_WARPS = KG_THREADS / 32;
-constexpr int CL_RING = 2048;                  // >= 32 lanes x 64 candidates: every candidate has at most one item alive
+// check, a few need one or more SATs (~250 instructions each), and triangles have between 1 and 64 candidates.  Done lane by lane
+// the SATs of a warp execute one or two lanes at a time and the candidate loops idle the lanes with few candidates (first version:
+// 4.5 of 32 lanes active, profiles/r1_final).  Here a warp owns 32 * CL_ROUNDS triangles, staged in shared memory, and both kinds
+// of work are spread over the lanes regardless of which triangle they belong to (measured on B200, 327 K-triangle mesh: one triangle
+// per lane and four warps per block is fastest -- more triangles per warp fill the SAT steps better but leave too few warps):
+//   * candidates: the (triangle slot, candidate) pairs of the warp are enumerated through a prefix sum of the candidate counts, 32
+//     per step, each lane doing one leaf-level margin check;
+//   * SATs: a candidate that needs one becomes an item (slot, candidate, level) in a per-warp ring; as soon as 32 items wait, every
+//     lane runs one SAT and continues that item's walk (margin check one level up, else the item re-enters the ring).
+// Same tests on the same boxes as pair_test, only scheduled differently.
+#ifndef BM_CL_THREADS
+#define BM_CL_THREADS 128
+#endif
+#ifndef BM_CL_ROUNDS
+#define BM_CL_ROUNDS 1
+#endif
+#ifndef BM_CL_LONG
+#define BM_CL_LONG 5
+#endif
+constexpr int CL_THREADS = BM_CL_THREADS;
+constexpr int CL_WARPS = CL_THREADS / 32;
+constexpr int CL_ROUNDS = BM_CL_ROUNDS;
+constexpr int CL_SLOTS = 32 * CL_ROUNDS;       // triangles per warp
+constexpr int CL_LONG = BM_CL_LONG;                     // levels a walk runs item by item before the warp finishes it in one step
+constexpr int CL_RING = 256;                   // never holds more than 31 + 32 + 32 items (drained whenever 32 wait)
 
 __device__ __forceinline__ void level_box(const Grid& g, int d, u32 ix, u32 iy, u32 iz, float bc[3], float hs[3])
 {
@@ -101,69 +119,72 @@ __device__ __forceinline__ void level_box(const Grid& g, int d, u32 ix, u32 iy, 
     bc[0] = (mx.x + mn.x) * .5f; bc[1] = (mx.y + mn.y) * .5f; bc[2] = (mx.z + mn.z) * .5f;       // BuildTree.cu:221-225
     hs[0] = (mx.x - mn.x) * .5f; hs[1] = (mx.y - mn.y) * .5f; hs[2] = (mx.z - mn.z) * .5f;
 }
-__device__ __forceinline__ bool vertex_inside(const TriSat& t, const float bc[3], const float hs[3], float m)
+// is one of the three vertices (9 floats) inside the box shrunk by m on every side?
+__device__ __forceinline__ bool vertex_inside(const float* v9, const float bc[3], const float hs[3], float m)
 {
     float hx = hs[0] - m, hy = hs[1] - m, hz = hs[2] - m;
 #pragma unroll
     for (int k = 0; k < 3; k++)
-        if (fabsf(t.v[k].x - bc[0]) <= hx && fabsf(t.v[k].y - bc[1]) <= hy && fabsf(t.v[k].z - bc[2]) <= hz) return true;
+        if (fabsf(v9[3 * k] - bc[0]) <= hx && fabsf(v9[3 * k + 1] - bc[1]) <= hy && fabsf(v9[3 * k + 2] - bc[2]) <= hz) return true;
     return false;
 }
 
-__global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, float margin,
+__global__ void __launch_bounds__(CL_THREADS) classify_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, float margin,
                                                               u32* __restrict__ counts, u64* __restrict__ masks, u64* __restrict__ infos,
                                                               u32* __restrict__ largeList, u32* largeCount)
 {
     __shared__ u32 ring[CL_WARPS][CL_RING];
-    __shared__ float sv[CL_WARPS][32][9];
-    __shared__ u32 sorg[CL_WARPS][32][4];               // x0, y0, z0, nx | ny << 8
-    __shared__ unsigned long long smask[CL_WARPS][32];
+    __shared__ float sv[CL_WARPS][CL_SLOTS][9];
+    __shared__ u32 sorg[CL_WARPS][CL_SLOTS][4];         // x0, y0, z0, nx | ny << 8
+    __shared__ u32 smask[CL_WARPS][CL_SLOTS][2];        // accepted candidates (bit k), as two words: 32-bit shared atomics are native
+    __shared__ u32 spre[CL_WARPS][CL_SLOTS + 1];        // exclusive prefix of the candidate counts, slot order
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = t < numTris;
-    float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
-    if (valid) { const float4* p = soup + 3 * (size_t)t; a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); }
-    TriSat ts; trisat_init(ts, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z));
-    int lo[3] = { 0, 0, 0 }, hi[3] = { -1, -1, -1 };
-    if (valid)
-    {
-        axis_range(g, 0, fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
-        axis_range(g, 1, fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
-        axis_range(g, 2, fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
-    }
-    bool empty = !valid || lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2];
-    u32 nx = empty ? 0u : (u32)(hi[0] - lo[0] + 1), ny = empty ? 0u : (u32)(hi[1] - lo[1] + 1), nz = empty ? 0u : (u32)(hi[2] - lo[2] + 1);
-    bool large = !empty && (u64)nx * ny * nz > 64ull;
-    u32 ncand = (empty || large) ? 0u : nx * ny * nz;
-    // stage this lane's triangle and candidate box for the other lanes
-    sv[w][lane][0] = a.x; sv[w][lane][1] = a.y; sv[w][lane][2] = a.z; sv[w][lane][3] = b.x; sv[w][lane][4] = b.y; sv[w][lane][5] = b.z;
-    sv[w][lane][6] = c.x; sv[w][lane][7] = c.y; sv[w][lane][8] = c.z;
-    sorg[w][lane][0] = (u32)lo[0]; sorg[w][lane][1] = (u32)lo[1]; sorg[w][lane][2] = (u32)lo[2]; sorg[w][lane][3] = nx | (ny << 8);
-    smask[w][lane] = 0ull;
-    __syncwarp();
+    const u32 tBase = (blockIdx.x * CL_WARPS + w) * CL_SLOTS;
 
-    // phase A: margin check of every candidate at leaf level; the rest is queued for a SAT at that level
-    u32 head = 0, tail = 0;                            // warp-uniform ring cursors (monotone; index = cursor % CL_RING)
-    u32 maxCand = __reduce_max_sync(FULL, ncand);
-    for (u32 k = 0; k < maxCand; k++)
+    // ---- stage the warp's triangles: slot = round * 32 + lane ------------------------------------------------------------------------
+    u32 carry = 0;
+    unsigned largeBits = 0, emptyBits = 0;              // per-lane: bit r = triangle of round r is large / has no candidate
+#pragma unroll
+    for (int r = 0; r < CL_ROUNDS; r++)
     {
-        bool need = false;
-        if (k < ncand)
+        u32 slot = r * 32 + lane, t = tBase + slot;
+        bool valid = t < numTris;
+        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+        if (valid) { const float4* p = soup + 3 * (size_t)t; a = __ldg(p); b = __ldg(p + 1); c = __ldg(p + 2); }
+        int lo[3] = { 0, 0, 0 }, hi[3] = { -1, -1, -1 };
+        if (valid)
         {
-            u32 ix = (u32)lo[0] + k % nx, iy = (u32)lo[1] + (k / nx) % ny, iz = (u32)lo[2] + k / (nx * ny);
-            float bc[3], hs[3]; level_box(g, g.D, ix, iy, iz, bc, hs);
-            if (vertex_inside(ts, bc, hs, margin)) smask[w][lane] |= 1ull << k;
-            else need = true;
+            axis_range(g, 0, fminf(a.x, fminf(b.x, c.x)), fmaxf(a.x, fmaxf(b.x, c.x)), lo[0], hi[0]);
+            axis_range(g, 1, fminf(a.y, fminf(b.y, c.y)), fmaxf(a.y, fmaxf(b.y, c.y)), lo[1], hi[1]);
+            axis_range(g, 2, fminf(a.z, fminf(b.z, c.z)), fmaxf(a.z, fmaxf(b.z, c.z)), lo[2], hi[2]);
         }
-        unsigned bits = __ballot_sync(FULL, need);
-        if (need) ring[w][(tail + __popc(bits & ((1u << lane) - 1u))) % CL_RING] = lane | (k << 5) | ((u32)g.D << 11);
-        tail += __popc(bits);
+        bool empty = !valid || lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2];
+        u32 nx = empty ? 0u : (u32)(hi[0] - lo[0] + 1), ny = empty ? 0u : (u32)(hi[1] - lo[1] + 1), nz = empty ? 0u : (u32)(hi[2] - lo[2] + 1);
+        bool large = !empty && (u64)nx * ny * nz > 64ull;
+        u32 ncand = (empty || large) ? 0u : nx * ny * nz;
+        if (large) largeBits |= 1u << r;
+        if (empty) emptyBits |= 1u << r;
+        float* v = sv[w][slot];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = b.x; v[4] = b.y; v[5] = b.z; v[6] = c.x; v[7] = c.y; v[8] = c.z;
+        sorg[w][slot][0] = (u32)lo[0]; sorg[w][slot][1] = (u32)lo[1]; sorg[w][slot][2] = (u32)lo[2]; sorg[w][slot][3] = nx | (ny << 8);
+        smask[w][slot][0] = 0u; smask[w][slot][1] = 0u;
+        u32 inc = ncand;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 x = __shfl_up_sync(FULL, inc, o); if (lane >= (unsigned)o) inc += x; }
+        spre[w][slot] = carry + inc - ncand;
+        carry += __shfl_sync(FULL, inc, 31);
     }
+    if (lane == 0) spre[w][CL_SLOTS] = carry;
+    const u32 total = carry;
     __syncwarp();
 
-    // phase B: drain the ring, 32 SATs per step
-    while (head < tail)
+    u32 head = 0, tail = 0;                            // warp-uniform ring cursors (monotone; index = cursor % CL_RING)
+    // one SAT per lane on the next (up to) 32 ring items; an item whose walk goes on re-enters the ring.  A walk that is still
+    // undecided CL_LONG levels above the leaf is almost always a triangle touching a major split plane (a vertex exactly on it: every
+    // ancestor on the far side fails the margin check up to level 1) -- up to 30 more SATs in a row.  Those levels are independent
+    // computations, so the warp evaluates them all at once, lane l taking level d - l, and replays the walk's decisions on the ballots.
+    auto drain_step = [&]()
     {
         u32 n = min(32u, tail - head);
         bool have = lane < n;
@@ -173,12 +194,12 @@ __global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const floa
         bool again = false; u32 nextItem = 0;
         if (have)
         {
-            u32 owner = item & 31u, k = (item >> 5) & 63u; int d = (int)(item >> 11);
+            u32 slot = item & 127u, k = (item >> 7) & 63u; int d = (int)(item >> 13);
+            const float* v = sv[w][slot];
             TriSat ot;
-            trisat_init(ot, mk3(sv[w][owner][0], sv[w][owner][1], sv[w][owner][2]), mk3(sv[w][owner][3], sv[w][owner][4], sv[w][owner][5]),
-                        mk3(sv[w][owner][6], sv[w][owner][7], sv[w][owner][8]));
-            u32 onx = sorg[w][owner][3] & 255u, ony = sorg[w][owner][3] >> 8;
-            u32 ix = sorg[w][owner][0] + k % onx, iy = sorg[w][owner][1] + (k / onx) % ony, iz = sorg[w][owner][2] + k / (onx * ony);
+            trisat_init(ot, mk3(v[0], v[1], v[2]), mk3(v[3], v[4], v[5]), mk3(v[6], v[7], v[8]));
+            u32 onx = sorg[w][slot][3] & 255u, ony = sorg[w][slot][3] >> 8;
+            u32 ix = sorg[w][slot][0] + k % onx, iy = sorg[w][slot][1] + (k / onx) % ony, iz = sorg[w][slot][2] + k / (onx * ony);
             float bc[3], hs[3]; level_box(g, d, ix, iy, iz, bc, hs);
             if (sat_box(ot, bc, hs))
             {
@@ -187,29 +208,94 @@ __global__ void __launch_bounds__(KG_THREADS) classify_kernel(Grid g, const floa
                 if (!accept)
                 {
                     level_box(g, d - 1, ix, iy, iz, bc, hs);
-                    if (vertex_inside(ot, bc, hs, margin)) accept = true;
-                    else { again = true; nextItem = owner | (k << 5) | ((u32)(d - 1) << 11); }
+                    if (vertex_inside(v, bc, hs, margin)) accept = true;
+                    else { again = true; nextItem = slot | (k << 7) | ((u32)(d - 1) << 13); }
                 }
-                if (accept) atomicOr(&smask[w][owner], 1ull << k);
+                if (accept) atomicOr(&smask[w][slot][k >> 5], 1u << (k & 31u));
             }
+        }
+        // long walks: all remaining levels at once
+        unsigned longBits = __ballot_sync(FULL, again && (int)(nextItem >> 13) <= g.D - CL_LONG);
+        if (again && (int)(nextItem >> 13) <= g.D - CL_LONG) again = false;
+        while (longBits)
+        {
+            int src = __ffs(longBits) - 1;
+            longBits &= longBits - 1;
+            u32 it = __shfl_sync(FULL, nextItem, src);
+            u32 slot = it & 127u, k = (it >> 7) & 63u; int d = (int)(it >> 13);       // state: SAT needed at level d (d <= 31: one lane per level)
+            int e = d - (int)lane;
+            bool valid = e >= 1, sOk = false, mOk = false;
+            if (valid)
+            {
+                const float* v = sv[w][slot];
+                TriSat ot;
+                trisat_init(ot, mk3(v[0], v[1], v[2]), mk3(v[3], v[4], v[5]), mk3(v[6], v[7], v[8]));
+                u32 onx = sorg[w][slot][3] & 255u, ony = sorg[w][slot][3] >> 8;
+                u32 ix = sorg[w][slot][0] + k % onx, iy = sorg[w][slot][1] + (k / onx) % ony, iz = sorg[w][slot][2] + k / (onx * ony);
+                float bc[3], hs[3]; level_box(g, e, ix, iy, iz, bc, hs);
+                sOk = sat_box(ot, bc, hs);
+                mOk = true;                                                              // level 1 passed its SAT: accepted
+                if (e > 1) { level_box(g, e - 1, ix, iy, iz, bc, hs); mOk = vertex_inside(v, bc, hs, margin); }
+            }
+            unsigned failMask = __ballot_sync(FULL, valid && !sOk), accMask = __ballot_sync(FULL, valid && sOk && mOk);
+            // the walk visits the lanes in order: the first lane that rejects (SAT fails) or accepts (SAT passes, then margin) decides
+            bool accepted = accMask && (!failMask || __ffs(accMask) < __ffs(failMask));
+            if (accepted && lane == 0) atomicOr(&smask[w][slot][k >> 5], 1u << (k & 31u));
         }
         unsigned bits = __ballot_sync(FULL, again);
         if (again) ring[w][(tail + __popc(bits & ((1u << lane) - 1u))) % CL_RING] = nextItem;
         tail += __popc(bits);
         __syncwarp();
-    }
-    if (!valid) return;
-    if (large)
+    };
+
+    // ---- candidates, 32 per step: leaf-level margin check; the rest is queued for a SAT at that level -----------------------------------
+    for (u32 j0 = 0; j0 < total; j0 += 32)
     {
-        // large triangle: handed to the warp-cooperative descent (large_kernel), which fills counts[t]
-        counts[t] = 0; masks[t] = 0; infos[t] = 1ull << 63;
-        largeList[atomicAdd(largeCount, 1u)] = t;
-        return;
+        u32 j = j0 + lane;
+        bool need = false; u32 item = 0;
+        if (j < total)
+        {
+            // slot of candidate j: the last slot whose prefix is <= j (slots without candidates share their successor's prefix)
+            u32 loS = 0, hiS = CL_SLOTS;
+#pragma unroll
+            for (int it = 0; it < 7; it++) { u32 mid = (loS + hiS) >> 1; if (spre[w][mid] <= j) loS = mid; else hiS = mid; }
+            while (spre[w][loS + 1] <= j) ++loS;       // (defensive; the search above already lands on the last such slot)
+            u32 slot = loS, k = j - spre[w][slot];
+            u32 nx = sorg[w][slot][3] & 255u, ny = sorg[w][slot][3] >> 8;
+            u32 ix = sorg[w][slot][0] + k % nx, iy = sorg[w][slot][1] + (k / nx) % ny, iz = sorg[w][slot][2] + k / (nx * ny);
+            float bc[3], hs[3]; level_box(g, g.D, ix, iy, iz, bc, hs);
+            if (vertex_inside(sv[w][slot], bc, hs, margin)) atomicOr(&smask[w][slot][k >> 5], 1u << (k & 31u));
+            else { need = true; item = slot | (k << 7) | ((u32)g.D << 13); }
+        }
+        unsigned bits = __ballot_sync(FULL, need);
+        if (need) ring[w][(tail + __popc(bits & ((1u << lane) - 1u))) % CL_RING] = item;
+        tail += __popc(bits);
+        __syncwarp();
+        while (tail - head >= 32u) drain_step();
     }
-    u64 mask = smask[w][lane];
-    counts[t] = (u32)__popcll(mask);
-    masks[t] = mask;
-    infos[t] = empty ? 0ull : ((u64)lo[0] | ((u64)lo[1] << 11) | ((u64)lo[2] << 22) | ((u64)nx << 33) | ((u64)ny << 40));
+    while (head < tail) drain_step();
+    __syncwarp();
+
+    // ---- results ----------------------------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < CL_ROUNDS; r++)
+    {
+        u32 slot = r * 32 + lane, t = tBase + slot;
+        if (t >= numTris) continue;
+        if (largeBits & (1u << r))
+        {
+            // large triangle: handed to the warp-cooperative descent (large_kernel), which fills counts[t]
+            counts[t] = 0; masks[t] = 0; infos[t] = 1ull << 63;
+            largeList[atomicAdd(largeCount, 1u)] = t;
+            continue;
+        }
+        u64 mask = (u64)smask[w][slot][0] | ((u64)smask[w][slot][1] << 32);
+        counts[t] = (u32)__popcll(mask);
+        masks[t] = mask;
+        u32 nxy = sorg[w][slot][3];
+        infos[t] = (emptyBits & (1u << r)) ? 0ull : ((u64)sorg[w][slot][0] | ((u64)sorg[w][slot][1] << 11) | ((u64)sorg[w][slot][2] << 22) |
+                                                     ((u64)(nxy & 255u) << 33) | ((u64)(nxy >> 8) << 40));
+    }
 }
 
 __global__ void __launch_bounds__(KG_THREADS) emit_flat_kernel(Grid g, const float4* __restrict__ soup, u32 numTris, const u32* __restrict__ offsets,
@@ -347,7 +433,7 @@ int classify_pairs(const Grid& g, const float4* d_soup, u32 numTris, float margi
 {
     if (!numTris) return BM_OK;
     BM_CUDA(cudaMemsetAsync(d_largeCount, 0, 4, s));
-    classify_kernel<<<div_up(numTris, KG_THREADS), KG_THREADS, 0, s>>>(g, d_soup, numTris, margin, d_counts, d_masks, d_infos, d_largeList, d_largeCount);
+    classify_kernel<<<div_up(numTris, CL_WARPS * CL_SLOTS), CL_THREADS, 0, s>>>(g, d_soup, numTris, margin, d_counts, d_masks, d_infos, d_largeList, d_largeCount);
     BM_LAUNCHED();
     // large triangles (their number stays on the device: the grid is fixed, warps loop over the list)
     large_kernel<false><<<(unsigned)sm_count() * 2, WD_WARPS * 32, 0, s>>>(g, d_soup, d_largeList, d_largeCount, d_counts, nullptr, nullptr, nullptr);
