@@ -98,8 +98,15 @@ struct CameraIn { const float* initialRays; float eye[3]; float orient[9]; };
 // d_workCounter: one u32 of device scratch per launch in flight (the persistent warps' work queue head)
 // d_numRays (nullable): the ray count is read from device memory at kernel start (<= n, which then only sizes the grid)
 int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numRays, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s);
+// Temporal tile scheduling of camera launches (nullable): the kernel records what every 8x4 pixel tile cost, and the next launch of
+// the same frame size starts the expensive tiles first (longest-processing-time-first), so that the handful of long silhouette rays
+// overlaps with the bulk of the frame instead of forming its tail.  Any order is a permutation of the same tiles: results do not depend on it.
+//   cost[tiles]  cost of each tile in the last launch          order[tiles]  tile to run at each position (valid when state[TS_OK] != 0)
+//   state: [0, 64) histogram of cost buckets, [64, 128) scatter cursors (both zeroed per launch), [TS_OK] set by the ordering kernel
+constexpr int TS_BUCKETS = 64, TS_OK = 128, TS_WORDS = 132;
+struct TileSched { u32* cost; u32* order; u32* state; u32 tiles; };
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
-                 u64* d_counters, u32* d_workCounter, cudaStream_t s);
+                 u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s);
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
 int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials, const bmTexture* d_textures,
                u32 numTextures, u32* d_pixels, cudaStream_t s);

@@ -281,6 +281,37 @@ __device__ __forceinline__ bool slot_to_ray(u32 slot, u64 n, u32 width, u32 heig
     return px < width && py < height;
 }
 
+// cost -> one of TS_BUCKETS classes, two per power of two
+__device__ __forceinline__ u32 tile_bucket(u32 cost)
+{
+    u32 l = 31u - (u32)__clz((int)(cost | 1u));
+    u32 b = 2u * l + (l ? ((cost >> (l - 1u)) & 1u) : 0u);
+    return b < (u32)TS_BUCKETS ? b : (u32)TS_BUCKETS - 1u;
+}
+
+// order[] = tiles by descending cost bucket (counting sort on the histogram the trace kernel filled; order inside a bucket is arbitrary).
+// The result is only declared usable when the histogram accounts for every tile, i.e. every tile was costed by the launch before.
+__global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, u32* __restrict__ order)
+{
+    __shared__ u32 base[TS_BUCKETS];
+    __shared__ u32 total;
+    if (threadIdx.x == 0)
+    {
+        u32 run = 0;
+        for (int b = TS_BUCKETS - 1; b >= 0; --b) { base[b] = run; run += state[b]; }
+        total = run;
+    }
+    __syncthreads();
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < tiles && total == tiles)
+    {
+        u32 b = tile_bucket(cost[i]);
+        u32 pos = base[b] + atomicAdd(&state[TS_BUCKETS + b], 1u);
+        if (pos < tiles) order[pos] = i;
+    }
+    if (i == 0) state[TS_OK] = (total == tiles) ? 1u : 0u;
+}
+
 // Persistent warps (one resident grid; every warp pulls work from a global counter), while-while traversal:
 //   refill idle lanes -> all lanes with a pending internal node walk nodes until none has one -> all lanes with a pending
 //   leaf test its triangles together -> lanes whose ray is finished write their result and become idle.
@@ -289,7 +320,7 @@ __device__ __forceinline__ bool slot_to_ray(u32 slot, u64 n, u32 width, u32 heig
 template <int MODE, bool CAMERA, bool COUNT>
 __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
-                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int refillMin)
+                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int refillMin, TileSched sched)
 {
     const u32 rootRef = tv.numLeaves >= 2 ? __ldg(tv.root) : (tv.numLeaves == 1 ? (0u | LEAF_BIT) : REF_EMPTY);
     if (numRaysDev) { n = __ldg(numRaysDev); totalSlots = (u32)n; }       // count produced on the device (bmBounceRays): no host round trip
@@ -303,20 +334,43 @@ __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const
     V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), ic = mk3(0, 0, 1), oi = mk3(0, 0, 0);
     HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
     u32 nv = 0, nt = 0, nc = 0, rayStart = 0, longest = 0;      // COUNT only: totals, and the longest single ray (the kernel's critical path)
+    // temporal tile scheduling (camera launches; see TileSched): the tile this warp is working on and when it started
+    const bool useOrder = CAMERA && sched.order != nullptr && sched.state[TS_OK] != 0u;
+    u32 curTile = 0xFFFFFFFFu;
+    long long tileStart = 0;
 
     for (;;)
     {
         // ---- refill -----------------------------------------------------------------------------------------------------
         unsigned idle = __ballot_sync(FULL, !active);
+        if (CAMERA && sched.cost && idle == FULL && curTile != 0xFFFFFFFFu)
+        {
+            // the warp's tile is finished: its cost (32-cycle units) and cost bucket
+            if (lane == 0)
+            {
+                unsigned long long c = (unsigned long long)(clock64() - tileStart) >> 5;
+                u32 cost = c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)c;
+                sched.cost[curTile] = cost;
+                atomicAdd(&sched.state[tile_bucket(cost)], 1u);
+            }
+            curTile = 0xFFFFFFFFu;
+        }
         if (idle && !exhausted && (__popc(idle) >= refillMin || idle == FULL))
         {
             u32 base = 0;
             if (lane == 0) base = atomicAdd(workCounter, (u32)__popc(idle));
             base = __shfl_sync(FULL, base, 0);
             if (base >= totalSlots) exhausted = true;
+            if (CAMERA && sched.cost && idle == FULL && !(base & 31u) && base < totalSlots)
+            {
+                curTile = base >> 5;
+                if (useOrder) curTile = __ldg(sched.order + curTile);
+                tileStart = clock64();
+            }
             if (!active)
             {
                 u32 slot = base + __popc(idle & ((1u << lane) - 1u));
+                if (useOrder && slot < totalSlots) slot = (__ldg(sched.order + (slot >> 5)) << 5) | (slot & 31u);
                 if (slot < totalSlots && slot_to_ray(slot, n, width, height, rayIdx))
                 {
                     if (CAMERA)
@@ -522,7 +576,7 @@ int refill_min(bool camera)
 
 template <int MODE, bool CAMERA, bool COUNT>
 int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
-                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, cudaStream_t s)
+                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
 {
     static int blocksPerSM = 0;
     if (!blocksPerSM)
@@ -537,21 +591,33 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     u64 cap = (u64)sm_count() * blocksPerSM;
     if (blocks > cap) blocks = cap;
     BM_CUDA(cudaMemsetAsync(d_workCounter, 0, 4, s));
+    TileSched ts = { nullptr, nullptr, nullptr, 0 };
+    const int refill = refill_min(CAMERA);
+    if (CAMERA && sched && !COUNT && refill == 32 && sched->tiles == (u32)(slots / 32))
+    {
+        ts = *sched;
+        BM_CUDA(cudaMemsetAsync(ts.state, 0, 2 * TS_BUCKETS * 4, s));          // histogram + cursors; the OK flag of the previous launch stays
+    }
     trace_kernel<MODE, CAMERA, COUNT><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
-                                                                            d_counters, d_workCounter, leaf_break(), refill_min(CAMERA));
+                                                                            d_counters, d_workCounter, leaf_break(), refill, ts);
     BM_LAUNCHED();
+    if (ts.cost)
+    {
+        tile_order_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.order);
+        BM_LAUNCHED();
+    }
     return BM_OK;
 }
 
 template <bool CAMERA>
 int dispatch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, int mode, bmHit* d_hits, u32* d_pixels,
-                   const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, cudaStream_t s)
+                   const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
 {
     if (mode == BM_TRACE_REFERENCE)
-        return d_counters ? launch_trace<BM_TRACE_REFERENCE, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
-                          : launch_trace<BM_TRACE_REFERENCE, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
-    return d_counters ? launch_trace<BM_TRACE_CLOSEST, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s)
-                      : launch_trace<BM_TRACE_CLOSEST, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
+        return d_counters ? launch_trace<BM_TRACE_REFERENCE, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s)
+                          : launch_trace<BM_TRACE_REFERENCE, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
+    return d_counters ? launch_trace<BM_TRACE_CLOSEST, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s)
+                      : launch_trace<BM_TRACE_CLOSEST, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
 }
 } // namespace
 
@@ -559,14 +625,14 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numR
 {
     if (!n) return BM_OK;
     CameraIn cam = {};
-    return dispatch_trace<false>(tv, d_rays, cam, n, d_numRays, 0, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, s);
+    return dispatch_trace<false>(tv, d_rays, cam, n, d_numRays, 0, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, nullptr, s);
 }
 
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
-                 u64* d_counters, u32* d_workCounter, cudaStream_t s)
+                 u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    return dispatch_trace<true>(tv, nullptr, cam, n, nullptr, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, s);
+    return dispatch_trace<true>(tv, nullptr, cam, n, nullptr, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
 }
 
 int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials, const bmTexture* d_textures,

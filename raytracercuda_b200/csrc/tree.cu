@@ -62,7 +62,8 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false, imported = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState;
+    u32 schedTiles = 0;              // frame size (in 8x4 tiles) the tile-scheduling buffers are set up for; 0 = none
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
     u32 maxLeaf = 0, overLeaves = 0;
@@ -77,7 +78,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -110,6 +111,7 @@ static int tree_build(bmTree* t)
     for (auto& m : t->staged) { t->meshBase.push_back((u32)T); T += m.numTris; }
     if (T >= 0xFFFFFFFFull) { set_error("more than 2^32-2 triangles"); return BM_ERROR_CAPACITY; }
     t->T = T; t->P = 0; t->L = 0; t->maxLeaf = 0; t->overLeaves = 0;
+    t->schedTiles = 0;               // a new scene: forget the tile costs of the old one
     BM_TRY(t->scalars.reserve(64)); BM_TRY(t->rootDev.reserve(16));
     BM_CUDA(cudaMemsetAsync(t->scalars.p, 0, 64, s));
     BM_CUDA(cudaMemsetAsync(t->rootDev.p, 0, 16, s));
@@ -419,7 +421,25 @@ extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t nu
     memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
     if (width && numRays % width) return BM_ERROR_INVALID_PARAMETER;
     BM_TRY(t->scalars.reserve(64));
-    return trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, t->stream);
+    // temporal tile scheduling (TileSched, bm_device.cuh): per tree and frame size; BM_TILE_ORDER=0 turns it off
+    static const bool tileOrderOn = !(getenv("BM_TILE_ORDER") && atoi(getenv("BM_TILE_ORDER")) == 0);
+    TileSched sched = { nullptr, nullptr, nullptr, 0 };
+    if (tileOrderOn && width && !d_counters)
+    {
+        uint32_t height = (uint32_t)(numRays / width);
+        uint64_t tiles = (uint64_t)((width + 7) / 8) * ((height + 3) / 4);
+        if (tiles >= 256 && tiles < 0x07FFFFFFull)
+        {
+            if (t->schedTiles != (u32)tiles)
+            {
+                BM_TRY(t->tileCost.reserve(tiles * 4)); BM_TRY(t->tileOrder.reserve(tiles * 4)); BM_TRY(t->tileState.reserve(TS_WORDS * 4));
+                BM_CUDA(cudaMemsetAsync(t->tileState.p, 0, TS_WORDS * 4, t->stream));      // no order yet
+                t->schedTiles = (u32)tiles;
+            }
+            sched = { t->tileCost.as<u32>(), t->tileOrder.as<u32>(), t->tileState.as<u32>(), (u32)tiles };
+        }
+    }
+    return trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream);
 }
 
 extern "C" int bmCameraRays(const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
