@@ -61,6 +61,8 @@ struct TreeView
 size_t scan_temp_bytes(size_t n);
 // out[i] = sum(in[0..i-1]); *d_total (device, nullable) = sum of all. in == out allowed. temp: scan_temp_bytes(n) bytes.
 int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s);
+// out[i] = number of hit records (tri != 0xFFFFFFFF) among d_hits[0..i-1]; *d_total = their number. Same temp as above.
+int exclusive_scan_hit_flags(const bmHit* d_hits, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s);
 
 // ---- sort.cu --------------------------------------------------------------------------------------------------------
 size_t sort_temp_bytes(size_t n);

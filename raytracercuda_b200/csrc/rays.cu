@@ -44,12 +44,6 @@ __global__ void camera_rays_kernel(CameraIn cam, u64 n, u32 width, float jitterX
     out[i] = o;
 }
 
-__global__ void hit_flags_kernel(const bmHit* __restrict__ hits, u64 n, u32* __restrict__ flags)
-{
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    flags[i] = hits[i].tri != 0xFFFFFFFFu ? 1u : 0u;
-}
 
 template <bool CAMERA>
 __global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, const bmHit* __restrict__ hits, const u32* __restrict__ offsets, u64 n,
@@ -159,9 +153,7 @@ int bounce_rays(const bmRay* d_rays, const CameraIn* cam, const bmHit* d_hits, u
                 u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s)
 {
     if (!n) { BM_CUDA(cudaMemsetAsync(d_count, 0, 4, s)); return BM_OK; }
-    hit_flags_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits, n, d_flagsAndOffsets);
-    BM_LAUNCHED();
-    BM_TRY(exclusive_scan_u32(d_flagsAndOffsets, d_flagsAndOffsets, n, d_count, d_scanTemp, s));
+    BM_TRY(exclusive_scan_hit_flags(d_hits, d_flagsAndOffsets, n, d_count, d_scanTemp, s));
     if (cam) bounce_kernel<true><<<div_up(n, 256), 256, 0, s>>>(nullptr, *cam, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex);
     else { CameraIn none = {}; bounce_kernel<false><<<div_up(n, 256), 256, 0, s>>>(d_rays, none, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex); }
     BM_LAUNCHED();

@@ -46,6 +46,9 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total)
 // order); the wait is bounded and traps instead of hanging.  status word = flag << 32 | value, flag 1 = aggregate, 2 = inclusive.
 #define ST_AGG (1ull << 32)
 #define ST_INC (2ull << 32)
+// HITS: the input is an array of 16-byte hit records and the scanned value is "this record is a hit" (bounce-ray compaction without a
+// separate flag pass)
+template <bool HITS>
 __global__ void __launch_bounds__(SCAN_THREADS) lookback_scan_kernel(const u32* in, u32* out, size_t n, u32* __restrict__ totalOut,   // in == out allowed
                                                                      u32* ticket, volatile unsigned long long* status, u32 numTiles)
 {
@@ -55,7 +58,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) lookback_scan_kernel(const u32* 
     const u32 tile = sTile;
     size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     u32 v[SCAN_ITEMS], s = 0;
-    if (base + SCAN_ITEMS <= n && (((uintptr_t)(in + base)) & 15) == 0)
+    if (HITS)
+    {
+        const uint4* h = reinterpret_cast<const uint4*>(in);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n && h[base + i].w != 0xFFFFFFFFu) ? 1u : 0u; s += v[i]; }
+    }
+    else if (base + SCAN_ITEMS <= n && (((uintptr_t)(in + base)) & 15) == 0)
     {
         const uint4* p = reinterpret_cast<const uint4*>(in + base);
         uint4 a = p[0], b = p[1];
@@ -165,7 +174,20 @@ int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void
     unsigned long long* status = (unsigned long long*)d_temp;
     u32* ticket = (u32*)(status + tiles);
     BM_CUDA(cudaMemsetAsync(d_temp, 0, tiles * 8 + 8, s));
-    lookback_scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_total, ticket, status, (u32)tiles);
+    lookback_scan_kernel<false><<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_total, ticket, status, (u32)tiles);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+
+// out[i] = number of hits among hits[0..i-1]; *d_total = number of hits
+int exclusive_scan_hit_flags(const bmHit* d_hits, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s)
+{
+    if (n == 0) { if (d_total) BM_CUDA(cudaMemsetAsync(d_total, 0, 4, s)); return BM_OK; }
+    size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    unsigned long long* status = (unsigned long long*)d_temp;
+    u32* ticket = (u32*)(status + tiles);
+    BM_CUDA(cudaMemsetAsync(d_temp, 0, tiles * 8 + 8, s));
+    lookback_scan_kernel<true><<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(reinterpret_cast<const u32*>(d_hits), d_out, n, d_total, ticket, status, (u32)tiles);
     BM_LAUNCHED();
     return BM_OK;
 }
