@@ -103,9 +103,11 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numR
 // Temporal tile scheduling of camera launches (nullable): the kernel records what every 8x4 pixel tile cost, and the next launch of
 // the same frame size starts the expensive tiles first (longest-processing-time-first), so that the handful of long silhouette rays
 // overlaps with the bulk of the frame instead of forming its tail.  Any order is a permutation of the same tiles: results do not depend on it.
-//   cost[tiles]  cost of each tile in the last launch          order[tiles]  tile to run at each position (valid when state[TS_OK] != 0)
-//   state: [0, 64) histogram of cost buckets, [64, 128) scatter cursors (both zeroed per launch), [TS_OK] set by the ordering kernel
-constexpr int TS_BUCKETS = 64, TS_OK = 128, TS_WORDS = 132;
+//   cost[tiles]  cost of each tile in the last launch          order[4*tiles]  work list of the next launch (valid when state[TS_OK] != 0):
+//                tiles by descending cost, the most expensive ones as four quarter entries; state[TS_ENTRIES] = its length
+//   state: [0, 64) histogram of cost buckets, [64, 128) scatter cursors, [TS_SUM] 64-bit total cost (all zeroed per launch), [TS_OK] and
+//          [TS_ENTRIES] set by the ordering kernel
+constexpr int TS_BUCKETS = 64, TS_SUM = 128, TS_OK = 130, TS_ENTRIES = 131, TS_WORDS = 132;       // [0, TS_OK) is zeroed before every launch
 struct TileSched { u32* cost; u32* order; u32* state; u32 tiles; };
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
                  u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s);

@@ -289,27 +289,69 @@ __device__ __forceinline__ u32 tile_bucket(u32 cost)
     return b < (u32)TS_BUCKETS ? b : (u32)TS_BUCKETS - 1u;
 }
 
-// order[] = tiles by descending cost bucket (counting sort on the histogram the trace kernel filled; order inside a bucket is arbitrary).
-// The result is only declared usable when the histogram accounts for every tile, i.e. every tile was costed by the launch before.
-__global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, u32* __restrict__ order)
+// After a camera launch: histogram of the tiles' cost buckets ...
+__global__ void tile_hist_kernel(u32 tiles, const u32* __restrict__ cost, u32* state)
+{
+    __shared__ u32 h[TS_BUCKETS];
+    if (threadIdx.x < TS_BUCKETS) h[threadIdx.x] = 0;
+    __syncthreads();
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 c = i < tiles ? cost[i] : 0u;
+    if (i < tiles) atomicAdd(&h[tile_bucket(c)], 1u);
+    // total cost of the frame (64 bits in state[TS_SUM], state[TS_SUM + 1])
+    unsigned long long sum = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(reinterpret_cast<unsigned long long*>(state + TS_SUM), sum);
+    __syncthreads();
+    if (threadIdx.x < TS_BUCKETS && h[threadIdx.x]) atomicAdd(&state[threadIdx.x], h[threadIdx.x]);
+}
+
+// ... then the work list of the next launch: tiles by descending cost bucket (counting sort; the order inside a bucket is arbitrary).
+// Tiles that would be the launch's critical path -- cost above splitPct % of the ideal makespan (total cost / resident warps); on the
+// bench frame some 250 silhouette tiles that each cost ~20x the average -- are entered as four QUARTERS (one 8-pixel row each, entry =
+// tile | (row + 1) << 28), so that four warps share them.  Quarters run at 8 of 32 lanes, so splitting more than those loses throughput
+// (measured: splitting the top 1/256 of the tiles -9 % launch time, the top 1/64 +0 %, the top 1/16 +27 %).  state[TS_ENTRIES] = number of entries; state[TS_OK] says the list is usable (every tile was costed).
+__global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, u32* __restrict__ order, u32 splitPct, u32 residentWarps)
 {
     __shared__ u32 base[TS_BUCKETS];
-    __shared__ u32 total;
+    __shared__ u32 total, entries, splitFrom;
     if (threadIdx.x == 0)
     {
-        u32 run = 0;
-        for (int b = TS_BUCKETS - 1; b >= 0; --b) { base[b] = run; run += state[b]; }
-        total = run;
+        u32 run = 0, sf = TS_BUCKETS;
+        if (splitPct)
+        {
+            unsigned long long sum = *reinterpret_cast<const unsigned long long*>(state + TS_SUM);
+            unsigned long long thr = sum / (residentWarps ? residentWarps : 1u) * splitPct / 100ull;        // cost a tile must exceed to be split
+            for (int b = TS_BUCKETS - 1; b >= 2; --b)
+            {
+                u32 l = (u32)b >> 1;
+                unsigned long long lower = (1ull << l) + (((u32)b & 1u) ? (1ull << (l - 1u)) : 0ull);     // smallest cost of bucket b
+                if (lower >= thr && thr > 0 && run + state[b] <= tiles / 32u) { run += state[b]; sf = (u32)b; } else break;
+            }
+        }
+        u32 pos = 0; run = 0;
+        for (int b = TS_BUCKETS - 1; b >= 0; --b) { base[b] = pos; pos += state[b] * ((u32)b >= sf ? 4u : 1u); run += state[b]; }
+        total = run; entries = pos; splitFrom = sf;
     }
     __syncthreads();
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < tiles && total == tiles)
     {
         u32 b = tile_bucket(cost[i]);
-        u32 pos = base[b] + atomicAdd(&state[TS_BUCKETS + b], 1u);
-        if (pos < tiles) order[pos] = i;
+        u32 k = atomicAdd(&state[TS_BUCKETS + b], 1u);
+        if (b >= splitFrom)
+        {
+            u32 pos = base[b] + 4u * k;
+            if (pos + 3u < 4u * tiles) { order[pos] = i | (1u << 28); order[pos + 1] = i | (2u << 28); order[pos + 2] = i | (3u << 28); order[pos + 3] = i | (4u << 28); }
+        }
+        else
+        {
+            u32 pos = base[b] + k;
+            if (pos < 4u * tiles) order[pos] = i;
+        }
     }
-    if (i == 0) state[TS_OK] = (total == tiles) ? 1u : 0u;
+    if (i == 0) { state[TS_ENTRIES] = entries; state[TS_OK] = (total == tiles) ? 1u : 0u; }
 }
 
 // Persistent warps (one resident grid; every warp pulls work from a global counter), while-while traversal:
@@ -336,6 +378,7 @@ __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const
     u32 nv = 0, nt = 0, nc = 0, rayStart = 0, longest = 0;      // COUNT only: totals, and the longest single ray (the kernel's critical path)
     // temporal tile scheduling (camera launches; see TileSched): the tile this warp is working on and when it started
     const bool useOrder = CAMERA && sched.order != nullptr && sched.state[TS_OK] != 0u;
+    if (useOrder) totalSlots = sched.state[TS_ENTRIES] * 32u;      // the work list may hold some tiles as four quarter entries
     u32 curTile = 0xFFFFFFFFu;
     long long tileStart = 0;
 
@@ -350,8 +393,7 @@ __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const
             {
                 unsigned long long c = (unsigned long long)(clock64() - tileStart) >> 5;
                 u32 cost = c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)c;
-                sched.cost[curTile] = cost;
-                atomicAdd(&sched.state[tile_bucket(cost)], 1u);
+                atomicAdd(&sched.cost[curTile], cost);          // zeroed before the launch; the quarters of a split tile add up
             }
             curTile = 0xFFFFFFFFu;
         }
@@ -361,17 +403,25 @@ __global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const
             if (lane == 0) base = atomicAdd(workCounter, (u32)__popc(idle));
             base = __shfl_sync(FULL, base, 0);
             if (base >= totalSlots) exhausted = true;
-            if (CAMERA && sched.cost && idle == FULL && !(base & 31u) && base < totalSlots)
+            u32 quarter = 0;                                     // 1..4: this fetch is one 8-pixel row of a split tile
+            if (CAMERA && sched.cost && base < totalSlots)
             {
-                curTile = base >> 5;
-                if (useOrder) curTile = __ldg(sched.order + curTile);
+                // (scheduled camera launches refill whole warps only: idle == FULL and base is a multiple of 32)
+                u32 entry = base >> 5;
+                if (useOrder) entry = __ldg(sched.order + entry);
+                curTile = entry & 0x0FFFFFFFu; quarter = entry >> 28;
                 tileStart = clock64();
             }
             if (!active)
             {
                 u32 slot = base + __popc(idle & ((1u << lane) - 1u));
-                if (useOrder && slot < totalSlots) slot = (__ldg(sched.order + (slot >> 5)) << 5) | (slot & 31u);
-                if (slot < totalSlots && slot_to_ray(slot, n, width, height, rayIdx))
+                bool take = slot < totalSlots;
+                if (CAMERA && sched.cost && take)
+                {
+                    if (quarter) { take = lane < 8u; slot = (curTile << 5) | ((quarter - 1u) << 3) | (lane & 7u); }
+                    else slot = (curTile << 5) | lane;
+                }
+                if (take && slot_to_ray(slot, n, width, height, rayIdx))
                 {
                     if (CAMERA)
                     {
@@ -567,6 +617,14 @@ int leaf_break()
 // 8x4 tile before taking the next one: keeping the lanes on neighbouring rays is worth more than filling the holes early); ray batches
 // want 8 (an incoherent batch on the 10 M soup: 54.9 Mrays/s at 8 vs 38.9 at 32; the c2 bounce batch loses 7 % against 32).
 // BM_REFILL_MIN overrides both, for tuning.
+// a tile is split into quarters when it cost more than this percentage of the ideal makespan; BM_TILE_SPLIT=0 disables splitting
+u32 tile_split_pct()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BM_TILE_SPLIT"); v = e ? atoi(e) : 75; if (v < 0) v = 75; }
+    return (u32)v;
+}
+
 int refill_min(bool camera)
 {
     static int v = 0;
@@ -596,14 +654,17 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     if (CAMERA && sched && !COUNT && refill == 32 && sched->tiles == (u32)(slots / 32))
     {
         ts = *sched;
-        BM_CUDA(cudaMemsetAsync(ts.state, 0, 2 * TS_BUCKETS * 4, s));          // histogram + cursors; the OK flag of the previous launch stays
+        BM_CUDA(cudaMemsetAsync(ts.state, 0, TS_OK * 4, s));          // histogram + cursors; OK flag and entry count of the previous launch stay
+        BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
     }
     trace_kernel<MODE, CAMERA, COUNT><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
                                                                             d_counters, d_workCounter, leaf_break(), refill, ts);
     BM_LAUNCHED();
     if (ts.cost)
     {
-        tile_order_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.order);
+        tile_hist_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state);
+        BM_LAUNCHED();
+        tile_order_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.order, tile_split_pct(), (u32)blocks * (TR_THREADS / 32));
         BM_LAUNCHED();
     }
     return BM_OK;

@@ -432,7 +432,7 @@ extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t nu
         {
             if (t->schedTiles != (u32)tiles)
             {
-                BM_TRY(t->tileCost.reserve(tiles * 4)); BM_TRY(t->tileOrder.reserve(tiles * 4)); BM_TRY(t->tileState.reserve(TS_WORDS * 4));
+                BM_TRY(t->tileCost.reserve(tiles * 4)); BM_TRY(t->tileOrder.reserve(tiles * 16)); BM_TRY(t->tileState.reserve(TS_WORDS * 4));
                 BM_CUDA(cudaMemsetAsync(t->tileState.p, 0, TS_WORDS * 4, t->stream));      // no order yet
                 t->schedTiles = (u32)tiles;
             }
