@@ -237,3 +237,47 @@ def test_export_import_replica_traces_identically(meshes, beam_lib, cuda_device)
     assert beam_lib.bmTreeStats(h, st8) == 0 and st8[2] == st["leaves"]
     beam_lib.bmTreeDestroy(h)
     t.close()
+
+
+@pytest.mark.parametrize("name,W,H", [("bunny", 640, 360), ("suzanne", 203, 77)])
+def test_repeated_frames_follow_the_tile_schedule_and_do_not_change(name, W, H, meshes, oracle_lib, beam_lib, cuda_device):
+    """From the second camera launch of a frame size on, the kernel follows the work list built from the previous launch's tile costs
+    (expensive tiles first, the costliest as four quarter entries).  Every frame -- same view, a moved eye (stale costs), another
+    resolution in between (state reset) -- must equal the oracle / the first frame bit for bit; partial tiles included (203x77)."""
+    import torch
+    from raytracercuda_b200.tree import Tree, hits_to_numpy, make_mesh_table
+    P, I, N = meshes[name]
+    t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+    s = OracleScene(oracle_lib); s.add_mesh(P, I, N); s.build()
+    Pd, Id = t._meshes[0]
+    Nd = torch.from_numpy(N).to(cuda_device)
+    table = make_mesh_table([(Pd, Id, Nd)], cuda_device)
+    rays = oracle_lib.initial_rays(W, H)
+    px = torch.empty(W * H, dtype=torch.int32, device=cuda_device)
+    want = {}
+    for eye in (EYE, [0.3, 0.1, -2.0]):
+        r = s.trace_camera(rays, eye, ID3, 0, NT)
+        otri = np.where(r["tri"] == 0xFFFFFFFF, np.uint32(0xFFFFFFFF), r["tri"]).astype(np.uint32)
+        want[tuple(eye)] = (otri, r["t"], r["pixels"], r["tie"] == 0)
+    seq = [EYE, EYE, EYE, [0.3, 0.1, -2.0], [0.3, 0.1, -2.0], EYE, EYE]
+    first = None
+    for k, eye in enumerate(seq):
+        hits, _ = t.trace_camera(rays, eye, ID3, pixels=px, mesh_table=table, width=W)
+        h = hits_to_numpy(hits); gp = px.cpu().numpy().view(np.uint32).copy()
+        otri, ot, opx, ok = want[tuple(eye)]
+        assert np.array_equal(h["tri"][ok], otri[ok]), "frame %d" % k
+        both = ok & (otri != 0xFFFFFFFF)
+        assert np.array_equal(h["t"][both], ot[both]), "frame %d" % k
+        assert np.array_equal(gp[ok], opx[ok]), "frame %d" % k
+        if k == 0:
+            first = (h["tri"].copy(), h["t"].copy(), gp)
+        if k in (1, 2, 5, 6):
+            assert np.array_equal(h["tri"], first[0]) and np.array_equal(h["t"], first[1]) and np.array_equal(gp, first[2]), "frame %d differs from frame 0" % k
+        if k == 4:
+            # another frame size in between resets the schedule
+            r2 = oracle_lib.initial_rays(64, 40)
+            h2, _ = t.trace_camera(r2, EYE, ID3, width=64)
+            o2 = s.trace_camera(r2, EYE, ID3, 0, NT)
+            ok2 = o2["tie"] == 0
+            assert np.array_equal(hits_to_numpy(h2)["tri"][ok2], o2["tri"][ok2])
+    t.close(); s.close()
