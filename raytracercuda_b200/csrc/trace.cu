@@ -359,8 +359,11 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
 //   leaf test its triangles together -> lanes whose ray is finished write their result and become idle.
 // Keeping the two phases warp-synchronous is what lifts SIMT efficiency: in the first version (profiles/r1_a) only 11 of
 // 32 lanes were active on average because leaf loops and node walks of different lanes serialised each other.
+#ifndef BM_TR_BLOCKS
+#define BM_TR_BLOCKS 6
+#endif
 template <int MODE, bool CAMERA, bool COUNT>
-__global__ void __launch_bounds__(TR_THREADS, 6) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
+__global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
                                                            const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int refillMin, TileSched sched)
 {
