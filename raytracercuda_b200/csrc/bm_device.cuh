@@ -39,10 +39,9 @@ int sm_count();
 //             face index in mesh).  EXCLUDED marks pairs beyond the reference's 256-faces-per-leaf cap (BuildTree.cuh:17).
 //  clusters : 32 bytes per group of CLUSTER consecutive pairs of one leaf: float4 (lo.xyz, hi.x) (hi.y, hi.z, -, -) = padded
 //             union of the group's whole triangles.  A leaf tests a group's triangles only if the ray's line meets its box.
-#ifndef BM_SUB_BITS
-#define BM_SUB_BITS 9
-#endif
-constexpr int SUB_BITS = BM_SUB_BITS;      // multiple of 3
+// in-cell sub-key width (Grid::subBits): 9 bits keep the sort key at 40 bits = 5 radix passes; meshes much finer than the leaf cells
+// (hundreds of faces per leaf) get 15 bits, which tightens the 4-face cluster boxes inside such leaves (tree.cu picks per build)
+constexpr int SUB_BITS_COARSE = 9, SUB_BITS_FINE = 15;
 constexpr int CLUSTER = 4;
 constexpr int NODE_F4 = 8, LEAF_F4 = 3, CLUSTER_F4 = 2;
 static const u32 LEAF_BIT = 0x80000000u;
@@ -82,7 +81,7 @@ int emit_pairs_flat(const Grid& g, const float4* d_soup, u32 numTris, const u32*
                     const u32* d_largeCount, u64* d_keys, u32* d_vals, cudaStream_t s);
 
 // ---- hierarchy.cu ---------------------------------------------------------------------------------------------------
-int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s);
+int mark_heads(const u64* d_keys, size_t n, int subBits, u32* d_flags, cudaStream_t s);
 int write_leaves(const Grid& g, const u64* d_keys, const u32* d_flags, const u32* d_leafIdx, size_t n, u32 numLeaves, float4* d_leaves, u32* d_clusterCounts,
                  u32* d_codes, cudaStream_t s);
 int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_ltris, cudaStream_t s);
@@ -92,7 +91,7 @@ int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* 
 // radix tree + tight boxes + reference-node data in one bottom-up pass; *d_root receives the root's node index
 int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
                     float4* d_nodes, u32* d_root, cudaStream_t s);
-int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, u64* d_out, cudaStream_t s);
+int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, int subBits, u64* d_out, cudaStream_t s);
 int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s);
 
 // ---- trace.cu -------------------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ inline void fill_grid(Grid& g, const HostGrid& h, const float* t0, const float* 
 {
     g.tab[0] = t0; g.tab[1] = t1; g.tab[2] = t2;
     for (int a = 0; a < 3; a++) { g.k[a] = h.k[a]; g.wmin[a] = h.wmin[a]; g.w[a] = h.w[a]; }
-    g.D = h.D; g.uniform = h.uniform;
+    g.D = h.D; g.uniform = h.uniform; g.subBits = 9;
 }
 
 // Replays the reference's subdivision rule on the world box (BuildTree.cu:196-216): at depth d the node is a leaf when

@@ -12,11 +12,11 @@ namespace bm
 {
 namespace
 {
-__global__ void mark_heads_kernel(const u64* __restrict__ keys, size_t n, u32* __restrict__ flags)
+__global__ void mark_heads_kernel(const u64* __restrict__ keys, size_t n, int subBits, u32* __restrict__ flags)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    flags[i] = (i == 0 || (keys[i] >> SUB_BITS) != (keys[i - 1] >> SUB_BITS)) ? 1u : 0u;
+    flags[i] = (i == 0 || (keys[i] >> subBits) != (keys[i - 1] >> subBits)) ? 1u : 0u;
 }
 
 __global__ void write_leaves_kernel(Grid g, const u64* __restrict__ keys, const u32* __restrict__ flags, const u32* __restrict__ leafIdx, size_t n,
@@ -28,7 +28,7 @@ __global__ void write_leaves_kernel(Grid g, const u64* __restrict__ keys, const 
     // run length: scan forward to the next head (leaves are short: <= a few hundred pairs)
     size_t j = i + 1;
     while (j < n && !flags[j]) ++j;
-    u32 l = leafIdx[i], code = (u32)(keys[i] >> SUB_BITS), cnt = (u32)(j - i);
+    u32 l = leafIdx[i], code = (u32)(keys[i] >> g.subBits), cnt = (u32)(j - i);
     u32 ix, iy, iz; decode_path(g.D, code, ix, iy, iz);
     V3 mn, mx; cell_box(g, g.D, ix, iy, iz, mn, mx);
     float4* o = leaves + LEAF_F4 * (size_t)l;
@@ -213,11 +213,11 @@ __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 nu
     }
 }
 
-// (code << SUB_BITS | sub, tri)  ->  (code << 32 | tri): the key whose order is the canonical (code, triangle) order
-__global__ void canonical_keys_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, size_t n, u64* __restrict__ out)
+// (code << subBits | sub, tri)  ->  (code << 32 | tri): the key whose order is the canonical (code, triangle) order
+__global__ void canonical_keys_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, size_t n, int subBits, u64* __restrict__ out)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = ((keys[i] >> SUB_BITS) << 32) | vals[i];
+    if (i < n) out[i] = ((keys[i] >> subBits) << 32) | vals[i];
 }
 __global__ void split_canonical_kernel(const u64* __restrict__ keys, size_t n, u32* __restrict__ code, u32* __restrict__ tri)
 {
@@ -228,10 +228,10 @@ __global__ void split_canonical_kernel(const u64* __restrict__ keys, size_t n, u
 }
 } // namespace
 
-int mark_heads(const u64* d_keys, size_t n, u32* d_flags, cudaStream_t s)
+int mark_heads(const u64* d_keys, size_t n, int subBits, u32* d_flags, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    mark_heads_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, n, d_flags);
+    mark_heads_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, n, subBits, d_flags);
     BM_LAUNCHED();
     return BM_OK;
 }
@@ -271,10 +271,10 @@ int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const floa
     BM_LAUNCHED();
     return BM_OK;
 }
-int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, u64* d_out, cudaStream_t s)
+int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, int subBits, u64* d_out, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    canonical_keys_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, d_vals, n, d_out);
+    canonical_keys_kernel<<<div_up(n, 256), 256, 0, s>>>(d_keys, d_vals, n, subBits, d_out);
     BM_LAUNCHED();
     return BM_OK;
 }

@@ -35,13 +35,13 @@ struct NoEmit { BM_HD void operator()(u32, u32, u32, u32) const {} };
 // cell (centre of the triangle's box clipped to the cell, 5 bits per axis).  The code part decides everything parity is
 // defined on; the sub-key only orders the triangles of one leaf spatially so that consecutive groups of four get tight
 // cluster boxes (hierarchy.cu).  It is not part of any reference behaviour, so its arithmetic is free.
-// sub-key of a pair: SUB_BITS-bit Morton code of the centre of (triangle box clipped to the cell) inside the cell
+// sub-key of a pair: g.subBits-bit Morton code of the centre of (triangle box clipped to the cell) inside the cell
 __device__ __forceinline__ u32 sub_key(const Grid& g, u32 ix, u32 iy, u32 iz, V3 tmin, V3 tmax)
 {
     V3 mn, mx; cell_box(g, g.D, ix, iy, iz, mn, mx);
     float cx = .5f * (fmaxf(tmin.x, mn.x) + fminf(tmax.x, mx.x)), cy = .5f * (fmaxf(tmin.y, mn.y) + fminf(tmax.y, mx.y)),
           cz = .5f * (fmaxf(tmin.z, mn.z) + fminf(tmax.z, mx.z));
-    constexpr int Q = 1 << (SUB_BITS / 3);
+    const int Q = 1 << (g.subBits / 3);
     int qx = (int)((cx - mn.x) / (mx.x - mn.x) * (float)Q), qy = (int)((cy - mn.y) / (mx.y - mn.y) * (float)Q), qz = (int)((cz - mn.z) / (mx.z - mn.z) * (float)Q);
     qx = min(max(qx, 0), Q - 1); qy = min(max(qy, 0), Q - 1); qz = min(max(qz, 0), Q - 1);
     return (spread3((u32)qx) << 2) | (spread3((u32)qy) << 1) | spread3((u32)qz);
@@ -52,7 +52,7 @@ struct WriteEmit
     u64* keys; u32* vals; u32 pos; u32 tri; const Grid* g; V3 tmin, tmax;
     __device__ void operator()(u32 code, u32 ix, u32 iy, u32 iz)
     {
-        keys[pos] = ((u64)code << SUB_BITS) | sub_key(*g, ix, iy, iz, tmin, tmax); vals[pos] = tri; ++pos;
+        keys[pos] = ((u64)code << g->subBits) | sub_key(*g, ix, iy, iz, tmin, tmax); vals[pos] = tri; ++pos;
     }
 };
 
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(KG_THREADS) emit_flat_kernel(Grid g, const flo
         u32 bit = (u32)__ffsll((long long)mask) - 1u;
         mask &= mask - 1ull;
         u32 ix = x0 + bit % nx, iy = y0 + (bit / nx) % ny, iz = z0 + bit / (nx * ny);
-        keys[pos] = ((u64)encode_path(g.D, ix, iy, iz) << SUB_BITS) | sub_key(g, ix, iy, iz, tmin, tmax);
+        keys[pos] = ((u64)encode_path(g.D, ix, iy, iz) << g.subBits) | sub_key(g, ix, iy, iz, tmin, tmax);
         vals[pos] = t;
         ++pos;
     }
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(WD_WARPS * 32) large_kernel(Grid g, const floa
                     if (EMIT)
                     {
                         u32 pos = outPos + __popc(leafBits & ((1u << lane) - 1u));
-                        keys[pos] = ((u64)encode_path(g.D, cx, cy, cz) << SUB_BITS) | sub_key(g, cx, cy, cz, tmin, tmax);
+                        keys[pos] = ((u64)encode_path(g.D, cx, cy, cz) << g.subBits) | sub_key(g, cx, cy, cz, tmin, tmax);
                         vals[pos] = t;
                     }
                 }

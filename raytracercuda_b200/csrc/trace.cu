@@ -365,7 +365,7 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
 template <int MODE, bool CAMERA, bool COUNT>
 __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
-                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int refillMin, TileSched sched)
+                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int leafWait, int refillMin, TileSched sched)
 {
     const u32 rootRef = tv.numLeaves >= 2 ? __ldg(tv.root) : (tv.numLeaves == 1 ? (0u | LEAF_BIT) : REF_EMPTY);
     if (numRaysDev) { n = __ldg(numRaysDev); totalSlots = (u32)n; }       // count produced on the device (bmBounceRays): no host round trip
@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
         if (!__any_sync(FULL, active)) break;
 
         // ---- phase 1: internal nodes, until no lane has one pending ----------------------------------------------------------
+        int waited = 0;                                    // node steps taken while at least leafBreak lanes were waiting at a leaf
         for (;;)
         {
             bool inner = active && cur != REF_EMPTY && !(cur & LEAF_BIT);
@@ -461,8 +462,10 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
             // ray batches (bounce / incoherent rays): once enough lanes wait at a leaf, serve them instead of idling them until the last
             // lane arrives -- such rays reach their leaves at very different times (a soup batch ran at 7 of 32 lanes, profiles/r1_c5).
             // Measured: threshold 16 gives +6 % (reference) / +24 % (closest) on the soup; camera launches (coherent 8x4 tiles) are
-            // 4 % faster without the rule, so they skip it.
-            if (!CAMERA && __popc(__ballot_sync(FULL, active && cur != REF_EMPTY && (cur & LEAF_BIT))) >= leafBreak) break;
+            // 4 % faster without the rule, so they skip it.  Coherent BATCHES (jittered camera rays of the multi-sample frames) lose 10 %
+            // if the break is immediate -- their stragglers are only a step or two behind -- so the waiting lanes first sit out
+            // LEAF_WAIT node steps.
+            if (!CAMERA && __popc(__ballot_sync(FULL, active && cur != REF_EMPTY && (cur & LEAF_BIT))) >= leafBreak && ++waited > leafWait) break;
             if (inner)
             {
                 if (COUNT) nv++;
@@ -616,6 +619,13 @@ int leaf_break()
     return v;
 }
 
+int leaf_wait()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BM_LEAF_WAIT"); v = e ? atoi(e) : 6; if (v < 0) v = 0; }
+    return v;
+}
+
 // A warp refills only when this many of its lanes are idle.  Measured: camera launches are 5 % faster at 32 (a warp finishes its whole
 // 8x4 tile before taking the next one: keeping the lanes on neighbouring rays is worth more than filling the holes early); ray batches
 // want 8 (an incoherent batch on the 10 M soup: 54.9 Mrays/s at 8 vs 38.9 at 32; the c2 bounce batch loses 7 % against 32).
@@ -661,7 +671,7 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
         BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
     }
     trace_kernel<MODE, CAMERA, COUNT><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
-                                                                            d_counters, d_workCounter, leaf_break(), refill, ts);
+                                                                            d_counters, d_workCounter, leaf_break(), leaf_wait(), refill, ts);
     BM_LAUNCHED();
     if (ts.cost)
     {
