@@ -1,5 +1,6 @@
 """GPU tier: the CUDA build path (keys -> sort -> leaves -> radix tree -> refit) through the C ABI, against the oracle.
 Bar (BASELINE.json north_star): keys, sorted primitive order and topology bit-exact; node bounds within 1e-5 relative."""
+import os
 import zlib
 
 import numpy as np
@@ -247,3 +248,33 @@ def test_flat_keygen_equals_descent_keygen(beam_lib, cuda_device, monkeypatch):
     assert out["flat"][0] == out["descent"][0]
     assert np.array_equal(out["flat"][1], out["descent"][1]) and np.array_equal(out["flat"][2], out["descent"][2])
     assert out["flat"][0]["pairs"] > 2 * n
+
+
+def test_three_kernel_sort_path_and_sub_key_widths_give_the_same_tree(meshes, beam_lib, cuda_device):
+    """The one-sweep radix passes against the three-kernel passes kept for >= 2^30 pairs (BM_SORT=3k), and the coarse against the fine
+    in-cell sub-key (BM_SUB_BITS): the canonical pair list, the topology and the statistics may not depend on either.  The knobs are read
+    once per process, so every variant runs in its own interpreter."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    prog = (
+        "import sys, json, zlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from raytracercuda_b200.tree import Tree\n"
+        "z = np.load(%r)\n"
+        "out = {}\n"
+        "for name in ('bunny', 'f16'):\n"
+        "    t = Tree('cuda:0'); t.add_mesh(z[name + '_pos'], z[name + '_idx']); t.build()\n"
+        "    c, tri = t.pairs(); topo = t.topology()\n"
+        "    out[name] = [t.stats(), zlib.crc32(c.tobytes()), zlib.crc32(tri.tobytes())] + [zlib.crc32(np.sort(np.asarray(a)).tobytes()) for a in topo[:2]]\n"
+        "    t.close()\n"
+        "print(json.dumps(out))\n") % (ROOT, os.path.join(ROOT, "tests", "golden", "meshes.npz"))
+    res = {}
+    for tag, env in (("default", {}), ("3k", {"BM_SORT": "3k"}), ("fine", {"BM_SUB_BITS": "15"}), ("coarse3k", {"BM_SUB_BITS": "3", "BM_SORT": "3k"})):
+        r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=300, env={**os.environ, **env})
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = json.loads(r.stdout.strip().splitlines()[-1])
+    for tag in ("3k", "fine", "coarse3k"):
+        assert res[tag] == res["default"], tag
+    assert res["default"]["bunny"][0]["pairs"] == 184931

@@ -281,3 +281,34 @@ def test_repeated_frames_follow_the_tile_schedule_and_do_not_change(name, W, H, 
             ok2 = o2["tie"] == 0
             assert np.array_equal(hits_to_numpy(h2)["tri"][ok2], o2["tri"][ok2])
     t.close(); s.close()
+
+
+def test_tree_views_trace_concurrently_and_identically(meshes, beam_lib, cuda_device):
+    """bmTreeView: two more handles on one built tree, each on its own stream, tracing the two halves of a frame at the same time;
+    the halves must equal the single-handle frame, and a view of an unbuilt tree is refused."""
+    import ctypes as C
+    import torch
+    from raytracercuda_b200 import _lib
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    P, I, N = meshes["bunny"]
+    t = Tree(cuda_device)
+    h = C.c_void_p()
+    assert beam_lib.bmTreeView(t.h, C.byref(h)) == 102                      # BM_ERROR_NOT_BUILT
+    t.add_mesh(P, I); t.build()
+    W, H = 320, 200
+    from raytracercuda_b200.host import ICamera
+    cam = ICamera.create(); cam.setInitialRays(W, H, -1, 1, -1, 1, 1)
+    rays = torch.from_numpy(cam.initialRays()).to(cuda_device)
+    whole, _ = t.trace_camera(rays, EYE, ID3, width=W)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(cuda_device), torch.cuda.Stream(cuda_device)
+    v1, v2 = t.view(s1), t.view(s2)
+    half = (H // 2) * W
+    for rep in range(3):                                                     # repeated: the views keep their own tile schedules
+        a, _ = v1.trace_camera(rays[:half], EYE, ID3, width=W)
+        b, _ = v2.trace_camera(rays[half:], EYE, ID3, width=W)
+        s1.synchronize(); s2.synchronize()
+        got = torch.cat([a, b])
+        assert torch.equal(got.view(torch.int32), whole.view(torch.int32)), "rep %d" % rep
+    assert v1.stats()["leaves"] == t.stats()["leaves"]
+    v1.close(); v2.close(); t.close()
