@@ -314,24 +314,27 @@ __global__ void tile_hist_kernel(u32 tiles, const u32* __restrict__ cost, u32* s
 // (measured: splitting the top 1/256 of the tiles -9 % launch time, the top 1/64 +0 %, the top 1/16 +27 %).  state[TS_ENTRIES] = number of entries; state[TS_OK] says the list is usable (every tile was costed).
 __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, u32* __restrict__ order, u32 splitPct, u32 residentWarps)
 {
-    __shared__ u32 base[TS_BUCKETS];
+    __shared__ u32 base[TS_BUCKETS], bins[TS_BUCKETS];
     __shared__ u32 total, entries, splitFrom;
+    __shared__ unsigned long long costSum;
+    if (threadIdx.x < TS_BUCKETS) bins[threadIdx.x] = state[threadIdx.x];      // one parallel read: the serial part below runs on shared memory
+    if (threadIdx.x == TS_BUCKETS) costSum = *reinterpret_cast<const unsigned long long*>(state + TS_SUM);
+    __syncthreads();
     if (threadIdx.x == 0)
     {
         u32 run = 0, sf = TS_BUCKETS;
         if (splitPct)
         {
-            unsigned long long sum = *reinterpret_cast<const unsigned long long*>(state + TS_SUM);
-            unsigned long long thr = sum / (residentWarps ? residentWarps : 1u) * splitPct / 100ull;        // cost a tile must exceed to be split
+            unsigned long long thr = costSum / (residentWarps ? residentWarps : 1u) * splitPct / 100ull;    // cost a tile must exceed to be split
             for (int b = TS_BUCKETS - 1; b >= 2; --b)
             {
                 u32 l = (u32)b >> 1;
                 unsigned long long lower = (1ull << l) + (((u32)b & 1u) ? (1ull << (l - 1u)) : 0ull);     // smallest cost of bucket b
-                if (lower >= thr && thr > 0 && run + state[b] <= tiles / 32u) { run += state[b]; sf = (u32)b; } else break;
+                if (lower >= thr && thr > 0 && run + bins[b] <= tiles / 32u) { run += bins[b]; sf = (u32)b; } else break;
             }
         }
         u32 pos = 0; run = 0;
-        for (int b = TS_BUCKETS - 1; b >= 0; --b) { base[b] = pos; pos += state[b] * ((u32)b >= sf ? 4u : 1u); run += state[b]; }
+        for (int b = TS_BUCKETS - 1; b >= 0; --b) { base[b] = pos; pos += bins[b] * ((u32)b >= sf ? 4u : 1u); run += bins[b]; }
         total = run; entries = pos; splitFrom = sf;
     }
     __syncthreads();
@@ -339,7 +342,12 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
     if (i < tiles && total == tiles)
     {
         u32 b = tile_bucket(cost[i]);
-        u32 k = atomicAdd(&state[TS_BUCKETS + b], 1u);
+        // one atomic per (warp, bucket): neighbouring tiles mostly share a bucket
+        unsigned live = __activemask(), peers = __match_any_sync(live, b), lane = threadIdx.x & 31u;
+        unsigned leader = __ffs(peers) - 1u;
+        u32 k = 0;
+        if (lane == leader) k = atomicAdd(&state[TS_BUCKETS + b], (u32)__popc(peers));
+        k = __shfl_sync(peers, k, (int)leader) + (u32)__popc(peers & ((1u << lane) - 1u));
         if (b >= splitFrom)
         {
             u32 pos = base[b] + 4u * k;
