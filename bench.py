@@ -666,7 +666,7 @@ def _oracle_scene(wl):
     return O, s
 
 
-def cpu_baseline(wl, initial_rays, bounce_rays, bounce_src, budget_rays=400_000):
+def cpu_baseline(wl, initial_rays, bounce_rays, bounce_src, budget_rays=2_100_000):
     """The CPU restatement of the reference path (oracle/oracle.cpp, kind "port") on the host cores, on a bounded sample of
     the same workload: the whole BVH build, then a strided sample of the primary rays plus the bounce rays they spawned."""
     cores = os.cpu_count() or 1
