@@ -532,7 +532,15 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if SPP == 1 and wl.bounces:
             whole_frame_bounce_list()
-        line["cpu_baseline"] = cpu_baseline(wl, rays_pinned.numpy(), rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None)
+        def gpu_frame_pixels(w_, h_):
+            """the product's pixels for the workload's scene at w_ x h_ (same camera), for the comparison with the reference build"""
+            c_ = host.ICamera.create(); assert c_.setInitialRays(w_, h_, *wl.frustum) == 0
+            r_ = torch.from_numpy(c_.initialRays()).to(dev); p_ = torch.empty(w_ * h_, dtype=torch.int32, device=dev)
+            _lib.check(L.bmTraceCamera(tree.h, r_.data_ptr(), w_ * h_, w_, _f3(eye), _f9(orient), 0, None, p_.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+            torch.cuda.synchronize(dev)
+            return p_.cpu().numpy().view(np.uint32)
+        line["cpu_baseline"] = cpu_baseline(wl, rays_pinned.numpy(), rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None,
+                                            gpu_pixels_fn=gpu_frame_pixels)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     if rank == 0:
@@ -666,7 +674,7 @@ def _oracle_scene(wl):
     return O, s
 
 
-def cpu_baseline(wl, initial_rays, bounce_rays, bounce_src, budget_rays=2_100_000):
+def cpu_baseline(wl, initial_rays, bounce_rays, bounce_src, budget_rays=2_100_000, gpu_pixels_fn=None):
     """The CPU restatement of the reference path (oracle/oracle.cpp, kind "port") on the host cores, on a bounded sample of
     the same workload: the whole BVH build, then a strided sample of the primary rays plus the bounce rays they spawned."""
     cores = os.cpu_count() or 1
@@ -684,9 +692,39 @@ def cpu_baseline(wl, initial_rays, bounce_rays, bounce_src, budget_rays=2_100_00
             r2 = s.trace_rays(B[:, :3], B[:, 3:], 0, cores)
             rays += B.shape[0]; secs += r2["seconds"]
     s.close()
-    return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
-            "sample": "every %d-th primary ray (%d) + the bounce rays they spawned, %d rays total, %d threads over rays; tree built on 1 thread" % (stride, sel.size, rays, cores),
-            "build": {"value": wl.num_tris / tb / 1e6, "unit": "Mtris/s", "cores": 1, "seconds": tb}}
+    out = {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+           "sample": "every %d-th primary ray (%d) + the bounce rays they spawned, %d rays total, %d threads over rays; tree built on 1 thread" % (stride, sel.size, rays, cores),
+           "build": {"value": wl.num_tris / tb / 1e6, "unit": "Mtris/s", "cores": 1, "seconds": tb}}
+    ref = reference_build_baseline(wl, gpu_pixels_fn)
+    if ref:
+        out["reference_build"] = ref
+    return out
+
+
+def reference_build_baseline(wl, gpu_pixels_fn=None, W=960, H=540):
+    """The UNMODIFIED reference (oracle/_ref/libbeam_ref.so: its own sources compiled in their CUDA-0 host mode, oracle/build_ref.sh)
+    through its public interface on one core -- it is not thread-safe and can only trace a camera's primary rays into pixels, so the
+    sample is the workload's scene at W x H primary rays.  When the GPU path's pixels for the same frame are supplied they are compared."""
+    try:
+        from oracle.bindings import RefLib, RefScene
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libbeam_ref.so")):
+            return None
+        s = RefScene(RefLib())
+        s.add_mesh(wl.positions, wl.indices, wl.normals)
+        tb = s.build()
+        err, px, sec = s.trace(W, H, wl.eye, np.eye(3, dtype=np.float32), wl.frustum)
+        s.close()
+        if err:
+            return {"kind": "reference", "error": int(err)}
+        out = {"kind": "reference", "value": W * H / sec / 1e6, "unit": "Mrays/s", "cores": 1,
+               "sample": "the workload's scene, %dx%d primary rays through IScene / ICamera::traceScene of the unmodified reference (CUDA 0 host mode)" % (W, H),
+               "build": {"value": wl.num_tris / tb / 1e6, "unit": "Mtris/s", "cores": 1, "seconds": tb}}
+        if gpu_pixels_fn is not None:
+            gp = gpu_pixels_fn(W, H)
+            out["gpu_pixels_equal_reference"] = bool(np.array_equal(np.asarray(gp, np.uint32).reshape(-1), np.asarray(px, np.uint32).reshape(-1)))
+        return out
+    except Exception as ex:                                   # the baseline is reported, never required
+        return {"kind": "reference", "unavailable": repr(ex)[:200]}
 
 
 def run_reference(args):
