@@ -1,10 +1,10 @@
 // hierarchy.cu -- from sorted (key, triangle) pairs to the traversable tree:
-//   leaf segmentation (distinct codes)  ->  Karras-style binary radix tree over the distinct codes, one thread per internal
-//   node  ->  bottom-up refit of tight boxes with one atomic counter per node  ->  128-byte nodes.
+//   leaf segmentation (distinct codes)  ->  binary radix tree over the distinct codes, built bottom-up in one pass together with
+//   the tight boxes (agglomerate_kernel)  ->  128-byte nodes.
 //
 // Topology equivalence with the reference: the reference kd node at depth d with TWO children is
 // exactly the radix-tree node whose keys share a d-bit prefix and then differ; single-child chain nodes of the reference
-// have no counterpart because they take no decision.  emit_hierarchy stores (prefix, prefixLen) and, precomputed from the
+// have no counterpart because they take no decision.  agglomerate_kernel stores (prefix, prefixLen) and, precomputed from the
 // grid tables, the node's cell box, split axis (prefixLen % 3) and split plane -- the reference's own values.
 #include "bm_device.cuh"
 

@@ -2,12 +2,13 @@
 // warp-level match/ballot ranking (north_star: "a device radix sort staged through shared memory, with warp-level scans
 // and ballots").
 //
-// Per pass:  tile histogram (1 read of the keys)  ->  exclusive scan of the digit-major [256][tiles] table  ->  scatter
-// (1 read of keys+values, 1 write).  A tile is 4096 consecutive pairs handled by 8 warps; warp w owns the contiguous
-// sub-range [512w, 512w+512) as 16 rows of 32 lanes, so (warp, row, lane) order == input order and ranking inside a digit
-// is stable.  In the scatter kernel the tile is first permuted into digit order in shared memory, then written out so that
-// consecutive threads write consecutive addresses of each digit run.
-// HBM traffic per pass: 4 B (histogram) + 8 B + 8 B per pair; 4 passes for the 31-bit codes of the default world.
+// One-sweep form (default): ONE histogram pass over the input counts every digit of every pass, then one kernel per pass ranks a
+// tile, obtains its per-digit global offsets by decoupled look-back over the preceding tiles, and scatters.  Three-kernel form (kept
+// for >= 2^30 pairs and as BM_SORT=3k): tile histogram -> exclusive scan of the digit-major [256][tiles] table -> scatter.
+// In both, a tile is 2048 (u64 keys) or 4096 (u32 keys) consecutive pairs handled by 8 warps; warp w owns a contiguous sub-range as
+// rows of 32 lanes, so (warp, row, lane) order == input order and ranking inside a digit is stable; the tile is first permuted into
+// digit order in shared memory, then written out so that consecutive threads write consecutive addresses of each digit run.
+// HBM traffic per pass: 12 B read + 12 B written per pair (+ 8 B once for the histogram); 5 passes for 31-bit codes + 9-bit sub-keys.
 #include <cstdlib>
 #include <cstring>
 #include "bm_device.cuh"

@@ -190,7 +190,7 @@ static int tree_build(bmTree* t)
     BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->flags.as<u32>(), leafIdx, P, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(),
                        t->leafBox.as<float4>(), pad, d_scal + 2, t->parentL.as<u32>(), s));     // parentL doubles as the overflow-leaf queue until emit_hierarchy fills it
     tm.mark("leaves+clusters+bounds");
-    // 5. hierarchy + refit
+    // 5. hierarchy and tight boxes, one bottom-up pass
     if (L >= 2)
     {
         BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4)); BM_TRY(t->nodeBox.reserve((L - 1) * 32));

@@ -1,4 +1,4 @@
-"""GPU tier: the CUDA build path (keys -> sort -> leaves -> radix tree -> refit) through the C ABI, against the oracle.
+"""GPU tier: the CUDA build path (keys -> sort -> leaves -> bottom-up radix tree with tight boxes) through the C ABI, against the oracle.
 Bar (BASELINE.json north_star): keys, sorted primitive order and topology bit-exact; node bounds within 1e-5 relative."""
 import os
 import zlib
