@@ -42,22 +42,63 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a thread every
+    2 ms (an nvidia-smi loop cannot place a sample inside a 20 ms region, least of all with eight GPUs); nvidia-smi is the fallback."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index; self.proc = None; self.path = None
+        self.thread = None; self.stop_flag = False; self.sm = []; self.mx = None; self.bits = 0; self.nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            return int(vis.split(",")[self.index])
+        return self.index
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
         try:
+            import pynvml
+            import threading
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None; self.thread = None
+        try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False); self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            n = self.nvml
+            names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
+            out["reasons"] = sorted(k for k, a in names if self.bits & int(getattr(n, a, 0)))
+            if self.sm:
+                out.update(sm_mhz=statistics.median(self.sm), sm_max_mhz=self.mx, samples=len(self.sm))
+            out["source"] = "nvml"
+            return out
         if not self.proc:
             out["reasons"] = ["nvidia-smi unavailable"]; return out
         time.sleep(0.15)
@@ -85,6 +126,7 @@ class ClockSampler:
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
         out["reasons"] = sorted(reasons)
+        out["source"] = "nvidia-smi"
         return out
 
 
