@@ -823,6 +823,13 @@ def run_reference(args):
                              "build": {"value": wl.num_tris / tb / 1e6, "unit": "Mtris/s", "cores": 1, "seconds": tb}},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     s.close()
+    # Why the port and not oracle/_ref: the unmodified reference is single-threaded (global emulation state) and can only trace a camera's
+    # primary rays into pixels, so it cannot run this metric's bounce rays nor use the host's cores; the port is validated bit for bit
+    # against it (tests/test_oracle_golden.py) and is the FASTER baseline.  The reference's own single-core number is reported beside it.
+    line["cpu_baseline"]["why_port"] = "the unmodified reference is single-threaded and traces camera rays only; the port (bit-exact against it) runs the whole metric on all cores and is the faster baseline"
+    ref = reference_build_baseline(wl)
+    if ref:
+        line["cpu_baseline"]["reference_build"] = ref
     print(json.dumps(line), flush=True)
 
 
