@@ -241,7 +241,8 @@ def run_b200(args):
         sp = C.c_void_p(stream.cuda_stream)
         for sidx in range(SPP):
             _lib.check(L.bmCameraRays(rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), jit[0], jit[1], sidx, args.seed, rays1.data_ptr(), sp), "bmCameraRays")
-            _lib.check(L.bmTraceRays(tree.h, rays1.data_ptr(), n, 0, hits1.data_ptr(), None), "bmTraceRays")
+            # the jittered camera rays of a sample are an image: traced in 8x4 tiles under the temporal tile schedule
+            _lib.check(L.bmTraceRaysTiled(tree.h, rays1.data_ptr(), n, W, 0, hits1.data_ptr(), None), "bmTraceRaysTiled")
             _lib.check(L.bmBounceRays(tree.h, rays1.data_ptr(), hits1.data_ptr(), n, sidx, 1, args.seed, rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRays")
             _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, 0, hits2.data_ptr(), None), "bmTraceRaysIndirect")
             _lib.check(L.bmProgressiveAccumulate(hits1.data_ptr(), n, hits2.data_ptr(), src2.data_ptr(), cnt2.data_ptr(), 0.25, acc.data_ptr(), cov.data_ptr(), sp), "accumulate")

@@ -190,6 +190,10 @@ int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, 
 /* Same, with the ray count read from DEVICE memory when the kernel starts (*d_numRays <= maxRays): lets a producer such as
  * bmBounceRays feed the trace without a host round trip. */
 int  bmTraceRaysIndirect(bmTree* tree, const bmRay* d_rays, const uint32_t* d_numRays, uint64_t maxRays, int mode, bmHit* d_hits, uint64_t* d_counters);
+/* A ray batch that IS an image -- width x (numRays / width) rays in row-major pixel order, e.g. the jittered camera rays of one sample of
+ * a multi-sample frame (bmCameraRays) -- traced with the camera launches' scheduling: 8x4 pixel tiles per warp and the temporal tile
+ * schedule (consecutive samples of a frame share it).  Same hits as bmTraceRays. */
+int  bmTraceRaysTiled(bmTree* tree, const bmRay* d_rays, uint64_t numRays, uint32_t width, int mode, bmHit* d_hits, uint64_t* d_counters);
 /* Camera rays (dir = orient * initialRays[i] from eye), hit records and/or shaded pixels (either may be null).
  * width = row length of the image the table describes (numRays % width == 0): warps then start on 8x4 pixel tiles; 0 = trace in
  * linear order.  Results are always written at index i of the table, whatever the order of traversal. */

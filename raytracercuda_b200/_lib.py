@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
     "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView",
-    "bmTraceRays", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
+    "bmTraceRays", "bmTraceRaysTiled", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
     "beamMeshCreate", "beamMeshDestroy", "beamMeshSetVertexData", "beamMeshSetIndices",
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     L.bmTreeRoot.argtypes = [vp, C.POINTER(u32)]
     L.bmTreeView.argtypes = [vp, C.POINTER(vp)]
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]
+    L.bmTraceRaysTiled.argtypes = [vp, vp, u64, u32, i32, vp, vp]
     L.bmTraceCamera.argtypes = [vp, vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32, vp, vp, vp, vp]
     L.bmHashKeys.argtypes = [vp, u64, vp, vp, vp]
     L.bmCameraRays.argtypes = [vp, u64, u32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float, u32, u32, vp, vp]

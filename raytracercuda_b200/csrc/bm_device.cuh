@@ -110,6 +110,8 @@ constexpr int TS_BUCKETS = 64, TS_SUM = 128, TS_OK = 130, TS_ENTRIES = 131, TS_W
 struct TileSched { u32* cost; u32* order; u32* state; u32 tiles; };
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
                  u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s);
+int trace_rays_tiled(const TreeView& tv, const bmRay* d_rays, u64 n, u32 width, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter,
+                     const TileSched* sched, cudaStream_t s);
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
 int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials, const bmTexture* d_textures,
                u32 numTextures, u32* d_pixels, cudaStream_t s);

@@ -237,7 +237,7 @@ public:
         for (u32 s = 0; s < samples; s++)
         {
             int r = bmCameraRays(rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, s, seed, r1.ptr<bmRay>(), nullptr);
-            if (!r) r = bmTraceRays(t, r1.ptr<bmRay>(), n, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr);
+            if (!r) r = bmTraceRaysTiled(t, r1.ptr<bmRay>(), n, raysWide, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr);
             if (!r) r = bmBounceRays(t, r1.ptr<bmRay>(), h1.ptr<bmHit>(), n, s, 1, seed, r2.ptr<bmRay>(), src.ptr<u32>(), cnt.ptr<u32>());
             if (!r) r = bmTraceRaysIndirect(t, r2.ptr<bmRay>(), cnt.ptr<u32>(), n, BM_TRACE_REFERENCE, h2.ptr<bmHit>(), nullptr);
             if (!r) r = bmProgressiveAccumulate(h1.ptr<bmHit>(), n, h2.ptr<bmHit>(), src.ptr<u32>(), cnt.ptr<u32>(), 0.25f, acc.ptr<float>(), cov.ptr<u32>(), nullptr);

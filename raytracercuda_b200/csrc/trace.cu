@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                 }
                 if (take && slot_to_ray(slot, n, width, height, rayIdx))
                 {
-                    if (CAMERA)
+                    if (CAMERA && !rays)
                     {
                         const float* r = cam.initialRays + 3 * rayIdx;
                         float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
@@ -724,6 +724,16 @@ int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticM
     shade_hits_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits, n, d_soup, d_meshData, d_materials, d_textures, numTextures, d_pixels);
     BM_LAUNCHED();
     return BM_OK;
+}
+
+// a ray batch that IS an image (width x n/width rays in row-major order, e.g. jittered camera rays): traced with the camera launches'
+// scheduling -- 8x4 tiles, whole-warp refills, temporal tile schedule -- instead of the generic batch scheduling
+int trace_rays_tiled(const TreeView& tv, const bmRay* d_rays, u64 n, u32 width, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter,
+                     const TileSched* sched, cudaStream_t s)
+{
+    if (!n) return BM_OK;
+    CameraIn cam = {};
+    return dispatch_trace<true>(tv, d_rays, cam, n, nullptr, width, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, sched, s);
 }
 
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s)

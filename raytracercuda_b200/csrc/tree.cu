@@ -422,19 +422,11 @@ extern "C" int bmTraceRaysIndirect(bmTree* t, const bmRay* d_rays, const uint32_
     return trace_rays(t->view(), d_rays, maxRays, d_numRays, mode, d_hits, d_counters, t->scalars.as<u32>() + 8, t->stream);
 }
 
-extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9, int mode,
-                             bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters)
+// temporal tile scheduling (TileSched, bm_device.cuh): per tree and frame size; BM_TILE_ORDER=0 turns it off
+static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uint64_t* d_counters, TileSched& sched)
 {
-    if (!t || !eye3 || !orient9 || (!d_initialRays3 && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
-    if (d_pixels && !d_meshData) return BM_ERROR_INVALID_PARAMETER;
-    if (!t->built) BM_TRY(tree_build(t));
-    CameraIn cam; cam.initialRays = d_initialRays3;
-    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
-    if (width && numRays % width) return BM_ERROR_INVALID_PARAMETER;
-    BM_TRY(t->scalars.reserve(64));
-    // temporal tile scheduling (TileSched, bm_device.cuh): per tree and frame size; BM_TILE_ORDER=0 turns it off
     static const bool tileOrderOn = !(getenv("BM_TILE_ORDER") && atoi(getenv("BM_TILE_ORDER")) == 0);
-    TileSched sched = { nullptr, nullptr, nullptr, 0 };
+    sched = { nullptr, nullptr, nullptr, 0 };
     if (tileOrderOn && width && !d_counters)
     {
         uint32_t height = (uint32_t)(numRays / width);
@@ -450,7 +442,32 @@ extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t nu
             sched = { t->tileCost.as<u32>(), t->tileOrder.as<u32>(), t->tileState.as<u32>(), (u32)tiles };
         }
     }
+    return BM_OK;
+}
+
+extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9, int mode,
+                             bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters)
+{
+    if (!t || !eye3 || !orient9 || (!d_initialRays3 && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
+    if (d_pixels && !d_meshData) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) BM_TRY(tree_build(t));
+    CameraIn cam; cam.initialRays = d_initialRays3;
+    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
+    if (width && numRays % width) return BM_ERROR_INVALID_PARAMETER;
+    BM_TRY(t->scalars.reserve(64));
+    TileSched sched;
+    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched));
     return trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream);
+}
+
+extern "C" int bmTraceRaysTiled(bmTree* t, const bmRay* d_rays, uint64_t numRays, uint32_t width, int mode, bmHit* d_hits, uint64_t* d_counters)
+{
+    if (!t || (!d_rays && numRays) || !width || (numRays % width) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) BM_TRY(tree_build(t));
+    BM_TRY(t->scalars.reserve(64));
+    TileSched sched;
+    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched));
+    return trace_rays_tiled(t->view(), d_rays, numRays, width, mode, d_hits, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream);
 }
 
 extern "C" int bmCameraRays(const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,

@@ -312,3 +312,34 @@ def test_tree_views_trace_concurrently_and_identically(meshes, beam_lib, cuda_de
         assert torch.equal(got.view(torch.int32), whole.view(torch.int32)), "rep %d" % rep
     assert v1.stats()["leaves"] == t.stats()["leaves"]
     v1.close(); v2.close(); t.close()
+
+
+def test_tiled_ray_batches_equal_plain_batches(meshes, beam_lib, cuda_device):
+    """bmTraceRaysTiled (image-shaped batches in 8x4 tiles under the tile schedule) against bmTraceRays on the jittered camera rays of
+    several samples, repeated so that the schedule of the previous launch is in use; partial tiles included (301 x 203)."""
+    import ctypes as C
+    import torch
+    from raytracercuda_b200 import _lib
+    from raytracercuda_b200.host import ICamera
+    from raytracercuda_b200.tree import Tree
+    L = beam_lib
+    P, I, N = meshes["bunny"]
+    t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+    W, H = 301, 203
+    n = W * H
+    cam = ICamera.create(); cam.setInitialRays(W, H, -1, 1, -1, 1, 1)
+    table = torch.from_numpy(cam.initialRays()).to(cuda_device)
+    a = torch.empty((n, 4), dtype=torch.float32, device=cuda_device); b = torch.empty_like(a)
+    for sample in range(5):
+        rays = t.camera_rays(table, EYE, ID3, width=W, jitter=(2.0 / W, 2.0 / H), sample=sample, seed=3)
+        for mode in (0, 1):
+            _lib.check(L.bmTraceRays(t.h, rays.data_ptr(), n, mode, a.data_ptr(), None), "bmTraceRays")
+            _lib.check(L.bmTraceRaysTiled(t.h, rays.data_ptr(), n, W, mode, b.data_ptr(), None), "bmTraceRaysTiled")
+            torch.cuda.synchronize()
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), "sample %d mode %d" % (sample, mode)
+    assert (a[:, 3].view(torch.int32) != -1).sum() > 5000
+    cnt = torch.zeros(4, dtype=torch.int64, device=cuda_device)
+    _lib.check(L.bmTraceRaysTiled(t.h, rays.data_ptr(), n, W, 0, b.data_ptr(), cnt.data_ptr()), "bmTraceRaysTiled")
+    assert int(cnt.cpu()[0]) > n
+    assert L.bmTraceRaysTiled(t.h, rays.data_ptr(), n, 0, 0, b.data_ptr(), None) == 2 and L.bmTraceRaysTiled(t.h, rays.data_ptr(), n, 11, 0, b.data_ptr(), None) == 2      # 301 * 203 is not a multiple of 11
+    t.close()
