@@ -192,12 +192,12 @@ public:
         IRenderTarget* rt = RenderTarget::get();
         if (rt && (rt->width() != raysWide || rt->height() != raysHigh)) return ERROR_RT_CAM_MISMATCH;
         if (!t) { for (size_t i = 0; i < n; i++) hostHits[i] = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu }; return ERROR_ALL_FINE; }
-        DeviceBuffer hits(n * sizeof(bmHit));
-        if (!hits.ok()) return ERROR_GPU_ALLOC_FAIL;
-        int r = bmTraceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, BM_TRACE_REFERENCE, hits.ptr<bmHit>(), rt ? rt->buffer<u32>() : nullptr,
+        DeviceBuffer* hits = scratch(0, n * sizeof(bmHit));
+        if (!hits) return ERROR_GPU_ALLOC_FAIL;
+        int r = bmTraceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, BM_TRACE_REFERENCE, hits->ptr<bmHit>(), rt ? rt->buffer<u32>() : nullptr,
                               m_table ? m_table->ptr<const bmStaticMeshData>() : nullptr, nullptr);
         if (r != BM_OK) return (u32)r;
-        hits.copyTo(hostHits, true);
+        if (cudaMemcpy(hostHits, hits->ptr<void>(), n * sizeof(bmHit), cudaMemcpyDeviceToHost) != cudaSuccess) return BM_ERROR_CUDA;
         return ERROR_ALL_FINE;
     }
     // hits -> deferred shading with the meshes' materials (ICamera::traceSceneTextured)
@@ -210,14 +210,13 @@ public:
         size_t n = (size_t)raysWide * raysHigh;
         bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
         if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); return ERROR_ALL_FINE; }
-        DeviceBuffer hits(n * sizeof(bmHit));
-        if (!hits.ok()) return ERROR_GPU_ALLOC_FAIL;
-        int r = bmTraceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, BM_TRACE_REFERENCE, hits.ptr<bmHit>(), nullptr, nullptr, nullptr);
-        if (!r) r = bmShadeHits(t, hits.ptr<bmHit>(), n, m_table->ptr<const bmStaticMeshData>(), m_materials->ptr<const bmMaterial>(),
+        DeviceBuffer* hits = scratch(0, n * sizeof(bmHit));
+        if (!hits) return ERROR_GPU_ALLOC_FAIL;
+        int r = bmTraceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, BM_TRACE_REFERENCE, hits->ptr<bmHit>(), nullptr, nullptr, nullptr);
+        if (!r) r = bmShadeHits(t, hits->ptr<bmHit>(), n, m_table->ptr<const bmStaticMeshData>(), m_materials->ptr<const bmMaterial>(),
                                 m_textures->ptr<const bmTexture>(), m_numTextures, rt->buffer<u32>());
         if (r != BM_OK) return (u32)r;
-        cudaDeviceSynchronize();                 // `hits` dies with this scope
-        return ERROR_ALL_FINE;
+        return ERROR_ALL_FINE;                    // asynchronous like traceScene: the caller synchronises (readPixels does)
     }
     // progressive frame (see ICamera::traceSceneProgressive): every sample = jittered camera rays -> trace -> bounce rays -> trace -> accumulate
     u32 marchProgressive(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh, float jx, float jy, u32 samples,
@@ -230,8 +229,10 @@ public:
         size_t n = (size_t)raysWide * raysHigh;
         bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
         if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); if (raysTraced) *raysTraced = 0; return ERROR_ALL_FINE; }
-        DeviceBuffer r1(n * sizeof(bmRay)), h1(n * sizeof(bmHit)), r2(n * sizeof(bmRay)), h2(n * sizeof(bmHit)), src(n * 4), cnt(4), acc(n * 4), cov(n * 4);
-        if (!r1.ok() || !h1.ok() || !r2.ok() || !h2.ok() || !src.ok() || !cnt.ok() || !acc.ok() || !cov.ok()) return ERROR_GPU_ALLOC_FAIL;
+        DeviceBuffer *ph1 = scratch(0, n * sizeof(bmHit)), *pr1 = scratch(1, n * sizeof(bmRay)), *pr2 = scratch(2, n * sizeof(bmRay)), *ph2 = scratch(3, n * sizeof(bmHit)),
+                     *psrc = scratch(4, n * 4), *pcnt = scratch(5, 4), *pacc = scratch(6, n * 4), *pcov = scratch(7, n * 4);
+        if (!ph1 || !pr1 || !pr2 || !ph2 || !psrc || !pcnt || !pacc || !pcov) return ERROR_GPU_ALLOC_FAIL;
+        DeviceBuffer &h1 = *ph1, &r1 = *pr1, &r2 = *pr2, &h2 = *ph2, &src = *psrc, &cnt = *pcnt, &acc = *pacc, &cov = *pcov;
         cudaMemset(acc.ptr<void>(), 0, n * 4); cudaMemset(cov.ptr<void>(), 0, n * 4);
         u64 total = 0;
         for (u32 s = 0; s < samples; s++)
@@ -242,16 +243,23 @@ public:
             if (!r) r = bmTraceRaysIndirect(t, r2.ptr<bmRay>(), cnt.ptr<u32>(), n, BM_TRACE_REFERENCE, h2.ptr<bmHit>(), nullptr);
             if (!r) r = bmProgressiveAccumulate(h1.ptr<bmHit>(), n, h2.ptr<bmHit>(), src.ptr<u32>(), cnt.ptr<u32>(), 0.25f, acc.ptr<float>(), cov.ptr<u32>(), nullptr);
             if (r) return (u32)r;
-            if (raysTraced) { u32 c = 0; cnt.copyTo(&c, true); total += n + c; }
+            if (raysTraced) { u32 c = 0; cudaMemcpy(&c, cnt.ptr<void>(), 4, cudaMemcpyDeviceToHost); total += n + c; }
         }
         int r = bmProgressiveResolve(acc.ptr<float>(), cov.ptr<u32>(), n, samples, rt->buffer<u32>(), nullptr);
         if (r) return (u32)r;
-        cudaDeviceSynchronize();                   // the scratch buffers above die with this scope
         if (raysTraced) *raysTraced = total;
         return ERROR_ALL_FINE;
     }
     void* rootKey() const { return m_root->ptr<void>(); }
 private:
+    // per-frame scratch (hit records, ray batches, accumulators) is kept between frames and only grows: a frame performs no cudaMalloc
+    DeviceBuffer* scratch(int slot, size_t bytes)
+    {
+        sptr<DeviceBuffer>& b = m_scratch[slot];
+        if (!b || b->size() < bytes) { b.reset(); b = std::make_shared<DeviceBuffer>(bytes); if (!b->ok()) { b.reset(); return nullptr; } }
+        return b.get();
+    }
+    sptr<DeviceBuffer> m_scratch[8];
     bmVec3 m_min, m_max;
     std::vector<sptr<Mesh>> m_meshes;
     sptr<DeviceBuffer> m_root, m_table, m_materials, m_textures;
