@@ -395,8 +395,10 @@ extern "C" int bmTreeView(const bmTree* src, bmTree** out)
     if (!src->built) return BM_ERROR_NOT_BUILT;
     uint64_t sz[8];
     BM_TRY(bmTreeArraySizes(src, sz));
-    bmTree* t = nullptr;
-    BM_TRY(bmTreeCreate(&t, src->hgrid.wmin, src->hgrid.wmax, 0.f, 0));
+    // no grid tables of its own: a view never builds, and the source's world (which may use a non-default leaf size or depth cap) is
+    // described by the copied host grid; the device grid points at the source's tables
+    bmTree* t = new bmTree();
+    t->hgrid = src->hgrid; t->dgrid = src->dgrid;
     t->L = src->L; t->P = src->P; t->T = src->T; t->meshBase = src->meshBase; t->maxLeaf = src->maxLeaf; t->overLeaves = src->overLeaves;
     t->nodes.adopt(src->nodes.p, sz[0]); t->leaves.adopt(src->leaves.p, sz[1]); t->ltris.adopt(src->ltris.p, sz[2]);
     t->clusters.adopt(src->clusters.p, sz[3]); t->soup.adopt(src->soup.p, sz[4]); t->rootDev.adopt(src->rootDev.p, 16);
