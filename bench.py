@@ -5,11 +5,14 @@ build Mtris/s) on N B200s of one node.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
 
 One STEP = one frame of the workload through the C ABI: primary rays of this rank's camera (bmTraceCamera, reference
-semantics), one diffuse bounce generation (bmCameraRays + bmBounceRays) and its trace (bmTraceRays); at N > 1 the ranks render
-interleaved rows of an N-times taller image with a replicated tree (weak scaling) and all-gather the framebuffer (NCCL).
-`value` = rays traced by all ranks / device time of the step with every input resident in HBM; `e2e` = the same step fed
-from pinned HOST buffers (camera table H2D each step, framebuffer + bounce hits D2H each step).  The BVH build (soup resident
--> tree traceable) is timed in the same run and reported under "build".  L2 is flushed between timed steps.
+semantics), one diffuse bounce generation (bmBounceRaysCamera) and its trace (bmTraceRaysIndirect: the bounce count stays on the
+device); at N > 1 the ranks render interleaved rows of an N-times taller image with a replicated tree (weak scaling) and all-gather
+the framebuffer (NCCL) under the bounce trace.  Multi-sample workloads (c3, c4): per sample bmCameraRays (jitter) -> bmTraceRaysTiled ->
+bmBounceRays -> bmTraceRaysIndirect -> bmProgressiveAccumulate, then bmProgressiveResolve.
+`value` = rays traced by all ranks / device time of the step with every input resident in HBM, each step bracketed by a synchronise;
+`e2e` = the same step fed from pinned HOST buffers (camera table H2D each step, framebuffer + bounce count + bounce hits D2H each
+step), frames pipelined three deep, the K steps timed as one bracket.  The BVH build (soup resident -> tree traceable) is timed in
+the same run and reported under "build".  L2 is flushed between timed steps (inside the compute stream in the e2e leg).
 """
 from __future__ import annotations
 
