@@ -397,6 +397,16 @@ def run_b200(args):
             S["rays"].copy_(rays_pinned, non_blocking=True)
             S["ev_h2d"] = torch.cuda.Event(); S["ev_h2d"].record(s_h2d)
 
+    e2e_graphs = None                                       # one CUDA graph per buffer set (filled in below): L2 flush + the frame's launches
+
+    def frame_calls(S):
+        """the frame's three C-ABI calls on buffer set S (single GPU, one band): what the per-slot CUDA graph captures"""
+        _lib.check(L.bmTraceCamera(tree.h, S["rays"].data_ptr(), n, W, _f3(eye), _f9(orient), 0, S["hits1"].data_ptr(), S["pixels"].data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+        if wl.bounces:
+            _lib.check(L.bmBounceRaysCamera(tree.h, S["rays"].data_ptr(), _f3(eye), _f9(orient), S["hits1"].data_ptr(), n, 0, 1, args.seed, S["rays2"].data_ptr(),
+                                            S["src2"].data_ptr(), S["cnt"].data_ptr()), "bmBounceRaysCamera")
+            _lib.check(L.bmTraceRaysIndirect(tree.h, S["rays2"].data_ptr(), S["cnt"].data_ptr(), n, 0, S["hits2"].data_ptr(), None), "bmTraceRaysIndirect")
+
     def e2e_compute(i):
         """kernels of frame i (asynchronous)"""
         S = slots[i % DEPTH]
@@ -404,8 +414,11 @@ def run_b200(args):
             stream.wait_event(S["ev_h2d"])
             if S["ev_d2h"] is not None:
                 stream.wait_event(S["ev_d2h"])              # ... and its results have left the device
-            flush.zero_()
-            frame(S["rays"], None, out=(S["hits1"], S["pixels"], S["rays2"], S["src2"], S["hits2"], S["cnt"], S["cnt_scratch"]))
+            if e2e_graphs is not None:
+                e2e_graphs[i % DEPTH].replay()
+            else:
+                flush.zero_()
+                frame(S["rays"], None, out=(S["hits1"], S["pixels"], S["rays2"], S["src2"], S["hits2"], S["cnt"], S["cnt_scratch"]))
             S["ev_comp"] = torch.cuda.Event(); S["ev_comp"].record(stream)
 
     def e2e_download(i):
@@ -456,6 +469,25 @@ def run_b200(args):
     e2e_rays = 0
     if SPP == 1:
         e2e_run(DEPTH + 1)                                   # warm-up (allocations, all slots touched)
+        if world == 1 and NB == 1 and not args.no_e2e_graph:
+            # the launch sequence of a frame is fixed: captured once per buffer set, replayed as one graph launch per frame
+            try:
+                torch.cuda.synchronize(dev)
+                graphs_ = []
+                for S in slots:
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_):
+                        tree.use_stream(torch.cuda.current_stream(dev))
+                        flush.zero_()
+                        frame_calls(S)
+                    graphs_.append(g_)
+                tree.use_stream(stream)
+                e2e_graphs = graphs_
+                e2e_run(DEPTH + 1)
+            except Exception as ex:                          # keep the run alive; the line says which path ran
+                sys.stderr.write("e2e: CUDA graph capture failed (%r): direct launches\n" % (ex,))
+                e2e_graphs = None
+                tree.use_stream(stream)
         lat = []
         for _ in range(3):                                   # latency of one frame on its own
             e0, e1 = ev(), ev(); sync_all(); e0.record(); e2e_run(1); e1.record(); sync_all(); lat.append(e0.elapsed_time(e1))
@@ -570,8 +602,9 @@ def run_b200(args):
                        "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
                     "single_frame_latency_ms": e2e_latency_ms,
-                    "pipeline": ("%d frames in flight on 3 streams (H2D of the camera table | L2 flush + trace + bounce + trace | D2H of framebuffer, bounce count and "
-                                 "bounce hit records sized by the device-side count); the K steps are one timed bracket, fill and drain included" % DEPTH) if SPP == 1
+                    "pipeline": ("%d frames in flight on 3 streams (H2D of the camera table | L2 flush + trace + bounce + trace%s | D2H of framebuffer, bounce count and "
+                                 "bounce hit records sized by the device-side count); the K steps are one timed bracket, fill and drain included"
+                                 % (DEPTH, ", replayed as one CUDA graph per frame" if e2e_graphs is not None else "")) if SPP == 1
                                 else "one frame at a time: H2D of the camera table, the multi-sample frame, D2H of the framebuffer"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build}
 
@@ -846,6 +879,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--bands", type=int, default=1, help="row bands of a frame issued concurrently on as many streams (tail filling)")
+    ap.add_argument("--no-e2e-graph", action="store_true", help="e2e leg: direct launches instead of one CUDA graph per frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5-mtris", type=float, default=100.0, help="workload c5: millions of soup triangles")
     ap.add_argument("--c5-mrays", type=float, default=16.0, help="workload c5: millions of incoherent rays per step per GPU")
