@@ -92,9 +92,14 @@ class ClockSampler:
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.thread is not None:
+            n = self.nvml
+            try:                                          # one more sample from this thread, the instant the timed region ends
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
             self.stop_flag = True
             self.thread.join(timeout=2)
-            n = self.nvml
             names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
                      ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
             out["reasons"] = sorted(k for k, a in names if self.bits & int(getattr(n, a, 0)))
