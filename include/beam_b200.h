@@ -141,8 +141,21 @@ enum {
     BM_TRACE_CLOSEST = 1     /* exhaustive closest hit with t >= 0 (ordered traversal with t-range culling) */
 };
 
-const char* bmLastErrorString(void);
+const char* bmLastErrorString(void);   /* text of the calling thread's last failed call */
 uint64_t bmLaunchCount(void);          /* kernels launched by this library so far in this process */
+
+/* Part 1's launchers return void, and the reference's CUDA_CALL prints and calls exit(1) on failure (CudaComon.cuh:59-68).  A shared
+ * library must not end its host: the FIRST failure inside bmInsertMeshInTree / bmMarch / bmClear / ... is kept as a process-wide
+ * sticky error (code as in the BM_ERROR_* list, 0 = none) until bmClearStickyError; the failing call has no effect. */
+int         bmStickyError(void);
+const char* bmStickyErrorString(void);
+void        bmClearStickyError(void);
+/* The owner of `treeRootNode` is about to free it: drops the tree registered under that pointer together with its device buffers
+ * (the reference frees its pools in ~SceneTree, SceneTree.cpp:55-68).  Unknown pointers are ignored. */
+void        bmReleaseScene(const void* treeRootNode);
+/* Stream (cudaStream_t) used by bmMarch / bmClear / the build of Part-1 trees on the CURRENT device; default 0, the legacy default
+ * stream the reference launches on. */
+void        bmSetPart1Stream(void* cudaStream);
 
 /* World box, leaf size and depth cap default to SceneTree.cpp:43-45 and BuildTree.cuh:14-18 when null / 0. */
 int  bmTreeCreate(bmTree** out, const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth);
@@ -200,6 +213,13 @@ int  bmTraceRaysTiled(bmTree* tree, const bmRay* d_rays, uint64_t numRays, uint3
 int  bmTraceCamera(bmTree* tree, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
                    int mode, bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters);
 
+/* bmTraceCamera with the sample jitter applied where the ray is formed (in the trace kernel's registers): sample == 0xFFFFFFFF is the
+ * exact pixel-centre table entry, otherwise the direction is jittered inside the pixel exactly as bmCameraRays would write it -- a
+ * multi-sample frame needs no per-sample ray buffer (SceneProgressive.cpp:27-77 is the stub this stands in for). */
+int  bmTraceCameraJittered(bmTree* tree, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                           float jitterX, float jitterY, uint32_t sample, uint32_t seed, int mode,
+                           bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters);
+
 /* Ray-batch producers for the multi-sample / bounce workloads (defined by this repo; the reference has no secondary rays,
  * SURVEY.md section 8d).  bmCameraRays writes the camera's rays as bmRay records; sample == 0xFFFFFFFF means the exact
  * pixel-centre table entry (identical to what bmMarch traces), otherwise the direction is jittered inside the pixel
@@ -214,6 +234,11 @@ int  bmBounceRays(bmTree* tree, const bmRay* d_rays, const bmHit* d_hits, uint64
 /* bmBounceRays for the hits of a bmTraceCamera / bmMarch launch: the primary rays are re-formed from the camera table */
 int  bmBounceRaysCamera(bmTree* tree, const float* d_initialRays3, const float* eye3, const float* orient9, const bmHit* d_hits,
                         uint64_t numRays, uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count);
+
+/* ... of a bmTraceCameraJittered launch (cameraSample / cameraSeed / jitter as given there) */
+int  bmBounceRaysCameraJittered(bmTree* tree, const float* d_initialRays3, const float* eye3, const float* orient9, float jitterX, float jitterY,
+                                uint32_t cameraSample, uint32_t cameraSeed, const bmHit* d_hits, uint64_t numRays,
+                                uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count);
 
 /* Progressive accumulation over samples (defined by this repo; the reference's SceneProgressive is an empty stub): one sample of a
  * pixel = `ambient` if its primary ray hit + (1 - ambient) if the diffuse bounce ray of that hit escaped.  d_accum (float) and

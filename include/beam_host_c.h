@@ -36,6 +36,11 @@ uint32_t beamRenderTargetUnlock(void* rt);
 void*    beamRenderTargetBuffer(void* rt);                        /* device pointer while locked */
 uint32_t beamRenderTargetReadPixels(void* rt, uint32_t* hostPixels);
 int      beamDeviceSynchronize(void);
+/* Pinned host staging for read-backs: with a pinned destination IRenderTarget::readPixels is one DMA on the copy stream, and with two
+ * render targets the download of frame i overlaps the kernels of frame i+1. */
+void*    beamHostAlloc(size_t bytes);
+void     beamHostFree(void* pinned);
+void*    beamHostStream(void);                                    /* cudaStream_t all host-class work of the current device is issued on */
 
 /* Wavefront OBJ import (replaces TestProgram/Model.cpp + Assimp; rules in raytracercuda_b200/csrc/objload.cpp).  Pure host code. */
 void*           beamObjLoad(const char* path, int splitByMaterial);   /* never NULL; check beamObjError */

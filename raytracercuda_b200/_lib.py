@@ -20,7 +20,8 @@ ABI_SYMBOLS = [
     "bmGetFaceStoreSize", "bmGetNodeStoreSize", "bmGetFaceGroupStoreSize", "bmClear",
     "bmResetSpace", "bmInsertMeshInSpace", "bmMarchSpace", "bmGetCellSize", "bmGetMaxHashElements",
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
-    "bmLastErrorString", "bmLaunchCount", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
+    "bmLastErrorString", "bmLaunchCount", "bmStickyError", "bmStickyErrorString", "bmClearStickyError", "bmReleaseScene", "bmSetPart1Stream",
+    "bmTraceCameraJittered", "bmBounceRaysCameraJittered", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
     "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView",
     "bmTraceRays", "bmTraceRaysTiled", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
     # include/beam_host_c.h
@@ -29,7 +30,7 @@ ABI_SYMBOLS = [
     "beamCameraCreate", "beamCameraDestroy", "beamCameraSetInitialRays", "beamCameraCopyInitialRays", "beamCameraClear",
     "beamCameraTraceScene", "beamCameraTraceSceneHits", "beamCameraTraceSceneProgressive",
     "beamRenderTargetCreateHeadless", "beamRenderTargetDestroy", "beamRenderTargetLock", "beamRenderTargetUnlock", "beamRenderTargetBuffer",
-    "beamRenderTargetReadPixels", "beamDeviceSynchronize",
+    "beamRenderTargetReadPixels", "beamDeviceSynchronize", "beamHostAlloc", "beamHostFree", "beamHostStream",
     "beamObjLoad", "beamObjError", "beamObjFree", "beamObjNumVertices", "beamObjNumMeshes", "beamObjHasNormals", "beamObjPositions", "beamObjNormals",
     "beamObjMeshNumIndices", "beamObjMeshIndices", "beamObjMeshName", "beamSceneLoadObj", "beamWritePPM",
     "beamMeshSetTexture", "beamCameraTraceSceneTextured", "beamObjHasUVs", "beamObjUVs", "beamObjMeshTexture", "beamBmpLoad", "beamImageFree",
@@ -157,6 +158,17 @@ def load() -> C.CDLL:
     L.beamBmpLoad.argtypes = [C.c_char_p, C.POINTER(u32), C.POINTER(u32)]; L.beamBmpLoad.restype = C.POINTER(u32)
     L.beamImageFree.argtypes = [C.POINTER(u32)]; L.beamImageFree.restype = None
     L.bmShadeHits.argtypes = [vp, vp, u64, vp, vp, vp, u32, vp]
+    L.bmStickyError.restype = i32
+    L.bmStickyErrorString.restype = C.c_char_p
+    L.bmClearStickyError.restype = None
+    L.bmReleaseScene.argtypes = [vp]; L.bmReleaseScene.restype = None
+    L.bmSetPart1Stream.argtypes = [vp]; L.bmSetPart1Stream.restype = None
+    fp = C.POINTER(C.c_float)
+    L.bmTraceCameraJittered.argtypes = [vp, vp, u64, u32, fp, fp, f, f, u32, u32, i32, vp, vp, vp, vp]
+    L.bmBounceRaysCameraJittered.argtypes = [vp, vp, fp, fp, f, f, u32, u32, vp, u64, u32, u32, u32, vp, vp, vp]
+    L.beamHostAlloc.argtypes = [C.c_size_t]; L.beamHostAlloc.restype = vp
+    L.beamHostFree.argtypes = [vp]; L.beamHostFree.restype = None
+    L.beamHostStream.restype = vp
     _lib = L
     return L
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include <string>
 #include "bm_math.cuh"
 #include "../../include/beam_b200.h"
@@ -14,12 +15,15 @@ void set_error(const std::string& s);
 const char* last_error();
 #define BM_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ::bm::set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); return BM_ERROR_CUDA; } } while (0)
 // after every kernel launch: count it (bmLaunchCount, the bench's gpu_launches evidence) and surface launch errors
-extern unsigned long long g_launches;
-#define BM_LAUNCHED() do { ++::bm::g_launches; BM_CUDA(cudaGetLastError()); } while (0)
+extern std::atomic<unsigned long long> g_launches;
+#define BM_LAUNCHED() do { ::bm::g_launches.fetch_add(1, std::memory_order_relaxed); BM_CUDA(cudaGetLastError()); } while (0)
 #define BM_TRY(expr) do { int r_ = (expr); if (r_ != BM_OK) return r_; } while (0)
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
-int sm_count();
+constexpr int MAX_DEVICES = 64;
+int current_device();        // cudaGetDevice, clamped to [0, MAX_DEVICES)
+int sm_count();              // of the current device (cached per device)
+void set_sticky(int code, const char* where);
 
 // ---- HBM layout of a finished tree (all index-based, no absolute pointers inside the arrays) --------------------------
 //
@@ -59,7 +63,9 @@ struct TreeView
 // ---- scan.cu --------------------------------------------------------------------------------------------------------
 size_t scan_temp_bytes(size_t n);
 // out[i] = sum(in[0..i-1]); *d_total (device, nullable) = sum of all. in == out allowed. temp: scan_temp_bytes(n) bytes.
-int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s);
+// d_total64 (device, nullable, must be zero before the call) receives the same total accumulated in 64 bits: a value >= 2^32 means the
+// u32 prefixes have wrapped
+int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s, unsigned long long* d_total64 = nullptr);
 // out[i] = number of hit records (tri != 0xFFFFFFFF) among d_hits[0..i-1]; *d_total = their number. Same temp as above.
 int exclusive_scan_hit_flags(const bmHit* d_hits, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s);
 
@@ -95,7 +101,47 @@ int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, int subBits, 
 int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s);
 
 // ---- trace.cu -------------------------------------------------------------------------------------------------------
-struct CameraIn { const float* initialRays; float eye[3]; float orient[9]; };
+// sample == 0xFFFFFFFF: the exact pixel-centre table entry (what bmMarch traces); otherwise the direction is jittered inside the pixel
+// (jitterX/Y = pixel size in units of zoom) by a counter-based hash of (ray, sample, seed) -- see camera_ray below
+struct CameraIn { const float* initialRays; float eye[3]; float orient[9]; float jitterX, jitterY; u32 sample, seed; };
+inline CameraIn make_camera(const float* d_initialRays3, const float* eye3, const float* orient9, float jx = 0.f, float jy = 0.f, u32 sample = 0xFFFFFFFFu, u32 seed = 0)
+{
+    CameraIn c; c.initialRays = d_initialRays3;
+    for (int i = 0; i < 3; i++) c.eye[i] = eye3 ? eye3[i] : 0.f;
+    for (int i = 0; i < 9; i++) c.orient[i] = orient9 ? orient9[i] : 0.f;
+    c.jitterX = jx; c.jitterY = jy; c.sample = sample; c.seed = seed;
+    return c;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ u32 pcg_hash(u32 v)
+{
+    u32 state = v * 747796405u + 2891336453u;
+    u32 word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ float u01(u32 h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
+// Ray i of a camera: dir = orient * initialRays[i] from eye (glm mat3 * vec3, type_mat3x3.inl:424-430; Camera.cpp:85-97), optionally
+// jittered.  ONE definition used by the trace kernels (which form camera rays in registers), bmCameraRays (which materialises them) and
+// the bounce generator (which re-forms the primary ray of a hit), so all three see the same bits.
+__device__ __forceinline__ void camera_ray(const CameraIn& cam, u64 i, V3& o, V3& d)
+{
+    const float* r = cam.initialRays + 3 * i;
+    float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
+    if (cam.sample != 0xFFFFFFFFu)
+    {
+        // jitter inside the pixel: the table stores unit vectors (rx,ry,zoom)*d; perturb in the image plane and renormalise
+        u32 h = pcg_hash((u32)i ^ pcg_hash(cam.sample * 0x9E3779B9u + cam.seed));
+        float jx = (u01(h) - .5f) * cam.jitterX, jy = (u01(pcg_hash(h)) - .5f) * cam.jitterY;
+        float s = 1.f / z;                       // z = zoom*d > 0
+        float px = x * s + jx, py = y * s + jy;  // in units of zoom
+        float inv = rsqrtf(1.f + px * px + py * py);
+        x = px * inv; y = py * inv; z = inv;
+    }
+    const float* m = cam.orient;
+    d = mk3(m[0] * x + m[3] * y + m[6] * z, m[1] * x + m[4] * y + m[7] * z, m[2] * x + m[5] * y + m[8] * z);
+    o = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
+}
+#endif
 // d_workCounter: one u32 of device scratch per launch in flight (the persistent warps' work queue head)
 // d_numRays (nullable): the ray count is read from device memory at kernel start (<= n, which then only sizes the grid)
 int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numRays, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s);
@@ -117,7 +163,8 @@ int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticM
                u32 numTextures, u32* d_pixels, cudaStream_t s);
 
 // ---- rays.cu --------------------------------------------------------------------------------------------------------
-int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* d_out, cudaStream_t s);
+int camera_rays(const CameraIn& cam, u64 n, bmRay* d_out, cudaStream_t s);
+int add_count(const u32* d_count, u64 add, u64* d_total, cudaStream_t s);      // *d_total += *d_count + add (ray accounting without a host round trip)
 int bounce_rays(const bmRay* d_rays, const CameraIn* cam, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed,
                 u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s);
 int progressive_accumulate(const bmHit* d_hits1, u64 n, const bmHit* d_hits2, const u32* d_src2, const u32* d_count2, float ambient, float* d_accum,

@@ -6,6 +6,7 @@
 // plus a flat C view of the classes (beam*) so tests and bench.py can drive them through ctypes with HOST buffers.
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include <algorithm>
 #include "bm_device.cuh"
@@ -13,6 +14,27 @@
 
 namespace Beam
 {
+// All work of the host classes -- uploads, kernels, clears -- is issued on ONE non-blocking stream per device (not the legacy default
+// stream, which would serialise against every other stream of the process); read-backs run on a second stream behind an event of
+// the frame they read, so the download of frame i overlaps the kernels of frame i+1 (two render targets = double buffering).
+struct HostStreams { cudaStream_t compute = nullptr, copy = nullptr; };
+static HostStreams& host_streams()
+{
+    static HostStreams per[bm::MAX_DEVICES];
+    static std::mutex m;
+    int dev = bm::current_device();
+    std::lock_guard<std::mutex> lk(m);
+    HostStreams& h = per[dev];
+    if (!h.compute)
+    {
+        if (cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); h.compute = nullptr; }
+        if (cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); h.copy = nullptr; }
+        bmSetPart1Stream(h.compute);         // bmMarch / bmClear of this device follow
+    }
+    return h;
+}
+static cudaStream_t host_stream() { return host_streams().compute; }
+
 // RAII device allocation (DeviceBuffer.h/.cpp with size_t sizes)
 class DeviceBuffer
 {
@@ -22,13 +44,13 @@ public:
     bool ok() const { return m_dev != nullptr; }
     void copyFrom(const void* host, bool wait)
     {
-        if (wait) cudaMemcpy(m_dev, host, m_size, cudaMemcpyHostToDevice);
-        else cudaMemcpyAsync(m_dev, host, m_size, cudaMemcpyHostToDevice);
+        cudaMemcpyAsync(m_dev, host, m_size, cudaMemcpyHostToDevice, host_stream());
+        if (wait) cudaStreamSynchronize(host_stream());
     }
     void copyTo(void* host, bool wait) const
     {
-        if (wait) cudaMemcpy(host, m_dev, m_size, cudaMemcpyDeviceToHost);
-        else cudaMemcpyAsync(host, m_dev, m_size, cudaMemcpyDeviceToHost);
+        cudaMemcpyAsync(host, m_dev, m_size, cudaMemcpyDeviceToHost, host_stream());
+        if (wait) cudaStreamSynchronize(host_stream());
     }
     template <typename T> T* ptr() const { return reinterpret_cast<T*>(m_dev); }
     size_t size() const { return m_size; }
@@ -39,25 +61,37 @@ private:
 class RenderTarget : public IRenderTarget
 {
 public:
-    RenderTarget(u32 w, u32 h, u32 pitch) : m_pitch(pitch), m_width(w), m_height(h), m_store((size_t)pitch * h) {}
-    ~RenderTarget() { if (m_locked) unlock(); }
+    RenderTarget(u32 w, u32 h, u32 pitch) : m_pitch(pitch), m_width(w), m_height(h), m_store((size_t)pitch * h)
+    {
+        if (cudaEventCreateWithFlags(&m_written, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); m_written = nullptr; }
+    }
+    ~RenderTarget() { if (m_locked) unlock(); if (m_written) cudaEventDestroy(m_written); }
     void* buffer() const override { return m_locked ? m_store.ptr<void>() : nullptr; }
     u32 pitch() const override { return m_pitch; }
     u32 width() const override { return m_width; }
     u32 height() const override { return m_height; }
     u32 lock() override { if (m_locked) return ERROR_UNLOCK_FIRST; m_locked = true; s_current = this; return ERROR_ALL_FINE; }
     u32 unlock() override { if (!m_locked) return ERROR_LOCK_FIRST; m_locked = false; if (s_current == this) s_current = nullptr; return ERROR_ALL_FINE; }
+    // every launch that writes this target records the event: a read-back waits for exactly the work that produced its pixels
+    void markWritten() { if (m_written) cudaEventRecord(m_written, host_stream()); }
     u32 readPixels(u32* host) const override
     {
         if (!host) return ERROR_INVALID_PARAMETER;
-        // the trace kernels write row-major without pitch, like bmMarchKernel (BuildTree.cu:489-495 indexes buffer[i])
-        if (cudaMemcpy(host, m_store.ptr<void>(), (size_t)m_width * m_height * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return BM_ERROR_CUDA;
-        return ERROR_ALL_FINE;
+        // the trace kernels write row-major without pitch, like bmMarchKernel (BuildTree.cu:489-495 indexes buffer[i]).
+        // Copy stream + event: with a second render target in flight the copy overlaps the next frame's kernels; `host` should be
+        // pinned (beamHostAlloc) for the copy to be a single DMA.
+        cudaStream_t cs = host_streams().copy;
+        if (m_written && cudaStreamWaitEvent(cs, m_written, 0) != cudaSuccess) return BM_ERROR_CUDA;
+        if (cudaMemcpyAsync(host, m_store.ptr<void>(), (size_t)m_width * m_height * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return BM_ERROR_CUDA;
+        if (cudaStreamSynchronize(cs) != cudaSuccess) return BM_ERROR_CUDA;
+        int sticky = bmStickyError();
+        return sticky ? (u32)sticky : ERROR_ALL_FINE;
     }
     bool ok() const { return m_store.ok(); }
     static IRenderTarget* get() { return s_current; }
 private:
     u32 m_pitch, m_width, m_height; bool m_locked = false; DeviceBuffer m_store;
+    cudaEvent_t m_written = nullptr;
     static IRenderTarget* s_current;
 };
 IRenderTarget* RenderTarget::s_current = nullptr;
@@ -71,6 +105,7 @@ sptr<IRenderTarget> IRenderTarget::createHeadless(u32 width, u32 height, u32 pit
 }
 
 class Scene;
+static void scene_mesh_changed(const wptr<IScene>& scene);      // defined after Scene
 class Mesh : public IMesh
 {
 public:
@@ -85,6 +120,7 @@ public:
         if (!buf->ok()) return ERROR_GPU_ALLOC_FAIL;
         buf->copyFrom(data, !asyncCopy);
         m_data[slotId] = buf; m_sizes[slotId] = numComponents; m_numVertices = numVertices;
+        scene_mesh_changed(m_scene);          // the owning scene's pointer tables name the replaced buffer
         return ERROR_ALL_FINE;
     }
     u32 setIndices(const u32* indices, u32 numIndices, bool asyncCopy) override
@@ -94,6 +130,7 @@ public:
         if (!buf->ok()) return ERROR_GPU_ALLOC_FAIL;
         buf->copyFrom(indices, !asyncCopy);
         m_indices = buf; m_numIndices = numIndices;
+        scene_mesh_changed(m_scene);
         return ERROR_ALL_FINE;
     }
     // the material of the mesh (SharedTypes.h:20-23 bmMaterial{int texture}): width*height host texels 0x00RRGGBB, row 0 = top
@@ -104,6 +141,7 @@ public:
         if (!buf->ok()) return ERROR_GPU_ALLOC_FAIL;
         buf->copyFrom(texels, true);
         m_texture = buf; m_texW = width; m_texH = height;
+        scene_mesh_changed(m_scene);          // a texture set after addMesh / updateGPUScene counts from the next frame on
         return ERROR_ALL_FINE;
     }
     wptr<IScene> scene() const override { return m_scene; }
@@ -117,7 +155,7 @@ public:
 sptr<IMesh> IMesh::create() { return std::make_shared<Mesh>(); }
 
 // Scene + SceneTree (Scene.cpp, SceneTree.cpp).  TREE is the only scene type with behaviour in the reference.
-class Scene : public IScene
+class Scene : public IScene, public std::enable_shared_from_this<Scene>
 {
 public:
     Scene()
@@ -125,11 +163,20 @@ public:
         m_min = { -30.f, -30.f, -30.f }; m_max = { 30.f, 30.f, 30.f };               // SceneTree.cpp:43-45
         m_root = std::make_shared<DeviceBuffer>(bmGetNodeSize());                       // identifies the tree to the bm* launchers
     }
-    void addMesh(const sptr<IMesh>& mesh) override { m_meshes.push_back(std::static_pointer_cast<Mesh>(mesh)); m_dirtyTable = true; }
+    // the tree behind m_root goes with the scene (the reference frees its pools in ~SceneTree, SceneTree.cpp:55-68): a recycled root
+    // address must never find a stale tree
+    ~Scene() override { if (m_root && m_root->ok()) bmReleaseScene(m_root->ptr<void>()); }
+    void addMesh(const sptr<IMesh>& mesh) override
+    {
+        auto m = std::static_pointer_cast<Mesh>(mesh);
+        m->m_scene = weak_from_this();
+        m_meshes.push_back(m); m_dirtyTable = true;
+    }
     void removeMesh(const IMesh& mesh) override
     {
-        for (auto it = m_meshes.begin(); it != m_meshes.end(); ++it) if (it->get() == &mesh) { m_meshes.erase(it); m_dirtyTable = true; break; }
+        for (auto it = m_meshes.begin(); it != m_meshes.end(); ++it) if (it->get() == &mesh) { (*it)->m_scene.reset(); m_meshes.erase(it); m_dirtyTable = true; break; }
     }
+    void meshChanged() { m_dirtyTable = true; }
     // Scene::updateMeshPtrs, Scene.cpp:58-79
     void updateMeshPtrs()
     {
@@ -172,6 +219,7 @@ public:
             bmInsertMeshInTree(m->m_data[VERTEX_DATA_POSITION]->ptr<const bmVec3>(), m->m_indices->ptr<u32>(), m->m_numIndices, i, &m_min, &m_max,
                                m_root->ptr<void>(), nullptr, nullptr, nullptr, nullptr);
         }
+        if (bmTree* t = bmTreeFromRoot(m_root->ptr<void>())) bmTreeSetStream(t, host_stream());
         bmBuildTree(m_root->ptr<void>());
     }
     // Scene::march + SceneTree::march, Scene.cpp:81-97, SceneTree.cpp:109-127
@@ -180,10 +228,13 @@ public:
         IRenderTarget* rt = RenderTarget::get();
         if (!rt) return ERROR_NO_RENDER_TARGET;
         if (rt->width() != raysWide || rt->height() != raysHigh) return ERROR_RT_CAM_MISMATCH;
+        updateMeshPtrs();                        // a vertex / index / texture buffer replaced since the last frame: never shade through a freed pointer
         bmVec3 eye = { eye3[0], eye3[1], eye3[2] }; bmMat3 orient; memcpy(orient.m, orient9, 36);
         bmMarch(m_root->ptr<void>(), &m_min, &m_max, rays->ptr<const bmVec3>(), rt->buffer<u32>(), rt->pitch(), rt->width(), rt->height(), &eye, &orient,
                 m_table ? m_table->ptr<const bmStaticMeshData>() : nullptr);
-        return ERROR_ALL_FINE;
+        static_cast<RenderTarget*>(rt)->markWritten();
+        int sticky = bmStickyError();              // the reference's launchers return void: a failure inside is kept, not fatal
+        return sticky ? (u32)sticky : ERROR_ALL_FINE;
     }
     u32 marchHits(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh, bmHit* hostHits)
     {
@@ -192,12 +243,15 @@ public:
         IRenderTarget* rt = RenderTarget::get();
         if (rt && (rt->width() != raysWide || rt->height() != raysHigh)) return ERROR_RT_CAM_MISMATCH;
         if (!t) { for (size_t i = 0; i < n; i++) hostHits[i] = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu }; return ERROR_ALL_FINE; }
+        updateMeshPtrs();
         DeviceBuffer* hits = scratch(0, n * sizeof(bmHit));
         if (!hits) return ERROR_GPU_ALLOC_FAIL;
         int r = bmTraceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, BM_TRACE_REFERENCE, hits->ptr<bmHit>(), rt ? rt->buffer<u32>() : nullptr,
                               m_table ? m_table->ptr<const bmStaticMeshData>() : nullptr, nullptr);
         if (r != BM_OK) return (u32)r;
-        if (cudaMemcpy(hostHits, hits->ptr<void>(), n * sizeof(bmHit), cudaMemcpyDeviceToHost) != cudaSuccess) return BM_ERROR_CUDA;
+        if (rt) static_cast<RenderTarget*>(rt)->markWritten();
+        if (cudaMemcpyAsync(hostHits, hits->ptr<void>(), n * sizeof(bmHit), cudaMemcpyDeviceToHost, host_stream()) != cudaSuccess) return BM_ERROR_CUDA;
+        if (cudaStreamSynchronize(host_stream()) != cudaSuccess) return BM_ERROR_CUDA;
         return ERROR_ALL_FINE;
     }
     // hits -> deferred shading with the meshes' materials (ICamera::traceSceneTextured)
@@ -206,7 +260,7 @@ public:
         IRenderTarget* rt = RenderTarget::get();
         if (!rt) return ERROR_NO_RENDER_TARGET;
         if (rt->width() != raysWide || rt->height() != raysHigh) return ERROR_RT_CAM_MISMATCH;
-        updateMeshPtrs();                        // a texture set after updateGPUScene still counts
+        updateMeshPtrs();                        // a texture set after updateGPUScene still counts (Mesh::setTexture marks the scene dirty)
         size_t n = (size_t)raysWide * raysHigh;
         bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
         if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); return ERROR_ALL_FINE; }
@@ -216,9 +270,13 @@ public:
         if (!r) r = bmShadeHits(t, hits->ptr<bmHit>(), n, m_table->ptr<const bmStaticMeshData>(), m_materials->ptr<const bmMaterial>(),
                                 m_textures->ptr<const bmTexture>(), m_numTextures, rt->buffer<u32>());
         if (r != BM_OK) return (u32)r;
+        static_cast<RenderTarget*>(rt)->markWritten();
         return ERROR_ALL_FINE;                    // asynchronous like traceScene: the caller synchronises (readPixels does)
     }
-    // progressive frame (see ICamera::traceSceneProgressive): every sample = jittered camera rays -> trace -> bounce rays -> trace -> accumulate
+    // progressive frame (see ICamera::traceSceneProgressive): every sample = camera rays (jittered inside the pixel when samples > 1; formed
+    // in the trace kernel's registers, never materialised) -> trace in the reference's semantics -> one diffuse bounce ray per hit ->
+    // CLOSEST-hit trace of the bounce rays (t >= 0: a bounce ray starts 1e-4 above its source triangle, whose plane the reference's
+    // any-sign acceptance would "hit" at t < 0) -> accumulate.  Nothing is read back inside the frame: ray accounting stays on the device.
     u32 marchProgressive(const float* eye3, const float* orient9, const sptr<DeviceBuffer>& rays, u32 raysWide, u32 raysHigh, float jx, float jy, u32 samples,
                          u32 seed, u64* raysTraced)
     {
@@ -228,26 +286,32 @@ public:
         if (samples == 0) return ERROR_INVALID_PARAMETER;
         size_t n = (size_t)raysWide * raysHigh;
         bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
-        if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); if (raysTraced) *raysTraced = 0; return ERROR_ALL_FINE; }
-        DeviceBuffer *ph1 = scratch(0, n * sizeof(bmHit)), *pr1 = scratch(1, n * sizeof(bmRay)), *pr2 = scratch(2, n * sizeof(bmRay)), *ph2 = scratch(3, n * sizeof(bmHit)),
-                     *psrc = scratch(4, n * 4), *pcnt = scratch(5, 4), *pacc = scratch(6, n * 4), *pcov = scratch(7, n * 4);
-        if (!ph1 || !pr1 || !pr2 || !ph2 || !psrc || !pcnt || !pacc || !pcov) return ERROR_GPU_ALLOC_FAIL;
-        DeviceBuffer &h1 = *ph1, &r1 = *pr1, &r2 = *pr2, &h2 = *ph2, &src = *psrc, &cnt = *pcnt, &acc = *pacc, &cov = *pcov;
-        cudaMemset(acc.ptr<void>(), 0, n * 4); cudaMemset(cov.ptr<void>(), 0, n * 4);
-        u64 total = 0;
+        if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); static_cast<RenderTarget*>(rt)->markWritten(); if (raysTraced) *raysTraced = 0; return ERROR_ALL_FINE; }
+        cudaStream_t st = host_stream();
+        DeviceBuffer *ph1 = scratch(0, n * sizeof(bmHit)), *pr2 = scratch(2, n * sizeof(bmRay)), *ph2 = scratch(3, n * sizeof(bmHit)),
+                     *psrc = scratch(4, n * 4), *pcnt = scratch(5, 16), *pacc = scratch(6, n * 4), *pcov = scratch(7, n * 4);
+        if (!ph1 || !pr2 || !ph2 || !psrc || !pcnt || !pacc || !pcov) return ERROR_GPU_ALLOC_FAIL;
+        DeviceBuffer &h1 = *ph1, &r2 = *pr2, &h2 = *ph2, &src = *psrc, &cnt = *pcnt, &acc = *pacc, &cov = *pcov;
+        u64* total = reinterpret_cast<u64*>(cnt.ptr<char>() + 8);
+        cudaMemsetAsync(acc.ptr<void>(), 0, n * 4, st); cudaMemsetAsync(cov.ptr<void>(), 0, n * 4, st); cudaMemsetAsync(cnt.ptr<void>(), 0, 16, st);
         for (u32 s = 0; s < samples; s++)
         {
-            int r = bmCameraRays(rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, s, seed, r1.ptr<bmRay>(), nullptr);
-            if (!r) r = bmTraceRaysTiled(t, r1.ptr<bmRay>(), n, raysWide, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr);
-            if (!r) r = bmBounceRays(t, r1.ptr<bmRay>(), h1.ptr<bmHit>(), n, s, 1, seed, r2.ptr<bmRay>(), src.ptr<u32>(), cnt.ptr<u32>());
-            if (!r) r = bmTraceRaysIndirect(t, r2.ptr<bmRay>(), cnt.ptr<u32>(), n, BM_TRACE_REFERENCE, h2.ptr<bmHit>(), nullptr);
-            if (!r) r = bmProgressiveAccumulate(h1.ptr<bmHit>(), n, h2.ptr<bmHit>(), src.ptr<u32>(), cnt.ptr<u32>(), 0.25f, acc.ptr<float>(), cov.ptr<u32>(), nullptr);
+            const u32 camSample = samples > 1 ? s : 0xFFFFFFFFu;          // one sample per pixel = the exact pixel-centre ray bmMarch traces
+            int r = bmTraceCameraJittered(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, camSample, seed, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr, nullptr, nullptr);
+            if (!r) r = bmBounceRaysCameraJittered(t, rays->ptr<const float>(), eye3, orient9, jx, jy, camSample, seed, h1.ptr<bmHit>(), n, s, 1, seed, r2.ptr<bmRay>(), src.ptr<u32>(), cnt.ptr<u32>());
+            if (!r) r = bmTraceRaysIndirect(t, r2.ptr<bmRay>(), cnt.ptr<u32>(), n, BM_TRACE_CLOSEST, h2.ptr<bmHit>(), nullptr);
+            if (!r) r = bmProgressiveAccumulate(h1.ptr<bmHit>(), n, h2.ptr<bmHit>(), src.ptr<u32>(), cnt.ptr<u32>(), 0.25f, acc.ptr<float>(), cov.ptr<u32>(), st);
+            if (!r && raysTraced) r = bm::add_count(cnt.ptr<u32>(), n, total, st);
             if (r) return (u32)r;
-            if (raysTraced) { u32 c = 0; cudaMemcpy(&c, cnt.ptr<void>(), 4, cudaMemcpyDeviceToHost); total += n + c; }
         }
-        int r = bmProgressiveResolve(acc.ptr<float>(), cov.ptr<u32>(), n, samples, rt->buffer<u32>(), nullptr);
+        int r = bmProgressiveResolve(acc.ptr<float>(), cov.ptr<u32>(), n, samples, rt->buffer<u32>(), st);
         if (r) return (u32)r;
-        if (raysTraced) *raysTraced = total;
+        static_cast<RenderTarget*>(rt)->markWritten();
+        if (raysTraced)
+        {
+            // ONE read-back per frame, after everything has been queued
+            if (cudaMemcpyAsync(raysTraced, total, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return BM_ERROR_CUDA;
+        }
         return ERROR_ALL_FINE;
     }
     void* rootKey() const { return m_root->ptr<void>(); }
@@ -267,6 +331,7 @@ private:
     bool m_dirtyTable = true;
 };
 sptr<IScene> IScene::create() { return std::make_shared<Scene>(); }
+static void scene_mesh_changed(const wptr<IScene>& scene) { if (auto s = scene.lock()) static_cast<Scene*>(s.get())->meshChanged(); }
 
 class Camera : public ICamera
 {
@@ -302,7 +367,9 @@ public:
     {
         IRenderTarget* rt = RenderTarget::get();
         if (!rt) return ERROR_NO_RENDER_TARGET;
+        host_streams();                           // makes the Part-1 launchers of this device use the host classes' stream
         bmClear(rt->buffer<u32>(), rt->pitch(), rt->width(), rt->height(), value);
+        static_cast<RenderTarget*>(rt)->markWritten();
         return ERROR_ALL_FINE;
     }
     u32 traceScene(const float* eye3, const float* orient3x3, sptr<IScene>& scene) override
@@ -368,4 +435,8 @@ uint32_t beamRenderTargetUnlock(void* r) { return (*(sptr<IRenderTarget>*)r)->un
 void* beamRenderTargetBuffer(void* r) { return (*(sptr<IRenderTarget>*)r)->buffer(); }
 uint32_t beamRenderTargetReadPixels(void* r, uint32_t* hostPixels) { return (*(sptr<IRenderTarget>*)r)->readPixels(hostPixels); }
 int   beamDeviceSynchronize() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : BM_ERROR_CUDA; }
+// pinned host staging for readPixels / traceSceneHits callers (a pageable destination makes the driver stage the copy in chunks)
+void* beamHostAlloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void  beamHostFree(void* p) { if (p) cudaFreeHost(p); }
+void* beamHostStream() { return host_stream(); }
 }

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <string>
 #include <vector>
@@ -46,7 +47,8 @@ void parse_mtl(const std::string& path, const std::string& dir, std::map<std::st
     fclose(f);
 }
 
-int resolve(long v, size_t count) { return v > 0 ? (int)(v - 1) : (int)((long)count + v); }
+// 1-based or negative (relative) OBJ index -> 0-based; anything outside [0, count) comes back as -1
+int resolve(long v, size_t count) { long r = v > 0 ? v - 1 : (long)count + v; return (v != 0 && r >= 0 && (size_t)r < count) ? (int)r : -1; }
 
 bool parse_obj(const char* path, bool splitByMaterial, ObjFile& out, std::string& err)
 {
@@ -111,9 +113,12 @@ bool parse_obj(const char* path, bool splitByMaterial, ObjFile& out, std::string
                     if (*q != '/') { char* e1; t = strtol(q, &e1, 10); hasT = e1 != q; q = e1; }
                     if (*q == '/') { ++q; char* e2; n = strtol(q, &e2, 10); hasN = e2 != q; q = e2; }
                 }
-                vs.push_back(resolve(v, out.pos.size() / 3));
-                ns.push_back(hasN ? resolve(n, vn.size() / 3) : -1);
-                ts.push_back(hasT ? resolve(t, vt.size() / 2) : -1);
+                // indices are validated the moment they are resolved (a negative or huge one must never size or index a table)
+                int rv = resolve(v, out.pos.size() / 3), rn = hasN ? resolve(n, vn.size() / 3) : -1, rt = hasT ? resolve(t, vt.size() / 2) : -1;
+                if (rv < 0 || (size_t)rv >= out.pos.size() / 3) { fclose(f); err = "face index out of range"; return false; }
+                if (hasN && (rn < 0 || (size_t)rn >= vn.size() / 3)) { fclose(f); err = "face normal index out of range"; return false; }
+                if (hasT && (rt < 0 || (size_t)rt >= vt.size() / 2)) { fclose(f); err = "face texture-coordinate index out of range"; return false; }
+                vs.push_back(rv); ns.push_back(rn); ts.push_back(rt);
             }
             if (vs.size() < 3) continue;
             auto it = groupOf.find(cur);
@@ -169,7 +174,12 @@ extern "C"
 void* beamObjLoad(const char* path, int splitByMaterial)
 {
     beamObj* o = new beamObj();
-    if (!path || !parse_obj(path, splitByMaterial != 0, o->file, o->error)) { if (!path) o->error = "null path"; o->file = ObjFile(); }
+    try
+    {
+        if (!path || !parse_obj(path, splitByMaterial != 0, o->file, o->error)) { if (!path) o->error = "null path"; o->file = ObjFile(); }
+    }
+    catch (const std::exception& ex) { o->error = std::string("OBJ loader: ") + ex.what(); o->file = ObjFile(); }     // no exception crosses the C ABI
+    catch (...) { o->error = "OBJ loader: unknown failure"; o->file = ObjFile(); }
     return o;
 }
 const char* beamObjError(void* h) { beamObj* o = (beamObj*)h; return o->error.empty() ? nullptr : o->error.c_str(); }

@@ -13,37 +13,18 @@ namespace bm
 {
 namespace
 {
-__device__ __forceinline__ u32 pcg_hash(u32 v)
-{
-    u32 state = v * 747796405u + 2891336453u;
-    u32 word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
-    return (word >> 22u) ^ word;
-}
-__device__ __forceinline__ float u01(u32 h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
-
-__global__ void camera_rays_kernel(CameraIn cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* __restrict__ out)
+__global__ void camera_rays_kernel(CameraIn cam, u64 n, bmRay* __restrict__ out)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float* r = cam.initialRays + 3 * i;
-    float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
-    if (sample != 0xFFFFFFFFu)
-    {
-        // jitter inside the pixel: the table stores unit vectors (rx,ry,zoom)*d; perturb in the image plane and renormalise
-        u32 h = pcg_hash((u32)i ^ pcg_hash(sample * 0x9E3779B9u + seed));
-        float jx = (u01(h) - .5f) * jitterX, jy = (u01(pcg_hash(h)) - .5f) * jitterY;
-        float s = 1.f / z;                       // z = zoom*d > 0
-        float px = x * s + jx, py = y * s + jy;  // in units of zoom
-        float inv = rsqrtf(1.f + px * px + py * py);
-        x = px * inv; y = py * inv; z = inv;
-    }
-    const float* m = cam.orient;
-    bmRay o;
-    o.o[0] = cam.eye[0]; o.o[1] = cam.eye[1]; o.o[2] = cam.eye[2];
-    o.d[0] = m[0] * x + m[3] * y + m[6] * z; o.d[1] = m[1] * x + m[4] * y + m[7] * z; o.d[2] = m[2] * x + m[5] * y + m[8] * z;
-    out[i] = o;
+    V3 o, d;
+    camera_ray(cam, i, o, d);
+    bmRay r;
+    r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z; r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
+    out[i] = r;
 }
 
+__global__ void add_count_kernel(const u32* __restrict__ count, u64 add, u64* total) { *total += (count ? (u64)*count : 0ull) + add; }
 
 template <bool CAMERA>
 __global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, const bmHit* __restrict__ hits, const u32* __restrict__ offsets, u64 n,
@@ -57,12 +38,10 @@ __global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, cons
     bmRay r;
     if (CAMERA)
     {
-        // the primary ray exactly as bmMarch / bmTraceCamera formed it (dir = orient * initialRays[i] from eye)
-        const float* q = cam.initialRays + 3 * i;
-        float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
-        const float* m = cam.orient;
-        r.o[0] = cam.eye[0]; r.o[1] = cam.eye[1]; r.o[2] = cam.eye[2];
-        r.d[0] = m[0] * x + m[3] * y + m[6] * z; r.d[1] = m[1] * x + m[4] * y + m[7] * z; r.d[2] = m[2] * x + m[5] * y + m[8] * z;
+        // the primary ray exactly as bmMarch / bmTraceCamera formed it (camera_ray: same function, same bits)
+        V3 co, cd;
+        camera_ray(cam, i, co, cd);
+        r.o[0] = co.x; r.o[1] = co.y; r.o[2] = co.z; r.d[0] = cd.x; r.d[1] = cd.y; r.d[2] = cd.z;
     }
     else r = rays[i];
     const float4* p = soup + 3 * (size_t)tri;
@@ -141,10 +120,17 @@ int progressive_resolve(const float* d_accum, const u32* d_covered, u64 n, u32 s
     return BM_OK;
 }
 
-int camera_rays(const CameraIn& cam, u64 n, u32 width, float jitterX, float jitterY, u32 sample, u32 seed, bmRay* d_out, cudaStream_t s)
+int camera_rays(const CameraIn& cam, u64 n, bmRay* d_out, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    camera_rays_kernel<<<div_up(n, 256), 256, 0, s>>>(cam, n, width, jitterX, jitterY, sample, seed, d_out);
+    camera_rays_kernel<<<div_up(n, 256), 256, 0, s>>>(cam, n, d_out);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+
+int add_count(const u32* d_count, u64 add, u64* d_total, cudaStream_t s)
+{
+    add_count_kernel<<<1, 1, 0, s>>>(d_count, add, d_total);
     BM_LAUNCHED();
     return BM_OK;
 }
@@ -155,7 +141,7 @@ int bounce_rays(const bmRay* d_rays, const CameraIn* cam, const bmHit* d_hits, u
     if (!n) { BM_CUDA(cudaMemsetAsync(d_count, 0, 4, s)); return BM_OK; }
     BM_TRY(exclusive_scan_hit_flags(d_hits, d_flagsAndOffsets, n, d_count, d_scanTemp, s));
     if (cam) bounce_kernel<true><<<div_up(n, 256), 256, 0, s>>>(nullptr, *cam, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex);
-    else { CameraIn none = {}; bounce_kernel<false><<<div_up(n, 256), 256, 0, s>>>(d_rays, none, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex); }
+    else { CameraIn none = make_camera(nullptr, nullptr, nullptr); bounce_kernel<false><<<div_up(n, 256), 256, 0, s>>>(d_rays, none, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex); }
     BM_LAUNCHED();
     return BM_OK;
 }

@@ -50,10 +50,11 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total)
 // separate flag pass)
 template <bool HITS>
 __global__ void __launch_bounds__(SCAN_THREADS) lookback_scan_kernel(const u32* in, u32* out, size_t n, u32* __restrict__ totalOut,   // in == out allowed
-                                                                     u32* ticket, volatile unsigned long long* status, u32 numTiles)
+                                                                     u32* ticket, volatile unsigned long long* status, u32 numTiles, unsigned long long* total64)
 {
     __shared__ u32 total, sTile, sPrefix;
-    if (threadIdx.x == 0) sTile = atomicAdd(ticket, 1u);
+    __shared__ unsigned long long wide;
+    if (threadIdx.x == 0) { sTile = atomicAdd(ticket, 1u); wide = 0ull; }
     __syncthreads();
     const u32 tile = sTile;
     size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
@@ -78,6 +79,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) lookback_scan_kernel(const u32* 
         for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
     }
     u32 ex = block_exclusive_scan(s, &total);
+    if (total64)
+    {
+        // the same sum in 64 bits, so that the caller can tell a total beyond 2^32 (the u32 prefixes have wrapped) from a valid one
+        unsigned long long w = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) w += v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, o);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&wide, w);
+        __syncthreads();
+        if (threadIdx.x == 0 && wide) atomicAdd(total64, wide);
+    }
     if (threadIdx.x < 32)
     {
         const unsigned FULL = 0xFFFFFFFFu, lane = threadIdx.x;
@@ -133,10 +146,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) lookback_scan_kernel(const u32* 
 
 // small arrays (digit tables of small sorts, cluster counts ...): one block walks the array tile by tile carrying the running
 // total -- one launch instead of three
-__global__ void __launch_bounds__(SCAN_THREADS) small_scan_kernel(const u32* in, u32* out, size_t n, u32* __restrict__ totalOut)
+__global__ void __launch_bounds__(SCAN_THREADS) small_scan_kernel(const u32* in, u32* out, size_t n, u32* __restrict__ totalOut, unsigned long long* total64)
 {
     __shared__ u32 total;
     u32 carry = 0;
+    unsigned long long wide = 0;
     for (size_t tileBase = 0; tileBase < n; tileBase += SCAN_TILE)
     {
         size_t base = tileBase + (size_t)threadIdx.x * SCAN_ITEMS;
@@ -144,12 +158,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) small_scan_kernel(const u32* in,
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
         u32 ex = block_exclusive_scan(s, &total) + carry;
+        if (total64) { for (int i = 0; i < SCAN_ITEMS; i++) wide += v[i]; }
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
         carry += total;
         __syncthreads();
     }
     if (totalOut && threadIdx.x == 0) *totalOut = carry;
+    if (total64 && wide) atomicAdd(total64, wide);
 }
 constexpr size_t SMALL_SCAN_MAX = 2 * (size_t)SCAN_TILE;     // beyond two tiles the serial walk loses (measured: 55 us at 63 K)
 } // namespace
@@ -161,12 +177,12 @@ size_t scan_temp_bytes(size_t n)
     return tiles * 8 + 256;
 }
 
-int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s)
+int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void* d_temp, cudaStream_t s, unsigned long long* d_total64)
 {
     if (n == 0) { if (d_total) BM_CUDA(cudaMemsetAsync(d_total, 0, 4, s)); return BM_OK; }
     if (n <= SMALL_SCAN_MAX)
     {
-        small_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_total);
+        small_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_total, d_total64);
         BM_LAUNCHED();
         return BM_OK;
     }
@@ -174,7 +190,7 @@ int exclusive_scan_u32(const u32* d_in, u32* d_out, size_t n, u32* d_total, void
     unsigned long long* status = (unsigned long long*)d_temp;
     u32* ticket = (u32*)(status + tiles);
     BM_CUDA(cudaMemsetAsync(d_temp, 0, tiles * 8 + 8, s));
-    lookback_scan_kernel<false><<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_total, ticket, status, (u32)tiles);
+    lookback_scan_kernel<false><<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(d_in, d_out, n, d_total, ticket, status, (u32)tiles, d_total64);
     BM_LAUNCHED();
     return BM_OK;
 }
@@ -187,7 +203,7 @@ int exclusive_scan_hit_flags(const bmHit* d_hits, u32* d_out, size_t n, u32* d_t
     unsigned long long* status = (unsigned long long*)d_temp;
     u32* ticket = (u32*)(status + tiles);
     BM_CUDA(cudaMemsetAsync(d_temp, 0, tiles * 8 + 8, s));
-    lookback_scan_kernel<true><<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(reinterpret_cast<const u32*>(d_hits), d_out, n, d_total, ticket, status, (u32)tiles);
+    lookback_scan_kernel<true><<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(reinterpret_cast<const u32*>(d_hits), d_out, n, d_total, ticket, status, (u32)tiles, nullptr);
     BM_LAUNCHED();
     return BM_OK;
 }

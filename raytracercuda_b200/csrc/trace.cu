@@ -434,14 +434,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                 }
                 if (take && slot_to_ray(slot, n, width, height, rayIdx))
                 {
-                    if (CAMERA && !rays)
-                    {
-                        const float* r = cam.initialRays + 3 * rayIdx;
-                        float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
-                        const float* m = cam.orient;                              // glm mat3 * vec3 (type_mat3x3.inl:424-430)
-                        d = mk3(m[0] * x + m[3] * y + m[6] * z, m[1] * x + m[4] * y + m[7] * z, m[2] * x + m[5] * y + m[8] * z);
-                        o = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
-                    }
+                    if (CAMERA && !rays) camera_ray(cam, rayIdx, o, d);      // formed in registers: no ray record is ever written or read
                     else
                     {
                         const float* r = reinterpret_cast<const float*>(rays + rayIdx);
@@ -657,10 +650,13 @@ template <int MODE, bool CAMERA, bool COUNT>
 int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
                  const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
 {
-    static int blocksPerSM = 0;
+    static std::atomic<int> occ[MAX_DEVICES];          // per device and per instantiation
+    const int dev = current_device();
+    int blocksPerSM = occ[dev].load(std::memory_order_relaxed);
     if (!blocksPerSM)
     {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
+        occ[dev].store(blocksPerSM, std::memory_order_relaxed);
     }
     u32 height = width ? (u32)((n + width - 1) / width) : 0;
     u64 slots = width ? (u64)((width + 7) / 8) * ((height + 3) / 4) * 32 : n;
@@ -706,7 +702,7 @@ int dispatch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam,
 int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numRays, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    CameraIn cam = {};
+    CameraIn cam = make_camera(nullptr, nullptr, nullptr);
     return dispatch_trace<false>(tv, d_rays, cam, n, d_numRays, 0, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, nullptr, s);
 }
 
@@ -732,7 +728,7 @@ int trace_rays_tiled(const TreeView& tv, const bmRay* d_rays, u64 n, u32 width, 
                      const TileSched* sched, cudaStream_t s)
 {
     if (!n) return BM_OK;
-    CameraIn cam = {};
+    CameraIn cam = make_camera(nullptr, nullptr, nullptr);
     return dispatch_trace<true>(tv, d_rays, cam, n, nullptr, width, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, sched, s);
 }
 

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -11,20 +12,38 @@
 
 namespace bm
 {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{ 0 };
 static thread_local std::string g_error;
 void set_error(const std::string& s) { g_error = s; }
 const char* last_error() { return g_error.c_str(); }
 
+// Sticky error of the void-returning Part-1 launchers (the reference's CUDA_CALL prints and exits, CudaComon.cuh:59-68; a shared
+// library must not end its host process): the first failure is kept, process-wide, until bmClearStickyError.
+static std::mutex g_stickyMutex;
+static int g_stickyCode = BM_OK;
+static std::string g_stickyText;
+void set_sticky(int code, const char* where)
+{
+    std::lock_guard<std::mutex> lk(g_stickyMutex);
+    if (g_stickyCode != BM_OK) return;
+    g_stickyCode = code ? code : BM_ERROR_CUDA;
+    g_stickyText = std::string(where) + ": " + g_error;
+    fprintf(stderr, "beam_b200: %s\n", g_stickyText.c_str());
+}
+
+// per device: a process may drive several GPUs (one tree each)
+int current_device() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) { cudaGetLastError(); dev = 0; } return dev; }
 int sm_count()
 {
-    static int n = 0;
-    if (!n)
+    static std::atomic<int> n[MAX_DEVICES];
+    int dev = current_device();
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (!v)
     {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+        n[dev].store(v, std::memory_order_relaxed);
     }
-    return n;
+    return v;
 }
 
 // grow-only device buffer: rebuilding a scene of the same size performs no allocation
@@ -139,11 +158,16 @@ static int tree_build(bmTree* t)
     else BM_TRY(count_pairs(t->dgrid, t->soup.as<float4>(), (u32)T, t->counts.as<u32>(), s));
     tm.mark("classify");
     u32* d_scal = t->scalars.as<u32>();
-    BM_TRY(exclusive_scan_u32(t->counts.as<u32>(), t->counts.as<u32>(), T, d_scal + 0, t->temp.p, s));
-    BM_CUDA(cudaMemcpyAsync(&t->hostScalars[0], d_scal + 0, 4, cudaMemcpyDeviceToHost, s));
+    // the pair total is also accumulated in 64 bits (scalars[12..13]): a scene with many world-spanning triangles can exceed 2^32 pairs,
+    // and the wrapped u32 offsets must never be used to size or address the pair arrays
+    BM_TRY(exclusive_scan_u32(t->counts.as<u32>(), t->counts.as<u32>(), T, d_scal + 0, t->temp.p, s, reinterpret_cast<unsigned long long*>(d_scal + 12)));
+    unsigned long long P64 = 0;
+    BM_CUDA(cudaMemcpyAsync(&P64, d_scal + 12, 8, cudaMemcpyDeviceToHost, s));
     BM_CUDA(cudaStreamSynchronize(s));
     tm.mark("scan+readback");
-    u64 P = t->hostScalars[0];
+    if (P64 >= 0xFFFFFFF0ull) { set_error("more than 2^32 (leaf, triangle) pairs: the scene does not fit the 32-bit pair index"); return BM_ERROR_CAPACITY; }
+    u64 P = P64;
+    t->hostScalars[0] = (u32)P64;
     t->P = P;
     if (P == 0) { t->built = true; return BM_OK; }      // every triangle outside the world box
     // 3. emit + sort: key = leaf code (D bits) | in-cell sub-key, payload = triangle id.  Fewer than 1.3 pairs per triangle means the
@@ -214,7 +238,16 @@ static int tree_finish_stats(bmTree* t)
 
 // ---- Part 2 -------------------------------------------------------------------------------------------------------------
 extern "C" const char* bmLastErrorString(void) { return bm::last_error(); }
-extern "C" uint64_t bmLaunchCount(void) { return bm::g_launches; }
+extern "C" uint64_t bmLaunchCount(void) { return bm::g_launches.load(std::memory_order_relaxed); }
+extern "C" int bmStickyError(void) { std::lock_guard<std::mutex> lk(bm::g_stickyMutex); return bm::g_stickyCode; }
+extern "C" const char* bmStickyErrorString(void)
+{
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(bm::g_stickyMutex);
+    copy = bm::g_stickyText;
+    return copy.c_str();
+}
+extern "C" void bmClearStickyError(void) { std::lock_guard<std::mutex> lk(bm::g_stickyMutex); bm::g_stickyCode = BM_OK; bm::g_stickyText.clear(); }
 
 extern "C" int bmTreeCreate(bmTree** out, const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth)
 {
@@ -447,19 +480,25 @@ static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uin
     return BM_OK;
 }
 
-extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9, int mode,
-                             bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters)
+extern "C" int bmTraceCameraJittered(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                                     float jitterX, float jitterY, uint32_t sample, uint32_t seed, int mode,
+                                     bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters)
 {
     if (!t || !eye3 || !orient9 || (!d_initialRays3 && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
     if (d_pixels && !d_meshData) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) BM_TRY(tree_build(t));
-    CameraIn cam; cam.initialRays = d_initialRays3;
-    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
+    CameraIn cam = make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, sample, seed);
     if (width && numRays % width) return BM_ERROR_INVALID_PARAMETER;
     BM_TRY(t->scalars.reserve(64));
     TileSched sched;
     BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched));
     return trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream);
+}
+
+extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9, int mode,
+                             bmHit* d_hits, uint32_t* d_pixels, const bmStaticMeshData* d_meshData, uint64_t* d_counters)
+{
+    return bmTraceCameraJittered(t, d_initialRays3, numRays, width, eye3, orient9, 0.f, 0.f, 0xFFFFFFFFu, 0, mode, d_hits, d_pixels, d_meshData, d_counters);
 }
 
 extern "C" int bmTraceRaysTiled(bmTree* t, const bmRay* d_rays, uint64_t numRays, uint32_t width, int mode, bmHit* d_hits, uint64_t* d_counters)
@@ -477,9 +516,8 @@ extern "C" int bmCameraRays(const float* d_initialRays3, uint64_t numRays, uint3
 {
     if ((!d_initialRays3 || !d_out) && numRays) return BM_ERROR_INVALID_PARAMETER;
     if (!eye3 || !orient9) return BM_ERROR_INVALID_PARAMETER;
-    CameraIn cam; cam.initialRays = d_initialRays3;
-    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
-    return camera_rays(cam, numRays, width, jitterX, jitterY, sample, seed, d_out, (cudaStream_t)stream);
+    (void)width;
+    return camera_rays(make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, sample, seed), numRays, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int bmBounceRays(bmTree* t, const bmRay* d_rays, const bmHit* d_hits, uint64_t numRays, uint32_t sample, uint32_t bounce, uint32_t seed,
@@ -492,16 +530,22 @@ extern "C" int bmBounceRays(bmTree* t, const bmRay* d_rays, const bmHit* d_hits,
     return bounce_rays(d_rays, nullptr, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
 }
 
-extern "C" int bmBounceRaysCamera(bmTree* t, const float* d_initialRays3, const float* eye3, const float* orient9, const bmHit* d_hits, uint64_t numRays,
-                                  uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count)
+extern "C" int bmBounceRaysCameraJittered(bmTree* t, const float* d_initialRays3, const float* eye3, const float* orient9, float jitterX, float jitterY,
+                                          uint32_t cameraSample, uint32_t cameraSeed, const bmHit* d_hits, uint64_t numRays,
+                                          uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count)
 {
     if (!t || !d_count || !eye3 || !orient9 || ((!d_initialRays3 || !d_hits || !d_out) && numRays) || numRays >= 0xFFFFFFFFull) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) return BM_ERROR_NOT_BUILT;
     BM_TRY(t->rayFlags.reserve(numRays * 4 + 4));
     BM_TRY(t->rayTemp.reserve(scan_temp_bytes(numRays)));
-    CameraIn cam; cam.initialRays = d_initialRays3;
-    memcpy(cam.eye, eye3, 12); memcpy(cam.orient, orient9, 36);
+    CameraIn cam = make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, cameraSample, cameraSeed);
     return bounce_rays(nullptr, &cam, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
+}
+
+extern "C" int bmBounceRaysCamera(bmTree* t, const float* d_initialRays3, const float* eye3, const float* orient9, const bmHit* d_hits, uint64_t numRays,
+                                  uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count)
+{
+    return bmBounceRaysCameraJittered(t, d_initialRays3, eye3, orient9, 0.f, 0.f, 0xFFFFFFFFu, 0, d_hits, numRays, sample, bounce, seed, d_out, d_srcIndex, d_count);
 }
 
 extern "C" int bmProgressiveAccumulate(const bmHit* d_hits1, uint64_t numRays, const bmHit* d_hits2, const uint32_t* d_src2, const uint32_t* d_count2,
@@ -538,12 +582,14 @@ namespace
 std::mutex g_regMutex;
 std::map<const void*, bmTree*> g_registry;      // rootNode device pointer -> tree
 
-[[noreturn]] void die(const char* what)
-{
-    // same policy as CUDA_CALL (CudaComon.cuh:59-68): print and exit; the reference's launchers return void
-    fprintf(stderr, "beam_b200: %s: %s\n", what, bm::last_error());
-    exit(1);
-}
+// The reference's launchers return void and CUDA_CALL exits the process on failure (CudaComon.cuh:59-68).  Here a failure is recorded
+// as the process-wide sticky error (bmStickyError / bmStickyErrorString / bmClearStickyError) and the call returns without effect;
+// the host classes (host.cu) turn it into their u32 error code.
+void fail(int code, const char* what) { bm::set_sticky(code, what); }
+
+// stream of the Part-1 launchers, per device (default: the legacy default stream, which is what the reference's launches use)
+cudaStream_t g_part1Stream[bm::MAX_DEVICES] = {};
+cudaStream_t part1_stream() { return g_part1Stream[bm::current_device()]; }
 
 bmTree* find_tree(const void* root)
 {
@@ -554,6 +600,22 @@ bmTree* find_tree(const void* root)
 }
 
 extern "C" bmTree* bmTreeFromRoot(const void* root) { return find_tree(root); }
+extern "C" void bmSetPart1Stream(void* cudaStream) { g_part1Stream[bm::current_device()] = (cudaStream_t)cudaStream; }
+
+// The owner of `rootNode` is about to free it (Scene's destructor; the reference frees its pools in ~SceneTree, SceneTree.cpp:55-68):
+// drop the tree and its device buffers, so that a recycled root address can never resolve to a stale tree.
+extern "C" void bmReleaseScene(const void* rootNode)
+{
+    bmTree* t = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_regMutex);
+        auto it = g_registry.find(rootNode);
+        if (it == g_registry.end()) return;
+        t = it->second;
+        g_registry.erase(it);
+    }
+    delete t;
+}
 
 extern "C" void bmResetScene(void* rootNode, void*, void*, void*, void*, void*, void*, uint32_t, uint32_t, uint32_t)
 {
@@ -565,20 +627,27 @@ extern "C" void bmResetScene(void* rootNode, void*, void*, void*, void*, void*, 
 extern "C" void bmInsertMeshInTree(const bmVec3* vertices, const uint32_t* indices, uint32_t numIndices, uint32_t meshIdx,
                                    const bmVec3* bMin, const bmVec3* bMax, void* treeRootNode, void*, void*, void*, void*)
 {
-    bmTree* t = find_tree(treeRootNode);
+    if (!bMin || !bMax) { bm::set_error("null world box"); fail(BM_ERROR_INVALID_PARAMETER, "bmInsertMeshInTree"); return; }
     float mn[3] = { bMin->x, bMin->y, bMin->z }, mx[3] = { bMax->x, bMax->y, bMax->z };
-    if (t && (memcmp(t->hgrid.wmin, mn, 12) != 0 || memcmp(t->hgrid.wmax, mx, 12) != 0))
+    bmTree* t = nullptr;
     {
+        // find, world-box check, erase and re-create under ONE lock: two threads inserting into the same scene see one tree
         std::lock_guard<std::mutex> lk(g_regMutex);
-        g_registry.erase(treeRootNode); delete t; t = nullptr;
+        auto it = g_registry.find(treeRootNode);
+        if (it != g_registry.end())
+        {
+            t = it->second;
+            if (memcmp(t->hgrid.wmin, mn, 12) != 0 || memcmp(t->hgrid.wmax, mx, 12) != 0) { g_registry.erase(it); delete t; t = nullptr; }
+        }
+        if (!t)
+        {
+            int r = bmTreeCreate(&t, mn, mx, 0.f, 0);
+            if (r != BM_OK) { fail(r, "bmInsertMeshInTree"); return; }
+            t->stream = part1_stream();
+            g_registry[treeRootNode] = t;
+        }
     }
-    if (!t)
-    {
-        if (bmTreeCreate(&t, mn, mx, 0.f, 0) != BM_OK) die("bmInsertMeshInTree");
-        std::lock_guard<std::mutex> lk(g_regMutex);
-        g_registry[treeRootNode] = t;
-    }
-    if (bmTreeAddMesh(t, (const float*)vertices, indices, numIndices, meshIdx) != BM_OK) { bm::set_error("invalid mesh arguments"); die("bmInsertMeshInTree"); }
+    if (bmTreeAddMesh(t, (const float*)vertices, indices, numIndices, meshIdx) != BM_OK) { bm::set_error("invalid mesh arguments"); fail(BM_ERROR_INVALID_PARAMETER, "bmInsertMeshInTree"); }
 }
 
 extern "C" int bmBuildTree(void* treeRootNode)
@@ -596,16 +665,19 @@ extern "C" void bmMarch(const void* root, const bmVec3*, const bmVec3*, const bm
     if (!t)
     {
         // no mesh was ever inserted: every pixel misses (BuildTree.cu:493-496)
-        if (bm::clear_u32(buffer, n, 255u << 8, 0) != BM_OK) die("bmMarch");
+        int r0 = bm::clear_u32(buffer, n, 255u << 8, part1_stream());
+        if (r0 != BM_OK) fail(r0, "bmMarch");
         return;
     }
-    if (bmTraceCamera(t, (const float*)initialRays, n, width, &eye->x, orient->m, BM_TRACE_REFERENCE, nullptr, buffer, meshData, nullptr) != BM_OK) die("bmMarch");
+    int r = bmTraceCamera(t, (const float*)initialRays, n, width, &eye->x, orient->m, BM_TRACE_REFERENCE, nullptr, buffer, meshData, nullptr);
+    if (r != BM_OK) fail(r, "bmMarch");
 }
 
 extern "C" void bmClear(uint32_t* buffer, uint32_t pitch, uint32_t, uint32_t height, uint32_t clearValue)
 {
     // RTClear.cu:21: maxAddr = pitch/4*height - 1, addresses clamped to it -> exactly pitch/4*height words are written
-    if (bm::clear_u32(buffer, (size_t)(pitch / 4) * height, clearValue, 0) != BM_OK) die("bmClear");
+    int r = bm::clear_u32(buffer, (size_t)(pitch / 4) * height, clearValue, part1_stream());
+    if (r != BM_OK) fail(r, "bmClear");
 }
 
 // sizes of the reference's structs (BuildTree.cu:546-555 on LP64)
@@ -631,14 +703,20 @@ extern "C" void bmResetSpace(void* cells)
 
 extern "C" void bmInsertMeshInSpace(const bmVec3* vertices, const uint32_t* indices, uint32_t numIndices, void*, uint32_t meshIdx, void* cells)
 {
-    bmTree* t = find_tree(cells);
-    if (!t)
+    bmTree* t = nullptr;
     {
-        if (bmTreeCreate(&t, nullptr, nullptr, 0.f, 0) != BM_OK) die("bmInsertMeshInSpace");
         std::lock_guard<std::mutex> lk(g_regMutex);
-        g_registry[cells] = t;
+        auto it = g_registry.find(cells);
+        if (it != g_registry.end()) t = it->second;
+        else
+        {
+            int r = bmTreeCreate(&t, nullptr, nullptr, 0.f, 0);
+            if (r != BM_OK) { fail(r, "bmInsertMeshInSpace"); return; }
+            t->stream = part1_stream();
+            g_registry[cells] = t;
+        }
     }
-    if (bmTreeAddMesh(t, (const float*)vertices, indices, numIndices, meshIdx) != BM_OK) { bm::set_error("invalid mesh arguments"); die("bmInsertMeshInSpace"); }
+    if (bmTreeAddMesh(t, (const float*)vertices, indices, numIndices, meshIdx) != BM_OK) { bm::set_error("invalid mesh arguments"); fail(BM_ERROR_INVALID_PARAMETER, "bmInsertMeshInSpace"); }
 }
 
 extern "C" void bmMarchSpace(const bmVec3* initialRays, uint32_t* buffer, uint32_t pitch, uint32_t width, uint32_t height,

@@ -68,7 +68,7 @@ def test_config2_full_frame_properties(oracle_lib, beam_lib, cuda_device):
     rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev); src = torch.empty(n, dtype=torch.int32, device=dev)
     cnt = torch.zeros(1, dtype=torch.int32, device=dev); hits2 = torch.empty((n, 4), dtype=torch.float32, device=dev)
     _lib.check(L.bmBounceRaysCamera(t.h, table.data_ptr(), eye, ori, hits[0].data_ptr(), n, 0, 1, 0, rays2.data_ptr(), src.data_ptr(), cnt.data_ptr()), "bmBounceRaysCamera")
-    _lib.check(L.bmTraceRaysIndirect(t.h, rays2.data_ptr(), cnt.data_ptr(), n, 0, hits2.data_ptr(), None), "bmTraceRaysIndirect")
+    _lib.check(L.bmTraceRaysIndirect(t.h, rays2.data_ptr(), cnt.data_ptr(), n, 1, hits2.data_ptr(), None), "bmTraceRaysIndirect")      # bounce rays: closest hit, t >= 0
     torch.cuda.synchronize()
     assert int(cnt.cpu()[0]) == nh
     assert torch.equal(src[:nh].long(), torch.nonzero(hit).squeeze(1))
@@ -87,7 +87,7 @@ def test_config2_full_frame_properties(oracle_lib, beam_lib, cuda_device):
     assert np.array_equal(h["t"][both], r["t"][both])
     sel2 = np.arange(0, nh, 53)
     R = rays2[torch.from_numpy(sel2).to(dev)].cpu().numpy()
-    r2 = s.trace_rays(R[:, :3], R[:, 3:], 0, NT)
+    r2 = s.trace_rays(R[:, :3], R[:, 3:], 1, NT)
     h2 = hits_to_numpy(hits2[torch.from_numpy(sel2).to(dev)])
     ok2 = r2["tie"] == 0
     assert (h2["tri"][ok2] == r2["tri"][ok2]).mean() >= 0.9999

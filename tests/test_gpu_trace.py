@@ -205,6 +205,15 @@ def test_bounce_rays_workflow(oracle_lib, beam_lib, cuda_device):
     assert (hits2[nb:].cpu().numpy() == -1.0).all()                               # nothing beyond the device count is touched
     r = s.trace_rays(B[:, :3], B[:, 3:], 0, NT)
     _compare(h2, r, t.mesh_bases(), what="bounce rays")
+    # In the reference's any-sign semantics nearly every bounce ray "hits" its own source triangle behind its origin (t = -1e-4 / cos):
+    # that is why the product traces bounce rays as closest hits with t >= 0 (host.cu marchProgressive, bench.py) -- same check there
+    self_hit = (h2["tri"] == h1["tri"][hit_idx]) & (h2["t"] < 0)
+    assert self_hit.mean() > 0.9
+    assert beam_lib.bmTraceRaysIndirect(t.h, out.data_ptr(), cnt.data_ptr(), n, 1, hits2.data_ptr(), None) == 0
+    h3 = hits_to_numpy(hits2[:nb])
+    r3 = s.trace_rays(B[:, :3], B[:, 3:], 1, NT)
+    _compare(h3, r3, t.mesh_bases(), what="bounce rays, closest mode")
+    assert (h3["t"][h3["tri"] != 0xFFFFFFFF] >= 0).all() and (h3["tri"] == 0xFFFFFFFF).mean() > 0.5
     t.close(); s.close()
 
 

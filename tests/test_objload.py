@@ -49,6 +49,18 @@ f 3 4 5
     assert beam_lib.beamObjError(beam_lib.beamObjLoad(b"/nonexistent.obj", 0)) is not None
 
 
+@pytest.mark.parametrize("face", ["f -9//1 1//1 2//1", "f 2000000000//1 1//1 2//1", "f 1//7 2//1 3//1", "f 1/99/1 2/1/1 3/1/1", "f 0 1 2",
+                                  "f 99999999999999999999 1 2"])
+def test_bad_face_indices_are_an_error_not_a_crash(tmp_path, beam_lib, face):
+    """an index outside the tables read so far must come back as a loader error through the C ABI (no exception, no giant allocation)"""
+    path = _write(tmp_path, "v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\n" + face + "\n")
+    h = beam_lib.beamObjLoad(path.encode(), 0)
+    err = beam_lib.beamObjError(h)
+    assert err is not None and b"out of range" in err
+    assert beam_lib.beamObjNumVertices(h) == 0 and beam_lib.beamObjNumMeshes(h) == 0
+    beam_lib.beamObjFree(h)
+
+
 def test_ppm(tmp_path, beam_lib):
     px = np.array([[255 << 16, 255 << 8], [255, 0x123456]], np.uint32)
     out = str(tmp_path / "o.ppm")
