@@ -133,6 +133,7 @@ class OracleLib:
         L.orc_scene_destroy.argtypes = [vp]
         L.orc_scene_add_mesh.argtypes = [vp, _f32p, vp, C.c_uint32, _u32p, C.c_uint32]
         L.orc_scene_build.argtypes = [vp]; L.orc_scene_build.restype = C.c_double
+        L.orc_scene_build_mt.argtypes = [vp, C.c_int]; L.orc_scene_build_mt.restype = C.c_double
         L.orc_scene_stats.argtypes = [vp, _u64p]
         L.orc_scene_pairs.argtypes = [vp, _u32p, _u32p, _u32p]
         L.orc_scene_branches.argtypes = [vp, _u32p, _u32p]
@@ -163,7 +164,11 @@ class OracleScene:
         err = self.O.lib.orc_scene_add_mesh(self.h, P, None if N is None else N.ctypes.data, P.shape[0], I, I.size)
         assert err == 0, err
 
-    def build(self) -> float:
+    def build(self, nthreads: int = 1) -> float:
+        """nthreads == 1: the serial insertion exactly as the reference's host mode performs it (the pinned path);
+        nthreads > 1: the same tree from per-thread descents (orc_scene_build_mt; asserted equal in tests/test_oracle_golden.py)"""
+        if nthreads > 1:
+            return self.O.lib.orc_scene_build_mt(self.h, int(nthreads))
         return self.O.lib.orc_scene_build(self.h)
 
     def stats(self) -> dict:

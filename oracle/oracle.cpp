@@ -6,7 +6,7 @@
 //
 // PARITY PINNING: the reference ships no tests or golden vectors.  This restatement is therefore
 // pinned against the UNMODIFIED reference compiled in its own CUDA-0 host mode (oracle/build_ref.sh -> oracle/_ref/):
-// tests/test_oracle_vs_ref.py asserts identical (leaf code, mesh, triangle) lists, node / leaf counts, pixels and
+// tests/test_oracle_golden.py asserts identical (leaf code, mesh, triangle) lists, node / leaf counts, pixels and
 // primitive results on f16 / suzanne / bunny and random soups, and tests/golden/ holds the fingerprints generated from
 // that reference build (tests/golden/make_golden.py), so the pin also holds where /root/reference is absent.
 //
@@ -186,6 +186,8 @@ struct Scene
     std::vector<Node> nodes;                       // nodes[0] = root
     std::vector<FaceRec> faces;                    // one per (triangle, leaf), allocation order (bmStore<bmFace>)
     std::vector<std::vector<u32>> leafFaces;       // per leaf: face record ids in insertion order, capped like the reference
+    // the same lists flattened after a build (leaf l = leafFlat[leafFirst[l] .. + leafCount[l])): what the traversal reads
+    std::vector<u32> leafFlat, leafCount; std::vector<u64> leafFirst;
     u64 overflowLeaves = 0;
     // canonical dump
     std::vector<u32> pc, pm, pt, bdepth, bprefix;
@@ -235,6 +237,12 @@ void insert_triangle(Scene& S, u32 meshIdx, u32 triIdx)
     } while (top >= 0);
 }
 
+void flatten_leaf_lists(Scene& S)
+{
+    S.leafFlat.clear(); S.leafFirst.clear(); S.leafCount.clear();
+    for (auto& l : S.leafFaces) { S.leafFirst.push_back(S.leafFlat.size()); S.leafCount.push_back((u32)l.size()); S.leafFlat.insert(S.leafFlat.end(), l.begin(), l.end()); }
+}
+
 void canonical_dump(Scene& S)
 {
     struct P { u64 path; u32 depth, mesh, tri; };
@@ -255,17 +263,19 @@ void canonical_dump(Scene& S)
             S.maxLeafDepth = std::max<u64>(S.maxLeafDepth, e.depth); S.minLeafDepth = std::min<u64>(S.minLeafDepth, e.depth);
             S.maxLeafFaces = std::max<u64>(S.maxLeafFaces, n.faceInsertIdx);
             if (n.faceInsertIdx > S.maxFacesPerLeaf) S.overflowLeaves++;
-            for (u32 r : S.leafFaces[n.leaf]) pairs.push_back({ e.path, e.depth, S.faces[r].mesh, S.faces[r].tri });
+            for (u64 k = S.leafFirst[n.leaf], ke = k + S.leafCount[n.leaf]; k < ke; k++) { const FaceRec& f = S.faces[S.leafFlat[k]]; pairs.push_back({ e.path, e.depth, f.mesh, f.tri }); }
         }
         else
         {
             if (n.left >= 0 && n.right >= 0) branches.push_back({ e.depth, (u32)e.path });
-            if (n.left >= 0)  st.push_back({ n.left, e.depth + 1, e.path << 1 });
+            // right first: the left subtree is popped first, so leaves come out in ascending path order
             if (n.right >= 0) st.push_back({ n.right, e.depth + 1, (e.path << 1) | 1 });
+            if (n.left >= 0)  st.push_back({ n.left, e.depth + 1, e.path << 1 });
         }
     }
-    std::sort(pairs.begin(), pairs.end(), [](const P& a, const P& b) {
-        if (a.path != b.path) return a.path < b.path; if (a.mesh != b.mesh) return a.mesh < b.mesh; return a.tri < b.tri; });
+    auto less = [](const P& a, const P& b) {
+        if (a.path != b.path) return a.path < b.path; if (a.mesh != b.mesh) return a.mesh < b.mesh; return a.tri < b.tri; };
+    if (!std::is_sorted(pairs.begin(), pairs.end(), less)) std::sort(pairs.begin(), pairs.end(), less);
     S.pc.clear(); S.pm.clear(); S.pt.clear();
     for (auto& p : pairs) { S.pc.push_back((u32)p.path); S.pm.push_back(p.mesh); S.pt.push_back(p.tri); }
     std::sort(branches.begin(), branches.end());
@@ -340,9 +350,10 @@ Hit march_ray(const Scene& S, V3 eye, V3 dir, int mode, u64* counters)
             {
                 if (cur.leaf >= 0)
                 {
-                    const std::vector<u32>& fl = S.leafFaces[cur.leaf];     // already capped to MAX_FACES_PER_BOX (:411)
-                    for (u32 r : fl)
+                    // already capped to MAX_FACES_PER_BOX (:411)
+                    for (u64 k = S.leafFirst[cur.leaf], ke = k + S.leafCount[cur.leaf]; k < ke; k++)
                     {
+                        u32 r = S.leafFlat[k];
                         const FaceRec& f = S.faces[r];
                         const Mesh& M = S.meshes[f.mesh];
                         float u, v;
@@ -503,6 +514,127 @@ double orc_scene_build(void* h)
     S->faces.clear(); S->leafFaces.clear();
     for (u32 m = 0; m < S->meshes.size(); m++)
         for (u32 t = 0; t < S->meshes[m].idx.size() / 3; t++) insert_triangle(*S, m, t);
+    flatten_leaf_lists(*S);
+    double t1 = now();
+    canonical_dump(*S);
+    return t1 - t0;
+}
+
+// The same tree built with `nthreads` host threads -- for the large-scene parity tests and the CPU baseline of the bench, where the serial
+// insertion (0.1-0.3 Mtris/s) would take minutes.  It relies on one property of bmInsertTriangleInTree: WHICH leaves a triangle reaches
+// depends only on the triangle and the (fixed) boxes, never on the tree built so far (BuildTree.cu:196-253 tests geometry only; nodes are
+// created on demand).  So threads collect (leaf path, mesh, triangle) pairs for disjoint triangle ranges with the very same descent
+// (collect_triangle), the pairs are sorted by (path, mesh, triangle) = every leaf's insertion order, and the nodes are created along the
+// sorted paths.  Node INDICES differ from the serial build (allocation order), nothing observable does: tests/test_oracle_golden.py
+// asserts equal pair lists, branch lists, statistics and traced hits against orc_scene_build.
+double orc_scene_build_mt(void* h, int nthreads)
+{
+    Scene* S = (Scene*)h;
+    if (nthreads < 1) nthreads = 1;
+    double t0 = now();
+    struct Pr { u64 path; u32 mesh, tri; };
+    std::vector<u64> meshBase(S->meshes.size() + 1, 0);
+    for (size_t m = 0; m < S->meshes.size(); m++) meshBase[m + 1] = meshBase[m] + S->meshes[m].idx.size() / 3;
+    const u64 T = meshBase.back();
+    std::vector<std::vector<Pr>> per(nthreads);
+    u32 leafDepth = 0;
+    {
+        // depth at which the descent stops: a function of the world box only (every node of a depth has the same box size)
+        V3 mn = S->wmin, mx = S->wmax; u32 d = 0, ax = 0;
+        for (;;)
+        {
+            V3 b = mx - mn;
+            if (fmin_(b.x, fmin_(b.y, b.z)) < S->minLeaf || d == S->maxDepth - 1) break;
+            mx[ax] = .5f * (mn[ax] + mx[ax]); ax = (ax + 1) % 3; d++;
+        }
+        leafDepth = d;
+    }
+    parallel_for(T, nthreads, [&](u64 a, u64 b, int tid) {
+        std::vector<Pr>& out = per[tid];
+        std::vector<StackNode> stack(S->maxDepth + 2);
+        std::vector<u64> paths(S->maxDepth + 2);
+        size_t m = std::upper_bound(meshBase.begin(), meshBase.end(), a) - meshBase.begin() - 1;
+        for (u64 g = a; g < b; g++)
+        {
+            while (g >= meshBase[m + 1]) m++;
+            const Mesh& M = S->meshes[m];
+            u32 triIdx = (u32)(g - meshBase[m]);
+            V3 v[3] = { M.pos[M.idx[3 * triIdx]], M.pos[M.idx[3 * triIdx + 1]], M.pos[M.idx[3 * triIdx + 2]] };
+            // insert_triangle's loop with the node bookkeeping replaced by the path bits (0 = left, 1 = right)
+            stack[0] = { S->wmin, S->wmax, 0, 0, 0 }; paths[0] = 0;
+            i32 top = 0;
+            do
+            {
+                StackNode st = stack[top]; u64 path = paths[top]; top--;
+                V3 bSize = st.mx - st.mn;
+                float dMin = fmin_(bSize.x, fmin_(bSize.y, bSize.z));
+                if ((dMin < S->minLeaf) || (st.depth == S->maxDepth - 1)) out.push_back({ path, (u32)m, triIdx });
+                else
+                {
+                    u32 ax = st.axis, nAxis = (ax + 1) % 3, ndepth = st.depth + 1;
+                    float s = .5f * (st.mn[ax] + st.mx[ax]);
+                    V3 lMax = st.mx, rMin = st.mn;
+                    lMax[ax] = s; rMin[ax] = s;
+                    V3 bc = (lMax + st.mn) * .5f, hs = (lMax - st.mn) * .5f;
+                    bool b1 = tri_box_overlap(&bc.x, &hs.x, v) != 0;
+                    bc = (st.mx + rMin) * .5f; hs = (st.mx - rMin) * .5f;
+                    bool b2 = tri_box_overlap(&bc.x, &hs.x, v) != 0;
+                    if (b1) { ++top; stack[top] = { st.mn, lMax, 0, ndepth, nAxis }; paths[top] = path << 1; }
+                    if (b2) { ++top; stack[top] = { rMin, st.mx, 0, ndepth, nAxis }; paths[top] = (path << 1) | 1; }
+                }
+            } while (top >= 0);
+        }
+    });
+    // bucket by the top bits of the path, sort the buckets in parallel: (path, mesh, tri) ascending
+    const int BB = leafDepth > 12 ? 12 : (int)leafDepth;
+    const u64 NB = 1ull << BB;
+    const int sh = (int)leafDepth - BB;
+    std::vector<u64> cnt(NB + 1, 0);
+    for (auto& v : per) for (auto& p : v) cnt[(p.path >> sh) + 1]++;
+    for (u64 i = 0; i < NB; i++) cnt[i + 1] += cnt[i];
+    const u64 P = cnt[NB];
+    std::vector<Pr> all(P);
+    {
+        std::vector<u64> cur(cnt.begin(), cnt.end() - 1);
+        for (auto& v : per) { for (auto& p : v) all[cur[p.path >> sh]++] = p; std::vector<Pr>().swap(v); }     // threads hold ascending triangle ranges: stable
+    }
+    parallel_for(NB, nthreads, [&](u64 a, u64 b, int) {
+        for (u64 k = a; k < b; k++)
+            std::sort(all.begin() + cnt[k], all.begin() + cnt[k + 1], [](const Pr& x, const Pr& y) {
+                if (x.path != y.path) return x.path < y.path; if (x.mesh != y.mesh) return x.mesh < y.mesh; return x.tri < y.tri; });
+    });
+    // nodes along the sorted paths; leaf lists capped like bmTreeNode::insertFace (first maxFacesPerLeaf insertions kept)
+    S->nodes.clear(); S->nodes.push_back({ -1, -1, -1, 0 });
+    S->faces.clear(); S->leafFaces.clear(); S->leafFlat.clear(); S->leafCount.clear(); S->leafFirst.clear();
+    S->faces.reserve(P); S->leafFlat.reserve(P);
+    std::vector<i32> pathNode(leafDepth + 1, 0);
+    u64 prev = 0; bool have = false;
+    for (u64 i = 0; i < P; i++)
+    {
+        const Pr& p = all[i];
+        const Mesh& M = S->meshes[p.mesh];
+        if (!have || p.path != prev)
+        {
+            u32 common = 0;
+            if (have) { u64 x = prev ^ p.path; u32 hb = 63 - (u32)__builtin_clzll(x); common = leafDepth - 1 - hb; }   // levels shared with the previous leaf
+            for (u32 d = common; d < leafDepth; d++)
+            {
+                int bit = (int)((p.path >> (leafDepth - 1 - d)) & 1);
+                S->nodes.push_back({ -1, -1, -1, 0 });
+                i32 nn = (i32)S->nodes.size() - 1;
+                if (bit) S->nodes[pathNode[d]].right = nn; else S->nodes[pathNode[d]].left = nn;
+                pathNode[d + 1] = nn;
+            }
+            Node& leaf = S->nodes[pathNode[leafDepth]];
+            leaf.leaf = (i32)S->leafCount.size();
+            S->leafFirst.push_back(S->leafFlat.size()); S->leafCount.push_back(0);
+            prev = p.path; have = true;
+        }
+        Node& leaf = S->nodes[pathNode[leafDepth]];
+        u32 rec = (u32)S->faces.size();
+        S->faces.push_back({ M.idx[3 * p.tri], M.idx[3 * p.tri + 1], M.idx[3 * p.tri + 2], p.mesh, p.tri });
+        if (leaf.faceInsertIdx++ < S->maxFacesPerLeaf) { S->leafFlat.push_back(rec); S->leafCount.back()++; }
+    }
     double t1 = now();
     canonical_dump(*S);
     return t1 - t0;

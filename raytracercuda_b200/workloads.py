@@ -56,9 +56,15 @@ def get(name: str) -> Workload:
         P, I, N = _bundled("f16")
         return Workload("c3small: f16, 4 spp + 1 bounce at 320x180", "test", P, I, N, 320, 180, 1, samples=4)
     if name == "c4":
-        P, I, N = synth.displaced_icosphere(9, seed=2)
-        return Workload("c4: tyra STAND-IN (displaced icosphere, 5,242,880 tris, seed 2; Content/tyra.obj is a missing blob) 3840x2160 16 spp jittered primary + 1 diffuse bounce",
-                        "configs[3]", P, I, N, 3840, 2160, 1, samples=16)
+        # Radius 4 (eye moved back with it): at the reference viewer's unit scale 5.2 M triangles would put ~600 faces into every 0.03 leaf
+        # cell, far beyond the reference's 256-face cap (BuildTree.cuh:17), where parity is not defined.  At this scale the
+        # largest leaf holds 156 faces (overflow_leaves == 0; 7,991,992 pairs, 151,134 leaves -- checked against the oracle).
+        P, I, N = synth.displaced_icosphere(9, seed=2, radius=4.0, amplitude=0.6)
+        return Workload("c4: tyra STAND-IN (displaced icosphere radius 4, 5,242,880 tris, seed 2; Content/tyra.obj is a missing blob) 3840x2160 16 spp jittered primary + 1 diffuse bounce",
+                        "configs[3]", P, I, N, 3840, 2160, 1, eye=(0.0, 0.0, -8.4), samples=16)
+    if name == "c4small":
+        P, I, N = synth.displaced_icosphere(5, seed=2, radius=4.0, amplitude=0.6)
+        return Workload("c4small: displaced icosphere radius 4, 20,480 tris, 320x180 2 spp + 1 bounce", "test", P, I, N, 320, 180, 1, eye=(0.0, 0.0, -8.4), samples=2)
     raise ValueError(name)
 
 

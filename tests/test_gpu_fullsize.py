@@ -95,3 +95,125 @@ def test_config2_full_frame_properties(oracle_lib, beam_lib, cuda_device):
     rel = np.abs(h2["t"][both2] - r2["t"][both2]) / np.maximum(np.abs(r2["t"][both2]), 1e-20)
     assert rel.size and rel.max() <= 1e-5
     t.close(); s.close()
+
+
+def _sample_against_oracle(s, rays_np, hits_sel, mode, what, bases=None):
+    """oracle vs GPU on one strided sample of a batch (identical ray records): id >= 99.99 % (ties in t excluded), t within 1e-5 relative"""
+    from raytracercuda_b200.tree import hits_to_numpy
+    r = s.trace_rays(rays_np[:, :3], rays_np[:, 3:], mode, NT)
+    h = hits_to_numpy(hits_sel)
+    ok = r["tie"] == 0
+    assert ok.sum() >= 0.99 * ok.size
+    agree = (h["tri"][ok] == r["tri"][ok]).mean()
+    assert agree >= 0.9999, "%s: triangle id agreement %.6f" % (what, agree)
+    both = ok & (r["tri"] != 0xFFFFFFFF) & (h["tri"] == r["tri"])
+    rel = np.abs(h["t"][both] - r["t"][both]) / np.maximum(np.abs(r["t"][both]), 1e-20)
+    assert rel.size and rel.max() <= 1e-5, "%s: t differs by %g relative" % (what, rel.max() if rel.size else -1)
+    return int(both.sum())
+
+
+def _multisample_frame_vs_oracle(L, dev, wl, samples, oracle_lib, stride1, stride2, check_pairs):
+    """Samples `samples` of a multi-sample workload at its FULL resolution: the jitter applied inside the trace kernel must give exactly the
+    rays bmCameraRays materialises, and strided samples of the primary batch (reference semantics) and of the bounce batch (closest hit) must
+    match the oracle on the same ray records."""
+    import torch
+    from raytracercuda_b200 import _lib
+    from raytracercuda_b200.host import ICamera
+    from raytracercuda_b200.tree import Tree
+    W, H = wl.width, wl.height
+    n = W * H
+    Pd = torch.from_numpy(wl.positions).to(dev); Id = torch.from_numpy(wl.indices.view(np.int32)).to(dev).reshape(-1)
+    t = Tree(dev); t.add_mesh(Pd, Id); t.build()
+    st = t.stats()
+    s = OracleScene(oracle_lib); s.add_mesh(wl.positions, wl.indices, wl.normals); s.build(NT)
+    so = s.stats()
+    assert st["overflow_leaves"] == 0 == so["overflow_leaves"], "parity is defined only where no leaf exceeds the reference's 256-face cap"
+    assert so["pairs"] == st["pairs"] and so["leaves"] == st["leaves"] and so["branches"] == st["nodes"]
+    if check_pairs:
+        code, tri = t.pairs(); oc, om, ot = s.pairs()
+        assert np.array_equal(code, oc) and np.array_equal(tri, ot), "sorted (leaf code, triangle) pairs differ from the oracle"
+    cam = ICamera.create(); assert cam.setInitialRays(W, H, *wl.frustum) == 0
+    table = torch.from_numpy(cam.initialRays()).to(dev)
+    eye = (C.c_float * 3)(*wl.eye); ori = (C.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    jx, jy = abs(wl.frustum[1] - wl.frustum[0]) / W / wl.frustum[4], abs(wl.frustum[3] - wl.frustum[2]) / H / wl.frustum[4]
+    hits1 = torch.empty((n, 4), dtype=torch.float32, device=dev); hitsB = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    rays1 = torch.empty((n, 6), dtype=torch.float32, device=dev); rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    raysB = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    src = torch.empty(n, dtype=torch.int32, device=dev); cnt = torch.zeros(1, dtype=torch.int32, device=dev); cntB = torch.zeros(1, dtype=torch.int32, device=dev)
+    hits2 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    checked = 0
+    for sidx in samples:
+        _lib.check(L.bmTraceCameraJittered(t.h, table.data_ptr(), n, W, eye, ori, jx, jy, sidx, 1, 0, hits1.data_ptr(), None, None, None), "bmTraceCameraJittered")
+        _lib.check(L.bmCameraRays(table.data_ptr(), n, W, eye, ori, jx, jy, sidx, 1, rays1.data_ptr(), C.c_void_p(t.stream.cuda_stream)), "bmCameraRays")
+        _lib.check(L.bmTraceRaysTiled(t.h, rays1.data_ptr(), n, W, 0, hitsB.data_ptr(), None), "bmTraceRaysTiled")
+        torch.cuda.synchronize()
+        assert torch.equal(hits1.view(torch.int32), hitsB.view(torch.int32)), "in-kernel jitter and materialised rays disagree"
+        _lib.check(L.bmBounceRaysCameraJittered(t.h, table.data_ptr(), eye, ori, jx, jy, sidx, 1, hits1.data_ptr(), n, sidx, 1, 1, rays2.data_ptr(), src.data_ptr(), cnt.data_ptr()), "bounce")
+        _lib.check(L.bmBounceRays(t.h, rays1.data_ptr(), hits1.data_ptr(), n, sidx, 1, 1, raysB.data_ptr(), None, cntB.data_ptr()), "bmBounceRays")
+        _lib.check(L.bmTraceRaysIndirect(t.h, rays2.data_ptr(), cnt.data_ptr(), n, 1, hits2.data_ptr(), None), "bmTraceRaysIndirect")
+        torch.cuda.synchronize()
+        nb = int(cnt.cpu()[0])
+        assert nb == int(cntB.cpu()[0]) == int((hits1[:, 3].view(torch.int32) != -1).sum()) > 0 and torch.equal(rays2[:nb], raysB[:nb])
+        sel = torch.arange(sidx % stride1, n, stride1, device=dev)
+        checked += _sample_against_oracle(s, rays1[sel].cpu().numpy(), hits1[sel], 0, "%s sample %d primary" % (wl.name[:2], sidx))
+        sel2 = torch.arange(sidx % stride2, nb, stride2, device=dev)
+        _sample_against_oracle(s, rays2[sel2].cpu().numpy(), hits2[sel2], 1, "%s sample %d bounce" % (wl.name[:2], sidx))
+        assert sel.numel() >= 20000 and sel2.numel() >= 20000
+    assert checked > 1000
+    t.close(); s.close()
+
+
+def test_config3_full_resolution_samples(oracle_lib, beam_lib, cuda_device):
+    """BASELINE config 3 (f16, 64 spp + bounce at 1920x1080): samples 0 and 63 at full resolution"""
+    from raytracercuda_b200 import workloads
+    wl = workloads.get("c3")
+    assert wl.width == 1920 and wl.height == 1080 and wl.samples == 64
+    # f16 covers 3.4 % of the frame: every 3rd bounce ray still gives > 20 K
+    _multisample_frame_vs_oracle(beam_lib, cuda_device, wl, (0, 63), oracle_lib, stride1=97, stride2=3, check_pairs=True)
+
+
+def test_config4_full_size(oracle_lib, beam_lib, cuda_device):
+    """BASELINE config 4 stand-in at FULL size (5,242,880 triangles, 3840x2160): pair list and leaf / node counts equal to the oracle's, no leaf
+    above the reference's face cap, samples 0 and 15 checked on strided samples"""
+    from raytracercuda_b200 import workloads
+    wl = workloads.get("c4")
+    assert wl.num_tris == 5242880 and wl.width == 3840 and wl.height == 2160 and wl.samples == 16
+    _multisample_frame_vs_oracle(beam_lib, cuda_device, wl, (0, 15), oracle_lib, stride1=401, stride2=83, check_pairs=True)
+
+
+def _host_mem_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def test_config5_soup_20m(oracle_lib, beam_lib, cuda_device):
+    """BASELINE config 5's soup at 20 M triangles (the bench runs 100 M; the oracle's node array would not fit the host there): the complete sorted
+    pair list and the leaf / two-child-node counts equal the oracle's, and 24 K incoherent rays agree in both trace modes."""
+    import torch
+    from raytracercuda_b200 import synth
+    from raytracercuda_b200.tree import Tree
+    dev = cuda_device
+    T = 20_000_000 if _host_mem_gb() >= 48 else 5_000_000          # the oracle needs ~0.6 KB of host memory per triangle of this soup
+    Pd, Id = synth.soup_torch(T, dev)
+    t = Tree(dev); t.add_mesh(Pd, Id); t.build()
+    st = t.stats()
+    P, I = synth.soup(T)
+    assert np.array_equal(P[:3000], Pd[:3000].cpu().numpy()) and np.array_equal(P[-3000:], Pd[-3000:].cpu().numpy())     # device generator == host generator
+    s = OracleScene(oracle_lib); s.add_mesh(P, I, None); s.build(NT)
+    so = s.stats()
+    assert so["pairs"] == st["pairs"] and so["leaves"] == st["leaves"] and so["branches"] == st["nodes"] and so["overflow_leaves"] == st["overflow_leaves"] == 0
+    code, tri = t.pairs(); oc, om, ot = s.pairs()
+    assert np.array_equal(code, oc) and np.array_equal(tri, ot), "sorted (leaf code, triangle) pairs differ from the oracle"
+    del code, tri, oc, om, ot
+    rays = synth.incoherent_rays(24000)
+    R = torch.from_numpy(rays).to(dev)
+    for mode in (0, 1):
+        hits = t.trace_rays(R, mode)
+        torch.cuda.synchronize()
+        _sample_against_oracle(s, rays, hits, mode, "c5 soup mode %d" % mode)
+    t.close(); s.close()

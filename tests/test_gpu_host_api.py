@@ -221,3 +221,78 @@ def test_progressive_frame(oracle_lib, beam_lib, cuda_device):
     assert cov_np.sum() > 1000 and 0.5 < (acc_np[cov_np] > 0.3 * SPP).mean() < 1
     assert rt.unlock() == 0
     t.close(); s.close()
+
+
+def test_scene_lifetime_and_late_mesh_changes(meshes, beam_lib, cuda_device):
+    """A destroyed scene takes its tree with it (its 32-byte root allocation is readily recycled by cudaMalloc: the next scene must not find
+    a stale tree), and buffers replaced on an already-added mesh reach the scene's pointer tables before the next frame."""
+    from raytracercuda_b200 import host as H
+    L = beam_lib
+    W = Hh = 64
+    cam = H.ICamera.create(); assert cam.setInitialRays(W, Hh, -1, 1, -1, 1, 1) == 0
+    rt = H.IRenderTarget.createHeadless(W, Hh); assert rt.lock() == 0
+    eye, ori = [0, 0, -2.1], np.eye(3, dtype=np.float32)
+    for round_ in range(6):
+        scene = _scene(meshes, ["suzanne"]); scene.updateGPUScene()
+        assert cam.traceScene(eye, ori, scene) == 0
+        first = rt.readPixels()
+        assert (first != 255 << 8).sum() > 100
+        root_tree = scene.tree_handle()
+        assert root_tree
+        del scene                                        # ~Scene -> bmReleaseScene: the tree and its buffers are gone
+        fresh = H.IScene.create()                        # very likely gets the same root address back
+        assert not fresh.tree_handle()
+        assert cam.traceScene(eye, ori, fresh) == 0      # nothing inserted: every pixel misses, as in the reference
+        assert (rt.readPixels() == 255 << 8).all()
+        del fresh
+    # replacing the normals of an added mesh: the shade must read the new buffer (and never the freed one)
+    P, I, N = meshes["suzanne"]
+    scene = H.IScene.create(); m = H.IMesh.create()
+    assert m.setIndices(I, I.size) == 0 and m.setVertexData(P, P.shape[0], 3, 0) == 0 and m.setVertexData(N, N.shape[0], 3, 1) == 0
+    scene.addMesh(m); scene.updateGPUScene()
+    assert cam.traceScene(eye, ori, scene) == 0
+    a = rt.readPixels()
+    flat = np.tile(np.array([[0, 0, 1]], np.float32), (P.shape[0], 1))
+    assert m.setVertexData(flat, P.shape[0], 3, 1) == 0
+    assert cam.traceScene(eye, ori, scene) == 0
+    b = rt.readPixels()
+    hit = a != 255 << 8
+    assert np.array_equal(hit, b != 255 << 8) and (b[hit] == 255 << 16).all() and (a[hit] != 255 << 16).any()
+    assert L.bmStickyError() == 0
+    assert rt.unlock() == 0
+
+
+def test_part1_failures_are_sticky_not_fatal(beam_lib, cuda_device):
+    """the reference's launchers return void and exit(1) on failure (CudaComon.cuh:59-68); this library keeps the first failure instead"""
+    import torch
+    from raytracercuda_b200._lib import bmVec3
+    L = beam_lib
+    L.bmClearStickyError()
+    root = torch.zeros(8, dtype=torch.int32, device=cuda_device)
+    pos = torch.zeros(9, dtype=torch.float32, device=cuda_device); idx = torch.arange(3, dtype=torch.int32, device=cuda_device)
+    lo, hi = bmVec3(-30, -30, -30), bmVec3(30, 30, 30)
+    L.bmInsertMeshInTree(pos.data_ptr(), idx.data_ptr(), 4, 0, C.byref(lo), C.byref(hi), root.data_ptr(), None, None, None, None)      # 4 indices: not triangles
+    assert L.bmStickyError() == 2 and b"bmInsertMeshInTree" in L.bmStickyErrorString()
+    bad_lo, bad_hi = bmVec3(0, 0, 0), bmVec3(1, 1e-9, 1)
+    L.bmInsertMeshInTree(pos.data_ptr(), idx.data_ptr(), 3, 0, C.byref(bad_lo), C.byref(bad_hi), root.data_ptr(), None, None, None, None)
+    assert L.bmStickyError() == 2                         # the FIRST failure is kept
+    L.bmClearStickyError()
+    assert L.bmStickyError() == 0
+    L.bmReleaseScene(root.data_ptr())
+    L.bmReleaseScene(root.data_ptr())                     # unknown roots are ignored
+    assert L.bmTreeFromRoot(root.data_ptr()) is None
+
+
+def test_pair_total_beyond_32_bits_is_a_capacity_error(beam_lib, cuda_device):
+    """2,600 world-spanning triangles reach ~2 M leaf cells each: the pair total passes 2^32 and must come back as BM_ERROR_CAPACITY,
+    not as wrapped offsets"""
+    from raytracercuda_b200.tree import Tree
+    n = 2600
+    z = np.linspace(-20, 20, n).astype(np.float32)
+    P = np.zeros((n, 3, 3), np.float32)
+    P[:, 0] = [-29.9, -29.9, 0]; P[:, 1] = [29.9, -29.9, 0]; P[:, 2] = [0, 29.9, 0]
+    P[:, :, 2] = z[:, None]
+    t = Tree(cuda_device); t.add_mesh(P.reshape(-1, 3), np.arange(3 * n, dtype=np.uint32))
+    r = beam_lib.bmTreeBuild(t.h)
+    assert r == 103 and b"pairs" in beam_lib.bmLastErrorString()
+    t.close()

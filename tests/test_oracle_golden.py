@@ -150,3 +150,32 @@ def test_oracle_equals_reference_on_random_soups(oracle_lib):
         r = b.trace_camera(oracle_lib.initial_rays(96, 96), eye, np.eye(3, dtype=np.float32))
         assert err == 0 and np.array_equal(px.reshape(-1), r["pixels"])
         a.close(); b.close()
+
+
+def test_threaded_build_equals_the_serial_insertion(oracle_lib, meshes):
+    """orc_scene_build_mt (used for the multi-million-triangle parity tests and the bench's CPU baseline) against the serial insertion that
+    restates the reference: identical pair lists, two-child nodes, statistics -- leaf cap included -- and traced hits in both modes."""
+    from raytracercuda_b200 import synth
+    rng = np.random.default_rng(5)
+    c = rng.uniform(-0.05, 0.05, (1500, 1, 3)).astype(np.float32)
+    dense = np.ascontiguousarray((c + rng.uniform(-0.02, 0.02, (1500, 3, 3)).astype(np.float32)).reshape(-1, 3))       # leaves over the 256-face cap
+    cases = [("f16",) + meshes["f16"], ("suzanne",) + meshes["suzanne"], ("soup",) + synth.soup(30000, extent=3.0, edge=0.05) + (None,),
+             ("dense", dense, np.arange(4500, dtype=np.uint32).reshape(-1, 3), None)]
+    rays = synth.incoherent_rays(4000, extent=3.0)
+    for name, P, I, N in cases:
+        a = OracleScene(oracle_lib); a.add_mesh(P, I, N); a.build()
+        b = OracleScene(oracle_lib); b.add_mesh(P, I, N); b.add_mesh(P[::-1].copy(), I, N)          # two meshes: the (mesh, triangle) order matters
+        a2 = OracleScene(oracle_lib); a2.add_mesh(P, I, N); a2.add_mesh(P[::-1].copy(), I, N); a2.build()
+        one = OracleScene(oracle_lib); one.add_mesh(P, I, N); one.build(5)
+        b.build(3)
+        for x, y in ((a, one), (a2, b)):
+            assert x.stats() == y.stats(), name
+            assert all(np.array_equal(p, q) for p, q in zip(x.pairs(), y.pairs())), name
+            assert all(np.array_equal(p, q) for p, q in zip(x.branches(), y.branches())), name
+            for mode in (0, 1):
+                rx = x.trace_rays(rays[:, :3], rays[:, 3:], mode, 2); ry = y.trace_rays(rays[:, :3], rays[:, 3:], mode, 2)
+                assert all(np.array_equal(rx[k], ry[k]) for k in ("t", "u", "v", "mesh", "tri", "tie", "pixels")), (name, mode)
+        if name == "dense":
+            assert a.stats()["overflow_leaves"] > 0
+        for s_ in (a, b, a2, one):
+            s_.close()
