@@ -32,6 +32,10 @@ sys.path.insert(0, ROOT)
 METRIC = "Mrays/s closest-hit (primary + diffuse)"
 FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 NODE_BYTES, TRI_BYTES, CLUSTER_BYTES, LEAF_BYTES = 96, 48, 32, 48     # bytes a visit reads: node = 6 float4 of its 128-byte record
+# Primary rays are traced in the reference's semantics (BM_TRACE_REFERENCE = 0, the parity mode).  Diffuse bounce rays are traced as closest
+# hits with t >= 0 (BM_TRACE_CLOSEST = 1): a bounce ray starts 1e-4 above its source triangle, and the reference's any-sign acceptance would
+# "hit" that triangle's plane at t < 0 in the first leaf it enters (99 % of bounce rays; tests/test_gpu_trace.py pins this).
+BOUNCE_MODE = 1
 
 
 def measured_peaks():
@@ -248,11 +252,12 @@ def run_b200(args):
         acc.zero_(); cov.zero_(); cnt_sum.zero_()
         sp = C.c_void_p(stream.cuda_stream)
         for sidx in range(SPP):
-            _lib.check(L.bmCameraRays(rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), jit[0], jit[1], sidx, args.seed, rays1.data_ptr(), sp), "bmCameraRays")
-            # the jittered camera rays of a sample are an image: traced in 8x4 tiles under the temporal tile schedule
-            _lib.check(L.bmTraceRaysTiled(tree.h, rays1.data_ptr(), n, W, 0, hits1.data_ptr(), None), "bmTraceRaysTiled")
-            _lib.check(L.bmBounceRays(tree.h, rays1.data_ptr(), hits1.data_ptr(), n, sidx, 1, args.seed, rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRays")
-            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, 0, hits2.data_ptr(), None), "bmTraceRaysIndirect")
+            # the sample's jitter is applied where the trace kernel forms the ray (no 24-byte ray record per sample is written or read);
+            # the launch is a camera launch: 8x4 tiles under the temporal tile schedule
+            _lib.check(L.bmTraceCameraJittered(tree.h, rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), jit[0], jit[1], sidx, args.seed, 0, hits1.data_ptr(), None, None, None), "bmTraceCameraJittered")
+            _lib.check(L.bmBounceRaysCameraJittered(tree.h, rays_in.data_ptr(), _f3(eye), _f9(orient), jit[0], jit[1], sidx, args.seed, hits1.data_ptr(), n, sidx, 1, args.seed,
+                                                    rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCameraJittered")
+            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRaysIndirect")
             _lib.check(L.bmProgressiveAccumulate(hits1.data_ptr(), n, hits2.data_ptr(), src2.data_ptr(), cnt2.data_ptr(), 0.25, acc.data_ptr(), cov.data_ptr(), sp), "accumulate")
             cnt_sum.add_(cnt2)
         _lib.check(L.bmProgressiveResolve(acc.data_ptr(), cov.data_ptr(), n, SPP, pixels.data_ptr(), sp), "resolve")
@@ -292,7 +297,7 @@ def run_b200(args):
                                                 o_rays2.data_ptr() + lo * 24, o_src2.data_ptr() + lo * 4, o_cnt.data_ptr() + k * 4), "bmBounceRaysCamera")
                 if marks is not None and NB == 1: marks[2].record()
                 # the bounce count stays on the device: the trace kernel reads it there (no host round trip inside the step)
-                _lib.check(L.bmTraceRaysIndirect(bt.h, o_rays2.data_ptr() + lo * 24, o_cnt.data_ptr() + k * 4, nbnd, 0, o_hits2.data_ptr() + lo * 16, None), "bmTraceRaysIndirect")
+                _lib.check(L.bmTraceRaysIndirect(bt.h, o_rays2.data_ptr() + lo * 24, o_cnt.data_ptr() + k * 4, nbnd, BOUNCE_MODE, o_hits2.data_ptr() + lo * 16, None), "bmTraceRaysIndirect")
             if NB > 1:
                 e_ = torch.cuda.Event(); e_.record(bs); stream.wait_event(e_)
         work = None
@@ -347,7 +352,7 @@ def run_b200(args):
     nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST sample only
     if nb_last and SPP == 1:
         cnt.zero_()
-        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, 0, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, BOUNCE_MODE, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
         torch.cuda.synchronize(dev)
         V2, K2, C2, LONG2 = [int(x) for x in cnt.cpu()]
 
@@ -410,7 +415,7 @@ def run_b200(args):
         if wl.bounces:
             _lib.check(L.bmBounceRaysCamera(tree.h, S["rays"].data_ptr(), _f3(eye), _f9(orient), S["hits1"].data_ptr(), n, 0, 1, args.seed, S["rays2"].data_ptr(),
                                             S["src2"].data_ptr(), S["cnt"].data_ptr()), "bmBounceRaysCamera")
-            _lib.check(L.bmTraceRaysIndirect(tree.h, S["rays2"].data_ptr(), S["cnt"].data_ptr(), n, 0, S["hits2"].data_ptr(), None), "bmTraceRaysIndirect")
+            _lib.check(L.bmTraceRaysIndirect(tree.h, S["rays2"].data_ptr(), S["cnt"].data_ptr(), n, BOUNCE_MODE, S["hits2"].data_ptr(), None), "bmTraceRaysIndirect")
 
     def e2e_compute(i):
         """kernels of frame i (asynchronous)"""
@@ -592,7 +597,7 @@ def run_b200(args):
             bounce_ms = []
             for _ in range(5):
                 flush.zero_(); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
-                _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, 0, hits2.data_ptr(), None), "bmTraceRays")
+                _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRays")
                 e1.record(); torch.cuda.synchronize(dev); bounce_ms.append(e0.elapsed_time(e1))
         bms2 = statistics.mean(bounce_ms)
         roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb / (bms2 * 1e-3) / 1e6, "rays": nb,
@@ -602,7 +607,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "rays_per_step_per_gpu": rays_step, "primary_rays_per_gpu": n * SPP, "bounce_rays_per_gpu": nb, "samples_per_pixel": SPP,
-                       "trace_mode": "reference semantics (BM_TRACE_REFERENCE)", "l2": "flushed between timed steps (256 MiB write)", "bands": NB, "cpu_affinity": numa,
+                       "trace_mode": "primary rays: reference semantics (BM_TRACE_REFERENCE); bounce rays: closest hit, t >= 0 (BM_TRACE_CLOSEST)", "l2": "flushed between timed steps (256 MiB write)", "bands": NB, "cpu_affinity": numa,
                        "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer overlapped with the bounce trace" if world > 1 else "single GPU",
                        "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
@@ -773,7 +778,7 @@ def cpu_baseline(wl, initial_rays, bounce_rays, bounce_src, budget_rays=2_100_00
         keep = (bounce_src % stride) == 0
         B = np.ascontiguousarray(bounce_rays[keep])
         if B.shape[0]:
-            r2 = s.trace_rays(B[:, :3], B[:, 3:], 0, cores)
+            r2 = s.trace_rays(B[:, :3], B[:, 3:], BOUNCE_MODE, cores)
             rays += B.shape[0]; secs += r2["seconds"]
     s.close()
     out = {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
@@ -847,7 +852,7 @@ def run_reference(args):
                 a = np.where(np.abs(nrm[:, :1]) > 0.9, np.array([[0, 1, 0]]), np.array([[1, 0, 0]]))
                 t1 = np.cross(nrm, a); t1 /= np.linalg.norm(t1, axis=1, keepdims=True); t2 = np.cross(nrm, t1)
                 nd = t1 * (rr * np.cos(phi))[:, None] + t2 * (rr * np.sin(phi))[:, None] + nrm * np.sqrt(np.maximum(0, 1 - u1))[:, None]
-                r2 = s.trace_rays((hp + 1e-4 * nrm).astype(np.float32), nd.astype(np.float32), 0, cores)
+                r2 = s.trace_rays((hp + 1e-4 * nrm).astype(np.float32), nd.astype(np.float32), BOUNCE_MODE, cores)
                 total += t.size; secs += r2["seconds"]
         return total, secs
 

@@ -116,8 +116,8 @@ bool parse_obj(const char* path, bool splitByMaterial, ObjFile& out, std::string
                 // indices are validated the moment they are resolved (a negative or huge one must never size or index a table)
                 int rv = resolve(v, out.pos.size() / 3), rn = hasN ? resolve(n, vn.size() / 3) : -1, rt = hasT ? resolve(t, vt.size() / 2) : -1;
                 if (rv < 0 || (size_t)rv >= out.pos.size() / 3) { fclose(f); err = "face index out of range"; return false; }
-                if (hasN && (rn < 0 || (size_t)rn >= vn.size() / 3)) { fclose(f); err = "face normal index out of range"; return false; }
-                if (hasT && (rt < 0 || (size_t)rt >= vt.size() / 2)) { fclose(f); err = "face texture-coordinate index out of range"; return false; }
+                // a normal / texture-coordinate reference outside the tables read so far is ignored (files in the wild name `vt` indices
+                // without any `vt` line); resolve() has already turned it into -1, so it can never size or index a table
                 vs.push_back(rv); ns.push_back(rn); ts.push_back(rt);
             }
             if (vs.size() < 3) continue;
