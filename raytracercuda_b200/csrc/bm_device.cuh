@@ -52,12 +52,15 @@ static const u32 LEAF_BIT = 0x80000000u;
 static const u32 EXCLUDED_BIT = 0x80000000u;
 struct TreeView
 {
-    const float4* nodes;
+    const float4* nodes;      // 128-byte binary records (null unless the tree was built with BM_NODE_LAYOUT=both|binary)
+    const uint4* wnodes;      // 64-byte wide records (bm_wide.cuh)
     const float4* leaves;
     const float4* ltris;
     const float4* clusters;
     u32 numLeaves;
     const u32* root;      // device: index of the root node (numLeaves >= 2; a single leaf is its own root)
+    Grid grid;            // the wide records store cell coordinates: boxes and planes are rebuilt from the grid
+    float leafExt[3];     // largest leaf-cell extent per axis (+ the boxes' pad): reach of a leaf cell beyond the triangles it holds
 };
 
 // ---- scan.cu --------------------------------------------------------------------------------------------------------
@@ -95,8 +98,9 @@ int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_
 int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* d_leafIdx, size_t numPairs, const u32* d_clusterFirst, float4* d_ltris,
                 float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, u32* d_overList, cudaStream_t s);
 // radix tree + tight boxes + reference-node data in one bottom-up pass; *d_root receives the root's node index
+// d_nodes (nullable): the 128-byte binary records; d_wnodes: the 64-byte wide records (bm_wide.cuh); d_nodeMeta: scratch, 8 bytes per node
 int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
-                    float4* d_nodes, u32* d_root, cudaStream_t s);
+                    float4* d_nodes, uint4* d_wnodes, uint2* d_nodeMeta, u32* d_root, cudaStream_t s);
 int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, int subBits, u64* d_out, cudaStream_t s);
 int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s);
 

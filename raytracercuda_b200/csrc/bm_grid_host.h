@@ -19,7 +19,7 @@ struct HostGrid
 inline void fill_grid(Grid& g, const HostGrid& h, const float* t0, const float* t1, const float* t2)
 {
     g.tab[0] = t0; g.tab[1] = t1; g.tab[2] = t2;
-    for (int a = 0; a < 3; a++) { g.k[a] = h.k[a]; g.wmin[a] = h.wmin[a]; g.w[a] = h.w[a]; }
+    for (int a = 0; a < 3; a++) { g.k[a] = h.k[a]; g.wmin[a] = h.wmin[a]; g.w[a] = h.w[a]; g.wext[a] = h.wmax[a] - h.wmin[a]; }
     g.D = h.D; g.uniform = h.uniform; g.subBits = 9;
 }
 

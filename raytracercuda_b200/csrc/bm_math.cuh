@@ -103,6 +103,7 @@ struct Grid
     // `uniform` is set and boundaries are computed instead of loaded (checked entry by entry on the host, bm_grid_host.h).
     int uniform;
     float wmin[3], w[3];
+    float wext[3];  // world extent per axis (wmax - wmin)
     // bits of the in-cell Morton sub-key appended to the leaf code in the sort key (3, 6, ... 15; chosen per build, tree.cu)
     int subBits;
 };

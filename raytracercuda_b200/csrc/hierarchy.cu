@@ -7,6 +7,7 @@
 // have no counterpart because they take no decision.  agglomerate_kernel stores (prefix, prefixLen) and, precomputed from the
 // grid tables, the node's cell box, split axis (prefixLen % 3) and split plane -- the reference's own values.
 #include "bm_device.cuh"
+#include "bm_wide.cuh"
 
 namespace bm
 {
@@ -166,8 +167,17 @@ __device__ __forceinline__ u32 range_delta(const u32* __restrict__ codes, int i,
 struct Box2 { float4 a, b; };                 // (lo.xyz, hi.x) (hi.y, hi.z, -, -)
 __device__ __forceinline__ Box2 load_box(const float4* p) { Box2 r; r.a = __ldcg(p); r.b = __ldcg(p + 1); return r; }   // written by another thread of this launch: bypass L1
 
+__device__ __forceinline__ WSlotBox slot_box(const Box2& b)
+{
+    WSlotBox r;
+    r.lo[0] = b.a.x; r.lo[1] = b.a.y; r.lo[2] = b.a.z; r.hi[0] = b.a.w; r.hi[1] = b.b.x; r.hi[2] = b.b.y;
+    return r;
+}
+
+// nodes128 (nullable): the uncompressed binary record of round 1 (BM_NODE_LAYOUT=both keeps it for A/B runs); wnodes: the 64-byte wide
+// record (bm_wide.cuh); nodeMeta[n] = (packed cell coordinates, depth) of node n, read back by n's parent when it absorbs n.
 __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 numLeaves, const float4* __restrict__ leafBox, float4* nodeBox,
-                                   int* otherBound, u32* childRefs, float4* nodes, u32* rootOut)
+                                   int* otherBound, u32* childRefs, float4* nodes, uint4* wnodes, uint2* nodeMeta, u32* rootOut)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = (int)numLeaves;
@@ -198,13 +208,42 @@ __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 nu
         u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
         int sh = g.k[axis] - axis_bits(plen, axis);   // >= 1: the node splits on this axis
         float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
-        float4* np = nodes + NODE_F4 * (size_t)parent;
-        np[0] = b0.a;                                                   // lo0.xyz hi0.x
-        np[1] = make_float4(b0.b.x, b0.b.y, b1.a.x, b1.a.y);            // hi0.yz lo1.xy
-        np[2] = make_float4(b1.a.z, b1.a.w, b1.b.x, b1.b.y);            // lo1.z hi1.xyz
-        np[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
-        np[4] = make_float4(mn.x, mn.y, mn.z, sp);
-        np[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
+        if (nodes)
+        {
+            float4* np = nodes + NODE_F4 * (size_t)parent;
+            np[0] = b0.a;                                                   // lo0.xyz hi0.x
+            np[1] = make_float4(b0.b.x, b0.b.y, b1.a.x, b1.a.y);            // hi0.yz lo1.xy
+            np[2] = make_float4(b1.a.z, b1.a.w, b1.b.x, b1.b.y);            // lo1.z hi1.xyz
+            np[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
+            np[4] = make_float4(mn.x, mn.y, mn.z, sp);
+            np[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
+        }
+        {
+            // the wide record: children that are internal nodes are absorbed (their own children become this record's slots)
+            const u32 cell0 = wide_pack_cell(g, ix, iy, iz);
+            u32 ref[4] = { c0, WREF_EMPTY, c1, WREF_EMPTY };
+            WSlotBox box[4];
+            box[0] = slot_box(b0); box[2] = slot_box(b1); box[1] = box[0]; box[3] = box[2];
+            u32 cellAB[2] = { 0u, 0u }, lenAB[2] = { WLEN_NONE, WLEN_NONE };
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+            {
+                const u32 c = h ? c1 : c0;
+                if (c & LEAF_BIT) continue;
+                uint2 m = __ldcg(&nodeMeta[c]);
+                cellAB[h] = m.x; lenAB[h] = m.y;
+                u32 g0 = __ldcg(&childRefs[2 * (size_t)c]), g1 = __ldcg(&childRefs[2 * (size_t)c + 1]);
+                ref[2 * h] = g0; ref[2 * h + 1] = g1;
+                box[2 * h] = slot_box(load_box((g0 & LEAF_BIT) ? leafBox + 2 * (size_t)(g0 & ~LEAF_BIT) : nodeBox + 2 * (size_t)g0));
+                box[2 * h + 1] = slot_box(load_box((g1 & LEAF_BIT) ? leafBox + 2 * (size_t)(g1 & ~LEAF_BIT) : nodeBox + 2 * (size_t)g1));
+            }
+            WQ rec[4];
+            wide_encode(g, cell0, (u32)plen, cellAB[0], lenAB[0], cellAB[1], lenAB[1], ref, box, rec);
+            uint4* wp = wnodes + WNODE_U4 * (size_t)parent;
+#pragma unroll
+            for (int k = 0; k < 4; k++) wp[k] = make_uint4(rec[k].x, rec[k].y, rec[k].z, rec[k].w);
+            __stcg(&nodeMeta[parent], make_uint2(cell0, (u32)plen));
+        }
         if (l == 0 && r == n - 1) { *rootOut = (u32)parent; return; }
         float4* o = nodeBox + 2 * (size_t)parent;
         __stcg(o, make_float4(fminf(b0.a.x, b1.a.x), fminf(b0.a.y, b1.a.y), fminf(b0.a.z, b1.a.z), fmaxf(b0.a.w, b1.a.w)));
@@ -263,11 +302,11 @@ int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* 
     return BM_OK;
 }
 int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
-                    float4* d_nodes, u32* d_root, cudaStream_t s)
+                    float4* d_nodes, uint4* d_wnodes, uint2* d_nodeMeta, u32* d_root, cudaStream_t s)
 {
     if (numLeaves < 2) return BM_OK;
     BM_CUDA(cudaMemsetAsync(d_otherBound, 0xFF, (size_t)(numLeaves - 1) * 4, s));
-    agglomerate_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_otherBound, d_childRefs, d_nodes, d_root);
+    agglomerate_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_otherBound, d_childRefs, d_nodes, d_wnodes, d_nodeMeta, d_root);
     BM_LAUNCHED();
     return BM_OK;
 }

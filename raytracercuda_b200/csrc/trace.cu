@@ -11,13 +11,14 @@
 //     triangle below it can be hit, so results are unchanged and most of the reference's ~97 node visits per ray vanish.
 #include <cstdlib>
 #include "bm_device.cuh"
+#include "bm_wide.cuh"
 
 namespace bm
 {
 namespace
 {
 constexpr int TR_THREADS = 128;
-constexpr int TR_STACK = 36;     // radix tree depth <= D <= 32
+constexpr int TR_STACK = 52;     // binary walk: depth <= D <= 32; wide walk: a visit pops one entry and pushes up to four, <= 16 wide levels
 constexpr int COOP_MAX_LANES = 8;   // at most this many pending leaves in a warp -> process the sizeable ones warp-cooperatively
 constexpr int COOP_MIN_FACES = 8;   // ... where sizeable = more than this many faces
 constexpr u32 REF_EMPTY = 0x7FFFFFFFu;   // "nothing left to visit" (never a valid internal index: N < 2^31 - 1)
@@ -89,6 +90,19 @@ __device__ __forceinline__ void closest_node(const TreeView& tv, u32 ref, V3 o, 
     bool nearHit = firstIs0 ? h0 : h1, farHit = firstIs0 ? h1 : h0;
     if (farHit) stack[++top] = farRef;
     if (nearHit) stack[++top] = nearRef;
+}
+
+// ---- the 64-byte wide node: one line in, up to four references out (wide_step, bm_wide.cuh) ---------------------------------------
+template <int MODE>
+__device__ __forceinline__ void wide_node(const TreeView& tv, u32 ref, V3 o, V3 d, V3 inv, V3 ic, V3 oi, V3 fm, float tbest, u32* stack, int& top)
+{
+    const uint4* np = tv.wnodes + WNODE_U4 * (size_t)ref;
+    const uint4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), e = __ldg(np + 3);
+    u32 push[4];
+    const int n = wide_step<MODE>(tv.grid, WQ{ a.x, a.y, a.z, a.w }, WQ{ b.x, b.y, b.z, b.w }, WQ{ c.x, c.y, c.z, c.w }, WQ{ e.x, e.y, e.z, e.w }, o, d, inv, ic, oi, fm,
+                                  tbest, push);
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < n) stack[++top] = push[k];
 }
 
 // One face against the ray.  The reference keeps the strict minimum while walking the leaf's list in insertion order, i.e. on
@@ -370,7 +384,7 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
 #ifndef BM_TR_BLOCKS
 #define BM_TR_BLOCKS 6
 #endif
-template <int MODE, bool CAMERA, bool COUNT>
+template <int MODE, bool CAMERA, bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
                                                            const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int leafWait, int refillMin, TileSched sched)
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
     u32 cur = REF_EMPTY;
     bool active = false, exhausted = false;
     u64 rayIdx = 0;
-    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), ic = mk3(0, 0, 1), oi = mk3(0, 0, 0);
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), ic = mk3(0, 0, 1), oi = mk3(0, 0, 0), fm = mk3(0, 0, 0);
     HitRec best = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
     u32 nv = 0, nt = 0, nc = 0, rayStart = 0, longest = 0;      // COUNT only: totals, and the longest single ray (the kernel's critical path)
     // temporal tile scheduling (camera launches; see TileSched): the tile this warp is working on and when it started
@@ -444,6 +458,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
                     ic = mk3(cull_inv(inv.x), cull_inv(inv.y), cull_inv(inv.z));
                     oi = o * ic;
+                    if (WIDE && MODE == BM_TRACE_REFERENCE) fm = mk3(tv.leafExt[0] * fabsf(ic.x), tv.leafExt[1] * fabsf(ic.y), tv.leafExt[2] * fabsf(ic.z));
                     best.t = FLT_MAX; best.u = 0.f; best.v = 0.f; best.tri = best.mesh = best.face = 0xFFFFFFFFu;
                     top = -1;
                     cur = rootRef;
@@ -470,7 +485,8 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
             if (inner)
             {
                 if (COUNT) nv++;
-                if (MODE == BM_TRACE_REFERENCE) ref_node(tv, cur, o, d, inv, ic, oi, stack, top);
+                if (WIDE) wide_node<MODE>(tv, cur, o, d, inv, ic, oi, fm, best.t, stack, top);
+                else if (MODE == BM_TRACE_REFERENCE) ref_node(tv, cur, o, d, inv, ic, oi, stack, top);
                 else closest_node(tv, cur, o, inv, best.t, stack, top);
                 cur = top >= 0 ? stack[top--] : REF_EMPTY;
             }
@@ -646,7 +662,15 @@ int refill_min(bool camera)
     return v > 0 ? v : (camera ? 32 : 8);
 }
 
-template <int MODE, bool CAMERA, bool COUNT>
+// node layout walked by the trace kernels: the 64-byte wide records unless BM_WIDE=0 asks for the binary records of a tree that has them
+bool use_wide(const TreeView& tv)
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BM_WIDE"); v = e ? atoi(e) : 1; }
+    return v != 0 || tv.nodes == nullptr;
+}
+
+template <int MODE, bool CAMERA, bool COUNT, bool WIDE>
 int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
                  const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
 {
@@ -655,7 +679,7 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     int blocksPerSM = occ[dev].load(std::memory_order_relaxed);
     if (!blocksPerSM)
     {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT, WIDE>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
         occ[dev].store(blocksPerSM, std::memory_order_relaxed);
     }
     u32 height = width ? (u32)((n + width - 1) / width) : 0;
@@ -674,7 +698,7 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
         BM_CUDA(cudaMemsetAsync(ts.state, 0, TS_OK * 4, s));          // histogram + cursors; OK flag and entry count of the previous launch stay
         BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
     }
-    trace_kernel<MODE, CAMERA, COUNT><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
+    trace_kernel<MODE, CAMERA, COUNT, WIDE><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
                                                                             d_counters, d_workCounter, leaf_break(), leaf_wait(), refill, ts);
     BM_LAUNCHED();
     if (ts.cost)
@@ -687,15 +711,23 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     return BM_OK;
 }
 
+template <bool CAMERA, bool WIDE>
+int dispatch_trace2(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, int mode, bmHit* d_hits, u32* d_pixels,
+                    const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
+{
+    if (mode == BM_TRACE_REFERENCE)
+        return d_counters ? launch_trace<BM_TRACE_REFERENCE, CAMERA, true, WIDE>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s)
+                          : launch_trace<BM_TRACE_REFERENCE, CAMERA, false, WIDE>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
+    return d_counters ? launch_trace<BM_TRACE_CLOSEST, CAMERA, true, WIDE>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s)
+                      : launch_trace<BM_TRACE_CLOSEST, CAMERA, false, WIDE>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
+}
+
 template <bool CAMERA>
 int dispatch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, int mode, bmHit* d_hits, u32* d_pixels,
                    const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
 {
-    if (mode == BM_TRACE_REFERENCE)
-        return d_counters ? launch_trace<BM_TRACE_REFERENCE, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s)
-                          : launch_trace<BM_TRACE_REFERENCE, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
-    return d_counters ? launch_trace<BM_TRACE_CLOSEST, CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s)
-                      : launch_trace<BM_TRACE_CLOSEST, CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
+    if (use_wide(tv)) return dispatch_trace2<CAMERA, true>(tv, d_rays, cam, n, d_numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
+    return dispatch_trace2<CAMERA, false>(tv, d_rays, cam, n, d_numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
 }
 } // namespace
 

@@ -81,7 +81,7 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false, imported = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState;
     u32 schedTiles = 0;              // frame size (in 8x4 tiles) the tile-scheduling buffers are set up for; 0 = none
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
@@ -91,13 +91,23 @@ struct bmTree
     TreeView view() const
     {
         TreeView v;
-        v.nodes = nodes.as<float4>(); v.leaves = leaves.as<float4>(); v.ltris = ltris.as<float4>(); v.clusters = clusters.as<float4>();
+        v.nodes = nodes.as<float4>(); v.wnodes = wnodes.as<uint4>(); v.leaves = leaves.as<float4>(); v.ltris = ltris.as<float4>(); v.clusters = clusters.as<float4>();
         v.numLeaves = (u32)L; v.root = rootDev.as<u32>();
+        v.grid = dgrid;
+        // reach of a leaf cell beyond the (padded) boxes of the triangles it holds: the largest cell extent per axis, with a margin for the
+        // float slab arithmetic of the cell tests
+        for (int a = 0; a < 3; a++)
+        {
+            float m = 0.f;
+            const std::vector<float>& tb = hgrid.tab[a];
+            for (size_t i = 0; i + 1 < tb.size(); i++) m = fmaxf(m, tb[i + 1] - tb[i]);
+            v.leafExt[a] = m * 1.0001f + (hgrid.wmax[a] - hgrid.wmin[a]) * (1.f / 262144.f);
+        }
         return v;
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &wnodes, &nodeMeta, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -218,9 +228,10 @@ static int tree_build(bmTree* t)
     if (L >= 2)
     {
         BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4)); BM_TRY(t->nodeBox.reserve((L - 1) * 32));
+        BM_TRY(t->wnodes.reserve((L - 1) * 64)); BM_TRY(t->nodeMeta.reserve((L - 1) * 8));
         BM_TRY(t->parentN.reserve((L - 1) * 8)); BM_TRY(t->visit.reserve((L - 1) * 4));
         BM_TRY(build_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->visit.as<int>(), t->parentN.as<u32>(),
-                               t->nodes.as<float4>(), t->rootDev.as<u32>(), s));
+                               t->nodes.as<float4>(), t->wnodes.as<uint4>(), t->nodeMeta.as<uint2>(), t->rootDev.as<u32>(), s));
     }
     tm.mark("hierarchy");
     t->built = true;

@@ -218,7 +218,8 @@ def test_progressive_frame(oracle_lib, beam_lib, cuda_device):
     want = np.where(cov_np, (g << 16) | (g << 8) | g, np.uint32(255 << 8)).astype(np.uint32)
     assert np.array_equal(got, want)
     assert np.array_equal(frame, got) and rays_traced == total
-    assert cov_np.sum() > 1000 and 0.5 < (acc_np[cov_np] > 0.3 * SPP).mean() < 1
+    # ambient occlusion of a displaced sphere: most bounce rays escape (pixels well above the ambient-only 0.25), some are occluded
+    assert cov_np.sum() > 1000 and (acc_np[cov_np] > 0.3 * SPP).mean() > 0.5 and (acc_np[cov_np] < SPP - 0.5).any()
     assert rt.unlock() == 0
     t.close(); s.close()
 

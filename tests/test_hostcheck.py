@@ -29,6 +29,8 @@ def hc():
     H.hc_decode.argtypes = [C.c_int, C.c_uint32, u32p]
     H.hc_box_ray.argtypes = [f32p] * 4; H.hc_box_ray.restype = C.c_float
     H.hc_tri_intersect.argtypes = [f32p] * 5 + [C.POINTER(C.c_float)] * 2; H.hc_tri_intersect.restype = C.c_float
+    H.hc_wide_trace.argtypes = [f32p, u32p, C.c_uint32, f32p, f32p, C.c_float, C.c_uint32, C.c_uint32, f32p, C.c_uint64, C.c_int, u32p, f32p,
+                                np.ctypeslib.ndpointer(np.uint64, flags="C")]
     H.hc_hash.argtypes = [C.c_uint32]; H.hc_hash.restype = C.c_uint32
     H.hc_map.argtypes = [C.c_float]; H.hc_map.restype = C.c_int32
     return H
@@ -165,3 +167,72 @@ def test_hash_keys(hc, golden):
         assert hc.hc_hash(k) == want
     for x, want in golden["hash"]["bmMap"]:
         assert hc.hc_map(x) == want
+
+
+def _wide_vs_oracle(hc, oracle_lib, P, I, N, rays, what, max_faces=256, wmin=(-30, -30, -30), wmax=(30, 30, 30), exact=True, modes=(0, 1)):
+    """complete traversals through the product's 64-byte wide records (encoder + traversal step of csrc/bm_wide.cuh, compiled for the CPU)
+    against the oracle: same winner and bit-equal t in both trace modes, and every decoded slot box encloses the exact one"""
+    P = np.ascontiguousarray(P, np.float32); Iflat = np.ascontiguousarray(I, np.uint32).reshape(-1); rays = np.ascontiguousarray(rays, np.float32)
+    s = OracleScene(oracle_lib, wmin=wmin, wmax=wmax, max_faces=max_faces); s.add_mesh(P, Iflat.reshape(-1, 3), N); s.build()
+    out = {}
+    for mode in modes:
+        tri = np.zeros(rays.shape[0], np.uint32); t = np.zeros(rays.shape[0], np.float32); st = np.zeros(4, np.uint64)
+        assert hc.hc_wide_trace(P, Iflat, Iflat.size // 3, np.array(wmin, np.float32), np.array(wmax, np.float32), 0.03, 38, max_faces, rays, rays.shape[0], mode, tri, t, st) == 0
+        r = s.trace_rays(rays[:, :3], rays[:, 3:], mode, 4)
+        ok = r["tie"] == 0
+        agree = (tri[ok] == r["tri"][ok]).mean()
+        assert agree == 1.0 if exact else agree >= 0.9999, (what, mode, agree)
+        both = ok & (tri == r["tri"]) & (tri != 0xFFFFFFFF)
+        assert np.array_equal(t[both], r["t"][both]), (what, mode)
+        assert st[2] == 0, "decoded culling boxes must enclose the exact ones"
+        out[mode] = (st[0] / rays.shape[0], r["node_visits"] / rays.shape[0], int(st[3]))
+    s.close()
+    return out
+
+
+def _rays_from(eye, dirs):
+    return np.concatenate([np.tile(np.asarray(eye, np.float32), (dirs.shape[0], 1)), dirs], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["f16", "suzanne", "bunny"])
+def test_wide_nodes_trace_like_the_oracle_on_meshes(name, hc, meshes, oracle_lib):
+    from raytracercuda_b200 import synth
+    P, I, N = meshes[name]
+    v = _wide_vs_oracle(hc, oracle_lib, P, I, N, _rays_from([0, 0, -2.1], oracle_lib.initial_rays(96, 96)), name + " camera")
+    assert v[0][0] < 0.25 * v[0][1]                    # a fraction of the reference's node visits
+    _wide_vs_oracle(hc, oracle_lib, P, I, N, synth.incoherent_rays(6000, extent=1.5), name + " incoherent")
+    assert v[0][2] == 0 and v[1][2] == 0               # no axis had to fall back to "unbounded"
+
+
+def test_wide_nodes_trace_like_the_oracle_on_soups(hc, oracle_lib):
+    from raytracercuda_b200 import synth
+    P, I = synth.soup(20000, extent=3.0, edge=0.05)
+    _wide_vs_oracle(hc, oracle_lib, P, I, None, synth.incoherent_rays(12000, extent=3.2), "soup")
+    # axis-parallel rays, in-plane rays, origins exactly on cell boundaries (the NaN / inf corners of the reference's slab test)
+    rng = np.random.default_rng(4)
+    n = 4000
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    o[::3, 0] = np.round(o[::3, 0] / 0.029296875) * 0.029296875; o[1::5, 1] = 0
+    d = np.zeros((n, 3), np.float32); d[np.arange(n), rng.integers(0, 3, n)] = rng.choice([-1, 1], n)
+    m = d[::7].shape[0]
+    d[::7] = rng.normal(size=(m, 3)); d[::7, 2] = 0; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    _wide_vs_oracle(hc, oracle_lib, P, I, None, np.concatenate([o, d], 1), "soup, degenerate rays")
+    # triangles far larger than the cells (quantisation grids anchored at the world box)
+    P, I = synth.soup(600, extent=22.0, edge=3.5)
+    _wide_vs_oracle(hc, oracle_lib, P, I, None, synth.incoherent_rays(4000, extent=29), "big triangles")
+    # ... some sticking out of the world box: the reference's semantics only know the part inside (a closest hit outside the world has no
+    # leaf cell to be found in), so only the reference mode is compared exactly there
+    P, I = synth.soup(600, extent=28.0, edge=3.5)
+    _wide_vs_oracle(hc, oracle_lib, P, I, None, synth.incoherent_rays(4000, extent=29), "big triangles across the world box", modes=(0,))
+    # leaves above the reference's face cap, a non-default world, and the table (non-closed-form) grid
+    c = rng.uniform(-0.05, 0.05, (1200, 1, 3)).astype(np.float32)
+    dense = np.ascontiguousarray((c + rng.uniform(-0.02, 0.02, (1200, 3, 3)).astype(np.float32)).reshape(-1, 3))
+    _wide_vs_oracle(hc, oracle_lib, dense, np.arange(3600, dtype=np.uint32), None, synth.incoherent_rays(4000, extent=0.3), "dense, capped leaves", max_faces=64, modes=(0,))      # (closest mode is defined without the cap)
+    P, I = synth.soup(5000, extent=2.5, edge=0.05)
+    _wide_vs_oracle(hc, oracle_lib, P + np.float32(1.0), I, None, synth.incoherent_rays(5000, extent=2.5) + np.array([1, 1, 1, 0, 0, 0], np.float32), "other world",
+                    wmin=(-3.1, -2.7, -2.2), wmax=(4.9, 5.3, 5.8))
+    os.environ["HC_NO_UNIFORM"] = "1"
+    try:
+        _wide_vs_oracle(hc, oracle_lib, P, I, None, synth.incoherent_rays(3000, extent=2.5), "table grid")
+    finally:
+        del os.environ["HC_NO_UNIFORM"]
