@@ -163,7 +163,7 @@ void bmTreeDestroy(bmTree* tree);
 int  bmTreeSetStream(bmTree* tree, void* cudaStream);          /* cudaStream_t; default 0 */
 int  bmTreeReset(bmTree* tree);                                /* forget staged meshes (bmResetScene) */
 int  bmTreeAddMesh(bmTree* tree, const float* d_positions, const uint32_t* d_indices, uint32_t numIndices, uint32_t meshIdx);
-/* keys -> sort -> leaves -> one bottom-up pass (radix tree + tight boxes) -> 128-byte nodes. Asynchronous on the tree's stream except for two
+/* keys -> sort -> leaves -> one bottom-up pass (radix tree + tight boxes) -> node records (see bmTreeNodeLayout). Asynchronous on the tree's stream except for two
  * 8-byte read-backs (pair and leaf counts) that size the later stages. */
 int  bmTreeBuild(bmTree* tree);
 int  bmBuildTree(void* treeRootNode);                          /* same, for a tree made through Part 1 */
@@ -190,7 +190,21 @@ int  bmTreeArraySizes(const bmTree* tree, uint64_t* sizes8);
 int  bmTreeExport(const bmTree* tree, void* d_nodes, void* d_leaves, void* d_ltris, void* d_clusters, void* d_soup);
 int  bmTreeRoot(const bmTree* tree, uint32_t* root);           /* reference of the root: node index, or 0x80000000 | 0 when the only leaf is the root */
 int  bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
-                  uint64_t numLeaves, uint64_t numPairs, uint64_t numTris, uint32_t root);
+                  uint64_t numLeaves, uint64_t numPairs, uint64_t numTris, uint32_t root, uint32_t nodeLayout,
+                  const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth);   /* layout + world of the source: bmTreeNodeLayout, bmTreeWorld */
+/* Node records of a built tree.  BM_NODES_BINARY: 128 bytes per internal node of the binary radix tree (two child boxes, child references,
+ * the reference node's cell box / split plane / axis precomputed); chosen while the node array stays cache-resident, where traversal is
+ * issue-bound.  BM_NODES_WIDE: 64 bytes, 64-byte aligned, per internal node: the node and its two children collapsed into a 4-wide record --
+ * integer cell coordinates of the three kd nodes (their boxes and planes are rebuilt exactly in the kernel) + four slot references + four
+ * culling boxes quantised to 8 bits per coordinate, rounded outwards (raytracercuda_b200/csrc/bm_wide.cuh); chosen for trees beyond the
+ * L2, where traversal is bound by memory round trips and bytes.  BM_NODE_LAYOUT=binary|wide|both and BM_WIDE_MIN_MB override the choice.
+ * Results do not depend on the layout. */
+enum { BM_NODES_BINARY = 0, BM_NODES_WIDE = 1, BM_NODES_BOTH = 2 };
+int  bmTreeNodeLayout(const bmTree* tree, uint32_t* layout);
+int  bmTreeWorld(const bmTree* tree, float* worldMin3, float* worldMax3, float* minLeafSize, uint32_t* maxDepth);   /* any pointer may be null */
+/* Parity aid for the wide records: the decoded culling boxes (24 floats per node: lo.xyz, hi.xyz of slots 0..3) and the slot references
+ * (4 per node; bit 31 = leaf, 0x7FFFFFFF = empty) into caller-provided DEVICE buffers. */
+int  bmTreeCopyWideSlots(const bmTree* tree, float* d_boxes24, uint32_t* d_refs4);
 /* A second, read-only handle on the arrays of a built tree (no copy) with its own stream (bmTreeSetStream), work counter and bounce
  * scratch: launches issued through different views of one tree may run concurrently, e.g. the two halves of a frame on two streams so
  * that the tail of one half's traversal is filled by the other half's work.  Valid until `tree` is rebuilt or destroyed. */

@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get("BEAM_B200_LIB") or os.path.join(HERE, "libbeam_b200.s
 BM_OK = 0
 BM_TRACE_REFERENCE = 0
 BM_TRACE_CLOSEST = 1
+BM_NODES_BINARY, BM_NODES_WIDE, BM_NODES_BOTH = 0, 1, 2
 ERROR_NAMES = {0: "ERROR_ALL_FINE", 1: "ERROR_NO_VERTICES", 2: "ERROR_INVALID_PARAMETER", 3: "ERROR_GPU_ALLOC_FAIL", 4: "ERROR_INVALID_FORMAT",
                5: "ERROR_RT_CAM_MISMATCH", 6: "ERROR_UNLOCK_FIRST", 7: "ERROR_LOCK_FIRST", 8: "ERROR_NO_RENDER_TARGET",
                100: "BM_ERROR_CUDA", 101: "BM_ERROR_UNSUPPORTED_WORLD", 102: "BM_ERROR_NOT_BUILT", 103: "BM_ERROR_CAPACITY"}
@@ -22,7 +23,7 @@ ABI_SYMBOLS = [
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmStickyError", "bmStickyErrorString", "bmClearStickyError", "bmReleaseScene", "bmSetPart1Stream",
     "bmTraceCameraJittered", "bmBounceRaysCameraJittered", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
-    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView", "bmTreeNodeLayout", "bmTreeWorld", "bmTreeCopyWideSlots",
     "bmTraceRays", "bmTraceRaysTiled", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
@@ -90,7 +91,10 @@ def load() -> C.CDLL:
     L.bmTreeMeshBases.argtypes = [vp, C.POINTER(u32), u32]
     L.bmTreeArraySizes.argtypes = [vp, C.POINTER(u64)]
     L.bmTreeExport.argtypes = [vp, vp, vp, vp, vp, vp]
-    L.bmTreeImport.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, u64, u64, u64, u32]
+    L.bmTreeImport.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, u64, u64, u64, u32, u32, vp, vp, C.c_float, u32]
+    L.bmTreeNodeLayout.argtypes = [vp, C.POINTER(u32)]
+    L.bmTreeWorld.argtypes = [vp, vp, vp, C.POINTER(C.c_float), C.POINTER(u32)]
+    L.bmTreeCopyWideSlots.argtypes = [vp, vp, vp]
     L.bmTreeRoot.argtypes = [vp, C.POINTER(u32)]
     L.bmTreeView.argtypes = [vp, C.POINTER(vp)]
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]

@@ -101,6 +101,9 @@ int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* 
 // d_nodes (nullable): the 128-byte binary records; d_wnodes: the 64-byte wide records (bm_wide.cuh); d_nodeMeta: scratch, 8 bytes per node
 int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
                     float4* d_nodes, uint4* d_wnodes, uint2* d_nodeMeta, u32* d_root, cudaStream_t s);
+int copy_topology(const Grid& g, const u32* d_childRefs, const uint2* d_nodeMeta, u32 numNodes, u32* d_prefixLen, u32* d_prefix, u32* d_child0, u32* d_child1, cudaStream_t s);
+int copy_child_boxes(const u32* d_childRefs, const float4* d_leafBox2, const float4* d_nodeBox2, u32 numNodes, float* d_boxes12, cudaStream_t s);
+int copy_wide_slots(const Grid& g, const uint4* d_wnodes, u32 numNodes, float* d_boxes24, u32* d_refs4, cudaStream_t s);
 int canonical_keys(const u64* d_keys, const u32* d_vals, size_t n, int subBits, u64* d_out, cudaStream_t s);
 int split_canonical(const u64* d_keys, size_t n, u32* d_code, u32* d_tri, cudaStream_t s);
 

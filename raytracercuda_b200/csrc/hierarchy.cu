@@ -221,6 +221,8 @@ __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 nu
         {
             // the wide record: children that are internal nodes are absorbed (their own children become this record's slots)
             const u32 cell0 = wide_pack_cell(g, ix, iy, iz);
+            if (wnodes)
+            {
             u32 ref[4] = { c0, WREF_EMPTY, c1, WREF_EMPTY };
             WSlotBox box[4];
             box[0] = slot_box(b0); box[2] = slot_box(b1); box[1] = box[0]; box[3] = box[2];
@@ -242,6 +244,7 @@ __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 nu
             uint4* wp = wnodes + WNODE_U4 * (size_t)parent;
 #pragma unroll
             for (int k = 0; k < 4; k++) wp[k] = make_uint4(rec[k].x, rec[k].y, rec[k].z, rec[k].w);
+            }
             __stcg(&nodeMeta[parent], make_uint2(cell0, (u32)plen));
         }
         if (l == 0 && r == n - 1) { *rootOut = (u32)parent; return; }
@@ -250,6 +253,52 @@ __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 nu
         __stcg(o + 1, make_float4(fmaxf(b0.b.x, b1.b.x), fmaxf(b0.b.y, b1.b.y), 0.f, 0.f));
         cur = (u32)parent;
     }
+}
+
+__global__ void copy_topology_kernel(Grid g, const u32* __restrict__ childRefs, const uint2* __restrict__ meta, u32 n, u32* __restrict__ plen, u32* __restrict__ prefix,
+                                     u32* __restrict__ c0, u32* __restrict__ c1)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 m = meta[i];
+    if (plen) plen[i] = m.y;
+    if (prefix) { u32 ix, iy, iz; wide_unpack_cell(g, m.x, ix, iy, iz); prefix[i] = m.y ? encode_path((int)m.y, ix, iy, iz) : 0u; }
+    if (c0) c0[i] = childRefs[2 * (size_t)i];
+    if (c1) c1[i] = childRefs[2 * (size_t)i + 1];
+}
+
+__global__ void copy_child_boxes_kernel(const u32* __restrict__ childRefs, const float4* __restrict__ leafBox, const float4* __restrict__ nodeBox, u32 n, float* __restrict__ out)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+        u32 c = childRefs[2 * (size_t)i + h];
+        const float4* p = (c & LEAF_BIT) ? leafBox + 2 * (size_t)(c & ~LEAF_BIT) : nodeBox + 2 * (size_t)c;
+        float4 a = p[0], b = p[1];
+        float* o = out + 12 * (size_t)i + 6 * h;
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
+    }
+}
+
+__global__ void copy_wide_slots_kernel(Grid g, const uint4* __restrict__ wnodes, u32 n, float* __restrict__ boxes, u32* __restrict__ refs)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = wnodes + WNODE_U4 * (size_t)i;
+    uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    WCell c0 = wide_cell(g, q0.x, (int)(q0.w & 0xFFu));
+    WFrame f = wide_frame(g, c0.mn, c0.mx, q3.z, q3.w, q0.w >> 24);
+    const u32 LW[3] = { q2.x, q2.y, q2.z }, HW[3] = { q2.w, q3.x, q3.y };
+    if (refs) { refs[4 * (size_t)i] = q1.x; refs[4 * (size_t)i + 1] = q1.y; refs[4 * (size_t)i + 2] = q1.z; refs[4 * (size_t)i + 3] = q1.w; }
+    if (boxes)
+        for (int s = 0; s < 4; s++)
+            for (int a = 0; a < 3; a++)
+            {
+                boxes[24 * (size_t)i + 6 * s + a] = wide_fma(wide_magic(LW[a], s), f.step[a], f.addLo[a]);
+                boxes[24 * (size_t)i + 6 * s + 3 + a] = wide_fma(wide_magic(HW[a], s), f.step[a], f.addHi[a]);
+            }
 }
 
 // (code << subBits | sub, tri)  ->  (code << 32 | tri): the key whose order is the canonical (code, triangle) order
@@ -307,6 +356,27 @@ int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const floa
     if (numLeaves < 2) return BM_OK;
     BM_CUDA(cudaMemsetAsync(d_otherBound, 0xFF, (size_t)(numLeaves - 1) * 4, s));
     agglomerate_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_otherBound, d_childRefs, d_nodes, d_wnodes, d_nodeMeta, d_root);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+int copy_topology(const Grid& g, const u32* d_childRefs, const uint2* d_nodeMeta, u32 numNodes, u32* d_prefixLen, u32* d_prefix, u32* d_child0, u32* d_child1, cudaStream_t s)
+{
+    if (!numNodes) return BM_OK;
+    copy_topology_kernel<<<div_up(numNodes, 256), 256, 0, s>>>(g, d_childRefs, d_nodeMeta, numNodes, d_prefixLen, d_prefix, d_child0, d_child1);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+int copy_child_boxes(const u32* d_childRefs, const float4* d_leafBox2, const float4* d_nodeBox2, u32 numNodes, float* d_boxes12, cudaStream_t s)
+{
+    if (!numNodes) return BM_OK;
+    copy_child_boxes_kernel<<<div_up(numNodes, 256), 256, 0, s>>>(d_childRefs, d_leafBox2, d_nodeBox2, numNodes, d_boxes12);
+    BM_LAUNCHED();
+    return BM_OK;
+}
+int copy_wide_slots(const Grid& g, const uint4* d_wnodes, u32 numNodes, float* d_boxes24, u32* d_refs4, cudaStream_t s)
+{
+    if (!numNodes) return BM_OK;
+    copy_wide_slots_kernel<<<div_up(numNodes, 256), 256, 0, s>>>(g, d_wnodes, numNodes, d_boxes24, d_refs4);
     BM_LAUNCHED();
     return BM_OK;
 }

@@ -21,6 +21,7 @@ constexpr int TR_THREADS = 128;
 constexpr int TR_STACK = 52;     // binary walk: depth <= D <= 32; wide walk: a visit pops one entry and pushes up to four, <= 16 wide levels
 constexpr int COOP_MAX_LANES = 8;   // at most this many pending leaves in a warp -> process the sizeable ones warp-cooperatively
 constexpr int COOP_MIN_FACES = 8;   // ... where sizeable = more than this many faces
+constexpr int TR_QUEUE_MAX = 8;      // leaves a lane of a ray batch may postpone (queueDepth <= this)
 constexpr u32 REF_EMPTY = 0x7FFFFFFFu;   // "nothing left to visit" (never a valid internal index: N < 2^31 - 1)
 
 struct HitRec { float t, u, v; u32 tri, mesh, face; };
@@ -387,15 +388,16 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
 template <int MODE, bool CAMERA, bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
-                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int leafWait, int refillMin, TileSched sched)
+                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int leafWait, int refillMin, int queueDepth, TileSched sched)
 {
     const u32 rootRef = tv.numLeaves >= 2 ? __ldg(tv.root) : (tv.numLeaves == 1 ? (0u | LEAF_BIT) : REF_EMPTY);
     if (numRaysDev) { n = __ldg(numRaysDev); totalSlots = (u32)n; }       // count produced on the device (bmBounceRays): no host round trip
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
+    __shared__ u32 pendS[CAMERA ? 1 : TR_QUEUE_MAX][TR_THREADS];      // postponed leaves of ray batches, [entry][thread]
     u32 stack[TR_STACK];
     int top = -1;
-    u32 cur = REF_EMPTY;
+    u32 cur = REF_EMPTY, npend = 0;
     bool active = false, exhausted = false;
     u64 rayIdx = 0;
     V3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), inv = mk3(0, 0, 1), ic = mk3(0, 0, 1), oi = mk3(0, 0, 0), fm = mk3(0, 0, 0);
@@ -469,20 +471,36 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
         }
         if (!__any_sync(FULL, active)) break;
 
-        // ---- phase 1: internal nodes, until no lane has one pending ----------------------------------------------------------
-        int waited = 0;                                    // node steps taken while at least leafBreak lanes were waiting at a leaf
+        // ---- phase 1: internal nodes ----------------------------------------------------------------------------------------------
+        // Ray batches carry a small queue of POSTPONED leaves per lane (queueDepth entries in shared memory): a lane that reaches a leaf
+        // notes it and walks on as if the leaf held no hit, and the noted leaves are tested together in phase 2, in the order they were
+        // met.  Incoherent rays reach their leaves at very different times: with lanes waiting AT their leaf, the node walk of a
+        // 20 M-triangle soup ran at 13 of 32 lanes (profiles/r2a).  Walking on is exact: what the traversal does after a leaf depends on
+        // the leaf only through "stop here" (reference mode: the first leaf with a hit ends the ray, so at worst the nodes visited past it
+        // were visited for nothing -- one leaf in ~15 of such a batch has a hit) or through the shrinking [0, best t] (closest mode: the
+        // cull lags by the queue).  queueDepth = 0 (camera launches: coherent tiles arrive at their leaves together) is the lane-waits rule.
+        int waited = 0;                                    // steps taken while at least leafBreak lanes could not move
         for (;;)
         {
-            bool inner = active && cur != REF_EMPTY && !(cur & LEAF_BIT);
-            if (!__any_sync(FULL, inner)) break;
-            // ray batches (bounce / incoherent rays): once enough lanes wait at a leaf, serve them instead of idling them until the last
-            // lane arrives -- such rays reach their leaves at very different times (a soup batch ran at 7 of 32 lanes, profiles/r1_c5).
-            // Measured: threshold 16 gives +6 % (reference) / +24 % (closest) on the soup; camera launches (coherent 8x4 tiles) are
-            // 4 % faster without the rule, so they skip it.  Coherent BATCHES (jittered camera rays of the multi-sample frames) lose 10 %
-            // if the break is immediate -- their stragglers are only a step or two behind -- so the waiting lanes first sit out
-            // LEAF_WAIT node steps.
-            if (!CAMERA && __popc(__ballot_sync(FULL, active && cur != REF_EMPTY && (cur & LEAF_BIT))) >= leafBreak && ++waited > leafWait) break;
-            if (inner)
+            const bool hasCur = active && cur != REF_EMPTY;
+            const bool inner = hasCur && !(cur & LEAF_BIT);
+            const bool canq = !CAMERA && hasCur && (cur & LEAF_BIT) && npend < (u32)queueDepth;
+            if (!__any_sync(FULL, inner || canq)) break;
+            if (!CAMERA)
+            {
+                // lanes that cannot move before the leaf phase: at a leaf with a full queue, or out of nodes with leaves still noted;
+                // lanes that are finished (or empty) and could take a new ray
+                const unsigned stalled = __ballot_sync(FULL, active && !inner && !canq && (hasCur || npend > 0u));
+                const unsigned spare = __ballot_sync(FULL, !active || (!hasCur && npend == 0u));
+                if (__popc(stalled) >= leafBreak && ++waited > leafWait) break;
+                if (queueDepth && !exhausted && __popc(spare) >= refillMin) break;
+            }
+            if (canq)
+            {
+                pendS[npend][threadIdx.x] = cur; npend++;
+                cur = top >= 0 ? stack[top--] : REF_EMPTY;
+            }
+            else if (inner)
             {
                 if (COUNT) nv++;
                 if (WIDE) wide_node<MODE>(tv, cur, o, d, inv, ic, oi, fm, best.t, stack, top);
@@ -492,17 +510,22 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
             }
         }
 
-        // ---- phase 2: one pending leaf per lane ---------------------------------------------------------------------------------
+        // ---- phase 2: the noted leaves of every lane, then the leaf it stands at --------------------------------------------------------
         // stage A: every lane scans the cluster boxes of its leaf (groups of CLUSTER faces) and keeps a bit mask of the groups the
         // ray's line meets; stage B: lanes pop one group at a time and test its faces in lock step.  Both loops are warp-uniform.
         bool finished = false;
+        const bool curLeaf = active && cur != REF_EMPTY && (cur & LEAF_BIT);
+        const u32 nleaf = active ? npend + (curLeaf ? 1u : 0u) : 0u;
+        const u32 rounds = __reduce_max_sync(FULL, nleaf);
+        for (u32 round = 0; round < rounds; round++)
         {
-            bool isLeaf = active && cur != REF_EMPTY && (cur & LEAF_BIT);
+            const bool isLeaf = !finished && round < nleaf;
+            const u32 lref = (!CAMERA && round < npend) ? pendS[round][threadIdx.x] : cur;
             u32 first = 0, cnt = 0, cfirst = 0;
             if (isLeaf)
             {
                 if (COUNT) nv++;
-                const float4* lp = tv.leaves + LEAF_F4 * (size_t)(cur & ~LEAF_BIT);
+                const float4* lp = tv.leaves + LEAF_F4 * (size_t)(lref & ~LEAF_BIT);
                 float4 r0 = __ldg(lp), r1 = __ldg(lp + 1), r2 = __ldg(lp + 2);
                 first = __float_as_uint(r0.y); cfirst = __float_as_uint(r0.w);
                 if (MODE == BM_TRACE_REFERENCE)
@@ -583,12 +606,10 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     }
                 }
             }
-            if (isLeaf)
-            {
-                if (MODE == BM_TRACE_REFERENCE && best.t != FLT_MAX) finished = true;              // :427-431
-                else cur = top >= 0 ? stack[top--] : REF_EMPTY;
-            }
+            if (isLeaf && MODE == BM_TRACE_REFERENCE && best.t != FLT_MAX) finished = true;          // :427-431: the first leaf with a hit ends the ray
         }
+        if (curLeaf && !finished) cur = top >= 0 ? stack[top--] : REF_EMPTY;
+        npend = 0;
 
         // ---- retire ------------------------------------------------------------------------------------------------------------
         if (active && (finished || cur == REF_EMPTY))
@@ -628,19 +649,28 @@ __global__ void hash_kernel(const float* __restrict__ pts, u64 n, u32* __restric
     if (hash) hash[i] = hash3((u32)cx, (u32)cy, (u32)cz);
 }
 
-// phase 1 hands over to phase 2 once this many lanes of a warp wait at a leaf (BM_LEAF_BREAK overrides, for tuning)
-int leaf_break()
+// leaves a lane of a ray batch postpones before it has to wait for the leaf phase (BM_LEAF_QUEUE overrides, 0 = wait at the first leaf)
+int queue_depth()
 {
-    static int v = 0;
-    if (!v) { const char* e = getenv("BM_LEAF_BREAK"); v = e ? atoi(e) : 16; if (v < 1) v = 1; if (v > 33) v = 33; }
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BM_LEAF_QUEUE"); v = e ? atoi(e) : 4; if (v < 0) v = 0; if (v > TR_QUEUE_MAX) v = TR_QUEUE_MAX; }
     return v;
 }
 
-int leaf_wait()
+// phase 1 hands over to phase 2 once this many lanes of a warp cannot move (BM_LEAF_BREAK overrides, for tuning): with lanes waiting at
+// their first leaf (queue depth 0) half the warp, with a leaf queue a quarter
+int leaf_break(int queueDepth)
 {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("BM_LEAF_WAIT"); v = e ? atoi(e) : 6; if (v < 0) v = 0; }
-    return v;
+    static int v = 0;
+    if (!v) { const char* e = getenv("BM_LEAF_BREAK"); v = e ? atoi(e) : -1; if (v == 0) v = 1; if (v > 33) v = 33; }
+    return v > 0 ? v : (queueDepth ? 8 : 16);
+}
+
+int leaf_wait(int queueDepth)
+{
+    static int v = -2;
+    if (v == -2) { const char* e = getenv("BM_LEAF_WAIT"); v = e ? atoi(e) : -1; }
+    return v >= 0 ? v : (queueDepth ? 2 : 6);
 }
 
 // A warp refills only when this many of its lanes are idle.  Measured: camera launches are 5 % faster at 32 (a warp finishes its whole
@@ -662,12 +692,13 @@ int refill_min(bool camera)
     return v > 0 ? v : (camera ? 32 : 8);
 }
 
-// node layout walked by the trace kernels: the 64-byte wide records unless BM_WIDE=0 asks for the binary records of a tree that has them
+// node records walked by the trace kernels (bmTreeNodeLayout)
 bool use_wide(const TreeView& tv)
 {
-    static int v = -1;
+    if (!tv.nodes || !tv.wnodes) return tv.wnodes != nullptr;      // the tree holds one kind of record
+    static int v = -1;                                              // BM_NODE_LAYOUT=both: BM_WIDE=0 walks the binary records (A/B runs)
     if (v < 0) { const char* e = getenv("BM_WIDE"); v = e ? atoi(e) : 1; }
-    return v != 0 || tv.nodes == nullptr;
+    return v != 0;
 }
 
 template <int MODE, bool CAMERA, bool COUNT, bool WIDE>
@@ -699,7 +730,7 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
         BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
     }
     trace_kernel<MODE, CAMERA, COUNT, WIDE><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
-                                                                            d_counters, d_workCounter, leaf_break(), leaf_wait(), refill, ts);
+                                                                            d_counters, d_workCounter, leaf_break(CAMERA ? 0 : queue_depth()), leaf_wait(CAMERA ? 0 : queue_depth()), refill, CAMERA ? 0 : queue_depth(), ts);
     BM_LAUNCHED();
     if (ts.cost)
     {

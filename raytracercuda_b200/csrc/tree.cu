@@ -58,7 +58,11 @@ struct DevBuf
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { p = nullptr; set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return BM_ERROR_GPU_ALLOC_FAIL; }
+        if (e != cudaSuccess)
+        {
+            cudaGetLastError();               // the failed allocation must not resurface as the "last error" of the next launch
+            p = nullptr; set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return BM_ERROR_GPU_ALLOC_FAIL;
+        }
         cap = want;
         return BM_OK;
     }
@@ -82,6 +86,7 @@ struct bmTree
     bool built = false, imported = false;
     // build products
     DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState;
+    int layout = BM_NODES_BINARY;    // which node records the last build wrote (BM_NODES_*; set by tree_build, or by bmTreeImport)
     u32 schedTiles = 0;              // frame size (in 8x4 tiles) the tile-scheduling buffers are set up for; 0 = none
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
@@ -91,7 +96,7 @@ struct bmTree
     TreeView view() const
     {
         TreeView v;
-        v.nodes = nodes.as<float4>(); v.wnodes = wnodes.as<uint4>(); v.leaves = leaves.as<float4>(); v.ltris = ltris.as<float4>(); v.clusters = clusters.as<float4>();
+        v.nodes = layout != BM_NODES_WIDE ? nodes.as<float4>() : nullptr; v.wnodes = layout != BM_NODES_BINARY ? wnodes.as<uint4>() : nullptr; v.leaves = leaves.as<float4>(); v.ltris = ltris.as<float4>(); v.clusters = clusters.as<float4>();
         v.numLeaves = (u32)L; v.root = rootDev.as<u32>();
         v.grid = dgrid;
         // reach of a leaf cell beyond the (padded) boxes of the triangles it holds: the largest cell extent per axis, with a margin for the
@@ -227,11 +232,25 @@ static int tree_build(bmTree* t)
     // 5. hierarchy and tight boxes, one bottom-up pass
     if (L >= 2)
     {
-        BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4)); BM_TRY(t->nodeBox.reserve((L - 1) * 32));
-        BM_TRY(t->wnodes.reserve((L - 1) * 64)); BM_TRY(t->nodeMeta.reserve((L - 1) * 8));
+        // Node records: the uncompressed 128-byte binary record while the node array stays cache-resident (a visit costs ~100 instructions and
+        // such scenes are issue-bound: c2 traces 27 % slower through the wide records), the compressed 64-byte wide record beyond that (a
+        // visit costs ~3x the instructions but half the memory round trips and a third of the bytes: +46 % on a 20 M-triangle soup).
+        // BM_NODE_LAYOUT = binary | wide | both overrides; BM_WIDE_MIN_MB moves the threshold (default 48 MB of binary records).
+        {
+            const char* lay = getenv("BM_NODE_LAYOUT"); const char* mb = getenv("BM_WIDE_MIN_MB");
+            double thr = (mb ? atof(mb) : 48.0) * 1048576.0;
+            t->layout = (double)(L - 1) * 128.0 > thr ? BM_NODES_WIDE : BM_NODES_BINARY;
+            if (lay && !strcmp(lay, "binary")) t->layout = BM_NODES_BINARY;
+            else if (lay && !strcmp(lay, "wide")) t->layout = BM_NODES_WIDE;
+            else if (lay && !strcmp(lay, "both")) t->layout = BM_NODES_BOTH;
+        }
+        if (t->layout != BM_NODES_WIDE) BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4));
+        if (t->layout != BM_NODES_BINARY) BM_TRY(t->wnodes.reserve((L - 1) * 64));
+        BM_TRY(t->nodeBox.reserve((L - 1) * 32)); BM_TRY(t->nodeMeta.reserve((L - 1) * 8));
         BM_TRY(t->parentN.reserve((L - 1) * 8)); BM_TRY(t->visit.reserve((L - 1) * 4));
         BM_TRY(build_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->visit.as<int>(), t->parentN.as<u32>(),
-                               t->nodes.as<float4>(), t->wnodes.as<uint4>(), t->nodeMeta.as<uint2>(), t->rootDev.as<u32>(), s));
+                               t->layout != BM_NODES_WIDE ? t->nodes.as<float4>() : nullptr, t->layout != BM_NODES_BINARY ? t->wnodes.as<uint4>() : nullptr,
+                               t->nodeMeta.as<uint2>(), t->rootDev.as<u32>(), s));
     }
     tm.mark("hierarchy");
     t->built = true;
@@ -342,24 +361,44 @@ extern "C" int bmTreeCopyPairs(const bmTree* tc, uint32_t* d_code, uint32_t* d_t
 extern "C" int bmTreeCopyTopology(const bmTree* t, uint32_t* d_prefixLen, uint32_t* d_prefix, uint32_t* d_child0, uint32_t* d_child1)
 {
     if (!t) return BM_ERROR_INVALID_PARAMETER;
-    if (!t->built) return BM_ERROR_NOT_BUILT;
+    if (!t->built || t->imported) return BM_ERROR_NOT_BUILT;
     if (t->L < 2) return BM_OK;
-    size_t N = t->L - 1;
-    const char* q3 = (const char*)t->nodes.p + 48;
-    const size_t stride = 16 * NODE_F4;
-    if (d_child0)    BM_CUDA(cudaMemcpy2DAsync(d_child0, 4, q3 + 0, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
-    if (d_child1)    BM_CUDA(cudaMemcpy2DAsync(d_child1, 4, q3 + 4, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
-    if (d_prefix)    BM_CUDA(cudaMemcpy2DAsync(d_prefix, 4, q3 + 8, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
-    if (d_prefixLen) BM_CUDA(cudaMemcpy2DAsync(d_prefixLen, 4, q3 + 12, stride, 4, N, cudaMemcpyDeviceToDevice, t->stream));
-    return BM_OK;
+    // from the hierarchy pass's own arrays (child references, cell coordinates + depth): the same for either node layout
+    return copy_topology(t->dgrid, t->parentN.as<u32>(), t->nodeMeta.as<uint2>(), (u32)(t->L - 1), d_prefixLen, d_prefix, d_child0, d_child1, t->stream);
 }
 
 extern "C" int bmTreeCopyChildBoxes(const bmTree* t, float* d_boxes12)
 {
     if (!t) return BM_ERROR_INVALID_PARAMETER;
-    if (!t->built) return BM_ERROR_NOT_BUILT;
+    if (!t->built || t->imported) return BM_ERROR_NOT_BUILT;
     if (t->L < 2) return BM_OK;
-    BM_CUDA(cudaMemcpy2DAsync(d_boxes12, 48, t->nodes.p, 16 * NODE_F4, 48, t->L - 1, cudaMemcpyDeviceToDevice, t->stream));
+    return copy_child_boxes(t->parentN.as<u32>(), t->leafBox.as<float4>(), t->nodeBox.as<float4>(), (u32)(t->L - 1), d_boxes12, t->stream);
+}
+
+// the quantised culling boxes a trace through the WIDE records actually uses, decoded: 24 floats per node (lo.xyz, hi.xyz of slots 0..3;
+// an empty slot gives lo > hi) and the four slot references.  Trees without wide records: BM_ERROR_NOT_BUILT.
+extern "C" int bmTreeCopyWideSlots(const bmTree* t, float* d_boxes24, uint32_t* d_refs4)
+{
+    if (!t) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built || t->layout == BM_NODES_BINARY) return BM_ERROR_NOT_BUILT;
+    if (t->L < 2) return BM_OK;
+    return copy_wide_slots(t->dgrid, t->wnodes.as<uint4>(), (u32)(t->L - 1), d_boxes24, d_refs4, t->stream);
+}
+
+extern "C" int bmTreeNodeLayout(const bmTree* t, uint32_t* layout)
+{
+    if (!t || !layout) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    *layout = (uint32_t)t->layout;
+    return BM_OK;
+}
+
+extern "C" int bmTreeWorld(const bmTree* t, float* worldMin3, float* worldMax3, float* minLeafSize, uint32_t* maxDepth)
+{
+    if (!t) return BM_ERROR_INVALID_PARAMETER;
+    for (int a = 0; a < 3; a++) { if (worldMin3) worldMin3[a] = t->hgrid.wmin[a]; if (worldMax3) worldMax3[a] = t->hgrid.wmax[a]; }
+    if (minLeafSize) *minLeafSize = t->hgrid.minLeaf;
+    if (maxDepth) *maxDepth = t->hgrid.maxDepth;
     return BM_OK;
 }
 
@@ -377,7 +416,7 @@ extern "C" int bmTreeArraySizes(const bmTree* t, uint64_t* sizes8)
     if (!t || !sizes8) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) return BM_ERROR_NOT_BUILT;
     size_t nC = t->P ? t->P / CLUSTER + t->L + 1 : 0;
-    sizes8[0] = t->L >= 2 ? (t->L - 1) * 16ull * NODE_F4 : 0;     // nodes
+    sizes8[0] = t->L >= 2 ? (t->L - 1) * (t->layout == BM_NODES_BINARY ? 16ull * NODE_F4 : 64ull) : 0;     // node records of the tree's layout (wide when it has both)
     sizes8[1] = t->L * 16ull * LEAF_F4;                             // leaves
     sizes8[2] = t->P * 48ull;                                       // triangle records
     sizes8[3] = nC * 16ull * CLUSTER_F4;                            // cluster boxes
@@ -404,7 +443,7 @@ extern "C" int bmTreeExport(const bmTree* t, void* d_nodes, void* d_leaves, void
 {
     uint64_t sz[8];
     BM_TRY(bmTreeArraySizes(t, sz));
-    const void* src[5] = { t->nodes.p, t->leaves.p, t->ltris.p, t->clusters.p, t->soup.p };
+    const void* src[5] = { t->layout == BM_NODES_BINARY ? t->nodes.p : t->wnodes.p, t->leaves.p, t->ltris.p, t->clusters.p, t->soup.p };
     void* dst[5] = { d_nodes, d_leaves, d_ltris, d_clusters, d_soup };
     for (int i = 0; i < 5; i++)
         if (dst[i] && sz[i]) BM_CUDA(cudaMemcpyAsync(dst[i], src[i], sz[i], cudaMemcpyDeviceToDevice, t->stream));
@@ -412,16 +451,19 @@ extern "C" int bmTreeExport(const bmTree* t, void* d_nodes, void* d_leaves, void
 }
 
 extern "C" int bmTreeImport(bmTree** out, const void* d_nodes, const void* d_leaves, const void* d_ltris, const void* d_clusters, const void* d_soup,
-                            uint64_t numLeaves, uint64_t numPairs, uint64_t numTris, uint32_t root)
+                            uint64_t numLeaves, uint64_t numPairs, uint64_t numTris, uint32_t root, uint32_t nodeLayout,
+                            const float* worldMin3, const float* worldMax3, float minLeafSize, uint32_t maxDepth)
 {
-    if (!out) return BM_ERROR_INVALID_PARAMETER;
+    if (!out || (nodeLayout != BM_NODES_BINARY && nodeLayout != BM_NODES_WIDE)) return BM_ERROR_INVALID_PARAMETER;
     bmTree* t = nullptr;
-    BM_TRY(bmTreeCreate(&t, nullptr, nullptr, 0.f, 0));
+    BM_TRY(bmTreeCreate(&t, worldMin3, worldMax3, minLeafSize, maxDepth));       // the wide records are decoded against the source tree's grid
     { int r = t->rootDev.reserve(16); if (r != BM_OK) { delete t; return r; } }
     if (cudaMemcpy(t->rootDev.p, &root, 4, cudaMemcpyHostToDevice) != cudaSuccess) { delete t; set_error("root upload failed"); return BM_ERROR_CUDA; }
     t->L = numLeaves; t->P = numPairs; t->T = numTris;
+    t->layout = (int)nodeLayout;
     size_t nC = numPairs ? numPairs / CLUSTER + numLeaves + 1 : 0;
-    t->nodes.adopt(d_nodes, numLeaves >= 2 ? (numLeaves - 1) * 16ull * NODE_F4 : 0);
+    if (nodeLayout == BM_NODES_BINARY) t->nodes.adopt(d_nodes, numLeaves >= 2 ? (numLeaves - 1) * 16ull * NODE_F4 : 0);
+    else t->wnodes.adopt(d_nodes, numLeaves >= 2 ? (numLeaves - 1) * 64ull : 0);
     t->leaves.adopt(d_leaves, numLeaves * 16ull * LEAF_F4);
     t->ltris.adopt(d_ltris, numPairs * 48ull);
     t->clusters.adopt(d_clusters, nC * 16ull * CLUSTER_F4);
@@ -444,7 +486,10 @@ extern "C" int bmTreeView(const bmTree* src, bmTree** out)
     bmTree* t = new bmTree();
     t->hgrid = src->hgrid; t->dgrid = src->dgrid;
     t->L = src->L; t->P = src->P; t->T = src->T; t->meshBase = src->meshBase; t->maxLeaf = src->maxLeaf; t->overLeaves = src->overLeaves;
-    t->nodes.adopt(src->nodes.p, sz[0]); t->leaves.adopt(src->leaves.p, sz[1]); t->ltris.adopt(src->ltris.p, sz[2]);
+    t->layout = src->layout;
+    if (src->layout != BM_NODES_WIDE) t->nodes.adopt(src->nodes.p, (src->L - (src->L ? 1 : 0)) * 16ull * NODE_F4);
+    if (src->layout != BM_NODES_BINARY) t->wnodes.adopt(src->wnodes.p, (src->L - (src->L ? 1 : 0)) * 64ull);
+    t->leaves.adopt(src->leaves.p, sz[1]); t->ltris.adopt(src->ltris.p, sz[2]);
     t->clusters.adopt(src->clusters.p, sz[3]); t->soup.adopt(src->soup.p, sz[4]); t->rootDev.adopt(src->rootDev.p, 16);
     t->stream = src->stream;
     t->built = true; t->imported = true;

@@ -41,13 +41,19 @@ def replicate_tree(tree: Tree | None, device, src: int = 0) -> Tree:
         return tree
     L = _lib.load()
     rank = dist.get_rank()
-    sizes = torch.zeros(9, dtype=torch.int64, device=device)
+    sizes = torch.zeros(12, dtype=torch.int64, device=device)
+    world_box = torch.zeros(7, dtype=torch.float32, device=device)
     if rank == src:
         s = (C.c_uint64 * 8)()
         _lib.check(L.bmTreeArraySizes(tree.h, s), "bmTreeArraySizes")
-        sizes.copy_(torch.tensor([int(x) for x in s] + [tree.root()], dtype=torch.int64))
+        wmin, wmax, min_leaf, max_depth = tree.world()
+        layout = tree.node_layout()
+        sizes.copy_(torch.tensor([int(x) for x in s] + [tree.root(), 1 if layout != _lib.BM_NODES_BINARY else 0, max_depth, 0], dtype=torch.int64))
+        world_box.copy_(torch.tensor(list(wmin) + list(wmax) + [min_leaf], dtype=torch.float32))
     dist.broadcast(sizes, src)
+    dist.broadcast(world_box, src)
     sz = [int(x) for x in sizes.cpu()]
+    wb = world_box.cpu().numpy().astype(np.float32)
     bufs = [torch.empty(max(b, 16), dtype=torch.uint8, device=device) for b in sz[:5]]
     if rank == src:
         _lib.check(L.bmTreeExport(tree.h, *[b.data_ptr() for b in bufs]), "bmTreeExport")
@@ -59,7 +65,8 @@ def replicate_tree(tree: Tree | None, device, src: int = 0) -> Tree:
     out = Tree.__new__(Tree)
     out.L = L; out.device = torch.device(device); out._meshes = []
     h = C.c_void_p()
-    _lib.check(L.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7], sz[8]), "bmTreeImport")
+    wmin = np.ascontiguousarray(wb[0:3]); wmax = np.ascontiguousarray(wb[3:6])
+    _lib.check(L.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7], sz[8], sz[9], wmin.ctypes.data, wmax.ctypes.data, float(wb[6]), sz[10]), "bmTreeImport")
     out.h = h
     out._imported_buffers = bufs          # keep the adopted memory alive with the handle
     out.use_stream(torch.cuda.current_stream(out.device))

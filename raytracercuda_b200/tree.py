@@ -80,6 +80,26 @@ class Tree:
         check(self.L.bmTreeRoot(self.h, C.byref(r)), "bmTreeRoot")
         return int(r.value)
 
+    def node_layout(self) -> int:
+        """BM_NODES_BINARY (128-byte binary records), BM_NODES_WIDE (64-byte 4-wide records) or BM_NODES_BOTH"""
+        v = C.c_uint32(0)
+        check(self.L.bmTreeNodeLayout(self.h, C.byref(v)), "bmTreeNodeLayout")
+        return int(v.value)
+
+    def world(self):
+        """(world_min[3], world_max[3], min_leaf, max_depth) of the tree's grid"""
+        a = np.zeros(3, np.float32); b = np.zeros(3, np.float32); ml = C.c_float(0); md = C.c_uint32(0)
+        check(self.L.bmTreeWorld(self.h, a.ctypes.data, b.ctypes.data, C.byref(ml), C.byref(md)), "bmTreeWorld")
+        return a, b, float(ml.value), int(md.value)
+
+    def wide_slots(self):
+        """decoded culling boxes (N,4,6) and slot references (N,4) of the wide records"""
+        N = self.stats()["nodes"]
+        b = torch.empty((N, 4, 6), dtype=torch.float32, device=self.device); r = torch.empty((N, 4), dtype=torch.int32, device=self.device)
+        check(self.L.bmTreeCopyWideSlots(self.h, b.data_ptr(), r.data_ptr()), "bmTreeCopyWideSlots")
+        self.stream.synchronize()
+        return b.cpu().numpy(), _u32(r)
+
     def mesh_bases(self) -> np.ndarray:
         n = len(self._meshes)
         b = (C.c_uint32 * max(n, 1))()

@@ -285,10 +285,10 @@ def test_part1_failures_are_sticky_not_fatal(beam_lib, cuda_device):
 
 
 def test_pair_total_beyond_32_bits_is_a_capacity_error(beam_lib, cuda_device):
-    """2,600 world-spanning triangles reach ~2 M leaf cells each: the pair total passes 2^32 and must come back as BM_ERROR_CAPACITY,
+    """4,600 world-spanning triangles reach ~1 M leaf cells each: the pair total passes 2^32 and must come back as BM_ERROR_CAPACITY,
     not as wrapped offsets"""
     from raytracercuda_b200.tree import Tree
-    n = 2600
+    n = 4600
     z = np.linspace(-20, 20, n).astype(np.float32)
     P = np.zeros((n, 3, 3), np.float32)
     P[:, 0] = [-29.9, -29.9, 0]; P[:, 1] = [29.9, -29.9, 0]; P[:, 2] = [0, 29.9, 0]

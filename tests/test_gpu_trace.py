@@ -217,35 +217,99 @@ def test_bounce_rays_workflow(oracle_lib, beam_lib, cuda_device):
     t.close(); s.close()
 
 
-def test_export_import_replica_traces_identically(meshes, beam_lib, cuda_device):
-    """multi-GPU replication path on one GPU: export the traversal arrays, adopt them as a read-only tree, trace both"""
+@pytest.mark.parametrize("layout", ["binary", "wide"])
+def test_export_import_replica_traces_identically(layout, meshes, beam_lib, cuda_device, monkeypatch):
+    """multi-GPU replication path on one GPU: export the traversal arrays, adopt them as a read-only tree, trace both -- for both node
+    layouts (the wide records are decoded against the source tree's grid, which travels with the import call)"""
     import ctypes as C
     import torch
     from raytracercuda_b200 import _lib
     from raytracercuda_b200.tree import Tree, hits_to_numpy
+    monkeypatch.setenv("BM_NODE_LAYOUT", layout)
     P, I, N = meshes["bunny"]
     t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+    assert t.node_layout() == (_lib.BM_NODES_WIDE if layout == "wide" else _lib.BM_NODES_BINARY)
     sz = (C.c_uint64 * 8)()
     assert beam_lib.bmTreeArraySizes(t.h, sz) == 0
     st = t.stats()
     assert (sz[5], sz[6], sz[7]) == (st["leaves"], st["pairs"], st["triangles"])
+    assert sz[0] == st["nodes"] * (64 if layout == "wide" else 128)
     bufs = [torch.empty(max(int(b), 16), dtype=torch.uint8, device=cuda_device) for b in sz[:5]]
     assert beam_lib.bmTreeExport(t.h, *[b.data_ptr() for b in bufs]) == 0
     torch.cuda.synchronize()
     h = C.c_void_p()
-    assert beam_lib.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7], t.root()) == 0
+    wmin, wmax, min_leaf, max_depth = t.world()
+    assert beam_lib.bmTreeImport(C.byref(h), *[b.data_ptr() for b in bufs], sz[5], sz[6], sz[7], t.root(), t.node_layout(), wmin.ctypes.data, wmax.ctypes.data,
+                                 min_leaf, max_depth) == 0
     rng = np.random.default_rng(5)
     R = torch.from_numpy(_ray_batch(rng, 40000, 2.5)).to(cuda_device)
-    a = hits_to_numpy(t.trace_rays(R, 0))
-    hits = torch.empty((R.shape[0], 4), dtype=torch.float32, device=cuda_device)
-    assert beam_lib.bmTraceRays(h, R.data_ptr(), R.shape[0], 0, hits.data_ptr(), None) == 0
-    b = hits_to_numpy(hits)
-    assert np.array_equal(a["tri"], b["tri"]) and np.array_equal(a["t"], b["t"])
+    for mode in (0, 1):
+        a = hits_to_numpy(t.trace_rays(R, mode))
+        hits = torch.empty((R.shape[0], 4), dtype=torch.float32, device=cuda_device)
+        assert beam_lib.bmTraceRays(h, R.data_ptr(), R.shape[0], mode, hits.data_ptr(), None) == 0
+        b = hits_to_numpy(hits)
+        assert np.array_equal(a["tri"], b["tri"]) and np.array_equal(a["t"], b["t"])
     assert beam_lib.bmTreeBuild(h) != 0                      # read-only
     st8 = (C.c_uint64 * 8)()
     assert beam_lib.bmTreeStats(h, st8) == 0 and st8[2] == st["leaves"]
     beam_lib.bmTreeDestroy(h)
     t.close()
+
+
+def test_wide_records_trace_like_binary_records_and_enclose_the_exact_boxes(meshes, oracle_lib, beam_lib, cuda_device, monkeypatch):
+    """The two node layouts of one tree (BM_NODE_LAYOUT=both): identical hits in both trace modes on camera rays and incoherent batches,
+    fewer node visits through the wide records, and every decoded (quantised) slot box encloses the exact box of the child it stands for."""
+    import torch
+    from raytracercuda_b200 import _lib, synth
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    monkeypatch.setenv("BM_NODE_LAYOUT", "both")
+    rng = np.random.default_rng(11)
+    Ps, Is = random_soup(rng, 150000, 4.0, 0.05)
+    for name, (P, I) in {"bunny": meshes["bunny"][:2], "f16": meshes["f16"][:2], "soup": (Ps, Is)}.items():
+        t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+        assert t.node_layout() == _lib.BM_NODES_BOTH
+        # slot boxes vs the exact child boxes: slots (0,1) are the children of child 0 when it is internal, else slot 0 is child 0 itself
+        plen, prefix, c0, c1 = t.topology()
+        exact = t.child_boxes().reshape(-1, 2, 6)                         # per node: boxes of its two children
+        wb, wr = t.wide_slots()
+        LEAF = 0x80000000
+        for h, c in ((0, c0), (1, c1)):
+            inner = (c & LEAF) == 0
+            ci = c[inner].astype(np.int64)
+            for k in (0, 1):                                              # absorbed child: its children's refs and boxes
+                ck = (c0 if k == 0 else c1)[ci]
+                assert np.array_equal(wr[inner, 2 * h + k], ck)
+                ex = exact[ci, k]
+                got = wb[inner, 2 * h + k]
+                assert (got[:, :3] <= ex[:, :3]).all() and (got[:, 3:] >= ex[:, 3:]).all(), name
+                slack = np.maximum(ex[:, :3] - got[:, :3], got[:, 3:] - ex[:, 3:]).max(1)
+                size = (ex[:, 3:] - ex[:, :3]).max(1)
+                assert np.median(slack / np.maximum(size, 1e-6)) < 0.05     # 8 bits per coordinate on the node's own grid
+            leaf = ~inner
+            assert np.array_equal(wr[leaf, 2 * h], c[leaf]) and (wr[leaf, 2 * h + 1] == 0x7FFFFFFF).all()
+            got = wb[leaf, 2 * h]; ex = exact[leaf, h]
+            assert (got[:, :3] <= ex[:, :3]).all() and (got[:, 3:] >= ex[:, 3:]).all()
+        rays = _ray_batch(rng, 60000, 2.5 if name != "soup" else 4.5)
+        R = torch.from_numpy(rays).to(cuda_device)
+        cam = torch.from_numpy(oracle_lib.initial_rays(320, 200)).to(cuda_device)
+        # results through a binary-only and a wide-only build of the same scene
+        t.close()
+        outs = {}
+        for lay in ("binary", "wide"):
+            monkeypatch.setenv("BM_NODE_LAYOUT", lay)
+            tt = Tree(cuda_device); tt.add_mesh(P, I); tt.build()
+            o = []
+            for mode in (0, 1):
+                hits, cnt = tt.trace_rays(R, mode, counters=True)
+                o.append((hits_to_numpy(hits), int(cnt.cpu()[0])))
+                hits, cnt = tt.trace_camera(cam, [0, 0, -2.1] if name != "soup" else [0, 0, -6.0], ID3, mode=mode, counters=True, width=320)
+                o.append((hits_to_numpy(hits), int(cnt.cpu()[0])))
+            outs[lay] = o
+            tt.close()
+        monkeypatch.setenv("BM_NODE_LAYOUT", "both")
+        for (hb, vb), (hw, vw) in zip(outs["binary"], outs["wide"]):
+            assert np.array_equal(hb["tri"], hw["tri"]) and np.array_equal(hb["t"], hw["t"]) and np.array_equal(hb["u"], hw["u"]), name
+            assert vw < vb, "the wide walk must take fewer node visits"
 
 
 @pytest.mark.parametrize("name,W,H", [("bunny", 640, 360), ("suzanne", 203, 77)])
