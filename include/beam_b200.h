@@ -166,6 +166,10 @@ int  bmTreeAddMesh(bmTree* tree, const float* d_positions, const uint32_t* d_ind
 /* keys -> sort -> leaves -> one bottom-up pass (radix tree + tight boxes) -> node records (see bmTreeNodeLayout). Asynchronous on the tree's stream except for two
  * 8-byte read-backs (pair and leaf counts) that size the later stages. */
 int  bmTreeBuild(bmTree* tree);
+/* CUDA-event times of the stages of the next builds (costs one synchronise per build): bmTreeLastBuildStages returns
+ * "gather <us> classify <us> ... total <us>" for the last timed build ("" before) */
+int  bmTreeEnableStageTiming(bmTree* tree, int on);
+const char* bmTreeLastBuildStages(const bmTree* tree);
 int  bmBuildTree(void* treeRootNode);                          /* same, for a tree made through Part 1 */
 bmTree* bmTreeFromRoot(const void* treeRootNode);              /* Part 1 handle -> Part 2 handle (NULL if unknown) */
 

@@ -85,7 +85,9 @@ namespace Beam
         // scaled by |n.z|, untextured ones the reference's pixel (bmShadeHits in beam_b200.h states the rule)
         virtual u32 traceSceneTextured(const float* eye3, const float* orient3x3, sptr<IScene>& scene) = 0;
         // what the reference's SceneProgressive (an empty stub, SceneProgressive.cpp:27-77) set out to do: `samples` jittered primary
-        // rays per pixel, one diffuse bounce ray per hit, accumulated and resolved into the locked render target
+        // rays per pixel (samples == 1: the exact pixel-centre rays traceScene uses), one diffuse bounce ray per hit traced as a closest hit,
+        // accumulated and resolved into the locked render target.  Asynchronous like traceScene; *raysTraced (nullable) is written by an
+        // asynchronous copy and is valid once readPixels of that target -- or a device synchronise -- has returned
         virtual u32 traceSceneProgressive(const float* eye3, const float* orient3x3, sptr<IScene>& scene, u32 samples, u32 seed, u64* raysTraced = nullptr) = 0;
     };
 }

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmStickyError", "bmStickyErrorString", "bmClearStickyError", "bmReleaseScene", "bmSetPart1Stream",
     "bmTraceCameraJittered", "bmBounceRaysCameraJittered", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
-    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView", "bmTreeNodeLayout", "bmTreeWorld", "bmTreeCopyWideSlots",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView", "bmTreeEnableStageTiming", "bmTreeLastBuildStages", "bmTreeNodeLayout", "bmTreeWorld", "bmTreeCopyWideSlots",
     "bmTraceRays", "bmTraceRaysTiled", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     L.bmTreeArraySizes.argtypes = [vp, C.POINTER(u64)]
     L.bmTreeExport.argtypes = [vp, vp, vp, vp, vp, vp]
     L.bmTreeImport.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, u64, u64, u64, u32, u32, vp, vp, C.c_float, u32]
+    L.bmTreeEnableStageTiming.argtypes = [vp, i32]
+    L.bmTreeLastBuildStages.argtypes = [vp]; L.bmTreeLastBuildStages.restype = C.c_char_p
     L.bmTreeNodeLayout.argtypes = [vp, C.POINTER(u32)]
     L.bmTreeWorld.argtypes = [vp, vp, vp, C.POINTER(C.c_float), C.POINTER(u32)]
     L.bmTreeCopyWideSlots.argtypes = [vp, vp, vp]

@@ -309,8 +309,11 @@ public:
         static_cast<RenderTarget*>(rt)->markWritten();
         if (raysTraced)
         {
-            // ONE read-back per frame, after everything has been queued
-            if (cudaMemcpyAsync(raysTraced, total, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return BM_ERROR_CUDA;
+            // ONE 8-byte read-back per frame, queued BEFORE the render target's "written" event and not waited for: like the pixels, the
+            // count is valid once readPixels of this frame's target (or a device synchronise) has returned.  With pinned memory
+            // (beamHostAlloc) the call stays asynchronous, so frames can be pipelined; a pageable destination makes the copy block.
+            if (cudaMemcpyAsync(raysTraced, total, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return BM_ERROR_CUDA;
+            static_cast<RenderTarget*>(rt)->markWritten();
         }
         return ERROR_ALL_FINE;
     }

@@ -86,6 +86,7 @@ struct bmTree
     bool built = false, imported = false;
     // build products
     DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState;
+    bool stageTiming = false; std::string lastStages;      // bmTreeEnableStageTiming / bmTreeLastBuildStages
     int layout = BM_NODES_BINARY;    // which node records the last build wrote (BM_NODES_*; set by tree_build, or by bmTreeImport)
     u32 schedTiles = 0;              // frame size (in 8x4 tiles) the tile-scheduling buffers are set up for; 0 = none
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
@@ -117,20 +118,23 @@ struct bmTree
     }
 };
 
-// BM_BUILD_TIMING=1: CUDA events between the stages of a build, printed to stderr (development aid; adds one synchronise at the end)
+// Stage times of a build: CUDA events between the stages (bmTreeEnableStageTiming, or BM_BUILD_TIMING=1 which also prints them to stderr).
+// Costs one extra synchronise at the end of the build, so it is off unless asked for; the result is kept as text "name us name us ... total us".
 struct StageTimer
 {
-    bool on; cudaStream_t s; std::vector<std::pair<const char*, cudaEvent_t>> ev;
-    StageTimer(cudaStream_t st) : on(getenv("BM_BUILD_TIMING") != nullptr), s(st) { mark("start"); }
+    bool on, print; cudaStream_t s; std::string* out; std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    StageTimer(cudaStream_t st, bool enabled, std::string* result) : on(enabled || getenv("BM_BUILD_TIMING") != nullptr), print(getenv("BM_BUILD_TIMING") != nullptr), s(st), out(result) { mark("start"); }
     void mark(const char* name) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back({ name, e }); }
     ~StageTimer()
     {
         if (!on) return;
         cudaStreamSynchronize(s);
-        std::string line = "beam_b200 build stages (us):";
-        for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); char b[96]; snprintf(b, sizeof b, " %s %.1f", ev[i].first, ms * 1e3f); line += b; }
+        std::string line;
+        for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); char b[96]; snprintf(b, sizeof b, "%s %.1f ", ev[i].first, ms * 1e3f); line += b; }
         float tot = 0; if (ev.size() > 1) cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
-        fprintf(stderr, "%s | total %.1f\n", line.c_str(), tot * 1e3f);
+        char b[64]; snprintf(b, sizeof b, "total %.1f", tot * 1e3f); line += b;
+        if (out) *out = line;
+        if (print) fprintf(stderr, "beam_b200 build stages (us): %s\n", line.c_str());
         for (auto& e : ev) cudaEventDestroy(e.second);
     }
 };
@@ -138,7 +142,7 @@ struct StageTimer
 static int tree_build(bmTree* t)
 {
     cudaStream_t s = t->stream;
-    StageTimer tm(s);
+    StageTimer tm(s, t->stageTiming, &t->lastStages);
     // 1. soup
     u64 T = 0;
     t->meshBase.clear();
@@ -179,7 +183,7 @@ static int tree_build(bmTree* t)
     unsigned long long P64 = 0;
     BM_CUDA(cudaMemcpyAsync(&P64, d_scal + 12, 8, cudaMemcpyDeviceToHost, s));
     BM_CUDA(cudaStreamSynchronize(s));
-    tm.mark("scan+readback");
+    tm.mark("scan_readback");
     if (P64 >= 0xFFFFFFF0ull) { set_error("more than 2^32 (leaf, triangle) pairs: the scene does not fit the 32-bit pair index"); return BM_ERROR_CAPACITY; }
     u64 P = P64;
     t->hostScalars[0] = (u32)P64;
@@ -219,7 +223,7 @@ static int tree_build(bmTree* t)
     BM_CUDA(cudaStreamSynchronize(s));
     u64 L = t->hostScalars[1];
     t->L = L;
-    tm.mark("heads+scan+pack+readback");
+    tm.mark("heads_scan_pack_readback");
     BM_TRY(t->leaves.reserve(L * 16 * LEAF_F4)); BM_TRY(t->clusterCounts.reserve(L * 4 + 4)); BM_TRY(t->codes.reserve(L * 4 + 4));
     BM_TRY(write_leaves(t->dgrid, t->sortedKeys, t->flags.as<u32>(), leafIdx, P, (u32)L, t->leaves.as<float4>(), t->clusterCounts.as<u32>(), t->codes.as<u32>(), s));
     BM_TRY(exclusive_scan_u32(t->clusterCounts.as<u32>(), t->clusterCounts.as<u32>(), L, nullptr, t->temp.p, s));
@@ -228,7 +232,7 @@ static int tree_build(bmTree* t)
     float pad = ext * (1.f / 1048576.f);
     BM_TRY(leaf_bounds(t->leaves.as<float4>(), (u32)L, t->flags.as<u32>(), leafIdx, P, t->clusterCounts.as<u32>(), t->ltris.as<float4>(), t->clusters.as<float4>(),
                        t->leafBox.as<float4>(), pad, d_scal + 2, t->parentL.as<u32>(), s));     // parentL doubles as the overflow-leaf queue until emit_hierarchy fills it
-    tm.mark("leaves+clusters+bounds");
+    tm.mark("leaves_clusters_bounds");
     // 5. hierarchy and tight boxes, one bottom-up pass
     if (L >= 2)
     {
@@ -329,6 +333,9 @@ extern "C" int bmTreeBuild(bmTree* t)
     if (t->imported) { set_error("imported (read-only) tree: rebuild not possible"); return BM_ERROR_INVALID_PARAMETER; }
     return tree_build(t);
 }
+
+extern "C" int bmTreeEnableStageTiming(bmTree* t, int on) { if (!t) return BM_ERROR_INVALID_PARAMETER; t->stageTiming = on != 0; return BM_OK; }
+extern "C" const char* bmTreeLastBuildStages(const bmTree* t) { return t ? t->lastStages.c_str() : ""; }
 
 extern "C" int bmTreeStats(const bmTree* tc, uint64_t* s)
 {

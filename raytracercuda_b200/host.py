@@ -148,6 +148,8 @@ class ICamera:
         e = self._f(eye3, 3); o = self._f(orient3x3, 9)
         rays = C.c_uint64(0)
         err = self.L.beamCameraTraceSceneProgressive(self.h, e.ctypes.data, o.ctypes.data, scene.h, int(samples), int(seed), C.byref(rays))
+        if err == 0:
+            device_synchronize()          # the count arrives by an asynchronous copy (valid after readPixels or a synchronise)
         return err, int(rays.value)
 
     def __del__(self):

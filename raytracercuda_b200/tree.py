@@ -80,6 +80,14 @@ class Tree:
         check(self.L.bmTreeRoot(self.h, C.byref(r)), "bmTreeRoot")
         return int(r.value)
 
+    def build_stages(self) -> dict:
+        """stage times (microseconds) of the last build made after enable_stage_timing(True)"""
+        w = self.L.bmTreeLastBuildStages(self.h).decode().split()
+        return {w[i]: float(w[i + 1]) for i in range(0, len(w) - 1, 2)}
+
+    def enable_stage_timing(self, on=True):
+        check(self.L.bmTreeEnableStageTiming(self.h, int(bool(on))), "bmTreeEnableStageTiming")
+
     def node_layout(self) -> int:
         """BM_NODES_BINARY (128-byte binary records), BM_NODES_WIDE (64-byte 4-wide records) or BM_NODES_BOTH"""
         v = C.c_uint32(0)
