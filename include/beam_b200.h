@@ -218,6 +218,14 @@ int  bmTreeView(const bmTree* tree, bmTree** out);
  * boxes tested} (the traversal work behind the bytes-per-ray roofline model) and keeps in [3] the largest number of such steps any
  * single ray needed (the launch's critical path). */
 int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters);
+/* How bmTraceRays walks trees far larger than the L2.  The top levels of the reference's kd-tree are an implicit grid (midpoint splits of the
+ * world box, BuildTree.cu:196-216), so a batch can be cut into one SEGMENT per (ray, brick of that grid entered), the segments sorted by
+ * brick and traced brick by brick out of the cache; per-ray results are merged in the order the reference's own traversal would have met
+ * the bricks (raytracercuda_b200/csrc/bricks.cu).  Hits are identical to the direct traversal in both modes.  mode: -1 automatic
+ * (traversal arrays above BM_BRICK_MIN_MB = 512 MB and >= 2^18 rays; BM_BRICKS=0|1 overrides), 0 never, 1 always; bits: depth of the
+ * brick grid, 3..15, 0 = default (12 = 16 x 16 x 16 bricks; BM_BRICK_BITS).  A bricked call synchronises the tree's stream once (the
+ * segment count sizes the sort). */
+int  bmTreeSetBricks(bmTree* tree, int mode, int bits);
 /* Same, with the ray count read from DEVICE memory when the kernel starts (*d_numRays <= maxRays): lets a producer such as
  * bmBounceRays feed the trace without a host round trip. */
 int  bmTraceRaysIndirect(bmTree* tree, const bmRay* d_rays, const uint32_t* d_numRays, uint64_t maxRays, int mode, bmHit* d_hits, uint64_t* d_counters);

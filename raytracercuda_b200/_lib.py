@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmStickyError", "bmStickyErrorString", "bmClearStickyError", "bmReleaseScene", "bmSetPart1Stream",
     "bmTraceCameraJittered", "bmBounceRaysCameraJittered", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
-    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView", "bmTreeEnableStageTiming", "bmTreeLastBuildStages", "bmTreeNodeLayout", "bmTreeWorld", "bmTreeCopyWideSlots",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView", "bmTreeEnableStageTiming", "bmTreeLastBuildStages", "bmTreeNodeLayout", "bmTreeWorld", "bmTreeCopyWideSlots", "bmTreeSetBricks",
     "bmTraceRays", "bmTraceRaysTiled", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
     L.bmTreeNodeLayout.argtypes = [vp, C.POINTER(u32)]
     L.bmTreeWorld.argtypes = [vp, vp, vp, C.POINTER(C.c_float), C.POINTER(u32)]
     L.bmTreeCopyWideSlots.argtypes = [vp, vp, vp]
+    L.bmTreeSetBricks.argtypes = [vp, i32, i32]
     L.bmTreeRoot.argtypes = [vp, C.POINTER(u32)]
     L.bmTreeView.argtypes = [vp, C.POINTER(vp)]
     L.bmTraceRays.argtypes = [vp, vp, u64, i32, vp, vp]

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbeam_b200.so")
-SOURCES = ["scan.cu", "sort.cu", "keygen.cu", "hierarchy.cu", "trace.cu", "rays.cu", "tree.cu", "host.cu", "objload.cpp"]
+SOURCES = ["scan.cu", "sort.cu", "keygen.cu", "hierarchy.cu", "trace.cu", "bricks.cu", "rays.cu", "tree.cu", "host.cu", "objload.cpp"]
 # -fmad=false: keys, traversal decisions and t must round like the reference's unfused host arithmetic (DESIGN.md "Rounding")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-ccbin", "g++", "-shared"]

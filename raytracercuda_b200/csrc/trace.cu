@@ -44,6 +44,23 @@ __device__ __forceinline__ bool line_hits_box_fma(V3 bMin, V3 bMax, V3 inv, V3 o
     return !(tf < tn);
 }
 
+// the same slabs for the CLOSEST mode's leaf-interior culling: the box must overlap the ray's [0, tbest] (a hit inside the unpadded box
+// has a t that every padded slab interval contains, so tf >= t >= 0 and tn <= t <= tbest: conservative like the line test)
+__device__ __forceinline__ bool seg_hits_box_fma(V3 bMin, V3 bMax, V3 inv, V3 oi, float tbest)
+{
+    float x0 = __fmaf_rn(bMin.x, inv.x, -oi.x), x1 = __fmaf_rn(bMax.x, inv.x, -oi.x);
+    float y0 = __fmaf_rn(bMin.y, inv.y, -oi.y), y1 = __fmaf_rn(bMax.y, inv.y, -oi.y);
+    float z0 = __fmaf_rn(bMin.z, inv.z, -oi.z), z1 = __fmaf_rn(bMax.z, inv.z, -oi.z);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return !(tf < tn) && !(tf < 0.f) && !(tn > tbest);
+}
+template <int MODE>
+__device__ __forceinline__ bool cluster_hit(V3 bMin, V3 bMax, V3 inv, V3 oi, float tbest)
+{
+    return MODE == BM_TRACE_REFERENCE ? line_hits_box_fma(bMin, bMax, inv, oi) : seg_hits_box_fma(bMin, bMax, inv, oi, tbest);
+}
+
 // ---- one step of each traversal flavour, shared by every kernel variant -------------------------------------------------
 // Internal node in REFERENCE mode: cell test with the reference's slab arithmetic, child order by the split plane
 // (BuildTree.cu:398-481), children whose tight box the ray's line misses are not pushed.
@@ -219,6 +236,7 @@ __device__ __forceinline__ void coop_leaf(const TreeView& tv, unsigned lane, int
     V3 ric = mk3(__shfl_sync(FULL, ic.x, owner), __shfl_sync(FULL, ic.y, owner), __shfl_sync(FULL, ic.z, owner));
     V3 roi = mk3(__shfl_sync(FULL, oi.x, owner), __shfl_sync(FULL, oi.y, owner), __shfl_sync(FULL, oi.z, owner));
     u32 lfirst = __shfl_sync(FULL, first, owner), lcnt = __shfl_sync(FULL, cnt, owner), lcf = __shfl_sync(FULL, cfirst, owner);
+    const float rbest = __shfl_sync(FULL, best.t, owner);
     HitRec mine = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
     u32 ngroups = (lcnt + CLUSTER - 1) / CLUSTER;
     u32 tests = 0, boxes = 0;
@@ -235,7 +253,7 @@ __device__ __forceinline__ void coop_leaf(const TreeView& tv, unsigned lane, int
                 const float4* cp = tv.clusters + CLUSTER_F4 * (size_t)(lcf + g);
                 float4 b0 = __ldg(cp), b1 = __ldg(cp + 1);
                 boxes++;
-                pass = line_hits_box_fma(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), ric, roi);
+                pass = cluster_hit<MODE>(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), ric, roi, rbest);
             }
         }
         unsigned bits = __ballot_sync(FULL, pass);
@@ -385,10 +403,14 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
 #ifndef BM_TR_BLOCKS
 #define BM_TR_BLOCKS 6
 #endif
-template <int MODE, bool CAMERA, bool COUNT, bool WIDE>
+// SEG (ray batches through bricks, bricks.cu): a slot is one SEGMENT -- (ray, brick, position of the brick in the ray's own visiting order) --
+// of a list sorted by brick; the lane walks the brick's subtree only and merges what it finds into the ray's 64-bit result key with
+// an atomic minimum (SegIn).  Everything between refill and retire is the same traversal.
+template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG>
 __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
-                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int leafWait, int refillMin, int queueDepth, TileSched sched)
+                                                           const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int leafWait, int refillMin, int queueDepth, TileSched sched,
+                                                           SegIn seg)
 {
     const u32 rootRef = tv.numLeaves >= 2 ? __ldg(tv.root) : (tv.numLeaves == 1 ? (0u | LEAF_BIT) : REF_EMPTY);
     if (numRaysDev) { n = __ldg(numRaysDev); totalSlots = (u32)n; }       // count produced on the device (bmBounceRays): no host round trip
@@ -408,6 +430,8 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
     if (useOrder) totalSlots = sched.state[TS_ENTRIES] * 32u;      // the work list may hold some tiles as four quarter entries
     u32 curTile = 0xFFFFFFFFu;
     long long tileStart = 0;
+    u32 segSeq = 0;                         // SEG: position of this brick in the ray's visiting order
+    unsigned long long segKey0 = ~0ull;     // SEG: the ray's result key when the segment started
 
     for (;;)
     {
@@ -448,7 +472,20 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     if (quarter) { take = lane < 8u; slot = (curTile << 5) | ((quarter - 1u) << 3) | (lane & 7u); }
                     else slot = (curTile << 5) | lane;
                 }
-                if (take && slot_to_ray(slot, n, width, height, rayIdx))
+                u32 startRef = rootRef;
+                if (SEG && take)
+                {
+                    // the segment: its ray, its brick's subtree, and what the ray's other segments have found so far.  REFERENCE: the first
+                    // brick (in the ray's own order) with a hit decides, so a segment behind a brick that already reported one is skipped;
+                    // CLOSEST: the best hit so far bounds this segment's search.
+                    const u32 key = __ldg(seg.keys + slot);
+                    rayIdx = __ldg(seg.rays + slot);
+                    segSeq = key >> 16;
+                    startRef = __ldg(seg.roots + (key & 0xFFFFu));
+                    segKey0 = __ldcg(seg.rayKey + rayIdx);
+                    if (MODE == BM_TRACE_REFERENCE && (u32)(segKey0 >> 32) < segSeq) take = false;
+                }
+                if (take && (SEG || slot_to_ray(slot, n, width, height, rayIdx)))
                 {
                     if (CAMERA && !rays) camera_ray(cam, rayIdx, o, d);      // formed in registers: no ray record is ever written or read
                     else
@@ -462,8 +499,9 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     oi = o * ic;
                     if (WIDE && MODE == BM_TRACE_REFERENCE) fm = mk3(tv.leafExt[0] * fabsf(ic.x), tv.leafExt[1] * fabsf(ic.y), tv.leafExt[2] * fabsf(ic.z));
                     best.t = FLT_MAX; best.u = 0.f; best.v = 0.f; best.tri = best.mesh = best.face = 0xFFFFFFFFu;
+                    if (SEG && MODE != BM_TRACE_REFERENCE && segKey0 != ~0ull) { best.t = __uint_as_float((u32)(segKey0 >> 32)); best.tri = (u32)segKey0; }
                     top = -1;
-                    cur = rootRef;
+                    cur = startRef;
                     active = true;
                     if (COUNT) rayStart = nv + nt + nc;
                 }
@@ -579,7 +617,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                                 if (i + k < scan)
                                 {
                                     if (COUNT) nc++;
-                                    if (line_hits_box_fma(mk3(b[2 * k].x, b[2 * k].y, b[2 * k].z), mk3(b[2 * k].w, b[2 * k + 1].x, b[2 * k + 1].y), ic, oi)) mask |= 1ull << (i + k);
+                                    if (cluster_hit<MODE>(mk3(b[2 * k].x, b[2 * k].y, b[2 * k].z), mk3(b[2 * k].w, b[2 * k + 1].x, b[2 * k + 1].y), ic, oi, best.t)) mask |= 1ull << (i + k);
                                 }
                             }
                         }
@@ -614,8 +652,22 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
         // ---- retire ------------------------------------------------------------------------------------------------------------
         if (active && (finished || cur == REF_EMPTY))
         {
+            if (SEG)
+            {
+                // REFERENCE: (position of the brick in the ray's order, triangle) -- the smallest position wins; CLOSEST: (t >= 0 as its
+                // bit pattern, triangle) -- the smallest t wins, the smaller id on a tie.  t, u, v are recomputed from the triangle afterwards.
+                if (best.tri != 0xFFFFFFFFu)
+                {
+                    const unsigned long long k = MODE == BM_TRACE_REFERENCE ? (((unsigned long long)segSeq << 32) | best.tri)
+                                                                            : (((unsigned long long)__float_as_uint(best.t == 0.f ? 0.f : best.t) << 32) | best.tri);
+                    if (k < segKey0) atomicMin(seg.rayKey + rayIdx, k);
+                }
+            }
+            else
+            {
             if (hits) { reinterpret_cast<float4*>(hits)[rayIdx] = make_float4(best.t, best.u, best.v, __uint_as_float(best.tri)); }
             if (pixels) pixels[rayIdx] = shade(best, meshData);
+            }
             active = false;
             if (COUNT) longest = max(longest, nv + nt + nc - rayStart);
         }
@@ -701,16 +753,16 @@ bool use_wide(const TreeView& tv)
     return v != 0;
 }
 
-template <int MODE, bool CAMERA, bool COUNT, bool WIDE>
+template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG = false>
 int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
-                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
+                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, SegIn seg = SegIn{ nullptr, nullptr, nullptr, nullptr })
 {
     static std::atomic<int> occ[MAX_DEVICES];          // per device and per instantiation
     const int dev = current_device();
     int blocksPerSM = occ[dev].load(std::memory_order_relaxed);
     if (!blocksPerSM)
     {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT, WIDE>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
         occ[dev].store(blocksPerSM, std::memory_order_relaxed);
     }
     u32 height = width ? (u32)((n + width - 1) / width) : 0;
@@ -729,8 +781,8 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
         BM_CUDA(cudaMemsetAsync(ts.state, 0, TS_OK * 4, s));          // histogram + cursors; OK flag and entry count of the previous launch stay
         BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
     }
-    trace_kernel<MODE, CAMERA, COUNT, WIDE><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
-                                                                            d_counters, d_workCounter, leaf_break(CAMERA ? 0 : queue_depth()), leaf_wait(CAMERA ? 0 : queue_depth()), refill, CAMERA ? 0 : queue_depth(), ts);
+    trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
+                                                                            d_counters, d_workCounter, leaf_break(CAMERA ? 0 : queue_depth()), leaf_wait(CAMERA ? 0 : queue_depth()), refill, CAMERA ? 0 : queue_depth(), ts, seg);
     BM_LAUNCHED();
     if (ts.cost)
     {
@@ -767,6 +819,23 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numR
     if (!n) return BM_OK;
     CameraIn cam = make_camera(nullptr, nullptr, nullptr);
     return dispatch_trace<false>(tv, d_rays, cam, n, d_numRays, 0, mode, d_hits, nullptr, nullptr, d_counters, d_workCounter, nullptr, s);
+}
+
+// the segments of a ray batch (bricks.cu): numSegs slots, each a (ray, brick) pair; results are merged into seg.rayKey
+int trace_segments(const TreeView& tv, const bmRay* d_rays, u64 numSegs, int mode, const SegIn& seg, u64* d_counters, u32* d_workCounter, cudaStream_t s)
+{
+    if (!numSegs) return BM_OK;
+    CameraIn cam = make_camera(nullptr, nullptr, nullptr);
+    const bool wide = use_wide(tv);
+#define BM_SEG_LAUNCH(M, C, W) launch_trace<M, false, C, W, true>(tv, d_rays, cam, numSegs, nullptr, 0, nullptr, nullptr, nullptr, d_counters, d_workCounter, nullptr, s, seg)
+    if (mode == BM_TRACE_REFERENCE)
+    {
+        if (wide) return d_counters ? BM_SEG_LAUNCH(BM_TRACE_REFERENCE, true, true) : BM_SEG_LAUNCH(BM_TRACE_REFERENCE, false, true);
+        return d_counters ? BM_SEG_LAUNCH(BM_TRACE_REFERENCE, true, false) : BM_SEG_LAUNCH(BM_TRACE_REFERENCE, false, false);
+    }
+    if (wide) return d_counters ? BM_SEG_LAUNCH(BM_TRACE_CLOSEST, true, true) : BM_SEG_LAUNCH(BM_TRACE_CLOSEST, false, true);
+    return d_counters ? BM_SEG_LAUNCH(BM_TRACE_CLOSEST, true, false) : BM_SEG_LAUNCH(BM_TRACE_CLOSEST, false, false);
+#undef BM_SEG_LAUNCH
 }
 
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,

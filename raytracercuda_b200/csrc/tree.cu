@@ -86,6 +86,10 @@ struct bmTree
     bool built = false, imported = false;
     // build products
     DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState;
+    DevBuf brickRoots, brickOcc, segKeysA, segKeysB, segValsA, segValsB, rayKey, segCount;      // ray batches traced brick by brick (bricks.cu)
+    int brickBits = 0;               // depth the brick table is valid for (0 = none; reset by every build)
+    int brickMode = -1, brickBitsWanted = 0;      // bmTreeSetBricks: -1 = automatic (BM_BRICKS), 0 = never, 1 = always; bits 0 = default (BM_BRICK_BITS)
+    size_t segCapacity = 0;
     bool stageTiming = false; std::string lastStages;      // bmTreeEnableStageTiming / bmTreeLastBuildStages
     int layout = BM_NODES_BINARY;    // which node records the last build wrote (BM_NODES_*; set by tree_build, or by bmTreeImport)
     u32 schedTiles = 0;              // frame size (in 8x4 tiles) the tile-scheduling buffers are set up for; 0 = none
@@ -113,7 +117,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &wnodes, &nodeMeta, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &wnodes, &nodeMeta, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState, &brickRoots, &brickOcc, &segKeysA, &segKeysB, &segValsA, &segValsB, &rayKey, &segCount };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -150,6 +154,7 @@ static int tree_build(bmTree* t)
     if (T >= 0xFFFFFFFFull) { set_error("more than 2^32-2 triangles"); return BM_ERROR_CAPACITY; }
     t->T = T; t->P = 0; t->L = 0; t->maxLeaf = 0; t->overLeaves = 0;
     t->schedTiles = 0;               // a new scene: forget the tile costs of the old one
+    t->brickBits = 0;                // ... and its brick table
     BM_TRY(t->scalars.reserve(64)); BM_TRY(t->rootDev.reserve(16));
     BM_CUDA(cudaMemsetAsync(t->scalars.p, 0, 64, s));
     BM_CUDA(cudaMemsetAsync(t->rootDev.p, 0, 16, s));
@@ -493,7 +498,7 @@ extern "C" int bmTreeView(const bmTree* src, bmTree** out)
     bmTree* t = new bmTree();
     t->hgrid = src->hgrid; t->dgrid = src->dgrid;
     t->L = src->L; t->P = src->P; t->T = src->T; t->meshBase = src->meshBase; t->maxLeaf = src->maxLeaf; t->overLeaves = src->overLeaves;
-    t->layout = src->layout;
+    t->layout = src->layout; t->brickMode = src->brickMode; t->brickBitsWanted = src->brickBitsWanted;
     if (src->layout != BM_NODES_WIDE) t->nodes.adopt(src->nodes.p, (src->L - (src->L ? 1 : 0)) * 16ull * NODE_F4);
     if (src->layout != BM_NODES_BINARY) t->wnodes.adopt(src->wnodes.p, (src->L - (src->L ? 1 : 0)) * 64ull);
     t->leaves.adopt(src->leaves.p, sz[1]); t->ltris.adopt(src->ltris.p, sz[2]);
@@ -504,11 +509,81 @@ extern "C" int bmTreeView(const bmTree* src, bmTree** out)
     return BM_OK;
 }
 
+// Ray batches against trees far beyond the L2 are traced brick by brick (bricks.cu; same results).  BM_BRICKS=0 never, =1 whenever the
+// tree has at least two leaves; default: traversal arrays above BM_BRICK_MIN_MB (512) and at least 2^18 rays.  BM_BRICK_BITS: depth of the
+// brick grid (default 12 = 16 x 16 x 16 bricks).
+static int brick_bits_for(const bmTree* t, uint64_t numRays)
+{
+    static const int mode = getenv("BM_BRICKS") ? atoi(getenv("BM_BRICKS")) : -1;
+    static const double minMB = getenv("BM_BRICK_MIN_MB") ? atof(getenv("BM_BRICK_MIN_MB")) : 512.0;
+    static const int bitsEnv = getenv("BM_BRICK_BITS") ? atoi(getenv("BM_BRICK_BITS")) : 12;
+    const int m = t->brickMode >= 0 ? t->brickMode : mode;
+    if (m == 0 || t->L < 2 || numRays == 0 || numRays >= 0xFFFFFFF0ull) return 0;
+    if (m < 0)
+    {
+        const double bytes = (double)(t->L - 1) * (t->layout == BM_NODES_BINARY ? 128.0 : 64.0) + (double)t->L * 48.0 + (double)t->P * 56.0;
+        if (bytes < minMB * 1048576.0 || numRays < (1ull << 18)) return 0;
+    }
+    int bits = t->brickBitsWanted ? t->brickBitsWanted : bitsEnv;
+    bits = bits < 3 ? 3 : (bits > BRICK_MAX_BITS ? BRICK_MAX_BITS : bits);
+    if (bits > t->hgrid.D - 1) bits = t->hgrid.D - 1;
+    return bits < 3 ? 0 : bits;
+}
+
+static int trace_bricked(bmTree* t, int bits, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters)
+{
+    cudaStream_t s = t->stream;
+    const TreeView tv = t->view();
+    if (t->brickBits != bits)
+    {
+        BM_TRY(t->brickRoots.reserve((size_t)4 << bits)); BM_TRY(t->brickOcc.reserve((size_t)2 << bits));
+        BM_TRY(brick_table(tv, bits, t->brickRoots.as<u32>(), t->brickOcc.as<unsigned char>(), s));
+        t->brickBits = bits;
+    }
+    BM_TRY(t->segCount.reserve(16)); BM_TRY(t->rayKey.reserve(numRays * 8));
+    size_t want = numRays * 24 + (1u << 20);
+    if (want > t->segCapacity) t->segCapacity = want;
+    unsigned long long S = 0;
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        if (t->segCapacity >= 0xFFFFFFF0ull) t->segCapacity = 0xFFFFFFEFull;
+        const size_t cap = t->segCapacity;
+        BM_TRY(t->segKeysA.reserve(cap * 4)); BM_TRY(t->segKeysB.reserve(cap * 4)); BM_TRY(t->segValsA.reserve(cap * 4)); BM_TRY(t->segValsB.reserve(cap * 4));
+        BM_TRY(brick_segments(tv, bits, t->brickRoots.as<u32>(), t->brickOcc.as<unsigned char>(), d_rays, numRays, mode, t->segKeysA.as<u32>(), t->segValsA.as<u32>(),
+                              (u32)cap, t->segCount.as<unsigned long long>(), s));
+        BM_CUDA(cudaMemcpyAsync(&S, t->segCount.p, 8, cudaMemcpyDeviceToHost, s));
+        BM_CUDA(cudaStreamSynchronize(s));
+        if (S <= cap) break;
+        if (S >= 0xFFFFFFF0ull || attempt == 1) { set_error("ray batch needs more than 2^32 brick segments: split the batch"); return BM_ERROR_CAPACITY; }
+        t->segCapacity = (size_t)S + (S >> 4);
+    }
+    BM_CUDA(cudaMemsetAsync(t->rayKey.p, 0xFF, numRays * 8, s));
+    if (S)
+    {
+        BM_TRY(t->temp.reserve(sort_temp_bytes((size_t)S)));
+        int inB = 0;
+        BM_TRY(radix_sort_pairs(t->segKeysA.as<u32>(), t->segValsA.as<u32>(), t->segKeysB.as<u32>(), t->segValsB.as<u32>(), (size_t)S, bits <= 8 ? 8 : 16, t->temp.p, s, &inB));
+        SegIn seg = { inB ? t->segKeysB.as<u32>() : t->segKeysA.as<u32>(), inB ? t->segValsB.as<u32>() : t->segValsA.as<u32>(), t->brickRoots.as<u32>(),
+                      t->rayKey.as<unsigned long long>() };
+        BM_TRY(trace_segments(tv, d_rays, S, mode, seg, d_counters, t->scalars.as<u32>() + 8, s));
+    }
+    if (d_hits) BM_TRY(brick_resolve(d_rays, numRays, mode, t->rayKey.as<unsigned long long>(), t->soup.as<float4>(), d_hits, s));
+    return BM_OK;
+}
+
+extern "C" int bmTreeSetBricks(bmTree* t, int mode, int bits)
+{
+    if (!t || mode < -1 || mode > 1 || bits < 0 || bits > BRICK_MAX_BITS) return BM_ERROR_INVALID_PARAMETER;
+    t->brickMode = mode; t->brickBitsWanted = bits;
+    return BM_OK;
+}
+
 extern "C" int bmTraceRays(bmTree* t, const bmRay* d_rays, uint64_t numRays, int mode, bmHit* d_hits, uint64_t* d_counters)
 {
     if (!t || (!d_rays && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
     if (!t->built) BM_TRY(tree_build(t));
     BM_TRY(t->scalars.reserve(64));
+    if (const int bits = brick_bits_for(t, numRays)) return trace_bricked(t, bits, d_rays, numRays, mode, d_hits, d_counters);
     return trace_rays(t->view(), d_rays, numRays, nullptr, mode, d_hits, d_counters, t->scalars.as<u32>() + 8, t->stream);
 }
 

@@ -88,6 +88,10 @@ class Tree:
     def enable_stage_timing(self, on=True):
         check(self.L.bmTreeEnableStageTiming(self.h, int(bool(on))), "bmTreeEnableStageTiming")
 
+    def set_bricks(self, mode: int = -1, bits: int = 0):
+        """how trace_rays walks big trees (bmTreeSetBricks): mode -1 automatic, 0 direct traversal, 1 brick by brick; bits = depth of the brick grid"""
+        _lib.check(self.L.bmTreeSetBricks(self.h, mode, bits), "bmTreeSetBricks")
+
     def node_layout(self) -> int:
         """BM_NODES_BINARY (128-byte binary records), BM_NODES_WIDE (64-byte 4-wide records) or BM_NODES_BOTH"""
         v = C.c_uint32(0)

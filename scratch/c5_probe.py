@@ -5,13 +5,14 @@ import torch
 from raytracercuda_b200 import synth, _lib
 from raytracercuda_b200.tree import Tree
 ap = argparse.ArgumentParser(); ap.add_argument("--mtris", type=float, default=20); ap.add_argument("--mrays", type=float, default=8)
-ap.add_argument("--modes", default="0"); ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--modes", default="0"); ap.add_argument("--bricks", type=int, default=-1); ap.add_argument("--bits", type=int, default=0); ap.add_argument("--reps", type=int, default=1)
 a = ap.parse_args()
 dev = "cuda:0"
 T = int(a.mtris * 1e6); n = int(a.mrays * 1e6)
 P, I = synth.soup_torch(T, dev)
 t = Tree(dev); t.add_mesh(P, I); t.build(); torch.cuda.synchronize()
 print(t.stats(), flush=True)
+t.set_bricks(a.bricks, a.bits)
 R = synth.incoherent_rays_torch(n, dev)
 hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
 for mode in [int(x) for x in a.modes.split(",")]:

@@ -416,3 +416,53 @@ def test_tiled_ray_batches_equal_plain_batches(meshes, beam_lib, cuda_device):
     assert int(cnt.cpu()[0]) > n
     assert L.bmTraceRaysTiled(t.h, rays.data_ptr(), n, 0, 0, b.data_ptr(), None) == 2 and L.bmTraceRaysTiled(t.h, rays.data_ptr(), n, 11, 0, b.data_ptr(), None) == 2      # 301 * 203 is not a multiple of 11
     t.close()
+
+
+@pytest.mark.parametrize("layout", ["binary", "wide"])
+def test_bricked_ray_batches_equal_the_direct_traversal(layout, meshes, oracle_lib, beam_lib, cuda_device, monkeypatch):
+    """bmTreeSetBricks: a batch cut into (ray, brick) segments, sorted by brick and merged per ray must give the hits of the direct
+    traversal bit for bit -- both modes, both node layouts, several brick depths (also depths that are no multiple of 3 and bricks smaller
+    than the populated region), rays with axis-parallel components, origins inside populated cells, a replica made by export/import --
+    and agree with the oracle like the direct traversal does."""
+    import ctypes as C
+    import torch
+    from raytracercuda_b200.tree import Tree, hits_to_numpy
+    monkeypatch.setenv("BM_NODE_LAYOUT", layout)
+    rng = np.random.default_rng(21)
+    Ps, Is = random_soup(rng, 40000, 6.0, 0.08)
+    scenes = [("soup", Ps, Is, None, 6.5), ("bunny", *meshes["bunny"], 2.5)]
+    for name, P, I, N, ext in scenes:
+        t = Tree(cuda_device); t.add_mesh(P, I); t.build()
+        R = _ray_batch(rng, 120000, ext)
+        R[::7, :3] *= 3.0                                  # origins far outside the populated region too
+        Rd = torch.from_numpy(R).to(cuda_device)
+        s = OracleScene(oracle_lib); s.add_mesh(P, I, N); s.build(NT)
+        for mode in (0, 1):
+            t.set_bricks(0)
+            a, ca = t.trace_rays(Rd, mode, counters=True)
+            a = hits_to_numpy(a)
+            r = s.trace_rays(R[:, :3], R[:, 3:], mode, NT)
+            _compare(a, r, t.mesh_bases(), what=f"{name} direct mode {mode}")
+            for bits in (3, 6, 10, 12, 15):
+                t.set_bricks(1, bits)
+                b, cb = t.trace_rays(Rd, mode, counters=True)
+                b = hits_to_numpy(b)
+                for k in ("tri", "t", "u", "v"):
+                    assert np.array_equal(a[k], b[k]), f"{name} {layout} mode {mode} bits {bits}: {k} differs on {(a[k] != b[k]).sum()} rays"
+                assert cb[0].item() > 0
+        # a replica (imported arrays) finds its bricks by itself
+        sz = (C.c_uint64 * 8)(); assert beam_lib.bmTreeArraySizes(t.h, sz) == 0
+        bufs = [torch.empty(max(int(x), 16), dtype=torch.uint8, device=cuda_device) for x in sz[:5]]
+        assert beam_lib.bmTreeExport(t.h, *[x.data_ptr() for x in bufs]) == 0
+        torch.cuda.synchronize()
+        h = C.c_void_p(); wmin, wmax, min_leaf, max_depth = t.world()
+        assert beam_lib.bmTreeImport(C.byref(h), *[x.data_ptr() for x in bufs], sz[5], sz[6], sz[7], t.root(), t.node_layout(), wmin.ctypes.data, wmax.ctypes.data,
+                                     min_leaf, max_depth) == 0
+        assert beam_lib.bmTreeSetBricks(h, 1, 9) == 0
+        hits = torch.empty((R.shape[0], 4), dtype=torch.float32, device=cuda_device)
+        assert beam_lib.bmTraceRays(h, Rd.data_ptr(), R.shape[0], 1, hits.data_ptr(), None) == 0
+        b = hits_to_numpy(hits)
+        assert np.array_equal(a["tri"], b["tri"]) and np.array_equal(a["t"], b["t"])
+        beam_lib.bmTreeDestroy(h)
+        t.close(); s.close()
+    assert beam_lib.bmTreeSetBricks(None, 0, 0) != 0
