@@ -176,7 +176,36 @@ def bind_near_gpu(index):
     return "unavailable"
 
 
+def orbit_pose(eye0, degrees):
+    """camera on a circle about the y axis looking at the origin: (eye, orient) with orient in glm's column-major order (m[3*col+row])"""
+    a = np.radians(float(degrees)); c, s_ = float(np.cos(a)), float(np.sin(a))
+    R = np.array([[c, 0.0, s_], [0.0, 1.0, 0.0], [-s_, 0.0, c]], np.float32)
+    return (R @ np.asarray(eye0, np.float32)).astype(np.float32), np.ascontiguousarray(R.T).reshape(-1)
+
+
+def profile_entry(name):
+    """numbers of a committed ncu capture (profiles/traffic.json): DRAM / L2 bytes and warp instructions per launch of a named kernel"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+    except Exception:
+        return None
+
+
+def l2_copy_peak(torch, dev):
+    """L2 bandwidth this GPU delivers to a plain copy whose 2 x 24 MiB working set stays in the cache (read + write bytes, best of 20)"""
+    a = torch.empty(24 << 20, dtype=torch.uint8, device=dev); b = torch.empty_like(a)
+    best = 1e30
+    for _ in range(3):
+        b.copy_(a)
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); b.copy_(a); e1.record(); torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    return 2 * a.numel() / (best * 1e-3) / 1e9
+
+
 def run_b200(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
@@ -200,16 +229,31 @@ def run_b200(args):
     from raytracercuda_b200.tree import Tree, make_mesh_table
     L = _lib.load()
     wl = workloads.get(args.workload)
-    W, H = wl.width, wl.height
+    SPP = wl.samples
+    # weak scaling (default; the driver's 1 -> 8 run): every rank renders a full-size image = interleaved rows of an N-times taller one.
+    # strong scaling (--scaling strong; default for the multi-sample c3 / c4 frames): ONE frame of the workload's size, rank r renders rows
+    # r, r + N, ... of it (interleaved rows = image tiles 1 row high: every rank sees the same mix of silhouette and background)
+    strong = (args.scaling == "strong") or (args.scaling == "auto" and SPP > 1)
+    W = wl.width
+    if strong and wl.height % world:
+        raise SystemExit("--scaling strong needs the image height to be a multiple of the GPU count")
+    H = wl.height // world if strong else wl.height
     n = W * H
-    eye = wl.eye; orient = np.eye(3, dtype=np.float32)
+    eye0 = np.asarray(wl.eye, np.float32)
     frustum = workloads.interleaved_rows_frustum(wl.frustum, H, rank, world)
+    moving = SPP == 1 and args.orbit_deg != 0.0          # the headline frame orbits the scene; multi-sample frames accumulate a static view
+    _f3 = lambda a: (C.c_float * 3)(*[float(x) for x in a])
+    _f9 = lambda a: (C.c_float * 9)(*[float(x) for x in np.asarray(a, np.float32).reshape(-1)])
+
+    def pose(i, orbit=True):
+        e, o = orbit_pose(eye0, args.orbit_deg * i if (orbit and moving) else 0.0)
+        return _f3(e), _f9(o), e, o
 
     # --- scene + camera resident on the device -------------------------------------------------------------------------
     cam = host.ICamera.create()
     assert cam.setInitialRays(W, H, *frustum) == 0
-    rays_pinned = torch.from_numpy(cam.initialRays()).pin_memory()
-    rays_dev = rays_pinned.to(dev)
+    rays_host = cam.initialRays()
+    rays_dev = torch.from_numpy(rays_host).to(dev)
     Pd = torch.from_numpy(wl.positions).to(dev); Id = torch.from_numpy(wl.indices.view(np.int32)).to(dev).reshape(-1); Nd = torch.from_numpy(wl.normals).to(dev)
     table = make_mesh_table([(Pd, Id, Nd)], dev)
     stream = torch.cuda.current_stream(dev)
@@ -223,39 +267,78 @@ def run_b200(args):
         build_once()
     from raytracercuda_b200.dist import replicate_tree
     tree = replicate_tree(built, dev, 0)
+    stat_keys = ("triangles", "pairs", "leaves", "nodes", "depth", "max_leaf_faces", "overflow_leaves", "meshes")
     stats_t = torch.zeros(8, dtype=torch.int64, device=dev)
     if rank == 0:
         s0 = built.stats()
-        stats_t.copy_(torch.tensor([s0[k] for k in ("triangles", "pairs", "leaves", "nodes", "depth", "max_leaf_faces", "overflow_leaves", "meshes")]))
+        stats_t.copy_(torch.tensor([s0[k] for k in stat_keys]))
     if world > 1:
         dist.broadcast(stats_t, 0)
-    st = dict(zip(("triangles", "pairs", "leaves", "nodes", "depth", "max_leaf_faces", "overflow_leaves", "meshes"), [int(x) for x in stats_t.cpu()]))
+    st = dict(zip(stat_keys, [int(x) for x in stats_t.cpu()]))
     hits1 = torch.empty((n, 4), dtype=torch.float32, device=dev); pixels = torch.empty(n, dtype=torch.int32, device=dev)
-    rays1 = torch.empty((n, 6), dtype=torch.float32, device=dev); rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev)
     src2 = torch.empty(n, dtype=torch.int32, device=dev); cnt2 = torch.zeros(1, dtype=torch.int32, device=dev)
     hits2 = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world, n), dtype=torch.int32, device=dev) if world > 1 else None
-    comm = torch.cuda.Stream(dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    pix_host = torch.empty(n, dtype=torch.int32).pin_memory(); hits2_host = torch.empty((n, 4), dtype=torch.float32).pin_memory()
     cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    SPP = wl.samples
     jit = (abs(wl.frustum[1] - wl.frustum[0]) / W / wl.frustum[4], abs(frustum[3] - frustum[2]) / H / wl.frustum[4])
     acc = torch.zeros(n, dtype=torch.float32, device=dev) if SPP > 1 else None
     cov = torch.zeros(n, dtype=torch.int32, device=dev) if SPP > 1 else None
     cnt_sum = torch.zeros(1, dtype=torch.int64, device=dev)
 
-    def frame_spp(rays_in):
+    # --- the framebuffer of all ranks on every rank -----------------------------------------------------------------------
+    # Preferred: symmetric memory -- every rank writes its rows straight into each peer's copy of the gathered frame with copy-engine
+    # transfers over NVLink (no SM is taken from the persistent trace grids); fallback: NCCL all-gather on a side stream.
+    gathered, comm, symm = None, None, None
+    if world > 1:
+        comm = torch.cuda.Stream(dev)
+        if not os.environ.get("BENCH_NO_SYMM"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                gathered = symm_mem.empty((world, n), dtype=torch.int32, device=dev)
+                hdl = symm_mem.rendezvous(gathered, dist.group.WORLD)
+                peers = [hdl.get_buffer(r_, (world, n), torch.int32) for r_ in range(world)]
+                symm = (hdl, peers)
+                # prove the path once against NCCL
+                probe = torch.full((n,), rank + 1, dtype=torch.int32, device=dev)
+                for r_ in range(world):
+                    peers[r_][rank].copy_(probe, non_blocking=True)
+                torch.cuda.synchronize(dev); dist.barrier(); torch.cuda.synchronize(dev)
+                want = torch.arange(1, world + 1, dtype=torch.int32, device=dev)
+                if not bool((gathered[:, 0] == want).all()) or not bool((gathered[:, -1] == want).all()):
+                    raise RuntimeError("symmetric-memory gather check failed")
+            except Exception as ex:
+                sys.stderr.write("rank %d: symmetric-memory gather unavailable (%r): NCCL all-gather\n" % (rank, ex))
+                symm = None
+        ok_t = torch.tensor([1 if symm is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        if int(ok_t.item()) == 0:
+            symm = None
+            gathered = torch.empty((world, n), dtype=torch.int32, device=dev)
+
+    def gather_frame(src_pixels, after_event):
+        """issue the gather of this rank's rows on the side stream once `after_event` has passed; returns a callable that makes the compute stream wait for it"""
+        with torch.cuda.stream(comm):
+            comm.wait_event(after_event)
+            if symm is not None:
+                for k in range(world):
+                    r_ = (rank + k) % world
+                    symm[1][r_][rank].copy_(src_pixels, non_blocking=True)
+                done = torch.cuda.Event(); done.record(comm)
+                return lambda: stream.wait_event(done)
+            work = dist.all_gather_into_tensor(gathered.view(-1), src_pixels, async_op=True)
+            return work.wait
+
+    def frame_spp(rays_in, p):
         """multi-sample frame (configs 3 and 4): per sample jittered camera rays -> trace -> bounce rays -> trace -> accumulate; resolve"""
         acc.zero_(); cov.zero_(); cnt_sum.zero_()
         sp = C.c_void_p(stream.cuda_stream)
         for sidx in range(SPP):
             # the sample's jitter is applied where the trace kernel forms the ray (no 24-byte ray record per sample is written or read);
             # the launch is a camera launch: 8x4 tiles under the temporal tile schedule
-            _lib.check(L.bmTraceCameraJittered(tree.h, rays_in.data_ptr(), n, W, _f3(eye), _f9(orient), jit[0], jit[1], sidx, args.seed, 0, hits1.data_ptr(), None, None, None), "bmTraceCameraJittered")
-            _lib.check(L.bmBounceRaysCameraJittered(tree.h, rays_in.data_ptr(), _f3(eye), _f9(orient), jit[0], jit[1], sidx, args.seed, hits1.data_ptr(), n, sidx, 1, args.seed,
+            _lib.check(L.bmTraceCameraJittered(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], jit[0], jit[1], sidx, args.seed, 0, hits1.data_ptr(), None, None, None), "bmTraceCameraJittered")
+            _lib.check(L.bmBounceRaysCameraJittered(tree.h, rays_in.data_ptr(), p[0], p[1], jit[0], jit[1], sidx, args.seed, hits1.data_ptr(), n, sidx, 1, args.seed,
                                                     rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCameraJittered")
             _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRaysIndirect")
             _lib.check(L.bmProgressiveAccumulate(hits1.data_ptr(), n, hits2.data_ptr(), src2.data_ptr(), cnt2.data_ptr(), 0.25, acc.data_ptr(), cov.data_ptr(), sp), "accumulate")
@@ -263,65 +346,38 @@ def run_b200(args):
         _lib.check(L.bmProgressiveResolve(acc.data_ptr(), cov.data_ptr(), n, SPP, pixels.data_ptr(), sp), "resolve")
         cnt_host.copy_(cnt_sum.to(torch.int32), non_blocking=True)
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), pixels)
+            e_ = torch.cuda.Event(); e_.record(stream)
+            gather_frame(pixels, e_)()
         return n * SPP
 
-    # The frame is issued as NB row bands on NB streams (each through its own view of the tree): the traversal kernels are persistent
-    # grids with a long tail (a few grazing rays), and the tail of one band is filled by the other bands' work.  NB = 1 is one launch.
-    NB = args.bands if (SPP == 1 and H % args.bands == 0) else 1
-    nbnd = n // NB
-    band_streams = [torch.cuda.Stream(dev) for _ in range(NB)] if NB > 1 else [stream]
-    band_trees = [tree.view(band_streams[k]) for k in range(NB)] if NB > 1 else [tree]
-    cntb = torch.zeros(NB, dtype=torch.int32, device=dev); cntb_host = torch.zeros(NB, dtype=torch.int32).pin_memory()
-
-    def frame(rays_in, marks=None, out=None):
+    def frame(rays_in, p, marks=None):
         """one step on the device; returns the primary rays traced by this rank (bounce rays are added by bounce_count())"""
         if SPP > 1:
             if marks is not None:
                 for m_ in marks: m_.record()
-            return frame_spp(rays_in)
-        o_hits1, o_pixels, o_rays2, o_src2, o_hits2, o_cnt, o_cnt_host = out if out is not None else (hits1, pixels, rays2, src2, hits2, cntb, cntb_host)
+            return frame_spp(rays_in, p)
         if marks is not None: marks[0].record()
-        ev0 = torch.cuda.Event(); ev0.record(stream)
-        prim_done = []
-        for k in range(NB):
-            lo = k * nbnd; bs = band_streams[k]; bt = band_trees[k]
-            if NB > 1: bs.wait_event(ev0)
-            _lib.check(L.bmTraceCamera(bt.h, rays_in.data_ptr() + lo * 12, nbnd, W, _f3(eye), _f9(orient), 0, o_hits1.data_ptr() + lo * 16, o_pixels.data_ptr() + lo * 4,
-                                       table.data_ptr(), None), "bmTraceCamera")
-            if marks is not None and NB == 1: marks[1].record()
-            if world > 1:
-                e_ = torch.cuda.Event(); e_.record(bs); prim_done.append(e_)
-            if wl.bounces:
-                _lib.check(L.bmBounceRaysCamera(bt.h, rays_in.data_ptr() + lo * 12, _f3(eye), _f9(orient), o_hits1.data_ptr() + lo * 16, nbnd, 0, 1, args.seed,
-                                                o_rays2.data_ptr() + lo * 24, o_src2.data_ptr() + lo * 4, o_cnt.data_ptr() + k * 4), "bmBounceRaysCamera")
-                if marks is not None and NB == 1: marks[2].record()
-                # the bounce count stays on the device: the trace kernel reads it there (no host round trip inside the step)
-                _lib.check(L.bmTraceRaysIndirect(bt.h, o_rays2.data_ptr() + lo * 24, o_cnt.data_ptr() + k * 4, nbnd, BOUNCE_MODE, o_hits2.data_ptr() + lo * 16, None), "bmTraceRaysIndirect")
-            if NB > 1:
-                e_ = torch.cuda.Event(); e_.record(bs); stream.wait_event(e_)
-        work = None
+        _lib.check(L.bmTraceCamera(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+        if marks is not None: marks[1].record()
+        wait = None
         if world > 1:
-            # the framebuffer is final once the primary launches are done: gather it on a side stream while the bounce rays are traced
-            with torch.cuda.stream(comm):
-                for e_ in prim_done: comm.wait_event(e_)
-                work = dist.all_gather_into_tensor(gathered.view(-1), o_pixels, async_op=True)
+            # the framebuffer is final once the primary launch is done: gather it on a side stream while the bounce rays are traced
+            e_ = torch.cuda.Event(); e_.record(stream)
+            wait = gather_frame(pixels, e_)
         if wl.bounces:
-            o_cnt_host.copy_(o_cnt, non_blocking=True)
+            _lib.check(L.bmBounceRaysCamera(tree.h, rays_in.data_ptr(), p[0], p[1], hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
+            if marks is not None: marks[2].record()
+            # the bounce count stays on the device: the trace kernel reads it there (no host round trip inside the step)
+            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRaysIndirect")
+            cnt_host.copy_(cnt2, non_blocking=True)
         if marks is not None: marks[3].record()
-        if work is not None:
-            work.wait()                    # the step ends when the gathered frame is complete
+        if wait is not None:
+            wait()                         # the step ends when the gathered frame is complete
         return n
 
     def bounce_count():
         stream.synchronize()
-        if SPP > 1:
-            return int(cnt_host[0]) if wl.bounces else 0
-        return int(cntb_host.sum()) if wl.bounces else 0
-
-    import ctypes as C
-    _f3 = lambda a: (C.c_float * 3)(*[float(x) for x in a])
-    _f9 = lambda a: (C.c_float * 9)(*[float(x) for x in np.asarray(a, np.float32).reshape(-1)])
+        return int(cnt_host[0]) if wl.bounces else 0
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -329,206 +385,132 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    def timed_steps(K, first_frame, orbit):
+        """K steps, L2 flushed before each, every step bracketed by a synchronise; returns (ms per step max over ranks, Mrays/s of all ranks, per-launch marks)"""
+        step_ms, prim_ms, bounce_ms = [], [], []
+        total_rays = 0
+        for k in range(K):
+            flush.zero_()
+            marks = [ev() for _ in range(4)]; e0, e1 = ev(), ev()
+            sync_all()
+            e0.record()
+            total_rays += frame(rays_dev, pose(first_frame + k, orbit), marks)
+            e1.record()
+            sync_all()
+            total_rays += bounce_count()
+            step_ms.append(e0.elapsed_time(e1)); prim_ms.append(marks[0].elapsed_time(marks[1]))
+            bounce_ms.append(marks[2].elapsed_time(marks[3]) if wl.bounces else 0.0)
+        t_sum = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev); r_sum = torch.tensor([float(total_rays)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_sum, op=dist.ReduceOp.MAX); dist.all_reduce(r_sum, op=dist.ReduceOp.SUM)
+        ms = float(t_sum.item()) / K
+        return ms, float(r_sum.item()) / K / (ms * 1e-3) / 1e6, statistics.mean(prim_ms), statistics.mean(bounce_ms)
+
     # --- warm-up -------------------------------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        rays_step = frame(rays_dev) + bounce_count()
-    # per-ray traversal counters of the same traversal (instrumented launch, outside the timed region)
-    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
-    _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
-    torch.cuda.synchronize(dev)
-    V1, K1, C1, LONG1 = [int(x) for x in cnt.cpu()]
-    def whole_frame_bounce_list():
-        """the frame's bounce rays as ONE compacted list in rays2 / src2 (the banded step leaves one list per band)"""
-        _lib.check(L.bmBounceRaysCamera(tree.h, rays_dev.data_ptr(), _f3(eye), _f9(orient), hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(),
-                                        src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
-        torch.cuda.synchronize(dev)
-        return int(cnt2.cpu()[0])
-    if SPP == 1:
-        nb = whole_frame_bounce_list() if wl.bounces else 0
-        assert nb == (int(cntb_host.sum()) if wl.bounces else 0), "band lists and the whole-frame list disagree"
-    else:
-        nb = int(cnt_host[0]) if wl.bounces else 0
-    V2 = K2 = C2 = 0
-    nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST sample only
-    if nb_last and SPP == 1:
-        cnt.zero_()
-        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, BOUNCE_MODE, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
-        torch.cuda.synchronize(dev)
-        V2, K2, C2, LONG2 = [int(x) for x in cnt.cpu()]
+    WU = max(args.warmup, 3)
+    for k in range(WU):
+        rays_step = frame(rays_dev, pose(k - WU)) + bounce_count()
 
     # --- timed: K steps, device resident, L2 flushed between steps --------------------------------------------------------
     sampler = ClockSampler(local)
     launches0 = L.bmLaunchCount()
     sync_all()
     sampler.start()
-    step_ms, prim_ms, bounce_ms = [], [], []
-    total_rays = 0
-    for _ in range(args.steps):
-        flush.zero_()
-        marks = [ev() for _ in range(4)]; e0, e1 = ev(), ev()
-        sync_all()
-        e0.record()
-        total_rays += frame(rays_dev, marks)
-        e1.record()
-        sync_all()
-        total_rays += bounce_count()
-        step_ms.append(e0.elapsed_time(e1)); prim_ms.append(marks[0].elapsed_time(marks[1]) if (NB == 1 or SPP > 1) else 0.0)
-        bounce_ms.append(marks[2].elapsed_time(marks[3]) if (wl.bounces and (NB == 1 or SPP > 1)) else 0.0)
+    ms_per_step, value, prim_moving_ms, bounce_moving_ms = timed_steps(args.steps, 0, True)
     clocks = sampler.stop()
     launches = L.bmLaunchCount() - launches0
-    # max over ranks of the summed step time; rays summed over ranks
-    t_sum = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev); r_sum = torch.tensor([float(total_rays)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_sum, op=dist.ReduceOp.MAX); dist.all_reduce(r_sum, op=dist.ReduceOp.SUM)
-    ms_per_step = float(t_sum.item()) / args.steps
-    value = float(r_sum.item()) / args.steps / (ms_per_step * 1e-3) / 1e6
+    static = None
+    if moving:
+        for k in range(3):
+            frame(rays_dev, pose(0, False)); bounce_count()
+        s_ms, s_val, s_prim, s_bounce = timed_steps(args.steps, 0, False)
+        static = {"value": s_val, "unit": "Mrays/s", "ms_per_step": s_ms, "primary_launch_ms": s_prim, "bounce_launch_ms": s_bounce,
+                  "note": "same step with the camera at rest: every frame repeats the previous one, the best case for the temporal tile schedule"}
+    # per-ray traversal counters of the static frame (instrumented launches, outside the timed region)
+    p0 = pose(0, False)
+    for k in range(2):
+        rays_static = frame(rays_dev, p0) + bounce_count()
+    nb = bounce_count() if SPP == 1 else int(cnt_host[0])
+    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+    _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, p0[0], p0[1], 0, hits1.data_ptr(), None, None, cnt.data_ptr()), "bmTraceCamera")
+    torch.cuda.synchronize(dev)
+    V1, K1, C1, LONG1 = [int(x) for x in cnt.cpu()]
+    V2 = K2 = C2 = 0
+    nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST sample only
+    if nb_last:
+        cnt.zero_()
+        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, BOUNCE_MODE, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+        torch.cuda.synchronize(dev)
+        V2, K2, C2, LONG2 = [int(x) for x in cnt.cpu()]
 
-    # --- timed: e2e through host buffers ---------------------------------------------------------------------------------
-    # Every step: the camera table comes from pinned host memory (H2D), the framebuffer, the bounce count and the bounce hit records go
-    # back to pinned host memory (D2H).  Frames are pipelined the way a renderer streams them: DEPTH buffer sets, three streams -- the
-    # upload of frame i+1 and the download of frame i-1 run while frame i is traced.  The K steps are timed as one bracket (fill and
-    # drain included); the latency of one un-pipelined frame is reported beside it.  The L2 flush runs inside the compute stream.
-    DEPTH = 3
-    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    slots = []
-    for _ in range(DEPTH if SPP == 1 else 0):
-        slots.append({"rays": torch.empty_like(rays_dev), "hits1": torch.empty_like(hits1), "pixels": torch.empty_like(pixels), "rays2": torch.empty_like(rays2),
-                      "src2": torch.empty_like(src2), "cnt": torch.zeros(NB, dtype=torch.int32, device=dev), "hits2": torch.empty_like(hits2),
-                      "pix_host": torch.empty(n, dtype=torch.int32).pin_memory(), "hits2_host": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
-                      "cnt_host": torch.zeros(NB, dtype=torch.int32).pin_memory(), "cnt_scratch": torch.zeros(NB, dtype=torch.int32).pin_memory(),
-                      "ev_comp": None, "ev_d2h": None, "ev_cnt": None})
+    # --- timed: e2e through the reference-facing host classes (include/beam_host_c.h) ---------------------------------------------
+    # What a Beam program does per frame: ICamera::traceSceneProgressive (c1: traceScene) with this frame's eye / orientation -- the camera's
+    # direction table was uploaded ONCE by setInitialRays, as in the reference (Camera.cpp:43-72, 85-97) -- then IRenderTarget::readPixels into
+    # pinned host memory.  Two render targets: the read-back of frame i-1 (copy stream) overlaps the kernels of frame i.  The scene was
+    # uploaded from HOST arrays through IMesh::setVertexData / setIndices and built by IScene::updateGPUScene.  The K frames are ONE bracket.
+    hs = torch.cuda.ExternalStream(int(L.beamHostStream()), device=dev)
+    scene = host.IScene.create(); mesh = host.IMesh.create()
+    assert mesh.setVertexData(wl.positions, wl.positions.shape[0], 3, host.VERTEX_DATA_POSITION) == 0
+    assert mesh.setVertexData(wl.normals, wl.normals.shape[0], 3, host.VERTEX_DATA_NORMAL) == 0
+    assert mesh.setIndices(wl.indices.reshape(-1), wl.indices.size) == 0
+    scene.addMesh(mesh); scene.updateGPUScene()
+    rts = [host.IRenderTarget.createHeadless(W, H) for _ in range(2)]
+    pix_pinned = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    rays_pinned = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
+    sticky0 = L.bmStickyError()
 
-    def e2e_upload(i):
-        """camera table of frame i, host -> device (asynchronous; issued two frames ahead so that it never gates the kernels)"""
-        S = slots[i % DEPTH]
-        with torch.cuda.stream(s_h2d):
-            if S["ev_comp"] is not None:
-                s_h2d.wait_event(S["ev_comp"])              # the previous frame in this slot has consumed its ray table
-            S["rays"].copy_(rays_pinned, non_blocking=True)
-            S["ev_h2d"] = torch.cuda.Event(); S["ev_h2d"].record(s_h2d)
+    def e2e_frame(i, p):
+        rt = rts[i % 2]
+        assert rt.lock() == 0
+        with torch.cuda.stream(hs):
+            flush.zero_()                                  # the L2 flush sits inside the host classes' stream, before the frame's kernels
+        if wl.bounces or SPP > 1:
+            err = L.beamCameraTraceSceneProgressive(cam.h, p[2].ctypes.data, p[3].ctypes.data, scene.h, SPP, args.seed, C.cast(rays_pinned[i % 2].data_ptr(), C.POINTER(C.c_uint64)))
+        else:
+            err = L.beamCameraTraceScene(cam.h, p[2].ctypes.data, p[3].ctypes.data, scene.h)
+            rays_pinned[i % 2][0] = n
+        assert err == 0, err
+        assert rt.unlock() == 0
 
-    e2e_graphs = None                                       # one CUDA graph per buffer set (filled in below): L2 flush + the frame's launches
+    def e2e_read(i):
+        err = L.beamRenderTargetReadPixels(rts[i % 2].h, pix_pinned[i % 2].data_ptr())
+        assert err == 0, err
+        return int(rays_pinned[i % 2][0])
 
-    def frame_calls(S):
-        """the frame's three C-ABI calls on buffer set S (single GPU, one band): what the per-slot CUDA graph captures"""
-        _lib.check(L.bmTraceCamera(tree.h, S["rays"].data_ptr(), n, W, _f3(eye), _f9(orient), 0, S["hits1"].data_ptr(), S["pixels"].data_ptr(), table.data_ptr(), None), "bmTraceCamera")
-        if wl.bounces:
-            _lib.check(L.bmBounceRaysCamera(tree.h, S["rays"].data_ptr(), _f3(eye), _f9(orient), S["hits1"].data_ptr(), n, 0, 1, args.seed, S["rays2"].data_ptr(),
-                                            S["src2"].data_ptr(), S["cnt"].data_ptr()), "bmBounceRaysCamera")
-            _lib.check(L.bmTraceRaysIndirect(tree.h, S["rays2"].data_ptr(), S["cnt"].data_ptr(), n, BOUNCE_MODE, S["hits2"].data_ptr(), None), "bmTraceRaysIndirect")
-
-    def e2e_compute(i):
-        """kernels of frame i (asynchronous)"""
-        S = slots[i % DEPTH]
-        with torch.cuda.stream(stream):
-            stream.wait_event(S["ev_h2d"])
-            if S["ev_d2h"] is not None:
-                stream.wait_event(S["ev_d2h"])              # ... and its results have left the device
-            if e2e_graphs is not None:
-                e2e_graphs[i % DEPTH].replay()
-            else:
-                flush.zero_()
-                frame(S["rays"], None, out=(S["hits1"], S["pixels"], S["rays2"], S["src2"], S["hits2"], S["cnt"], S["cnt_scratch"]))
-            S["ev_comp"] = torch.cuda.Event(); S["ev_comp"].record(stream)
-
-    def e2e_download(i):
-        """framebuffer + bounce count of frame i to the host (asynchronous)"""
-        S = slots[i % DEPTH]
-        with torch.cuda.stream(s_d2h):
-            s_d2h.wait_event(S["ev_comp"])
-            S["pix_host"].copy_(S["pixels"], non_blocking=True)
-            S["cnt_host"].copy_(S["cnt"], non_blocking=True)
-            S["ev_cnt"] = torch.cuda.Event(); S["ev_cnt"].record(s_d2h)
-
-    def e2e_finish(i):
-        """host side of frame i: wait for its bounce count, fetch exactly that many hit records; returns the rays of the frame"""
-        S = slots[i % DEPTH]
-        S["ev_cnt"].synchronize()
-        total = n
-        with torch.cuda.stream(s_d2h):
-            for k in range(NB if wl.bounces else 0):
-                c = int(S["cnt_host"][k]); lo = k * nbnd
-                total += c
-                if c:
-                    S["hits2_host"][lo:lo + c].copy_(S["hits2"][lo:lo + c], non_blocking=True)
-            S["ev_d2h"] = torch.cuda.Event(); S["ev_d2h"].record(s_d2h)
-        return total
-
-    def e2e_run(K):
+    def e2e_run(K, first):
         total = 0
-        for i in range(min(2, K)):
-            e2e_upload(i)
+        poses = [pose(first + i) for i in range(K)]
         for i in range(K):
-            e2e_compute(i)
-            if i + 2 < K:
-                e2e_upload(i + 2)
+            e2e_frame(i, poses[i])
             if i:
-                total += e2e_finish(i - 1)
-            e2e_download(i)
-        total += e2e_finish(K - 1)
-        stream.wait_event(slots[(K - 1) % DEPTH]["ev_d2h"])
+                total += e2e_read(i - 1)
+        total += e2e_read(K - 1)
         return total
 
-    def frame_e2e_spp():
-        e2e_rays_dev.copy_(rays_pinned, non_blocking=True)
-        total = frame_spp(e2e_rays_dev)
-        pix_host.copy_(pixels, non_blocking=True)
-        stream.synchronize()
-        return total + int(cnt_host[0])
-
-    e2e_rays = 0
-    if SPP == 1:
-        e2e_run(DEPTH + 1)                                   # warm-up (allocations, all slots touched)
-        if world == 1 and NB == 1 and not args.no_e2e_graph:
-            # the launch sequence of a frame is fixed: captured once per buffer set, replayed as one graph launch per frame
-            try:
-                torch.cuda.synchronize(dev)
-                graphs_ = []
-                for S in slots:
-                    g_ = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g_):
-                        tree.use_stream(torch.cuda.current_stream(dev))
-                        flush.zero_()
-                        frame_calls(S)
-                    graphs_.append(g_)
-                tree.use_stream(stream)
-                e2e_graphs = graphs_
-                e2e_run(DEPTH + 1)
-            except Exception as ex:                          # keep the run alive; the line says which path ran
-                sys.stderr.write("e2e: CUDA graph capture failed (%r): direct launches\n" % (ex,))
-                e2e_graphs = None
-                tree.use_stream(stream)
-        lat = []
-        for _ in range(3):                                   # latency of one frame on its own
-            e0, e1 = ev(), ev(); sync_all(); e0.record(); e2e_run(1); e1.record(); sync_all(); lat.append(e0.elapsed_time(e1))
-        e0, e1 = ev(), ev()
-        sync_all()
-        e0.record(); e2e_rays = e2e_run(args.steps); e1.record()
-        sync_all()
-        e2e_total_ms = e0.elapsed_time(e1)
-        e2e_latency_ms = statistics.mean(lat)
-    else:
-        e2e_rays_dev = torch.empty_like(rays_dev)
-        for _ in range(2):
-            frame_e2e_spp()
-        e2e_total_ms = 0.0
-        for _ in range(args.steps):
-            flush.zero_()
-            e0, e1 = ev(), ev()
-            sync_all()
-            e0.record(); e2e_rays += frame_e2e_spp(); e1.record()
-            sync_all()
-            e2e_total_ms += e0.elapsed_time(e1)
-        e2e_latency_ms = e2e_total_ms / args.steps
+    e2e_run(3, -3)
+    lat = []
+    for k in range(3):                                       # latency of one frame on its own
+        e0, e1 = ev(), ev(); sync_all(); e0.record(hs); e2e_run(1, k); e1.record(hs); sync_all(); lat.append(e0.elapsed_time(e1))
+    e0, e1 = ev(), ev()
+    sync_all()
+    e0.record(hs); e2e_rays = e2e_run(args.steps, 0); e1.record(hs)
+    sync_all()
+    e2e_total_ms = e0.elapsed_time(e1)
+    e2e_latency_ms = statistics.mean(lat)
+    assert L.bmStickyError() == sticky0
     t2 = torch.tensor([e2e_total_ms], dtype=torch.float64, device=dev); r2 = torch.tensor([float(e2e_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
     e2e_value = float(r2.item()) / (float(t2.item()) * 1e-3) / 1e6
-    h2d = n * 12
-    d2h = n * 4 + 4 * NB + (nb * 16 if (wl.bounces and SPP == 1) else 0)
+    # the e2e frame of a static pose must show the pixels of the device-timed path (same kernels behind both)
+    e2e_frame(0, pose(0, False)); e2e_read(0)
+    e2e_pixels = pix_pinned[0].clone()
+    h2d = 48
+    d2h = n * 4 + 8
+    del scene, mesh
 
     # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
-    build_ms = []
+    build_ms, stages = [], ""
     if rank == 0:
         for i in range(2 + args.steps):
             flush.zero_()
@@ -538,6 +520,8 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
             if i >= 2:
                 build_ms.append(e0.elapsed_time(e1))
+        built.enable_stage_timing(True); build_once(); torch.cuda.synchronize(dev)
+        stages = L.bmTreeLastBuildStages(built.h).decode(); built.enable_stage_timing(False)
     rep_ms = 0.0
     if world > 1:
         # replication cost: export + NCCL broadcast of the arrays + import, max over ranks
@@ -551,85 +535,140 @@ def run_b200(args):
             reps.append(e0.elapsed_time(e1))
             if rank != 0:
                 _t.close()
-        rt = torch.tensor([min(reps)], dtype=torch.float64, device=dev)
-        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
-        rep_ms = float(rt.item())
+        rt_ = torch.tensor([min(reps)], dtype=torch.float64, device=dev)
+        dist.all_reduce(rt_, op=dist.ReduceOp.MAX)
+        rep_ms = float(rt_.item())
     bt = torch.tensor([statistics.mean(build_ms) if build_ms else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.broadcast(bt, 0)
     bms = float(bt.item())
     peak, peak_src = measured_peaks()
-    build_bytes = 48 * st["triangles"] + 12 * st["pairs"] + 128 * st["nodes"] + 48 * st["pairs"] + 48 * st["leaves"] + 8 * st["pairs"]
+    node_b = 128 if st["nodes"] * 128 <= 48 * 1048576 else 64
+    build_bytes = 48 * st["triangles"] + 12 * st["pairs"] + node_b * st["nodes"] + 48 * st["pairs"] + 48 * st["leaves"] + 8 * st["pairs"]
     build = {"metric": "BVH build Mtris/s", "value": st["triangles"] / (bms * 1e-3) / 1e6, "unit": "Mtris/s", "ms": bms,
-             "triangles": st["triangles"], "pairs": st["pairs"], "leaves": st["leaves"], "nodes": st["nodes"],
-             "roofline": {"bound": "hbm", "achieved": build_bytes / (bms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+             "triangles": st["triangles"], "pairs": st["pairs"], "leaves": st["leaves"], "nodes": st["nodes"], "overflow_leaves": st["overflow_leaves"], "max_leaf_faces": st["max_leaf_faces"],
+             "stages_us": stages,
+             "roofline": {"bound": "latency" if st["triangles"] < 5_000_000 else "hbm", "achieved": build_bytes / (bms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": build_bytes / (bms * 1e-3) / 1e9 / peak, "traffic": None,
-                          "algorithmic_bytes": build_bytes, "note": "compulsory bytes of the whole build: 48 B/tri soup read + 12 B/pair (8 B key + 4 B id) written + outputs (128 B/node, 48 B/leaf, 48 B/pair triangle record, 32 B per 4 pairs cluster box); sort passes excluded (SURVEY 8d); " + peak_src},
+                          "algorithmic_bytes": build_bytes, "note": "compulsory bytes of the whole build: 48 B/tri soup read + 12 B/pair (8 B key + 4 B id) written + outputs (%d B/node, 48 B/leaf, 48 B/pair triangle record, 32 B per 4 pairs cluster box); sort passes excluded (SURVEY 8d); at this size the build is a chain of ~30 short launches, bound by launch latency, not by HBM; " % node_b + peak_src},
              "replication": ("built on rank 0, arrays replicated to %d peers by NCCL broadcast in %.3f ms (not included in ms)" % (world - 1, rep_ms)) if world > 1 else "single GPU",
              "replicate_ms": rep_ms}
 
-    # --- roofline of the dominant kernel: the primary-ray trace launch ---------------------------------------------------
-    pms = statistics.mean(prim_ms)
-    if SPP > 1 or NB > 1:
-        # multi-sample / banded frames interleave launches: time the dominant kernel (one camera launch of the frame's rays) on its own
+    # --- roofline of the dominant kernel: the primary-ray trace launch (static frame, the one the committed ncu capture profiled) ----------
+    def time_launch(fn, reps=7):
         tt = []
-        for _ in range(5):
-            flush.zero_(); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
-            _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, _f3(eye), _f9(orient), 0, hits1.data_ptr(), None, None, None), "bmTraceCamera")
-            e1.record(); torch.cuda.synchronize(dev); tt.append(e0.elapsed_time(e1))
-        pms = statistics.mean(tt)
-    prim_bytes = n * (12 + 16 + 4) + NODE_BYTES * V1 + TRI_BYTES * K1 + CLUSTER_BYTES * C1
-    roofline = {"bound": "hbm", "kernel": "trace_kernel<camera> (bmTraceCamera, reference semantics)", "achieved": prim_bytes / (pms * 1e-3) / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": prim_bytes / (pms * 1e-3) / 1e9 / peak, "traffic": None,
-                "ms_per_launch": pms, "mrays_per_s": n / (pms * 1e-3) / 1e6,
-                "bytes_per_ray": prim_bytes / n, "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n, "cluster_boxes_per_ray": C1 / n, "longest_ray_steps": LONG1,
-                "note": "algorithmic bytes = 12 B ray + 16 B hit + 4 B pixel + 96 B x node/leaf visits + 32 B x cluster boxes + 48 B x triangle tests (counters of the same traversal); "
-                        + peak_src + "; the tree (~%.0f MB) is L2-resident on B200, so this kernel is latency/issue-bound, not HBM-bound (SURVEY 8d)" %
-                        ((st["nodes"] * 128 + st["pairs"] * 56 + st["leaves"] * 48) / 1e6)}
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        if tr:
-            roofline["traffic"] = tr["dram_bytes_per_launch"]; roofline["traffic_source"] = tr["source"]
-    except Exception:
-        pass
-    if wl.bounces and nb and SPP == 1:
-        if NB > 1:
-            bounce_ms = []
-            for _ in range(5):
-                flush.zero_(); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
-                _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRays")
-                e1.record(); torch.cuda.synchronize(dev); bounce_ms.append(e0.elapsed_time(e1))
-        bms2 = statistics.mean(bounce_ms)
-        roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb / (bms2 * 1e-3) / 1e6, "rays": nb,
-                                     "node_visits_per_ray": V2 / nb, "tri_tests_per_ray": K2 / nb, "cluster_boxes_per_ray": C2 / nb,
-                                     "achieved": (nb * (24 + 16) + NODE_BYTES * V2 + TRI_BYTES * K2 + CLUSTER_BYTES * C2) / (bms2 * 1e-3) / 1e9}
+        for _ in range(reps):
+            flush.zero_(); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev); tt.append(e0.elapsed_time(e1))
+        return statistics.mean(tt[2:])
+    pms = time_launch(lambda: _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, p0[0], p0[1], 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera"))
+    prim_bytes = n * (12 + 16 + 4) + (NODE_BYTES if node_b == 128 else 64) * V1 + TRI_BYTES * K1 + CLUSTER_BYTES * C1
+    sm_clock_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
+    issue_peak = 148 * 4 * sm_clock_ghz                       # warp instructions per ns = G inst/s: 4 schedulers per SM, one issue per clock each
+    prof = profile_entry(args.workload) if (world == 1 or not strong) else None
+    tree_mb = (st["nodes"] * node_b + st["pairs"] * 56 + st["leaves"] * 48) / 1e6
+    roofline = {"kernel": "trace_kernel<camera> (bmTraceCamera, reference semantics), static frame", "ms_per_launch": pms, "mrays_per_s": n / (pms * 1e-3) / 1e6,
+                "algorithmic_bytes_per_ray": prim_bytes / n, "algorithmic_gbs": prim_bytes / (pms * 1e-3) / 1e9,
+                "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n, "cluster_boxes_per_ray": C1 / n, "longest_ray_steps": LONG1,
+                "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
+    if prof and tree_mb < 100:
+        # the tree is L2-resident: the kernel is bound by instruction issue / cache latency, not by HBM (DRAM moves ~1 % of the algorithmic bytes)
+        l2_peak = l2_copy_peak(torch, dev)
+        inst = prof["warp_instructions_per_launch"]
+        roofline.update({"bound": "issue", "achieved": inst / (pms * 1e-3) / 1e9, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": inst / (pms * 1e-3) / 1e9 / issue_peak,
+                         "traffic": prof["dram_bytes_per_launch"], "traffic_source": prof["source"],
+                         "dram": {"achieved_gbs": prof["dram_bytes_per_launch"] / (pms * 1e-3) / 1e9, "frac_of_hbm_peak": prof["dram_bytes_per_launch"] / (pms * 1e-3) / 1e9 / peak},
+                         "l2": {"lts_bytes_per_launch": prof["lts_bytes_per_launch"], "achieved_gbs": prof["lts_bytes_per_launch"] / (pms * 1e-3) / 1e9, "copy_peak_gbs": l2_peak,
+                                "frac": prof["lts_bytes_per_launch"] / (pms * 1e-3) / 1e9 / l2_peak, "peak_source": "live: torch copy of two L2-resident 24 MiB buffers (read + write bytes)",
+                                "ncu_pct_of_peak": prof.get("lts_pct_of_peak")},
+                         "lanes_per_instruction": prof.get("lanes_per_instruction"), "ipc": prof.get("ipc"),
+                         "note": "the %.0f MB tree is L2-resident: bound = instruction issue (peak = 148 SMs x 4 schedulers x %.3f GHz; warp instructions and L2 / DRAM bytes per launch from the committed ncu capture of this very launch, duration measured live); "
+                                 "the algorithmic bytes per ray are served from L1 / L2, which is why algorithmic_gbs may exceed the HBM peak" % (tree_mb, sm_clock_ghz)})
+    else:
+        tr = prof["dram_bytes_per_launch"] if prof else None
+        a_gbs = (tr if tr else prim_bytes) / (pms * 1e-3) / 1e9
+        roofline.update({"bound": "hbm", "achieved": a_gbs, "peak": peak, "unit": "GB/s", "frac": a_gbs / peak, "traffic": tr,
+                         "note": ("achieved = measured DRAM bytes per launch (committed ncu capture) / live duration" if tr else
+                                  "no ncu capture of this configuration is committed: achieved = algorithmic bytes (96 B x node visits + 32 B x cluster boxes + 48 B x triangle tests + ray / hit / pixel records) / live duration; "
+                                  "part of them is served from L2 (tree %.0f MB)" % tree_mb) + "; " + peak_src})
+    if wl.bounces and nb_last:
+        bms2 = time_launch(lambda: _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRays"))
+        roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb_last / (bms2 * 1e-3) / 1e6, "rays": nb_last, "mode": "closest hit",
+                                     "node_visits_per_ray": V2 / nb_last, "tri_tests_per_ray": K2 / nb_last, "cluster_boxes_per_ray": C2 / nb_last}
+        pb = profile_entry(args.workload + "_bounce")
+        if pb and world == 1:
+            roofline["bounce_launch"].update({"bound": "issue", "frac": pb["warp_instructions_per_launch"] / (bms2 * 1e-3) / 1e9 / issue_peak, "traffic": pb["dram_bytes_per_launch"],
+                                              "lanes_per_instruction": pb.get("lanes_per_instruction"), "traffic_source": pb["source"]})
+    # the metric's name says closest hit: the same primary launch in BM_TRACE_CLOSEST (exhaustive, t >= 0) beside the reference-semantics number
+    hits_c = torch.empty_like(hits1)
+    cms = time_launch(lambda: _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, p0[0], p0[1], 1, hits_c.data_ptr(), None, None, None), "bmTraceCamera"))
+    _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, p0[0], p0[1], 0, hits1.data_ptr(), pixels.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+    torch.cuda.synchronize(dev)
+    same = float((hits_c[:, 3].view(torch.int32) == hits1[:, 3].view(torch.int32)).float().mean())
+    closest_mode = {"primary_launch_ms": cms, "primary_mrays_per_s": n / (cms * 1e-3) / 1e6, "reference_mode_primary_launch_ms": pms,
+                    "same_triangle_as_reference_mode": same,
+                    "note": "BM_TRACE_CLOSEST = exhaustive closest hit with t >= 0; the reference's own semantics (first leaf with a hit, any sign of t) is the parity mode the primary rays are timed in; bounce rays are always traced in closest mode"}
+    e2e_equal = bool(torch.equal(e2e_pixels.to(dev), pixels)) if (SPP == 1 and not wl.bounces) else None
 
-    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": WU,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "rays_per_step_per_gpu": rays_step, "primary_rays_per_gpu": n * SPP, "bounce_rays_per_gpu": nb, "samples_per_pixel": SPP,
-                       "trace_mode": "primary rays: reference semantics (BM_TRACE_REFERENCE); bounce rays: closest hit, t >= 0 (BM_TRACE_CLOSEST)", "l2": "flushed between timed steps (256 MiB write)", "bands": NB, "cpu_affinity": numa,
-                       "sharding": "interleaved image rows per rank, replicated tree, NCCL all-gather of the framebuffer overlapped with the bounce trace" if world > 1 else "single GPU",
-                       "camera": {"eye": list(eye), "frustum": list(wl.frustum), "orient": "identity"}},
+                       "image_per_gpu": [W, H],
+                       "trace_mode": "primary rays: reference semantics (BM_TRACE_REFERENCE); bounce rays: closest hit, t >= 0 (BM_TRACE_CLOSEST)", "l2": "flushed between timed steps (256 MiB write)", "cpu_affinity": numa,
+                       "sharding": ("interleaved image rows per rank, replicated tree, framebuffer of all ranks assembled on every rank by %s, overlapped with the bounce trace"
+                                    % ("copy-engine writes into the peers' symmetric memory over NVLink" if symm is not None else "NCCL all-gather")) if world > 1 else "single GPU",
+                       "camera": {"eye": [float(x) for x in eye0], "frustum": list(wl.frustum),
+                                  "motion": ("orbit about the y axis, %.3g degrees per frame, looking at the origin (every frame differs from the one the tile schedule learnt from)" % args.orbit_deg) if moving else "static"}},
+            "primary_launch_ms": prim_moving_ms, "bounce_launch_ms": bounce_moving_ms,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
-                    "single_frame_latency_ms": e2e_latency_ms,
-                    "pipeline": ("%d frames in flight on 3 streams (H2D of the camera table | L2 flush + trace + bounce + trace%s | D2H of framebuffer, bounce count and "
-                                 "bounce hit records sized by the device-side count); the K steps are one timed bracket, fill and drain included"
-                                 % (DEPTH, ", replayed as one CUDA graph per frame" if e2e_graphs is not None else "")) if SPP == 1
-                                else "one frame at a time: H2D of the camera table, the multi-sample frame, D2H of the framebuffer"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build}
+                    "single_frame_latency_ms": e2e_latency_ms, "pixels_equal_device_path": e2e_equal,
+                    "api": "host classes through include/beam_host_c.h: " + ("beamCameraTraceSceneProgressive" if (wl.bounces or SPP > 1) else "beamCameraTraceScene") + " + beamRenderTargetReadPixels; scene uploaded from host arrays by beamMeshSetVertexData / beamMeshSetIndices, built by beamSceneUpdateGPUScene",
+                    "pipeline": "per frame: eye + orientation (48 B, kernel arguments; the camera's direction table was uploaded once by setInitialRays, as the reference does) -> frame on the host classes' stream -> "
+                                "read-back of the framebuffer and the ray count into pinned memory on the copy stream; two render targets, so the read-back of frame i-1 overlaps frame i; K frames = one timed bracket"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build, "closest_mode": closest_mode}
+    if static is not None:
+        line["static_camera"] = static
 
+    if rank == 0 and world == 1 and not args.no_hbm_leg and args.workload == "c2":
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            line["hbm_leg"] = hbm_leg(torch, dev, L, args)
+        except Exception as ex:                               # reported, never fatal for the headline
+            line["hbm_leg"] = {"error": repr(ex)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if SPP == 1 and wl.bounces:
-            whole_frame_bounce_list()
+            _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, p0[0], p0[1], 0, hits1.data_ptr(), None, None, None), "bmTraceCamera")
+            _lib.check(L.bmBounceRaysCamera(tree.h, rays_dev.data_ptr(), p0[0], p0[1], hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
+            torch.cuda.synchronize(dev)
+            nb = int(cnt2.item())
         def gpu_frame_pixels(w_, h_):
             """the product's pixels for the workload's scene at w_ x h_ (same camera), for the comparison with the reference build"""
             c_ = host.ICamera.create(); assert c_.setInitialRays(w_, h_, *wl.frustum) == 0
             r_ = torch.from_numpy(c_.initialRays()).to(dev); p_ = torch.empty(w_ * h_, dtype=torch.int32, device=dev)
-            _lib.check(L.bmTraceCamera(tree.h, r_.data_ptr(), w_ * h_, w_, _f3(eye), _f9(orient), 0, None, p_.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
+            _lib.check(L.bmTraceCamera(tree.h, r_.data_ptr(), w_ * h_, w_, p0[0], p0[1], 0, None, p_.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
             torch.cuda.synchronize(dev)
             return p_.cpu().numpy().view(np.uint32)
-        line["cpu_baseline"] = cpu_baseline(wl, rays_pinned.numpy(), rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None,
+        line["cpu_baseline"] = cpu_baseline(wl, rays_host, rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None,
                                             gpu_pixels_fn=gpu_frame_pixels)
+        def ours_scene(name_):
+            """this library on one of the reference-kernel scenes: build (best of 3) and the primary launch at 1280x720 (mean of 5 after warm-up)"""
+            P_, I_, N_ = workloads._bundled(name_) if name_ in ("f16", "suzanne", "bunny") else (wl.positions, wl.indices, wl.normals)
+            Pd_ = torch.from_numpy(P_).to(dev); Id_ = torch.from_numpy(I_.view(np.int32)).to(dev).reshape(-1); Nd_ = torch.from_numpy(N_).to(dev)
+            tab_ = make_mesh_table([(Pd_, Id_, Nd_)], dev)
+            t_ = Tree(dev); bt_ = []
+            for _ in range(4):
+                t_.reset(); t_.add_mesh(Pd_, Id_); e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record(); t_.build(); e1.record(); torch.cuda.synchronize(dev); bt_.append(e0.elapsed_time(e1))
+            c_ = host.ICamera.create(); assert c_.setInitialRays(1280, 720, *wl.frustum) == 0
+            r_ = torch.from_numpy(c_.initialRays()).to(dev); p_ = torch.empty(1280 * 720, dtype=torch.int32, device=dev)
+            e_ = _f3([0.0, 0.0, -2.1]); o_ = _f9(np.eye(3, dtype=np.float32)); tt_ = []
+            for _ in range(8):
+                e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
+                _lib.check(L.bmTraceCamera(t_.h, r_.data_ptr(), 1280 * 720, 1280, e_, o_, 0, None, p_.data_ptr(), tab_.data_ptr(), None), "bmTraceCamera")
+                e1.record(); torch.cuda.synchronize(dev); tt_.append(e0.elapsed_time(e1))
+            t_.close()
+            return {"build_ms": min(bt_[1:]), "build_mtris_per_s": I_.shape[0] / (min(bt_[1:]) * 1e-3) / 1e6, "trace_ms": statistics.mean(tt_[3:]),
+                    "primary_mrays_per_s": 1280 * 720 / (statistics.mean(tt_[3:]) * 1e-3) / 1e6}
+        line["reference_cuda_b200"] = reference_cuda_baseline(args.workload, ours_scene)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     if rank == 0:
@@ -640,11 +679,106 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def hbm_leg(torch, dev, L, args):
+    """The memory-bound side of the path inside the default line: a 20 M-triangle soup (tree ~6 GB, 50 x the L2) and 16 M incoherent rays --
+    BASELINE config 5 at a size that builds and traces in about two seconds.  Both traversal forms are timed: the direct one (one DRAM round
+    trip per node: the HBM-bound kernel, its fraction from the DRAM bytes of the committed ncu capture) and the brick-by-brick one bmTraceRays
+    chooses for such trees (same hits, the bytes mostly served by the L2: issue-bound)."""
+    from raytracercuda_b200 import _lib, synth
+    from raytracercuda_b200.tree import Tree
+    T, n = int(args.hbm_mtris * 1e6), int(args.hbm_mrays * 1e6)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    Pd, Id = synth.soup_torch(T, dev)
+    t = Tree(dev)
+    bms = []
+    for i in range(3):
+        t.reset(); t.add_mesh(Pd, Id)
+        e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record(); t.build(); e1.record(); torch.cuda.synchronize(dev); bms.append(e0.elapsed_time(e1))
+    t.enable_stage_timing(True); t.reset(); t.add_mesh(Pd, Id); t.build(); torch.cuda.synchronize(dev)
+    stages = L.bmTreeLastBuildStages(t.h).decode(); t.enable_stage_timing(False)
+    st = t.stats()
+    R = synth.incoherent_rays_torch(n, dev)
+    hits = torch.empty((n, 4), dtype=torch.float32, device=dev); ref_hits = torch.empty_like(hits)
+    peak, peak_src = measured_peaks()
+    out = {"workload": "c5-class: synthetic %.0f M-triangle soup, %.0f M incoherent rays per launch (origin uniform in the world, direction uniform on the sphere)" % (args.hbm_mtris, args.hbm_mrays),
+           "tree_gb": (st["nodes"] * 64 + st["pairs"] * 56 + st["leaves"] * 48) / 1e9, "triangles": st["triangles"], "pairs": st["pairs"], "leaves": st["leaves"],
+           "build": {"value": T / (min(bms) * 1e-3) / 1e6, "unit": "Mtris/s", "ms": min(bms), "stages_us": stages}}
+    for bricks, key in ((0, "direct"), (1, "bricked")):
+        t.set_bricks(bricks, 0)
+        leg = {}
+        for mode, mname in ((0, "reference"), (1, "closest")):
+            ms = []
+            for r in range(4):
+                e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record()
+                _lib.check(L.bmTraceRays(t.h, R.data_ptr(), n, mode, hits.data_ptr(), None), "bmTraceRays")
+                e1.record(); torch.cuda.synchronize(dev); ms.append(e0.elapsed_time(e1))
+            m_ = statistics.mean(ms[1:])
+            leg[mname] = {"ms_per_launch": m_, "mrays_per_s": n / (m_ * 1e-3) / 1e6}
+            if bricks == 0 and mode == 0:
+                ref_hits.copy_(hits)
+            if bricks == 1 and mode == 0:
+                leg["hits_equal_direct"] = bool(torch.equal(hits.view(torch.int32), ref_hits.view(torch.int32)))      # bit patterns: a miss carries tri = 0xFFFFFFFF, a NaN as float
+            if mode == 0:
+                cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+                _lib.check(L.bmTraceRays(t.h, R.data_ptr(), n, mode, hits.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+                torch.cuda.synchronize(dev)
+                V, K, Cc, LONG = [int(x) for x in cnt.cpu()]
+                leg["node_visits_per_ray"] = V / n; leg["tri_tests_per_ray"] = K / n
+                leg["algorithmic_bytes_per_ray"] = 40 + 64 * V / n + 48 * K / n
+        prof = profile_entry("hbm_leg_" + key)
+        ms0 = leg["reference"]["ms_per_launch"]
+        if prof:
+            scale = n / prof["rays_per_launch"]               # the capture traced rays_per_launch rays of the same batch: bytes scale with the ray count
+            dram = prof["dram_bytes_per_launch"] * scale
+            leg["roofline"] = {"bound": prof["bound"], "traffic": dram, "traffic_source": prof["source"], "dram_gbs": dram / (ms0 * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": dram / (ms0 * 1e-3) / 1e9 / peak, "peak": peak, "ipc": prof.get("ipc"), "lanes_per_instruction": prof.get("lanes_per_instruction"),
+                               "note": "reference-mode launch; DRAM bytes of the committed capture scaled to this launch's ray count, duration measured live; " + peak_src}
+        else:
+            a = leg["algorithmic_bytes_per_ray"] * n / (ms0 * 1e-3) / 1e9
+            leg["roofline"] = {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None, "note": "algorithmic bytes (64 B x node visits + 48 B x triangle tests + 40 B ray / hit), no capture committed; " + peak_src}
+        out[key] = leg
+    out["value"] = out["bricked"]["reference"]["mrays_per_s"]; out["unit"] = "Mrays/s"
+    out["value_note"] = "reference semantics through bmTraceRays as shipped (brick by brick for this tree size); closest-hit and direct-traversal numbers beside it"
+    t.close()
+    return out
+
+
+def reference_cuda_baseline(workload, ours=None):
+    """Second baseline (north_star): the reference's OWN CUDA kernels (BuildTree.cu / RTClear.cu) rebuilt for sm_100a by oracle/build_ref_cuda.sh, run
+    per scene in a process of their own (their pool allocation is racy, BuildTree.cu:13-18,43-50, and dies on larger meshes).  Part of the
+    cpu_baseline leg: the only place bench.py may execute anything under oracle/."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libbeam_refcuda.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libbeam_refcuda.so not built (needs /root/reference at build time)"}
+    out = {"what": "Raytracer/BuildTree.cu + RTClear.cu of the reference compiled for sm_100a (--use_fast_math as shipped), primary rays at 1280x720 through its own host classes"}
+    for name in ("f16", "suzanne", "bunny", workload):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_refcuda.py"), name, "1280", "720", "3"], capture_output=True, text=True, timeout=180)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode == 0 and line:
+                d = json.loads(line[-1])
+                out[name] = {"triangles": d["triangles"], "build_mtris_per_s": d["build_mtris_per_s"], "primary_mrays_per_s": d["primary_mrays_per_s"], "build_ms": d["build_ms"], "trace_ms": d["trace_ms"]}
+            else:
+                out[name] = "crashed (exit %d: %s)" % (r.returncode, (r.stderr.strip().splitlines() or ["no message"])[-1][:160])
+        except subprocess.TimeoutExpired:
+            out[name] = "timed out (180 s)"
+        except Exception as ex:
+            out[name] = "unavailable (%r)" % (ex,)
+        if ours is not None:
+            try:
+                out["this_library_" + name] = ours(name)
+            except Exception as ex:
+                out["this_library_" + name] = "unavailable (%r)" % (ex,)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def run_c5(args):
-    """BASELINE config 5: counter-based triangle soup (default 100 M triangles) built once, then incoherent ray batches (origin uniform
-    in the world, direction uniform on the sphere) traced in reference mode.  One step = one batch of --c5-mrays million rays per rank;
-    ranks trace different batches against a replicated tree (weak scaling).  This is the HBM-bound case: the tree is far larger than L2."""
+    """BASELINE config 5: counter-based triangle soup (default 100 M triangles) built once on rank 0 and replicated, then ONE fixed batch of
+    incoherent rays (origin uniform in the world, direction uniform on the sphere; --c5-total-mrays, default 256 M, generated on the device)
+    split by range over the ranks -- strong scaling.  One step = the whole batch, traced in launches of --c5-mrays million rays per rank,
+    in the reference's semantics through bmTraceRays as shipped (brick by brick for a tree of this size); the closest-hit mode and the direct
+    traversal are timed beside it on one launch."""
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -663,9 +797,15 @@ def run_c5(args):
     from raytracercuda_b200.dist import replicate_tree
     from raytracercuda_b200.tree import Tree
     L = _lib.load()
-    T = int(args.c5_mtris * 1e6); n = int(args.c5_mrays * 1e6)
+    T = int(args.c5_mtris * 1e6); chunk = int(args.c5_mrays * 1e6)
+    total = int(args.c5_total_mrays * 1e6)
+    total -= total % (world * chunk) if total >= world * chunk else 0
+    if total < world * chunk:
+        total = world * chunk
+    mine = total // world                                   # rays [rank * mine, (rank + 1) * mine) of the batch
+    nchunks = mine // chunk
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    built, build_ms, st = None, [], None
+    built, build_ms, st, stages = None, [], None, ""
     if rank == 0:
         Pd, Id = synth.soup_torch(T, dev)
         built = Tree(dev)
@@ -673,20 +813,26 @@ def run_c5(args):
             built.reset(); built.add_mesh(Pd, Id)
             e0, e1 = ev(), ev(); torch.cuda.synchronize(dev); e0.record(); built.build(); e1.record(); torch.cuda.synchronize(dev)
             build_ms.append(e0.elapsed_time(e1))
+        built.enable_stage_timing(True); built.reset(); built.add_mesh(Pd, Id); built.build(); torch.cuda.synchronize(dev)
+        stages = L.bmTreeLastBuildStages(built.h).decode(); built.enable_stage_timing(False)
         st = built.stats()
     e0, e1 = ev(), ev(); torch.cuda.synchronize(dev)
     if world > 1: dist.barrier()
     e0.record(); tree = replicate_tree(built, dev, 0); e1.record(); torch.cuda.synchronize(dev)
-    rep_ms = e0.elapsed_time(e1) if world > 1 else 0.0
+    rep_t = torch.tensor([e0.elapsed_time(e1) if world > 1 else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rep_t, op=dist.ReduceOp.MAX)
+    rep_ms = float(rep_t.item())
     stt = torch.zeros(4, dtype=torch.int64, device=dev)
     if rank == 0:
         stt.copy_(torch.tensor([st["triangles"], st["pairs"], st["leaves"], st["nodes"]]))
     if world > 1:
         dist.broadcast(stt, 0)
     Tn, Pn, Ln, Nn = [int(x) for x in stt.cpu()]
-    rays = synth.incoherent_rays_torch(n, dev, start=rank * n)
-    hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    rays_pinned = rays.cpu().pin_memory(); hits_host = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    # the rank's share of the batch, two chunk buffers: chunk k+1 is generated (counter-based, on the device) while ... no: generation is
+    # outside the timed region -- the share is materialised once if it fits (24 B per ray), else regenerated per chunk before the step
+    rays_all = [synth.incoherent_rays_torch(chunk, dev, start=rank * mine + k * chunk) for k in range(nchunks)]
+    hits = torch.empty((chunk, 4), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def sync_all():
@@ -694,59 +840,95 @@ def run_c5(args):
         if world > 1:
             dist.barrier(); torch.cuda.synchronize(dev)
 
-    def step(src):
-        _lib.check(L.bmTraceRays(tree.h, src.data_ptr(), n, 0, hits.data_ptr(), None), "bmTraceRays")
-    for _ in range(max(args.warmup, 3)):
-        step(rays)
-    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
-    _lib.check(L.bmTraceRays(tree.h, rays.data_ptr(), n, 0, hits.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+    hit_count = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def step(mode=0, count=False):
+        for k in range(nchunks):
+            _lib.check(L.bmTraceRays(tree.h, rays_all[k].data_ptr(), chunk, mode, hits.data_ptr(), None), "bmTraceRays")
+            if count:
+                hit_count.add_((hits[:, 3].view(torch.int32) != -1).sum())
+    for _ in range(max(min(args.warmup, 1), 1)):
+        step(count=True)
     torch.cuda.synchronize(dev)
-    V, K, Cc, LONG = [int(x) for x in cnt.cpu()]
-    hit_rate = float((hits[:, 3].view(torch.int32) != -1).float().mean())
+    hit_rate = float(hit_count.item()) / mine
     sampler = ClockSampler(local); launches0 = L.bmLaunchCount()
     sync_all(); sampler.start()
     ms = []
     for _ in range(args.steps):
-        a, b = ev(), ev(); sync_all(); a.record(); step(rays); b.record(); sync_all(); ms.append(a.elapsed_time(b))
+        a, b = ev(), ev(); sync_all(); a.record(); step(); b.record(); sync_all(); ms.append(a.elapsed_time(b))
     clocks = sampler.stop(); launches = L.bmLaunchCount() - launches0
     tsum = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tsum, op=dist.ReduceOp.MAX)
     ms_per_step = float(tsum.item()) / args.steps
-    value = n * world / (ms_per_step * 1e-3) / 1e6
-    e2e_dev = torch.empty_like(rays); ems = []
-    for i in range(2 + args.steps):
+    value = total / (ms_per_step * 1e-3) / 1e6
+
+    # one launch on its own: per mode, as shipped (bricks chosen by the library) and with the direct traversal; counters of the traversal
+    R0 = rays_all[0]
+    def one(mode, bricks):
+        _lib.check(L.bmTreeSetBricks(tree.h, bricks, 0), "bmTreeSetBricks")
+        tt = []
+        for r in range(3):
+            a, b = ev(), ev(); torch.cuda.synchronize(dev); a.record()
+            _lib.check(L.bmTraceRays(tree.h, R0.data_ptr(), chunk, mode, hits.data_ptr(), None), "bmTraceRays")
+            b.record(); torch.cuda.synchronize(dev); tt.append(a.elapsed_time(b))
+        m_ = statistics.mean(tt[1:])
+        return {"ms_per_launch": m_, "mrays_per_s": chunk / (m_ * 1e-3) / 1e6}
+    legs = {"as_shipped": {"reference": one(0, -1), "closest": one(1, -1)}, "direct": {"reference": one(0, 0), "closest": one(1, 0)}}
+    _lib.check(L.bmTreeSetBricks(tree.h, -1, 0), "bmTreeSetBricks")
+    cnt = torch.zeros(4, dtype=torch.int64, device=dev)
+    _lib.check(L.bmTraceRays(tree.h, R0.data_ptr(), chunk, 0, hits.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+    torch.cuda.synchronize(dev)
+    V, K, Cc, LONG = [int(x) for x in cnt.cpu()]
+
+    # e2e: one launch's rays from pinned host memory, its hit records back to pinned host memory
+    rays_pinned = R0.cpu().pin_memory(); hits_host = torch.empty((chunk, 4), dtype=torch.float32).pin_memory()
+    e2e_dev = torch.empty_like(R0); ems = []
+    for i in range(2 + min(args.steps, 5)):
         a, b = ev(), ev(); sync_all(); a.record()
-        e2e_dev.copy_(rays_pinned, non_blocking=True); step(e2e_dev); hits_host.copy_(hits, non_blocking=True)
+        e2e_dev.copy_(rays_pinned, non_blocking=True)
+        _lib.check(L.bmTraceRays(tree.h, e2e_dev.data_ptr(), chunk, 0, hits.data_ptr(), None), "bmTraceRays")
+        hits_host.copy_(hits, non_blocking=True)
         b.record(); sync_all()
         if i >= 2: ems.append(a.elapsed_time(b))
-    t2 = torch.tensor([sum(ems)], dtype=torch.float64, device=dev)
+    t2 = torch.tensor([statistics.mean(ems)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = n * world / (float(t2.item()) / args.steps * 1e-3) / 1e6
+    e2e_value = chunk * world / (float(t2.item()) * 1e-3) / 1e6
     peak, peak_src = measured_peaks()
-    by = n * (24 + 16) + NODE_BYTES * V + CLUSTER_BYTES * Cc + TRI_BYTES * K
-    kms = statistics.mean(ms)
+    by = chunk * (24 + 16) + 64 * V + CLUSTER_BYTES * Cc + TRI_BYTES * K
+    kms = legs["as_shipped"]["reference"]["ms_per_launch"]
     bt = torch.tensor([min(build_ms) if build_ms else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.broadcast(bt, 0)
     bms = float(bt.item())
-    build_bytes = 48 * Tn + 12 * Pn + 128 * Nn + 48 * Pn + 48 * Ln + 8 * Pn
-    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c5: synthetic %.0f M-triangle soup (splitmix64 seed 12345), incoherent rays (seed 54321), %.0f M rays per step per GPU, reference semantics" % (args.c5_mtris, args.c5_mrays),
-                       "rays_per_step_per_gpu": n, "l2": "tree (%.1f GB) and ray batch (%.1f GB) far exceed L2" % ((Nn * 128 + Pn * 56 + Ln * 48) / 1e9, n * 40 / 1e9),
-                       "sharding": "ray batches per rank, tree built on rank 0 and replicated by NCCL broadcast" if world > 1 else "single GPU", "hit_rate": hit_rate},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 16, "ms_per_step": float(t2.item()) / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "trace_kernel<rays> (bmTraceRays, reference semantics)", "achieved": by / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": by / (kms * 1e-3) / 1e9 / peak, "traffic": None, "ms_per_launch": kms, "bytes_per_ray": by / n, "node_visits_per_ray": V / n,
-                         "tri_tests_per_ray": K / n, "cluster_boxes_per_ray": Cc / n, "longest_ray_steps": LONG,
-                         "note": "24 B ray + 16 B hit + 96 B x node/leaf visits + 32 B x cluster boxes + 48 B x triangle tests; " + peak_src},
+    build_bytes = 48 * Tn + 12 * Pn + 64 * Nn + 48 * Pn + 48 * Ln + 8 * Pn
+    prof = profile_entry("c5")
+    roof = {"kernel": "bmTraceRays, reference semantics, one launch of %d rays as shipped (segments + sort + trace_kernel<SEG> + resolve)" % chunk,
+            "ms_per_launch": kms, "algorithmic_bytes_per_ray": by / chunk, "algorithmic_gbs": by / (kms * 1e-3) / 1e9, "node_visits_per_ray": V / chunk, "tri_tests_per_ray": K / chunk,
+            "longest_segment_steps": LONG}
+    if prof:
+        dram = prof["dram_bytes_per_launch"] * chunk / prof["rays_per_launch"]
+        roof.update({"bound": prof.get("bound", "issue"), "traffic": dram, "traffic_source": prof["source"], "achieved": dram / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": dram / (kms * 1e-3) / 1e9 / peak, "ipc": prof.get("ipc"), "lanes_per_instruction": prof.get("lanes_per_instruction"),
+                     "note": "achieved = DRAM bytes of the committed ncu capture (scaled by ray count) / live duration: the bricked traversal serves most node bytes from L2 and is bound by instruction issue, so the HBM fraction is low by design; the direct traversal is the HBM-bound form (see `direct`); " + peak_src})
+    else:
+        roof.update({"bound": "hbm", "achieved": by / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": by / (kms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "note": "algorithmic bytes: 24 B ray + 16 B hit + 64 B x node visits + 48 B x triangle tests; " + peak_src})
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c5: synthetic %.0f M-triangle soup (splitmix64 seed 12345), one batch of %.0f M incoherent rays (seed 54321) split by range over the ranks, %.0f M rays per launch, reference semantics" % (args.c5_mtris, total / 1e6, args.c5_mrays),
+                       "rays_per_step": total, "rays_per_step_per_gpu": mine, "launches_per_step_per_gpu": nchunks,
+                       "l2": "tree (%.1f GB) and ray batch far exceed L2" % ((Nn * 64 + Pn * 56 + Ln * 48) / 1e9),
+                       "sharding": "ray batch split by range, tree built on rank 0 and replicated by NCCL broadcast" if world > 1 else "single GPU", "hit_rate": hit_rate},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": chunk * 24, "d2h_bytes_per_step": chunk * 16, "ms_per_step": float(t2.item()),
+                    "note": "one launch per rank: rays from pinned host memory, hit records back to pinned host memory"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "one_launch": legs,
             "build": {"metric": "BVH build Mtris/s", "value": Tn / (bms * 1e-3) / 1e6 if bms else None, "unit": "Mtris/s", "ms": bms, "triangles": Tn, "pairs": Pn, "leaves": Ln, "nodes": Nn,
+                      "stages_us": stages,
                       "roofline": {"bound": "hbm", "achieved": build_bytes / (bms * 1e-3) / 1e9 if bms else None, "peak": peak, "unit": "GB/s",
                                    "frac": build_bytes / (bms * 1e-3) / 1e9 / peak if bms else None, "traffic": None, "algorithmic_bytes": build_bytes},
-                      "replicate_ms": rep_ms}}
+                      "replicate_ms": rep_ms, "replication": "NCCL broadcast of %.1f GB of arrays to %d peers" % ((Nn * 64 + Pn * 56 + Ln * 48 + Tn * 48 + (Pn / 4 + Ln) * 32) / 1e9, world - 1) if world > 1 else "single GPU"}}
     sys.stdout.flush(); os.dup2(saved_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -888,11 +1070,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--bands", type=int, default=1, help="row bands of a frame issued concurrently on as many streams (tail filling)")
-    ap.add_argument("--no-e2e-graph", action="store_true", help="e2e leg: direct launches instead of one CUDA graph per frame")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"], help="N > 1: weak = every rank renders a full-size image (rows of an N-times taller one); strong = one frame of the workload's size split by rows; auto = weak for c1 / c2, strong for the multi-sample c3 / c4 frames and for c5")
+    ap.add_argument("--orbit-deg", type=float, default=1.0, help="camera orbit per frame in degrees (single-sample workloads; 0 = static camera)")
+    ap.add_argument("--no-hbm-leg", action="store_true", help="skip the c5-class (20 M triangles / 16 M incoherent rays) leg of the default line")
+    ap.add_argument("--hbm-mtris", type=float, default=20.0); ap.add_argument("--hbm-mrays", type=float, default=16.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5-mtris", type=float, default=100.0, help="workload c5: millions of soup triangles")
-    ap.add_argument("--c5-mrays", type=float, default=16.0, help="workload c5: millions of incoherent rays per step per GPU")
+    ap.add_argument("--c5-mrays", type=float, default=16.0, help="workload c5: millions of incoherent rays per launch")
+    ap.add_argument("--c5-total-mrays", type=float, default=256.0, help="workload c5: millions of rays of the whole batch (split over the ranks)")
     ap.add_argument("--reference-rays", type=int, default=200_000, help="primary rays per step of the --impl reference sample")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -223,7 +223,7 @@ int  bmTraceRays(bmTree* tree, const bmRay* d_rays, uint64_t numRays, int mode, 
  * brick and traced brick by brick out of the cache; per-ray results are merged in the order the reference's own traversal would have met
  * the bricks (raytracercuda_b200/csrc/bricks.cu).  Hits are identical to the direct traversal in both modes.  mode: -1 automatic
  * (traversal arrays above BM_BRICK_MIN_MB = 512 MB and >= 2^18 rays; BM_BRICKS=0|1 overrides), 0 never, 1 always; bits: depth of the
- * brick grid, 3..15, 0 = default (12 = 16 x 16 x 16 bricks; BM_BRICK_BITS).  A bricked call synchronises the tree's stream once (the
+ * brick grid, 3..15, 0 = default (6 = 4 x 4 x 4 bricks, fewer for trees below 256 MB; BM_BRICK_BITS overrides).  A bricked call synchronises the tree's stream once (the
  * segment count sizes the sort). */
 int  bmTreeSetBricks(bmTree* tree, int mode, int bits);
 /* Same, with the ray count read from DEVICE memory when the kernel starts (*d_numRays <= maxRays): lets a producer such as

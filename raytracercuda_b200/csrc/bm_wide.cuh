@@ -50,11 +50,16 @@ BM_HD WCell wide_cell(const Grid& g, u32 packed, int len)
 {
     WCell c;
     u32 ix, iy, iz; wide_unpack_cell(g, packed, ix, iy, iz);
-    cell_box(g, len, ix, iy, iz, c.mn, c.mx);
-    c.axis = len % 3;
-    u32 ia = c.axis == 0 ? ix : (c.axis == 1 ? iy : iz);
-    int sh = g.k[c.axis] - axis_bits(len, c.axis);      // >= 1: an internal node splits on this axis
-    c.split = grid_at(g, c.axis, ((ia << 1) | 1u) << (sh - 1));
+    // cell_box with the three axis_bits() folded into one division: splits on x, y, z among depths 0..len-1 = q + (r > 0), q + (r > 1), q
+    const int q = len / 3, r = len - 3 * q;
+    const int sx = g.k[0] - q - (r > 0 ? 1 : 0), sy = g.k[1] - q - (r > 1 ? 1 : 0), sz = g.k[2] - q;
+    c.mn.x = grid_at(g, 0, ix << sx); c.mx.x = grid_at(g, 0, (ix + 1) << sx);
+    c.mn.y = grid_at(g, 1, iy << sy); c.mx.y = grid_at(g, 1, (iy + 1) << sy);
+    c.mn.z = grid_at(g, 2, iz << sz); c.mx.z = grid_at(g, 2, (iz + 1) << sz);
+    c.axis = r;
+    // the reference's own expression (BuildTree.cu:443); equal to the grid boundary between the two halves, which the host tables
+    // produce with this very midpoint (bm_grid_host.h)
+    c.split = .5f * (get(c.mx, r) + get(c.mn, r));
     return c;
 }
 
@@ -253,14 +258,18 @@ BM_HD int wide_step(const Grid& g, WQ q0, WQ q1, WQ q2, WQ q3, V3 o, V3 d, V3 in
     if (MODE == BM_TRACE_REFERENCE)
     {
         bool a01 = true, b23 = true, aFirst = true;          // lower slot / lower half first
-        if (h[0] && h[1])
+        // the cell of an absorbed child is rebuilt only where both of its slots survive; a lane rarely needs both children, so the first
+        // pass serves whichever one it needs (one instruction stream for the warp instead of two half-empty ones) and the second the rest
+        const bool needA = h[0] && h[1], needB = h[2] && h[3];
+        if (needA || needB)
         {
-            const WCell cA = wide_cell(g, q0.y, (int)((q0.w >> 8) & 0xFFu));
-            const float bd = box_ray(cA.mn, cA.mx, o, inv);
-            if (bd == FLT_MAX) h[0] = h[1] = false;
-            else a01 = get(o, cA.axis) + bd * get(d, cA.axis) < cA.split;                           // :443-444
+            const WCell cX = wide_cell(g, needA ? q0.y : q0.z, (int)((q0.w >> (needA ? 8 : 16)) & 0xFFu));
+            const float bd = box_ray(cX.mn, cX.mx, o, inv);
+            const bool lowFirst = get(o, cX.axis) + bd * get(d, cX.axis) < cX.split;                // :443-444
+            if (needA) { if (bd == FLT_MAX) h[0] = h[1] = false; else a01 = lowFirst; }
+            else { if (bd == FLT_MAX) h[2] = h[3] = false; else b23 = lowFirst; }
         }
-        if (h[2] && h[3])
+        if (needA && needB)
         {
             const WCell cB = wide_cell(g, q0.z, (int)((q0.w >> 16) & 0xFFu));
             const float bd = box_ray(cB.mn, cB.mx, o, inv);

@@ -37,6 +37,16 @@ __device__ u32 lower_bound_code(const TreeView& tv, u32 lo, u32 hi, u64 key)
     return lo;
 }
 
+// Bricks and the implicit nodes above them are addressed by their cell coordinates: index(depth; ix, iy, iz) = ix << (by + bz) | iy << bz | iz
+// with bx, by, bz = splits on each axis among depths 0..depth-1; occ[(1 << depth) + index] is the node's occupancy, roots[index] at
+// depth `bits` the brick's subtree.
+__device__ __forceinline__ u32 cell_index(int depth, u32 ix, u32 iy, u32 iz)
+{
+    const int q = depth / 3, r = depth - 3 * q;
+    const int by = q + (r > 1 ? 1 : 0), bz = q;
+    return (ix << (by + bz)) | (iy << bz) | iz;
+}
+
 __global__ void brick_table_kernel(TreeView tv, int bits, u32* __restrict__ roots, unsigned char* __restrict__ occ)
 {
     const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,17 +64,22 @@ __global__ void brick_table_kernel(TreeView tv, int bits, u32* __restrict__ root
         const int hb = 31 - __clz((int)(cl ^ cr));
         ref = lower_bound_code(tv, lo, end, (u64)((cr >> hb) << hb)) - 1u;
     }
-    roots[b] = ref;
-    occ[(1u << bits) + b] = ref != BRICK_EMPTY;
+    u32 ix, iy, iz; decode_path(bits, b, ix, iy, iz);       // b is the brick's path code (the leading bits of its leaves' codes)
+    const u32 at = cell_index(bits, ix, iy, iz);
+    roots[at] = ref;
+    occ[(1u << bits) + at] = ref != BRICK_EMPTY;
 }
 
 // occupancy of the implicit levels above the bricks, one level per launch (a level has at most 2^14 nodes)
 __global__ void brick_occ_kernel(int depth, unsigned char* occ)
 {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (1u << depth)) return;
-    const u32 h = (1u << depth) + i;
-    occ[h] = occ[2 * h] | occ[2 * h + 1];
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;      // path code of the depth-`depth` node
+    if (p >= (1u << depth)) return;
+    u32 c[3]; decode_path(depth, p, c[0], c[1], c[2]);
+    const int axis = depth % 3;
+    u32 lo[3] = { c[0], c[1], c[2] }, hi[3] = { c[0], c[1], c[2] };
+    lo[axis] = 2u * c[axis]; hi[axis] = 2u * c[axis] + 1u;
+    occ[(1u << depth) + cell_index(depth, c[0], c[1], c[2])] = occ[(2u << depth) + cell_index(depth + 1, lo[0], lo[1], lo[2])] | occ[(2u << depth) + cell_index(depth + 1, hi[0], hi[1], hi[2])];
 }
 
 // The implicit top of the reference's traversal for one ray (oracle.cpp march_ray / BuildTree.cu:394-481 restricted to depth <= B):
@@ -73,6 +88,11 @@ __global__ void brick_occ_kernel(int depth, unsigned char* occ)
 // (the reference has no such node).  CLOSEST: the direct traversal culls with the boxes of whole triangles, which reach beyond their
 // cells by at most a triangle; a hit point itself always lies in a cell of its triangle, up to rounding, so here the cells are grown by
 // `pad` and every brick the forward ray touches is noted (the order only affects how early the search interval shrinks).
+// Segments are traced in WAVES of their position in the ray's order (0-1, 2-4, 5-9, 10+), brick by brick inside a wave: what a ray found in
+// an earlier wave is known when its later segments come up, so they are skipped (REFERENCE: the first brick with a hit decides) or start
+// with the search interval already cut (CLOSEST).  Without waves a batch with a 69 % hit rate walked 46 % more nodes than the direct traversal.
+__device__ __forceinline__ u32 seg_wave(u32 k) { return k < 2u ? 0u : (k < 5u ? 1u : (k < 10u ? 2u : 3u)); }
+
 template <int MODE>
 __global__ void __launch_bounds__(256) brick_segments_kernel(Grid g, int bits, const u32* __restrict__ roots, const unsigned char* __restrict__ occ,
                                                               const bmRay* __restrict__ rays, u64 n, float pad, u32* __restrict__ keys, u32* __restrict__ rayIdx,
@@ -86,30 +106,88 @@ __global__ void __launch_bounds__(256) brick_segments_kernel(Grid g, int bits, c
         const float* r = reinterpret_cast<const float*>(rays + i);
         const V3 o = mk3(__ldg(r), __ldg(r + 1), __ldg(r + 2)), d = mk3(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5));
         const V3 inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
-        u32 stack[BRICK_MAX_BITS + 2];
-        int top = 0;
-        stack[0] = 0u;                                    // depth << 16 | path
-        while (top >= 0)
+        // The cell of a child shares five of its six slab planes with its parent, so the slab distances (bMin - o) * inv, (bMax - o) * inv
+        // of bmBoxRayIntersect (CudaComon.cuh:158-172) are carried down and only the split plane's is computed per level -- the same
+        // operations on the same operands as evaluating the child's box from scratch, hence the same bits.  The near child continues in
+        // registers; the far one waits on a small stack with its slab distances.
+        u32 sE[BRICK_MAX_BITS + 1];
+        float sT[BRICK_MAX_BITS + 1][6];
+        int top = -1;
+        u32 e = 0u;                                       // depth << 24 | ix << 16 | iy << 8 | iz
+        float tlo[3], thi[3];                             // (bMin - o) * inv, (bMax - o) * inv per axis
         {
-            const u32 e = stack[top--];
-            const int depth = (int)(e >> 16);
-            const u32 path = e & 0xFFFFu;
-            u32 ix, iy, iz; decode_path(depth, path, ix, iy, iz);
-            V3 mn, mx; cell_box(g, depth, ix, iy, iz, mn, mx);
-            if (MODE != BM_TRACE_REFERENCE) { mn = mn - mk3(pad, pad, pad); mx = mx + mk3(pad, pad, pad); }
-            const float boxDist = box_ray(mn, mx, o, inv);
-            if (boxDist == FLT_MAX) continue;
-            if (depth == bits) { if (cnt < (u32)BR_MAX_SEGS) list[cnt++] = (unsigned short)path; continue; }
-            const int axis = depth % 3;
-            const u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
-            const int sh = g.k[axis] - axis_bits(depth, axis);
-            const float split = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
-            const float p = get(o, axis) + boxDist * get(d, axis);
-            const bool leftFirst = p < split;
-            const u32 h = (2u << depth) + (path << 1);    // heap index of the lower child
-            const u32 nearBit = leftFirst ? 0u : 1u, farBit = nearBit ^ 1u;
-            if (occ[h + farBit]) stack[++top] = ((u32)(depth + 1) << 16) | ((path << 1) | farBit);
-            if (occ[h + nearBit]) stack[++top] = ((u32)(depth + 1) << 16) | ((path << 1) | nearBit);
+            const float oo[3] = { o.x, o.y, o.z }, ii[3] = { inv.x, inv.y, inv.z };
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+            {
+                float lo = grid_at(g, a, 0u), hi = grid_at(g, a, 1u << g.k[a]);
+                if (MODE != BM_TRACE_REFERENCE) { lo -= pad; hi += pad; }
+                tlo[a] = (lo - oo[a]) * ii[a]; thi[a] = (hi - oo[a]) * ii[a];
+            }
+        }
+        for (;;)
+        {
+            bool pop = true;
+            // bmBoxRayIntersect on the carried slab distances
+            const float ftmax = fmin_(fmax_(tlo[0], thi[0]), fmin_(fmax_(tlo[1], thi[1]), fmax_(tlo[2], thi[2])));
+            if (!(ftmax < 0.f))
+            {
+                const float ftmin = fmax_(fmin_(tlo[0], thi[0]), fmax_(fmin_(tlo[1], thi[1]), fmin_(tlo[2], thi[2])));
+                if (ftmax >= ftmin)
+                {
+                    const float boxDist = fmax_(0.f, ftmin);
+                    const int depth = (int)(e >> 24);
+                    const u32 ix = (e >> 16) & 0xFFu, iy = (e >> 8) & 0xFFu, iz = e & 0xFFu;
+                    const int q = depth / 3, axis = depth - 3 * q;
+                    const int by = q + (axis > 1 ? 1 : 0), bz = q;
+                    if (depth == bits) { if (cnt < (u32)BR_MAX_SEGS) list[cnt++] = (unsigned short)((ix << (by + bz)) | (iy << bz) | iz); }
+                    else
+                    {
+                        const u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+                        const int sh = (axis == 0 ? g.k[0] : (axis == 1 ? g.k[1] : g.k[2])) - q - 1;      // leaf-level shift of the children's cells on this axis
+                        const u32 bi = ((ia << 1) | 1u) << sh;
+                        const float split = axis == 0 ? grid_at(g, 0, bi) : (axis == 1 ? grid_at(g, 1, bi) : grid_at(g, 2, bi));      // = .5f * (max + min) of the cell, BuildTree.cu:443
+                        const float oa = get(o, axis), ia_ = get(inv, axis);
+                        const float p = oa + boxDist * get(d, axis);
+                        const bool lowFirst = p < split;
+                        // the split plane as the low child's bMax and the high child's bMin (CLOSEST: each grown by the pad)
+                        const float tLowMax = ((MODE != BM_TRACE_REFERENCE ? split + pad : split) - oa) * ia_;
+                        const float tHighMin = ((MODE != BM_TRACE_REFERENCE ? split - pad : split) - oa) * ia_;
+                        const u32 cx = axis == 0 ? 2u * ix : ix, cy = axis == 1 ? 2u * iy : iy, cz = axis == 2 ? 2u * iz : iz;
+                        const int cby = by + (axis == 1 ? 1 : 0), cbz = bz + (axis == 2 ? 1 : 0);
+                        const u32 lowIdx = (cx << (cby + cbz)) | (cy << cbz) | cz;
+                        const u32 stepIdx = axis == 0 ? (1u << (cby + cbz)) : (axis == 1 ? (1u << cbz) : 1u);      // index distance between the two children
+                        const u32 lowEntry = ((u32)(depth + 1) << 24) | (cx << 16) | (cy << 8) | cz;
+                        const u32 stepEntry = axis == 0 ? (1u << 16) : (axis == 1 ? (1u << 8) : 1u);
+                        const unsigned char* oc = occ + (2u << depth) + lowIdx;
+                        const bool hasLow = oc[0] != 0, hasHigh = oc[stepIdx] != 0;
+                        const bool nearLow = lowFirst ? hasLow || !hasHigh : !hasHigh;      // the child to continue with: the near one if it exists, else the other
+                        if (hasLow && hasHigh)
+                        {
+                            // far child onto the stack with its slab distances
+                            ++top;
+                            sE[top] = lowFirst ? lowEntry + stepEntry : lowEntry;
+#pragma unroll
+                            for (int a = 0; a < 3; a++) { sT[top][a] = tlo[a]; sT[top][3 + a] = thi[a]; }
+                            if (lowFirst) sT[top][axis] = tHighMin; else sT[top][3 + axis] = tLowMax;
+                        }
+                        if (hasLow || hasHigh)
+                        {
+                            pop = false;
+                            if (nearLow) { e = lowEntry; if (axis == 0) thi[0] = tLowMax; else if (axis == 1) thi[1] = tLowMax; else thi[2] = tLowMax; }
+                            else { e = lowEntry + stepEntry; if (axis == 0) tlo[0] = tHighMin; else if (axis == 1) tlo[1] = tHighMin; else tlo[2] = tHighMin; }
+                        }
+                    }
+                }
+            }
+            if (pop)
+            {
+                if (top < 0) break;
+                e = sE[top];
+#pragma unroll
+                for (int a = 0; a < 3; a++) { tlo[a] = sT[top][a]; thi[a] = sT[top][3 + a]; }
+                --top;
+            }
         }
     }
     // one append per warp
@@ -125,7 +203,7 @@ __global__ void __launch_bounds__(256) brick_segments_kernel(Grid g, int bits, c
     for (u32 k = 0; k < cnt; k++)
     {
         const unsigned long long pos = at + k;
-        if (pos < capacity) { keys[pos] = (k << 16) | list[k]; rayIdx[pos] = (u32)i; }
+        if (pos < capacity) { keys[pos] = (k << 24) | (seg_wave(k) << bits) | list[k]; rayIdx[pos] = (u32)i; }
     }
 }
 

@@ -174,10 +174,10 @@ __device__ __forceinline__ WSlotBox slot_box(const Box2& b)
     return r;
 }
 
-// nodes128 (nullable): the uncompressed binary record of round 1 (BM_NODE_LAYOUT=both keeps it for A/B runs); wnodes: the 64-byte wide
-// record (bm_wide.cuh); nodeMeta[n] = (packed cell coordinates, depth) of node n, read back by n's parent when it absorbs n.
+// nodes (nullable): the 128-byte binary records; nodeMeta[n] = (packed cell coordinates, depth) of node n.  The 64-byte wide records are
+// written by wide_encode_kernel below from childRefs / nodeMeta / the boxes this pass leaves behind.
 __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 numLeaves, const float4* __restrict__ leafBox, float4* nodeBox,
-                                   int* otherBound, u32* childRefs, float4* nodes, uint4* wnodes, uint2* nodeMeta, u32* rootOut)
+                                   int* otherBound, u32* childRefs, float4* nodes, uint2* nodeMeta, u32* rootOut)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = (int)numLeaves;
@@ -203,13 +203,13 @@ __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 nu
         int plen = __clz(cl ^ cr) - (32 - D);         // common prefix length inside the D-bit code (l < r: codes differ)
         u32 prefix = plen > 0 ? (cl >> (D - plen)) : 0u;
         u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
-        V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
-        int axis = plen % 3;
-        u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
-        int sh = g.k[axis] - axis_bits(plen, axis);   // >= 1: the node splits on this axis
-        float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
         if (nodes)
         {
+            V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
+            int axis = plen % 3;
+            u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+            int sh = g.k[axis] - axis_bits(plen, axis);   // >= 1: the node splits on this axis
+            float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
             float4* np = nodes + NODE_F4 * (size_t)parent;
             np[0] = b0.a;                                                   // lo0.xyz hi0.x
             np[1] = make_float4(b0.b.x, b0.b.y, b1.a.x, b1.a.y);            // hi0.yz lo1.xy
@@ -218,41 +218,59 @@ __global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 nu
             np[4] = make_float4(mn.x, mn.y, mn.z, sp);
             np[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
         }
-        {
-            // the wide record: children that are internal nodes are absorbed (their own children become this record's slots)
-            const u32 cell0 = wide_pack_cell(g, ix, iy, iz);
-            if (wnodes)
-            {
-            u32 ref[4] = { c0, WREF_EMPTY, c1, WREF_EMPTY };
-            WSlotBox box[4];
-            box[0] = slot_box(b0); box[2] = slot_box(b1); box[1] = box[0]; box[3] = box[2];
-            u32 cellAB[2] = { 0u, 0u }, lenAB[2] = { WLEN_NONE, WLEN_NONE };
-#pragma unroll
-            for (int h = 0; h < 2; h++)
-            {
-                const u32 c = h ? c1 : c0;
-                if (c & LEAF_BIT) continue;
-                uint2 m = __ldcg(&nodeMeta[c]);
-                cellAB[h] = m.x; lenAB[h] = m.y;
-                u32 g0 = __ldcg(&childRefs[2 * (size_t)c]), g1 = __ldcg(&childRefs[2 * (size_t)c + 1]);
-                ref[2 * h] = g0; ref[2 * h + 1] = g1;
-                box[2 * h] = slot_box(load_box((g0 & LEAF_BIT) ? leafBox + 2 * (size_t)(g0 & ~LEAF_BIT) : nodeBox + 2 * (size_t)g0));
-                box[2 * h + 1] = slot_box(load_box((g1 & LEAF_BIT) ? leafBox + 2 * (size_t)(g1 & ~LEAF_BIT) : nodeBox + 2 * (size_t)g1));
-            }
-            WQ rec[4];
-            wide_encode(g, cell0, (u32)plen, cellAB[0], lenAB[0], cellAB[1], lenAB[1], ref, box, rec);
-            uint4* wp = wnodes + WNODE_U4 * (size_t)parent;
-#pragma unroll
-            for (int k = 0; k < 4; k++) wp[k] = make_uint4(rec[k].x, rec[k].y, rec[k].z, rec[k].w);
-            }
-            __stcg(&nodeMeta[parent], make_uint2(cell0, (u32)plen));
-        }
+        // (cell coordinates, depth) of the node: what the wide-record pass and bmTreeCopyTopology read
+        __stcg(&nodeMeta[parent], make_uint2(wide_pack_cell(g, ix, iy, iz), (u32)plen));
         if (l == 0 && r == n - 1) { *rootOut = (u32)parent; return; }
         float4* o = nodeBox + 2 * (size_t)parent;
         __stcg(o, make_float4(fminf(b0.a.x, b1.a.x), fminf(b0.a.y, b1.a.y), fminf(b0.a.z, b1.a.z), fmaxf(b0.a.w, b1.a.w)));
         __stcg(o + 1, make_float4(fmaxf(b0.b.x, b1.b.x), fmaxf(b0.b.y, b1.b.y), 0.f, 0.f));
         cur = (u32)parent;
     }
+}
+
+// The 64-byte wide records (bm_wide.cuh), one thread per internal node AFTER the bottom-up pass: node b's record absorbs its internal
+// children (their own children become b's slots), so it needs the child references, cell coordinates and boxes of two levels below b.
+// Inside the climb only the second arrival of every node is alive, a handful of lanes per warp, and the encoder (a search for the
+// quantisation grid, ~400 instructions) ran at that occupancy: 151 of 218 ms of a 100 M-triangle build.  Here every lane has a node.
+__global__ void __launch_bounds__(128) wide_encode_kernel(Grid g, u32 numNodes, const u32* __restrict__ childRefs, const uint2* __restrict__ nodeMeta,
+                                                          const float4* __restrict__ leafBox, const float4* __restrict__ nodeBox, uint4* __restrict__ wnodes)
+{
+    const u32 n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= numNodes) return;
+    const uint2 m0 = __ldg(&nodeMeta[n]);
+    const uint2 cc = __ldg(reinterpret_cast<const uint2*>(childRefs) + n);
+    const u32 c[2] = { cc.x, cc.y };
+    u32 ref[4] = { c[0], WREF_EMPTY, c[1], WREF_EMPTY };
+    WSlotBox box[4];
+    u32 cellAB[2] = { 0u, 0u }, lenAB[2] = { WLEN_NONE, WLEN_NONE };
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+        if (c[h] & LEAF_BIT)
+        {
+            const float4* p = leafBox + 2 * (size_t)(c[h] & ~LEAF_BIT);
+            Box2 b; b.a = __ldg(p); b.b = __ldg(p + 1);
+            box[2 * h] = slot_box(b); box[2 * h + 1] = box[2 * h];
+            continue;
+        }
+        const uint2 m = __ldg(&nodeMeta[c[h]]);
+        cellAB[h] = m.x; lenAB[h] = m.y;
+        const uint2 gg = __ldg(reinterpret_cast<const uint2*>(childRefs) + c[h]);
+        ref[2 * h] = gg.x; ref[2 * h + 1] = gg.y;
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+        {
+            const u32 gref = k ? gg.y : gg.x;
+            const float4* p = (gref & LEAF_BIT) ? leafBox + 2 * (size_t)(gref & ~LEAF_BIT) : nodeBox + 2 * (size_t)gref;
+            Box2 b; b.a = __ldg(p); b.b = __ldg(p + 1);
+            box[2 * h + k] = slot_box(b);
+        }
+    }
+    WQ rec[4];
+    wide_encode(g, m0.x, m0.y, cellAB[0], lenAB[0], cellAB[1], lenAB[1], ref, box, rec);
+    uint4* wp = wnodes + WNODE_U4 * (size_t)n;
+#pragma unroll
+    for (int k = 0; k < 4; k++) wp[k] = make_uint4(rec[k].x, rec[k].y, rec[k].z, rec[k].w);
 }
 
 __global__ void copy_topology_kernel(Grid g, const u32* __restrict__ childRefs, const uint2* __restrict__ meta, u32 n, u32* __restrict__ plen, u32* __restrict__ prefix,
@@ -355,8 +373,13 @@ int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const floa
 {
     if (numLeaves < 2) return BM_OK;
     BM_CUDA(cudaMemsetAsync(d_otherBound, 0xFF, (size_t)(numLeaves - 1) * 4, s));
-    agglomerate_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_otherBound, d_childRefs, d_nodes, d_wnodes, d_nodeMeta, d_root);
+    agglomerate_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_otherBound, d_childRefs, d_nodes, d_nodeMeta, d_root);
     BM_LAUNCHED();
+    if (d_wnodes)
+    {
+        wide_encode_kernel<<<div_up(numLeaves - 1, 128), 128, 0, s>>>(g, numLeaves - 1, d_childRefs, d_nodeMeta, d_leafBox2, d_nodeBox2, d_wnodes);
+        BM_LAUNCHED();
+    }
     return BM_OK;
 }
 int copy_topology(const Grid& g, const u32* d_childRefs, const uint2* d_nodeMeta, u32 numNodes, u32* d_prefixLen, u32* d_prefix, u32* d_child0, u32* d_child1, cudaStream_t s)

@@ -221,6 +221,123 @@ __device__ __forceinline__ u32 orderable(float f)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// ---- bulk-asynchronous staging of a leaf's run (BM_TMA_LEAF=1 builds) --------------------------------------------------------------
+// A leaf's triangle records are ONE contiguous run of 48-byte records and its cluster boxes one run of 32-byte records: the shape the
+// bulk copy engine wants.  The warp-cooperative leaf stages up to 32 groups (128 faces, 6 KB) and their boxes (1 KB) into the warp's
+// shared-memory buffer with two cp.async.bulk transfers completing on one mbarrier, then tests boxes and faces out of shared memory:
+// one asynchronous round trip instead of the two dependent rounds of per-lane loads (boxes, then the faces of the groups that pass).
+#ifndef BM_TMA_LEAF
+#define BM_TMA_LEAF 0
+#endif
+constexpr int TMA_GROUPS = 32;                                            // groups staged per step
+constexpr int TMA_TRI_BYTES = TMA_GROUPS * CLUSTER * 48, TMA_BOX_BYTES = TMA_GROUPS * 32;
+constexpr int TMA_WARP_BYTES = TMA_TRI_BYTES + TMA_BOX_BYTES;            // 7,168 bytes per warp
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+// coop_leaf with the run staged through shared memory (same tests, same winner rule)
+template <int MODE, bool COUNT>
+__device__ __forceinline__ void coop_leaf_staged(const TreeView& tv, unsigned lane, int owner, V3 o, V3 d, V3 ic, V3 oi, u32 first, u32 cnt, u32 cfirst,
+                                                 HitRec& best, u32& nt, u32& nc, unsigned char* stage, unsigned long long* bar, u32& phase)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    V3 ro = mk3(__shfl_sync(FULL, o.x, owner), __shfl_sync(FULL, o.y, owner), __shfl_sync(FULL, o.z, owner));
+    V3 rd = mk3(__shfl_sync(FULL, d.x, owner), __shfl_sync(FULL, d.y, owner), __shfl_sync(FULL, d.z, owner));
+    V3 ric = mk3(__shfl_sync(FULL, ic.x, owner), __shfl_sync(FULL, ic.y, owner), __shfl_sync(FULL, ic.z, owner));
+    V3 roi = mk3(__shfl_sync(FULL, oi.x, owner), __shfl_sync(FULL, oi.y, owner), __shfl_sync(FULL, oi.z, owner));
+    u32 lfirst = __shfl_sync(FULL, first, owner), lcnt = __shfl_sync(FULL, cnt, owner), lcf = __shfl_sync(FULL, cfirst, owner);
+    const float rbest = __shfl_sync(FULL, best.t, owner);
+    HitRec mine = { FLT_MAX, 0.f, 0.f, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };
+    const u32 ngroups = (lcnt + CLUSTER - 1) / CLUSTER;
+    u32 tests = 0, boxes = 0;
+    const float4* sTri = reinterpret_cast<const float4*>(stage);
+    const float4* sBox = reinterpret_cast<const float4*>(stage + TMA_TRI_BYTES);
+    for (u32 gbase = 0; gbase < ngroups; gbase += TMA_GROUPS)
+    {
+        const u32 gHere = min(ngroups - gbase, (u32)TMA_GROUPS);
+        const u32 f0 = gbase * CLUSTER, fHere = min(lcnt - f0, (u32)(TMA_GROUPS * CLUSTER));
+        const bool needBoxes = ngroups > 1;
+        if (lane == 0)
+        {
+            // the buffer was last read through the generic proxy: order those reads before the async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, fHere * 48u + (needBoxes ? gHere * 32u : 0u));
+            bulk_g2s(stage, tv.ltris + 3 * (size_t)(lfirst + f0), fHere * 48u, bar);
+            if (needBoxes) bulk_g2s(stage + TMA_TRI_BYTES, tv.clusters + CLUSTER_F4 * (size_t)(lcf + gbase), gHere * 32u, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        bool pass = false;
+        if (lane < gHere)
+        {
+            if (!needBoxes) pass = true;
+            else
+            {
+                float4 b0 = sBox[CLUSTER_F4 * lane], b1 = sBox[CLUSTER_F4 * lane + 1];
+                boxes++;
+                pass = cluster_hit<MODE>(mk3(b0.x, b0.y, b0.z), mk3(b0.w, b1.x, b1.y), ric, roi, rbest);
+            }
+        }
+        unsigned bits = __ballot_sync(FULL, pass);
+        u32 npass = __popc(bits);
+        for (u32 k0 = 0; k0 < npass; k0 += 8)
+        {
+            u32 k = k0 + (lane >> 2);
+            if (k < npass)
+            {
+                u32 grp = __fns(bits, 0, (int)k + 1);
+                u32 i = grp * CLUSTER + (lane & 3);
+                if (i < fHere)
+                {
+                    const float4* p = sTri + 3 * i;
+                    float4 a = p[0], b = p[1], c = p[2];
+                    tests++;
+                    test_face<MODE>(a, b, c, ro, rd, mine);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    u32 khi = orderable(mine.t), klo = mine.tri;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1)
+    {
+        u32 ohi = __shfl_xor_sync(FULL, khi, m), olo = __shfl_xor_sync(FULL, klo, m);
+        if (ohi < khi || (ohi == khi && olo < klo)) { khi = ohi; klo = olo; }
+    }
+    unsigned who = __ballot_sync(FULL, orderable(mine.t) == khi && mine.tri == klo);
+    int w = __ffs(who) - 1;
+    float wt = __shfl_sync(FULL, mine.t, w), wu = __shfl_sync(FULL, mine.u, w), wv = __shfl_sync(FULL, mine.v, w);
+    u32 wtri = __shfl_sync(FULL, mine.tri, w), wmesh = __shfl_sync(FULL, mine.mesh, w), wface = __shfl_sync(FULL, mine.face, w);
+    if (COUNT) { tests = __reduce_add_sync(FULL, tests); boxes = __reduce_add_sync(FULL, boxes); }
+    if ((int)lane == owner)
+    {
+        if (COUNT) { nt += tests; nc += boxes; }
+        if (wt < best.t || (wt == best.t && wt != FLT_MAX && wtri < best.tri))
+        {
+            best.t = wt; best.u = wu; best.v = wv; best.tri = wtri; best.mesh = wmesh; best.face = wface;
+        }
+    }
+}
+
 // Warp-cooperative leaf: all 32 lanes work on ONE ray's leaf -- 32 cluster boxes per step, then 32 faces per step (8 passing groups
 // of 4) -- and a 64-bit min-reduction picks the winner under the reference's rule (strict minimum d of any sign, smaller id on a
 // tie).  Used when only a few lanes of the warp have a leaf pending (the tail of a launch is a handful of long, grazing rays whose
@@ -417,6 +534,13 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31;
     __shared__ u32 pendS[CAMERA ? 1 : TR_QUEUE_MAX][TR_THREADS];      // postponed leaves of ray batches, [entry][thread]
+#if BM_TMA_LEAF
+    __shared__ __align__(128) unsigned char stageS[TR_THREADS / 32][TMA_WARP_BYTES];
+    __shared__ __align__(8) unsigned long long barS[TR_THREADS / 32];
+    u32 barPhase = 0;
+    if ((threadIdx.x & 31) == 0) { mbar_init(&barS[threadIdx.x >> 5], 1u); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+#endif
     u32 stack[TR_STACK];
     int top = -1;
     u32 cur = REF_EMPTY, npend = 0;
@@ -480,8 +604,8 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     // CLOSEST: the best hit so far bounds this segment's search.
                     const u32 key = __ldg(seg.keys + slot);
                     rayIdx = __ldg(seg.rays + slot);
-                    segSeq = key >> 16;
-                    startRef = __ldg(seg.roots + (key & 0xFFFFu));
+                    segSeq = key >> 24;
+                    startRef = __ldg(seg.roots + (key & seg.brickMask));
                     segKey0 = __ldcg(seg.rayKey + rayIdx);
                     if (MODE == BM_TRACE_REFERENCE && (u32)(segKey0 >> 32) < segSeq) take = false;
                 }
@@ -582,7 +706,11 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                 {
                     int owner = __ffs(pend) - 1;
                     pend &= pend - 1;
+#if BM_TMA_LEAF
+                    coop_leaf_staged<MODE, COUNT>(tv, lane, owner, o, d, ic, oi, first, cnt, cfirst, best, nt, nc, stageS[threadIdx.x >> 5], &barS[threadIdx.x >> 5], barPhase);
+#else
                     coop_leaf<MODE, COUNT>(tv, lane, owner, o, d, ic, oi, first, cnt, cfirst, best, nt, nc);
+#endif
                 }
                 if (cnt > (u32)COOP_MIN_FACES) cnt = 0;   // done: skip the per-lane path below
             }
@@ -755,7 +883,7 @@ bool use_wide(const TreeView& tv)
 
 template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG = false>
 int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
-                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, SegIn seg = SegIn{ nullptr, nullptr, nullptr, nullptr })
+                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, SegIn seg = SegIn{ nullptr, nullptr, nullptr, nullptr, 0u })
 {
     static std::atomic<int> occ[MAX_DEVICES];          // per device and per instantiation
     const int dev = current_device();

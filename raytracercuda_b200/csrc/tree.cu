@@ -516,15 +516,21 @@ static int brick_bits_for(const bmTree* t, uint64_t numRays)
 {
     static const int mode = getenv("BM_BRICKS") ? atoi(getenv("BM_BRICKS")) : -1;
     static const double minMB = getenv("BM_BRICK_MIN_MB") ? atof(getenv("BM_BRICK_MIN_MB")) : 512.0;
-    static const int bitsEnv = getenv("BM_BRICK_BITS") ? atoi(getenv("BM_BRICK_BITS")) : 12;
+    static const int bitsEnv = getenv("BM_BRICK_BITS") ? atoi(getenv("BM_BRICK_BITS")) : 0;
+    static const double brickMB = getenv("BM_BRICK_MB") ? atof(getenv("BM_BRICK_MB")) : 4.0;
     const int m = t->brickMode >= 0 ? t->brickMode : mode;
     if (m == 0 || t->L < 2 || numRays == 0 || numRays >= 0xFFFFFFF0ull) return 0;
-    if (m < 0)
-    {
-        const double bytes = (double)(t->L - 1) * (t->layout == BM_NODES_BINARY ? 128.0 : 64.0) + (double)t->L * 48.0 + (double)t->P * 56.0;
-        if (bytes < minMB * 1048576.0 || numRays < (1ull << 18)) return 0;
-    }
+    const double bytes = (double)(t->L - 1) * (t->layout == BM_NODES_BINARY ? 128.0 : 64.0) + (double)t->L * 48.0 + (double)t->P * 56.0;
+    if (m < 0 && (bytes < minMB * 1048576.0 || numRays < (1ull << 18))) return 0;
     int bits = t->brickBitsWanted ? t->brickBitsWanted : bitsEnv;
+    if (!bits)
+    {
+        // Measured on 20 M- and 100 M-triangle soups (8 - 16 M incoherent rays): 4 x 4 x 4 bricks beat 8^3 and 16^3 even where a brick is far
+        // larger than the L2 -- what pays is that the rays in flight share a region and meet its nodes together, while every additional
+        // segment per ray costs a sort entry and a restart.  Small trees get fewer bricks (BM_BRICK_MB = smallest brick worth having).
+        bits = 6;
+        while (bits > 3 && bytes / (double)(1u << bits) < brickMB * 1048576.0) bits -= 3;
+    }
     bits = bits < 3 ? 3 : (bits > BRICK_MAX_BITS ? BRICK_MAX_BITS : bits);
     if (bits > t->hgrid.D - 1) bits = t->hgrid.D - 1;
     return bits < 3 ? 0 : bits;
@@ -562,9 +568,9 @@ static int trace_bricked(bmTree* t, int bits, const bmRay* d_rays, uint64_t numR
     {
         BM_TRY(t->temp.reserve(sort_temp_bytes((size_t)S)));
         int inB = 0;
-        BM_TRY(radix_sort_pairs(t->segKeysA.as<u32>(), t->segValsA.as<u32>(), t->segKeysB.as<u32>(), t->segValsB.as<u32>(), (size_t)S, bits <= 8 ? 8 : 16, t->temp.p, s, &inB));
+        BM_TRY(radix_sort_pairs(t->segKeysA.as<u32>(), t->segValsA.as<u32>(), t->segKeysB.as<u32>(), t->segValsB.as<u32>(), (size_t)S, bits + 2, t->temp.p, s, &inB));      // by (wave, brick)
         SegIn seg = { inB ? t->segKeysB.as<u32>() : t->segKeysA.as<u32>(), inB ? t->segValsB.as<u32>() : t->segValsA.as<u32>(), t->brickRoots.as<u32>(),
-                      t->rayKey.as<unsigned long long>() };
+                      t->rayKey.as<unsigned long long>(), (1u << bits) - 1u };
         BM_TRY(trace_segments(tv, d_rays, S, mode, seg, d_counters, t->scalars.as<u32>() + 8, s));
     }
     if (d_hits) BM_TRY(brick_resolve(d_rays, numRays, mode, t->rayKey.as<unsigned long long>(), t->soup.as<float4>(), d_hits, s));
