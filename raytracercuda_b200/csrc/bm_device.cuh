@@ -61,6 +61,7 @@ struct TreeView
     const u32* root;      // device: index of the root node (numLeaves >= 2; a single leaf is its own root)
     Grid grid;            // the wide records store cell coordinates: boxes and planes are rebuilt from the grid
     float leafExt[3];     // largest leaf-cell extent per axis (+ the boxes' pad): reach of a leaf cell beyond the triangles it holds
+    float cellPad;        // CLOSEST mode culls with cells grown by this much (world extent * 2^-18: far above the rounding of a hit point)
 };
 
 // ---- scan.cu --------------------------------------------------------------------------------------------------------
@@ -167,7 +168,7 @@ int trace_rays_tiled(const TreeView& tv, const bmRay* d_rays, u64 n, u32 width, 
                      const TileSched* sched, cudaStream_t s);
 // Segments of a ray batch traced brick by brick (bricks.cu): keys[i] = position of the brick in the ray's visiting order << 24 | wave << bits | brick,
 // rays[i] = ray index, sorted by (wave, brick); roots[brick] = reference of the brick's subtree; rayKey[ray] = the ray's merged result.
-struct SegIn { const u32* keys; const u32* rays; const u32* roots; unsigned long long* rayKey; u32 brickMask; };
+struct SegIn { const u32* keys; const u32* rays; const u32* roots; unsigned long long* rayKey; u32 brickMask; u32 brickShift; };      // brick = (key >> brickShift) & brickMask
 int trace_segments(const TreeView& tv, const bmRay* d_rays, u64 numSegs, int mode, const SegIn& seg, u64* d_counters, u32* d_workCounter, cudaStream_t s);
 int clear_u32(u32* d_buf, size_t n, u32 value, cudaStream_t s);
 int shade_hits(const bmHit* d_hits, u64 n, const float4* d_soup, const bmStaticMeshData* d_meshData, const bmMaterial* d_materials, const bmTexture* d_textures,
@@ -182,6 +183,7 @@ constexpr int BRICK_MAX_BITS = 15;
 // roots[2^bits]: reference of the subtree holding exactly the leaves whose code starts with the brick's bits (BRICK_EMPTY: none);
 // occ[2^(bits+1)]: heap over the levels above (occ[(1 << d) + path] != 0: some leaf below the depth-d node `path`)
 int brick_table(const TreeView& tv, int bits, u32* d_roots, unsigned char* d_occ, cudaStream_t s);
+int brick_coherence_bits(int bits);      // low key bits that order the segments of one brick by entry point and direction octant (sort on bits + 2 + these)
 // one entry per (ray, brick entered), in the ray's visiting order: keys = order << 24 | wave << bits | brick, rays = ray index.  *d_count receives the
 // number of entries the batch needs; entries beyond `capacity` are not written.
 int brick_segments(const TreeView& tv, int bits, const u32* d_roots, const unsigned char* d_occ, const bmRay* d_rays, u64 n, int mode,

@@ -95,14 +95,25 @@ __device__ __forceinline__ bool box_interval(V3 bMin, V3 bMax, V3 o, V3 inv, flo
 
 // Internal node in CLOSEST mode: both tight boxes against [0, best.t], near child on top of the stack.  A popped subtree
 // whose box lies beyond the hit found meanwhile is rejected again when its own node is visited (its children fail).
+//
+// The stored child boxes are unions of WHOLE triangles (what the reference mode needs: it accepts a hit wherever the line meets a triangle
+// of a leaf whose cell the ray enters).  A closest hit with t >= 0 at point P is always found through the leaf whose CELL holds P -- every
+// cell a triangle overlaps lists it -- so here each child box is first cut down to the child's half of the node's cell (grown by cellPad
+// against rounding): a triangle spanning thousands of cells (f16's wings) no longer drags every ray near it through all of its leaves.
 __device__ __forceinline__ void closest_node(const TreeView& tv, u32 ref, V3 o, V3 inv, float tbest, u32* stack, int& top)
 {
     const float4* np = tv.nodes + NODE_F4 * (size_t)ref;
-    float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    float4 q4 = __ldg(np + 4), q5 = __ldg(np + 5), q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
     u32 c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y);
+    const float pad = tv.cellPad;
+    const int axis = (int)__float_as_uint(q5.w);
+    const V3 cmn = mk3(q4.x - pad, q4.y - pad, q4.z - pad), cmx = mk3(q5.x + pad, q5.y + pad, q5.z + pad);
+    const float sLo = q4.w - pad, sHi = q4.w + pad;                      // split plane: upper bound of child 0's half, lower bound of child 1's
+    const V3 hi0 = mk3(axis == 0 ? sHi : cmx.x, axis == 1 ? sHi : cmx.y, axis == 2 ? sHi : cmx.z);
+    const V3 lo1 = mk3(axis == 0 ? sLo : cmn.x, axis == 1 ? sLo : cmn.y, axis == 2 ? sLo : cmn.z);
     float t0, t1;
-    bool h0 = box_interval(mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), o, inv, tbest, t0);
-    bool h1 = box_interval(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), o, inv, tbest, t1);
+    bool h0 = box_interval(mk3(fmaxf(q0.x, cmn.x), fmaxf(q0.y, cmn.y), fmaxf(q0.z, cmn.z)), mk3(fminf(q0.w, hi0.x), fminf(q1.x, hi0.y), fminf(q1.y, hi0.z)), o, inv, tbest, t0);
+    bool h1 = box_interval(mk3(fmaxf(q1.z, lo1.x), fmaxf(q1.w, lo1.y), fmaxf(q2.x, lo1.z)), mk3(fminf(q2.y, cmx.x), fminf(q2.z, cmx.y), fminf(q2.w, cmx.z)), o, inv, tbest, t1);
     bool firstIs0 = t0 <= t1;
     u32 nearRef = firstIs0 ? c0 : c1, farRef = firstIs0 ? c1 : c0;
     bool nearHit = firstIs0 ? h0 : h1, farHit = firstIs0 ? h1 : h0;
@@ -605,7 +616,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     const u32 key = __ldg(seg.keys + slot);
                     rayIdx = __ldg(seg.rays + slot);
                     segSeq = key >> 24;
-                    startRef = __ldg(seg.roots + (key & seg.brickMask));
+                    startRef = __ldg(seg.roots + ((key >> seg.brickShift) & seg.brickMask));
                     segKey0 = __ldcg(seg.rayKey + rayIdx);
                     if (MODE == BM_TRACE_REFERENCE && (u32)(segKey0 >> 32) < segSeq) take = false;
                 }
@@ -694,7 +705,13 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                 {
                     if (box_ray(mk3(r1.x, r1.y, r1.z), mk3(r1.w, r2.x, r2.y), o, inv) != FLT_MAX) cnt = __float_as_uint(r0.z);      // BuildTree.cu:405-406
                 }
-                else cnt = __float_as_uint(r0.z);
+                else
+                {
+                    // CLOSEST: a hit inside this leaf's cell (grown by cellPad) is the only kind this leaf has to find (see closest_node)
+                    const float pad = tv.cellPad;
+                    float tn;
+                    if (box_interval(mk3(r1.x - pad, r1.y - pad, r1.z - pad), mk3(r1.w + pad, r2.x + pad, r2.y + pad), o, inv, best.t, tn)) cnt = __float_as_uint(r0.z);
+                }
             }
             // few lanes with a sizeable leaf to test: let the whole warp work on them one after the other (small leaves are cheaper
             // on their own lane)
@@ -883,7 +900,7 @@ bool use_wide(const TreeView& tv)
 
 template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG = false>
 int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
-                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, SegIn seg = SegIn{ nullptr, nullptr, nullptr, nullptr, 0u })
+                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, SegIn seg = SegIn{ nullptr, nullptr, nullptr, nullptr, 0u, 0u })
 {
     static std::atomic<int> occ[MAX_DEVICES];          // per device and per instantiation
     const int dev = current_device();

@@ -113,6 +113,7 @@ struct bmTree
             for (size_t i = 0; i + 1 < tb.size(); i++) m = fmaxf(m, tb[i + 1] - tb[i]);
             v.leafExt[a] = m * 1.0001f + (hgrid.wmax[a] - hgrid.wmin[a]) * (1.f / 262144.f);
         }
+        v.cellPad = fmaxf(fmaxf(hgrid.wmax[0] - hgrid.wmin[0], hgrid.wmax[1] - hgrid.wmin[1]), hgrid.wmax[2] - hgrid.wmin[2]) * (1.f / 262144.f);
         return v;
     }
     ~bmTree()
@@ -568,9 +569,9 @@ static int trace_bricked(bmTree* t, int bits, const bmRay* d_rays, uint64_t numR
     {
         BM_TRY(t->temp.reserve(sort_temp_bytes((size_t)S)));
         int inB = 0;
-        BM_TRY(radix_sort_pairs(t->segKeysA.as<u32>(), t->segValsA.as<u32>(), t->segKeysB.as<u32>(), t->segValsB.as<u32>(), (size_t)S, bits + 2, t->temp.p, s, &inB));      // by (wave, brick)
+        BM_TRY(radix_sort_pairs(t->segKeysA.as<u32>(), t->segValsA.as<u32>(), t->segKeysB.as<u32>(), t->segValsB.as<u32>(), (size_t)S, bits + 2 + brick_coherence_bits(bits), t->temp.p, s, &inB));      // by (wave, brick, entry point + octant)
         SegIn seg = { inB ? t->segKeysB.as<u32>() : t->segKeysA.as<u32>(), inB ? t->segValsB.as<u32>() : t->segValsA.as<u32>(), t->brickRoots.as<u32>(),
-                      t->rayKey.as<unsigned long long>(), (1u << bits) - 1u };
+                      t->rayKey.as<unsigned long long>(), (1u << bits) - 1u, (u32)brick_coherence_bits(bits) };
         BM_TRY(trace_segments(tv, d_rays, S, mode, seg, d_counters, t->scalars.as<u32>() + 8, s));
     }
     if (d_hits) BM_TRY(brick_resolve(d_rays, numRays, mode, t->rayKey.as<unsigned long long>(), t->soup.as<float4>(), d_hits, s));
