@@ -276,9 +276,11 @@ def run_b200(args):
         dist.broadcast(stats_t, 0)
     st = dict(zip(stat_keys, [int(x) for x in stats_t.cpu()]))
     hits1 = torch.empty((n, 4), dtype=torch.float32, device=dev); pixels = torch.empty(n, dtype=torch.int32, device=dev)
-    rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev)
-    src2 = torch.empty(n, dtype=torch.int32, device=dev); cnt2 = torch.zeros(1, dtype=torch.int32, device=dev)
-    hits2 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    # multi-sample frames collect the bounce rays of GROUP samples in one list, traced by one launch (as ICamera::traceSceneProgressive does)
+    GROUP = max(1, min(SPP, 8, (32 << 20) // n))
+    rays2 = torch.empty((n * GROUP, 6), dtype=torch.float32, device=dev)
+    src2 = torch.empty(n * GROUP, dtype=torch.int32, device=dev); cnt2 = torch.zeros(1, dtype=torch.int32, device=dev)
+    hits2 = torch.empty((n * GROUP, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -334,14 +336,18 @@ def run_b200(args):
         """multi-sample frame (configs 3 and 4): per sample jittered camera rays -> trace -> bounce rays -> trace -> accumulate; resolve"""
         acc.zero_(); cov.zero_(); cnt_sum.zero_()
         sp = C.c_void_p(stream.cuda_stream)
-        for sidx in range(SPP):
-            # the sample's jitter is applied where the trace kernel forms the ray (no 24-byte ray record per sample is written or read);
-            # the launch is a camera launch: 8x4 tiles under the temporal tile schedule
-            _lib.check(L.bmTraceCameraJittered(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], jit[0], jit[1], sidx, args.seed, 0, hits1.data_ptr(), None, None, None), "bmTraceCameraJittered")
-            _lib.check(L.bmBounceRaysCameraJittered(tree.h, rays_in.data_ptr(), p[0], p[1], jit[0], jit[1], sidx, args.seed, hits1.data_ptr(), n, sidx, 1, args.seed,
-                                                    rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCameraJittered")
-            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRaysIndirect")
-            _lib.check(L.bmProgressiveAccumulate(hits1.data_ptr(), n, hits2.data_ptr(), src2.data_ptr(), cnt2.data_ptr(), 0.25, acc.data_ptr(), cov.data_ptr(), sp), "accumulate")
+        for s0 in range(0, SPP, GROUP):
+            g_ = min(GROUP, SPP - s0)
+            cnt2.zero_()
+            for sidx in range(s0, s0 + g_):
+                # the sample's jitter is applied where the trace kernel forms the ray (no 24-byte ray record per sample is written or read);
+                # the launch is a camera launch: 8x4 tiles under the temporal tile schedule
+                _lib.check(L.bmTraceCameraJittered(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], jit[0], jit[1], sidx, args.seed, 0, hits1.data_ptr(), None, None, None), "bmTraceCameraJittered")
+                _lib.check(L.bmProgressiveAccumulate(hits1.data_ptr(), n, None, None, None, 0.25, acc.data_ptr(), cov.data_ptr(), sp), "accumulate")
+                _lib.check(L.bmBounceRaysCameraAppend(tree.h, rays_in.data_ptr(), p[0], p[1], jit[0], jit[1], sidx, args.seed, hits1.data_ptr(), n, sidx, 1, args.seed,
+                                                      rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCameraAppend")
+            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n * g_, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRaysIndirect")
+            _lib.check(L.bmProgressiveAccumulateBounce(hits2.data_ptr(), src2.data_ptr(), cnt2.data_ptr(), n * g_, 0.75, acc.data_ptr(), sp), "accumulate bounce")
             cnt_sum.add_(cnt2)
         _lib.check(L.bmProgressiveResolve(acc.data_ptr(), cov.data_ptr(), n, SPP, pixels.data_ptr(), sp), "resolve")
         cnt_host.copy_(cnt_sum.to(torch.int32), non_blocking=True)
@@ -436,7 +442,7 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     V1, K1, C1, LONG1 = [int(x) for x in cnt.cpu()]
     V2 = K2 = C2 = 0
-    nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST sample only
+    nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST group of samples only
     if nb_last:
         cnt.zero_()
         _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, BOUNCE_MODE, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
@@ -648,7 +654,8 @@ def run_b200(args):
             _lib.check(L.bmTraceCamera(tree.h, r_.data_ptr(), w_ * h_, w_, p0[0], p0[1], 0, None, p_.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
             torch.cuda.synchronize(dev)
             return p_.cpu().numpy().view(np.uint32)
-        line["cpu_baseline"] = cpu_baseline(wl, rays_host, rays2[:nb].cpu().numpy() if nb else None, src2[:nb].cpu().numpy() if nb else None,
+        nbb = nb if SPP == 1 else nb_last                    # multi-sample frames: the bounce list of the last group of samples
+        line["cpu_baseline"] = cpu_baseline(wl, rays_host, rays2[:nbb].cpu().numpy() if nbb else None, src2[:nbb].cpu().numpy() if nbb else None,
                                             gpu_pixels_fn=gpu_frame_pixels)
         def ours_scene(name_):
             """this library on one of the reference-kernel scenes: build (best of 3) and the primary launch at 1280x720 (mean of 5 after warm-up)"""

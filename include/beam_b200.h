@@ -266,6 +266,14 @@ int  bmBounceRaysCameraJittered(bmTree* tree, const float* d_initialRays3, const
                                 uint32_t cameraSample, uint32_t cameraSeed, const bmHit* d_hits, uint64_t numRays,
                                 uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count);
 
+/* Append form of bmBounceRaysCameraJittered: the rays go BEHIND the *d_total rays already in d_out / d_srcIndex (device uint32, in/out; the
+ * caller zeroes it before the first call and sizes the buffers for all samples it will append), so that the bounce rays of several samples
+ * of a frame are traced by one bmTraceRaysIndirect launch -- one sample of a small scene yields too few to fill the GPU.  d_srcIndex
+ * receives the pixel (index in the camera table) of every ray; the same pixel may appear once per appended sample. */
+int  bmBounceRaysCameraAppend(bmTree* tree, const float* d_initialRays3, const float* eye3, const float* orient9, float jitterX, float jitterY,
+                              uint32_t cameraSample, uint32_t cameraSeed, const bmHit* d_hits, uint64_t numRays,
+                              uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_total);
+
 /* Progressive accumulation over samples (defined by this repo; the reference's SceneProgressive is an empty stub): one sample of a
  * pixel = `ambient` if its primary ray hit + (1 - ambient) if the diffuse bounce ray of that hit escaped.  d_accum (float) and
  * d_covered (uint32) are per pixel and must start zeroed; d_hits2 / d_src2 / d_count2 are bmBounceRays' outputs after tracing (pass
@@ -273,6 +281,9 @@ int  bmBounceRaysCameraJittered(bmTree* tree, const float* d_initialRays3, const
  * reference's miss colour (255 << 8) where no sample ever hit. */
 int  bmProgressiveAccumulate(const bmHit* d_hits1, uint64_t numRays, const bmHit* d_hits2, const uint32_t* d_src2, const uint32_t* d_count2,
                              float ambient, float* d_accum, uint32_t* d_covered, void* cudaStream);
+/* the bounce half of bmProgressiveAccumulate for a list that holds several samples (bmBounceRaysCameraAppend): d_accum[d_src2[k]] +=
+ * weight for every escaped ray k < *d_count2, with atomic adds (a pixel may occur once per sample); maxRays sizes the launch */
+int  bmProgressiveAccumulateBounce(const bmHit* d_hits2, const uint32_t* d_src2, const uint32_t* d_count2, uint64_t maxRays, float weight, float* d_accum, void* cudaStream);
 int  bmProgressiveResolve(const float* d_accum, const uint32_t* d_covered, uint64_t numRays, uint32_t samples, uint32_t* d_pixels, void* cudaStream);
 
 /* Deferred shading of hit records (what the reference's bmHitCallback / bmMaterial / VERTEX_DATA_UV1 declare but never implement,

@@ -195,7 +195,8 @@ int brick_resolve(const bmRay* d_rays, u64 n, int mode, const unsigned long long
 int camera_rays(const CameraIn& cam, u64 n, bmRay* d_out, cudaStream_t s);
 int add_count(const u32* d_count, u64 add, u64* d_total, cudaStream_t s);      // *d_total += *d_count + add (ray accounting without a host round trip)
 int bounce_rays(const bmRay* d_rays, const CameraIn* cam, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed,
-                u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s);
+                u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s, u32* d_appendTotal = nullptr);
+int progressive_accumulate_bounce(const bmHit* d_hits2, const u32* d_src2, const u32* d_count2, u64 maxRays, float weight, float* d_accum, cudaStream_t s);
 int progressive_accumulate(const bmHit* d_hits1, u64 n, const bmHit* d_hits2, const u32* d_src2, const u32* d_count2, float ambient, float* d_accum,
                            u32* d_covered, cudaStream_t s);
 int progressive_resolve(const float* d_accum, const u32* d_covered, u64 n, u32 samples, u32* d_pixels, cudaStream_t s);

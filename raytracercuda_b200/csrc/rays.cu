@@ -28,7 +28,8 @@ __global__ void add_count_kernel(const u32* __restrict__ count, u64 add, u64* to
 
 template <bool CAMERA>
 __global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, const bmHit* __restrict__ hits, const u32* __restrict__ offsets, u64 n,
-                              const float4* __restrict__ soup, u32 sample, u32 bounce, u32 seed, bmRay* __restrict__ out, u32* __restrict__ srcIndex)
+                              const float4* __restrict__ soup, u32 sample, u32 bounce, u32 seed, bmRay* __restrict__ out, u32* __restrict__ srcIndex,
+                              const u32* __restrict__ appendBase)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -66,7 +67,7 @@ __global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, cons
     bmRay o;
     o.o[0] = hp.x + 1e-4f * nrm.x; o.o[1] = hp.y + 1e-4f * nrm.y; o.o[2] = hp.z + 1e-4f * nrm.z;
     o.d[0] = nd.x; o.d[1] = nd.y; o.d[2] = nd.z;
-    u32 k = offsets[i];
+    u32 k = offsets[i] + (appendBase ? *appendBase : 0u);      // append mode: behind the rays other launches already put into the list
     out[k] = o;
     if (srcIndex) srcIndex[k] = (u32)i;
 }
@@ -88,6 +89,15 @@ __global__ void accumulate_bounce_kernel(const bmHit* __restrict__ hits2, const 
     if (k >= *count) return;
     if (hits2[k].tri == 0xFFFFFFFFu) accum[src[k]] += weight;       // src is injective (one bounce ray per primary hit): no atomics needed
 }
+// a list that holds the bounce rays of SEVERAL samples may name a pixel more than once: atomic adds
+__global__ void accumulate_bounce_atomic_kernel(const bmHit* __restrict__ hits2, const u32* __restrict__ src, const u32* __restrict__ count, float weight,
+                                                float* __restrict__ accum)
+{
+    u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *count) return;
+    if (hits2[k].tri == 0xFFFFFFFFu) atomicAdd(&accum[src[k]], weight);
+}
+__global__ void append_count_kernel(u32* total, const u32* __restrict__ count) { *total += *count; }
 __global__ void resolve_kernel(const float* __restrict__ accum, const u32* __restrict__ covered, u64 n, float invSamples, u32* __restrict__ pixels)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,6 +120,13 @@ int progressive_accumulate(const bmHit* d_hits1, u64 n, const bmHit* d_hits2, co
         accumulate_bounce_kernel<<<div_up(n, 256), 256, 0, s>>>(d_hits2, d_src2, d_count2, 1.f - ambient, d_accum);
         BM_LAUNCHED();
     }
+    return BM_OK;
+}
+int progressive_accumulate_bounce(const bmHit* d_hits2, const u32* d_src2, const u32* d_count2, u64 maxRays, float weight, float* d_accum, cudaStream_t s)
+{
+    if (!maxRays) return BM_OK;
+    accumulate_bounce_atomic_kernel<<<div_up(maxRays, 256), 256, 0, s>>>(d_hits2, d_src2, d_count2, weight, d_accum);
+    BM_LAUNCHED();
     return BM_OK;
 }
 int progressive_resolve(const float* d_accum, const u32* d_covered, u64 n, u32 samples, u32* d_pixels, cudaStream_t s)
@@ -136,13 +153,16 @@ int add_count(const u32* d_count, u64 add, u64* d_total, cudaStream_t s)
 }
 
 int bounce_rays(const bmRay* d_rays, const CameraIn* cam, const bmHit* d_hits, u64 n, const float4* d_soup, u32 sample, u32 bounce, u32 seed,
-                u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s)
+                u32* d_flagsAndOffsets, void* d_scanTemp, bmRay* d_out, u32* d_srcIndex, u32* d_count, cudaStream_t s, u32* d_appendTotal)
 {
+    // d_appendTotal (nullable, device): append mode -- the rays go behind the *d_appendTotal rays already in d_out / d_srcIndex and the
+    // total grows by this launch's count (d_count then receives this launch's own count)
     if (!n) { BM_CUDA(cudaMemsetAsync(d_count, 0, 4, s)); return BM_OK; }
     BM_TRY(exclusive_scan_hit_flags(d_hits, d_flagsAndOffsets, n, d_count, d_scanTemp, s));
-    if (cam) bounce_kernel<true><<<div_up(n, 256), 256, 0, s>>>(nullptr, *cam, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex);
-    else { CameraIn none = make_camera(nullptr, nullptr, nullptr); bounce_kernel<false><<<div_up(n, 256), 256, 0, s>>>(d_rays, none, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex); }
+    if (cam) bounce_kernel<true><<<div_up(n, 256), 256, 0, s>>>(nullptr, *cam, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex, d_appendTotal);
+    else { CameraIn none = make_camera(nullptr, nullptr, nullptr); bounce_kernel<false><<<div_up(n, 256), 256, 0, s>>>(d_rays, none, d_hits, d_flagsAndOffsets, n, d_soup, sample, bounce, seed, d_out, d_srcIndex, d_appendTotal); }
     BM_LAUNCHED();
+    if (d_appendTotal) { append_count_kernel<<<1, 1, 0, s>>>(d_appendTotal, d_count); BM_LAUNCHED(); }
     return BM_OK;
 }
 } // namespace bm

@@ -79,7 +79,26 @@ __device__ __forceinline__ void ref_node(const TreeView& tv, u32 ref, V3 o, V3 d
     bool h1 = line_hits_box_fma(mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w), ic, oi);
     u32 nearRef = leftFirst ? c0 : c1, farRef = leftFirst ? c1 : c0;
     bool nearHit = leftFirst ? h0 : h1, farHit = leftFirst ? h1 : h0;
-    if (farHit) stack[++top] = farRef;
+    if (farHit)
+    {
+        // Does the forward ray reach the FAR half of this cell at all?  Every leaf cell below the far child lies inside that half, and the
+        // reference tests a leaf only if the ray enters its cell (:398-406), so a far half the ray provably misses cannot contribute: the
+        // child would be rejected by its own cell test on arrival, and is not pushed.  Cheap slabs (one FMA per plane; five planes are the
+        // cell's, the sixth is the split plane) with a margin that covers their rounding, including the cancellation when |o / d| is large:
+        // the decision is only ever "provably missed".
+        const float sx0 = __fmaf_rn(q4.x, ic.x, -oi.x), sx1 = __fmaf_rn(q5.x, ic.x, -oi.x);
+        const float sy0 = __fmaf_rn(q4.y, ic.y, -oi.y), sy1 = __fmaf_rn(q5.y, ic.y, -oi.y);
+        const float sz0 = __fmaf_rn(q4.z, ic.z, -oi.z), sz1 = __fmaf_rn(q5.z, ic.z, -oi.z);
+        const float ts = __fmaf_rn(q4.w, get(ic, axis), -get(oi, axis));
+        // far = upper half when the near one is the lower: its low plane on `axis` is the split plane
+        const float ax0 = axis == 0 ? (leftFirst ? ts : sx0) : sx0, ax1 = axis == 0 ? (leftFirst ? sx1 : ts) : sx1;
+        const float ay0 = axis == 1 ? (leftFirst ? ts : sy0) : sy0, ay1 = axis == 1 ? (leftFirst ? sy1 : ts) : sy1;
+        const float az0 = axis == 2 ? (leftFirst ? ts : sz0) : sz0, az1 = axis == 2 ? (leftFirst ? sz1 : ts) : sz1;
+        const float tn = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fminf(az0, az1));
+        const float tf = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fmaxf(az0, az1));
+        const float margin = 1e-5f * (fabsf(tn) + fabsf(tf) + fabsf(oi.x) + fabsf(oi.y) + fabsf(oi.z)) + 1e-30f;
+        if (!(tf + margin < fmaxf(tn, 0.f))) stack[++top] = farRef;
+    }
     if (nearHit) stack[++top] = nearRef;
 }
 

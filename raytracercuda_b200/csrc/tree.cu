@@ -687,6 +687,28 @@ extern "C" int bmBounceRaysCameraJittered(bmTree* t, const float* d_initialRays3
     return bounce_rays(nullptr, &cam, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex, d_count, t->stream);
 }
 
+// append form: the bounce rays of several samples collected in ONE list (traced by one bmTraceRaysIndirect launch: a single sample of a
+// small scene yields too few bounce rays to fill the GPU).  *d_total (device u32, in/out) = rays already in d_out / d_srcIndex.
+extern "C" int bmBounceRaysCameraAppend(bmTree* t, const float* d_initialRays3, const float* eye3, const float* orient9, float jitterX, float jitterY,
+                                        uint32_t cameraSample, uint32_t cameraSeed, const bmHit* d_hits, uint64_t numRays,
+                                        uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_total)
+{
+    if (!t || !d_total || !eye3 || !orient9 || ((!d_initialRays3 || !d_hits || !d_out) && numRays) || numRays >= 0xFFFFFFFFull) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    BM_TRY(t->rayFlags.reserve(numRays * 4 + 4));
+    BM_TRY(t->rayTemp.reserve(scan_temp_bytes(numRays)));
+    BM_TRY(t->scalars.reserve(64));
+    CameraIn cam = make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, cameraSample, cameraSeed);
+    return bounce_rays(nullptr, &cam, d_hits, numRays, t->soup.as<float4>(), sample, bounce, seed, t->rayFlags.as<u32>(), t->rayTemp.p, d_out, d_srcIndex,
+                       t->scalars.as<u32>() + 14, t->stream, d_total);
+}
+
+extern "C" int bmProgressiveAccumulateBounce(const bmHit* d_hits2, const uint32_t* d_src2, const uint32_t* d_count2, uint64_t maxRays, float weight, float* d_accum, void* stream)
+{
+    if ((!d_hits2 || !d_src2 || !d_count2 || !d_accum) && maxRays) return BM_ERROR_INVALID_PARAMETER;
+    return progressive_accumulate_bounce(d_hits2, d_src2, d_count2, maxRays, weight, d_accum, (cudaStream_t)stream);
+}
+
 extern "C" int bmBounceRaysCamera(bmTree* t, const float* d_initialRays3, const float* eye3, const float* orient9, const bmHit* d_hits, uint64_t numRays,
                                   uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_count)
 {
