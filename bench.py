@@ -231,8 +231,10 @@ def run_b200(args):
     wl = workloads.get(args.workload)
     SPP = wl.samples
     # weak scaling (default; the driver's 1 -> 8 run): every rank renders a full-size image = interleaved rows of an N-times taller one.
-    # strong scaling (--scaling strong; default for the multi-sample c3 / c4 frames): ONE frame of the workload's size, rank r renders rows
-    # r, r + N, ... of it (interleaved rows = image tiles 1 row high: every rank sees the same mix of silhouette and background)
+    # strong scaling (--scaling strong; default for the multi-sample c3 / c4 frames): ONE frame of the workload's size; rank r renders the
+    # bands of 4 rows r, r + N, ... of it (interleaved image tiles one 8x4 tile row high: every rank sees the same mix of silhouette and
+    # background, and its 8x4 tiles are tiles of neighbouring pixels of the real image); the e2e leg, which goes through
+    # ICamera::setInitialRays, renders rows r, r + N, ... (the only interleave a frustum can express)
     strong = (args.scaling == "strong") or (args.scaling == "auto" and SPP > 1)
     W = wl.width
     if strong and wl.height % world:
@@ -253,6 +255,14 @@ def run_b200(args):
     cam = host.ICamera.create()
     assert cam.setInitialRays(W, H, *frustum) == 0
     rays_host = cam.initialRays()
+    H_e2e, n_e2e, frustum_h = H, n, H
+    if strong and world > 1:
+        cam_full = host.ICamera.create()
+        assert cam_full.setInitialRays(W, wl.height, *wl.frustum) == 0
+        rows = np.array([y for y in range(wl.height) if (y // 4) % world == rank], np.int64)
+        rays_host = np.ascontiguousarray(cam_full.initialRays().reshape(wl.height, W, 3)[rows].reshape(-1, 3))
+        H = int(rows.size); n = W * H; frustum_h = wl.height
+        del cam_full
     rays_dev = torch.from_numpy(rays_host).to(dev)
     Pd = torch.from_numpy(wl.positions).to(dev); Id = torch.from_numpy(wl.indices.view(np.int32)).to(dev).reshape(-1); Nd = torch.from_numpy(wl.normals).to(dev)
     table = make_mesh_table([(Pd, Id, Nd)], dev)
@@ -275,40 +285,44 @@ def run_b200(args):
     if world > 1:
         dist.broadcast(stats_t, 0)
     st = dict(zip(stat_keys, [int(x) for x in stats_t.cpu()]))
-    hits1 = torch.empty((n, 4), dtype=torch.float32, device=dev); pixels = torch.empty(n, dtype=torch.int32, device=dev)
-    # multi-sample frames collect the bounce rays of GROUP samples in one list, traced by one launch (as ICamera::traceSceneProgressive does)
+    pixels = torch.empty(n, dtype=torch.int32, device=dev)
+    # multi-sample frames trace GROUP samples of every pixel per launch, then the bounce rays of those samples in one bounce launch (as ICamera::traceSceneProgressive does)
     GROUP = max(1, min(SPP, 8, (32 << 20) // n))
-    rays2 = torch.empty((n * GROUP, 6), dtype=torch.float32, device=dev)
-    src2 = torch.empty(n * GROUP, dtype=torch.int32, device=dev); cnt2 = torch.zeros(1, dtype=torch.int32, device=dev)
+    hits1 = torch.empty((n * GROUP, 4), dtype=torch.float32, device=dev)
     hits2 = torch.empty((n * GROUP, 4), dtype=torch.float32, device=dev)
+    nbounce = torch.zeros(1, dtype=torch.int64, device=dev)              # bounce rays traced in the step (counted by the bounce launches)
+    # instrumentation outside the timed region (traversal counters, CPU baseline): the bounce rays of one sample as a list
+    rays2 = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    src2 = torch.empty(n, dtype=torch.int32, device=dev); cnt2 = torch.zeros(1, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    cnt_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    cnt_host = torch.zeros(1, dtype=torch.int64).pin_memory()
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    jit = (abs(wl.frustum[1] - wl.frustum[0]) / W / wl.frustum[4], abs(frustum[3] - frustum[2]) / H / wl.frustum[4])
+    jit = (abs(wl.frustum[1] - wl.frustum[0]) / W / wl.frustum[4], abs(frustum[3] - frustum[2]) / frustum_h / wl.frustum[4])
     acc = torch.zeros(n, dtype=torch.float32, device=dev) if SPP > 1 else None
     cov = torch.zeros(n, dtype=torch.int32, device=dev) if SPP > 1 else None
-    cnt_sum = torch.zeros(1, dtype=torch.int64, device=dev)
 
     # --- the framebuffer of all ranks on every rank -----------------------------------------------------------------------
     # Preferred: symmetric memory -- every rank writes its rows straight into each peer's copy of the gathered frame with copy-engine
     # transfers over NVLink (no SM is taken from the persistent trace grids); fallback: NCCL all-gather on a side stream.
     gathered, comm, symm = None, None, None
+    n_max = n
     if world > 1:
+        nm = torch.tensor([n], dtype=torch.int64, device=dev); dist.all_reduce(nm, op=dist.ReduceOp.MAX); n_max = int(nm.item())
         comm = torch.cuda.Stream(dev)
         if not os.environ.get("BENCH_NO_SYMM"):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                gathered = symm_mem.empty((world, n), dtype=torch.int32, device=dev)
+                gathered = symm_mem.empty((world, n_max), dtype=torch.int32, device=dev)
                 hdl = symm_mem.rendezvous(gathered, dist.group.WORLD)
-                peers = [hdl.get_buffer(r_, (world, n), torch.int32) for r_ in range(world)]
+                peers = [hdl.get_buffer(r_, (world, n_max), torch.int32) for r_ in range(world)]
                 symm = (hdl, peers)
                 # prove the path once against NCCL
                 probe = torch.full((n,), rank + 1, dtype=torch.int32, device=dev)
                 for r_ in range(world):
-                    peers[r_][rank].copy_(probe, non_blocking=True)
+                    peers[r_][rank][:n].copy_(probe, non_blocking=True)
                 torch.cuda.synchronize(dev); dist.barrier(); torch.cuda.synchronize(dev)
                 want = torch.arange(1, world + 1, dtype=torch.int32, device=dev)
-                if not bool((gathered[:, 0] == want).all()) or not bool((gathered[:, -1] == want).all()):
+                if not bool((gathered[:, 0] == want).all()):
                     raise RuntimeError("symmetric-memory gather check failed")
             except Exception as ex:
                 sys.stderr.write("rank %d: symmetric-memory gather unavailable (%r): NCCL all-gather\n" % (rank, ex))
@@ -317,7 +331,10 @@ def run_b200(args):
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         if int(ok_t.item()) == 0:
             symm = None
-            gathered = torch.empty((world, n), dtype=torch.int32, device=dev)
+            gathered = torch.empty((world, n_max), dtype=torch.int32, device=dev)
+    pixels_padded = None
+    if world > 1 and symm is None and n != n_max:
+        pixels_padded = torch.zeros(n_max, dtype=torch.int32, device=dev)     # NCCL all-gather wants equal shares
 
     def gather_frame(src_pixels, after_event):
         """issue the gather of this rank's rows on the side stream once `after_event` has passed; returns a callable that makes the compute stream wait for it"""
@@ -326,31 +343,28 @@ def run_b200(args):
             if symm is not None:
                 for k in range(world):
                     r_ = (rank + k) % world
-                    symm[1][r_][rank].copy_(src_pixels, non_blocking=True)
+                    symm[1][r_][rank][:n].copy_(src_pixels, non_blocking=True)
                 done = torch.cuda.Event(); done.record(comm)
                 return lambda: stream.wait_event(done)
+            if pixels_padded is not None:
+                pixels_padded[:n].copy_(src_pixels); src_pixels = pixels_padded
             work = dist.all_gather_into_tensor(gathered.view(-1), src_pixels, async_op=True)
             return work.wait
 
     def frame_spp(rays_in, p):
         """multi-sample frame (configs 3 and 4): per sample jittered camera rays -> trace -> bounce rays -> trace -> accumulate; resolve"""
-        acc.zero_(); cov.zero_(); cnt_sum.zero_()
+        acc.zero_(); cov.zero_(); nbounce.zero_()
         sp = C.c_void_p(stream.cuda_stream)
         for s0 in range(0, SPP, GROUP):
             g_ = min(GROUP, SPP - s0)
-            cnt2.zero_()
-            for sidx in range(s0, s0 + g_):
-                # the sample's jitter is applied where the trace kernel forms the ray (no 24-byte ray record per sample is written or read);
-                # the launch is a camera launch: 8x4 tiles under the temporal tile schedule
-                _lib.check(L.bmTraceCameraJittered(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], jit[0], jit[1], sidx, args.seed, 0, hits1.data_ptr(), None, None, None), "bmTraceCameraJittered")
-                _lib.check(L.bmProgressiveAccumulate(hits1.data_ptr(), n, None, None, None, 0.25, acc.data_ptr(), cov.data_ptr(), sp), "accumulate")
-                _lib.check(L.bmBounceRaysCameraAppend(tree.h, rays_in.data_ptr(), p[0], p[1], jit[0], jit[1], sidx, args.seed, hits1.data_ptr(), n, sidx, 1, args.seed,
-                                                      rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCameraAppend")
-            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n * g_, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRaysIndirect")
-            _lib.check(L.bmProgressiveAccumulateBounce(hits2.data_ptr(), src2.data_ptr(), cnt2.data_ptr(), n * g_, 0.75, acc.data_ptr(), sp), "accumulate bounce")
-            cnt_sum.add_(cnt2)
+            # g_ jittered samples of every pixel in one camera launch (the jitter is applied where the kernel forms the ray: no 24-byte ray
+            # record is written or read), then one bounce launch for the hits of those samples: bounce rays formed in registers, traced as
+            # closest hits, accumulated where they end.  Both walk 8x4 tiles under their temporal tile schedules.
+            _lib.check(L.bmTraceCameraSamples(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], jit[0], jit[1], s0, g_, args.seed, 0, hits1.data_ptr(), None), "bmTraceCameraSamples")
+            _lib.check(L.bmTraceBounceCamera(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], jit[0], jit[1], s0, g_, args.seed, hits1.data_ptr(), s0, 1, args.seed, None, 0.25, 0.75,
+                                             acc.data_ptr(), cov.data_ptr(), nbounce.data_ptr(), None), "bmTraceBounceCamera")
         _lib.check(L.bmProgressiveResolve(acc.data_ptr(), cov.data_ptr(), n, SPP, pixels.data_ptr(), sp), "resolve")
-        cnt_host.copy_(cnt_sum.to(torch.int32), non_blocking=True)
+        cnt_host.copy_(nbounce, non_blocking=True)
         if world > 1:
             e_ = torch.cuda.Event(); e_.record(stream)
             gather_frame(pixels, e_)()
@@ -371,11 +385,13 @@ def run_b200(args):
             e_ = torch.cuda.Event(); e_.record(stream)
             wait = gather_frame(pixels, e_)
         if wl.bounces:
-            _lib.check(L.bmBounceRaysCamera(tree.h, rays_in.data_ptr(), p[0], p[1], hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
+            nbounce.zero_()
             if marks is not None: marks[2].record()
-            # the bounce count stays on the device: the trace kernel reads it there (no host round trip inside the step)
-            _lib.check(L.bmTraceRaysIndirect(tree.h, rays2.data_ptr(), cnt2.data_ptr(), n, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRaysIndirect")
-            cnt_host.copy_(cnt2, non_blocking=True)
+            # bounce launch: every pixel with a primary hit forms its diffuse bounce ray in registers and traces it as a closest hit (hit
+            # records by pixel in hits2); the ray count stays on the device
+            _lib.check(L.bmTraceBounceCamera(tree.h, rays_in.data_ptr(), n, W, p[0], p[1], 0.0, 0.0, 0xFFFFFFFF, 1, 0, hits1.data_ptr(), 0, 1, args.seed, hits2.data_ptr(), 0.0, 0.0,
+                                             None, None, nbounce.data_ptr(), None), "bmTraceBounceCamera")
+            cnt_host.copy_(nbounce, non_blocking=True)
         if marks is not None: marks[3].record()
         if wait is not None:
             wait()                         # the step ends when the gathered frame is complete
@@ -442,11 +458,19 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     V1, K1, C1, LONG1 = [int(x) for x in cnt.cpu()]
     V2 = K2 = C2 = 0
-    nb_last = int(cnt2.cpu()[0]) if wl.bounces else 0      # rays2 holds the bounce rays of the LAST group of samples only
-    if nb_last:
-        cnt.zero_()
-        _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, BOUNCE_MODE, hits2.data_ptr(), cnt.data_ptr()), "bmTraceRays")
+    nb_last = 0
+    def bounce_launch(counters=None):
+        """the bounce launch of the pixel-centre frame in hits1 (instrumentation and per-launch timing)"""
+        _lib.check(L.bmTraceBounceCamera(tree.h, rays_dev.data_ptr(), n, W, p0[0], p0[1], 0.0, 0.0, 0xFFFFFFFF, 1, 0, hits1.data_ptr(), 0, 1, args.seed, hits2.data_ptr(), 0.0, 0.0,
+                                         None, None, nbounce.data_ptr(), counters.data_ptr() if counters is not None else None), "bmTraceBounceCamera")
+    if wl.bounces:
+        # the same bounce rays as a list (bmBounceRaysCamera) for the CPU baseline, and the bounce launch with traversal counters
+        _lib.check(L.bmBounceRaysCamera(tree.h, rays_dev.data_ptr(), p0[0], p0[1], hits1.data_ptr(), n, 0, 1, args.seed, rays2.data_ptr(), src2.data_ptr(), cnt2.data_ptr()), "bmBounceRaysCamera")
+        cnt.zero_(); nbounce.zero_()
+        bounce_launch(cnt)
         torch.cuda.synchronize(dev)
+        nb_last = int(nbounce.item())
+        assert nb_last == int(cnt2.item()), "bounce launch and bounce list disagree on the number of rays"
         V2, K2, C2, LONG2 = [int(x) for x in cnt.cpu()]
 
     # --- timed: e2e through the reference-facing host classes (include/beam_host_c.h) ---------------------------------------------
@@ -460,8 +484,8 @@ def run_b200(args):
     assert mesh.setVertexData(wl.normals, wl.normals.shape[0], 3, host.VERTEX_DATA_NORMAL) == 0
     assert mesh.setIndices(wl.indices.reshape(-1), wl.indices.size) == 0
     scene.addMesh(mesh); scene.updateGPUScene()
-    rts = [host.IRenderTarget.createHeadless(W, H) for _ in range(2)]
-    pix_pinned = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    rts = [host.IRenderTarget.createHeadless(W, H_e2e) for _ in range(2)]
+    pix_pinned = [torch.empty(n_e2e, dtype=torch.int32).pin_memory() for _ in range(2)]
     rays_pinned = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)]
     sticky0 = L.bmStickyError()
 
@@ -474,7 +498,7 @@ def run_b200(args):
             err = L.beamCameraTraceSceneProgressive(cam.h, p[2].ctypes.data, p[3].ctypes.data, scene.h, SPP, args.seed, C.cast(rays_pinned[i % 2].data_ptr(), C.POINTER(C.c_uint64)))
         else:
             err = L.beamCameraTraceScene(cam.h, p[2].ctypes.data, p[3].ctypes.data, scene.h)
-            rays_pinned[i % 2][0] = n
+            rays_pinned[i % 2][0] = n_e2e
         assert err == 0, err
         assert rt.unlock() == 0
 
@@ -512,7 +536,7 @@ def run_b200(args):
     e2e_frame(0, pose(0, False)); e2e_read(0)
     e2e_pixels = pix_pinned[0].clone()
     h2d = 48
-    d2h = n * 4 + 8
+    d2h = n_e2e * 4 + 8
     del scene, mesh
 
     # --- timed: BVH build (soup resident -> tree traceable) ---------------------------------------------------------------
@@ -576,29 +600,35 @@ def run_b200(args):
                 "algorithmic_bytes_per_ray": prim_bytes / n, "algorithmic_gbs": prim_bytes / (pms * 1e-3) / 1e9,
                 "node_visits_per_ray": V1 / n, "tri_tests_per_ray": K1 / n, "cluster_boxes_per_ray": C1 / n, "longest_ray_steps": LONG1,
                 "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
-    if prof and tree_mb < 100:
-        # the tree is L2-resident: the kernel is bound by instruction issue / cache latency, not by HBM (DRAM moves ~1 % of the algorithmic bytes)
+    if prof:
+        # bound = the resource the launch uses the largest share of, both shares from the committed ncu capture of this very launch
+        # (warp instructions, DRAM and L2 bytes per launch) over the duration measured live
         l2_peak = l2_copy_peak(torch, dev)
         inst = prof["warp_instructions_per_launch"]
-        roofline.update({"bound": "issue", "achieved": inst / (pms * 1e-3) / 1e9, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": inst / (pms * 1e-3) / 1e9 / issue_peak,
+        issue_frac = inst / (pms * 1e-3) / 1e9 / issue_peak
+        dram_gbs = prof["dram_bytes_per_launch"] / (pms * 1e-3) / 1e9
+        hbm_bound = dram_gbs / peak > issue_frac
+        roofline.update({"bound": "hbm" if hbm_bound else "issue",
+                         "achieved": dram_gbs if hbm_bound else inst / (pms * 1e-3) / 1e9, "peak": peak if hbm_bound else issue_peak, "unit": "GB/s" if hbm_bound else "Gwarp-inst/s",
+                         "frac": dram_gbs / peak if hbm_bound else issue_frac,
                          "traffic": prof["dram_bytes_per_launch"], "traffic_source": prof["source"],
-                         "dram": {"achieved_gbs": prof["dram_bytes_per_launch"] / (pms * 1e-3) / 1e9, "frac_of_hbm_peak": prof["dram_bytes_per_launch"] / (pms * 1e-3) / 1e9 / peak},
+                         "issue": {"achieved_gwarp_inst_per_s": inst / (pms * 1e-3) / 1e9, "peak": issue_peak, "frac": issue_frac},
+                         "dram": {"achieved_gbs": dram_gbs, "frac_of_hbm_peak": dram_gbs / peak},
                          "l2": {"lts_bytes_per_launch": prof["lts_bytes_per_launch"], "achieved_gbs": prof["lts_bytes_per_launch"] / (pms * 1e-3) / 1e9, "copy_peak_gbs": l2_peak,
                                 "frac": prof["lts_bytes_per_launch"] / (pms * 1e-3) / 1e9 / l2_peak, "peak_source": "live: torch copy of two L2-resident 24 MiB buffers (read + write bytes)",
                                 "ncu_pct_of_peak": prof.get("lts_pct_of_peak")},
                          "lanes_per_instruction": prof.get("lanes_per_instruction"), "ipc": prof.get("ipc"),
-                         "note": "the %.0f MB tree is L2-resident: bound = instruction issue (peak = 148 SMs x 4 schedulers x %.3f GHz; warp instructions and L2 / DRAM bytes per launch from the committed ncu capture of this very launch, duration measured live); "
-                                 "the algorithmic bytes per ray are served from L1 / L2, which is why algorithmic_gbs may exceed the HBM peak" % (tree_mb, sm_clock_ghz)})
+                         "note": "tree %.0f MB; issue peak = 148 SMs x 4 schedulers x %.3f GHz; warp instructions and L2 / DRAM bytes per launch from the committed ncu capture of this very launch, duration measured live; "
+                                 "the algorithmic bytes per ray are mostly served from L1 / L2, which is why algorithmic_gbs may exceed the HBM peak" % (tree_mb, sm_clock_ghz)})
     else:
-        tr = prof["dram_bytes_per_launch"] if prof else None
-        a_gbs = (tr if tr else prim_bytes) / (pms * 1e-3) / 1e9
-        roofline.update({"bound": "hbm", "achieved": a_gbs, "peak": peak, "unit": "GB/s", "frac": a_gbs / peak, "traffic": tr,
-                         "note": ("achieved = measured DRAM bytes per launch (committed ncu capture) / live duration" if tr else
-                                  "no ncu capture of this configuration is committed: achieved = algorithmic bytes (96 B x node visits + 32 B x cluster boxes + 48 B x triangle tests + ray / hit / pixel records) / live duration; "
-                                  "part of them is served from L2 (tree %.0f MB)" % tree_mb) + "; " + peak_src})
+        # no committed capture of this configuration (e.g. a rank's share of a strong-scaling frame): no fraction is claimed
+        roofline.update({"bound": "unprofiled", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                         "note": "no ncu capture of this configuration is committed, so no roofline fraction is claimed; algorithmic_gbs = (96 or 64 B x node visits + 32 B x cluster boxes + "
+                                 "48 B x triangle tests + ray / hit / pixel records) / live duration, mostly served from L1 / L2 (tree %.0f MB); " % tree_mb + peak_src})
     if wl.bounces and nb_last:
-        bms2 = time_launch(lambda: _lib.check(L.bmTraceRays(tree.h, rays2.data_ptr(), nb_last, BOUNCE_MODE, hits2.data_ptr(), None), "bmTraceRays"))
-        roofline["bounce_launch"] = {"ms_per_launch": bms2, "mrays_per_s": nb_last / (bms2 * 1e-3) / 1e6, "rays": nb_last, "mode": "closest hit",
+        _lib.check(L.bmTraceCamera(tree.h, rays_dev.data_ptr(), n, W, p0[0], p0[1], 0, hits1.data_ptr(), None, None, None), "bmTraceCamera")
+        bms2 = time_launch(lambda: bounce_launch())
+        roofline["bounce_launch"] = {"kernel": "trace_kernel<closest, camera, bounce> (bmTraceBounceCamera), static frame", "ms_per_launch": bms2, "mrays_per_s": nb_last / (bms2 * 1e-3) / 1e6, "rays": nb_last, "mode": "closest hit",
                                      "node_visits_per_ray": V2 / nb_last, "tri_tests_per_ray": K2 / nb_last, "cluster_boxes_per_ray": C2 / nb_last}
         pb = profile_entry(args.workload + "_bounce")
         if pb and world == 1:
@@ -654,7 +684,7 @@ def run_b200(args):
             _lib.check(L.bmTraceCamera(tree.h, r_.data_ptr(), w_ * h_, w_, p0[0], p0[1], 0, None, p_.data_ptr(), table.data_ptr(), None), "bmTraceCamera")
             torch.cuda.synchronize(dev)
             return p_.cpu().numpy().view(np.uint32)
-        nbb = nb if SPP == 1 else nb_last                    # multi-sample frames: the bounce list of the last group of samples
+        nbb = nb if SPP == 1 else nb_last                    # multi-sample frames: the bounce list of the pixel-centre sample
         line["cpu_baseline"] = cpu_baseline(wl, rays_host, rays2[:nbb].cpu().numpy() if nbb else None, src2[:nbb].cpu().numpy() if nbb else None,
                                             gpu_pixels_fn=gpu_frame_pixels)
         def ours_scene(name_):

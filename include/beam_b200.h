@@ -274,6 +274,28 @@ int  bmBounceRaysCameraAppend(bmTree* tree, const float* d_initialRays3, const f
                               uint32_t cameraSample, uint32_t cameraSeed, const bmHit* d_hits, uint64_t numRays,
                               uint32_t sample, uint32_t bounce, uint32_t seed, bmRay* d_out, uint32_t* d_srcIndex, uint32_t* d_total);
 
+/* Multi-sample camera launch: `sampleCount` jittered samples (firstSample .. firstSample + sampleCount - 1, each the ray
+ * bmTraceCameraJittered(..., sample, seed, ...) traces) of every pixel in ONE launch; d_hits holds sampleCount * numRays records,
+ * sample-major (record of sample k, pixel i at k * numRays + i).  The launch walks the image in 8x4 tiles, the samples of a tile one after
+ * the other, expensive tiles first (temporal tile schedule): a multi-sample frame no longer pays one launch tail per sample. */
+int  bmTraceCameraSamples(bmTree* tree, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                          float jitterX, float jitterY, uint32_t firstSample, uint32_t sampleCount, uint32_t seed, int mode, bmHit* d_hits, uint64_t* d_counters);
+
+/* Bounce launch: every pixel whose primary ray hit (d_hits1, laid out as bmTraceCameraSamples / bmTraceCamera[Jittered] wrote it) traces the
+ * diffuse bounce ray of that hit -- bit for bit the ray bmBounceRaysCamera[Jittered] would append to a list, formed in registers instead --
+ * as a closest hit with t >= 0.  No compaction and no ray list: the rays of a warp are the hits of one 8x4 pixel tile, and the launch runs
+ * under its own temporal tile schedule.
+ *   cameraSample0  0xFFFFFFFF: the primary rays were the exact pixel-centre rays (sampleCount must be 1); else the first camera sample
+ *   bounceSample0  index of the launch's first sample in the bounce rays' random sequence (bmBounceRays' `sample`)
+ *   d_hits2        nullable; sampleCount * numRays records, written ONLY where the primary ray hit
+ *   d_accum, d_covered  nullable; the progressive estimator (bmProgressiveAccumulate) applied where a bounce ray ends:
+ *                  d_accum[i] += ambient + (escaped ? weight : 0), d_covered[i] = 1
+ *   d_rayCount     nullable, device uint64: += number of bounce rays traced */
+int  bmTraceBounceCamera(bmTree* tree, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                         float jitterX, float jitterY, uint32_t cameraSample0, uint32_t sampleCount, uint32_t cameraSeed, const bmHit* d_hits1,
+                         uint32_t bounceSample0, uint32_t bounce, uint32_t seed, bmHit* d_hits2, float ambient, float weight, float* d_accum,
+                         uint32_t* d_covered, uint64_t* d_rayCount, uint64_t* d_counters);
+
 /* Progressive accumulation over samples (defined by this repo; the reference's SceneProgressive is an empty stub): one sample of a
  * pixel = `ambient` if its primary ray hit + (1 - ambient) if the diffuse bounce ray of that hit escaped.  d_accum (float) and
  * d_covered (uint32) are per pixel and must start zeroed; d_hits2 / d_src2 / d_count2 are bmBounceRays' outputs after tracing (pass

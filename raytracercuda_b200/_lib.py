@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "bmMarchProgressive", "bmGetStoreSize", "bmGetFaceClusterSize", "bmGetBvhNodeSize", "bmGetRaySize", "bmGetRayBoxSize", "bmGetRayFaceSize", "bmRayFaceHitClusterSize",
     "bmLastErrorString", "bmLaunchCount", "bmStickyError", "bmStickyErrorString", "bmClearStickyError", "bmReleaseScene", "bmSetPart1Stream",
     "bmTraceCameraJittered", "bmBounceRaysCameraJittered", "bmTreeCreate", "bmTreeDestroy", "bmTreeSetStream", "bmTreeReset", "bmTreeAddMesh", "bmTreeBuild", "bmBuildTree",
-    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView", "bmTreeEnableStageTiming", "bmTreeLastBuildStages", "bmTreeNodeLayout", "bmTreeWorld", "bmTreeCopyWideSlots", "bmTreeSetBricks", "bmBounceRaysCameraAppend", "bmProgressiveAccumulateBounce",
+    "bmTreeFromRoot", "bmTreeStats", "bmTreeCopyPairs", "bmTreeCopyTopology", "bmTreeCopyChildBoxes", "bmTreeMeshBases", "bmTreeArraySizes", "bmTreeExport", "bmTreeImport", "bmTreeRoot", "bmTreeView", "bmTreeEnableStageTiming", "bmTreeLastBuildStages", "bmTreeNodeLayout", "bmTreeWorld", "bmTreeCopyWideSlots", "bmTreeSetBricks", "bmBounceRaysCameraAppend", "bmProgressiveAccumulateBounce", "bmTraceCameraSamples", "bmTraceBounceCamera",
     "bmTraceRays", "bmTraceRaysTiled", "bmTraceCamera", "bmHashKeys", "bmCameraRays", "bmBounceRays", "bmBounceRaysCamera", "bmTraceRaysIndirect", "bmProgressiveAccumulate", "bmProgressiveResolve", "bmShadeHits",
     # include/beam_host_c.h
     "beamSceneCreate", "beamSceneDestroy", "beamSceneAddMesh", "beamSceneRemoveMesh", "beamSceneUpdateGPUScene", "beamSceneTree",
@@ -175,6 +175,8 @@ def load() -> C.CDLL:
     L.bmBounceRaysCameraJittered.argtypes = [vp, vp, fp, fp, f, f, u32, u32, vp, u64, u32, u32, u32, vp, vp, vp]
     L.bmBounceRaysCameraAppend.argtypes = [vp, vp, fp, fp, f, f, u32, u32, vp, u64, u32, u32, u32, vp, vp, vp]
     L.bmProgressiveAccumulateBounce.argtypes = [vp, vp, vp, u64, f, vp, vp]
+    L.bmTraceCameraSamples.argtypes = [vp, vp, u64, u32, fp, fp, f, f, u32, u32, u32, i32, vp, vp]
+    L.bmTraceBounceCamera.argtypes = [vp, vp, u64, u32, fp, fp, f, f, u32, u32, u32, vp, u32, u32, u32, vp, f, f, vp, vp, vp, vp]
     L.beamHostAlloc.argtypes = [C.c_size_t]; L.beamHostAlloc.restype = vp
     L.beamHostFree.argtypes = [vp]; L.beamHostFree.restype = None
     L.beamHostStream.restype = vp

@@ -27,15 +27,37 @@ def _stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """every source is compiled to its own object (in parallel; an object is rebuilt when its source, any header of csrc/ or include/, or
+    this script is newer), then linked: a one-file change rebuilds in seconds"""
     if not force and not _stale():
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(HERE, "_obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
+    inc = os.path.join(HERE, "..", "include")
+    headers += [os.path.join(inc, f) for f in os.listdir(inc)] + [__file__]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(name):
+        src = os.path.join(CSRC, name); obj = os.path.join(obj_dir, name + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_header):
+            return obj, 0, ""
+        r = subprocess.run(["nvcc"] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, r.returncode, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]))
+    for _, rc, out in results:
+        if verbose or rc != 0:
+            sys.stderr.write(out)
+    if any(rc != 0 for _, rc, _ in results):
         raise RuntimeError("nvcc failed building libbeam_b200.so")
+    r = subprocess.run(["nvcc"] + NVCC_FLAGS + ["-o", LIB] + [o for o, _, _ in results], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking libbeam_b200.so")
     return LIB
 
 

@@ -131,14 +131,14 @@ __device__ __forceinline__ float u01(u32 h) { return (float)(h >> 8) * (1.0f / 1
 // Ray i of a camera: dir = orient * initialRays[i] from eye (glm mat3 * vec3, type_mat3x3.inl:424-430; Camera.cpp:85-97), optionally
 // jittered.  ONE definition used by the trace kernels (which form camera rays in registers), bmCameraRays (which materialises them) and
 // the bounce generator (which re-forms the primary ray of a hit), so all three see the same bits.
-__device__ __forceinline__ void camera_ray(const CameraIn& cam, u64 i, V3& o, V3& d)
+__device__ __forceinline__ void camera_ray(const CameraIn& cam, u64 i, u32 sample, V3& o, V3& d)
 {
     const float* r = cam.initialRays + 3 * i;
     float x = __ldg(r), y = __ldg(r + 1), z = __ldg(r + 2);
-    if (cam.sample != 0xFFFFFFFFu)
+    if (sample != 0xFFFFFFFFu)
     {
         // jitter inside the pixel: the table stores unit vectors (rx,ry,zoom)*d; perturb in the image plane and renormalise
-        u32 h = pcg_hash((u32)i ^ pcg_hash(cam.sample * 0x9E3779B9u + cam.seed));
+        u32 h = pcg_hash((u32)i ^ pcg_hash(sample * 0x9E3779B9u + cam.seed));
         float jx = (u01(h) - .5f) * cam.jitterX, jy = (u01(pcg_hash(h)) - .5f) * cam.jitterY;
         float s = 1.f / z;                       // z = zoom*d > 0
         float px = x * s + jx, py = y * s + jy;  // in units of zoom
@@ -149,7 +149,39 @@ __device__ __forceinline__ void camera_ray(const CameraIn& cam, u64 i, V3& o, V3
     d = mk3(m[0] * x + m[3] * y + m[6] * z, m[1] * x + m[4] * y + m[7] * z, m[2] * x + m[5] * y + m[8] * z);
     o = mk3(cam.eye[0], cam.eye[1], cam.eye[2]);
 }
+__device__ __forceinline__ void camera_ray(const CameraIn& cam, u64 i, V3& o, V3& d) { camera_ray(cam, i, cam.sample, o, d); }
+
+// The diffuse bounce ray of a hit (rays.cu): origin = hit point + 1e-4 n, direction cosine-weighted about the geometric normal n (flipped
+// towards the side the incoming ray came from), random numbers = counter-based hash of (ray index, sample, bounce, seed).  ONE definition
+// used by bounce_kernel (which writes the ray into a list) and by the trace kernels' bounce launches (which form it in registers).
+__device__ __forceinline__ void bounce_ray(V3 ro, V3 rd, float t, u32 tri, const float4* __restrict__ soup, u64 i, u32 sample, u32 bounce, u32 seed, V3& o, V3& d)
+{
+    const float4* p = soup + 3 * (size_t)tri;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    V3 e1 = mk3(b.x - a.x, b.y - a.y, b.z - a.z), e2 = mk3(c.x - a.x, c.y - a.y, c.z - a.z);
+    V3 nrm = cross3(e1, e2);
+    float len2 = dot3(nrm, nrm);
+    nrm = len2 > 0.f ? nrm * rsqrtf(len2) : mk3(0.f, 0.f, 1.f);
+    if (dot3(nrm, rd) > 0.f) nrm = nrm * -1.f;                 // face the side the ray came from
+    V3 hp = mk3(ro.x + t * rd.x, ro.y + t * rd.y, ro.z + t * rd.z);
+    u32 h = pcg_hash((u32)i ^ pcg_hash(seed ^ pcg_hash(sample * 0x9E3779B9u + bounce * 0x85EBCA6Bu)));
+    float u1 = u01(h), u2 = u01(pcg_hash(h ^ 0xB5297A4Du));
+    float rr = sqrtf(u1), phi = 6.28318530718f * u2;
+    float lx = rr * cosf(phi), ly = rr * sinf(phi), lz = sqrtf(fmaxf(0.f, 1.f - u1));
+    // branchless orthonormal basis (Duff et al. 2017)
+    float sgn = copysignf(1.f, nrm.z);
+    float aa = -1.f / (sgn + nrm.z), bb = nrm.x * nrm.y * aa;
+    V3 t1 = mk3(1.f + sgn * nrm.x * nrm.x * aa, sgn * bb, -sgn * nrm.x), t2 = mk3(bb, sgn + nrm.y * nrm.y * aa, -nrm.y);
+    d = mk3(t1.x * lx + t2.x * ly + nrm.x * lz, t1.y * lx + t2.y * ly + nrm.y * lz, t1.z * lx + t2.z * ly + nrm.z * lz);
+    o = mk3(hp.x + 1e-4f * nrm.x, hp.y + 1e-4f * nrm.y, hp.z + 1e-4f * nrm.z);
+}
 #endif
+// Bounce launches (bmTraceBounceCamera): the camera launch's slots are the pixels of `samples` consecutive samples of a frame; a lane whose
+// pixel has a primary hit (hits1[sample * n + pixel]) forms that hit's diffuse bounce ray in registers and traces it, the others stay idle.
+// No compaction, no ray list: the rays of a warp are the hits of one 8x4 tile, and the launch runs under its own temporal tile schedule.
+// accum / covered (nullable): the progressive estimator is applied where the ray retires (accum[pixel] += ambient + (escaped ? weight : 0)).
+struct BounceIn { const bmHit* hits1; const float4* soup; u32 sample, bounce, seed;      // sample = index of the launch's first sample in the bounce rays' random sequence
+                  float* accum; u32* covered; float ambient, weight; unsigned long long* rayCount; };
 // d_workCounter: one u32 of device scratch per launch in flight (the persistent warps' work queue head)
 // d_numRays (nullable): the ray count is read from device memory at kernel start (<= n, which then only sizes the grid)
 int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numRays, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter, cudaStream_t s);
@@ -162,8 +194,10 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numR
 //          [TS_ENTRIES] set by the ordering kernel
 constexpr int TS_BUCKETS = 64, TS_SUM = 128, TS_OK = 130, TS_ENTRIES = 131, TS_WORDS = 132;       // [0, TS_OK) is zeroed before every launch
 struct TileSched { u32* cost; u32* order; u32* state; u32 tiles; };
+// samples > 1: the launch covers samples cam.sample .. cam.sample + samples - 1 of every pixel (jitter applied in the kernel); d_hits then holds
+// samples * n records, sample-major.  bounce (nullable): a bounce launch (BounceIn).
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
-                 u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s);
+                 u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, u32 samples = 1, const BounceIn* bounce = nullptr);
 int trace_rays_tiled(const TreeView& tv, const bmRay* d_rays, u64 n, u32 width, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter,
                      const TileSched* sched, cudaStream_t s);
 // Segments of a ray batch traced brick by brick (bricks.cu): keys[i] = position of the brick in the ray's visiting order << 24 | wave << bits | brick,

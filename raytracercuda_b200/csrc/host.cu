@@ -288,29 +288,24 @@ public:
         bmTree* t = bmTreeFromRoot(m_root->ptr<void>());
         if (!t) { bmClear(rt->buffer<u32>(), rt->pitch(), raysWide, raysHigh, 255u << 8); static_cast<RenderTarget*>(rt)->markWritten(); if (raysTraced) *raysTraced = 0; return ERROR_ALL_FINE; }
         cudaStream_t st = host_stream();
-        // the bounce rays of up to `group` samples are collected in one list and traced by ONE launch (a single sample of a small scene
-        // yields too few bounce rays to fill the GPU: f16 at 1080p, 71 K rays per sample); the list is capped at 32 M rays
+        // up to `group` samples of every pixel per launch (bmTraceCameraSamples), then ONE bounce launch for the hits of those samples
+        // (bmTraceBounceCamera: the bounce rays are formed in the kernel and accumulated where they end; no ray list, no compaction).  A
+        // single sample of a small scene yields too few bounce rays to fill the GPU: f16 at 1080p, 71 K per sample.
         const u32 group = (u32)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(samples, 8), (size_t)(32u << 20) / std::max<size_t>(n, 1)));
-        DeviceBuffer *ph1 = scratch(0, n * sizeof(bmHit)), *pr2 = scratch(2, n * group * sizeof(bmRay)), *ph2 = scratch(3, n * group * sizeof(bmHit)),
-                     *psrc = scratch(4, n * group * 4), *pcnt = scratch(5, 16), *pacc = scratch(6, n * 4), *pcov = scratch(7, n * 4);
-        if (!ph1 || !pr2 || !ph2 || !psrc || !pcnt || !pacc || !pcov) return ERROR_GPU_ALLOC_FAIL;
-        DeviceBuffer &h1 = *ph1, &r2 = *pr2, &h2 = *ph2, &src = *psrc, &cnt = *pcnt, &acc = *pacc, &cov = *pcov;
+        DeviceBuffer *ph1 = scratch(0, n * group * sizeof(bmHit)), *pcnt = scratch(5, 16), *pacc = scratch(6, n * 4), *pcov = scratch(7, n * 4);
+        if (!ph1 || !pcnt || !pacc || !pcov) return ERROR_GPU_ALLOC_FAIL;
+        DeviceBuffer &h1 = *ph1, &cnt = *pcnt, &acc = *pacc, &cov = *pcov;
         u64* total = reinterpret_cast<u64*>(cnt.ptr<char>() + 8);
         cudaMemsetAsync(acc.ptr<void>(), 0, n * 4, st); cudaMemsetAsync(cov.ptr<void>(), 0, n * 4, st); cudaMemsetAsync(cnt.ptr<void>(), 0, 16, st);
         for (u32 s0 = 0; s0 < samples; s0 += group)
         {
             const u32 g = std::min(group, samples - s0);
-            int r = cudaMemsetAsync(cnt.ptr<void>(), 0, 4, st) == cudaSuccess ? BM_OK : BM_ERROR_CUDA;      // the group's bounce list starts empty
-            for (u32 s = s0; s < s0 + g && !r; s++)
-            {
-                const u32 camSample = samples > 1 ? s : 0xFFFFFFFFu;          // one sample per pixel = the exact pixel-centre ray bmMarch traces
-                r = bmTraceCameraJittered(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, camSample, seed, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr, nullptr, nullptr);
-                if (!r) r = bmProgressiveAccumulate(h1.ptr<bmHit>(), n, nullptr, nullptr, nullptr, 0.25f, acc.ptr<float>(), cov.ptr<u32>(), st);
-                if (!r) r = bmBounceRaysCameraAppend(t, rays->ptr<const float>(), eye3, orient9, jx, jy, camSample, seed, h1.ptr<bmHit>(), n, s, 1, seed, r2.ptr<bmRay>(), src.ptr<u32>(), cnt.ptr<u32>());
-            }
-            if (!r) r = bmTraceRaysIndirect(t, r2.ptr<bmRay>(), cnt.ptr<u32>(), n * g, BM_TRACE_CLOSEST, h2.ptr<bmHit>(), nullptr);
-            if (!r) r = bmProgressiveAccumulateBounce(h2.ptr<bmHit>(), src.ptr<u32>(), cnt.ptr<u32>(), n * g, 0.75f, acc.ptr<float>(), st);
-            if (!r && raysTraced) r = bm::add_count(cnt.ptr<u32>(), n * g, total, st);
+            const u32 camSample = samples > 1 ? s0 : 0xFFFFFFFFu;             // one sample per pixel = the exact pixel-centre ray bmMarch traces
+            int r = samples > 1 ? bmTraceCameraSamples(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, s0, g, seed, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr)
+                                : bmTraceCameraJittered(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, camSample, seed, BM_TRACE_REFERENCE, h1.ptr<bmHit>(), nullptr, nullptr, nullptr);
+            if (!r) r = bmTraceBounceCamera(t, rays->ptr<const float>(), n, raysWide, eye3, orient9, jx, jy, camSample, g, seed, h1.ptr<bmHit>(), s0, 1, seed, nullptr, 0.25f, 0.75f,
+                                            acc.ptr<float>(), cov.ptr<u32>(), raysTraced ? total : nullptr, nullptr);
+            if (!r && raysTraced) r = bm::add_count(nullptr, n * g, total, st);
             if (r) return (u32)r;
         }
         int r = bmProgressiveResolve(acc.ptr<float>(), cov.ptr<u32>(), n, samples, rt->buffer<u32>(), st);

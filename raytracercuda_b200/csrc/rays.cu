@@ -45,28 +45,10 @@ __global__ void bounce_kernel(const bmRay* __restrict__ rays, CameraIn cam, cons
         r.o[0] = co.x; r.o[1] = co.y; r.o[2] = co.z; r.d[0] = cd.x; r.d[1] = cd.y; r.d[2] = cd.z;
     }
     else r = rays[i];
-    const float4* p = soup + 3 * (size_t)tri;
-    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    V3 e1 = mk3(b.x - a.x, b.y - a.y, b.z - a.z), e2 = mk3(c.x - a.x, c.y - a.y, c.z - a.z);
-    V3 nrm = cross3(e1, e2);
-    float len2 = dot3(nrm, nrm);
-    nrm = len2 > 0.f ? nrm * rsqrtf(len2) : mk3(0.f, 0.f, 1.f);
-    V3 d = mk3(r.d[0], r.d[1], r.d[2]);
-    if (dot3(nrm, d) > 0.f) nrm = nrm * -1.f;                 // face the side the ray came from
-    float t = hf.x;
-    V3 hp = mk3(r.o[0] + t * d.x, r.o[1] + t * d.y, r.o[2] + t * d.z);
-    u32 h = pcg_hash((u32)i ^ pcg_hash(seed ^ pcg_hash(sample * 0x9E3779B9u + bounce * 0x85EBCA6Bu)));
-    float u1 = u01(h), u2 = u01(pcg_hash(h ^ 0xB5297A4Du));
-    float rr = sqrtf(u1), phi = 6.28318530718f * u2;
-    float lx = rr * cosf(phi), ly = rr * sinf(phi), lz = sqrtf(fmaxf(0.f, 1.f - u1));
-    // branchless orthonormal basis (Duff et al. 2017)
-    float sgn = copysignf(1.f, nrm.z);
-    float aa = -1.f / (sgn + nrm.z), bb = nrm.x * nrm.y * aa;
-    V3 t1 = mk3(1.f + sgn * nrm.x * nrm.x * aa, sgn * bb, -sgn * nrm.x), t2 = mk3(bb, sgn + nrm.y * nrm.y * aa, -nrm.y);
-    V3 nd = mk3(t1.x * lx + t2.x * ly + nrm.x * lz, t1.y * lx + t2.y * ly + nrm.y * lz, t1.z * lx + t2.z * ly + nrm.z * lz);
+    V3 bo, bd;
+    bounce_ray(mk3(r.o[0], r.o[1], r.o[2]), mk3(r.d[0], r.d[1], r.d[2]), hf.x, tri, soup, i, sample, bounce, seed, bo, bd);
     bmRay o;
-    o.o[0] = hp.x + 1e-4f * nrm.x; o.o[1] = hp.y + 1e-4f * nrm.y; o.o[2] = hp.z + 1e-4f * nrm.z;
-    o.d[0] = nd.x; o.d[1] = nd.y; o.d[2] = nd.z;
+    o.o[0] = bo.x; o.o[1] = bo.y; o.o[2] = bo.z; o.d[0] = bd.x; o.d[1] = bd.y; o.d[2] = bd.z;
     u32 k = offsets[i] + (appendBase ? *appendBase : 0u);      // append mode: behind the rays other launches already put into the list
     out[k] = o;
     if (srcIndex) srcIndex[k] = (u32)i;

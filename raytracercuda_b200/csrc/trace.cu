@@ -10,6 +10,7 @@
 //   * additionally a child whose tight box (union of its whole triangles) is missed by the ray's LINE is not pushed: no
 //     triangle below it can be hit, so results are unchanged and most of the reference's ~97 node visits per ray vanish.
 #include <cstdlib>
+#include <cstring>
 #include "bm_device.cuh"
 #include "bm_wide.cuh"
 
@@ -553,11 +554,13 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
 // SEG (ray batches through bricks, bricks.cu): a slot is one SEGMENT -- (ray, brick, position of the brick in the ray's own visiting order) --
 // of a list sorted by brick; the lane walks the brick's subtree only and merges what it finds into the ray's 64-bit result key with
 // an atomic minimum (SegIn).  Everything between refill and retire is the same traversal.
-template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG>
+// BOUNCE (bounce launches, BounceIn): a camera launch whose lanes trace the diffuse bounce ray of their pixel's primary hit.
+// samples > 1 (camera launches): the slots enumerate `samples` consecutive samples of every pixel, tile by tile.
+template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG, bool BOUNCE>
 __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeView tv, const bmRay* __restrict__ rays, CameraIn cam, u64 n, u32 width, u32 height,
                                                            u32 totalSlots, const u32* __restrict__ numRaysDev, bmHit* __restrict__ hits, u32* __restrict__ pixels,
                                                            const bmStaticMeshData* __restrict__ meshData, u64* counters, u32* workCounter, int leafBreak, int leafWait, int refillMin, int queueDepth, TileSched sched,
-                                                           SegIn seg)
+                                                           SegIn seg, u32 samples, BounceIn bnc)
 {
     const u32 rootRef = tv.numLeaves >= 2 ? __ldg(tv.root) : (tv.numLeaves == 1 ? (0u | LEAF_BIT) : REF_EMPTY);
     if (numRaysDev) { n = __ldg(numRaysDev); totalSlots = (u32)n; }       // count produced on the device (bmBounceRays): no host round trip
@@ -581,7 +584,10 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
     u32 nv = 0, nt = 0, nc = 0, rayStart = 0, longest = 0;      // COUNT only: totals, and the longest single ray (the kernel's critical path)
     // temporal tile scheduling (camera launches; see TileSched): the tile this warp is working on and when it started
     const bool useOrder = CAMERA && sched.order != nullptr && sched.state[TS_OK] != 0u;
-    if (useOrder) totalSlots = sched.state[TS_ENTRIES] * 32u;      // the work list may hold some tiles as four quarter entries
+    const u32 sampleSlots = (CAMERA || BOUNCE) ? totalSlots / samples : totalSlots;      // slots of one sample (camera launches without a schedule)
+    if (useOrder) totalSlots = sched.state[TS_ENTRIES] * 32u * samples;      // the work list may hold some tiles as four quarter entries
+    u32 raySample = 0;                      // CAMERA: which of the launch's samples this lane's ray belongs to
+    u32 nBounce = 0;                        // BOUNCE: rays this lane has traced
     u32 curTile = 0xFFFFFFFFu;
     long long tileStart = 0;
     u32 segSeq = 0;                         // SEG: position of this brick in the ray's visiting order
@@ -609,10 +615,12 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
             base = __shfl_sync(FULL, base, 0);
             if (base >= totalSlots) exhausted = true;
             u32 quarter = 0;                                     // 1..4: this fetch is one 8-pixel row of a split tile
+            u32 fetchSample = 0;
             if (CAMERA && sched.cost && base < totalSlots)
             {
                 // (scheduled camera launches refill whole warps only: idle == FULL and base is a multiple of 32)
                 u32 entry = base >> 5;
+                if (samples > 1u) { fetchSample = entry % samples; entry /= samples; }      // the samples of a tile follow each other: expensive tiles first for all of them
                 if (useOrder) entry = __ldg(sched.order + entry);
                 curTile = entry & 0x0FFFFFFFu; quarter = entry >> 28;
                 tileStart = clock64();
@@ -626,6 +634,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     if (quarter) { take = lane < 8u; slot = (curTile << 5) | ((quarter - 1u) << 3) | (lane & 7u); }
                     else slot = (curTile << 5) | lane;
                 }
+                else if ((CAMERA || BOUNCE) && samples > 1u && take) { fetchSample = slot / sampleSlots; slot -= fetchSample * sampleSlots; }
                 u32 startRef = rootRef;
                 if (SEG && take)
                 {
@@ -639,9 +648,27 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                     segKey0 = __ldcg(seg.rayKey + rayIdx);
                     if (MODE == BM_TRACE_REFERENCE && (u32)(segKey0 >> 32) < segSeq) take = false;
                 }
-                if (take && (SEG || slot_to_ray(slot, n, width, height, rayIdx)))
+                if (take && !SEG) take = slot_to_ray(slot, n, width, height, rayIdx);
+                float bt = 0.f; u32 btri = 0xFFFFFFFFu;
+                if (BOUNCE && take)
                 {
-                    if (CAMERA && !rays) camera_ray(cam, rayIdx, o, d);      // formed in registers: no ray record is ever written or read
+                    // the pixel's primary hit of this sample: no hit, no bounce ray
+                    const float4 hf = __ldg(reinterpret_cast<const float4*>(bnc.hits1) + (size_t)fetchSample * n + rayIdx);
+                    bt = hf.x; btri = __float_as_uint(hf.w);
+                    take = btri != 0xFFFFFFFFu;
+                }
+                if (take)
+                {
+                    if (CAMERA || BOUNCE) raySample = fetchSample;
+                    const u32 camSample = cam.sample == 0xFFFFFFFFu ? cam.sample : cam.sample + fetchSample;
+                    if (BOUNCE)
+                    {
+                        V3 co, cd;
+                        camera_ray(cam, rayIdx, camSample, co, cd);      // the primary ray exactly as its own launch formed it
+                        bounce_ray(co, cd, bt, btri, bnc.soup, rayIdx, bnc.sample + fetchSample, bnc.bounce, bnc.seed, o, d);
+                        nBounce++;
+                    }
+                    else if (CAMERA && !rays) camera_ray(cam, rayIdx, camSample, o, d);      // formed in registers: no ray record is ever written or read
                     else
                     {
                         const float* r = reinterpret_cast<const float*>(rays + rayIdx);
@@ -661,7 +688,9 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                 }
             }
         }
-        if (!__any_sync(FULL, active)) break;
+        // nothing to do: the work list is drained -- or the slots just fetched held no ray (a bounce launch's tile without primary hits,
+        // segments another brick has already decided): fetch again
+        if (!__any_sync(FULL, active)) { if (exhausted) break; continue; }
 
         // ---- phase 1: internal nodes ----------------------------------------------------------------------------------------------
         // Ray batches carry a small queue of POSTPONED leaves per lane (queueDepth entries in shared memory): a lane that reaches a leaf
@@ -829,12 +858,25 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
             }
             else
             {
-            if (hits) { reinterpret_cast<float4*>(hits)[rayIdx] = make_float4(best.t, best.u, best.v, __uint_as_float(best.tri)); }
-            if (pixels) pixels[rayIdx] = shade(best, meshData);
+                const size_t at = (CAMERA || BOUNCE) ? (size_t)raySample * n + rayIdx : (size_t)rayIdx;
+                if (hits) { reinterpret_cast<float4*>(hits)[at] = make_float4(best.t, best.u, best.v, __uint_as_float(best.tri)); }
+                if (pixels) pixels[rayIdx] = shade(best, meshData);
+                if (BOUNCE)
+                {
+                    // the progressive estimator, applied where the ray ends: this sample of the pixel had a primary hit (ambient) whose bounce
+                    // ray escaped (+ weight) or not.  Several samples of a pixel may retire at once: atomic (the terms are exact in binary)
+                    if (bnc.accum) atomicAdd(bnc.accum + rayIdx, bnc.ambient + (best.tri == 0xFFFFFFFFu ? bnc.weight : 0.f));
+                    if (bnc.covered) bnc.covered[rayIdx] = 1u;
+                }
             }
             active = false;
             if (COUNT) longest = max(longest, nv + nt + nc - rayStart);
         }
+    }
+    if (BOUNCE && bnc.rayCount)
+    {
+        nBounce = __reduce_add_sync(FULL, nBounce);
+        if (lane == 0 && nBounce) atomicAdd(bnc.rayCount, (unsigned long long)nBounce);
     }
     if (COUNT)
     {
@@ -917,21 +959,24 @@ bool use_wide(const TreeView& tv)
     return v != 0;
 }
 
-template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG = false>
+template <int MODE, bool CAMERA, bool COUNT, bool WIDE, bool SEG = false, bool BOUNCE = false>
 int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u64 n, const u32* d_numRays, u32 width, bmHit* d_hits, u32* d_pixels,
-                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, SegIn seg = SegIn{ nullptr, nullptr, nullptr, nullptr, 0u, 0u })
+                 const bmStaticMeshData* d_meshData, u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, SegIn seg = SegIn{ nullptr, nullptr, nullptr, nullptr, 0u, 0u },
+                 u32 samples = 1, const BounceIn* bounce = nullptr)
 {
     static std::atomic<int> occ[MAX_DEVICES];          // per device and per instantiation
     const int dev = current_device();
     int blocksPerSM = occ[dev].load(std::memory_order_relaxed);
     if (!blocksPerSM)
     {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG, BOUNCE>, TR_THREADS, 0) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 4;
         occ[dev].store(blocksPerSM, std::memory_order_relaxed);
     }
     u32 height = width ? (u32)((n + width - 1) / width) : 0;
-    u64 slots = width ? (u64)((width + 7) / 8) * ((height + 3) / 4) * 32 : n;
-    if (slots >= 0xFFFFFFF0ull) { set_error("more than 2^32 rays in one launch"); return BM_ERROR_CAPACITY; }
+    const u64 sampleSlots = width ? (u64)((width + 7) / 8) * ((height + 3) / 4) * 32 : n;
+    if (!(CAMERA || BOUNCE) || !samples) samples = 1;
+    u64 slots = sampleSlots * samples;
+    if ((samples > 1 ? slots * 4 : slots) >= 0xFFFFFFF0ull) { set_error("more than 2^32 rays in one launch"); return BM_ERROR_CAPACITY; }       // a schedule may list a tile as four quarter entries
     u64 warps = (slots + 31) / 32;
     u64 blocks = (warps + TR_THREADS / 32 - 1) / (TR_THREADS / 32);
     u64 cap = (u64)sm_count() * blocksPerSM;
@@ -939,14 +984,16 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     BM_CUDA(cudaMemsetAsync(d_workCounter, 0, 4, s));
     TileSched ts = { nullptr, nullptr, nullptr, 0 };
     const int refill = refill_min(CAMERA);
-    if (CAMERA && sched && !COUNT && refill == 32 && sched->tiles == (u32)(slots / 32))
+    if (CAMERA && sched && !COUNT && refill == 32 && sched->tiles == (u32)(sampleSlots / 32))
     {
         ts = *sched;
         BM_CUDA(cudaMemsetAsync(ts.state, 0, TS_OK * 4, s));          // histogram + cursors; OK flag and entry count of the previous launch stay
         BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
     }
-    trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
-                                                                            d_counters, d_workCounter, leaf_break(CAMERA ? 0 : queue_depth()), leaf_wait(CAMERA ? 0 : queue_depth()), refill, CAMERA ? 0 : queue_depth(), ts, seg);
+    const BounceIn none = { nullptr, nullptr, 0u, 0u, 0u, nullptr, nullptr, 0.f, 0.f, nullptr };
+    trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG, BOUNCE><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
+                                                                            d_counters, d_workCounter, leaf_break(CAMERA ? 0 : queue_depth()), leaf_wait(CAMERA ? 0 : queue_depth()), refill, CAMERA ? 0 : queue_depth(), ts, seg,
+                                                                            samples, bounce ? *bounce : none);
     BM_LAUNCHED();
     if (ts.cost)
     {
@@ -1003,9 +1050,43 @@ int trace_segments(const TreeView& tv, const bmRay* d_rays, u64 numSegs, int mod
 }
 
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
-                 u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s)
+                 u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, u32 samples, const BounceIn* bounce)
 {
     if (!n) return BM_OK;
+    if (samples > 1u && (cam.sample == 0xFFFFFFFFu || d_pixels)) { set_error("a multi-sample camera launch needs jittered samples and writes no pixels"); return BM_ERROR_INVALID_PARAMETER; }
+    const SegIn noSeg = SegIn{ nullptr, nullptr, nullptr, nullptr, 0u, 0u };
+    const bool wide = use_wide(tv);
+#define BM_CAM_LAUNCH(M, C, W, B) launch_trace<M, true, C, W, false, B>(tv, nullptr, cam, n, nullptr, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s, noSeg, samples, bounce)
+#define BM_BATCH_BOUNCE(C, W) launch_trace<BM_TRACE_CLOSEST, false, C, W, false, true>(tv, nullptr, cam, n, nullptr, width, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, nullptr, s, noSeg, samples, bounce)
+    if (bounce)
+    {
+        // bounce launches are closest-hit launches (t >= 0: in the reference's any-sign semantics a bounce ray "hits" its own source triangle)
+        if (mode != BM_TRACE_CLOSEST) { set_error("bounce launches trace closest hits"); return BM_ERROR_INVALID_PARAMETER; }
+        // Scheduling: the slots are the pixels in 8x4 tile order either way.  "tiles" (default): whole tiles per warp under the launch's own
+        // temporal tile schedule, as camera launches; "batch" (BM_BOUNCE_STYLE=batch): lanes refill as they fall idle and postpone leaves, as
+        // ray batches do.  Measured (B200, frame of c2 / c3 / c4): tiles 0.864 / 13.48 / 55.1 ms, batch 0.910 / 13.64 / 55.6 ms -- in batch
+        // style every warp pays a work-counter round trip per 8 slots of background, which costs more than the idle lanes of a tile.
+        static const bool tiles = !(getenv("BM_BOUNCE_STYLE") && !strcmp(getenv("BM_BOUNCE_STYLE"), "batch"));
+        if (!tiles)
+        {
+            if (wide) return d_counters ? BM_BATCH_BOUNCE(true, true) : BM_BATCH_BOUNCE(false, true);
+            return d_counters ? BM_BATCH_BOUNCE(true, false) : BM_BATCH_BOUNCE(false, false);
+        }
+        if (wide) return d_counters ? BM_CAM_LAUNCH(BM_TRACE_CLOSEST, true, true, true) : BM_CAM_LAUNCH(BM_TRACE_CLOSEST, false, true, true);
+        return d_counters ? BM_CAM_LAUNCH(BM_TRACE_CLOSEST, true, false, true) : BM_CAM_LAUNCH(BM_TRACE_CLOSEST, false, false, true);
+    }
+    if (samples > 1u)
+    {
+        if (mode == BM_TRACE_REFERENCE)
+        {
+            if (wide) return d_counters ? BM_CAM_LAUNCH(BM_TRACE_REFERENCE, true, true, false) : BM_CAM_LAUNCH(BM_TRACE_REFERENCE, false, true, false);
+            return d_counters ? BM_CAM_LAUNCH(BM_TRACE_REFERENCE, true, false, false) : BM_CAM_LAUNCH(BM_TRACE_REFERENCE, false, false, false);
+        }
+        if (wide) return d_counters ? BM_CAM_LAUNCH(BM_TRACE_CLOSEST, true, true, false) : BM_CAM_LAUNCH(BM_TRACE_CLOSEST, false, true, false);
+        return d_counters ? BM_CAM_LAUNCH(BM_TRACE_CLOSEST, true, false, false) : BM_CAM_LAUNCH(BM_TRACE_CLOSEST, false, false, false);
+    }
+#undef BM_CAM_LAUNCH
+#undef BM_BATCH_BOUNCE
     return dispatch_trace<true>(tv, nullptr, cam, n, nullptr, width, mode, d_hits, d_pixels, d_meshData, d_counters, d_workCounter, sched, s);
 }
 

@@ -85,13 +85,14 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false, imported = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState, tileCostB, tileOrderB, tileStateB;
     DevBuf brickRoots, brickOcc, segKeysA, segKeysB, segValsA, segValsB, rayKey, segCount;      // ray batches traced brick by brick (bricks.cu)
     int brickBits = 0;               // depth the brick table is valid for (0 = none; reset by every build)
     int brickMode = -1, brickBitsWanted = 0;      // bmTreeSetBricks: -1 = automatic (BM_BRICKS), 0 = never, 1 = always; bits 0 = default (BM_BRICK_BITS)
     size_t segCapacity = 0;
     bool stageTiming = false; std::string lastStages;      // bmTreeEnableStageTiming / bmTreeLastBuildStages
     int layout = BM_NODES_BINARY;    // which node records the last build wrote (BM_NODES_*; set by tree_build, or by bmTreeImport)
+    u32 schedTilesB = 0;             // the same for bounce launches (their own costs: a tile's bounce rays are not its primary rays)
     u32 schedTiles = 0;              // frame size (in 8x4 tiles) the tile-scheduling buffers are set up for; 0 = none
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
     u64 T = 0, P = 0, L = 0;
@@ -118,7 +119,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &wnodes, &nodeMeta, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState, &brickRoots, &brickOcc, &segKeysA, &segKeysB, &segValsA, &segValsB, &rayKey, &segCount };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &wnodes, &nodeMeta, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState, &tileCostB, &tileOrderB, &tileStateB, &brickRoots, &brickOcc, &segKeysA, &segKeysB, &segValsA, &segValsB, &rayKey, &segCount };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -154,7 +155,7 @@ static int tree_build(bmTree* t)
     for (auto& m : t->staged) { t->meshBase.push_back((u32)T); T += m.numTris; }
     if (T >= 0xFFFFFFFFull) { set_error("more than 2^32-2 triangles"); return BM_ERROR_CAPACITY; }
     t->T = T; t->P = 0; t->L = 0; t->maxLeaf = 0; t->overLeaves = 0;
-    t->schedTiles = 0;               // a new scene: forget the tile costs of the old one
+    t->schedTiles = 0; t->schedTilesB = 0;               // a new scene: forget the tile costs of the old one
     t->brickBits = 0;                // ... and its brick table
     BM_TRY(t->scalars.reserve(64)); BM_TRY(t->rootDev.reserve(16));
     BM_CUDA(cudaMemsetAsync(t->scalars.p, 0, 64, s));
@@ -603,8 +604,10 @@ extern "C" int bmTraceRaysIndirect(bmTree* t, const bmRay* d_rays, const uint32_
 }
 
 // temporal tile scheduling (TileSched, bm_device.cuh): per tree and frame size; BM_TILE_ORDER=0 turns it off
-static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uint64_t* d_counters, TileSched& sched)
+static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uint64_t* d_counters, TileSched& sched, bool bounceLaunch = false)
 {
+    DevBuf& tileCost = bounceLaunch ? t->tileCostB : t->tileCost; DevBuf& tileOrder = bounceLaunch ? t->tileOrderB : t->tileOrder; DevBuf& tileState = bounceLaunch ? t->tileStateB : t->tileState;
+    u32& schedTiles = bounceLaunch ? t->schedTilesB : t->schedTiles;
     static const bool tileOrderOn = !(getenv("BM_TILE_ORDER") && atoi(getenv("BM_TILE_ORDER")) == 0);
     sched = { nullptr, nullptr, nullptr, 0 };
     if (tileOrderOn && width && !d_counters)
@@ -613,13 +616,13 @@ static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uin
         uint64_t tiles = (uint64_t)((width + 7) / 8) * ((height + 3) / 4);
         if (tiles >= 256 && tiles < 0x07FFFFFFull)
         {
-            if (t->schedTiles != (u32)tiles)
+            if (schedTiles != (u32)tiles)
             {
-                BM_TRY(t->tileCost.reserve(tiles * 4)); BM_TRY(t->tileOrder.reserve(tiles * 16)); BM_TRY(t->tileState.reserve(TS_WORDS * 4));
-                BM_CUDA(cudaMemsetAsync(t->tileState.p, 0, TS_WORDS * 4, t->stream));      // no order yet
-                t->schedTiles = (u32)tiles;
+                BM_TRY(tileCost.reserve(tiles * 4)); BM_TRY(tileOrder.reserve(tiles * 16)); BM_TRY(tileState.reserve(TS_WORDS * 4));
+                BM_CUDA(cudaMemsetAsync(tileState.p, 0, TS_WORDS * 4, t->stream));      // no order yet
+                schedTiles = (u32)tiles;
             }
-            sched = { t->tileCost.as<u32>(), t->tileOrder.as<u32>(), t->tileState.as<u32>(), (u32)tiles };
+            sched = { tileCost.as<u32>(), tileOrder.as<u32>(), tileState.as<u32>(), (u32)tiles };
         }
     }
     return BM_OK;
@@ -638,6 +641,45 @@ extern "C" int bmTraceCameraJittered(bmTree* t, const float* d_initialRays3, uin
     TileSched sched;
     BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched));
     return trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream);
+}
+
+// `sampleCount` jittered samples of every pixel in ONE launch (samples firstSample .. firstSample + sampleCount - 1; the slots enumerate the samples
+// of a tile one after the other under the temporal tile schedule): d_hits holds sampleCount * numRays records, sample-major
+extern "C" int bmTraceCameraSamples(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                                    float jitterX, float jitterY, uint32_t firstSample, uint32_t sampleCount, uint32_t seed, int mode, bmHit* d_hits, uint64_t* d_counters)
+{
+    if (!t || !eye3 || !orient9 || ((!d_initialRays3 || !d_hits) && numRays) || (mode != BM_TRACE_REFERENCE && mode != BM_TRACE_CLOSEST)) return BM_ERROR_INVALID_PARAMETER;
+    if (!sampleCount || firstSample == 0xFFFFFFFFu || firstSample + sampleCount < firstSample || !width || (numRays % width)) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) BM_TRY(tree_build(t));
+    CameraIn cam = make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, firstSample, seed);
+    BM_TRY(t->scalars.reserve(64));
+    TileSched sched;
+    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched));
+    return trace_camera(t->view(), cam, numRays, width, mode, d_hits, nullptr, nullptr, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream, sampleCount);
+}
+
+// Bounce launch: every pixel whose primary ray hit (d_hits1[k * numRays + i] of sample k, as bmTraceCameraSamples / bmTraceCamera[Jittered] wrote
+// it) traces that hit's diffuse bounce ray -- the ray bmBounceRaysCamera[Jittered] would put into a list, formed in registers instead -- as
+// a closest hit with t >= 0.  The launch walks the image in 8x4 tiles under its own temporal tile schedule: no compaction, no ray list.
+//   cameraSample0 : 0xFFFFFFFF = the primary rays were the exact pixel-centre rays (sampleCount must be 1), else the first camera sample
+//   bounceSample0 : index of the first sample in the bounce rays' random sequence (sample k of the launch uses bounceSample0 + k)
+//   d_hits2 (nullable) : sampleCount * numRays records, written only where the primary ray hit
+//   d_accum / d_covered (nullable) : progressive estimator applied where the bounce ray ends, accum[i] += ambient + (escaped ? weight : 0), covered[i] = 1
+//   d_rayCount (nullable, device u64) : += number of bounce rays traced
+extern "C" int bmTraceBounceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
+                                   float jitterX, float jitterY, uint32_t cameraSample0, uint32_t sampleCount, uint32_t cameraSeed, const bmHit* d_hits1,
+                                   uint32_t bounceSample0, uint32_t bounce, uint32_t seed, bmHit* d_hits2, float ambient, float weight, float* d_accum, uint32_t* d_covered,
+                                   uint64_t* d_rayCount, uint64_t* d_counters)
+{
+    if (!t || !eye3 || !orient9 || ((!d_initialRays3 || !d_hits1) && numRays) || !sampleCount || !width || (numRays % width)) return BM_ERROR_INVALID_PARAMETER;
+    if (cameraSample0 == 0xFFFFFFFFu && sampleCount != 1) return BM_ERROR_INVALID_PARAMETER;
+    if (!t->built) return BM_ERROR_NOT_BUILT;
+    CameraIn cam = make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, cameraSample0, cameraSeed);
+    BM_TRY(t->scalars.reserve(64));
+    TileSched sched;
+    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched, true));
+    BounceIn b = { d_hits1, t->soup.as<float4>(), bounceSample0, bounce, seed, d_accum, d_covered, ambient, weight, reinterpret_cast<unsigned long long*>(d_rayCount) };
+    return trace_camera(t->view(), cam, numRays, width, BM_TRACE_CLOSEST, d_hits2, nullptr, nullptr, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream, sampleCount, &b);
 }
 
 extern "C" int bmTraceCamera(bmTree* t, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9, int mode,

@@ -1,6 +1,6 @@
 import csv, collections, subprocess, sys
 rep=sys.argv[1]; top=int(sys.argv[2]) if len(sys.argv)>2 else 40
-out=subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass'],capture_output=True,text=True).stdout
+out=subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass']+sys.argv[3:],capture_output=True,text=True).stdout
 rows=list(csv.reader(out.splitlines()))
 cur_file=None; cur_line=None
 agg=collections.defaultdict(lambda:[0,0,0,''])

@@ -467,3 +467,76 @@ def test_bricked_ray_batches_equal_the_direct_traversal(layout, meshes, oracle_l
         beam_lib.bmTreeDestroy(h)
         t.close(); s.close()
     assert beam_lib.bmTreeSetBricks(None, 0, 0) != 0
+
+
+def test_bounce_launch_and_multi_sample_launch_equal_the_per_sample_lists(beam_lib, cuda_device):
+    """bmTraceCameraSamples (several jittered samples of every pixel in one launch) and bmTraceBounceCamera (bounce rays formed in the
+    kernel, no ray list) against the launches they replace: per sample bmTraceCameraJittered, bmBounceRaysCameraJittered ->
+    bmTraceRays(closest) -> bmProgressiveAccumulate.  Same rays, same traversal: hit records bit-equal, accumulators equal."""
+    import ctypes as C
+    import torch
+    from raytracercuda_b200 import host as H, workloads
+    from raytracercuda_b200.tree import Tree
+    L = beam_lib
+    wl = workloads.get("c2small")
+    W, Hh = 176, 100
+    n = W * Hh
+    cam = H.ICamera.create(); assert cam.setInitialRays(W, Hh, -1, 1, -1, 1, 1) == 0
+    table = torch.from_numpy(cam.initialRays()).to(cuda_device)
+    t = Tree(cuda_device); t.add_mesh(wl.positions, wl.indices); t.build()
+    eye = (C.c_float * 3)(0.0, 0.0, -2.1); ori = (C.c_float * 9)(*np.eye(3, dtype=np.float32).reshape(-1))
+    jx, jy = 2.0 / W, 2.0 / Hh
+    SEED, S0, G = 7, 2, 3
+    dev = cuda_device
+    f4 = lambda m: torch.empty((m, 4), dtype=torch.float32, device=dev)
+    for width in (W, ):
+        # --- pixel-centre frame: bounce launch vs list ---------------------------------------------------------------------------
+        h1 = f4(n)
+        assert L.bmTraceCamera(t.h, table.data_ptr(), n, width, eye, ori, 0, h1.data_ptr(), None, None, None) == 0
+        r2 = torch.empty((n, 6), dtype=torch.float32, device=dev); src = torch.empty(n, dtype=torch.int32, device=dev); cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        assert L.bmBounceRaysCamera(t.h, table.data_ptr(), eye, ori, h1.data_ptr(), n, 0, 1, SEED, r2.data_ptr(), src.data_ptr(), cnt.data_ptr()) == 0
+        nb = int(cnt.item()); assert nb > 1000
+        h2_list = f4(n)
+        assert L.bmTraceRays(t.h, r2.data_ptr(), nb, 1, h2_list.data_ptr(), None) == 0
+        for rep in range(2):                      # the second launch runs under the tile schedule the first one recorded
+            h2 = torch.full((n, 4), -7.0, dtype=torch.float32, device=dev); count = torch.zeros(1, dtype=torch.int64, device=dev)
+            acc = torch.zeros(n, dtype=torch.float32, device=dev); cov = torch.zeros(n, dtype=torch.int32, device=dev)
+            assert L.bmTraceBounceCamera(t.h, table.data_ptr(), n, width, eye, ori, 0.0, 0.0, 0xFFFFFFFF, 1, 0, h1.data_ptr(), 0, 1, SEED, h2.data_ptr(), 0.25, 0.75,
+                                         acc.data_ptr(), cov.data_ptr(), count.data_ptr(), None) == 0
+            torch.cuda.synchronize()
+            assert int(count.item()) == nb
+            s_ = src[:nb].long()
+            assert torch.equal(h2[s_].view(torch.int32), h2_list[:nb].view(torch.int32))
+            hit = h1[:, 3].view(torch.int32) != -1
+            assert bool((h2[~hit] == -7.0).all())                                           # written only where the primary ray hit
+            want = torch.zeros(n, dtype=torch.float32, device=dev); want[hit] = 0.25
+            esc = s_[h2_list[:nb, 3].view(torch.int32) == -1]; want[esc] += 0.75
+            assert torch.equal(acc, want) and torch.equal(cov.bool(), hit)
+        # --- G jittered samples in one launch vs one launch per sample -------------------------------------------------------------
+        for rep in range(2):
+            hs = f4(n * G)
+            assert L.bmTraceCameraSamples(t.h, table.data_ptr(), n, width, eye, ori, jx, jy, S0, G, SEED, 0, hs.data_ptr(), None) == 0
+            acc = torch.zeros(n, dtype=torch.float32, device=dev); cov = torch.zeros(n, dtype=torch.int32, device=dev); count = torch.zeros(1, dtype=torch.int64, device=dev)
+            h2s = torch.full((n * G, 4), -7.0, dtype=torch.float32, device=dev)
+            assert L.bmTraceBounceCamera(t.h, table.data_ptr(), n, width, eye, ori, jx, jy, S0, G, SEED, hs.data_ptr(), S0, 1, SEED, h2s.data_ptr(), 0.25, 0.75,
+                                         acc.data_ptr(), cov.data_ptr(), count.data_ptr(), None) == 0
+            want = torch.zeros(n, dtype=torch.float32, device=dev); wcov = torch.zeros(n, dtype=torch.bool, device=dev); total = 0
+            for k in range(G):
+                hk = f4(n)
+                assert L.bmTraceCameraJittered(t.h, table.data_ptr(), n, width, eye, ori, jx, jy, S0 + k, SEED, 0, hk.data_ptr(), None, None, None) == 0
+                assert torch.equal(hk.view(torch.int32), hs[k * n:(k + 1) * n].view(torch.int32)), "sample %d of the multi-sample launch differs" % k
+                assert L.bmBounceRaysCameraJittered(t.h, table.data_ptr(), eye, ori, jx, jy, S0 + k, SEED, hk.data_ptr(), n, S0 + k, 1, SEED, r2.data_ptr(), src.data_ptr(), cnt.data_ptr()) == 0
+                nbk = int(cnt.item()); total += nbk
+                assert L.bmTraceRays(t.h, r2.data_ptr(), nbk, 1, h2_list.data_ptr(), None) == 0
+                s_ = src[:nbk].long()
+                assert torch.equal(h2s[k * n:(k + 1) * n][s_].view(torch.int32), h2_list[:nbk].view(torch.int32)), "bounce hits of sample %d differ" % k
+                hit = hk[:, 3].view(torch.int32) != -1
+                want[hit] += 0.25; wcov |= hit
+                want[s_[h2_list[:nbk, 3].view(torch.int32) == -1]] += 0.75
+            torch.cuda.synchronize()
+            assert int(count.item()) == total
+            assert torch.equal(acc, want) and torch.equal(cov.bool(), wcov)
+    # argument checks: a pixel-centre frame is one sample; a multi-sample camera launch needs jittered samples
+    assert L.bmTraceBounceCamera(t.h, table.data_ptr(), n, W, eye, ori, 0.0, 0.0, 0xFFFFFFFF, 2, 0, h1.data_ptr(), 0, 1, SEED, None, 0.25, 0.75, None, None, None, None) != 0
+    assert L.bmTraceCameraSamples(t.h, table.data_ptr(), n, W, eye, ori, jx, jy, 0xFFFFFFFF, 1, SEED, 0, hs.data_ptr(), None) != 0
+    t.close()
