@@ -99,8 +99,8 @@ int pack_leaf_tris(const float4* d_soup, const u32* d_vals, size_t n, float4* d_
 int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* d_leafIdx, size_t numPairs, const u32* d_clusterFirst, float4* d_ltris,
                 float4* d_clusters, float4* d_leafBox2, float pad, u32* d_stats, u32* d_overList, cudaStream_t s);
 // radix tree + tight boxes + reference-node data in one bottom-up pass; *d_root receives the root's node index
-// d_nodes (nullable): the 128-byte binary records; d_wnodes: the 64-byte wide records (bm_wide.cuh); d_nodeMeta: scratch, 8 bytes per node
-int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
+// d_meet: scratch, 8 bytes per node (where the two children of a node meet); d_nodes (nullable): the 128-byte binary records; d_wnodes: the 64-byte wide records (bm_wide.cuh); d_nodeMeta: scratch, 8 bytes per node
+int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, unsigned long long* d_meet, u32* d_childRefs,
                     float4* d_nodes, uint4* d_wnodes, uint2* d_nodeMeta, u32* d_root, cudaStream_t s);
 int copy_topology(const Grid& g, const u32* d_childRefs, const uint2* d_nodeMeta, u32 numNodes, u32* d_prefixLen, u32* d_prefix, u32* d_child0, u32* d_child1, cudaStream_t s);
 int copy_child_boxes(const u32* d_childRefs, const float4* d_leafBox2, const float4* d_nodeBox2, u32 numNodes, float* d_boxes12, cudaStream_t s);

@@ -6,6 +6,7 @@
 // exactly the radix-tree node whose keys share a d-bit prefix and then differ; single-child chain nodes of the reference
 // have no counterpart because they take no decision.  agglomerate_kernel stores (prefix, prefixLen) and, precomputed from the
 // grid tables, the node's cell box, split axis (prefixLen % 3) and split plane -- the reference's own values.
+#include <cstdlib>
 #include "bm_device.cuh"
 #include "bm_wide.cuh"
 
@@ -174,56 +175,80 @@ __device__ __forceinline__ WSlotBox slot_box(const Box2& b)
     return r;
 }
 
-// nodes (nullable): the 128-byte binary records; nodeMeta[n] = (packed cell coordinates, depth) of node n.  The 64-byte wide records are
-// written by wide_encode_kernel below from childRefs / nodeMeta / the boxes this pass leaves behind.
-__global__ void agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 numLeaves, const float4* __restrict__ leafBox, float4* nodeBox,
-                                   int* otherBound, u32* childRefs, float4* nodes, uint2* nodeMeta, u32* rootOut)
+// What a finished node receives (both phases of agglomerate_kernel): the 128-byte binary record (nodes, nullable) and nodeMeta[n] =
+// (packed cell coordinates, depth).  The 64-byte wide records are written by wide_encode_kernel below from childRefs / nodeMeta / the
+// boxes this pass leaves behind.
+__device__ __forceinline__ void finish_node(const Grid& g, int D, const u32* __restrict__ codes, int parent, int l, int r, u32 c0, u32 c1, const Box2& b0, const Box2& b1,
+                                            float4* nodes, uint2* nodeMeta)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 cl = __ldg(codes + l), cr = __ldg(codes + r);
+    int plen = __clz(cl ^ cr) - (32 - D);         // common prefix length inside the D-bit code (l < r: codes differ)
+    u32 prefix = plen > 0 ? (cl >> (D - plen)) : 0u;
+    u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
+    if (nodes)
+    {
+        V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
+        int axis = plen % 3;
+        u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+        int sh = g.k[axis] - axis_bits(plen, axis);   // >= 1: the node splits on this axis
+        float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
+        float4* np = nodes + NODE_F4 * (size_t)parent;
+        np[0] = b0.a;                                                   // lo0.xyz hi0.x
+        np[1] = make_float4(b0.b.x, b0.b.y, b1.a.x, b1.a.y);            // hi0.yz lo1.xy
+        np[2] = make_float4(b1.a.z, b1.a.w, b1.b.x, b1.b.y);            // lo1.z hi1.xyz
+        np[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
+        np[4] = make_float4(mn.x, mn.y, mn.z, sp);
+        np[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
+    }
+    // (cell coordinates, depth) of the node: what the wide-record pass and bmTreeCopyTopology read
+    __stcg(&nodeMeta[parent], make_uint2(wide_pack_cell(g, ix, iy, iz), (u32)plen));
+}
+__device__ __forceinline__ Box2 unite(const Box2& b0, const Box2& b1)
+{
+    Box2 m;
+    m.a = make_float4(fminf(b0.a.x, b1.a.x), fminf(b0.a.y, b1.a.y), fminf(b0.a.z, b1.a.z), fmaxf(b0.a.w, b1.a.w));
+    m.b = make_float4(fmaxf(b0.b.x, b1.b.x), fmaxf(b0.b.y, b1.b.y), 0.f, 0.f);
+    return m;
+}
+
+// One 64-bit exchange per arrival carries everything the two children of a node have to tell each other: (subtree reference, far bound of
+// its key range).  The second arrival therefore learns its sibling from the exchange itself -- its loads of the sibling's box depend on
+// the value returned, so they cannot be issued early and need no fence -- and is the one that writes the node's child references.  A
+// device-wide fence remains only where a thread has written something another thread will read: the box of a NODE it has just finished,
+// before it arrives at that node's parent; a leaf's box was there before the launch.  That is one fence per internal node instead of
+// three (the pass was bound by them: membar 11.5 of 24 stall cycles per issue, profiles/r2_SUMMARY.md).
+// Tried and dropped: meeting through shared memory for nodes whose range lies inside the block's leaves (no fences at all for ~94 % of
+// the nodes).  Finding out whether a parent is such a node needs the far end of the sibling's range -- a walk over the deltas as long as
+// the sibling is large, by the few lanes still climbing: 2.7x the instructions, 10.5 instead of 8.3 ms on 50 M leaves.
+constexpr int AGG_THREADS = 128;
+__global__ void __launch_bounds__(AGG_THREADS) agglomerate_kernel(Grid g, const u32* __restrict__ codes, u32 numLeaves, const float4* __restrict__ leafBox, float4* nodeBox,
+                                                                  unsigned long long* meet, u32* childRefs, float4* nodes, uint2* nodeMeta, u32* rootOut)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = (int)numLeaves;
     if (i >= n) return;
     const int D = g.D;
     int l = i, r = i;
     u32 cur = (u32)i | LEAF_BIT;
+    Box2 box; box.a = __ldg(leafBox + 2 * (size_t)i); box.b = __ldg(leafBox + 2 * (size_t)i + 1);
     for (;;)
     {
-        bool leftChild = (l == 0) || (r != n - 1 && range_delta(codes, r, n) < range_delta(codes, l - 1, n));
-        int parent = leftChild ? r : l - 1;
-        childRefs[2 * (size_t)parent + (leftChild ? 0 : 1)] = cur;
-        __threadfence();
-        int other = atomicExch(&otherBound[parent], leftChild ? l : r);
-        if (other == -1) return;                      // first arrival: the sibling will finish this node
-        __threadfence();
-        if (leftChild) r = other; else l = other;
-        // second arrival: both children are known and their boxes written
-        u32 c0 = __ldcg(&childRefs[2 * (size_t)parent]), c1 = __ldcg(&childRefs[2 * (size_t)parent + 1]);
-        Box2 b0 = load_box((c0 & LEAF_BIT) ? leafBox + 2 * (size_t)(c0 & ~LEAF_BIT) : nodeBox + 2 * (size_t)c0);
-        Box2 b1 = load_box((c1 & LEAF_BIT) ? leafBox + 2 * (size_t)(c1 & ~LEAF_BIT) : nodeBox + 2 * (size_t)c1);
-        u32 cl = __ldg(codes + l), cr = __ldg(codes + r);
-        int plen = __clz(cl ^ cr) - (32 - D);         // common prefix length inside the D-bit code (l < r: codes differ)
-        u32 prefix = plen > 0 ? (cl >> (D - plen)) : 0u;
-        u32 ix, iy, iz; decode_path(plen, prefix, ix, iy, iz);
-        if (nodes)
-        {
-            V3 mn, mx; cell_box(g, plen, ix, iy, iz, mn, mx);
-            int axis = plen % 3;
-            u32 ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
-            int sh = g.k[axis] - axis_bits(plen, axis);   // >= 1: the node splits on this axis
-            float sp = grid_at(g, axis, ((ia << 1) | 1u) << (sh - 1));
-            float4* np = nodes + NODE_F4 * (size_t)parent;
-            np[0] = b0.a;                                                   // lo0.xyz hi0.x
-            np[1] = make_float4(b0.b.x, b0.b.y, b1.a.x, b1.a.y);            // hi0.yz lo1.xy
-            np[2] = make_float4(b1.a.z, b1.a.w, b1.b.x, b1.b.y);            // lo1.z hi1.xyz
-            np[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(prefix), __uint_as_float((u32)plen));
-            np[4] = make_float4(mn.x, mn.y, mn.z, sp);
-            np[5] = make_float4(mx.x, mx.y, mx.z, __uint_as_float((u32)axis));
-        }
-        // (cell coordinates, depth) of the node: what the wide-record pass and bmTreeCopyTopology read
-        __stcg(&nodeMeta[parent], make_uint2(wide_pack_cell(g, ix, iy, iz), (u32)plen));
+        const bool leftChild = (l == 0) || (r != n - 1 && range_delta(codes, r, n) < range_delta(codes, l - 1, n));
+        const int parent = leftChild ? r : l - 1;
+        if (!(cur & LEAF_BIT)) __threadfence();       // nodeBox[cur], written below in the previous round, before anybody can learn of `cur`
+        const unsigned long long other = atomicExch(&meet[parent], ((unsigned long long)cur << 32) | (u32)(leftChild ? l : r));
+        if (other == ~0ull) return;                   // first arrival: the sibling will finish this node
+        const u32 sib = (u32)(other >> 32);
+        if (leftChild) r = (int)(u32)other; else l = (int)(u32)other;
+        const Box2 sb = load_box((sib & LEAF_BIT) ? leafBox + 2 * (size_t)(sib & ~LEAF_BIT) : nodeBox + 2 * (size_t)sib);
+        const u32 c0 = leftChild ? cur : sib, c1 = leftChild ? sib : cur;
+        const Box2& b0 = leftChild ? box : sb; const Box2& b1 = leftChild ? sb : box;
+        __stcg(reinterpret_cast<uint2*>(childRefs) + parent, make_uint2(c0, c1));
+        finish_node(g, D, codes, parent, l, r, c0, c1, b0, b1, nodes, nodeMeta);
         if (l == 0 && r == n - 1) { *rootOut = (u32)parent; return; }
-        float4* o = nodeBox + 2 * (size_t)parent;
-        __stcg(o, make_float4(fminf(b0.a.x, b1.a.x), fminf(b0.a.y, b1.a.y), fminf(b0.a.z, b1.a.z), fmaxf(b0.a.w, b1.a.w)));
-        __stcg(o + 1, make_float4(fmaxf(b0.b.x, b1.b.x), fmaxf(b0.b.y, b1.b.y), 0.f, 0.f));
+        box = unite(b0, b1);
+        float4* o = nodeBox + 2 * (size_t)parent;       // read by the thread that finishes the parent, and by wide_encode_kernel
+        __stcg(o, box.a); __stcg(o + 1, box.b);
         cur = (u32)parent;
     }
 }
@@ -368,12 +393,12 @@ int leaf_bounds(float4* d_leaves, u32 numLeaves, const u32* d_flags, const u32* 
     BM_LAUNCHED();
     return BM_OK;
 }
-int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, int* d_otherBound, u32* d_childRefs,
+int build_hierarchy(const Grid& g, const u32* d_codes, u32 numLeaves, const float4* d_leafBox2, float4* d_nodeBox2, unsigned long long* d_meet, u32* d_childRefs,
                     float4* d_nodes, uint4* d_wnodes, uint2* d_nodeMeta, u32* d_root, cudaStream_t s)
 {
     if (numLeaves < 2) return BM_OK;
-    BM_CUDA(cudaMemsetAsync(d_otherBound, 0xFF, (size_t)(numLeaves - 1) * 4, s));
-    agglomerate_kernel<<<div_up(numLeaves, 128), 128, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_otherBound, d_childRefs, d_nodes, d_nodeMeta, d_root);
+    BM_CUDA(cudaMemsetAsync(d_meet, 0xFF, (size_t)(numLeaves - 1) * 8, s));
+    agglomerate_kernel<<<div_up(numLeaves, AGG_THREADS), AGG_THREADS, 0, s>>>(g, d_codes, numLeaves, d_leafBox2, d_nodeBox2, d_meet, d_childRefs, d_nodes, d_nodeMeta, d_root);
     BM_LAUNCHED();
     if (d_wnodes)
     {

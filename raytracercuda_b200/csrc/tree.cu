@@ -258,8 +258,8 @@ static int tree_build(bmTree* t)
         if (t->layout != BM_NODES_WIDE) BM_TRY(t->nodes.reserve((L - 1) * 16 * NODE_F4));
         if (t->layout != BM_NODES_BINARY) BM_TRY(t->wnodes.reserve((L - 1) * 64));
         BM_TRY(t->nodeBox.reserve((L - 1) * 32)); BM_TRY(t->nodeMeta.reserve((L - 1) * 8));
-        BM_TRY(t->parentN.reserve((L - 1) * 8)); BM_TRY(t->visit.reserve((L - 1) * 4));
-        BM_TRY(build_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->visit.as<int>(), t->parentN.as<u32>(),
+        BM_TRY(t->parentN.reserve((L - 1) * 8)); BM_TRY(t->visit.reserve((L - 1) * 8));
+        BM_TRY(build_hierarchy(t->dgrid, t->codes.as<u32>(), (u32)L, t->leafBox.as<float4>(), t->nodeBox.as<float4>(), t->visit.as<unsigned long long>(), t->parentN.as<u32>(),
                                t->layout != BM_NODES_WIDE ? t->nodes.as<float4>() : nullptr, t->layout != BM_NODES_BINARY ? t->wnodes.as<uint4>() : nullptr,
                                t->nodeMeta.as<uint2>(), t->rootDev.as<u32>(), s));
     }
