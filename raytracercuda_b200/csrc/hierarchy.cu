@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(AGG_THREADS) agglomerate_kernel(Grid g, const 
     {
         const bool leftChild = (l == 0) || (r != n - 1 && range_delta(codes, r, n) < range_delta(codes, l - 1, n));
         const int parent = leftChild ? r : l - 1;
-        if (!(cur & LEAF_BIT)) __threadfence();       // nodeBox[cur], written below in the previous round, before anybody can learn of `cur`
+        // release: nodeBox[cur], written below in the previous round, is visible before anybody can learn of `cur`.  A release fence is enough
+        // for that (__threadfence() is the sequentially consistent one: MEMBAR.SC.GPU + CCTL.IVALL; this is MEMBAR.ALL.GPU, no L1 invalidate)
+        if (!(cur & LEAF_BIT)) asm volatile("fence.release.gpu;" ::: "memory");
         const unsigned long long other = atomicExch(&meet[parent], ((unsigned long long)cur << 32) | (u32)(leftChild ? l : r));
         if (other == ~0ull) return;                   // first arrival: the sibling will finish this node
         const u32 sib = (u32)(other >> 32);

@@ -146,6 +146,12 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const K* __re
 // the tiles before it by decoupled look-back (thread d walks digit d's chain).  Tiles are numbered by an atomic ticket in the order
 // the blocks start, so a block only waits for blocks that already run; waits are bounded and trap.  status word: flag << 30 | count.
 constexpr int RS_MAX_PASSES = 8;
+// one-sweep tile: items per thread (the tile is staged in DYNAMIC shared memory, so it may exceed the 48 KB static limit)
+#ifndef BM_OS_ITEMS64
+#define BM_OS_ITEMS64 12
+#endif
+template <class K> struct OsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : BM_OS_ITEMS64; static constexpr int TILE = RS_THREADS * ITEMS;
+                                  static constexpr size_t SMEM = (size_t)TILE * (sizeof(K) + 4); };
 constexpr u32 OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_VAL = (1u << 30) - 1u;
 
 template <class K>
@@ -172,13 +178,14 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const K* __r
                                                                     K* __restrict__ keysOut, u32* __restrict__ valsOut, size_t n, int shift,
                                                                     const u32* __restrict__ passHist, u32* ticket, volatile u32* status)
 {
-    constexpr int RS_ITEMS = RsCfg<K>::ITEMS, RS_TILE = RsCfg<K>::TILE;
+    constexpr int RS_ITEMS = OsCfg<K>::ITEMS, RS_TILE = OsCfg<K>::TILE;
     __shared__ u32 warpHist[RS_WARPS][RS_BINS + 1];     // +1: bin 256 swallows the out-of-range tail
     __shared__ u32 digitStart[RS_BINS + 1];
     __shared__ u32 globalBase[RS_BINS];
     __shared__ u32 scanTmp[RS_WARPS];
-    __shared__ K sKeys[RS_TILE];
-    __shared__ u32 sVals[RS_TILE];
+    extern __shared__ __align__(16) unsigned char osDyn[];
+    K* sKeys = reinterpret_cast<K*>(osDyn);
+    u32* sVals = reinterpret_cast<u32*>(osDyn + (size_t)RS_TILE * sizeof(K));
     __shared__ u32 sTile;
 
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -318,15 +325,22 @@ static int radix_sort_impl(K* d_keysA, u32* d_valsA, K* d_keysB, u32* d_valsB, s
         u32* hist = (u32*)((char*)scanTemp + scan_temp_bytes(tiles * RS_BINS));
         u32* ticket = hist + RS_MAX_PASSES * RS_BINS;
         BM_CUDA(cudaMemsetAsync(hist, 0, RS_MAX_PASSES * RS_BINS * 4 + 4, s));
+        const size_t osTiles = (n + OsCfg<K>::TILE - 1) / OsCfg<K>::TILE;
+        static std::atomic<int> smemSet[MAX_DEVICES];
+        if (!smemSet[current_device()].load(std::memory_order_relaxed))
+        {
+            BM_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OsCfg<K>::SMEM));
+            smemSet[current_device()].store(1, std::memory_order_relaxed);
+        }
         unsigned hb = (unsigned)((n + RS_THREADS * 16 - 1) / (RS_THREADS * 16));
         unsigned cap = (unsigned)sm_count() * 8;
         radix_all_hist_kernel<K><<<hb < cap ? hb : cap, RS_THREADS, 0, s>>>(ka, n, passes, hist);
         BM_LAUNCHED();
         for (int p = 0; p < passes; p++)
         {
-            BM_CUDA(cudaMemsetAsync(counts, 0, tiles * RS_BINS * 4, s));
+            BM_CUDA(cudaMemsetAsync(counts, 0, osTiles * RS_BINS * 4, s));
             if (p) BM_CUDA(cudaMemsetAsync(ticket, 0, 4, s));
-            radix_onesweep_kernel<K><<<(unsigned)tiles, RS_THREADS, 0, s>>>(ka, va, kb, vb, n, 8 * p, hist + p * RS_BINS, ticket, counts);
+            radix_onesweep_kernel<K><<<(unsigned)osTiles, RS_THREADS, OsCfg<K>::SMEM, s>>>(ka, va, kb, vb, n, 8 * p, hist + p * RS_BINS, ticket, counts);
             BM_LAUNCHED();
             K* t = ka; ka = kb; kb = t;
             u32* tv = va; va = vb; vb = tv;
