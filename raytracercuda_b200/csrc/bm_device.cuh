@@ -193,11 +193,15 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numR
 //   state: [0, 64) histogram of cost buckets, [64, 128) scatter cursors, [TS_SUM] 64-bit total cost (all zeroed per launch), [TS_OK] and
 //          [TS_ENTRIES] set by the ordering kernel
 constexpr int TS_BUCKETS = 64, TS_SUM = 128, TS_OK = 130, TS_ENTRIES = 131, TS_WORDS = 132;       // [0, TS_OK) is zeroed before every launch
-struct TileSched { u32* cost; u32* order; u32* state; u32 tiles; };
+//   hitFlag (nullable, camera launches): hitFlag[tile] = 1 where some ray of the tile hit
+//   filter  (nullable, bounce launches): the hitFlag array of the camera launch whose hits this launch follows up -- the work list is then
+//                made just BEFORE the launch: tiles that pass the filter, by descending cost in the previous bounce launch
+struct TileSched { u32* cost; u32* order; u32* state; u32 tiles; u32* hitFlag; const u32* filter; };
 // samples > 1: the launch covers samples cam.sample .. cam.sample + samples - 1 of every pixel (jitter applied in the kernel); d_hits then holds
 // samples * n records, sample-major.  bounce (nullable): a bounce launch (BounceIn).
 int trace_camera(const TreeView& tv, const CameraIn& cam, u64 n, u32 width, int mode, bmHit* d_hits, u32* d_pixels, const bmStaticMeshData* d_meshData,
                  u64* d_counters, u32* d_workCounter, const TileSched* sched, cudaStream_t s, u32 samples = 1, const BounceIn* bounce = nullptr);
+bool tile_sched_usable();
 int trace_rays_tiled(const TreeView& tv, const bmRay* d_rays, u64 n, u32 width, int mode, bmHit* d_hits, u64* d_counters, u32* d_workCounter,
                      const TileSched* sched, cudaStream_t s);
 // Segments of a ray batch traced brick by brick (bricks.cu): keys[i] = position of the brick in the ray's visiting order << 24 | wave << bits | brick,

@@ -471,14 +471,16 @@ __device__ __forceinline__ u32 tile_bucket(u32 cost)
 }
 
 // After a camera launch: histogram of the tiles' cost buckets ...
-__global__ void tile_hist_kernel(u32 tiles, const u32* __restrict__ cost, u32* state)
+// filter (nullable): only tiles with filter[i] != 0 take part (bounce launches: the tiles in which the camera launch had hits)
+__global__ void tile_hist_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, const u32* __restrict__ filter)
 {
     __shared__ u32 h[TS_BUCKETS];
     if (threadIdx.x < TS_BUCKETS) h[threadIdx.x] = 0;
     __syncthreads();
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 c = i < tiles ? cost[i] : 0u;
-    if (i < tiles) atomicAdd(&h[tile_bucket(c)], 1u);
+    const bool in = i < tiles && (!filter || filter[i] != 0u);
+    u32 c = in ? cost[i] : 0u;
+    if (in) atomicAdd(&h[tile_bucket(c)], 1u);
     // total cost of the frame (64 bits in state[TS_SUM], state[TS_SUM + 1])
     unsigned long long sum = c;
 #pragma unroll
@@ -493,7 +495,8 @@ __global__ void tile_hist_kernel(u32 tiles, const u32* __restrict__ cost, u32* s
 // bench frame some 250 silhouette tiles that each cost ~20x the average -- are entered as four QUARTERS (one 8-pixel row each, entry =
 // tile | (row + 1) << 28), so that four warps share them.  Quarters run at 8 of 32 lanes, so splitting more than those loses throughput
 // (measured: splitting the top 1/256 of the tiles -9 % launch time, the top 1/64 +0 %, the top 1/16 +27 %).  state[TS_ENTRIES] = number of entries; state[TS_OK] says the list is usable (every tile was costed).
-__global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, u32* __restrict__ order, u32 splitPct, u32 residentWarps)
+// samples: a tile's cost is the sum over the launch's samples, but each sample of it is a work item of its own
+__global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, u32* __restrict__ order, u32 splitPct, u32 residentWarps, const u32* __restrict__ filter, u32 samples)
 {
     __shared__ u32 base[TS_BUCKETS], bins[TS_BUCKETS];
     __shared__ u32 total, entries, splitFrom;
@@ -506,7 +509,7 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
         u32 run = 0, sf = TS_BUCKETS;
         if (splitPct)
         {
-            unsigned long long thr = costSum / (residentWarps ? residentWarps : 1u) * splitPct / 100ull;    // cost a tile must exceed to be split
+            unsigned long long thr = costSum / (residentWarps ? residentWarps : 1u) * splitPct / 100ull * (samples ? samples : 1u);    // cost a tile must exceed to be split
             for (int b = TS_BUCKETS - 1; b >= 2; --b)
             {
                 u32 l = (u32)b >> 1;
@@ -520,7 +523,9 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
     }
     __syncthreads();
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < tiles && total == tiles)
+    // without a filter the list is usable only if every tile was costed by the previous launch; a filtered list holds exactly the tiles
+    // that passed the filter (a tile that has no cost yet lands in the cheapest class)
+    if (i < tiles && (filter ? filter[i] != 0u : total == tiles))
     {
         u32 b = tile_bucket(cost[i]);
         // one atomic per (warp, bucket): neighbouring tiles mostly share a bucket
@@ -540,7 +545,7 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
             if (pos < 4u * tiles) order[pos] = i;
         }
     }
-    if (i == 0) { state[TS_ENTRIES] = entries; state[TS_OK] = (total == tiles) ? 1u : 0u; }
+    if (i == 0) { state[TS_ENTRIES] = entries; state[TS_OK] = (filter || total == tiles) ? 1u : 0u; }
 }
 
 // Persistent warps (one resident grid; every warp pulls work from a global counter), while-while traversal:
@@ -606,6 +611,7 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
                 u32 cost = c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)c;
                 atomicAdd(&sched.cost[curTile], cost);          // zeroed before the launch; the quarters of a split tile add up
             }
+
             curTile = 0xFFFFFFFFu;
         }
         if (idle && !exhausted && (__popc(idle) >= refillMin || idle == FULL))
@@ -859,6 +865,9 @@ __global__ void __launch_bounds__(TR_THREADS, BM_TR_BLOCKS) trace_kernel(TreeVie
             else
             {
                 const size_t at = (CAMERA || BOUNCE) ? (size_t)raySample * n + rayIdx : (size_t)rayIdx;
+                // tiles with at least one hit (in any sample), for the bounce launch that follows: its work list leaves the others out
+                // (the lanes of a warp share the tile: one store per warp instruction)
+                if (CAMERA && !BOUNCE && sched.hitFlag && best.tri != 0xFFFFFFFFu) sched.hitFlag[curTile] = 1u;
                 if (hits) { reinterpret_cast<float4*>(hits)[at] = make_float4(best.t, best.u, best.v, __uint_as_float(best.tri)); }
                 if (pixels) pixels[rayIdx] = shade(best, meshData);
                 if (BOUNCE)
@@ -950,6 +959,11 @@ int refill_min(bool camera)
     return v > 0 ? v : (camera ? 32 : 8);
 }
 
+} // namespace
+// camera launches run under a tile schedule only when they refill whole warps (the default; BM_REFILL_MIN overrides it for tuning)
+bool tile_sched_usable() { return refill_min(true) == 32; }
+namespace
+{
 // node records walked by the trace kernels (bmTreeNodeLayout)
 bool use_wide(const TreeView& tv)
 {
@@ -988,18 +1002,28 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     {
         ts = *sched;
         BM_CUDA(cudaMemsetAsync(ts.state, 0, TS_OK * 4, s));          // histogram + cursors; OK flag and entry count of the previous launch stay
+        if (ts.filter)
+        {
+            // a filtered work list is made just before the launch it serves (the filter is what the preceding camera launch found out):
+            // tiles that passed, by descending cost in the previous launch of this kind
+            tile_hist_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.filter);
+            BM_LAUNCHED();
+            tile_order_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.order, tile_split_pct(), (u32)blocks * (TR_THREADS / 32), ts.filter, samples);
+            BM_LAUNCHED();
+        }
         BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
+        if (ts.hitFlag) BM_CUDA(cudaMemsetAsync(ts.hitFlag, 0, (size_t)ts.tiles * 4, s));
     }
     const BounceIn none = { nullptr, nullptr, 0u, 0u, 0u, nullptr, nullptr, 0.f, 0.f, nullptr };
     trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG, BOUNCE><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
                                                                             d_counters, d_workCounter, leaf_break(CAMERA ? 0 : queue_depth()), leaf_wait(CAMERA ? 0 : queue_depth()), refill, CAMERA ? 0 : queue_depth(), ts, seg,
                                                                             samples, bounce ? *bounce : none);
     BM_LAUNCHED();
-    if (ts.cost)
+    if (ts.cost && !ts.filter)
     {
-        tile_hist_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state);
+        tile_hist_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, nullptr);
         BM_LAUNCHED();
-        tile_order_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.order, tile_split_pct(), (u32)blocks * (TR_THREADS / 32));
+        tile_order_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.order, tile_split_pct(), (u32)blocks * (TR_THREADS / 32), nullptr, samples);
         BM_LAUNCHED();
     }
     return BM_OK;

@@ -85,13 +85,16 @@ struct bmTree
     std::vector<u32> meshBase;       // indexed by position in `staged` order
     bool built = false, imported = false;
     // build products
-    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState, tileCostB, tileOrderB, tileStateB;
+    DevBuf soup, counts, keysA, valsA, keysB, valsB, flags, temp, leaves, ltris, clusters, clusterCounts, leafBox, nodeBox, parentN, parentL, visit, nodes, wnodes, nodeMeta, scalars, rayFlags, rayTemp, canonA, canonB, canonV, masks, infos, codes, largeList, rootDev, tileCost, tileOrder, tileState, tileCostB, tileOrderB, tileStateB, tileHitFlag;
     DevBuf brickRoots, brickOcc, segKeysA, segKeysB, segValsA, segValsB, rayKey, segCount;      // ray batches traced brick by brick (bricks.cu)
     int brickBits = 0;               // depth the brick table is valid for (0 = none; reset by every build)
     int brickMode = -1, brickBitsWanted = 0;      // bmTreeSetBricks: -1 = automatic (BM_BRICKS), 0 = never, 1 = always; bits 0 = default (BM_BRICK_BITS)
     size_t segCapacity = 0;
     bool stageTiming = false; std::string lastStages;      // bmTreeEnableStageTiming / bmTreeLastBuildStages
     int layout = BM_NODES_BINARY;    // which node records the last build wrote (BM_NODES_*; set by tree_build, or by bmTreeImport)
+    // the tiles with hits of the last camera launch (TileSched::hitFlag) and the hit records they describe: a bounce launch over exactly
+    // those records (same buffer, same shape) leaves the other tiles out of its work list
+    struct { const void* hits = nullptr; u64 n = 0; u32 width = 0, samples = 0; bool valid = false; } lastCamera;
     u32 schedTilesB = 0;             // the same for bounce launches (their own costs: a tile's bounce rays are not its primary rays)
     u32 schedTiles = 0;              // frame size (in 8x4 tiles) the tile-scheduling buffers are set up for; 0 = none
     u64* sortedKeys = nullptr; u32* sortedVals = nullptr;
@@ -119,7 +122,7 @@ struct bmTree
     }
     ~bmTree()
     {
-        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &wnodes, &nodeMeta, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState, &tileCostB, &tileOrderB, &tileStateB, &brickRoots, &brickOcc, &segKeysA, &segKeysB, &segValsA, &segValsB, &rayKey, &segCount };
+        DevBuf* all[] = { &tables, &soup, &counts, &keysA, &valsA, &keysB, &valsB, &flags, &temp, &leaves, &ltris, &clusters, &clusterCounts, &canonA, &canonB, &canonV, &masks, &infos, &codes, &largeList, &rootDev, &leafBox, &nodeBox, &parentN, &parentL, &visit, &nodes, &wnodes, &nodeMeta, &scalars, &rayFlags, &rayTemp, &tileCost, &tileOrder, &tileState, &tileCostB, &tileOrderB, &tileStateB, &tileHitFlag, &brickRoots, &brickOcc, &segKeysA, &segKeysB, &segValsA, &segValsB, &rayKey, &segCount };
         for (DevBuf* b : all) b->release();
     }
 };
@@ -155,7 +158,7 @@ static int tree_build(bmTree* t)
     for (auto& m : t->staged) { t->meshBase.push_back((u32)T); T += m.numTris; }
     if (T >= 0xFFFFFFFFull) { set_error("more than 2^32-2 triangles"); return BM_ERROR_CAPACITY; }
     t->T = T; t->P = 0; t->L = 0; t->maxLeaf = 0; t->overLeaves = 0;
-    t->schedTiles = 0; t->schedTilesB = 0;               // a new scene: forget the tile costs of the old one
+    t->schedTiles = 0; t->schedTilesB = 0; t->lastCamera.valid = false;               // a new scene: forget the tile costs of the old one
     t->brickBits = 0;                // ... and its brick table
     BM_TRY(t->scalars.reserve(64)); BM_TRY(t->rootDev.reserve(16));
     BM_CUDA(cudaMemsetAsync(t->scalars.p, 0, 64, s));
@@ -604,13 +607,15 @@ extern "C" int bmTraceRaysIndirect(bmTree* t, const bmRay* d_rays, const uint32_
 }
 
 // temporal tile scheduling (TileSched, bm_device.cuh): per tree and frame size; BM_TILE_ORDER=0 turns it off
-static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uint64_t* d_counters, TileSched& sched, bool bounceLaunch = false)
+static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uint64_t* d_counters, TileSched& sched, bool bounceLaunch = false, u32 hitListSamples = 0)
 {
+    static const bool hitListOn = !(getenv("BM_BOUNCE_LIST") && atoi(getenv("BM_BOUNCE_LIST")) == 0);
+    if (!bounceLaunch) t->lastCamera.valid = false;
     DevBuf& tileCost = bounceLaunch ? t->tileCostB : t->tileCost; DevBuf& tileOrder = bounceLaunch ? t->tileOrderB : t->tileOrder; DevBuf& tileState = bounceLaunch ? t->tileStateB : t->tileState;
     u32& schedTiles = bounceLaunch ? t->schedTilesB : t->schedTiles;
     static const bool tileOrderOn = !(getenv("BM_TILE_ORDER") && atoi(getenv("BM_TILE_ORDER")) == 0);
-    sched = { nullptr, nullptr, nullptr, 0 };
-    if (tileOrderOn && width && !d_counters)
+    sched = { nullptr, nullptr, nullptr, 0, nullptr, nullptr };
+    if (tileOrderOn && width && !d_counters && tile_sched_usable())
     {
         uint32_t height = (uint32_t)(numRays / width);
         uint64_t tiles = (uint64_t)((width + 7) / 8) * ((height + 3) / 4);
@@ -622,7 +627,12 @@ static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uin
                 BM_CUDA(cudaMemsetAsync(tileState.p, 0, TS_WORDS * 4, t->stream));      // no order yet
                 schedTiles = (u32)tiles;
             }
-            sched = { tileCost.as<u32>(), tileOrder.as<u32>(), tileState.as<u32>(), (u32)tiles };
+            sched = { tileCost.as<u32>(), tileOrder.as<u32>(), tileState.as<u32>(), (u32)tiles, nullptr, nullptr };
+            if (!bounceLaunch && hitListSamples && hitListOn)
+            {
+                BM_TRY(t->tileHitFlag.reserve(tiles * 4));
+                sched.hitFlag = t->tileHitFlag.as<u32>();
+            }
         }
     }
     return BM_OK;
@@ -639,8 +649,10 @@ extern "C" int bmTraceCameraJittered(bmTree* t, const float* d_initialRays3, uin
     if (width && numRays % width) return BM_ERROR_INVALID_PARAMETER;
     BM_TRY(t->scalars.reserve(64));
     TileSched sched;
-    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched));
-    return trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream);
+    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched, false, d_hits ? 1u : 0u));
+    BM_TRY(trace_camera(t->view(), cam, numRays, width, mode, d_hits, d_pixels, d_meshData, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream));
+    if (sched.hitFlag) { t->lastCamera.hits = d_hits; t->lastCamera.n = numRays; t->lastCamera.width = width; t->lastCamera.samples = 1; t->lastCamera.valid = true; }
+    return BM_OK;
 }
 
 // `sampleCount` jittered samples of every pixel in ONE launch (samples firstSample .. firstSample + sampleCount - 1; the slots enumerate the samples
@@ -654,8 +666,10 @@ extern "C" int bmTraceCameraSamples(bmTree* t, const float* d_initialRays3, uint
     CameraIn cam = make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, firstSample, seed);
     BM_TRY(t->scalars.reserve(64));
     TileSched sched;
-    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched));
-    return trace_camera(t->view(), cam, numRays, width, mode, d_hits, nullptr, nullptr, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream, sampleCount);
+    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched, false, sampleCount));
+    BM_TRY(trace_camera(t->view(), cam, numRays, width, mode, d_hits, nullptr, nullptr, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream, sampleCount));
+    if (sched.hitFlag) { t->lastCamera.hits = d_hits; t->lastCamera.n = numRays; t->lastCamera.width = width; t->lastCamera.samples = sampleCount; t->lastCamera.valid = true; }
+    return BM_OK;
 }
 
 // Bounce launch: every pixel whose primary ray hit (d_hits1[k * numRays + i] of sample k, as bmTraceCameraSamples / bmTraceCamera[Jittered] wrote
@@ -677,8 +691,11 @@ extern "C" int bmTraceBounceCamera(bmTree* t, const float* d_initialRays3, uint6
     CameraIn cam = make_camera(d_initialRays3, eye3, orient9, jitterX, jitterY, cameraSample0, cameraSeed);
     BM_TRY(t->scalars.reserve(64));
     TileSched sched;
-    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched, true));
     BounceIn b = { d_hits1, t->soup.as<float4>(), bounceSample0, bounce, seed, d_accum, d_covered, ambient, weight, reinterpret_cast<unsigned long long*>(d_rayCount) };
+    BM_TRY(tile_sched_for(t, numRays, width, d_counters, sched, true));
+    // the camera launch that wrote these hit records flagged its tiles with hits: the work list leaves the others out
+    if (sched.cost && t->lastCamera.valid && t->lastCamera.hits == d_hits1 && t->lastCamera.n == numRays && t->lastCamera.width == width && t->lastCamera.samples == sampleCount)
+        sched.filter = t->tileHitFlag.as<u32>();
     return trace_camera(t->view(), cam, numRays, width, BM_TRACE_CLOSEST, d_hits2, nullptr, nullptr, d_counters, t->scalars.as<u32>() + 8, sched.cost ? &sched : nullptr, t->stream, sampleCount, &b);
 }
 
