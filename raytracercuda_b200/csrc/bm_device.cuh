@@ -46,7 +46,10 @@ void set_sticky(int code, const char* where);
 // in-cell sub-key width (Grid::subBits): 9 bits keep the sort key at 40 bits = 5 radix passes; meshes much finer than the leaf cells
 // (hundreds of faces per leaf) get 15 bits, which tightens the 4-face cluster boxes inside such leaves (tree.cu picks per build)
 constexpr int SUB_BITS_COARSE = 9, SUB_BITS_FINE = 15;
-constexpr int CLUSTER = 4;
+#ifndef BM_CLUSTER
+#define BM_CLUSTER 4
+#endif
+constexpr int CLUSTER = BM_CLUSTER;          // faces per cluster box (a power of two <= 32)
 constexpr int NODE_F4 = 8, LEAF_F4 = 3, CLUSTER_F4 = 2;
 static const u32 LEAF_BIT = 0x80000000u;
 static const u32 EXCLUDED_BIT = 0x80000000u;

@@ -329,13 +329,13 @@ __device__ __forceinline__ void coop_leaf_staged(const TreeView& tv, unsigned la
         }
         unsigned bits = __ballot_sync(FULL, pass);
         u32 npass = __popc(bits);
-        for (u32 k0 = 0; k0 < npass; k0 += 8)
+        for (u32 k0 = 0; k0 < npass; k0 += 32 / CLUSTER)
         {
-            u32 k = k0 + (lane >> 2);
+            u32 k = k0 + lane / CLUSTER;
             if (k < npass)
             {
                 u32 grp = __fns(bits, 0, (int)k + 1);
-                u32 i = grp * CLUSTER + (lane & 3);
+                u32 i = grp * CLUSTER + lane % CLUSTER;
                 if (i < fHere)
                 {
                     const float4* p = sTri + 3 * i;
@@ -407,13 +407,13 @@ __device__ __forceinline__ void coop_leaf(const TreeView& tv, unsigned lane, int
         unsigned bits = __ballot_sync(FULL, pass);
         // faces of the passing groups, 8 groups (32 faces) per step
         u32 npass = __popc(bits);
-        for (u32 k0 = 0; k0 < npass; k0 += 8)
+        for (u32 k0 = 0; k0 < npass; k0 += 32 / CLUSTER)
         {
-            u32 k = k0 + (lane >> 2);
+            u32 k = k0 + lane / CLUSTER;
             if (k < npass)
             {
                 u32 grp = gbase + __fns(bits, 0, (int)k + 1);
-                u32 i = grp * CLUSTER + (lane & 3);
+                u32 i = grp * CLUSTER + lane % CLUSTER;
                 if (i < lcnt)
                 {
                     const float4* p = tv.ltris + 3 * (size_t)(lfirst + i);
