@@ -78,6 +78,53 @@ BM_HD float tri_intersect(V3 orig, V3 dir, V3 v0, V3 e1, V3 e2, float& u, float&
     return dot3(e2, qvec) * invDet;
 }
 
+BM_HD float fma_(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+
+// Conservative pre-test in front of tri_intersect: true = tri_intersect WOULD return FLT_MAX ("no hit"), decided without its division
+// and in fused arithmetic.  It may answer false for a triangle the exact test then rejects; it never answers true for one the exact test
+// accepts, so results do not depend on it.
+// tri_intersect accepts when u = fl(U * fl(1 / D)) lies in [0, 1], v = fl(V * fl(1 / D)) >= 0 and fl(u + v) <= 1 with
+//   D = e1 . (dir x e2),  U = tvec . (dir x e2),  V = dir . (tvec x e1),
+// all evaluated in unfused float arithmetic; each product / quotient contributes a relative error of at most 2^-24, hence acceptance
+// implies  0 <= U / D <= 1 + 3 eps,  0 <= V / D  and  (U + V) / D <= 1 + 5 eps  for the UNFUSED values.  The fused values computed here
+// differ from those by at most 9 eps * B with B the sum of the absolute values of all products involved (B = sum_i |x_i| (|a_j b_k| +
+// |a_k b_j|) for a triple product): 2 eps from each cross-product component in either arithmetic, 3 eps from the dot product.  With
+// s = sign(D') the tests below therefore use a margin of K (B_U + B_D) etc. with K = 4e-6 = 67 eps, seven times the bound; they also hold
+// when D' and D disagree in sign (then both are below the bound in magnitude, and so must U and V be for the exact test to accept).
+// A NaN anywhere answers false (every comparison fails), leaving the decision to the exact test.
+BM_HD bool tri_reject(V3 orig, V3 dir, V3 v0, V3 e1, V3 e2)
+{
+    const float K = 4e-6f;
+    // dir x e2 and its termwise absolute bound
+    const float px = fma_(dir.y, e2.z, -(e2.y * dir.z)), py = fma_(dir.z, e2.x, -(e2.z * dir.x)), pz = fma_(dir.x, e2.y, -(e2.x * dir.y));
+    const float ax = fma_(fabsf(dir.y), fabsf(e2.z), fabsf(e2.y * dir.z)), ay = fma_(fabsf(dir.z), fabsf(e2.x), fabsf(e2.z * dir.x)),
+                az = fma_(fabsf(dir.x), fabsf(e2.y), fabsf(e2.x * dir.y));
+    const float D = fma_(e1.z, pz, fma_(e1.y, py, e1.x * px));
+    const float bD = fma_(fabsf(e1.z), az, fma_(fabsf(e1.y), ay, fabsf(e1.x) * ax));
+    const V3 t = orig - v0;
+    const float U = fma_(t.z, pz, fma_(t.y, py, t.x * px));
+    const float bU = fma_(fabsf(t.z), az, fma_(fabsf(t.y), ay, fabsf(t.x) * ax));
+    const bool neg = D < 0.f;
+    const float aD = fabsf(D), a = neg ? -U : U, mU = K * (bU + bD);
+    if (a < -mU || a > aD + mU) return true;
+    // tvec x e1
+    const float qx = fma_(t.y, e1.z, -(e1.y * t.z)), qy = fma_(t.z, e1.x, -(e1.z * t.x)), qz = fma_(t.x, e1.y, -(e1.x * t.y));
+    const float cx = fma_(fabsf(t.y), fabsf(e1.z), fabsf(e1.y * t.z)), cy = fma_(fabsf(t.z), fabsf(e1.x), fabsf(e1.z * t.x)),
+                cz = fma_(fabsf(t.x), fabsf(e1.y), fabsf(e1.x * t.y));
+    const float V = fma_(dir.z, qz, fma_(dir.y, qy, dir.x * qx));
+    const float bV = fma_(fabsf(dir.z), cz, fma_(fabsf(dir.y), cy, fabsf(dir.x) * cx));
+    const float b = neg ? -V : V;
+    if (b < -K * (bV + bD)) return true;
+    return a + b > aD + K * (bU + bV + bD);
+}
+
 // Hash.cu:17-33 bmHash (Fletcher-16 over the 4 little-endian bytes), :41-47 bmHash3(uint3), :56-59 bmMap
 BM_HD u32 hash32(u32 h)
 {

@@ -18,6 +18,13 @@ namespace bm
 {
 namespace
 {
+// Conservative fused pre-test in front of the exact triangle test (tri_reject, bm_math.cuh): OFF.  It catches 99.9 % of ordinary misses for
+// a third of the exact test's instructions (tests/test_hostcheck.py), but the face loops run ~10 lanes at a time and one of them passes
+// the pre-test in ~85 % of the trips, so the warp executes both tests: c2 step 0.850 -> 0.884 ms, c4 frame 52.8 -> 56.1 ms with it
+// (profiles/r2_SUMMARY.md).  Kept as a compile-time variant (-DBM_TRI_PRETEST=1) with its CPU property test.
+#ifndef BM_TRI_PRETEST
+#define BM_TRI_PRETEST 0
+#endif
 constexpr int TR_THREADS = 128;
 constexpr int TR_STACK = 52;     // binary walk: depth <= D <= 32; wide walk: a visit pops one entry and pushes up to four, <= 16 wide levels
 constexpr int COOP_MAX_LANES = 8;   // at most this many pending leaves in a warp -> process the sizeable ones warp-cooperatively
@@ -163,6 +170,9 @@ __device__ __forceinline__ void test_face(float4 a, float4 b, float4 c, V3 o, V3
     u32 meshBits = __float_as_uint(b.w);
     if (MODE == BM_TRACE_REFERENCE && (meshBits & EXCLUDED_BIT)) return;       // beyond the 256-face cap of its leaf
     float u, v;
+#if BM_TRI_PRETEST
+    if (tri_reject(o, d, f4xyz(a), f4xyz(b), f4xyz(c))) return;       // provably no hit (bm_math.cuh): the exact test and its division are skipped
+#endif
     float dd = tri_intersect(o, d, f4xyz(a), f4xyz(b), f4xyz(c), u, v);
     if (MODE != BM_TRACE_REFERENCE && !(dd >= 0.f)) return;
     u32 tri = __float_as_uint(a.w);

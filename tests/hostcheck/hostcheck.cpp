@@ -86,6 +86,25 @@ float hc_tri_intersect(const float* o, const float* d, const float* v0, const fl
     return tri_intersect(mk3(o[0],o[1],o[2]), mk3(d[0],d[1],d[2]), a, b - a, c - a, *u, *v);
 }
 
+// tri_reject (the conservative pre-test in front of tri_intersect) against tri_intersect itself on n (ray, triangle) pairs:
+// counts[0] = accepted by the exact test, [1] = rejected by it, [2] = rejected by the pre-test, [3] = VIOLATIONS: rejected by the pre-test
+// although the exact test accepts (must stay 0)
+void hc_tri_pretest(const float* o, const float* d, const float* tri9, uint64_t n, uint64_t* counts)
+{
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (uint64_t i = 0; i < n; i++)
+    {
+        V3 a = mk3(tri9[9*i], tri9[9*i+1], tri9[9*i+2]), b = mk3(tri9[9*i+3], tri9[9*i+4], tri9[9*i+5]), c = mk3(tri9[9*i+6], tri9[9*i+7], tri9[9*i+8]);
+        V3 oo = mk3(o[3*i], o[3*i+1], o[3*i+2]), dd = mk3(d[3*i], d[3*i+1], d[3*i+2]);
+        float u, v;
+        const float t = tri_intersect(oo, dd, a, b - a, c - a, u, v);
+        const bool accept = !(t == FLT_MAX), rej = tri_reject(oo, dd, a, b - a, c - a);
+        counts[accept ? 0 : 1]++;
+        if (rej) counts[2]++;
+        if (rej && accept) counts[3]++;
+    }
+}
+
 // ---- the 64-byte wide node (bm_wide.cuh) on the CPU: the product's encoder and traversal step (the very functions the kernels call) over
 // a radix tree built here the plain way, so that the no-GPU tier can compare complete traversals with the oracle ----------------------
 namespace

@@ -29,6 +29,7 @@ def hc():
     H.hc_decode.argtypes = [C.c_int, C.c_uint32, u32p]
     H.hc_box_ray.argtypes = [f32p] * 4; H.hc_box_ray.restype = C.c_float
     H.hc_tri_intersect.argtypes = [f32p] * 5 + [C.POINTER(C.c_float)] * 2; H.hc_tri_intersect.restype = C.c_float
+    H.hc_tri_pretest.argtypes = [f32p, f32p, f32p, C.c_uint64, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")]; H.hc_tri_pretest.restype = None
     H.hc_wide_trace.argtypes = [f32p, u32p, C.c_uint32, f32p, f32p, C.c_float, C.c_uint32, C.c_uint32, f32p, C.c_uint64, C.c_int, u32p, f32p,
                                 np.ctypeslib.ndpointer(np.uint64, flags="C")]
     H.hc_hash.argtypes = [C.c_uint32]; H.hc_hash.restype = C.c_uint32
@@ -236,3 +237,51 @@ def test_wide_nodes_trace_like_the_oracle_on_soups(hc, oracle_lib):
         _wide_vs_oracle(hc, oracle_lib, P, I, None, synth.incoherent_rays(3000, extent=2.5), "table grid")
     finally:
         del os.environ["HC_NO_UNIFORM"]
+
+
+def test_triangle_pretest_never_rejects_what_the_exact_test_accepts(hc):
+    """tri_reject (bm_math.cuh): the fused, division-free pre-test the trace kernels run in front of the reference-order triangle test.
+    It must never answer "no hit" where tri_intersect accepts; checked on rays aimed AT edges, vertices and interiors of random triangles
+    (targets computed in double, so the exact test's u, v land within rounding of 0, 1 and u + v = 1), on near-parallel rays, on huge,
+    tiny and needle triangles, and on far origins -- and it has to be worth running: it must catch most of the misses."""
+    rng = np.random.default_rng(2024)
+    total = np.zeros(4, np.uint64)
+    for scale, far in ((1.0, 1.0), (1e-3, 1.0), (40.0, 1.0), (1.0, 50.0), (0.02, 30.0)):
+        n = 400_000
+        tri = (rng.standard_normal((n, 3, 3)) * scale).astype(np.float64)
+        kind = rng.integers(0, 6, n)
+        needle = kind == 5
+        tri[needle, 2] = tri[needle, 1] + (tri[needle, 2] - tri[needle, 1]) * 1e-4           # nearly degenerate
+        # target point on the triangle's plane: barycentric (u, v) chosen on / near the acceptance boundary
+        u = rng.random(n); v = rng.random(n) * (1 - u)
+        edge = rng.integers(0, 4, n)
+        on = kind <= 2
+        u = np.where(on & (edge == 0), 0.0, u); v = np.where(on & (edge == 1), 0.0, v)
+        v = np.where(on & (edge == 2), 1.0 - u, v)
+        u = np.where(on & (edge == 3), np.round(u), u); v = np.where(on & (edge == 3), np.where(u == 1, 0.0, np.round(v)), v)     # vertices
+        miss = kind == 3
+        u = np.where(miss, rng.standard_normal(n) * 2, u); v = np.where(miss, rng.standard_normal(n) * 2, v)
+        target = tri[:, 0] + u[:, None] * (tri[:, 1] - tri[:, 0]) + v[:, None] * (tri[:, 2] - tri[:, 0])
+        org = target + rng.standard_normal((n, 3)) * scale * far
+        par = kind == 4                                                                                  # rays (nearly) inside the plane
+        inplane = (tri[:, 1] - tri[:, 0]) * rng.standard_normal((n, 1)) + (tri[:, 2] - tri[:, 0]) * rng.standard_normal((n, 1))
+        nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+        org = np.where(par[:, None], target + inplane + nrm * (rng.standard_normal((n, 1)) * 1e-7), org)
+        d = target - org
+        d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-300)
+        counts = np.zeros(4, np.uint64)
+        hc.hc_tri_pretest(np.ascontiguousarray(org, np.float32).reshape(-1), np.ascontiguousarray(d, np.float32).reshape(-1),
+                          np.ascontiguousarray(tri, np.float32).reshape(-1), n, counts)
+        assert counts[3] == 0, "pre-test rejected %d accepted hits at scale %g / distance %g" % (counts[3], scale, far)
+        assert counts[0] > 0.2 * n and counts[1] > 0.1 * n                 # both outcomes are exercised
+        total += counts
+    # ordinary misses (what a leaf's face loop mostly sees: the ray passes somewhere near the triangle): nearly all must be caught
+    n = 400_000
+    tri = rng.standard_normal((n, 3, 3)).astype(np.float32)
+    org = (rng.standard_normal((n, 3)) * 3).astype(np.float32)
+    d = (tri.mean(axis=1) + rng.standard_normal((n, 3)) * 1.5 - org).astype(np.float64)
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    counts = np.zeros(4, np.uint64)
+    hc.hc_tri_pretest(np.ascontiguousarray(org).reshape(-1), np.ascontiguousarray(d).reshape(-1), np.ascontiguousarray(tri).reshape(-1), n, counts)
+    assert counts[3] == 0 and counts[0] > 1000
+    assert counts[2] >= 0.999 * counts[1], "the pre-test catches only %.2f %% of ordinary misses" % (100.0 * counts[2] / counts[1])
