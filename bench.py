@@ -765,11 +765,16 @@ def hbm_leg(torch, dev, L, args):
         prof = profile_entry("hbm_leg_" + key)
         ms0 = leg["reference"]["ms_per_launch"]
         if prof:
-            scale = n / prof["rays_per_launch"]               # the capture traced rays_per_launch rays of the same batch: bytes scale with the ray count
+            scale = n / prof["rays_per_launch"]               # the capture traced rays_per_launch rays of the same batch: bytes and instructions scale with the ray count
             dram = prof["dram_bytes_per_launch"] * scale
-            leg["roofline"] = {"bound": prof["bound"], "traffic": dram, "traffic_source": prof["source"], "dram_gbs": dram / (ms0 * 1e-3) / 1e9,
-                               "frac_of_hbm_peak": dram / (ms0 * 1e-3) / 1e9 / peak, "peak": peak, "ipc": prof.get("ipc"), "lanes_per_instruction": prof.get("lanes_per_instruction"),
-                               "note": "reference-mode launch; DRAM bytes of the committed capture scaled to this launch's ray count, duration measured live; " + peak_src}
+            issue_peak = 148 * 4 * 1.965
+            issue_frac = prof["warp_instructions_per_launch"] * scale / (ms0 * 1e-3) / 1e9 / issue_peak
+            hbm_frac = dram / (ms0 * 1e-3) / 1e9 / peak
+            leg["roofline"] = {"bound": "hbm" if hbm_frac > issue_frac else "issue", "frac": max(hbm_frac, issue_frac),
+                               "traffic": dram, "traffic_source": prof["source"], "dram_gbs": dram / (ms0 * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": hbm_frac, "peak": peak, "frac_of_issue_peak": issue_frac, "issue_peak_gwarp_inst_per_s": issue_peak,
+                               "ipc": prof.get("ipc"), "lanes_per_instruction": prof.get("lanes_per_instruction"), "long_scoreboard_stall": prof.get("long_scoreboard_stall"),
+                               "note": "reference-mode launch; DRAM bytes and warp instructions of the trace kernel in the committed capture scaled to this launch's ray count, duration of the whole call measured live; bound = the larger share; " + peak_src}
         else:
             a = leg["algorithmic_bytes_per_ray"] * n / (ms0 * 1e-3) / 1e9
             leg["roofline"] = {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None, "note": "algorithmic bytes (64 B x node visits + 48 B x triangle tests + 40 B ray / hit), no capture committed; " + peak_src}
@@ -946,9 +951,16 @@ def run_c5(args):
             "longest_segment_steps": LONG}
     if prof:
         dram = prof["dram_bytes_per_launch"] * chunk / prof["rays_per_launch"]
-        roof.update({"bound": prof.get("bound", "issue"), "traffic": dram, "traffic_source": prof["source"], "achieved": dram / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": dram / (kms * 1e-3) / 1e9 / peak, "ipc": prof.get("ipc"), "lanes_per_instruction": prof.get("lanes_per_instruction"),
-                     "note": "achieved = DRAM bytes of the committed ncu capture (scaled by ray count) / live duration: the bricked traversal serves most node bytes from L2 and is bound by instruction issue, so the HBM fraction is low by design; the direct traversal is the HBM-bound form (see `direct`); " + peak_src})
+        issue_peak = 148 * 4 * ((clocks.get("sm_mhz") or 1965.0) / 1e3)
+        inst_rate = prof["warp_instructions_per_launch"] * chunk / prof["rays_per_launch"] / (kms * 1e-3) / 1e9
+        hbm_frac, issue_frac = dram / (kms * 1e-3) / 1e9 / peak, inst_rate / issue_peak
+        hb = hbm_frac > issue_frac
+        roof.update({"bound": "hbm" if hb else "issue", "achieved": dram / (kms * 1e-3) / 1e9 if hb else inst_rate, "peak": peak if hb else issue_peak, "unit": "GB/s" if hb else "Gwarp-inst/s",
+                     "frac": max(hbm_frac, issue_frac), "traffic": dram, "traffic_source": prof["source"],
+                     "dram": {"achieved_gbs": dram / (kms * 1e-3) / 1e9, "frac_of_hbm_peak": hbm_frac}, "issue": {"achieved_gwarp_inst_per_s": inst_rate, "peak": issue_peak, "frac": issue_frac},
+                     "ipc": prof.get("ipc"), "lanes_per_instruction": prof.get("lanes_per_instruction"),
+                     "note": "DRAM bytes and warp instructions of trace_kernel<SEG> in the committed ncu capture (scaled by ray count) / live duration of the whole call; bound = the larger share: the bricked traversal "
+                             "is bound by instruction issue (~500 thread instructions per 4-wide node visit), its DRAM traffic is a third of the direct traversal's; " + peak_src})
     else:
         roof.update({"bound": "hbm", "achieved": by / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": by / (kms * 1e-3) / 1e9 / peak, "traffic": None,
                      "note": "algorithmic bytes: 24 B ray + 16 B hit + 64 B x node visits + 48 B x triangle tests; " + peak_src})
@@ -1013,24 +1025,32 @@ def reference_build_baseline(wl, gpu_pixels_fn=None, W=960, H=540):
     """The UNMODIFIED reference (oracle/_ref/libbeam_ref.so: its own sources compiled in their CUDA-0 host mode, oracle/build_ref.sh)
     through its public interface on one core -- it is not thread-safe and can only trace a camera's primary rays into pixels, so the
     sample is the workload's scene at W x H primary rays.  When the GPU path's pixels for the same frame are supplied they are compared."""
+    # in a process of its own: the reference's fixed-size pools overflow on scenes beyond what it was written for (a segmentation fault,
+    # not an error code), and a crash is a result to report, not a reason to lose the bench line
     try:
-        from oracle.bindings import RefLib, RefScene
         if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libbeam_ref.so")):
             return None
-        s = RefScene(RefLib())
-        s.add_mesh(wl.positions, wl.indices, wl.normals)
-        tb = s.build()
-        err, px, sec = s.trace(W, H, wl.eye, np.eye(3, dtype=np.float32), wl.frustum)
-        s.close()
-        if err:
-            return {"kind": "reference", "error": int(err)}
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            npy = os.path.join(td, "pixels.npy")
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_ref_build.py"), wl.key, str(W), str(H), npy], capture_output=True, text=True, timeout=900)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode != 0 or not line:
+                return {"kind": "reference", "crashed": "exit %d%s" % (r.returncode, " (signal %d: its fixed-size pools overflow on this scene)" % -r.returncode if r.returncode < 0 else "")}
+            d = json.loads(line[-1])
+            if d["error"]:
+                return {"kind": "reference", "error": int(d["error"])}
+            px = np.load(npy)
+        tb, sec = d["build_seconds"], d["trace_seconds"]
         out = {"kind": "reference", "value": W * H / sec / 1e6, "unit": "Mrays/s", "cores": 1,
-               "sample": "the workload's scene, %dx%d primary rays through IScene / ICamera::traceScene of the unmodified reference (CUDA 0 host mode)" % (W, H),
+               "sample": "the workload's scene, %dx%d primary rays through IScene / ICamera::traceScene of the unmodified reference (CUDA 0 host mode), in a process of its own" % (W, H),
                "build": {"value": wl.num_tris / tb / 1e6, "unit": "Mtris/s", "cores": 1, "seconds": tb}}
         if gpu_pixels_fn is not None:
             gp = gpu_pixels_fn(W, H)
             out["gpu_pixels_equal_reference"] = bool(np.array_equal(np.asarray(gp, np.uint32).reshape(-1), np.asarray(px, np.uint32).reshape(-1)))
         return out
+    except subprocess.TimeoutExpired:
+        return {"kind": "reference", "unavailable": "timed out (900 s)"}
     except Exception as ex:                                   # the baseline is reported, never required
         return {"kind": "reference", "unavailable": repr(ex)[:200]}
 

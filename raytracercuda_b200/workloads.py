@@ -26,6 +26,7 @@ class Workload:
     eye: tuple = synth.EYE
     frustum: tuple = synth.FRUSTUM
     samples: int = 1           # jittered samples per pixel (1 = the exact pixel-centre table, as the reference traces it)
+    key: str = ""              # the name get() was called with
 
     @property
     def num_tris(self):
@@ -38,6 +39,12 @@ def _bundled(name):
 
 
 def get(name: str) -> Workload:
+    wl = _get(name)
+    wl.key = name
+    return wl
+
+
+def _get(name: str) -> Workload:
     if name == "c1":
         P, I, N = _bundled("bunny")
         return Workload("c1: Content/bunny.obj (69,630 tris) BVH build + 1 spp primary closest-hit at 1280x720", "configs[0]", P, I, N, 1280, 720, 0)

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 key, rep, pat = sys.argv[1], sys.argv[2], sys.argv[3]
 idx = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 0
 kv = dict(a.split("=", 1) for a in sys.argv[4:] if "=" in a)
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines())); hdr = rows[0]
 cands = [r for r in rows[2:] if pat in r[hdr.index("Kernel Name")]]
 r = cands[idx]
@@ -16,7 +16,7 @@ def to_bytes(n):
     v = g(n); u = unit(n)
     return None if v is None else v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
 dur = g("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit("gpu__time_duration.sum"), 1e-6)   # ms
-base = os.path.basename(rep).replace(".ncu-rep", "")
+base = os.path.basename(rep).replace(".ncu-rep", "").replace("_rawpage.csv", "")
 summary = os.path.join(ROOT, "profiles", base + "_raw.txt")
 with open(summary, "a") as f:
     f.write("---- %s  [%s, launch %d of the capture]\n" % (r[hdr.index("Kernel Name")], key, idx))
@@ -31,7 +31,7 @@ e = {"kernel": r[hdr.index("Kernel Name")][:100], "ms_in_capture": dur,
      "lanes_per_instruction": g("smsp__thread_inst_executed_per_inst_executed.ratio"),
      "long_scoreboard_stall": g("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
      "l1_hit_pct": g("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": g("lts__t_sector_hit_rate.pct"),
-     "source": "profiles/%s_raw.txt (ncu --set full --clock-control none; %s)" % (base, os.path.basename(rep))}
+     "source": "profiles/%s_raw.txt (ncu --set full --clock-control none; %s)" % (base, os.path.basename(rep).replace("_rawpage.csv", ".ncu-rep"))}
 if "rays" in kv: e["rays_per_launch"] = int(float(kv["rays"]))
 if "bound" in kv: e["bound"] = kv["bound"]
 if "note" in kv: e["note"] = kv["note"]
