@@ -518,6 +518,13 @@ def run_b200(args):
         return total
 
     e2e_run(3, -3)
+    fl = []
+    for k in range(5):                                       # what the L2 flush inside every e2e frame costs on its own
+        e0, e1 = ev(), ev(); sync_all(); e0.record(hs)
+        with torch.cuda.stream(hs):
+            flush.zero_()
+        e1.record(hs); sync_all(); fl.append(e0.elapsed_time(e1))
+    e2e_flush_ms = statistics.mean(fl[1:])
     lat = []
     for k in range(3):                                       # latency of one frame on its own
         e0, e1 = ev(), ev(); sync_all(); e0.record(hs); e2e_run(1, k); e1.record(hs); sync_all(); lat.append(e0.elapsed_time(e1))
@@ -656,10 +663,11 @@ def run_b200(args):
                                   "motion": ("orbit about the y axis, %.3g degrees per frame, looking at the origin (every frame differs from the one the tile schedule learnt from)" % args.orbit_deg) if moving else "static"}},
             "primary_launch_ms": prim_moving_ms, "bounce_launch_ms": bounce_moving_ms,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(t2.item()) / args.steps,
-                    "single_frame_latency_ms": e2e_latency_ms, "pixels_equal_device_path": e2e_equal,
+                    "single_frame_latency_ms": e2e_latency_ms, "l2_flush_ms_inside_every_frame": e2e_flush_ms, "pixels_equal_device_path": e2e_equal,
                     "api": "host classes through include/beam_host_c.h: " + ("beamCameraTraceSceneProgressive" if (wl.bounces or SPP > 1) else "beamCameraTraceScene") + " + beamRenderTargetReadPixels; scene uploaded from host arrays by beamMeshSetVertexData / beamMeshSetIndices, built by beamSceneUpdateGPUScene",
                     "pipeline": "per frame: eye + orientation (48 B, kernel arguments; the camera's direction table was uploaded once by setInitialRays, as the reference does) -> frame on the host classes' stream -> "
-                                "read-back of the framebuffer and the ray count into pinned memory on the copy stream; two render targets, so the read-back of frame i-1 overlaps frame i; K frames = one timed bracket"},
+                                "read-back of the framebuffer and the ray count into pinned memory on the copy stream; two render targets, so the read-back of frame i-1 overlaps frame i; K frames = one timed bracket, "
+                                "which therefore also contains one 256 MiB L2 flush per frame (l2_flush_ms_inside_every_frame; the device-timed step flushes outside its bracket)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "build": build, "closest_mode": closest_mode}
     if static is not None:
         line["static_camera"] = static
