@@ -259,7 +259,7 @@ def run_b200(args):
     if strong and world > 1:
         cam_full = host.ICamera.create()
         assert cam_full.setInitialRays(W, wl.height, *wl.frustum) == 0
-        rows = np.array([y for y in range(wl.height) if (y // 4) % world == rank], np.int64)
+        rows = workloads.band_rows(wl.height, rank, world)
         rays_host = np.ascontiguousarray(cam_full.initialRays().reshape(wl.height, W, 3)[rows].reshape(-1, 3))
         H = int(rows.size); n = W * H; frustum_h = wl.height
         del cam_full

@@ -150,6 +150,7 @@ constexpr int RS_MAX_PASSES = 8;
 #ifndef BM_OS_ITEMS64
 #define BM_OS_ITEMS64 12
 #endif
+// (tiles of 1024 keys for small inputs were tried: a 503 K-pair sort takes 103 us with them, 94 us with the 3072-key tiles)
 template <class K> struct OsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : BM_OS_ITEMS64; static constexpr int TILE = RS_THREADS * ITEMS;
                                   static constexpr size_t SMEM = (size_t)TILE * (sizeof(K) + 4); };
 constexpr u32 OS_AGG = 1u << 30, OS_INC = 2u << 30, OS_VAL = (1u << 30) - 1u;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_all_hist_kernel(const K* __r
 template <class K>
 __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const K* __restrict__ keysIn, const u32* __restrict__ valsIn,
                                                                     K* __restrict__ keysOut, u32* __restrict__ valsOut, size_t n, int shift,
-                                                                    const u32* __restrict__ passHist, u32* ticket, volatile u32* status)
+                                                                    const u32* __restrict__ passHist, u32* ticket, volatile u32* status, u32* ticketNext, u32* statusNext)
 {
     constexpr int RS_ITEMS = OsCfg<K>::ITEMS, RS_TILE = OsCfg<K>::TILE;
     __shared__ u32 warpHist[RS_WARPS][RS_BINS + 1];     // +1: bin 256 swallows the out-of-range tail
@@ -193,6 +194,10 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const K* __r
     for (int i = threadIdx.x; i < RS_WARPS * (RS_BINS + 1); i += RS_THREADS) (&warpHist[0][0])[i] = 0;
     __syncthreads();
     const u32 tile = sTile;
+    // the NEXT pass's ticket and status words (the tables alternate; the other one was last used by the pass before this one, which has
+    // ended): zeroed here, so that a pass is one kernel and nothing else on the stream
+    statusNext[(size_t)tile * RS_BINS + threadIdx.x] = 0u;
+    if (tile == 0 && threadIdx.x == 0) *ticketNext = 0u;
 
     const size_t tileBase = (size_t)tile * RS_TILE;
     const size_t warpBase = tileBase + (size_t)w * (RS_ITEMS * 32);
@@ -298,11 +303,17 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const K* __r
 }
 } // namespace
 
+// smallest tile of any path and key width: sizes the per-tile tables
+static constexpr size_t layout_tile()
+{
+    return (size_t)RS_THREADS * (BM_OS_ITEMS64 < 8 ? BM_OS_ITEMS64 : 8);
+}
+
 size_t sort_temp_bytes(size_t n)
 {
-    const size_t RS_TILE = RsCfg<u64>::TILE;      // the smaller tile -> the larger table
+    const size_t RS_TILE = layout_tile();         // the smallest tile any path uses -> the largest table
     size_t tiles = (n + RS_TILE - 1) / RS_TILE;
-    size_t counts = ((tiles * RS_BINS * 4 + 255) / 256) * 256;      // per-tile digit table (three-kernel path) or status words (one-sweep)
+    size_t counts = ((2 * tiles * RS_BINS * 4 + 255) / 256) * 256;  // per-tile digit table (three-kernel path) or two alternating tables of status words (one-sweep)
     return counts + scan_temp_bytes(tiles * RS_BINS) + RS_MAX_PASSES * RS_BINS * 4 + 256;
 }
 
@@ -315,16 +326,17 @@ static int radix_sort_impl(K* d_keysA, u32* d_valsA, K* d_keysB, u32* d_valsB, s
     if (n == 0) return BM_OK;
     const size_t RS_TILE = RsCfg<K>::TILE;
     size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    const size_t layoutTiles = (n + layout_tile() - 1) / layout_tile();      // as sort_temp_bytes lays the buffer out
     u32* counts = (u32*)d_temp;
-    void* scanTemp = (char*)d_temp + ((tiles * RS_BINS * 4 + 255) / 256) * 256;
+    void* scanTemp = (char*)d_temp + ((2 * layoutTiles * RS_BINS * 4 + 255) / 256) * 256;
     K *ka = d_keysA, *kb = d_keysB; u32 *va = d_valsA, *vb = d_valsB;
     static const bool threeKernel = getenv("BM_SORT") && strcmp(getenv("BM_SORT"), "3k") == 0;
     if (!threeKernel && n < (size_t)OS_VAL && passes <= RS_MAX_PASSES)
     {
         // layout: [status tiles*256 u32][scan temp (unused here)][hist passes*256 u32][ticket]
-        u32* hist = (u32*)((char*)scanTemp + scan_temp_bytes(tiles * RS_BINS));
-        u32* ticket = hist + RS_MAX_PASSES * RS_BINS;
-        BM_CUDA(cudaMemsetAsync(hist, 0, RS_MAX_PASSES * RS_BINS * 4 + 4, s));
+        u32* hist = (u32*)((char*)scanTemp + scan_temp_bytes(layoutTiles * RS_BINS));
+        u32* ticket = hist + RS_MAX_PASSES * RS_BINS;                    // two tickets, two status tables: passes alternate between them
+        BM_CUDA(cudaMemsetAsync(hist, 0, RS_MAX_PASSES * RS_BINS * 4 + 8, s));
         const size_t osTiles = (n + OsCfg<K>::TILE - 1) / OsCfg<K>::TILE;
         static std::atomic<int> smemSet[MAX_DEVICES];
         if (!smemSet[current_device()].load(std::memory_order_relaxed))
@@ -336,11 +348,11 @@ static int radix_sort_impl(K* d_keysA, u32* d_valsA, K* d_keysB, u32* d_valsB, s
         unsigned cap = (unsigned)sm_count() * 8;
         radix_all_hist_kernel<K><<<hb < cap ? hb : cap, RS_THREADS, 0, s>>>(ka, n, passes, hist);
         BM_LAUNCHED();
+        BM_CUDA(cudaMemsetAsync(counts, 0, osTiles * RS_BINS * 4, s));          // the first pass's table; every pass zeroes the next one's
         for (int p = 0; p < passes; p++)
         {
-            BM_CUDA(cudaMemsetAsync(counts, 0, osTiles * RS_BINS * 4, s));
-            if (p) BM_CUDA(cudaMemsetAsync(ticket, 0, 4, s));
-            radix_onesweep_kernel<K><<<(unsigned)osTiles, RS_THREADS, OsCfg<K>::SMEM, s>>>(ka, va, kb, vb, n, 8 * p, hist + p * RS_BINS, ticket, counts);
+            u32* st = counts + (size_t)(p & 1) * osTiles * RS_BINS; u32* stNext = counts + (size_t)((p + 1) & 1) * osTiles * RS_BINS;
+            radix_onesweep_kernel<K><<<(unsigned)osTiles, RS_THREADS, OsCfg<K>::SMEM, s>>>(ka, va, kb, vb, n, 8 * p, hist + p * RS_BINS, ticket + (p & 1), st, ticket + ((p + 1) & 1), stNext);
             BM_LAUNCHED();
             K* t = ka; ka = kb; kb = t;
             u32* tv = va; va = vb; vb = tv;

@@ -75,6 +75,13 @@ def _get(name: str) -> Workload:
     raise ValueError(name)
 
 
+def band_rows(height, rank, world, band=4):
+    """Rows of a `height`-row image that rank `rank` of `world` renders in a strong-scaling frame: the bands of `band` consecutive rows
+    rank, rank + world, ...  (band = the height of the trace kernels' 8x4 pixel tiles, so a rank's tiles are tiles of neighbouring pixels
+    of the real image).  Every row belongs to exactly one rank; ranks may differ by one band."""
+    return np.array([y for y in range(height) if (y // band) % world == rank], np.int64)
+
+
 def interleaved_rows_frustum(frustum, height, rank, world):
     """Frustum (left,right,top,bottom,zoom) whose `height` rows are rows rank, rank+world, ... of the image that has
     height*world rows over the full frustum: ICamera::setInitialRays(W, height, *this) then yields exactly those rows

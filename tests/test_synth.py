@@ -36,3 +36,16 @@ def test_icosphere_counts():
         e = np.sort(np.concatenate([I[:, [0, 1]], I[:, [1, 2]], I[:, [2, 0]]]).astype(np.int64), axis=1)
         _, cnt = np.unique(e[:, 0] * (P.shape[0] + 1) + e[:, 1], return_counts=True)
         assert (cnt == 2).all()
+
+
+def test_band_rows_partition_the_image():
+    """strong scaling (bench.py --scaling strong): every image row is rendered by exactly one rank, in bands of 4 rows dealt round robin"""
+    from raytracercuda_b200 import workloads
+    for height, world in ((2160, 8), (1080, 8), (1080, 4), (720, 2), (37, 3), (4, 8)):
+        parts = [workloads.band_rows(height, r, world) for r in range(world)]
+        allrows = np.concatenate(parts)
+        assert np.array_equal(np.sort(allrows), np.arange(height))
+        sizes = [p.size for p in parts]
+        assert max(sizes) - min(sizes) <= 4
+        for r, p in enumerate(parts):
+            assert ((p // 4) % world == r).all() and (np.diff(p) > 0).all()
