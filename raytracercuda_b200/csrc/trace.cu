@@ -506,7 +506,7 @@ __global__ void tile_hist_kernel(u32 tiles, const u32* __restrict__ cost, u32* s
 // tile | (row + 1) << 28), so that four warps share them.  Quarters run at 8 of 32 lanes, so splitting more than those loses throughput
 // (measured: splitting the top 1/256 of the tiles -9 % launch time, the top 1/64 +0 %, the top 1/16 +27 %).  state[TS_ENTRIES] = number of entries; state[TS_OK] says the list is usable (every tile was costed).
 // samples: a tile's cost is the sum over the launch's samples, but each sample of it is a work item of its own
-__global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* state, u32* __restrict__ order, u32 splitPct, u32 residentWarps, const u32* __restrict__ filter, u32 samples)
+__global__ void tile_order_kernel(u32 tiles, u32* __restrict__ cost, u32* state, u32* __restrict__ order, u32 splitPct, u32 residentWarps, const u32* __restrict__ filter, u32 samples)
 {
     __shared__ u32 base[TS_BUCKETS], bins[TS_BUCKETS];
     __shared__ u32 total, entries, splitFrom;
@@ -533,11 +533,14 @@ __global__ void tile_order_kernel(u32 tiles, const u32* __restrict__ cost, u32* 
     }
     __syncthreads();
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    // this kernel is the last reader of the costs: it leaves them zeroed for the launch that accumulates the next ones
+    const u32 myCost = i < tiles ? cost[i] : 0u;
+    if (i < tiles) cost[i] = 0u;
     // without a filter the list is usable only if every tile was costed by the previous launch; a filtered list holds exactly the tiles
     // that passed the filter (a tile that has no cost yet lands in the cheapest class)
     if (i < tiles && (filter ? filter[i] != 0u : total == tiles))
     {
-        u32 b = tile_bucket(cost[i]);
+        u32 b = tile_bucket(myCost);
         // one atomic per (warp, bucket): neighbouring tiles mostly share a bucket
         unsigned live = __activemask(), peers = __match_any_sync(live, b), lane = threadIdx.x & 31u;
         unsigned leader = __ffs(peers) - 1u;
@@ -1005,13 +1008,13 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
     u64 blocks = (warps + TR_THREADS / 32 - 1) / (TR_THREADS / 32);
     u64 cap = (u64)sm_count() * blocksPerSM;
     if (blocks > cap) blocks = cap;
-    BM_CUDA(cudaMemsetAsync(d_workCounter, 0, 4, s));
     TileSched ts = { nullptr, nullptr, nullptr, 0 };
     const int refill = refill_min(CAMERA);
     if (CAMERA && sched && !COUNT && refill == 32 && sched->tiles == (u32)(sampleSlots / 32))
     {
         ts = *sched;
-        BM_CUDA(cudaMemsetAsync(ts.state, 0, TS_OK * 4, s));          // histogram + cursors; OK flag and entry count of the previous launch stay
+        BM_CUDA(cudaMemsetAsync(ts.state, 0, (TS_WORK + 1) * 4, s));          // histogram, cursors, cost sum and the work counter; OK flag and entry count of the previous launch stay
+        d_workCounter = ts.state + TS_WORK;
         if (ts.filter)
         {
             // a filtered work list is made just before the launch it serves (the filter is what the preceding camera launch found out):
@@ -1021,9 +1024,9 @@ int launch_trace(const TreeView& tv, const bmRay* d_rays, const CameraIn& cam, u
             tile_order_kernel<<<div_up(ts.tiles, 256), 256, 0, s>>>(ts.tiles, ts.cost, ts.state, ts.order, tile_split_pct(), (u32)blocks * (TR_THREADS / 32), ts.filter, samples);
             BM_LAUNCHED();
         }
-        BM_CUDA(cudaMemsetAsync(ts.cost, 0, (size_t)ts.tiles * 4, s));
         if (ts.hitFlag) BM_CUDA(cudaMemsetAsync(ts.hitFlag, 0, (size_t)ts.tiles * 4, s));
     }
+    else BM_CUDA(cudaMemsetAsync(d_workCounter, 0, 4, s));
     const BounceIn none = { nullptr, nullptr, 0u, 0u, 0u, nullptr, nullptr, 0.f, 0.f, nullptr };
     trace_kernel<MODE, CAMERA, COUNT, WIDE, SEG, BOUNCE><<<(unsigned)blocks, TR_THREADS, 0, s>>>(tv, d_rays, cam, n, width, height, (u32)slots, d_numRays, d_hits, d_pixels, d_meshData,
                                                                             d_counters, d_workCounter, leaf_break(CAMERA ? 0 : queue_depth()), leaf_wait(CAMERA ? 0 : queue_depth()), refill, CAMERA ? 0 : queue_depth(), ts, seg,

@@ -625,6 +625,7 @@ static int tile_sched_for(bmTree* t, uint64_t numRays, uint32_t width, const uin
             {
                 BM_TRY(tileCost.reserve(tiles * 4)); BM_TRY(tileOrder.reserve(tiles * 16)); BM_TRY(tileState.reserve(TS_WORDS * 4));
                 BM_CUDA(cudaMemsetAsync(tileState.p, 0, TS_WORDS * 4, t->stream));      // no order yet
+                BM_CUDA(cudaMemsetAsync(tileCost.p, 0, tiles * 4, t->stream));          // from here on the ordering kernel keeps the costs zeroed between launches
                 schedTiles = (u32)tiles;
             }
             sched = { tileCost.as<u32>(), tileOrder.as<u32>(), tileState.as<u32>(), (u32)tiles, nullptr, nullptr };
