@@ -290,7 +290,11 @@ int  bmTraceCameraSamples(bmTree* tree, const float* d_initialRays3, uint64_t nu
  *   d_hits2        nullable; sampleCount * numRays records, written ONLY where the primary ray hit
  *   d_accum, d_covered  nullable; the progressive estimator (bmProgressiveAccumulate) applied where a bounce ray ends:
  *                  d_accum[i] += ambient + (escaped ? weight : 0), d_covered[i] = 1
- *   d_rayCount     nullable, device uint64: += number of bounce rays traced */
+ *   d_rayCount     nullable, device uint64: += number of bounce rays traced
+ * A camera launch that writes hit records also flags the 8x4 tiles in which a ray hit.  When d_hits1 is the buffer the LAST camera launch
+ * on this handle wrote (same pointer, numRays, width and sampleCount) the bounce launch leaves the unflagged tiles out of its work list;
+ * the caller must not have changed the records in between (trace into another buffer instead).  Any other camera launch on the handle,
+ * a rebuild, or BM_BOUNCE_LIST=0 makes the bounce launch walk every tile.  Results are the same either way. */
 int  bmTraceBounceCamera(bmTree* tree, const float* d_initialRays3, uint64_t numRays, uint32_t width, const float* eye3, const float* orient9,
                          float jitterX, float jitterY, uint32_t cameraSample0, uint32_t sampleCount, uint32_t cameraSeed, const bmHit* d_hits1,
                          uint32_t bounceSample0, uint32_t bounce, uint32_t seed, bmHit* d_hits2, float ambient, float weight, float* d_accum,
