@@ -27,8 +27,14 @@ namespace
 #endif
 constexpr int TR_THREADS = 128;
 constexpr int TR_STACK = 52;     // binary walk: depth <= D <= 32; wide walk: a visit pops one entry and pushes up to four, <= 16 wide levels
-constexpr int COOP_MAX_LANES = 8;   // at most this many pending leaves in a warp -> process the sizeable ones warp-cooperatively
-constexpr int COOP_MIN_FACES = 8;   // ... where sizeable = more than this many faces
+#ifndef BM_COOP_MAX_LANES
+#define BM_COOP_MAX_LANES 8
+#endif
+#ifndef BM_COOP_MIN_FACES
+#define BM_COOP_MIN_FACES 8
+#endif
+constexpr int COOP_MAX_LANES = BM_COOP_MAX_LANES;   // at most this many pending leaves in a warp -> process the sizeable ones warp-cooperatively
+constexpr int COOP_MIN_FACES = BM_COOP_MIN_FACES;   // ... where sizeable = more than this many faces
 constexpr int TR_QUEUE_MAX = 8;      // leaves a lane of a ray batch may postpone (queueDepth <= this)
 constexpr u32 REF_EMPTY = 0x7FFFFFFFu;   // "nothing left to visit" (never a valid internal index: N < 2^31 - 1)
 
